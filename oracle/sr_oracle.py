@@ -1,0 +1,283 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference hot path.
+
+Nothing under studiosr_b200/ may import this module; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do,
+and only as the checker.
+
+Parity status: PINNED.  The reference holds no golden vectors for this path
+(tests/models/* assert shapes only), so the oracle is pinned by
+fixtures produced by *executing the unmodified reference* in the build
+container (oracle/make_golden.py -> tests/golden/*.npz); tests/test_oracle.py
+checks every function below against them.
+
+The restatement is functional (weights are a plain dict keyed like the
+reference ``state_dict``), works in fp32 or fp64, and derives the shifted-window
+mask and relative-position bias from token coordinates rather than from
+materialised index / mask tensors.  Each function cites the reference lines it
+follows (paths relative to /root/reference/studiosr/models/).
+"""
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+
+RGB_MEAN = (0.4488, 0.4371, 0.4040)  # common.py:223
+
+
+# --------------------------------------------------------------------------- padding
+def pad_for_eval(x: torch.Tensor, ws: int) -> torch.Tensor:
+    """swinir.py:249-255 -- ALWAYS pads by (L//ws+1)*ws-L in [1,ws] rows/cols with an
+    edge-inclusive mirror (row L+i == row L-1-i)."""
+    _, _, h, w = x.shape
+    H = (h // ws + 1) * ws
+    W = (w // ws + 1) * ws
+    ridx = torch.tensor([i if i < h else 2 * h - 1 - i for i in range(H)])
+    cidx = torch.tensor([j if j < w else 2 * w - 1 - j for j in range(W)])
+    return x[:, :, ridx][:, :, :, cidx]
+
+
+def pad_for_train(x: torch.Tensor, ws: int) -> torch.Tensor:
+    """common.py:277-282 -- reflect pad (edge-exclusive mirror) up to the next multiple."""
+    _, _, h, w = x.shape
+    H = (h + ws - 1) // ws * ws
+    W = (w + ws - 1) // ws * ws
+    ridx = torch.tensor([i if i < h else 2 * (h - 1) - i for i in range(H)])
+    cidx = torch.tensor([j if j < w else 2 * (w - 1) - j for j in range(W)])
+    return x[:, :, ridx][:, :, :, cidx]
+
+
+# --------------------------------------------------------------------------- attention
+def _region(p: torch.Tensor, L: int, ws: int, shift: int) -> torch.Tensor:
+    """common.py:253-262 -- slice id of a coordinate in the *shifted* frame."""
+    r = torch.zeros_like(p)
+    r = torch.where(p >= L - ws, torch.ones_like(p), r)
+    r = torch.where(p >= L - shift, torch.full_like(p, 2), r)
+    return r
+
+
+def shift_mask(H: int, W: int, ws: int, shift: int, dtype) -> torch.Tensor:
+    """common.py:250-274 -- [nW, N, N] additive mask, -100 where region ids differ.
+    With shift == 0 the reference's slices degenerate (slice(-0,None) overwrites
+    everything with one id) and the mask is all zero."""
+    nW = (H // ws) * (W // ws)
+    N = ws * ws
+    if shift == 0:
+        return torch.zeros(nW, N, N, dtype=dtype)
+    t = torch.arange(N)
+    iy, ix = t // ws, t % ws
+    out = torch.empty(nW, N, N, dtype=dtype)
+    for wy in range(H // ws):
+        for wx in range(W // ws):
+            rid = 3 * _region(wy * ws + iy, H, ws, shift) + _region(wx * ws + ix, W, ws, shift)
+            diff = rid[None, :] != rid[:, None]
+            out[wy * (W // ws) + wx] = torch.where(diff, -100.0, 0.0).to(dtype)
+    return out
+
+
+def rel_pos_bias(table: torch.Tensor, ws: int) -> torch.Tensor:
+    """swinir.py:57-67,86-91 -- bias[h, i, j] = table[(yi-yj+ws-1)*(2ws-1) + (xi-xj+ws-1), h]."""
+    t = torch.arange(ws * ws)
+    iy, ix = t // ws, t % ws
+    idx = (iy[:, None] - iy[None, :] + ws - 1) * (2 * ws - 1) + (ix[:, None] - ix[None, :] + ws - 1)
+    return table[idx.reshape(-1)].reshape(ws * ws, ws * ws, -1).permute(2, 0, 1)
+
+
+def window_attention(P: Dict, pre: str, xw: torch.Tensor, heads: int, ws: int, mask) -> torch.Tensor:
+    """swinir.py:78-105 -- xw [nWB, N, C] -> [nWB, N, C]."""
+    nWB, N, C = xw.shape
+    d = C // heads
+    qkv = xw @ P[pre + ".qkv.weight"].t() + P[pre + ".qkv.bias"]
+    qkv = qkv.reshape(nWB, N, 3, heads, d)
+    q = qkv[:, :, 0].transpose(1, 2) * (d**-0.5)  # [nWB, heads, N, d]
+    k = qkv[:, :, 1].transpose(1, 2)
+    v = qkv[:, :, 2].transpose(1, 2)
+    s = q @ k.transpose(-1, -2) + rel_pos_bias(P[pre + ".relative_position_bias_table"], ws)[None]
+    if mask is not None:
+        nW = mask.shape[0]
+        s = (s.reshape(nWB // nW, nW, heads, N, N) + mask[None, :, None]).reshape(nWB, heads, N, N)
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(nWB, N, C)
+    return o @ P[pre + ".proj.weight"].t() + P[pre + ".proj.bias"]
+
+
+def to_windows(x: torch.Tensor, ws: int) -> torch.Tensor:
+    """common.py:236-240 -- [B,H,W,C] -> [B*nW, ws*ws, C]."""
+    B, H, W, C = x.shape
+    x = x.reshape(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5)
+    return x.reshape(-1, ws * ws, C)
+
+
+def from_windows(xw: torch.Tensor, ws: int, B: int, H: int, W: int) -> torch.Tensor:
+    """common.py:243-247."""
+    C = xw.shape[-1]
+    x = xw.reshape(B, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5)
+    return x.reshape(B, H, W, C)
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def gelu(x):
+    """nn.GELU() default = exact erf form (common.py:186)."""
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def swin_block(P: Dict, pre: str, x: torch.Tensor, heads: int, ws: int, shift: int) -> torch.Tensor:
+    """swinir.py:146-174 with drop_path == identity -- x [B,H,W,C]."""
+    B, H, W, C = x.shape
+    y = layer_norm(x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
+    if shift > 0:
+        y = torch.roll(y, (-shift, -shift), (1, 2))
+    mask = shift_mask(H, W, ws, shift, x.dtype)  # the reference adds a mask on every block (swinir.py:161)
+    a = window_attention(P, pre + ".attn", to_windows(y, ws), heads, ws, mask)
+    y = from_windows(a, ws, B, H, W)
+    if shift > 0:
+        y = torch.roll(y, (shift, shift), (1, 2))
+    x = x + y
+    y = layer_norm(x, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
+    y = gelu(y @ P[pre + ".mlp.fc1.weight"].t() + P[pre + ".mlp.fc1.bias"])
+    y = y @ P[pre + ".mlp.fc2.weight"].t() + P[pre + ".mlp.fc2.bias"]
+    return x + y
+
+
+def conv3x3(P: Dict, name: str, x: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d(cin, cout, 3, 1, 1) on NCHW."""
+    return F.conv2d(x, P[name + ".weight"], P[name + ".bias"], padding=1)
+
+
+def pixel_shuffle(x: torch.Tensor, r: int) -> torch.Tensor:
+    """nn.PixelShuffle: out[b, c, y*r+i, x*r+j] = in[b, c*r*r + i*r + j, y, x]."""
+    B, Crr, H, W = x.shape
+    C = Crr // (r * r)
+    return x.reshape(B, C, r, r, H, W).permute(0, 1, 4, 2, 5, 3).reshape(B, C, H * r, W * r)
+
+
+def _upsampler(P: Dict, pre: str, x: torch.Tensor, scale: int, n_feats: int, num_out_ch=None):
+    """common.py:124-137."""
+    from .synth import upsampler_convs
+
+    for i, _, r in upsampler_convs(scale, n_feats, num_out_ch):
+        x = pixel_shuffle(conv3x3(P, f"{pre}.{i}", x), r)
+    return x
+
+
+# --------------------------------------------------------------------------- SwinIR
+def swinir_forward(P: Dict, x: torch.Tensor, cfg: Dict, training: bool = False) -> torch.Tensor:
+    """swinir.py:353-372 (+ forward_features :342-351, RSTB :245-246), drop_path off.
+
+    x: [B, n_colors, H, W] float -> [B, n_colors, s*H, s*W]."""
+    dt = x.dtype
+    P = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in P.items()}
+    ws, s, C = cfg["window_size"], cfg["scale"], cfg["embed_dim"]
+    h0, w0 = x.shape[2:]
+    x = pad_for_train(x, ws) if training else pad_for_eval(x, ws)
+    mean = torch.tensor(RGB_MEAN, dtype=dt).view(1, 3, 1, 1)
+    x = x / cfg["img_range"] - mean  # common.py:228-230
+    x0 = conv3x3(P, "conv_first", x)
+    t = x0.permute(0, 2, 3, 1)
+    t = layer_norm(t, P["patch_embed.norm.weight"], P["patch_embed.norm.bias"])
+    for li, depth in enumerate(cfg["depths"]):
+        g = t
+        for bi in range(depth):
+            shift = 0 if bi % 2 == 0 else ws // 2
+            t = swin_block(P, f"layers.{li}.residual_group.blocks.{bi}", t, cfg["num_heads"][li], ws, shift)
+        t = conv3x3(P, f"layers.{li}.conv", t.permute(0, 3, 1, 2)).permute(0, 2, 3, 1) + g
+    t = layer_norm(t, P["norm.weight"], P["norm.bias"])
+    y = conv3x3(P, "conv_after_body", t.permute(0, 3, 1, 2)) + x0
+    if cfg["upsampler"] == "pixelshuffle":
+        y = F.leaky_relu(conv3x3(P, "conv_before_upsample.0", y), 0.01)
+        y = conv3x3(P, "conv_last", _upsampler(P, "upsample", y, s, 64))
+    else:
+        y = _upsampler(P, "upsample", y, s, C, cfg["n_colors"])
+    y = (y + mean) * cfg["img_range"]  # common.py:232-233
+    return y[:, :, : h0 * s, : w0 * s]
+
+
+# --------------------------------------------------------------------------- EDSR
+def edsr_forward(P: Dict, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
+    """edsr.py:39-48 with ResBlock common.py:140-153 and MeanShift common.py:108-121."""
+    dt = x.dtype
+    P = {k: v.to(dt) for k, v in P.items()}
+    x = F.conv2d(x, P["sub_mean.weight"], P["sub_mean.bias"])
+    x = conv3x3(P, "head.0", x)
+    r = x
+    n = cfg["n_resblocks"]
+    for i in range(n):
+        b = conv3x3(P, f"body.{i}.body.2", torch.relu(conv3x3(P, f"body.{i}.body.0", r)))
+        r = b * cfg["res_scale"] + r
+    r = conv3x3(P, f"body.{n}", r) + x
+    y = conv3x3(P, "tail.1", _upsampler(P, "tail.0", r, cfg["scale"], cfg["n_feats"]))
+    return F.conv2d(y, P["add_mean.weight"], P["add_mean.bias"])
+
+
+# --------------------------------------------------------------------------- Model.inference + tiler
+def quantize_u8(y: torch.Tensor, img_range: float) -> torch.Tensor:
+    """common.py:44-45 -- [3,H,W] float -> [H,W,3] uint8 (round half to even, clip)."""
+    scale = 255.0 if img_range == 1.0 else 1.0
+    return (y.permute(1, 2, 0) * scale).round().clip(0, 255).to(torch.uint8)
+
+
+def inference_u8(forward, image_u8, img_range: float = 1.0):
+    """common.py:36-48 -- numpy uint8 [H,W,3] -> numpy uint8 [sH,sW,3]; `forward` is an
+    eval-mode fp32 model forward."""
+    import numpy as np
+
+    scale = 255.0 if img_range == 1.0 else 1.0
+    x = torch.from_numpy(image_u8.astype(np.float32) / scale).permute(2, 0, 1).unsqueeze(0)
+    return quantize_u8(forward(x)[0], img_range).numpy()
+
+
+def tile_starts(L: int, tile: int, stride: int):
+    """Tile origins along one axis: 0, stride, ... with the last tile clamped to L - tile."""
+    if L <= tile:
+        return [0]
+    s = list(range(0, L - tile, stride)) + [L - tile]
+    return s
+
+
+def ramp_weight(tile: int, overlap: int, first: bool, last: bool, scale: int) -> torch.Tensor:
+    """1-D blend weight over scale*tile output samples: linear ramp across the `overlap`
+    LR pixels shared with a neighbour, flat 1 elsewhere (no ramp at the frame border)."""
+    n, o = tile * scale, overlap * scale
+    w = torch.ones(n, dtype=torch.float64)
+    ramp = (torch.arange(o, dtype=torch.float64) + 0.5) / o
+    if not first:
+        w[:o] = ramp
+    if not last:
+        w[n - o:] = ramp.flip(0)
+    return w
+
+
+def tiled_upscale(forward, x: torch.Tensor, scale: int, tile: int = 64, overlap: int = 16) -> torch.Tensor:
+    """NEW capability (the reference has no tiler): the oracle is this tiler
+    calling the reference-equivalent eval forward per tile.  x [1,3,H,W] float.
+
+    Tiles are tile x tile LR crops at stride tile-overlap (last one clamped to the
+    border); outputs are blended with separable linear ramps and normalised by the
+    accumulated weight.  When the last tile is clamped its overlap with the previous
+    tile is larger than `overlap`; the ramp still spans `overlap` pixels, so the
+    normalisation by the weight sum is what keeps the blend exact."""
+    _, C, H, W = x.shape
+    ys, xs = tile_starts(H, tile, tile - overlap), tile_starts(W, tile, tile - overlap)
+    th, tw = min(tile, H), min(tile, W)
+    acc = torch.zeros(C, H * scale, W * scale, dtype=torch.float64)
+    wsum = torch.zeros(H * scale, W * scale, dtype=torch.float64)
+    for iy, y0 in enumerate(ys):
+        wy = ramp_weight(th, min(overlap, th), iy == 0, iy == len(ys) - 1, scale)
+        for ix, x0 in enumerate(xs):
+            wx = ramp_weight(tw, min(overlap, tw), ix == 0, ix == len(xs) - 1, scale)
+            out = forward(x[:, :, y0 : y0 + th, x0 : x0 + tw])[0].to(torch.float64)
+            w2 = wy[:, None] * wx[None, :]
+            acc[:, y0 * scale : (y0 + th) * scale, x0 * scale : (x0 + tw) * scale] += out * w2
+            wsum[y0 * scale : (y0 + th) * scale, x0 * scale : (x0 + tw) * scale] += w2
+    return (acc / wsum).to(x.dtype).unsqueeze(0)
+
+
+def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 255.0) -> float:
+    """utils/metrics.py:36-49 on already-cropped arrays (no Y conversion)."""
+    mse = ((a.double() - b.double()) ** 2).mean().item()
+    return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)

@@ -1,0 +1,89 @@
+"""CPU: pin the oracle restatement (oracle/sr_oracle.py) against fixtures produced by
+executing the unmodified reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sr_oracle as O
+from oracle import synth
+from tests.conftest import load_golden
+
+SWINIR_CASES = [
+    "swinir_tiny_x4_eval_2x20x28", "swinir_tiny_x4_eval_1x16x16", "swinir_tiny_x4_train_1x12x12",
+    "swinir_tiny_x4_train_2x16x24", "swinir_tiny_x2_eval_1x12x12", "swinir_tiny_x3_eval_1x8x8",
+    "swinir_tiny_x8_eval_1x8x8", "swinir_light_x4_eval_1x12x20", "swinir_full_x4_eval_cfg1",
+]
+EDSR_CASES = ["edsr_tiny_x4_2x12x20", "edsr_tiny_x2_1x9x11", "edsr_tiny_x3_1x8x8", "edsr_full_x4_1x24x24"]
+
+
+@pytest.mark.parametrize("name", SWINIR_CASES)
+def test_swinir_oracle_matches_reference_golden(name, golden_meta):
+    c = golden_meta[name]
+    P = synth.swinir_weights(c["cfg"], c["wseed"])
+    x = synth.image_batch(c["shape"], c["xseed"])
+    y = O.swinir_forward(P, x, c["cfg"], training=c["training"])
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    # same fp32 math, different op order: reference fp32-vs-fp64 noise is 3.6e-7
+    assert (y - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name", EDSR_CASES)
+def test_edsr_oracle_matches_reference_golden(name, golden_meta):
+    c = golden_meta[name]
+    P = synth.edsr_weights(c["cfg"], c["wseed"])
+    x = synth.image_batch(c["shape"], c["xseed"])
+    y = O.edsr_forward(P, x, c["cfg"])
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert (y - ref).abs().max().item() < 2e-5
+
+
+def test_ops_match_reference(golden_meta):
+    g = load_golden("swinir_ops")
+    c = golden_meta["swinir_ops"]
+    assert np.array_equal(O.shift_mask(24, 32, 8, 4, torch.float32).numpy(), g["mask_24x32_ws8_s4"])
+    assert np.array_equal(O.shift_mask(16, 16, 8, 0, torch.float32).numpy(), g["mask_16x16_ws8_s0"])
+    assert np.array_equal(synth.relative_position_index(8).numpy(), g["rpi_ws8"])
+    xpad = synth.image_batch((1, 3, 13, 16), c["pad_seed"])
+    assert np.array_equal(O.pad_for_eval(xpad, 8).numpy(), g["pad_eval_13x16"])
+    assert np.array_equal(O.pad_for_train(xpad, 8).numpy(), g["pad_train_13x16"])
+    P = synth.swinir_weights(c["cfg"], c["wseed"])
+    xb = torch.randn(2, 16, 24, 60, generator=torch.Generator().manual_seed(c["xb_seed"]))
+    yb = O.swin_block(P, c["block"], xb, 6, 8, 4)
+    assert np.abs(yb.numpy() - g["block_shift4_out"]).max() < 1e-5
+    xw = torch.randn(6, 64, 60, generator=torch.Generator().manual_seed(c["xw_seed"]))
+    a = O.window_attention(P, c["block"] + ".attn", xw, 6, 8, O.shift_mask(16, 24, 8, 4, torch.float32))
+    assert np.abs(a.numpy() - g["winattn_masked_out"]).max() < 1e-5
+    a = O.window_attention(P, c["block"] + ".attn", xw, 6, 8, None)
+    assert np.abs(a.numpy() - g["winattn_nomask_out"]).max() < 1e-5
+
+
+def test_inference_u8_matches_reference(golden_meta):
+    g = load_golden("swinir_tiny_x4_inference_u8")
+    cfg = golden_meta["swinir_ops"]["cfg"]
+    P = synth.swinir_weights(cfg, 11)
+    out = O.inference_u8(lambda x: O.swinir_forward(P, x, cfg), g["img"])
+    # uint8 rounding can flip on 1e-6 float noise: allow a handful of +-1 LSB
+    d = np.abs(out.astype(np.int32) - g["out"].astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+def test_fp64_oracle_close_to_fp32_golden(golden_meta):
+    name = "swinir_tiny_x4_eval_2x20x28"
+    c = golden_meta[name]
+    P = synth.swinir_weights(c["cfg"], c["wseed"])
+    x = synth.image_batch(c["shape"], c["xseed"]).double()
+    y = O.swinir_forward(P, x, c["cfg"])
+    ref = torch.from_numpy(load_golden(name)["y"]).double()
+    assert (y - ref).abs().max().item() < 2e-5
+
+
+def test_tiler_identity_and_tile_starts():
+    assert O.tile_starts(960, 64, 48) == list(range(0, 896, 48)) + [896]
+    assert len(O.tile_starts(960, 64, 48)) == 20 and len(O.tile_starts(540, 64, 48)) == 11
+    assert O.tile_starts(50, 64, 48) == [0]
+    # a forward that is a pure x4 nearest upsample must be reproduced exactly by the blend
+    x = synth.image_batch((1, 3, 100, 130), 5)
+    up = lambda t: t.repeat_interleave(4, 2).repeat_interleave(4, 3)
+    y = O.tiled_upscale(up, x, 4, tile=64, overlap=16)
+    assert (y - up(x)).abs().max().item() < 1e-6
