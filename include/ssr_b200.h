@@ -1,0 +1,162 @@
+/*
+ * libssr_b200 -- C ABI of the B200-native (sm_100a) super-resolution hot path.
+ *
+ * The reference (veritross/studiosr) is pure PyTorch and has no FFI of its own
+ * (SURVEY.md §8b); the boundary it fixes is the Python class API of
+ * `studiosr.models`.  This header is the C-ABI that sits directly beneath the
+ * drop-in classes in studiosr_b200/models/ and is what any other host (C++,
+ * ctypes, cgo, JNI ...) would bind.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is either a HOST pointer or a CUDA DEVICE
+ *     pointer as documented per argument; no torch types, no hidden allocations of
+ *     activation memory (the caller owns inputs, outputs and the workspace).
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as
+ *     void*); nothing synchronises the host unless documented (the *_host entry).
+ *   - return value: 0 = success, negative = SSR_E_* ; the message is available from
+ *     ssr_last_error() (thread-local).
+ *   - there is no CPU fallback: on a device that is not sm_100 every compute entry
+ *     returns SSR_E_ARCH.
+ */
+#ifndef SSR_B200_H
+#define SSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSR_VERSION 100
+
+enum {
+  SSR_OK = 0,
+  SSR_E_INVALID = -1,   /* bad argument / shape / unknown parameter name */
+  SSR_E_ARCH = -2,      /* device is not sm_100 (B200) */
+  SSR_E_CUDA = -3,      /* CUDA runtime / driver error (message has the detail) */
+  SSR_E_STATE = -4,     /* model not finalised / missing parameter */
+  SSR_E_WORKSPACE = -5  /* workspace too small */
+};
+
+enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1 };
+
+/* arithmetic of the contractions */
+enum {
+  SSR_PREC_FP32 = 0, /* CUDA-core fp32 FMA (bit-faithful to the reference's fp32 semantics up to summation order) */
+  SSR_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 activations, fp32 accumulate */
+  SSR_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate, fp32 residual stream / LN / softmax */
+};
+
+/* padding applied before the network, i.e. which reference branch of SwinIR.forward is mirrored */
+enum {
+  SSR_PAD_EVAL = 0, /* swinir.py:249-255 check_image_size_for_eval: always pads, edge-inclusive mirror */
+  SSR_PAD_TRAIN = 1 /* common.py:277-282 check_image_size: reflect pad to the next multiple */
+};
+
+#define SSR_MAX_LAYERS 16
+
+/* Mirrors the constructor arguments of studiosr.models.SwinIR (swinir.py:259-274) and
+ * studiosr.models.EDSR (edsr.py:13-21). */
+typedef struct ssr_model_config {
+  int arch;      /* SSR_ARCH_* */
+  int precision; /* SSR_PREC_* */
+  int scale;     /* 2, 3, 4 or 8 */
+  int n_colors;  /* 3 */
+  float img_range;
+  /* SwinIR */
+  int embed_dim;
+  int n_layers;
+  int depths[SSR_MAX_LAYERS];
+  int num_heads[SSR_MAX_LAYERS];
+  int window_size;
+  float mlp_ratio;
+  int upsampler; /* 0 = "pixelshuffle", 1 = "pixelshuffledirect" */
+  /* EDSR */
+  int n_feats;
+  int n_resblocks;
+  float res_scale;
+} ssr_model_config;
+
+typedef struct ssr_model ssr_model_t;
+
+int ssr_version(void);
+const char* ssr_last_error(void);
+/* 0 if `device` (CUDA ordinal) is an sm_100 part, SSR_E_ARCH otherwise. */
+int ssr_device_check(int device);
+
+/* ---- model life cycle: replaces nn.Module construction + load_state_dict ------------------
+ * ssr_model_set_param takes the reference's state_dict entry `name` (e.g.
+ * "layers.0.residual_group.blocks.1.attn.qkv.weight") as a HOST fp32 array in PyTorch layout
+ * ([out,in] linear, [out,in,kh,kw] conv).  Integer buffers (relative_position_index) are
+ * derived internally and need not be passed.  ssr_model_finalize re-packs everything into the
+ * padded K-major device layouts the kernels consume and uploads it; it may be
+ * called again after parameters change. */
+int ssr_model_create(const ssr_model_config* cfg, int device, ssr_model_t** out);
+int ssr_model_set_param(ssr_model_t* m, const char* name, const float* host_data, int64_t numel);
+int ssr_model_finalize(ssr_model_t* m);
+void ssr_model_destroy(ssr_model_t* m);
+
+/* ---- forward: replaces SwinIR.forward (swinir.py:353-372) / EDSR.forward (edsr.py:39-48) ----
+ * x: DEVICE fp32 NCHW [B, n_colors, H, W];  y: DEVICE fp32 NCHW [B, n_colors, scale*H, scale*W].
+ * pad_mode selects the eval / train padding branch (ignored by EDSR). */
+size_t ssr_model_workspace_bytes(const ssr_model_t* m, int B, int H, int W, int pad_mode);
+int ssr_model_forward(ssr_model_t* m, const float* x, float* y, int B, int H, int W, int pad_mode,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Model.inference (common.py:36-48) on device buffers ----------------------------------
+ * img: DEVICE uint8 HWC [H, W, 3] -> out: DEVICE uint8 HWC [scale*H, scale*W, 3];
+ * /255 (img_range == 1), eval-mode forward, *255, round-half-even, clip, all fused into the
+ * first / last kernels.  Batch of `B` independent images of the same size. */
+int ssr_model_upscale_u8(ssr_model_t* m, const uint8_t* img, uint8_t* out, int B, int H, int W,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- tiled full-frame inference (BASELINE.json config 5; new capability, the reference has no
+ * tiler): frame DEVICE uint8 HWC [H, W, 3] -> DEVICE uint8 HWC [scale*H, scale*W, 3].  Tiles of
+ * tile x tile LR pixels at stride tile-overlap (last clamped to the border) run as one batch
+ * through the eval forward; outputs are blended with separable linear ramps (oracle:
+ * oracle/sr_oracle.py:tiled_upscale).  Tiles [tile_begin, tile_end) of the row-major tile list
+ * are processed (for sharding a frame across ranks); pass 0, -1 for all. */
+int ssr_tiled_num_tiles(int H, int W, int tile, int overlap);
+size_t ssr_model_tiled_workspace_bytes(const ssr_model_t* m, int H, int W, int tile, int overlap, int chunk_tiles);
+int ssr_model_upscale_tiled_u8(ssr_model_t* m, const uint8_t* frame, uint8_t* out, int H, int W, int tile,
+                               int overlap, int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, HOST buffers (pinned or pageable): H2D copy, compute, D2H copy, stream synchronise. */
+int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, uint8_t* out_host, int H, int W,
+                                    int tile, int overlap, int chunk_tiles, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+int64_t ssr_launch_count(void);
+
+/* ---- op-level entry points (used by the parity tests; same kernels the model path runs) -----
+ * All tensors DEVICE fp32 in the reference's own layouts; the library packs / pads internally
+ * into scratch carved from `workspace`. */
+
+/* nn.Linear with the fused epilogue of the model path:
+ *   v = act(x[M,K] @ W[N,K]^T + b) (+ res[M,N]);  y = v;  y_ln = LayerNorm(v) * ln_w + ln_b (eps 1e-5)
+ * act: 0 none, 1 relu, 2 leaky-relu(0.01), 3 exact-erf GELU.  res, ln_w/ln_b, y, y_ln may be NULL.
+ * Replaces nn.Linear / Mlp / nn.LayerNorm call sites swinir.py:80,103,151,172 and common.py:184-194. */
+int ssr_op_linear(int precision, const float* x, const float* W, const float* b, const float* res, int act,
+                  const float* ln_w, const float* ln_b, float* y, float* y_ln, int M, int K, int N, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* nn.Conv2d(Cin, Cout, 3, 1, 1) on NCHW fp32 (swinir.py:241,316,321-326; common.py:104,124-153):
+ *   v = act(conv(x) + b) * alpha (+ res);  optional nn.PixelShuffle(ps_r) folded into the store, in which
+ * case y is [B, Cout/ps_r^2, H*ps_r, W*ps_r] (ps_r = 0/1: none; exclusive with res). */
+int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b, const float* res, float* y, int B,
+                   int Cin, int Cout, int H, int Wd, int act, float alpha, int ps_r, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* SwinIR (shifted-)window attention core, swinir.py:78-105 minus the two Linear layers, together with
+ * the roll / window_partition / window_reverse / calculate_mask around it (swinir.py:154-168,
+ * common.py:236-274): qkv [B,H,W,3*C] (q|k|v, each head-major, un-scaled) -> o [B,H,W,C]; q scaling,
+ * relative-position bias (table [(2ws-1)^2, heads]) and the shift mask are applied inside the kernel. */
+int ssr_op_window_attention(int precision, const float* qkv, const float* bias_table, float* o, int B, int H, int W,
+                            int C, int heads, int ws, int shift, void* workspace, size_t workspace_bytes,
+                            void* stream);
+size_t ssr_op_workspace_bytes(int64_t max_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSR_B200_H */

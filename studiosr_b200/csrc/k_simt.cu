@@ -1,0 +1,674 @@
+// CUDA-core kernels: the exact-fp32 implicit GEMM (SSR_PREC_FP32), fp32 window attention,
+// LayerNorm, and the memory-bound ends of the network (first conv with fused input handling,
+// last conv with fused output handling, tile blend) plus layout utilities.
+#include <math.h>
+
+#include "ssr_device.cuh"
+
+namespace ssr {
+
+// =============================================================================================
+// fp32 implicit GEMM, fused epilogue.  Tile: 32 rows x BN columns, K step 16, 256 threads; thread
+// (ty = warp, tx = lane) owns rows ty*4..+3 and columns tx + 32*j.
+// =============================================================================================
+constexpr int SG_BM = 32;
+constexpr int SG_BK = 16;
+
+template <int BN>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g) {
+  extern __shared__ float smem[];
+  float* As = smem;                          // [BM][BK+1]
+  float* Ws = smem + SG_BM * (SG_BK + 1);    // [BK][BN]
+  float* Vs = smem;                          // [BM][BN+1], aliases As/Ws after the main loop
+  constexpr int NJ = BN / 32;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int m0 = blockIdx.x * SG_BM, n0 = blockIdx.y * BN;
+  const float* __restrict__ A = reinterpret_cast<const float*>(g.A);
+  const float* __restrict__ Wt = reinterpret_cast<const float*>(g.Wt);
+  const int Ktot = g.taps * g.KP;
+
+  float acc[4][NJ];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0f;
+
+  const int lr = tid >> 3, lk = (tid & 7) * 2;
+  const int lm = m0 + lr;
+  const bool lvalid = lm < g.M;
+  int px = 0, py = 0, pb = 0;
+  if (g.taps == 9 && lvalid) {
+    px = lm % g.W;
+    py = (lm / g.W) % g.H;
+    pb = lm / (g.W * g.H);
+  }
+  for (int tap = 0; tap < g.taps; ++tap) {
+    const float* arow = nullptr;
+    if (lvalid) {
+      if (g.taps == 9) {
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        if (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) arow = A + ((size_t)(pb * g.H + yy) * g.W + xx) * g.lda;
+      } else {
+        arow = A + (size_t)lm * g.lda;
+      }
+    }
+    for (int k0 = 0; k0 < g.KP; k0 += SG_BK) {
+      float2 av = arow ? *reinterpret_cast<const float2*>(arow + k0 + lk) : make_float2(0.f, 0.f);
+      As[lr * (SG_BK + 1) + lk] = av.x;
+      As[lr * (SG_BK + 1) + lk + 1] = av.y;
+      for (int n = tid; n < BN; n += 256) {
+        const float4* wp = reinterpret_cast<const float4*>(Wt + (size_t)(n0 + n) * Ktot + (size_t)tap * g.KP + k0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = __ldg(wp + q);
+          Ws[(q * 4 + 0) * BN + n] = w.x;
+          Ws[(q * 4 + 1) * BN + n] = w.y;
+          Ws[(q * 4 + 2) * BN + n] = w.z;
+          Ws[(q * 4 + 3) * BN + n] = w.w;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < SG_BK; ++kk) {
+        float a[4], w[NJ];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[(ty * 4 + i) * (SG_BK + 1) + kk];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) w[j] = Ws[kk * BN + tx + 32 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  const int Cps = g.ps_r > 1 ? g.N / (g.ps_r * g.ps_r) : 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    const bool valid = m < g.M;
+    int b = 0, y = 0, x = 0;
+    if (valid && g.ps_r > 1) {
+      x = m % g.W;
+      y = (m / g.W) % g.H;
+      b = m / (g.W * g.H);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int n = n0 + tx + 32 * j;
+      float v = 0.0f;
+      if (valid) {
+        v = apply_act(acc[i][j] + __ldg(g.bias + n), g.act, g.slope) * g.alpha;
+        if (g.res) v += g.res[(size_t)m * g.ldres + n];
+        if (n >= g.N) v = 0.0f;
+        if (g.out_f32) g.out_f32[(size_t)m * g.ld_f32 + n] = v;
+        if (g.out_T) {
+          float* o = reinterpret_cast<float*>(g.out_T);
+          const float vs = g.round_tf32 ? round_tf32(v) : v;
+          if (g.ps_r > 1) {
+            if (n < g.N) o[ps_offset(b, y, x, n, g.H, g.W, g.ps_r, Cps, g.ld_T)] = vs;
+          } else {
+            o[(size_t)m * g.ld_T + n] = vs;
+          }
+        }
+      }
+      if (g.out_ln) acc[i][j] = v;
+    }
+  }
+  if (g.out_ln) {  // BN == NP here (host guarantees gridDim.y == 1)
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) Vs[(ty * 4 + i) * (BN + 1) + tx + 32 * j] = acc[i][j];
+    __syncthreads();
+    float* o = reinterpret_cast<float*>(g.out_ln);
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty * 4 + i, m = m0 + r;
+      if (m >= g.M) continue;
+      float s = 0.0f;
+      for (int n = tx; n < g.N; n += 32) s += Vs[r * (BN + 1) + n];
+      const float mean = warp_sum(s) / (float)g.N;
+      float q = 0.0f;
+      for (int n = tx; n < g.N; n += 32) {
+        const float d = Vs[r * (BN + 1) + n] - mean;
+        q += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)g.N + g.eps);
+      for (int n = tx; n < BN; n += 32) {
+        float yv = 0.0f;
+        if (n < g.N) yv = (Vs[r * (BN + 1) + n] - mean) * rstd * __ldg(g.gamma + n) + __ldg(g.beta + n);
+        o[(size_t)m * g.ld_ln + n] = g.round_tf32 ? round_tf32(yv) : yv;
+      }
+    }
+  }
+}
+
+template <int BN>
+static int launch_gemm_simt_bn(const GemmArgs& g, cudaStream_t s) {
+  const size_t main_bytes = (size_t)(SG_BM * (SG_BK + 1) + SG_BK * BN) * sizeof(float);
+  const size_t ln_bytes = (size_t)SG_BM * (BN + 1) * sizeof(float);
+  const size_t smem = main_bytes > ln_bytes ? main_bytes : ln_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSR_CUDA(cudaFuncSetAttribute(gemm_simt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((g.M + SG_BM - 1) / SG_BM, g.NP / BN);
+  gemm_simt_kernel<BN><<<grid, 256, smem, s>>>(g);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t s) {
+  SSR_CHECK(g.NP % 64 == 0 && g.KP % 16 == 0, SSR_E_INVALID, "gemm_simt: NP=%d KP=%d not padded", g.NP, g.KP);
+  if (g.out_ln) {
+    SSR_CHECK(g.NP <= 256, SSR_E_INVALID, "gemm_simt: fused LayerNorm needs NP<=256 (NP=%d)", g.NP);
+    switch (g.NP) {
+      case 64: return launch_gemm_simt_bn<64>(g, s);
+      case 128: return launch_gemm_simt_bn<128>(g, s);
+      case 192: return launch_gemm_simt_bn<192>(g, s);
+      case 256: return launch_gemm_simt_bn<256>(g, s);
+    }
+  }
+  if (g.NP % 256 == 0) return launch_gemm_simt_bn<256>(g, s);
+  if (g.NP % 192 == 0) return launch_gemm_simt_bn<192>(g, s);
+  if (g.NP % 128 == 0) return launch_gemm_simt_bn<128>(g, s);
+  return launch_gemm_simt_bn<64>(g, s);
+}
+
+// =============================================================================================
+// fp32 (shifted-)window attention: one CTA per window, loops heads and 64-query row blocks.
+// =============================================================================================
+__global__ void __launch_bounds__(256) attn_simt_kernel(const AttnArgs a) {
+  extern __shared__ float smem[];
+  const int N = a.ws * a.ws;
+  const int DPp = a.DP + 1;
+  float* ks = smem;                // [N][DP+1]
+  float* vs = ks + N * DPp;        // [N][DP+1]
+  float* qs = vs + N * DPp;        // [64][DP+1]
+  float* S = qs + 64 * DPp;        // [64][N+1]
+  int* pix = reinterpret_cast<int*>(S + 64 * (N + 1));  // [N] source row index of each window token
+  int* rid = pix + N;                                   // [N] shift-mask region id
+
+  const int nwx = a.W / a.ws, nwy = a.H / a.ws;
+  int w = blockIdx.x;
+  const int wx = w % nwx;
+  w /= nwx;
+  const int wy = w % nwy;
+  const int b = w / nwy;
+  const int tid = threadIdx.x;
+  const float* qkv = reinterpret_cast<const float*>(a.qkv);
+  float* o = reinterpret_cast<float*>(a.o);
+  const int nb = 2 * a.ws - 1;
+
+  for (int t = tid; t < N; t += blockDim.x) {
+    const int sy = wy * a.ws + t / a.ws, sx = wx * a.ws + t % a.ws;
+    const int yy = (sy + a.shift) % a.H, xx = (sx + a.shift) % a.W;
+    pix[t] = (b * a.H + yy) * a.W + xx;
+    rid[t] = a.shift > 0 ? 3 * shift_region(sy, a.H, a.ws, a.shift) + shift_region(sx, a.W, a.ws, a.shift) : 0;
+  }
+  __syncthreads();
+
+  for (int h = 0; h < a.heads; ++h) {
+    for (int e = tid; e < N * a.DP; e += blockDim.x) {
+      const int t = e / a.DP, j = e % a.DP;
+      const float* row = qkv + (size_t)pix[t] * a.ld_qkv + h * a.DP + j;
+      ks[t * DPp + j] = row[a.QP];
+      vs[t * DPp + j] = row[2 * a.QP];
+    }
+    const float* btab = a.bias + (size_t)h * nb * nb;
+    for (int q0 = 0; q0 < N; q0 += 64) {
+      __syncthreads();
+      for (int e = tid; e < 64 * a.DP; e += blockDim.x) {
+        const int t = e / a.DP, j = e % a.DP;
+        qs[t * DPp + j] = qkv[(size_t)pix[q0 + t] * a.ld_qkv + h * a.DP + j];
+      }
+      __syncthreads();
+      for (int e = tid; e < 64 * N; e += blockDim.x) {
+        const int i = e / N, j = e % N;
+        const int ti = q0 + i;
+        float s = 0.0f;
+        for (int c = 0; c < a.d; ++c) s = fmaf(qs[i * DPp + c], ks[j * DPp + c], s);
+        const int dy = ti / a.ws - j / a.ws + a.ws - 1, dx = ti % a.ws - j % a.ws + a.ws - 1;
+        s += __ldg(btab + dy * nb + dx);
+        if (rid[ti] != rid[j]) s += -100.0f;
+        S[i * (N + 1) + j] = s;
+      }
+      __syncthreads();
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int i = warp; i < 64; i += 8) {
+        float mx = -INFINITY;
+        for (int j = lane; j < N; j += 32) mx = fmaxf(mx, S[i * (N + 1) + j]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < N; j += 32) {
+          const float p = expf(S[i * (N + 1) + j] - mx);
+          S[i * (N + 1) + j] = p;
+          sum += p;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < N; j += 32) S[i * (N + 1) + j] *= inv;
+      }
+      __syncthreads();
+      for (int e = tid; e < 64 * a.DP; e += blockDim.x) {
+        const int i = e / a.DP, c = e % a.DP;
+        float acc = 0.0f;
+        if (c < a.d)
+          for (int j = 0; j < N; ++j) acc = fmaf(S[i * (N + 1) + j], vs[j * DPp + c], acc);
+        o[(size_t)pix[q0 + i] * a.ld_o + h * a.DP + c] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_attn_simt(const AttnArgs& a, cudaStream_t s) {
+  const int N = a.ws * a.ws;
+  SSR_CHECK(N % 64 == 0, SSR_E_INVALID, "attn_simt: window_size^2 must be a multiple of 64 (ws=%d)", a.ws);
+  SSR_CHECK(a.H % a.ws == 0 && a.W % a.ws == 0, SSR_E_INVALID, "attn: %dx%d not a multiple of ws=%d", a.H, a.W, a.ws);
+  const size_t smem = (size_t)(2 * N * (a.DP + 1) + 64 * (a.DP + 1) + 64 * (N + 1)) * sizeof(float) + 2 * N * sizeof(int);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    SSR_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int nwin = a.B * (a.H / a.ws) * (a.W / a.ws);
+  attn_simt_kernel<<<nwin, 256, smem, s>>>(a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// =============================================================================================
+// LayerNorm (one warp per row), optionally two chained LNs (patch_embed.norm -> blocks.0.norm1).
+// =============================================================================================
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.M) return;
+  const float* x = a.in + (size_t)warp * a.ld_in;
+  float v[8];
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane + 32 * j;
+    v[j] = n < a.C ? x[n] : 0.0f;
+    s += v[j];
+  }
+  float mean = warp_sum(s) / (float)a.C;
+  float q = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane + 32 * j;
+    if (n < a.C) q += (v[j] - mean) * (v[j] - mean);
+  }
+  float rstd = rsqrtf(warp_sum(q) / (float)a.C + a.eps);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane + 32 * j;
+    v[j] = n < a.C ? (v[j] - mean) * rstd * __ldg(a.g1 + n) + __ldg(a.b1 + n) : 0.0f;
+    if (a.out_f32 && n < a.CP) a.out_f32[(size_t)warp * a.ld_f32 + n] = v[j];
+  }
+  if (!a.out_T) return;
+  if (a.g2) {
+    s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    mean = warp_sum(s) / (float)a.C;
+    q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (lane + 32 * j < a.C) q += (v[j] - mean) * (v[j] - mean);
+    rstd = rsqrtf(warp_sum(q) / (float)a.C + a.eps);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = lane + 32 * j;
+      v[j] = n < a.C ? (v[j] - mean) * rstd * __ldg(a.g2 + n) + __ldg(a.b2 + n) : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane + 32 * j;
+    if (n < a.CP) store_elem(a.out_T, (size_t)warp * a.ld_T + n, a.elem, v[j], a.round_tf32);
+  }
+}
+
+int launch_layernorm(const LnArgs& a, cudaStream_t s) {
+  SSR_CHECK(a.CP <= 256, SSR_E_INVALID, "layernorm: C padded %d > 256", a.CP);
+  const int blocks = (a.M + 7) / 8;
+  layernorm_kernel<<<blocks, 256, 0, s>>>(a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// =============================================================================================
+// First conv: n_colors(3) -> Cout, fused uint8/float input, tile addressing, mirror pad, affine.
+// CTA = 16 consecutive padded pixels x Cout channels (thread = channel).
+// =============================================================================================
+constexpr int CF_PIX = 16;
+
+__device__ __forceinline__ int mirror_index(int i, int n, int pad_mode) {
+  if (i < n) return i;
+  return pad_mode == 0 ? 2 * n - 1 - i : 2 * (n - 1) - i;
+}
+
+__global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstArgs a) {
+  __shared__ float patch[CF_PIX][28];
+  const int tid = threadIdx.x;
+  const int M = a.B * a.Hp * a.Wp;
+  const int m0 = blockIdx.x * CF_PIX;
+  for (int e = tid; e < CF_PIX * 27; e += blockDim.x) {
+    const int p = e / 27, k = e % 27;
+    const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+    const int m = m0 + p;
+    float v = 0.0f;
+    if (m < M) {
+      const int x = m % a.Wp, y = (m / a.Wp) % a.Hp, b = m / (a.Wp * a.Hp);
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      if (yy >= 0 && yy < a.Hp && xx >= 0 && xx < a.Wp) {
+        int sy = mirror_index(yy, a.h, a.pad_mode), sx = mirror_index(xx, a.w, a.pad_mode);
+        int img = b;
+        if (a.tile_mode) {
+          const int t = a.tile_begin + b;
+          const int ty = t / a.tiles_x, tx = t % a.tiles_x;
+          int y0 = ty * a.stride, x0 = tx * a.stride;
+          if (y0 > a.fh - a.h) y0 = a.fh - a.h;
+          if (x0 > a.fw - a.w) x0 = a.fw - a.w;
+          sy += y0;
+          sx += x0;
+          img = 0;
+        }
+        float raw;
+        if (a.in_u8)
+          raw = (float)reinterpret_cast<const uint8_t*>(a.in)[((size_t)(img * a.fh + sy) * a.fw + sx) * 3 + ci];
+        else
+          raw = reinterpret_cast<const float*>(a.in)[((size_t)(img * 3 + ci) * a.fh + sy) * a.fw + sx];
+        v = raw * a.in_scale + a.in_shift[ci];
+      }
+    }
+    patch[p][k] = v;
+  }
+  __syncthreads();
+  const int c = tid;
+  const int ldmax = a.out_f32 ? a.ld_f32 : a.ld_T;
+  if (c >= ldmax && !(a.out_T && c < a.ld_T)) return;
+  float w[27];
+  float bias = 0.0f;
+  if (c < a.Cout) {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) w[k] = __ldg(a.Wc + c * 27 + k);
+    bias = __ldg(a.bias + c);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) w[k] = 0.0f;
+  }
+  for (int p = 0; p < CF_PIX; ++p) {
+    const int m = m0 + p;
+    if (m >= M) break;
+    float acc = bias;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc = fmaf(patch[p][k], w[k], acc);
+    if (a.out_f32 && c < a.ld_f32) a.out_f32[(size_t)m * a.ld_f32 + c] = acc;
+    if (a.out_T && c < a.ld_T) store_elem(a.out_T, (size_t)m * a.ld_T + c, a.elem, acc, a.round_tf32);
+  }
+}
+
+int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s) {
+  SSR_CHECK(a.Cout <= 256 && a.ld_f32 <= 256 && a.ld_T <= 256, SSR_E_INVALID, "conv_first: Cout=%d > 256", a.Cout);
+  const int M = a.B * a.Hp * a.Wp;
+  conv_first_kernel<<<(M + CF_PIX - 1) / CF_PIX, 256, 0, s>>>(a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// =============================================================================================
+// Last conv: Cin -> 3 with fused bias / affine / crop / (fp32 NCHW | uint8 HWC) store.
+// One thread per output pixel; weights staged in shared memory as [tap][ci][4].
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) conv_last_kernel(const ConvLastArgs a) {
+  extern __shared__ float wsm[];  // [9*Cin][4]
+  for (int e = threadIdx.x; e < 9 * a.Cin * 4; e += blockDim.x) wsm[e] = __ldg(a.Wc + e);
+  __syncthreads();
+  const long long total = (long long)a.B * a.ch * a.cw;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % a.cw), y = (int)((idx / a.cw) % a.ch), b = (int)(idx / ((long long)a.cw * a.ch));
+  const T* in = reinterpret_cast<const T*>(a.in);
+  float acc0 = a.bias[0], acc1 = a.bias[1], acc2 = a.bias[2];
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= a.Hs || xx < 0 || xx >= a.Ws) continue;
+    const T* row = in + ((size_t)(b * a.Hs + yy) * a.Ws + xx) * a.ldi;
+    const float4* w4 = reinterpret_cast<const float4*>(wsm) + tap * a.Cin;
+    if constexpr (sizeof(T) == 2) {
+      for (int c = 0; c < a.Cin; c += 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + c);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(hp[q]);
+          const float4 wa = w4[c + 2 * q], wb = w4[c + 2 * q + 1];
+          acc0 = fmaf(f.x, wa.x, acc0); acc1 = fmaf(f.x, wa.y, acc1); acc2 = fmaf(f.x, wa.z, acc2);
+          acc0 = fmaf(f.y, wb.x, acc0); acc1 = fmaf(f.y, wb.y, acc1); acc2 = fmaf(f.y, wb.z, acc2);
+        }
+      }
+    } else {
+      for (int c = 0; c < a.Cin; c += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(row + c);
+        const float4 w0 = w4[c], w1 = w4[c + 1], w2 = w4[c + 2], w3 = w4[c + 3];
+        acc0 = fmaf(f.x, w0.x, acc0); acc1 = fmaf(f.x, w0.y, acc1); acc2 = fmaf(f.x, w0.z, acc2);
+        acc0 = fmaf(f.y, w1.x, acc0); acc1 = fmaf(f.y, w1.y, acc1); acc2 = fmaf(f.y, w1.z, acc2);
+        acc0 = fmaf(f.z, w2.x, acc0); acc1 = fmaf(f.z, w2.y, acc1); acc2 = fmaf(f.z, w2.z, acc2);
+        acc0 = fmaf(f.w, w3.x, acc0); acc1 = fmaf(f.w, w3.y, acc1); acc2 = fmaf(f.w, w3.z, acc2);
+      }
+    }
+  }
+  const float r0 = (acc0 + a.out_shift[0]) * a.out_scale;
+  const float r1 = (acc1 + a.out_shift[1]) * a.out_scale;
+  const float r2 = (acc2 + a.out_shift[2]) * a.out_scale;
+  if (a.out_f32) {
+    const size_t plane = (size_t)a.ch * a.cw;
+    float* o = a.out_f32 + (size_t)b * 3 * plane + (size_t)y * a.cw + x;
+    o[0] = r0;
+    o[plane] = r1;
+    o[2 * plane] = r2;
+  }
+  if (a.out_u8) {
+    uint8_t* o = a.out_u8 + ((size_t)(b * a.ch + y) * a.cw + x) * 3;
+    o[0] = (uint8_t)fminf(fmaxf(rintf(r0 * a.u8_scale), 0.0f), 255.0f);
+    o[1] = (uint8_t)fminf(fmaxf(rintf(r1 * a.u8_scale), 0.0f), 255.0f);
+    o[2] = (uint8_t)fminf(fmaxf(rintf(r2 * a.u8_scale), 0.0f), 255.0f);
+  }
+}
+
+int launch_conv_last(const ConvLastArgs& a, cudaStream_t s) {
+  SSR_CHECK(a.Cin % 8 == 0 && a.Cin <= 256, SSR_E_INVALID, "conv_last: Cin=%d", a.Cin);
+  const long long total = (long long)a.B * a.ch * a.cw;
+  const int blocks = (int)((total + 127) / 128);
+  const size_t smem = (size_t)9 * a.Cin * 4 * sizeof(float);
+  if (a.elem == 2)
+    conv_last_kernel<__nv_bfloat16><<<blocks, 128, smem, s>>>(a);
+  else
+    conv_last_kernel<float><<<blocks, 128, smem, s>>>(a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// =============================================================================================
+// Tile blend (gather form): out(Y,X) = sum_t w_t * tile_t / sum_t w_t over the tiles covering it.
+// =============================================================================================
+__device__ __forceinline__ int tile_origin(int i, int stride, int L, int tile) {
+  const int o = i * stride;
+  return o > L - tile ? L - tile : o;
+}
+__device__ __forceinline__ float ramp_w(int p, int n, int o, bool first, bool last) {
+  // p in [0,n): position inside the tile (output samples); o: ramp length (output samples)
+  float w = 1.0f;
+  if (!first && p < o) w = ((float)p + 0.5f) / (float)o;
+  if (!last && p >= n - o) w *= ((float)(n - 1 - p) + 0.5f) / (float)o;
+  return w;
+}
+
+__global__ void __launch_bounds__(256) blend_kernel(const BlendArgs a) {
+  const int OW = a.W * a.scale, OH = a.H * a.scale;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)OW * OH) return;
+  const int X = (int)(idx % OW), Y = (int)(idx / OW);
+  const int th = a.tile < a.H ? a.tile : a.H, tw = a.tile < a.W ? a.tile : a.W;
+  const int stride = a.tile - a.overlap;
+  const int ts_h = th * a.scale, ts_w = tw * a.scale;
+  const int oy = (a.overlap < th ? a.overlap : th) * a.scale, ox = (a.overlap < tw ? a.overlap : tw) * a.scale;
+  float acc[3] = {0.f, 0.f, 0.f};
+  float wsum = 0.0f;
+  for (int iy = 0; iy < a.tiles_y; ++iy) {
+    const int y0 = tile_origin(iy, stride, a.H, th) * a.scale;
+    if (y0 > Y) break;
+    if (Y >= y0 + ts_h) continue;
+    const float wy = ramp_w(Y - y0, ts_h, oy, iy == 0, iy == a.tiles_y - 1);
+    for (int ix = 0; ix < a.tiles_x; ++ix) {
+      const int x0 = tile_origin(ix, stride, a.W, tw) * a.scale;
+      if (x0 > X) break;
+      if (X >= x0 + ts_w) continue;
+      const float w = wy * ramp_w(X - x0, ts_w, ox, ix == 0, ix == a.tiles_x - 1);
+      const float* t = a.tiles + (size_t)(iy * a.tiles_x + ix) * 3 * ts_h * ts_w + (size_t)(Y - y0) * ts_w + (X - x0);
+      acc[0] += w * t[0];
+      acc[1] += w * t[(size_t)ts_h * ts_w];
+      acc[2] += w * t[2 * (size_t)ts_h * ts_w];
+      wsum += w;
+    }
+  }
+  uint8_t* o = a.out + ((size_t)Y * OW + X) * 3;
+  const float inv = 1.0f / wsum;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = (uint8_t)fminf(fmaxf(rintf(acc[c] * inv * a.u8_scale), 0.0f), 255.0f);
+}
+
+int launch_blend(const BlendArgs& a, cudaStream_t s) {
+  const long long total = (long long)a.W * a.scale * a.H * a.scale;
+  blend_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// =============================================================================================
+// layout utilities (op-level tests and model-independent glue)
+// =============================================================================================
+__global__ void pack_rows_kernel(const float* in, int rows, int cols, void* out, int ld, int elem, int rtf32) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * ld) return;
+  const int c = (int)(idx % ld);
+  const long long r = idx / ld;
+  store_elem(out, (size_t)idx, elem, c < cols ? in[r * cols + c] : 0.0f, rtf32);
+}
+int launch_pack_rows(const float* in, int rows, int cols, void* out, int ld, int elem, int rtf32, cudaStream_t s) {
+  const long long total = (long long)rows * ld;
+  pack_rows_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(in, rows, cols, out, ld, elem, rtf32);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+__global__ void unpack_rows_kernel(const void* in, int ld, int elem, float* out, int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int c = (int)(idx % cols);
+  const long long r = idx / cols;
+  out[idx] = load_elem(in, (size_t)(r * ld + c), elem);
+}
+int launch_unpack_rows(const void* in, int ld, int elem, float* out, int rows, int cols, cudaStream_t s) {
+  const long long total = (long long)rows * cols;
+  unpack_rows_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(in, ld, elem, out, rows, cols);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+int launch_fill_zero(void* p, size_t bytes, cudaStream_t s) {
+  SSR_CUDA(cudaMemsetAsync(p, 0, bytes, s));
+  return SSR_OK;
+}
+
+// reference qkv layout [M][3][heads][d] (fp32, un-scaled) -> padded [M][3][heads][DP], q scaled
+__global__ void repack_qkv_kernel(const float* qkv, void* out, int M, int C, int heads, int DP, int QP, float qscale,
+                                  int elem, int rtf32) {
+  const int d = C / heads;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * 3 * QP) return;
+  const int col = (int)(idx % (3 * QP));
+  const long long m = idx / (3 * QP);
+  const int part = col / QP, hc = col % QP, h = hc / DP, j = hc % DP;
+  float v = 0.0f;
+  if (h < heads && j < d) {
+    v = qkv[m * 3 * C + part * C + h * d + j];
+    if (part == 0) v *= qscale;
+  }
+  store_elem(out, (size_t)idx, elem, v, rtf32);
+}
+int launch_repack_qkv(const float* qkv, void* out, int M, int C, int heads, int DP, int QP, float qscale, int elem,
+                      int rtf32, cudaStream_t s) {
+  const long long total = (long long)M * 3 * QP;
+  repack_qkv_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, out, M, C, heads, DP, QP, qscale, elem, rtf32);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+__global__ void unpack_heads_kernel(const void* o, int ld, int elem, float* out, int M, int heads, int d, int DP) {
+  const int C = heads * d;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * C) return;
+  const int c = (int)(idx % C);
+  const long long m = idx / C;
+  out[idx] = load_elem(o, (size_t)(m * ld + (c / d) * DP + c % d), elem);
+}
+int launch_unpack_heads(const void* o, int ld, int elem, float* out, int M, int heads, int d, int DP, cudaStream_t s) {
+  const long long total = (long long)M * heads * d;
+  unpack_heads_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(o, ld, elem, out, M, heads, d, DP);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* in, void* out, int B, int C, int H, int W, int ld, int elem, int rtf32) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * ld) return;
+  const int c = (int)(idx % ld);
+  const long long p = idx / ld;
+  const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+  store_elem(out, (size_t)idx, elem, c < C ? in[((size_t)(b * C + c) * H + y) * W + x] : 0.0f, rtf32);
+}
+int launch_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int ld, int elem, int rtf32,
+                        cudaStream_t s) {
+  const long long total = (long long)B * H * W * ld;
+  nchw_to_nhwc_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(in, out, B, C, H, W, ld, elem, rtf32);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+__global__ void nhwc_to_nchw_kernel(const void* in, int ld, int elem, float* out, int B, int C, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * C * H * W) return;
+  const int x = (int)(idx % W), y = (int)((idx / W) % H), c = (int)((idx / ((long long)W * H)) % C);
+  const int b = (int)(idx / ((long long)W * H * C));
+  out[idx] = load_elem(in, ((size_t)(b * H + y) * W + x) * ld + c, elem);
+}
+int launch_nhwc_to_nchw(const void* in, int ld, int elem, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  const long long total = (long long)B * C * H * W;
+  nhwc_to_nchw_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(in, ld, elem, out, B, C, H, W);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+}  // namespace ssr

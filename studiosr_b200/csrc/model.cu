@@ -1,0 +1,967 @@
+// Host side of libssr_b200: model handle, weight packing, workspace planning and the launch
+// sequences of SwinIR (swinir.py:353-372) and EDSR (edsr.py:39-48), plus the C ABI.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ssr_internal.cuh"
+
+namespace ssr {
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static const float kRgbMean[3] = {0.4488f, 0.4371f, 0.4040f};  // common.py:223 / :111
+
+static inline float tf32_round_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) {
+    u += 0x00001000u;
+    u &= 0xffffe000u;
+  }
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Lin {           // one packed (implicit-)GEMM layer
+  size_t w_off = 0;    // arena offset of T [NP][taps*KP]
+  size_t b_off = 0;    // arena offset of float [NP]
+  int K = 0, KP = 0, N = 0, NP = 0, taps = 1, ps_r = 0;
+};
+struct LNp {
+  size_t g_off = 0, b_off = 0;
+};
+struct Block {
+  LNp norm1, norm2;
+  Lin qkv, proj, fc1, fc2;
+  size_t bias_off = 0;  // float [heads][(2ws-1)^2]
+};
+struct Layer {
+  std::vector<Block> blocks;
+  Lin conv;
+  int heads = 0, d = 0, DP = 0, QP = 0;
+};
+
+}  // namespace ssr
+
+using namespace ssr;
+
+struct ssr_model {
+  ssr_model_config cfg;
+  int device = 0;
+  int elem = 4;  // bytes per activation / weight element
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> params;
+  // packed
+  std::vector<uint8_t> host_arena;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  // SwinIR
+  int C = 0, CP = 0, HID = 0, HP = 0, QPmax = 0;
+  std::vector<Layer> layers;
+  LNp pe_norm, final_norm;
+  size_t conv_first_w = 0, conv_first_b = 0;
+  Lin conv_after_body, conv_before_up;
+  std::vector<Lin> up;  // upsample convs
+  size_t conv_last_w = 0;
+  float conv_last_bias[3] = {0, 0, 0};
+  int last_cin = 64;
+  // EDSR
+  int F = 0, FP = 0;
+  std::vector<Lin> res_a, res_b;
+  Lin body_tail;
+  float sub_bias[3] = {0, 0, 0}, add_bias[3] = {0, 0, 0};
+
+  template <typename T>
+  T* dev(size_t off) const { return reinterpret_cast<T*>(arena + off); }
+};
+
+namespace ssr {
+
+// ---------------------------------------------------------------------------------------------
+// packing helpers (host)
+static size_t arena_alloc(ssr_model* m, size_t bytes) {
+  size_t off = (m->host_arena.size() + 255) & ~(size_t)255;
+  m->host_arena.resize(off + bytes, 0);
+  return off;
+}
+
+static void store_w(ssr_model* m, size_t off, size_t idx, float v) {
+  if (m->elem == 2) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    memcpy(m->host_arena.data() + off + idx * 2, &h, 2);
+  } else {
+    if (m->cfg.precision == SSR_PREC_TF32) v = tf32_round_host(v);
+    memcpy(m->host_arena.data() + off + idx * 4, &v, 4);
+  }
+}
+
+static const std::vector<float>* find_param(ssr_model* m, const std::string& name, size_t numel) {
+  auto it = m->params.find(name);
+  if (it == m->params.end()) {
+    set_error("missing parameter '%s'", name.c_str());
+    return nullptr;
+  }
+  if (it->second.size() != numel) {
+    set_error("parameter '%s' has %zu elements, expected %zu", name.c_str(), it->second.size(), numel);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+static size_t pack_vec(ssr_model* m, const std::vector<float>& v, int NP, float scale = 1.0f) {
+  size_t off = arena_alloc(m, (size_t)NP * 4);
+  float* dst = reinterpret_cast<float*>(m->host_arena.data() + off);
+  for (size_t i = 0; i < v.size(); ++i) dst[i] = v[i] * scale;
+  return off;
+}
+
+// nn.Linear [N][K] -> [NP][KP]; row_src(n') / col_src(k') give the source index or -1 (zero)
+template <typename RowF, typename ColF, typename ScaleF>
+static int pack_linear(ssr_model* m, const std::string& name, int N, int K, int NP, int KP, RowF row_src, ColF col_src,
+                       ScaleF row_scale, Lin* out) {
+  const std::vector<float>* W = find_param(m, name + ".weight", (size_t)N * K);
+  const std::vector<float>* B = find_param(m, name + ".bias", (size_t)N);
+  if (!W || !B) return SSR_E_STATE;
+  out->K = K; out->KP = KP; out->N = N; out->NP = NP; out->taps = 1; out->ps_r = 0;
+  out->w_off = arena_alloc(m, (size_t)NP * KP * m->elem);
+  out->b_off = arena_alloc(m, (size_t)NP * 4);
+  float* bd = reinterpret_cast<float*>(m->host_arena.data() + out->b_off);
+  for (int n = 0; n < NP; ++n) {
+    const int sn = row_src(n);
+    if (sn < 0) continue;
+    const float sc = row_scale(n);
+    bd = reinterpret_cast<float*>(m->host_arena.data() + out->b_off);
+    bd[n] = (*B)[sn] * sc;
+    for (int k = 0; k < KP; ++k) {
+      const int sk = col_src(k);
+      if (sk >= 0) store_w(m, out->w_off, (size_t)n * KP + k, (*W)[(size_t)sn * K + sk] * sc);
+    }
+  }
+  return SSR_OK;
+}
+
+// nn.Conv2d [Cout][Cin][3][3] -> [NP][9*KP] (k = tap*KP + c); ps_r > 1 permutes the output rows to
+// (i, j, c) order so the pixel-shuffled store is channel-contiguous.
+static int pack_conv(ssr_model* m, const std::string& name, int Cout, int Cin, int ps_r, Lin* out) {
+  const std::vector<float>* W = find_param(m, name + ".weight", (size_t)Cout * Cin * 9);
+  const std::vector<float>* B = find_param(m, name + ".bias", (size_t)Cout);
+  if (!W || !B) return SSR_E_STATE;
+  const int NP = round_up(Cout, 64), KP = round_up(Cin, 64);
+  out->K = Cin; out->KP = KP; out->N = Cout; out->NP = NP; out->taps = 9; out->ps_r = ps_r;
+  out->w_off = arena_alloc(m, (size_t)NP * 9 * KP * m->elem);
+  out->b_off = arena_alloc(m, (size_t)NP * 4);
+  const int rr = ps_r > 1 ? ps_r * ps_r : 1, Cps = Cout / rr;
+  for (int n = 0; n < Cout; ++n) {
+    int sn = n;
+    if (ps_r > 1) {
+      const int q = n / Cps, c = n % Cps;
+      sn = c * rr + q;  // q = i*r + j
+    }
+    reinterpret_cast<float*>(m->host_arena.data() + out->b_off)[n] = (*B)[sn];
+    for (int tap = 0; tap < 9; ++tap)
+      for (int c = 0; c < Cin; ++c)
+        store_w(m, out->w_off, (size_t)n * 9 * KP + (size_t)tap * KP + c, (*W)[((size_t)sn * Cin + c) * 9 + tap]);
+  }
+  return SSR_OK;
+}
+
+static int pack_ln(ssr_model* m, const std::string& name, int C, int CP, LNp* out) {
+  const std::vector<float>* g = find_param(m, name + ".weight", (size_t)C);
+  const std::vector<float>* b = find_param(m, name + ".bias", (size_t)C);
+  if (!g || !b) return SSR_E_STATE;
+  out->g_off = pack_vec(m, *g, CP);
+  out->b_off = pack_vec(m, *b, CP);
+  return SSR_OK;
+}
+
+static void upsampler_plan(int scale, std::vector<int>* rs) {  // common.py:124-137
+  rs->clear();
+  if ((scale & (scale - 1)) == 0) {
+    for (int s = scale; s > 1; s >>= 1) rs->push_back(2);
+  } else {
+    rs->push_back(scale);
+  }
+}
+
+static int pack_conv_last(ssr_model* m, const std::string& name, int Cin, size_t* w_off, float* bias3) {
+  const std::vector<float>* W = find_param(m, name + ".weight", (size_t)3 * Cin * 9);
+  const std::vector<float>* B = find_param(m, name + ".bias", 3);
+  if (!W || !B) return SSR_E_STATE;
+  *w_off = arena_alloc(m, (size_t)9 * Cin * 4 * 4);
+  float* dst = reinterpret_cast<float*>(m->host_arena.data() + *w_off);
+  for (int tap = 0; tap < 9; ++tap)
+    for (int c = 0; c < Cin; ++c)
+      for (int co = 0; co < 3; ++co) dst[((size_t)tap * Cin + c) * 4 + co] = (*W)[((size_t)co * Cin + c) * 9 + tap];
+  for (int i = 0; i < 3; ++i) bias3[i] = (*B)[i];
+  return SSR_OK;
+}
+
+static int pack_conv_first(ssr_model* m, const std::string& name, int Cout, size_t* w_off, size_t* b_off) {
+  const std::vector<float>* W = find_param(m, name + ".weight", (size_t)Cout * 27);
+  const std::vector<float>* B = find_param(m, name + ".bias", (size_t)Cout);
+  if (!W || !B) return SSR_E_STATE;
+  *w_off = pack_vec(m, *W, Cout * 27);
+  *b_off = pack_vec(m, *B, Cout);
+  return SSR_OK;
+}
+
+static int finalize_swinir(ssr_model* m) {
+  const ssr_model_config& c = m->cfg;
+  SSR_CHECK(c.n_colors == 3, SSR_E_INVALID, "n_colors must be 3");
+  SSR_CHECK(c.window_size == 8 || c.precision == SSR_PREC_FP32, SSR_E_INVALID,
+            "tensor-core window attention supports window_size 8 (got %d)", c.window_size);
+  const int C = c.embed_dim;
+  m->C = C;
+  m->CP = round_up(C, 64);
+  m->HID = (int)(C * c.mlp_ratio);
+  m->HP = round_up(m->HID, 64);
+  SSR_CHECK(m->CP <= 256, SSR_E_INVALID, "embed_dim %d > 256 not supported", C);
+  const int nb = (2 * c.window_size - 1) * (2 * c.window_size - 1);
+  SSR_TRY(pack_conv_first(m, "conv_first", C, &m->conv_first_w, &m->conv_first_b));
+  SSR_TRY(pack_ln(m, "patch_embed.norm", C, m->CP, &m->pe_norm));
+  m->layers.clear();
+  m->QPmax = 0;
+  for (int li = 0; li < c.n_layers; ++li) {
+    Layer L;
+    L.heads = c.num_heads[li];
+    SSR_CHECK(L.heads > 0 && C % L.heads == 0, SSR_E_INVALID, "embed_dim %d not divisible by heads %d", C, L.heads);
+    L.d = C / L.heads;
+    SSR_CHECK(L.d <= 32, SSR_E_INVALID, "head_dim %d > 32 not supported", L.d);
+    L.DP = L.d <= 16 ? 16 : 32;
+    L.QP = round_up(L.heads * L.DP, 64);
+    if (L.QP > m->QPmax) m->QPmax = L.QP;
+    const int d = L.d, DP = L.DP, QP = L.QP, heads = L.heads;
+    const float qscale = 1.0f / sqrtf((float)d);
+    for (int bi = 0; bi < c.depths[li]; ++bi) {
+      Block B;
+      char pre[128];
+      snprintf(pre, sizeof(pre), "layers.%d.residual_group.blocks.%d", li, bi);
+      const std::string p(pre);
+      SSR_TRY(pack_ln(m, p + ".norm1", C, m->CP, &B.norm1));
+      SSR_TRY(pack_ln(m, p + ".norm2", C, m->CP, &B.norm2));
+      // qkv rows: n' = part*QP + h*DP + j  <-  part*C + h*d + j ; q rows scaled by d^-0.5 (swinir.py:83)
+      auto qkv_row = [=](int n) {
+        const int part = n / QP, hc = n % QP, h = hc / DP, j = hc % DP;
+        return (h < heads && j < d) ? part * C + h * d + j : -1;
+      };
+      auto qkv_scale = [=](int n) { return n < QP ? qscale : 1.0f; };
+      auto ident_c = [=](int k) { return k < C ? k : -1; };
+      auto one = [](int) { return 1.0f; };
+      SSR_TRY(pack_linear(m, p + ".attn.qkv", 3 * C, C, 3 * QP, m->CP, qkv_row, ident_c, qkv_scale, &B.qkv));
+      B.qkv.N = 3 * QP;  // all padded columns are produced (zeros) so the attention kernel can read them
+      auto proj_col = [=](int k) {
+        const int h = k / DP, j = k % DP;
+        return (h < heads && j < d) ? h * d + j : -1;
+      };
+      SSR_TRY(pack_linear(m, p + ".attn.proj", C, C, m->CP, QP, ident_c, proj_col, one, &B.proj));
+      const int HID = m->HID;
+      auto ident_h = [=](int k) { return k < HID ? k : -1; };
+      SSR_TRY(pack_linear(m, p + ".mlp.fc1", HID, C, m->HP, m->CP, ident_h, ident_c, one, &B.fc1));
+      SSR_TRY(pack_linear(m, p + ".mlp.fc2", C, HID, m->CP, m->HP, ident_c, ident_h, one, &B.fc2));
+      // relative position bias table [(2ws-1)^2][heads] -> [heads][(2ws-1)^2]
+      const std::vector<float>* T = find_param(m, p + ".attn.relative_position_bias_table", (size_t)nb * heads);
+      if (!T) return SSR_E_STATE;
+      B.bias_off = arena_alloc(m, (size_t)heads * nb * 4);
+      float* bt = reinterpret_cast<float*>(m->host_arena.data() + B.bias_off);
+      for (int h = 0; h < heads; ++h)
+        for (int i = 0; i < nb; ++i) bt[h * nb + i] = (*T)[(size_t)i * heads + h];
+      L.blocks.push_back(B);
+    }
+    char nm[64];
+    snprintf(nm, sizeof(nm), "layers.%d.conv", li);
+    SSR_TRY(pack_conv(m, nm, C, C, 0, &L.conv));
+    m->layers.push_back(L);
+  }
+  SSR_TRY(pack_ln(m, "norm", C, m->CP, &m->final_norm));
+  SSR_TRY(pack_conv(m, "conv_after_body", C, C, 0, &m->conv_after_body));
+  std::vector<int> rs;
+  upsampler_plan(c.scale, &rs);
+  m->up.clear();
+  if (c.upsampler == 0) {
+    SSR_TRY(pack_conv(m, "conv_before_upsample.0", 64, C, 0, &m->conv_before_up));
+    for (size_t i = 0; i < rs.size(); ++i) {
+      Lin L;
+      char nm[64];
+      snprintf(nm, sizeof(nm), "upsample.%d", (int)(2 * i));
+      SSR_TRY(pack_conv(m, nm, rs[i] * rs[i] * 64, 64, rs[i], &L));
+      m->up.push_back(L);
+    }
+    m->last_cin = 64;
+    SSR_TRY(pack_conv_last(m, "conv_last", 64, &m->conv_last_w, m->conv_last_bias));
+  } else {
+    // pixelshuffledirect: one conv C -> scale^2 * 3, stored un-shuffled; the shuffle happens in the finish kernel
+    Lin L;
+    SSR_TRY(pack_conv(m, "upsample.0", c.scale * c.scale * 3, C, 0, &L));
+    m->up.push_back(L);
+  }
+  return SSR_OK;
+}
+
+static int finalize_edsr(ssr_model* m) {
+  const ssr_model_config& c = m->cfg;
+  SSR_CHECK(c.n_colors == 3, SSR_E_INVALID, "n_colors must be 3");
+  m->F = c.n_feats;
+  m->FP = round_up(m->F, 64);
+  SSR_CHECK(m->FP <= 256, SSR_E_INVALID, "n_feats %d > 256 not supported", m->F);
+  SSR_TRY(pack_conv_first(m, "head.0", m->F, &m->conv_first_w, &m->conv_first_b));
+  const std::vector<float>* sb = find_param(m, "sub_mean.bias", 3);
+  const std::vector<float>* ab = find_param(m, "add_mean.bias", 3);
+  if (!sb || !ab) return SSR_E_STATE;
+  for (int i = 0; i < 3; ++i) {
+    m->sub_bias[i] = (*sb)[i];
+    m->add_bias[i] = (*ab)[i];
+  }
+  m->res_a.assign(c.n_resblocks, Lin());
+  m->res_b.assign(c.n_resblocks, Lin());
+  for (int i = 0; i < c.n_resblocks; ++i) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "body.%d.body.0", i);
+    SSR_TRY(pack_conv(m, nm, m->F, m->F, 0, &m->res_a[i]));
+    snprintf(nm, sizeof(nm), "body.%d.body.2", i);
+    SSR_TRY(pack_conv(m, nm, m->F, m->F, 0, &m->res_b[i]));
+  }
+  char nm[64];
+  snprintf(nm, sizeof(nm), "body.%d", c.n_resblocks);
+  SSR_TRY(pack_conv(m, nm, m->F, m->F, 0, &m->body_tail));
+  std::vector<int> rs;
+  upsampler_plan(c.scale, &rs);
+  m->up.clear();
+  for (size_t i = 0; i < rs.size(); ++i) {
+    Lin L;
+    snprintf(nm, sizeof(nm), "tail.0.%d", (int)(2 * i));
+    SSR_TRY(pack_conv(m, nm, rs[i] * rs[i] * m->F, m->F, rs[i], &L));
+    m->up.push_back(L);
+  }
+  m->last_cin = m->F;
+  SSR_TRY(pack_conv_last(m, "tail.1", m->F, &m->conv_last_w, m->conv_last_bias));
+  return SSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace planning
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+static void padded_size(const ssr_model* m, int H, int W, int pad_mode, int* Hp, int* Wp) {
+  if (m->cfg.arch != SSR_ARCH_SWINIR) {
+    *Hp = H;
+    *Wp = W;
+    return;
+  }
+  const int ws = m->cfg.window_size;
+  if (pad_mode == SSR_PAD_EVAL) {
+    *Hp = (H / ws + 1) * ws;
+    *Wp = (W / ws + 1) * ws;
+  } else {
+    *Hp = (H + ws - 1) / ws * ws;
+    *Wp = (W + ws - 1) / ws * ws;
+  }
+}
+
+struct SwinWs {
+  float *x0, *g, *t;
+  void *xn, *qkv, *o, *hbuf, *tb, *cbu, *hr[2];
+  size_t hr_elems[2];
+};
+
+static size_t plan_swinir(const ssr_model* m, void* base, int B, int Hp, int Wp, SwinWs* w) {
+  Carver c(base);
+  const size_t T = (size_t)B * Hp * Wp, e = m->elem;
+  w->x0 = (float*)c.take(T * m->CP * 4);
+  w->g = (float*)c.take(T * m->CP * 4);
+  w->t = (float*)c.take(T * m->CP * 4);
+  w->xn = c.take(T * m->CP * e);
+  w->qkv = c.take(T * 3 * m->QPmax * e);
+  w->o = c.take(T * m->QPmax * e);
+  w->hbuf = c.take(T * m->HP * e);
+  w->tb = c.take(T * m->CP * e);
+  w->cbu = c.take(T * 64 * e);
+  // high-resolution ping-pong buffers of the pixel-shuffle tail (64 channels)
+  size_t need[2] = {0, 0};
+  size_t px = T;
+  for (size_t i = 0; i < m->up.size() && m->cfg.upsampler == 0; ++i) {
+    px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
+    if (px * 64 > need[i & 1]) need[i & 1] = px * 64;
+  }
+  if (m->cfg.upsampler == 1) need[0] = T * m->up[0].NP;
+  for (int i = 0; i < 2; ++i) {
+    w->hr_elems[i] = need[i];
+    w->hr[i] = need[i] ? c.take(need[i] * e) : nullptr;
+  }
+  return c.off + 1024;
+}
+
+struct EdsrWs {
+  float *x, *r;
+  void *rb, *tmp, *hr[2];
+};
+static size_t plan_edsr(const ssr_model* m, void* base, int B, int H, int W, EdsrWs* w) {
+  Carver c(base);
+  const size_t T = (size_t)B * H * W, e = m->elem;
+  w->x = (float*)c.take(T * m->FP * 4);
+  w->r = (float*)c.take(T * m->FP * 4);
+  w->rb = c.take(T * m->FP * e);
+  w->tmp = c.take(T * m->FP * e);
+  size_t need[2] = {0, 0};
+  size_t px = T;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
+    if (px * m->FP > need[i & 1]) need[i & 1] = px * m->FP;
+  }
+  for (int i = 0; i < 2; ++i) w->hr[i] = need[i] ? c.take(need[i] * e) : nullptr;
+  return c.off + 1024;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+static int run_gemm(const ssr_model* m, GemmArgs& g, cudaStream_t s) {
+  g.round_tf32 = m->cfg.precision == SSR_PREC_TF32;
+  if (m->cfg.precision == SSR_PREC_FP32) return launch_gemm_simt(g, s);
+  return launch_gemm_tc(g, m->elem, s);
+}
+
+static GemmArgs gemm_base(const ssr_model* m, const Lin& L, const void* A, int lda, int B, int H, int W) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A;
+  g.lda = lda;
+  g.B = B;
+  g.H = H;
+  g.W = W;
+  g.M = B * H * W;
+  g.taps = L.taps;
+  g.KP = L.KP;
+  g.Wt = m->arena + L.w_off;
+  g.N = L.N;
+  g.NP = L.NP;
+  g.bias = m->dev<float>(L.b_off);
+  g.act = ACT_NONE;
+  g.slope = 0.01f;
+  g.alpha = 1.0f;
+  g.eps = 1e-5f;
+  g.ps_r = L.ps_r;
+  return g;
+}
+
+static void set_ln(const ssr_model* m, GemmArgs& g, const LNp& ln, void* out, int ld) {
+  g.out_ln = out;
+  g.ld_ln = ld;
+  g.gamma = m->dev<float>(ln.g_off);
+  g.beta = m->dev<float>(ln.b_off);
+}
+
+// pixel-shuffle tail shared by SwinIR ("pixelshuffle") and EDSR: cur [B,H,W,ch] -> conv_last
+struct InputSpec {
+  const void* in;
+  int in_u8;
+  int fh, fw;  // frame / image size
+  int tile_mode, tile, stride, tiles_x, tile_begin;
+};
+struct OutputSpec {
+  float* out_f32;
+  uint8_t* out_u8;
+};
+
+static int run_tail(ssr_model* m, const void* cur, int ch_ld, int B, int Hp, int Wp, void* hr0, void* hr1, int h, int w,
+                    const float* out_shift, float out_scale, const OutputSpec& out, cudaStream_t s) {
+  int H = Hp, W = Wp;
+  void* bufs[2] = {hr0, hr1};
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    const Lin& L = m->up[i];
+    GemmArgs g = gemm_base(m, L, cur, ch_ld, B, H, W);
+    g.out_T = bufs[i & 1];
+    g.ld_T = ch_ld;
+    SSR_TRY(run_gemm(m, g, s));
+    cur = bufs[i & 1];
+    H *= L.ps_r;
+    W *= L.ps_r;
+  }
+  ConvLastArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = cur;
+  a.ldi = ch_ld;
+  a.Cin = m->last_cin;
+  a.elem = m->elem;
+  a.B = B;
+  a.Hs = H;
+  a.Ws = W;
+  a.ch = h * m->cfg.scale;
+  a.cw = w * m->cfg.scale;
+  a.Wc = m->dev<float>(m->conv_last_w);
+  for (int i = 0; i < 3; ++i) {
+    a.bias[i] = m->conv_last_bias[i];
+    a.out_shift[i] = out_shift[i];
+  }
+  a.out_scale = out_scale;
+  a.out_f32 = out.out_f32;
+  a.out_u8 = out.out_u8;
+  a.u8_scale = m->cfg.img_range == 1.0f ? 255.0f : 1.0f;
+  return launch_conv_last(a, s);
+}
+
+static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, int pad_mode,
+                          void* ws, size_t ws_bytes, cudaStream_t s) {
+  const ssr_model_config& c = m->cfg;
+  int Hp, Wp;
+  padded_size(m, h, w, pad_mode, &Hp, &Wp);
+  if (pad_mode == SSR_PAD_TRAIN)
+    SSR_CHECK(Hp - h < h && Wp - w < w, SSR_E_INVALID, "reflect padding needs pad < size (%dx%d)", h, w);
+  SwinWs W;
+  const size_t need = plan_swinir(m, ws, B, Hp, Wp, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+  const int CP = m->CP, e = m->elem;
+  const int T = B * Hp * Wp;
+  const int rtf = c.precision == SSR_PREC_TF32;
+
+  {  // pad + normalise + conv_first (swinir.py:356-361)
+    ConvFirstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in.in;
+    a.in_u8 = in.in_u8;
+    a.fh = in.fh;
+    a.fw = in.fw;
+    a.tile_mode = in.tile_mode;
+    a.tile = in.tile;
+    a.stride = in.stride;
+    a.tiles_x = in.tiles_x;
+    a.tile_begin = in.tile_begin;
+    a.h = h;
+    a.w = w;
+    a.Hp = Hp;
+    a.Wp = Wp;
+    a.pad_mode = pad_mode;
+    a.B = B;
+    const float u8s = (in.in_u8 && c.img_range == 1.0f) ? 1.0f / 255.0f : 1.0f;
+    a.in_scale = u8s / c.img_range;
+    for (int i = 0; i < 3; ++i) a.in_shift[i] = -kRgbMean[i];
+    a.Wc = m->dev<float>(m->conv_first_w);
+    a.bias = m->dev<float>(m->conv_first_b);
+    a.Cout = m->C;
+    a.out_f32 = W.x0;
+    a.ld_f32 = CP;
+    a.elem = e;
+    SSR_TRY(launch_conv_first(a, s));
+  }
+  {  // patch_embed.norm -> g (residual stream), chained with layers.0.blocks.0.norm1 -> xn
+    LnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = W.x0;
+    a.ld_in = CP;
+    a.M = T;
+    a.C = m->C;
+    a.CP = CP;
+    a.g1 = m->dev<float>(m->pe_norm.g_off);
+    a.b1 = m->dev<float>(m->pe_norm.b_off);
+    a.out_f32 = W.g;
+    a.ld_f32 = CP;
+    const Block& b0 = m->layers[0].blocks[0];
+    a.g2 = m->dev<float>(b0.norm1.g_off);
+    a.b2 = m->dev<float>(b0.norm1.b_off);
+    a.out_T = W.xn;
+    a.ld_T = CP;
+    a.elem = e;
+    a.round_tf32 = rtf;
+    a.eps = 1e-5f;
+    SSR_TRY(launch_layernorm(a, s));
+  }
+  SSR_CUDA(cudaMemsetAsync(W.o, 0, (size_t)T * m->QPmax * e, s));
+  const int nL = (int)m->layers.size();
+  for (int li = 0; li < nL; ++li) {
+    const Layer& L = m->layers[li];
+    const int depth = (int)L.blocks.size();
+    for (int bi = 0; bi < depth; ++bi) {
+      const Block& blk = L.blocks[bi];
+      {  // qkv projection (swinir.py:80); q scale folded into the packed weights
+        GemmArgs g = gemm_base(m, blk.qkv, W.xn, CP, B, Hp, Wp);
+        g.out_T = W.qkv;
+        g.ld_T = 3 * L.QP;
+        SSR_TRY(run_gemm(m, g, s));
+      }
+      {  // roll + partition + attention + reverse + roll (swinir.py:154-168, 83-102)
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.qkv = W.qkv;
+        a.ld_qkv = 3 * L.QP;
+        a.QP = L.QP;
+        a.o = W.o;
+        a.ld_o = L.QP;
+        a.bias = m->dev<float>(blk.bias_off);
+        a.B = B;
+        a.H = Hp;
+        a.W = Wp;
+        a.ws = c.window_size;
+        a.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
+        a.heads = L.heads;
+        a.d = L.d;
+        a.DP = L.DP;
+        if (e == 2)
+          SSR_TRY(launch_attn_mma(a, s));
+        else
+          SSR_TRY(launch_attn_simt(a, s));
+      }
+      {  // proj + residual (swinir.py:103,171) with norm2 fused into the epilogue
+        GemmArgs g = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
+        g.res = bi == 0 ? W.g : W.t;
+        g.ldres = CP;
+        g.out_f32 = W.t;
+        g.ld_f32 = CP;
+        set_ln(m, g, blk.norm2, W.xn, CP);
+        SSR_TRY(run_gemm(m, g, s));
+      }
+      {  // fc1 + GELU (common.py:185-186)
+        GemmArgs g = gemm_base(m, blk.fc1, W.xn, CP, B, Hp, Wp);
+        g.act = ACT_GELU;
+        g.out_T = W.hbuf;
+        g.ld_T = m->HP;
+        SSR_TRY(run_gemm(m, g, s));
+      }
+      {  // fc2 + residual (swinir.py:172); epilogue = next block's norm1, or a T copy for the RSTB conv
+        GemmArgs g = gemm_base(m, blk.fc2, W.hbuf, m->HP, B, Hp, Wp);
+        g.res = W.t;
+        g.ldres = CP;
+        if (bi + 1 < depth) {
+          g.out_f32 = W.t;
+          g.ld_f32 = CP;
+          set_ln(m, g, L.blocks[bi + 1].norm1, W.xn, CP);
+        } else {
+          g.out_T = W.tb;
+          g.ld_T = CP;
+        }
+        SSR_TRY(run_gemm(m, g, s));
+      }
+    }
+    {  // RSTB conv + group residual (swinir.py:245-246); epilogue = next layer's first norm1 or the final norm
+      GemmArgs g = gemm_base(m, L.conv, W.tb, CP, B, Hp, Wp);
+      g.res = W.g;
+      g.ldres = CP;
+      if (li + 1 < nL) {
+        g.out_f32 = W.g;
+        g.ld_f32 = CP;
+        set_ln(m, g, m->layers[li + 1].blocks[0].norm1, W.xn, CP);
+      } else {
+        set_ln(m, g, m->final_norm, W.xn, CP);
+      }
+      SSR_TRY(run_gemm(m, g, s));
+    }
+  }
+  {  // conv_after_body + long skip (swinir.py:362)
+    GemmArgs g = gemm_base(m, m->conv_after_body, W.xn, CP, B, Hp, Wp);
+    g.res = W.x0;
+    g.ldres = CP;
+    g.out_T = W.tb;
+    g.ld_T = CP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  float shift[3] = {kRgbMean[0], kRgbMean[1], kRgbMean[2]};
+  if (c.upsampler == 0) {
+    GemmArgs g = gemm_base(m, m->conv_before_up, W.tb, CP, B, Hp, Wp);
+    g.act = ACT_LEAKY;
+    g.slope = 0.01f;
+    g.out_T = W.cbu;
+    g.ld_T = 64;
+    SSR_TRY(run_gemm(m, g, s));
+    return run_tail(m, W.cbu, 64, B, Hp, Wp, W.hr[0], W.hr[1], h, w, shift, c.img_range, out, s);
+  }
+  set_error("upsampler 'pixelshuffledirect' is not implemented yet");
+  return SSR_E_INVALID;
+}
+
+static int forward_edsr(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, void* ws,
+                        size_t ws_bytes, cudaStream_t s) {
+  const ssr_model_config& c = m->cfg;
+  EdsrWs W;
+  const size_t need = plan_edsr(m, ws, B, h, w, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+  const int FP = m->FP, e = m->elem;
+  {  // sub_mean + head (edsr.py:40-41)
+    ConvFirstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in.in;
+    a.in_u8 = in.in_u8;
+    a.fh = in.fh;
+    a.fw = in.fw;
+    a.tile_mode = in.tile_mode;
+    a.tile = in.tile;
+    a.stride = in.stride;
+    a.tiles_x = in.tiles_x;
+    a.tile_begin = in.tile_begin;
+    a.h = h;
+    a.w = w;
+    a.Hp = h;
+    a.Wp = w;
+    a.pad_mode = 2;
+    a.B = B;
+    a.in_scale = (in.in_u8 && c.img_range == 1.0f) ? 1.0f / 255.0f : 1.0f;
+    for (int i = 0; i < 3; ++i) a.in_shift[i] = m->sub_bias[i];
+    a.Wc = m->dev<float>(m->conv_first_w);
+    a.bias = m->dev<float>(m->conv_first_b);
+    a.Cout = m->F;
+    a.out_f32 = W.x;
+    a.ld_f32 = FP;
+    a.out_T = W.rb;
+    a.ld_T = FP;
+    a.elem = e;
+    a.round_tf32 = c.precision == SSR_PREC_TF32;
+    SSR_TRY(launch_conv_first(a, s));
+  }
+  for (int i = 0; i < c.n_resblocks; ++i) {  // ResBlock (common.py:150-153)
+    GemmArgs ga = gemm_base(m, m->res_a[i], W.rb, FP, B, h, w);
+    ga.act = ACT_RELU;
+    ga.out_T = W.tmp;
+    ga.ld_T = FP;
+    SSR_TRY(run_gemm(m, ga, s));
+    GemmArgs gb = gemm_base(m, m->res_b[i], W.tmp, FP, B, h, w);
+    gb.alpha = c.res_scale;
+    gb.res = i == 0 ? W.x : W.r;
+    gb.ldres = FP;
+    gb.out_f32 = W.r;
+    gb.ld_f32 = FP;
+    gb.out_T = W.rb;
+    gb.ld_T = FP;
+    SSR_TRY(run_gemm(m, gb, s));
+  }
+  {  // body tail conv + long skip (edsr.py:43-44)
+    GemmArgs g = gemm_base(m, m->body_tail, W.rb, FP, B, h, w);
+    g.res = W.x;
+    g.ldres = FP;
+    g.out_T = W.tmp;
+    g.ld_T = FP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  return run_tail(m, W.tmp, FP, B, h, w, W.hr[0], W.hr[1], h, w, m->add_bias, 1.0f, out, s);
+}
+
+static int check_ready(ssr_model* m) {
+  SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
+  SSR_CHECK(m->finalized, SSR_E_STATE, "model not finalised (call ssr_model_finalize)");
+  int dev = -1;
+  SSR_CUDA(cudaGetDevice(&dev));
+  if (dev != m->device) SSR_CUDA(cudaSetDevice(m->device));
+  return SSR_OK;
+}
+
+static int forward_any(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, int pad_mode,
+                       void* ws, size_t ws_bytes, cudaStream_t s) {
+  SSR_CHECK(B > 0 && h > 0 && w > 0, SSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, h, w);
+  if (m->cfg.arch == SSR_ARCH_SWINIR) return forward_swinir(m, in, out, B, h, w, pad_mode, ws, ws_bytes, s);
+  return forward_edsr(m, in, out, B, h, w, ws, ws_bytes, s);
+}
+
+static size_t workspace_any(const ssr_model* m, int B, int H, int W, int pad_mode) {
+  if (m->cfg.arch == SSR_ARCH_SWINIR) {
+    int Hp, Wp;
+    padded_size(m, H, W, pad_mode, &Hp, &Wp);
+    SwinWs w;
+    return plan_swinir(m, nullptr, B, Hp, Wp, &w);
+  }
+  EdsrWs w;
+  return plan_edsr(m, nullptr, B, H, W, &w);
+}
+
+static int num_tiles_1d(int L, int tile, int stride) {
+  if (L <= tile) return 1;
+  return (L - tile + stride - 1) / stride + 1;
+}
+
+}  // namespace ssr
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int ssr_version(void) { return SSR_VERSION; }
+const char* ssr_last_error(void) { return g_err; }
+int64_t ssr_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int ssr_device_check(int device) {
+  cudaDeviceProp p;
+  SSR_CUDA(cudaGetDeviceProperties(&p, device));
+  SSR_CHECK(p.major == 10, SSR_E_ARCH, "device %d is sm_%d%d; libssr_b200 needs sm_100 (B200) and has no fallback", device,
+            p.major, p.minor);
+  return SSR_OK;
+}
+
+int ssr_model_create(const ssr_model_config* cfg, int device, ssr_model_t** out) {
+  SSR_CHECK(cfg && out, SSR_E_INVALID, "null argument");
+  SSR_CHECK(cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_EDSR, SSR_E_INVALID, "unknown arch %d", cfg->arch);
+  SSR_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SSR_E_INVALID, "unknown precision %d", cfg->precision);
+  SSR_CHECK(cfg->scale >= 1 && cfg->scale <= 8, SSR_E_INVALID, "bad scale %d", cfg->scale);
+  if (cfg->arch == SSR_ARCH_SWINIR)
+    SSR_CHECK(cfg->n_layers > 0 && cfg->n_layers <= SSR_MAX_LAYERS, SSR_E_INVALID, "bad n_layers %d", cfg->n_layers);
+  SSR_TRY(ssr_device_check(device));
+  ssr_model* m = new ssr_model();
+  m->cfg = *cfg;
+  m->device = device;
+  m->elem = cfg->precision == SSR_PREC_BF16 ? 2 : 4;
+  *out = m;
+  return SSR_OK;
+}
+
+int ssr_model_set_param(ssr_model_t* m, const char* name, const float* host_data, int64_t numel) {
+  SSR_CHECK(m && name && host_data && numel > 0, SSR_E_INVALID, "bad argument to ssr_model_set_param");
+  m->params[name].assign(host_data, host_data + numel);
+  m->finalized = false;
+  return SSR_OK;
+}
+
+int ssr_model_finalize(ssr_model_t* m) {
+  SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
+  SSR_CUDA(cudaSetDevice(m->device));
+  m->host_arena.clear();
+  int r = m->cfg.arch == SSR_ARCH_SWINIR ? finalize_swinir(m) : finalize_edsr(m);
+  if (r != SSR_OK) return r;
+  if (m->arena && m->arena_bytes < m->host_arena.size()) {
+    cudaFree(m->arena);
+    m->arena = nullptr;
+  }
+  if (!m->arena) {
+    m->arena_bytes = m->host_arena.size();
+    SSR_CUDA(cudaMalloc(&m->arena, m->arena_bytes));
+  }
+  SSR_CUDA(cudaMemcpy(m->arena, m->host_arena.data(), m->host_arena.size(), cudaMemcpyHostToDevice));
+  m->host_arena.clear();
+  m->host_arena.shrink_to_fit();
+  m->finalized = true;
+  return SSR_OK;
+}
+
+void ssr_model_destroy(ssr_model_t* m) {
+  if (!m) return;
+  if (m->arena) cudaFree(m->arena);
+  delete m;
+}
+
+size_t ssr_model_workspace_bytes(const ssr_model_t* m, int B, int H, int W, int pad_mode) {
+  if (!m || !m->finalized) return 0;
+  return workspace_any(m, B, H, W, pad_mode);
+}
+
+int ssr_model_forward(ssr_model_t* m, const float* x, float* y, int B, int H, int W, int pad_mode, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  SSR_TRY(check_ready(m));
+  SSR_CHECK(x && y, SSR_E_INVALID, "null tensor");
+  InputSpec in{x, 0, H, W, 0, 0, 0, 0, 0};
+  OutputSpec out{y, nullptr};
+  return forward_any(m, in, out, B, H, W, pad_mode, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ssr_model_upscale_u8(ssr_model_t* m, const uint8_t* img, uint8_t* outp, int B, int H, int W, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  SSR_TRY(check_ready(m));
+  SSR_CHECK(img && outp, SSR_E_INVALID, "null tensor");
+  InputSpec in{img, 1, H, W, 0, 0, 0, 0, 0};
+  OutputSpec out{nullptr, outp};
+  return forward_any(m, in, out, B, H, W, SSR_PAD_EVAL, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ssr_tiled_num_tiles(int H, int W, int tile, int overlap) {
+  if (tile <= overlap || H <= 0 || W <= 0) return 0;
+  return num_tiles_1d(H, tile, tile - overlap) * num_tiles_1d(W, tile, tile - overlap);
+}
+
+static size_t tiled_layout(const ssr_model_t* m, int H, int W, int tile, int overlap, int chunk, size_t* tiles_off,
+                           size_t* dev_in_off, size_t* dev_out_off) {
+  const int th = tile < H ? tile : H, tw = tile < W ? tile : W;
+  const int nt = ssr_tiled_num_tiles(H, W, tile, overlap);
+  if (chunk <= 0 || chunk > nt) chunk = nt;
+  const int s = m->cfg.scale;
+  size_t off = (workspace_any(m, chunk, th, tw, SSR_PAD_EVAL) + 1023) & ~(size_t)1023;
+  *tiles_off = off;
+  off += ((size_t)nt * 3 * th * s * tw * s * 4 + 1023) & ~(size_t)1023;
+  *dev_in_off = off;
+  off += ((size_t)H * W * 3 + 1023) & ~(size_t)1023;
+  *dev_out_off = off;
+  off += ((size_t)H * s * W * s * 3 + 1023) & ~(size_t)1023;
+  return off;
+}
+
+size_t ssr_model_tiled_workspace_bytes(const ssr_model_t* m, int H, int W, int tile, int overlap, int chunk_tiles) {
+  if (!m || !m->finalized || tile <= overlap) return 0;
+  size_t a, b, c;
+  return tiled_layout(m, H, W, tile, overlap, chunk_tiles, &a, &b, &c);
+}
+
+int ssr_model_upscale_tiled_u8(ssr_model_t* m, const uint8_t* frame, uint8_t* outp, int H, int W, int tile, int overlap,
+                               int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream) {
+  SSR_TRY(check_ready(m));
+  SSR_CHECK(frame && outp && workspace, SSR_E_INVALID, "null buffer");
+  SSR_CHECK(tile > overlap && overlap >= 0, SSR_E_INVALID, "tile %d must exceed overlap %d", tile, overlap);
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t tiles_off, in_off, out_off;
+  const size_t need = tiled_layout(m, H, W, tile, overlap, chunk_tiles, &tiles_off, &in_off, &out_off);
+  SSR_CHECK(need <= workspace_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  const int th = tile < H ? tile : H, tw = tile < W ? tile : W, stride = tile - overlap;
+  const int tiles_x = num_tiles_1d(W, tile, stride), tiles_y = num_tiles_1d(H, tile, stride);
+  const int nt = tiles_x * tiles_y;
+  int chunk = chunk_tiles;
+  if (chunk <= 0 || chunk > nt) chunk = nt;
+  const int sc = m->cfg.scale;
+  float* tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + tiles_off);
+  for (int t0 = 0; t0 < nt; t0 += chunk) {
+    const int nb = nt - t0 < chunk ? nt - t0 : chunk;
+    InputSpec in{frame, 1, H, W, 1, tile, stride, tiles_x, t0};
+    OutputSpec out{tiles + (size_t)t0 * 3 * th * sc * tw * sc, nullptr};
+    SSR_TRY(forward_any(m, in, out, nb, th, tw, SSR_PAD_EVAL, workspace, tiles_off, s));
+  }
+  BlendArgs b;
+  b.tiles = tiles;
+  b.out = outp;
+  b.H = H;
+  b.W = W;
+  b.scale = sc;
+  b.tile = tile;
+  b.overlap = overlap;
+  b.tiles_x = tiles_x;
+  b.tiles_y = tiles_y;
+  b.u8_scale = m->cfg.img_range == 1.0f ? 255.0f : 1.0f;
+  return launch_blend(b, s);
+}
+
+int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, uint8_t* out_host, int H, int W, int tile,
+                                    int overlap, int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream) {
+  SSR_TRY(check_ready(m));
+  SSR_CHECK(frame_host && out_host && workspace, SSR_E_INVALID, "null buffer");
+  SSR_CHECK(tile > overlap && overlap >= 0, SSR_E_INVALID, "tile %d must exceed overlap %d", tile, overlap);
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t tiles_off, in_off, out_off;
+  const size_t need = tiled_layout(m, H, W, tile, overlap, chunk_tiles, &tiles_off, &in_off, &out_off);
+  SSR_CHECK(need <= workspace_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  uint8_t* din = reinterpret_cast<uint8_t*>(workspace) + in_off;
+  uint8_t* dout = reinterpret_cast<uint8_t*>(workspace) + out_off;
+  const int sc = m->cfg.scale;
+  SSR_CUDA(cudaMemcpyAsync(din, frame_host, (size_t)H * W * 3, cudaMemcpyHostToDevice, s));
+  SSR_TRY(ssr_model_upscale_tiled_u8(m, din, dout, H, W, tile, overlap, chunk_tiles, workspace, workspace_bytes, stream));
+  SSR_CUDA(cudaMemcpyAsync(out_host, dout, (size_t)H * sc * W * sc * 3, cudaMemcpyDeviceToHost, s));
+  SSR_CUDA(cudaStreamSynchronize(s));
+  return SSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// Op-level C ABI used by the parity tests: fp32 tensors in the reference's own layouts go in,
+// get packed into the padded device layouts on the fly, run through the SAME kernels the model
+// path launches, and come back as fp32.
+#include <math.h>
+#include <string.h>
+
+#include "ssr_device.cuh"
+
+namespace ssr {
+
+__global__ void pack_conv_w_kernel(const float* W, const float* b, void* Wt, float* bias, int Cout, int Cin, int NP,
+                                   int KP, int ps_r, int elem, int rtf32) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)NP * 9 * KP;
+  if (idx >= total) return;
+  const int k = (int)(idx % (9 * KP));
+  const int n = (int)(idx / (9 * KP));
+  const int tap = k / KP, c = k % KP;
+  float v = 0.0f;
+  int sn = -1;
+  if (n < Cout) {
+    sn = n;
+    if (ps_r > 1) {
+      const int rr = ps_r * ps_r, Cps = Cout / rr;
+      sn = (n % Cps) * rr + n / Cps;
+    }
+    if (c < Cin) v = W[((size_t)sn * Cin + c) * 9 + tap];
+  }
+  store_elem(Wt, (size_t)idx, elem, v, rtf32);
+  if (k == 0) bias[n] = sn >= 0 ? b[sn] : 0.0f;
+}
+
+__global__ void transpose_table_kernel(const float* in, float* out, int nb2, int heads) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nb2 * heads) return;
+  const int h = idx / nb2, i = idx % nb2;
+  out[idx] = in[i * heads + h];
+}
+
+struct Carve {
+  uint8_t* base;
+  size_t off = 0, cap;
+  Carve(void* p, size_t c) : base(reinterpret_cast<uint8_t*>(p)), cap(c) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base + off;
+    off += bytes;
+    return off <= cap ? p : nullptr;
+  }
+};
+
+static int dispatch_gemm(int precision, GemmArgs& g, int elem, cudaStream_t s) {
+  g.round_tf32 = precision == SSR_PREC_TF32;
+  if (precision == SSR_PREC_FP32) return launch_gemm_simt(g, s);
+  return launch_gemm_tc(g, elem, s);
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" {
+
+size_t ssr_op_workspace_bytes(int64_t max_elems) { return (size_t)max_elems * 4 * 8 + (1 << 20); }
+
+int ssr_op_linear(int precision, const float* x, const float* W, const float* b, const float* res, int act,
+                  const float* ln_w, const float* ln_b, float* y, float* y_ln, int M, int K, int N, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  SSR_CHECK(x && W && b && M > 0 && K > 0 && N > 0 && workspace, SSR_E_INVALID, "ssr_op_linear: bad argument");
+  SSR_CHECK(precision >= 0 && precision <= 2, SSR_E_INVALID, "bad precision");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int elem = precision == SSR_PREC_BF16 ? 2 : 4, rtf = precision == SSR_PREC_TF32;
+  const int KP = round_up(K, 64), NP = round_up(N, 64);
+  Carve c(workspace, workspace_bytes);
+  void* xp = c.take((size_t)M * KP * elem);
+  void* wp = c.take((size_t)NP * KP * elem);
+  float* bp = (float*)c.take((size_t)NP * 4);
+  float* rp = res ? (float*)c.take((size_t)M * NP * 4) : nullptr;
+  float* gp = ln_w ? (float*)c.take((size_t)NP * 4) : nullptr;
+  float* bep = ln_w ? (float*)c.take((size_t)NP * 4) : nullptr;
+  float* yp = (float*)c.take((size_t)M * NP * 4);
+  void* ylp = ln_w ? c.take((size_t)M * NP * elem) : nullptr;
+  SSR_CHECK(yp && (!ln_w || ylp), SSR_E_WORKSPACE, "ssr_op_linear: workspace too small (%zu B)", workspace_bytes);
+  SSR_TRY(launch_pack_rows(x, M, K, xp, KP, elem, rtf, s));
+  SSR_CUDA(cudaMemsetAsync(wp, 0, (size_t)NP * KP * elem, s));
+  SSR_TRY(launch_pack_rows(W, N, K, wp, KP, elem, rtf, s));
+  SSR_TRY(launch_pack_rows(b, 1, N, bp, NP, 4, 0, s));
+  if (res) SSR_TRY(launch_pack_rows(res, M, N, rp, NP, 4, 0, s));
+  if (ln_w) {
+    SSR_TRY(launch_pack_rows(ln_w, 1, N, gp, NP, 4, 0, s));
+    SSR_TRY(launch_pack_rows(ln_b, 1, N, bep, NP, 4, 0, s));
+  }
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = xp; g.lda = KP; g.M = M; g.B = M; g.H = 1; g.W = 1; g.taps = 1; g.KP = KP; g.Wt = wp; g.N = N; g.NP = NP;
+  g.bias = bp; g.act = act; g.slope = 0.01f; g.alpha = 1.0f; g.res = rp; g.ldres = NP; g.out_f32 = yp; g.ld_f32 = NP;
+  g.eps = 1e-5f;
+  if (ln_w) {
+    g.out_ln = ylp; g.ld_ln = NP; g.gamma = gp; g.beta = bep;
+  }
+  SSR_TRY(dispatch_gemm(precision, g, elem, s));
+  if (y) SSR_TRY(launch_unpack_rows(yp, NP, 4, y, M, N, s));
+  if (ln_w && y_ln) SSR_TRY(launch_unpack_rows(ylp, NP, elem, y_ln, M, N, s));
+  return SSR_OK;
+}
+
+int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b, const float* res, float* y, int B,
+                   int Cin, int Cout, int H, int Wd, int act, float alpha, int ps_r, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  SSR_CHECK(x && W && b && y && workspace, SSR_E_INVALID, "ssr_op_conv3x3: bad argument");
+  SSR_CHECK(precision >= 0 && precision <= 2, SSR_E_INVALID, "bad precision");
+  SSR_CHECK(!(res && ps_r > 1), SSR_E_INVALID, "residual and pixel-shuffle are exclusive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int elem = precision == SSR_PREC_BF16 ? 2 : 4, rtf = precision == SSR_PREC_TF32;
+  const int KP = round_up(Cin, 64), NP = round_up(Cout, 64);
+  const int r = ps_r > 1 ? ps_r : 1;
+  const int Cps = Cout / (r * r), ldo = ps_r > 1 ? round_up(Cps, 64) : NP;
+  const size_t M = (size_t)B * H * Wd;
+  Carve c(workspace, workspace_bytes);
+  void* xp = c.take(M * KP * elem);
+  void* wp = c.take((size_t)NP * 9 * KP * elem);
+  float* bp = (float*)c.take((size_t)NP * 4);
+  float* rp = res ? (float*)c.take(M * NP * 4) : nullptr;
+  void* yp = c.take(M * r * r * ldo * elem);
+  float* yf = res ? (float*)c.take(M * NP * 4) : nullptr;
+  SSR_CHECK(yp && (!res || yf), SSR_E_WORKSPACE, "ssr_op_conv3x3: workspace too small (%zu B)", workspace_bytes);
+  SSR_TRY(launch_nchw_to_nhwc(x, xp, B, Cin, H, Wd, KP, elem, rtf, s));
+  {
+    const long long total = (long long)NP * 9 * KP;
+    pack_conv_w_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(W, b, wp, bp, Cout, Cin, NP, KP, ps_r, elem, rtf);
+    count_launch();
+    SSR_CUDA(cudaGetLastError());
+  }
+  if (res) SSR_TRY(launch_nchw_to_nhwc(res, rp, B, Cout, H, Wd, NP, 4, 0, s));
+  if (ps_r > 1) SSR_CUDA(cudaMemsetAsync(yp, 0, M * r * r * ldo * elem, s));
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = xp; g.lda = KP; g.M = (int)M; g.B = B; g.H = H; g.W = Wd; g.taps = 9; g.KP = KP; g.Wt = wp; g.N = Cout;
+  g.NP = NP; g.bias = bp; g.act = act; g.slope = 0.01f; g.alpha = alpha; g.eps = 1e-5f; g.ps_r = ps_r;
+  if (res) {
+    g.res = rp; g.ldres = NP; g.out_f32 = yf; g.ld_f32 = NP;
+  } else {
+    g.out_T = yp; g.ld_T = ldo;
+  }
+  SSR_TRY(dispatch_gemm(precision, g, elem, s));
+  if (res) return launch_nhwc_to_nchw(yf, NP, 4, y, B, Cout, H, Wd, s);
+  return launch_nhwc_to_nchw(yp, ldo, elem, y, B, Cps, H * r, Wd * r, s);
+}
+
+int ssr_op_window_attention(int precision, const float* qkv, const float* bias_table, float* o, int B, int H, int W, int C,
+                            int heads, int ws, int shift, void* workspace, size_t workspace_bytes, void* stream) {
+  SSR_CHECK(qkv && bias_table && o && workspace, SSR_E_INVALID, "ssr_op_window_attention: bad argument");
+  SSR_CHECK(heads > 0 && C % heads == 0, SSR_E_INVALID, "C=%d not divisible by heads=%d", C, heads);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int elem = precision == SSR_PREC_BF16 ? 2 : 4, rtf = precision == SSR_PREC_TF32;
+  const int d = C / heads;
+  SSR_CHECK(d <= 32, SSR_E_INVALID, "head_dim %d > 32", d);
+  const int DP = d <= 16 ? 16 : 32, QP = round_up(heads * DP, 64);
+  const size_t M = (size_t)B * H * W;
+  const int nb2 = (2 * ws - 1) * (2 * ws - 1);
+  Carve c(workspace, workspace_bytes);
+  void* qp = c.take(M * 3 * QP * elem);
+  void* op = c.take(M * QP * elem);
+  float* tp = (float*)c.take((size_t)nb2 * heads * 4);
+  SSR_CHECK(tp, SSR_E_WORKSPACE, "ssr_op_window_attention: workspace too small (%zu B)", workspace_bytes);
+  // repack with head_dim padding: out [M][3][QP]
+  SSR_CUDA(cudaMemsetAsync(qp, 0, M * 3 * QP * elem, s));
+  SSR_CUDA(cudaMemsetAsync(op, 0, M * QP * elem, s));
+  SSR_TRY(launch_repack_qkv(qkv, qp, (int)M, C, heads, DP, QP, 1.0f / sqrtf((float)d), elem, rtf, s));
+  transpose_table_kernel<<<(nb2 * heads + 255) / 256, 256, 0, s>>>(bias_table, tp, nb2, heads);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = qp; a.ld_qkv = 3 * QP; a.QP = QP; a.o = op; a.ld_o = QP; a.bias = tp;
+  a.B = B; a.H = H; a.W = W; a.ws = ws; a.shift = shift; a.heads = heads; a.d = d; a.DP = DP;
+  if (elem == 2)
+    SSR_TRY(launch_attn_mma(a, s));
+  else
+    SSR_TRY(launch_attn_simt(a, s));
+  return launch_unpack_heads(op, QP, elem, o, (int)M, heads, d, DP, s);
+}
+
+}  // extern "C"

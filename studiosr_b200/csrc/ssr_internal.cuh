@@ -1,0 +1,169 @@
+// Internal declarations shared by the kernels and the host-side model executor.
+// Not part of the public ABI (see include/ssr_b200.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ssr_b200.h"
+
+namespace ssr {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SSR_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ssr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return SSR_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
+#define SSR_CHECK(cond, code, ...)   \
+  do {                               \
+    if (!(cond)) {                   \
+      ssr::set_error(__VA_ARGS__);   \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+#define SSR_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != SSR_OK) return _r; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_GELU = 3 };
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// One fused "implicit GEMM + epilogue" launch.  Rows are NHWC pixels / tokens.
+//   acc[m][n] = sum_{tap,c} A[pix(m)+tap][c] * Wt[n][tap*KP + c]
+//   v = act(acc + bias[n]) * alpha + res[m][n]
+//   out_f32[m][n] = v ; out_T[m][n] (or pixel-shuffled) = T(v) ; out_ln[m][n] = T(LN(v)*gamma+beta)
+struct GemmArgs {
+  const void* A;  // T [B*H*W][lda]
+  int lda;
+  int M;  // B*H*W
+  int B, H, W;
+  int taps;        // 1 (linear) or 9 (3x3 conv, zero pad 1)
+  int KP;          // padded input channels (multiple of 64)
+  const void* Wt;  // T [NP][taps*KP]
+  int N, NP;       // real / padded output channels (NP multiple of 64; pads are zero)
+  const float* bias;  // [NP]
+  int act;
+  float slope;
+  float alpha;
+  const float* res;  // fp32 [M][ldres] or null
+  int ldres;
+  float* out_f32;  // or null
+  int ld_f32;
+  void* out_T;  // or null
+  int ld_T;
+  int ps_r;      // PixelShuffle factor folded into the out_T store (0/1 = none); N = r*r*Cps
+  void* out_ln;  // or null
+  int ld_ln;
+  const float* gamma;  // [NP] (pads zero)
+  const float* beta;
+  float eps;
+  int round_tf32;  // round T=float stores to tf32 (rna) so the next tf32 MMA sees exact operands
+};
+
+struct AttnArgs {
+  const void* qkv;  // T [B*H*W][ld_qkv]; q | k | v, each [heads][DP] (q pre-scaled)
+  int ld_qkv;
+  int QP;   // heads*DP
+  void* o;  // T [B*H*W][ld_o], channel = head*DP + j
+  int ld_o;
+  const float* bias;  // [heads][(2ws-1)^2]
+  int B, H, W, ws, shift, heads, d, DP;
+};
+
+struct LnArgs {
+  const float* in;  // [M][ld_in]
+  int ld_in;
+  int M, C, CP;
+  const float *g1, *b1;  // first LN
+  float* out_f32;        // LN1 result (or null)
+  int ld_f32;
+  const float *g2, *b2;  // optional second LN applied to the first one's output (or null)
+  void* out_T;           // T(LN2(LN1(x))) or T(LN1(x)) if g2 null (or null)
+  int ld_T;
+  int elem;  // sizeof(T): 2 or 4
+  int round_tf32;
+  float eps;
+};
+
+// first conv (n_colors -> Cout) fused with: uint8/float input, tile addressing into a frame,
+// mirror padding (eval / train flavour) and the input affine (normalisation / MeanShift).
+struct ConvFirstArgs {
+  const void* in;  // float NCHW [Bimg,3,fh,fw]  or uint8 HWC [Bimg,fh,fw,3]
+  int in_u8;
+  int fh, fw;  // source image / frame size
+  // tile mode: batch item b is the th x tw crop at (ty0[b], tx0[b]) of image 0; otherwise the whole image b
+  int tile_mode, tile, stride, tiles_x, tile_begin;
+  int h, w;    // logical (un-padded) input size per batch item
+  int Hp, Wp;  // padded size
+  int pad_mode;  // 0 eval (edge-inclusive mirror), 1 train (reflect), 2 none
+  int B;
+  float in_scale;
+  float in_shift[3];
+  const float* Wc;    // [Cout][27] (ci,ky,kx)
+  const float* bias;  // [Cout]
+  int Cout;
+  float* out_f32;  // [B*Hp*Wp][ld_f32] or null
+  int ld_f32;
+  void* out_T;
+  int ld_T;
+  int elem;
+  int round_tf32;
+};
+
+// last conv (Cin -> 3) fused with bias, output affine (un-normalise / MeanShift), crop and either
+// fp32 NCHW store or uint8 HWC quantisation (round-half-even, clip).
+struct ConvLastArgs {
+  const void* in;  // T [B][Hs][Ws][ldi]
+  int ldi, Cin, elem;
+  int B, Hs, Ws;  // input (padded, upscaled) size
+  int ch, cw;     // cropped output size
+  const float* Wc;  // [9][Cin][4] (tap, ci, co padded to 4)
+  float bias[3];
+  float out_shift[3];
+  float out_scale;
+  float* out_f32;  // NCHW [B,3,ch,cw] or null
+  uint8_t* out_u8;  // HWC [B,ch,cw,3] or null
+  float u8_scale;
+};
+
+struct BlendArgs {
+  const float* tiles;  // [nt][3][ts][ts] fp32 (ts = tile*scale)
+  uint8_t* out;        // [H*s][W*s][3]
+  int H, W, scale, tile, overlap, tiles_x, tiles_y;
+  float u8_scale;
+};
+
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
+int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s);
+int launch_attn_simt(const AttnArgs& a, cudaStream_t s);
+int launch_attn_mma(const AttnArgs& a, cudaStream_t s);
+int launch_layernorm(const LnArgs& a, cudaStream_t s);
+int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s);
+int launch_conv_last(const ConvLastArgs& a, cudaStream_t s);
+int launch_blend(const BlendArgs& a, cudaStream_t s);
+// fp32 [rows][cols] -> T [rows][ld] (zero pad), optional per-row-block scale; used by op-level tests
+int launch_pack_rows(const float* in, int rows, int cols, void* out, int ld, int elem, int round_tf32, cudaStream_t s);
+int launch_unpack_rows(const void* in, int ld, int elem, float* out, int rows, int cols, cudaStream_t s);
+int launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
+int launch_repack_qkv(const float* qkv, void* out, int M, int C, int heads, int DP, int QP, float qscale, int elem,
+                      int round_tf32, cudaStream_t s);
+int launch_unpack_heads(const void* o, int ld, int elem, float* out, int M, int heads, int d, int DP, cudaStream_t s);
+int launch_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int ld, int elem, int round_tf32,
+                        cudaStream_t s);
+int launch_nhwc_to_nchw(const void* in, int ld, int elem, float* out, int B, int C, int H, int W, cudaStream_t s);
+
+}  // namespace ssr

@@ -1,0 +1,215 @@
+"""Host-side mirror of studiosr/models/common.py: the `Model` base class keeps the reference's
+public surface (inference, inference_with_self_ensemble, get_model_config, get_training_config,
+from_pretrained, export; common.py:29-98) while every forward is executed by libssr_b200."""
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..native import NativeModel
+
+# precision of the fp32 (non-autocast) forward: "fp32" = CUDA-core FMA, "tf32" = tcgen05 kind::tf32
+DEFAULT_FP32_MODE = os.environ.get("STUDIOSR_B200_FP32_MODE", "fp32")
+
+
+def diverge_images(image: torch.Tensor) -> List[torch.Tensor]:
+    """The 8 rot90 / fliplr variants of an HWC image, in the order of common.py:10-16."""
+    out = []
+    for k in range(4):
+        r = torch.rot90(image, k=k, dims=[0, 1])
+        out += [r, torch.fliplr(r)]
+    return out
+
+
+def converge_images(images: List[torch.Tensor]) -> torch.Tensor:
+    """Inverse of diverge_images followed by the mean (common.py:19-26)."""
+    back = []
+    for i, im in enumerate(images):
+        if i & 1:
+            im = torch.fliplr(im)
+        back.append(torch.rot90(im, k=i // 2, dims=[1, 0]))
+    return torch.mean(torch.stack(back), dim=0)
+
+
+class _NativeForward(torch.autograd.Function):
+    """Forward through libssr_b200; backward is not part of this round and fails loudly."""
+
+    @staticmethod
+    def forward(ctx, x, model, precision, pad_mode, *params):
+        return model._native(x.device, precision).forward(x, model.scale, pad_mode)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError(
+            "studiosr_b200: the sm_100a backward kernels are not built yet (forward/inference only in this round)")
+
+
+class Model(nn.Module):
+    ARCH = -1
+
+    def __init__(self, scale: int = 4, n_colors: int = 3, img_range: float = 1.0) -> None:
+        super().__init__()
+        self.scale: int = scale
+        self.n_colors: int = n_colors
+        self.img_range: float = img_range
+        self.precision: Optional[str] = None  # None = auto: bf16 under bf16 autocast, else DEFAULT_FP32_MODE
+        self._natives: Dict = {}
+
+    # ---- native plumbing ------------------------------------------------------------------
+    def _native_config(self, precision: int) -> "_lib.ModelConfig":
+        raise NotImplementedError
+
+    def _param_version(self):
+        return tuple((id(t), t._version) for t in self.state_dict(keep_vars=True).values() if t.is_floating_point())
+
+    def _native(self, device, precision: str) -> NativeModel:
+        device = torch.device(device)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), precision)
+        nat = self._natives.get(key)
+        if nat is None:
+            nat = NativeModel(self._native_config(_lib.PRECISIONS[precision]), device)
+            self._natives[key] = nat
+        ver = self._param_version()
+        if nat.version != ver:
+            nat.load_state(self.state_dict(keep_vars=True), ver)
+        return nat
+
+    def _resolve_precision(self, x: torch.Tensor) -> str:
+        if self.precision is not None:
+            return self.precision
+        if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return "bf16"
+        return DEFAULT_FP32_MODE
+
+    def _pad_mode(self) -> int:
+        return _lib.PAD_TRAIN if self.training else _lib.PAD_EVAL
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError(
+                f"{type(self).__name__}: studiosr_b200 executes on a CUDA sm_100 (B200) device only; "
+                "there is no CPU / PyTorch fallback path")
+        assert x.dim() == 4 and x.shape[1] == self.n_colors, "expected [B, n_colors, H, W]"
+        precision = self._resolve_precision(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            params = [p for p in self.parameters() if p.requires_grad]
+            return _NativeForward.apply(x, self, precision, self._pad_mode(), *params)
+        return self._native(x.device, precision).forward(x, self.scale, self._pad_mode())
+
+    def _device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    # ---- reference API (common.py:36-98) -----------------------------------------------------
+    @torch.inference_mode()
+    def inference(self, image: np.ndarray) -> np.ndarray:
+        """uint8 HWC -> uint8 HWC (common.py:36-48).  /255, forward, *255, round, clip and the uint8
+        cast are fused into the first / last kernels; only the uint8 image crosses PCIe."""
+        self.eval()
+        dev = self._device()
+        img = torch.from_numpy(np.ascontiguousarray(image)).to(dev)
+        precision = self.precision or DEFAULT_FP32_MODE
+        out = self._native(dev, precision).upscale_u8(img.unsqueeze(0), self.scale)[0]
+        return out.cpu().numpy()
+
+    @torch.inference_mode()
+    def inference_with_self_ensemble(self, image: np.ndarray) -> np.ndarray:
+        """8-way rot/flip self-ensemble (common.py:50-67)."""
+        self.eval()
+        dev = self._device()
+        scale = 255.0 if self.img_range == 1.0 else 1.0
+        img = torch.from_numpy(image.astype(np.float32) / scale).to(dev)
+        outs = []
+        for im in diverge_images(img):
+            x = im.permute(2, 0, 1).unsqueeze(0).contiguous()
+            outs.append(self.forward(x)[0].permute(1, 2, 0))
+        out = converge_images(outs) * scale
+        return out.round().clip(0, 255).to(torch.uint8).cpu().numpy()
+
+    @torch.inference_mode()
+    def inference_tiled(self, image: np.ndarray, tile: int = 64, overlap: int = 16, precision: Optional[str] = None,
+                        out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Full-frame tiled inference (BASELINE.json config 5; the reference has no tiler): host uint8
+        HWC -> host uint8 HWC through ONE C-ABI call (H2D, batched tiles, blend, D2H)."""
+        self.eval()
+        dev = self._device()
+        H, W, _ = image.shape
+        if out is None:
+            out = np.empty((H * self.scale, W * self.scale, 3), dtype=np.uint8)
+        nat = self._native(dev, precision or self.precision or DEFAULT_FP32_MODE)
+        return nat.upscale_tiled_u8_host(np.ascontiguousarray(image), out, self.scale, tile, overlap)
+
+    def get_model_config(self) -> Dict:
+        return dict(scale=self.scale, n_colors=self.n_colors, img_range=self.img_range)
+
+    def get_training_config(self) -> Dict:
+        return dict()
+
+    @classmethod
+    def from_pretrained(cls, scale: int = 4) -> "Model":
+        return cls(scale=scale)
+
+    def export(self, path: Optional[str] = None, input_shape: List[int] = [1, 3, 256, 256], format: str = "onnx") -> str:
+        raise NotImplementedError("ONNX export of the native path is out of scope (SURVEY.md §2, common.py:84-98)")
+
+
+BaseModule = Model
+
+
+def conv2d(in_channels: int, out_channels: int, kernel_size: int) -> nn.Module:
+    return nn.Conv2d(in_channels, out_channels, kernel_size, padding=kernel_size // 2)
+
+
+RGB_MEAN = (0.4488, 0.4371, 0.4040)
+
+
+class MeanShift(nn.Conv2d):
+    """Frozen 1x1 conv holding +-img_range*mean (common.py:108-121); executed as a fused affine."""
+
+    def __init__(self, img_range: float, rgb_mean=RGB_MEAN, rgb_std=(1.0, 1.0, 1.0), sign: int = -1) -> None:
+        super().__init__(3, 3, kernel_size=1)
+        std = torch.tensor(rgb_std, dtype=torch.float32)
+        self.weight.data = torch.eye(3).view(3, 3, 1, 1) / std.view(3, 1, 1, 1)
+        self.bias.data = sign * img_range * torch.tensor(rgb_mean, dtype=torch.float32) / std
+        for p in self.parameters():
+            p.requires_grad = False
+
+
+def upsampler_stages(scale: int, n_feats: int, num_out_ch: Optional[int] = None):
+    """[(cout, r)] of the conv + PixelShuffle stages of common.py:124-137."""
+    if num_out_ch is not None:
+        return [(scale * scale * num_out_ch, scale)]
+    if scale & (scale - 1) == 0:
+        out, s = [], scale
+        while s > 1:
+            out.append((4 * n_feats, 2))
+            s //= 2
+        return out
+    return [(scale * scale * n_feats, scale)]
+
+
+class Upsampler(nn.Sequential):
+    """Parameter container with the reference's Sequential indices (conv at 0, 2, ...)."""
+
+    def __init__(self, scale: int, n_feats: int, num_out_ch: Optional[int] = None) -> None:
+        mods = []
+        cin = n_feats
+        for cout, r in upsampler_stages(scale, n_feats, num_out_ch):
+            mods += [conv2d(cin, cout, 3), nn.PixelShuffle(r)]
+        super().__init__(*mods)
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features: int, hidden_features: int) -> None:
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.fc2 = nn.Linear(hidden_features, in_features)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, n_feats: int, kernel_size: int, res_scale: float = 1.0) -> None:
+        super().__init__()
+        self.body = nn.Sequential(conv2d(n_feats, n_feats, kernel_size), nn.ReLU(True), conv2d(n_feats, n_feats, kernel_size))
+        self.res_scale = res_scale

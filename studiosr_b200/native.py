@@ -1,0 +1,104 @@
+"""Host-side glue between the drop-in nn.Modules and the C ABI: per-(device, precision) native
+handles, weight (re)packing keyed on parameter versions, and grow-only workspaces.  PyTorch is
+used only for device memory and streams here."""
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class NativeModel:
+    """One packed copy of a module's weights inside libssr_b200 (for one device and precision)."""
+
+    def __init__(self, cfg: "_lib.ModelConfig", device: torch.device):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("studiosr_b200 runs on CUDA sm_100 devices only (no CPU fallback)")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.index = idx
+        self.handle = _lib.c_void_p()
+        _lib.check(self.lib.ssr_model_create(_lib.ctypes.byref(cfg), idx, _lib.ctypes.byref(self.handle)))
+        self.version = None
+        self._ws: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.ssr_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- weights ------------------------------------------------------------------------------
+    def load_state(self, state: Dict[str, torch.Tensor], version) -> None:
+        with torch.cuda.device(self.index):
+            for name, t in state.items():
+                if not t.is_floating_point():
+                    continue  # integer buffers (relative_position_index) are derived natively
+                h = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                _lib.check(self.lib.ssr_model_set_param(self.handle, name.encode(), h.data_ptr(), h.numel()))
+            _lib.check(self.lib.ssr_model_finalize(self.handle))
+        self.version = version
+
+    # -- workspace ----------------------------------------------------------------------------
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # -- entry points -------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, scale: int, pad_mode: int) -> torch.Tensor:
+        B, C, H, W = x.shape
+        x = x.detach().to(torch.float32).contiguous()
+        y = torch.empty((B, C, H * scale, W * scale), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.index):
+            need = self.lib.ssr_model_workspace_bytes(self.handle, B, H, W, pad_mode)
+            ws = self.workspace(need)
+            _lib.check(self.lib.ssr_model_forward(self.handle, x.data_ptr(), y.data_ptr(), B, H, W, pad_mode,
+                                                  ws.data_ptr(), ws.numel(), _stream_ptr(x.device)))
+        return y
+
+    def upscale_u8(self, img: torch.Tensor, scale: int) -> torch.Tensor:
+        """img: uint8 [B,H,W,3] on the device -> uint8 [B,sH,sW,3]."""
+        B, H, W, _ = img.shape
+        out = torch.empty((B, H * scale, W * scale, 3), dtype=torch.uint8, device=img.device)
+        with torch.cuda.device(self.index):
+            need = self.lib.ssr_model_workspace_bytes(self.handle, B, H, W, _lib.PAD_EVAL)
+            ws = self.workspace(need)
+            _lib.check(self.lib.ssr_model_upscale_u8(self.handle, img.data_ptr(), out.data_ptr(), B, H, W,
+                                                     ws.data_ptr(), ws.numel(), _stream_ptr(img.device)))
+        return out
+
+    def upscale_tiled_u8(self, frame: torch.Tensor, scale: int, tile: int, overlap: int, chunk: int = 0) -> torch.Tensor:
+        """frame: uint8 [H,W,3] on the device -> uint8 [sH,sW,3] (tiles batched, blended on device)."""
+        H, W, _ = frame.shape
+        out = torch.empty((H * scale, W * scale, 3), dtype=torch.uint8, device=frame.device)
+        with torch.cuda.device(self.index):
+            need = self.lib.ssr_model_tiled_workspace_bytes(self.handle, H, W, tile, overlap, chunk)
+            ws = self.workspace(need)
+            _lib.check(self.lib.ssr_model_upscale_tiled_u8(self.handle, frame.data_ptr(), out.data_ptr(), H, W, tile,
+                                                           overlap, chunk, ws.data_ptr(), ws.numel(),
+                                                           _stream_ptr(frame.device)))
+        return out
+
+    def upscale_tiled_u8_host(self, frame: np.ndarray, out: np.ndarray, scale: int, tile: int, overlap: int,
+                              chunk: int = 0) -> np.ndarray:
+        """HOST uint8 [H,W,3] -> HOST uint8 [sH,sW,3]; H2D + compute + D2H + sync inside the call."""
+        H, W, _ = frame.shape
+        assert frame.dtype == np.uint8 and frame.flags["C_CONTIGUOUS"]
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.shape == (H * scale, W * scale, 3)
+        with torch.cuda.device(self.index):
+            need = self.lib.ssr_model_tiled_workspace_bytes(self.handle, H, W, tile, overlap, chunk)
+            ws = self.workspace(need)
+            _lib.check(self.lib.ssr_model_upscale_tiled_u8_host(
+                self.handle, frame.ctypes.data, out.ctypes.data, H, W, tile, overlap, chunk, ws.data_ptr(), ws.numel(),
+                _stream_ptr(self.device)))
+        return out

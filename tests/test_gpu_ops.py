@@ -1,0 +1,114 @@
+"""-m gpu: op-level parity of the CUDA kernels (through the C ABI) against the oracle restatement
+on the same seeded inputs.  Tolerances: fp32 CUDA-core path ~1e-5 (summation order only);
+tf32 / bf16 tensor-core paths are judged relative to the output scale."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sr_oracle as O
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+PRECS = ["fp32", "tf32", "bf16"]
+# max-abs error allowed relative to the reference output's RMS
+REL_TOL = {"fp32": 2e-5, "tf32": 2e-3, "bf16": 2.5e-2}
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _close(y, ref, prec, what):
+    scale = ref.pow(2).mean().sqrt().item() + 1e-6
+    err = (y.cpu() - ref).abs().max().item()
+    assert math.isfinite(err) and err <= REL_TOL[prec] * scale * 4, f"{what} [{prec}]: max err {err:.3e} vs rms {scale:.3e}"
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("M,K,N,act,use_res,use_ln", [
+    (5184, 180, 540, 0, False, False),   # qkv at cfg1 size
+    (5184, 180, 180, 0, True, True),     # proj + residual + LN epilogue
+    (1000, 180, 360, 3, False, False),   # fc1 + GELU, ragged M
+    (777, 360, 180, 0, True, True),      # fc2 + residual + LN, ragged M
+    (130, 60, 120, 3, False, False),     # tiny config
+    (64, 120, 60, 0, True, True),
+    (1, 180, 180, 0, False, False),      # single row
+])
+def test_linear(prec, M, K, N, act, use_res, use_ln):
+    g = _gen(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K**0.5
+    b = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g) if use_res else None
+    lw = 1 + 0.1 * torch.randn(N, generator=g) if use_ln else None
+    lb = 0.1 * torch.randn(N, generator=g) if use_ln else None
+    v = x @ W.t() + b
+    if act == 3:
+        v = O.gelu(v)
+    if use_res:
+        v = v + res
+    c = lambda t: None if t is None else t.cuda()
+    y, y_ln = G.op_linear(prec, c(x), c(W), c(b), c(res), act, c(lw), c(lb))
+    _close(y, v, prec, "linear")
+    if use_ln:
+        _close(y_ln, O.layer_norm(v, lw, lb), prec, "linear+LN")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,Cin,Cout,H,W,act,ps_r,use_res", [
+    (1, 180, 180, 72, 72, 0, 0, True),    # RSTB conv at cfg1 size + residual
+    (2, 180, 64, 24, 40, 2, 0, False),    # conv_before_upsample + LeakyReLU
+    (2, 64, 256, 16, 24, 0, 2, False),    # upsample conv + PixelShuffle(2)
+    (1, 64, 576, 9, 13, 0, 3, False),     # x3 upsampler, ragged size
+    (3, 60, 60, 8, 8, 1, 0, True),        # tiny config, ReLU
+    (1, 256, 256, 12, 20, 1, 0, False),   # EDSR body conv
+])
+def test_conv3x3(prec, B, Cin, Cout, H, W, act, ps_r, use_res):
+    g = _gen(B + Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    Wt = torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(B, Cout, H, W, generator=g) if use_res else None
+    alpha = 0.1 if use_res else 1.0
+    v = F.conv2d(x, Wt, b, padding=1)
+    if act == 1:
+        v = torch.relu(v)
+    elif act == 2:
+        v = F.leaky_relu(v, 0.01)
+    v = v * alpha
+    if use_res:
+        v = v + res
+    if ps_r > 1:
+        v = O.pixel_shuffle(v, ps_r)
+    y = G.op_conv3x3(prec, x.cuda(), Wt.cuda(), b.cuda(), None if res is None else res.cuda(), act, alpha, ps_r)
+    assert y.shape == v.shape
+    _close(y, v, prec, "conv3x3")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,H,W,C,heads,shift", [
+    (1, 72, 72, 180, 6, 0), (1, 72, 72, 180, 6, 4), (2, 16, 24, 180, 6, 4), (3, 8, 8, 64, 4, 4), (2, 24, 16, 60, 6, 4),
+])
+def test_window_attention(prec, B, H, W, C, heads, shift):
+    ws, d = 8, C // heads
+    g = _gen(B + H + W + C + shift)
+    qkv = torch.randn(B, H, W, 3 * C, generator=g)
+    table = torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5
+    # oracle: roll -> windows -> attention core -> reverse -> roll (no linear layers)
+    q = torch.roll(qkv, (-shift, -shift), (1, 2)) if shift else qkv
+    qw = O.to_windows(q, ws).reshape(-1, ws * ws, 3, heads, d)
+    Q = qw[:, :, 0].transpose(1, 2) * d**-0.5
+    K = qw[:, :, 1].transpose(1, 2)
+    V = qw[:, :, 2].transpose(1, 2)
+    s = Q @ K.transpose(-1, -2) + O.rel_pos_bias(table, ws)[None]
+    mask = O.shift_mask(H, W, ws, shift, torch.float32)
+    nW = mask.shape[0]
+    s = (s.reshape(B, nW, heads, 64, 64) + mask[None, :, None]).reshape(-1, heads, 64, 64)
+    o = (torch.softmax(s, -1) @ V).transpose(1, 2).reshape(-1, 64, C)
+    o = O.from_windows(o, ws, B, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    y = G.op_window_attention(prec, qkv.cuda(), table.cuda(), heads, ws, shift)
+    _close(y, o, prec, "window attention")
