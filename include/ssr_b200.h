@@ -129,6 +129,12 @@ int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, u
 
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 int64_t ssr_launch_count(void);
+/* Per-launch device timing for the roofline report: between begin and end every kernel launch is
+ * bracketed by CUDA events on its own stream.  ssr_profile_end synchronises the device and writes a
+ * JSON object {"<kernel class>": {"launches", "ms", "flops", "bytes"}} (algorithmic FLOPs / bytes
+ * with un-padded dimensions) into `json`.  Not for use inside timed regions. */
+int ssr_profile_begin(void);
+int ssr_profile_end(char* json, size_t capacity);
 
 /* ---- op-level entry points (used by the parity tests; same kernels the model path runs) -----
  * All tensors DEVICE fp32 in the reference's own layouts; the library packs / pads internally

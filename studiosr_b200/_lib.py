@@ -46,6 +46,8 @@ SYMBOLS = {
     "ssr_model_upscale_tiled_u8_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                                 c_void_p, c_size_t, c_void_p]),
     "ssr_launch_count": (c_int64, []),
+    "ssr_profile_begin": (c_int, []),
+    "ssr_profile_end": (c_int, [c_char_p, c_size_t]),
     "ssr_op_linear": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ssr_op_conv3x3": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -192,6 +192,8 @@ int launch_attn_mma(const AttnArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)AM_N * (a.ld_qkv * 2 + 16) + (size_t)a.heads * 225 * 4 + 2 * AM_N * 4;
   SSR_CHECK(smem <= 200 * 1024, SSR_E_INVALID, "attn_mma: window tile needs %zu B of shared memory", smem);
   const int nwin = a.B * (a.H / 8) * (a.W / 8);
+  // algorithmic work: QK^T and PV, 2*64*64*d MACs... = 4*64*64*d FLOP per (window, head); q,k,v read + o written
+  ProfScope prof("attn_mma", 4.0 * nwin * 64 * 64 * a.d * a.heads, 4.0 * nwin * 64 * a.heads * a.d * 2, s);
   static size_t attr16 = 0, attr32 = 0;
   if (a.DP == 32) {
     if (smem > attr32) {

@@ -519,6 +519,7 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(grid_x, g.NP / BLOCK_N);
+  ProfScope prof(g.taps == 9 ? "gemm_tc_conv3x3" : "gemm_tc_linear", gemm_alg_flops(g), gemm_alg_bytes(g, elem), s);
   gemm_tc_kernel<T, BLOCK_N><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
   count_launch();
   SSR_CUDA(cudaGetLastError());

@@ -158,6 +158,7 @@ static int launch_gemm_simt_bn(const GemmArgs& g, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid((g.M + SG_BM - 1) / SG_BM, g.NP / BN);
+  ProfScope prof(g.taps == 9 ? "gemm_fp32_conv3x3" : "gemm_fp32_linear", gemm_alg_flops(g), gemm_alg_bytes(g, 4), s);
   gemm_simt_kernel<BN><<<grid, 256, smem, s>>>(g);
   count_launch();
   SSR_CUDA(cudaGetLastError());
@@ -279,6 +280,7 @@ int launch_attn_simt(const AttnArgs& a, cudaStream_t s) {
     attr = smem;
   }
   const int nwin = a.B * (a.H / a.ws) * (a.W / a.ws);
+  ProfScope prof("attn_fp32", 4.0 * nwin * N * N * a.d * a.heads, 4.0 * nwin * N * a.heads * a.d * 4, s);
   attn_simt_kernel<<<nwin, 256, smem, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
@@ -341,6 +343,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
 int launch_layernorm(const LnArgs& a, cudaStream_t s) {
   SSR_CHECK(a.CP <= 256, SSR_E_INVALID, "layernorm: C padded %d > 256", a.CP);
   const int blocks = (a.M + 7) / 8;
+  ProfScope prof("layernorm", 0.0, (double)a.M * a.C * (4 + (a.out_f32 ? 4 : 0) + (a.out_T ? a.elem : 0)), s);
   layernorm_kernel<<<blocks, 256, 0, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
@@ -422,6 +425,8 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstArgs a) 
 int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s) {
   SSR_CHECK(a.Cout <= 256 && a.ld_f32 <= 256 && a.ld_T <= 256, SSR_E_INVALID, "conv_first: Cout=%d > 256", a.Cout);
   const int M = a.B * a.Hp * a.Wp;
+  ProfScope prof("conv_first", 2.0 * M * 27 * a.Cout,
+                 (double)M * (3 * (a.in_u8 ? 1 : 4) + a.Cout * ((a.out_f32 ? 4 : 0) + (a.out_T ? a.elem : 0))), s);
   conv_first_kernel<<<(M + CF_PIX - 1) / CF_PIX, 256, 0, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
@@ -494,6 +499,8 @@ int launch_conv_last(const ConvLastArgs& a, cudaStream_t s) {
   const long long total = (long long)a.B * a.ch * a.cw;
   const int blocks = (int)((total + 127) / 128);
   const size_t smem = (size_t)9 * a.Cin * 4 * sizeof(float);
+  ProfScope prof("conv_last", 2.0 * total * 9 * a.Cin * 3,
+                 (double)a.B * a.Hs * a.Ws * a.Cin * a.elem + (double)total * 3 * (a.out_f32 ? 4 : 1), s);
   if (a.elem == 2)
     conv_last_kernel<__nv_bfloat16><<<blocks, 128, smem, s>>>(a);
   else
@@ -554,6 +561,7 @@ __global__ void __launch_bounds__(256) blend_kernel(const BlendArgs a) {
 
 int launch_blend(const BlendArgs& a, cudaStream_t s) {
   const long long total = (long long)a.W * a.scale * a.H * a.scale;
+  ProfScope prof("blend", 0.0, (double)total * 3 + (double)a.tiles_x * a.tiles_y * 3 * 4 * a.tile * a.tile * a.scale * a.scale, s);
   blend_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());

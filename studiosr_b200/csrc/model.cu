@@ -26,6 +26,40 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- profiling -------------------------------------------------------------------------------
+struct ProfRec {
+  const char* cls;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec*> g_prof;
+
+ProfScope::ProfScope(const char* cls, double flops, double bytes, cudaStream_t s) : stream(s) {
+  if (!g_prof_on) return;
+  ProfRec* r = new ProfRec{cls, flops, bytes, nullptr, nullptr};
+  cudaEventCreate(&r->e0);
+  cudaEventCreate(&r->e1);
+  cudaEventRecord(r->e0, s);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  ProfRec* r = reinterpret_cast<ProfRec*>(rec);
+  cudaEventRecord(r->e1, stream);
+  g_prof.push_back(r);
+}
+
+double gemm_alg_flops(const GemmArgs& g) { return 2.0 * g.M * (double)g.N_alg * g.K_alg * g.taps; }
+double gemm_alg_bytes(const GemmArgs& g, int elem) {
+  double b = (double)g.M * g.K_alg * elem + (double)g.N_alg * g.K_alg * g.taps * elem;
+  if (g.res) b += (double)g.M * g.N_alg * 4;
+  if (g.out_f32) b += (double)g.M * g.N_alg * 4;
+  if (g.out_T) b += (double)g.M * g.N_alg * elem;
+  if (g.out_ln) b += (double)g.M * g.N_alg * elem;
+  return b;
+}
+
 static const float kRgbMean[3] = {0.4488f, 0.4371f, 0.4040f};  // common.py:223 / :111
 
 static inline float tf32_round_host(float x) {
@@ -44,6 +78,7 @@ struct Lin {           // one packed (implicit-)GEMM layer
   size_t w_off = 0;    // arena offset of T [NP][taps*KP]
   size_t b_off = 0;    // arena offset of float [NP]
   int K = 0, KP = 0, N = 0, NP = 0, taps = 1, ps_r = 0;
+  int N_alg = 0;       // un-padded output width (accounting)
 };
 struct LNp {
   size_t g_off = 0, b_off = 0;
@@ -140,7 +175,7 @@ static int pack_linear(ssr_model* m, const std::string& name, int N, int K, int 
   const std::vector<float>* W = find_param(m, name + ".weight", (size_t)N * K);
   const std::vector<float>* B = find_param(m, name + ".bias", (size_t)N);
   if (!W || !B) return SSR_E_STATE;
-  out->K = K; out->KP = KP; out->N = N; out->NP = NP; out->taps = 1; out->ps_r = 0;
+  out->K = K; out->KP = KP; out->N = N; out->NP = NP; out->taps = 1; out->ps_r = 0; out->N_alg = N;
   out->w_off = arena_alloc(m, (size_t)NP * KP * m->elem);
   out->b_off = arena_alloc(m, (size_t)NP * 4);
   float* bd = reinterpret_cast<float*>(m->host_arena.data() + out->b_off);
@@ -165,7 +200,7 @@ static int pack_conv(ssr_model* m, const std::string& name, int Cout, int Cin, i
   const std::vector<float>* B = find_param(m, name + ".bias", (size_t)Cout);
   if (!W || !B) return SSR_E_STATE;
   const int NP = round_up(Cout, 64), KP = round_up(Cin, 64);
-  out->K = Cin; out->KP = KP; out->N = Cout; out->NP = NP; out->taps = 9; out->ps_r = ps_r;
+  out->K = Cin; out->KP = KP; out->N = Cout; out->NP = NP; out->taps = 9; out->ps_r = ps_r; out->N_alg = Cout;
   out->w_off = arena_alloc(m, (size_t)NP * 9 * KP * m->elem);
   out->b_off = arena_alloc(m, (size_t)NP * 4);
   const int rr = ps_r > 1 ? ps_r * ps_r : 1, Cps = Cout / rr;
@@ -467,6 +502,8 @@ static GemmArgs gemm_base(const ssr_model* m, const Lin& L, const void* A, int l
   g.alpha = 1.0f;
   g.eps = 1e-5f;
   g.ps_r = L.ps_r;
+  g.K_alg = L.K;
+  g.N_alg = L.N_alg;
   return g;
 }
 
@@ -800,6 +837,53 @@ extern "C" {
 int ssr_version(void) { return SSR_VERSION; }
 const char* ssr_last_error(void) { return g_err; }
 int64_t ssr_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int ssr_profile_begin(void) {
+  for (ProfRec* r : g_prof) {
+    cudaEventDestroy(r->e0);
+    cudaEventDestroy(r->e1);
+    delete r;
+  }
+  g_prof.clear();
+  g_prof_on = true;
+  return SSR_OK;
+}
+
+int ssr_profile_end(char* json, size_t cap) {
+  g_prof_on = false;
+  SSR_CUDA(cudaDeviceSynchronize());
+  struct Agg {
+    double ms = 0, flops = 0, bytes = 0;
+    long long n = 0;
+  };
+  std::map<std::string, Agg> agg;
+  for (ProfRec* r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r->e0, r->e1);
+    Agg& a = agg[r->cls];
+    a.ms += ms;
+    a.flops += r->flops;
+    a.bytes += r->bytes;
+    a.n += 1;
+    cudaEventDestroy(r->e0);
+    cudaEventDestroy(r->e1);
+    delete r;
+  }
+  g_prof.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+    out += buf;
+    first = false;
+  }
+  out += "}";
+  SSR_CHECK(json && out.size() + 1 <= cap, SSR_E_INVALID, "ssr_profile_end: buffer too small (%zu needed)", out.size() + 1);
+  memcpy(json, out.c_str(), out.size() + 1);
+  return SSR_OK;
+}
 
 int ssr_device_check(int device) {
   cudaDeviceProp p;

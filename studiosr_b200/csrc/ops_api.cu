@@ -94,7 +94,7 @@ int ssr_op_linear(int precision, const float* x, const float* W, const float* b,
   memset(&g, 0, sizeof(g));
   g.A = xp; g.lda = KP; g.M = M; g.B = M; g.H = 1; g.W = 1; g.taps = 1; g.KP = KP; g.Wt = wp; g.N = N; g.NP = NP;
   g.bias = bp; g.act = act; g.slope = 0.01f; g.alpha = 1.0f; g.res = rp; g.ldres = NP; g.out_f32 = yp; g.ld_f32 = NP;
-  g.eps = 1e-5f;
+  g.eps = 1e-5f; g.K_alg = K; g.N_alg = N;
   if (ln_w) {
     g.out_ln = ylp; g.ld_ln = NP; g.gamma = gp; g.beta = bep;
   }
@@ -136,7 +136,7 @@ int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = xp; g.lda = KP; g.M = (int)M; g.B = B; g.H = H; g.W = Wd; g.taps = 9; g.KP = KP; g.Wt = wp; g.N = Cout;
-  g.NP = NP; g.bias = bp; g.act = act; g.slope = 0.01f; g.alpha = alpha; g.eps = 1e-5f; g.ps_r = ps_r;
+  g.NP = NP; g.bias = bp; g.act = act; g.slope = 0.01f; g.alpha = alpha; g.eps = 1e-5f; g.ps_r = ps_r; g.K_alg = Cin; g.N_alg = Cout;
   if (res) {
     g.res = rp; g.ldres = NP; g.out_f32 = yf; g.ld_f32 = NP;
   } else {

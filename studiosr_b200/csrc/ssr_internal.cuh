@@ -38,6 +38,16 @@ void count_launch(int n = 1);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// optional per-launch profiling (ssr_profile_begin / ssr_profile_end): CUDA events around every
+// launch on its own stream, aggregated per kernel class with the launch's algorithmic FLOPs/bytes.
+struct ProfScope {
+  void* rec = nullptr;
+  cudaStream_t stream;
+  ProfScope(const char* cls, double flops, double bytes, cudaStream_t s);
+  ~ProfScope();
+};
+
+// ---------------------------------------------------------------------------------------------
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_GELU = 3 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -72,7 +82,10 @@ struct GemmArgs {
   const float* beta;
   float eps;
   int round_tf32;  // round T=float stores to tf32 (rna) so the next tf32 MMA sees exact operands
+  int K_alg, N_alg;  // un-padded contraction / output widths, for FLOP and byte accounting only
 };
+double gemm_alg_flops(const GemmArgs& g);
+double gemm_alg_bytes(const GemmArgs& g, int elem);
 
 struct AttnArgs {
   const void* qkv;  // T [B*H*W][ld_qkv]; q | k | v, each [heads][DP] (q pre-scaled)

@@ -20,7 +20,10 @@ SWINIR_CASES = [
     "swinir_tiny_x8_eval_1x8x8", "swinir_full_x4_eval_cfg1",
 ]
 EDSR_CASES = ["edsr_tiny_x4_2x12x20", "edsr_tiny_x2_1x9x11", "edsr_tiny_x3_1x8x8", "edsr_full_x4_1x24x24"]
-ABS_TOL = {"fp32": 1e-4, "tf32": 1e-3}
+# "fp32" (CUDA-core FMA) carries the north-star fp32 claim (<= 1e-3; held to 1e-4 here).  "tf32" is an
+# opt-in tensor-core mode whose single-pass 10-bit-mantissa operands land at ~1e-3 (measured 9.5e-4 ..
+# 1.1e-3 on these cases), i.e. AT the fp32 tolerance, so it is held to 2e-3 and never used for that claim.
+ABS_TOL = {"fp32": 1e-4, "tf32": 2e-3}
 
 
 def _swinir(cfg, wseed):
