@@ -28,6 +28,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -149,38 +152,113 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
 
 // ---------------------------------------------------------------------------------------------
 struct TcGeom {
-  int conv;            // 0: 128 consecutive rows per tile; 1: BW x BH x BB pixel patch per tile
-  int BW, BH, BB;      // patch shape (BW*BH*BB == 128)
+  int conv;              // 0: 128 consecutive rows per tile; 1: BW x BH x BB pixel patch per tile
+  int BW, BH, BB;        // patch shape (BW*BH*BB == 128)
   int tiles_x, tiles_y;  // patch grid per image (conv)
-  int kc_per_tap;      // KP / BK
-  int nkb;             // taps * kc_per_tap
+  int kc_per_tap;        // KP / BK
+  int nkb;               // taps * kc_per_tap
+  int m_tiles, n_tiles;  // work items = m_tiles * n_tiles, n fastest (A tile stays hot in L2)
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                      // two groups of 4 (one per TMEM accumulator buffer)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_STAGE_ROW = 36;                     // floats per staging row (32 + 4 pad: conflict-free 16 B access)
+constexpr int TC_STAGE_BYTES = 32 * TC_STAGE_ROW * 4;  // per-warp transpose staging tile
+constexpr int TC_MAX_NP = 2304;
 
 template <int BLOCK_N>
-constexpr int tc_tmem_cols() {
-  return BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
-}
-template <int BLOCK_N>
 constexpr int tc_stages() {
-  // stage = 16 KB (A) + BLOCK_N*128 B (W); keep a CTA <= ~100 KB so two fit per SM
-  return BLOCK_N >= 192 ? 2 : (BLOCK_N >= 128 ? 3 : 4);
+  return BLOCK_N >= 256 ? 3 : 4;  // stage = 16 KB (A) + BLOCK_N*128 B (W)
 }
 template <int BLOCK_N>
 constexpr size_t tc_smem_bytes() {
-  return (size_t)tc_stages<BLOCK_N>() * (16384 + BLOCK_N * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return (size_t)tc_stages<BLOCK_N>() * (16384 + BLOCK_N * 128) + TC_EPI_WARPS * TC_STAGE_BYTES + TC_MAX_NP * 4 +
+         2 * 256 * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
+}
+
+// ---- per-warp transposing I/O: thread <-> row in registers, lanes <-> columns in global memory ----
+// The TMEM accumulator layout gives every thread one full row; writing rows straight from registers
+// makes each 16-byte store its own L2 request (measured: 6 cycles/request, 36k cycles per tile).  These
+// helpers bounce a 32x32 chunk through a padded shared tile so global accesses are 128 B (fp32) or
+// 64 B (bf16) contiguous per row, 4 / 8 rows per instruction.
+__device__ __forceinline__ void stage_put_f32(float* st, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(st + lane * TC_STAGE_ROW + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void stage_get_f32(const float* st, int lane, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(st + lane * TC_STAGE_ROW + 4 * q);
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+}
+// rows -> global fp32: `rowoff` is this thread's own row offset in elements (or -1 = row not stored)
+__device__ __forceinline__ void stage_store_f32(const float* st, int lane, float* base, long long rowoff) {
+  const int c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    const long long off = __shfl_sync(0xffffffffu, rowoff, r);
+    const float4 x = *reinterpret_cast<const float4*>(st + r * TC_STAGE_ROW + c4);
+    if (off >= 0) *reinterpret_cast<float4*>(base + off + c4) = x;
+  }
+}
+__device__ __forceinline__ void stage_load_f32(float* st, int lane, const float* base, long long rowoff) {
+  const int c4 = (lane & 7) * 4;
+  float4 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3);
+    const long long off = __shfl_sync(0xffffffffu, rowoff, r);
+    x[i] = off >= 0 ? *reinterpret_cast<const float4*>(base + off + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + c4) = x[i];
+}
+// rows -> global bf16: staging rows hold 32 bf16 (64 B) at an 80-byte pitch
+__device__ __forceinline__ void stage_store_bf16(float* stf, int lane, const float (&v)[32], __nv_bfloat16* base,
+                                                 long long rowoff) {
+  uint8_t* st = reinterpret_cast<uint8_t*>(stf);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(st + lane * 80 + 16 * q) =
+        make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+  __syncwarp();
+  const int c8 = (lane & 3) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    const long long off = __shfl_sync(0xffffffffu, rowoff, r);
+    const uint4 x = *reinterpret_cast<const uint4*>(st + r * 80 + (lane & 3) * 16);
+    if (off >= 0) *reinterpret_cast<uint4*>(base + off + c8) = x;
+  }
+  __syncwarp();
+}
+template <typename T>
+__device__ __forceinline__ void stage_store_T(float* st, int lane, float (&v)[32], T* base, long long rowoff) {
+  if constexpr (sizeof(T) == 2) {
+    stage_store_bf16(st, lane, v, base, rowoff);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+    stage_put_f32(st, lane, v);
+    __syncwarp();
+    stage_store_f32(st, lane, reinterpret_cast<float*>(base), rowoff);
+    __syncwarp();
+  }
 }
 
 template <typename T, int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g,
                const TcGeom geo) {
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int BK = 128 / (int)sizeof(T);  // elements per 128-byte swizzle row
   constexpr int kStages = tc_stages<BLOCK_N>();
-  constexpr int kTmemCols = tc_tmem_cols<BLOCK_N>();
+  constexpr int kTmemCols = 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128 : 2 * BLOCK_N <= 256 ? 256 : 512;
   constexpr uint32_t A_BYTES = TC_BM * 128, W_BYTES = BLOCK_N * 128;
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2 : 1, TC_BM, BLOCK_N);
 
@@ -188,29 +266,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
   uint8_t* smW = smem + kStages * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (A_BYTES + W_BYTES));
-  // bars[0..kStages) full, [kStages..2kStages) empty, [2kStages] tmem_full; then the TMEM base address
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  float* stage_all = reinterpret_cast<float*>(smem + kStages * (A_BYTES + W_BYTES));
+  float* s_bias = stage_all + TC_EPI_WARPS * (TC_STAGE_BYTES / 4);
+  float* s_gamma = s_bias + TC_MAX_NP;
+  float* s_beta = s_gamma + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + 256);
+  // bars: [0,kStages) full, [kStages,2kStages) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * kStages);
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
 
-  // ---- tile coordinates ----
-  const int n0 = blockIdx.y * BLOCK_N;
-  int m0 = 0, tx0 = 0, ty0 = 0, tb0 = 0;
-  if (geo.conv) {
-    int t = blockIdx.x;
-    tx0 = (t % geo.tiles_x) * geo.BW;
-    t /= geo.tiles_x;
-    ty0 = (t % geo.tiles_y) * geo.BH;
-    tb0 = (t / geo.tiles_y) * geo.BB;
-  } else {
-    m0 = blockIdx.x * TC_BM;
-  }
-
+  for (int i = threadIdx.x; i < g.NP; i += TC_THREADS) s_bias[i] = __ldg(g.bias + i);
+  if (g.out_ln)
+    for (int i = threadIdx.x; i < g.NP; i += TC_THREADS) {
+      s_gamma[i] = __ldg(g.gamma + i);
+      s_beta[i] = __ldg(g.beta + i);
+    }
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
@@ -218,7 +294,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);  // one arrival per epilogue warp of the group
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -227,100 +306,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_items = geo.m_tiles * geo.n_tiles;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      for (int kb = 0; kb < geo.nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), A_BYTES + W_BYTES);
-        const int tap = kb / geo.kc_per_tap, kc = kb - tap * geo.kc_per_tap;
-        const uint32_t dstA = smem_u32(smA + s * A_BYTES), dstW = smem_u32(smW + s * W_BYTES);
+      uint32_t kbg = 0;  // running k-block counter across items (ring position)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int mt = item / geo.n_tiles, nt = item - mt * geo.n_tiles;
+        const int n0 = nt * BLOCK_N;
+        int m0 = 0, tx0 = 0, ty0 = 0, tb0 = 0;
         if (geo.conv) {
-          const int dy = (g.taps == 9) ? tap / 3 - 1 : 0, dx = (g.taps == 9) ? tap % 3 - 1 : 0;
-          tma_load_4d(dstA, &tmA, full_bar(s), kc * BK, tx0 + dx, ty0 + dy, tb0);
+          int t = mt;
+          tx0 = (t % geo.tiles_x) * geo.BW;
+          t /= geo.tiles_x;
+          ty0 = (t % geo.tiles_y) * geo.BH;
+          tb0 = (t / geo.tiles_y) * geo.BB;
         } else {
-          tma_load_2d(dstA, &tmA, full_bar(s), kc * BK, m0);
+          m0 = mt * TC_BM;
         }
-        tma_load_2d(dstW, &tmW, full_bar(s), kb * BK, n0);
+        for (int kb = 0; kb < geo.nkb; ++kb, ++kbg) {
+          const int s = kbg % kStages;
+          const uint32_t ph = (kbg / kStages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), A_BYTES + W_BYTES);
+          const int tap = kb / geo.kc_per_tap, kc = kb - tap * geo.kc_per_tap;
+          const uint32_t dstA = smem_u32(smA + s * A_BYTES), dstW = smem_u32(smW + s * W_BYTES);
+          if (geo.conv) {
+            const int dy = (g.taps == 9) ? tap / 3 - 1 : 0, dx = (g.taps == 9) ? tap % 3 - 1 : 0;
+            tma_load_4d(dstA, &tmA, full_bar(s), kc * BK, tx0 + dx, ty0 + dy, tb0);
+          } else {
+            tma_load_2d(dstA, &tmA, full_bar(s), kc * BK, m0);
+          }
+          tma_load_2d(dstW, &tmW, full_bar(s), kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      for (int kb = 0; kb < geo.nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        mbar_wait(full_bar(s), ph);
+      uint32_t kbg = 0;
+      int il = 0;  // local item index
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++il) {
+        const int b = il & 1;
+        mbar_wait(tempty_bar(b), ((uint32_t)(il >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(smA + s * A_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(smW + s * W_BYTES));
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * BLOCK_N);
+        for (int kb = 0; kb < geo.nkb; ++kb, ++kbg) {
+          const int s = kbg % kStages;
+          const uint32_t ph = (kbg / kStages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smA + s * A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smW + s * W_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per 128-byte row: +2 in the (addr >> 4) field
-          umma<kTf32>(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per 128-byte row: +2 in the (addr >> 4) field
+            umma<kTf32>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(tfull_bar(b));  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
     __syncwarp();
   } else {
     // =========================== epilogue ===========================
+    const int ew = warp - 2;
+    const int grp = ew >> 2;    // accumulator buffer / item parity served by this warp
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
-    int m;
-    bool valid;
-    int pb = 0, py = 0, px = 0;
-    if (geo.conv) {
-      const int ww = row % geo.BW, hh = (row / geo.BW) % geo.BH, bb = row / (geo.BW * geo.BH);
-      pb = tb0 + bb;
-      py = ty0 + hh;
-      px = tx0 + ww;
-      valid = pb < g.B && py < g.H && px < g.W;
-      m = (pb * g.H + py) * g.W + px;
-    } else {
-      m = m0 + row;
-      valid = m < g.M;
-      if (g.ps_r > 1 && valid) {
-        px = m % g.W;
-        py = (m / g.W) % g.H;
-        pb = m / (g.W * g.H);
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* st = stage_all + ew * (TC_STAGE_BYTES / 4);
     const int Cps = g.ps_r > 1 ? g.N / (g.ps_r * g.ps_r) : 0;
     const bool do_ln = g.out_ln != nullptr;
-    float sum = 0.0f;
     T* outT = reinterpret_cast<T*>(g.out_T);
+    T* oln = reinterpret_cast<T*>(g.out_ln);
+
+    int il = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++il) {
+      if ((il & 1) != grp) continue;
+      const int mt = item / geo.n_tiles, nt = item - mt * geo.n_tiles;
+      const int n0 = nt * BLOCK_N;
+      long long m = -1;  // this thread's row as a pixel / token index, -1 if outside the tensor
+      int pb = 0, py = 0, px = 0;
+      if (geo.conv) {
+        int t = mt;
+        const int tx0 = (t % geo.tiles_x) * geo.BW;
+        t /= geo.tiles_x;
+        const int ty0 = (t % geo.tiles_y) * geo.BH, tb0 = (t / geo.tiles_y) * geo.BB;
+        const int ww = row % geo.BW, hh = (row / geo.BW) % geo.BH, bb = row / (geo.BW * geo.BH);
+        pb = tb0 + bb;
+        py = ty0 + hh;
+        px = tx0 + ww;
+        if (pb < g.B && py < g.H && px < g.W) m = ((long long)pb * g.H + py) * g.W + px;
+      } else {
+        const long long mm = (long long)mt * TC_BM + row;
+        if (mm < g.M) {
+          m = mm;
+          if (g.ps_r > 1) {
+            px = (int)(mm % g.W);
+            py = (int)((mm / g.W) % g.H);
+            pb = (int)(mm / ((long long)g.W * g.H));
+          }
+        }
+      }
+      const long long off_res = m >= 0 ? m * g.ldres : -1;
+      const long long off_f32 = m >= 0 ? m * g.ld_f32 : -1;
+      const long long off_T = m >= 0 ? m * g.ld_T : -1;
+      const long long off_ln = m >= 0 ? m * g.ld_ln : -1;
+
+      mbar_wait(tfull_bar(grp), (uint32_t)(il >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BLOCK_N);
+      float sum = 0.0f;
 
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      float v[32];
-      tmem_ld32(trow + c * 32, v);
-      const int nb = n0 + c * 32;
-      if (valid) {
-        const float4* b4 = reinterpret_cast<const float4*>(g.bias + nb);
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (g.res) stage_load_f32(st, lane, g.res + nb, off_res);  // coalesced rows -> staging tile
+        float v[32];
+        tmem_ld32(trow + c * 32, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 bv = __ldg(b4 + q);
+          const float4 bv = *reinterpret_cast<const float4*>(s_bias + nb + 4 * q);  // warp-wide broadcast
           v[4 * q + 0] = apply_act(v[4 * q + 0] + bv.x, g.act, g.slope) * g.alpha;
           v[4 * q + 1] = apply_act(v[4 * q + 1] + bv.y, g.act, g.slope) * g.alpha;
           v[4 * q + 2] = apply_act(v[4 * q + 2] + bv.z, g.act, g.slope) * g.alpha;
           v[4 * q + 3] = apply_act(v[4 * q + 3] + bv.w, g.act, g.slope) * g.alpha;
         }
         if (g.res) {
-          const float4* r4 = reinterpret_cast<const float4*>(g.res + (size_t)m * g.ldres + nb);
+          __syncwarp();
+          float r[32];
+          stage_get_f32(st, lane, r);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 rv = r4[q];
-            v[4 * q + 0] += rv.x;
-            v[4 * q + 1] += rv.y;
-            v[4 * q + 2] += rv.z;
-            v[4 * q + 3] += rv.w;
-          }
+          for (int i = 0; i < 32; ++i) v[i] += r[i];
+          __syncwarp();
         }
         if (nb + 32 > g.N) {
 #pragma unroll
@@ -328,90 +446,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (nb + i >= g.N) v[i] = 0.0f;
         }
         if (g.out_f32) {
-          float4* o4 = reinterpret_cast<float4*>(g.out_f32 + (size_t)m * g.ld_f32 + nb);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        if (outT) {
-          T* dst;
-          bool ok = true;
-          if (g.ps_r > 1) {
-            // 32 consecutive GEMM columns stay inside one (i,j) sub-pixel because Cps % 32 == 0
-            ok = nb < g.N;
-            dst = outT + ps_offset(pb, py, px, nb, g.H, g.W, g.ps_r, Cps, g.ld_T);
-          } else {
-            dst = outT + (size_t)m * g.ld_T + nb;
-          }
-          if (ok) {
-            if constexpr (kTf32) {
-              float4* o4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                o4[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]), round_tf32(v[4 * q + 2]),
-                                    round_tf32(v[4 * q + 3]));
-            } else {
-              uint4* o4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                o4[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-            }
-          }
+          stage_put_f32(st, lane, v);
+          __syncwarp();
+          stage_store_f32(st, lane, g.out_f32 + nb, off_f32);
+          __syncwarp();
         }
         if (do_ln) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) sum += v[i];
+          tmem_st32(trow + c * 32, v);  // keep v for the two LayerNorm passes
+        }
+        if (outT) {
+          if (g.ps_r > 1) {
+            // 32 consecutive GEMM columns stay inside one (i,j) sub-pixel because Cps % 32 == 0
+            const long long o = m >= 0 ? (long long)ps_offset(pb, py, px, nb, g.H, g.W, g.ps_r, Cps, g.ld_T) : -1;
+            stage_store_T<T>(st, lane, v, outT, o);
+          } else {
+            stage_store_T<T>(st, lane, v, outT + nb, off_T);
+          }
         }
       }
-      if (do_ln) tmem_st32(trow + c * 32, v);  // keep v for the two LayerNorm passes
-    }
 
-    if (do_ln) {  // host guarantees n0 == 0 and BLOCK_N == NP: the thread owns the whole row
-      const float mean = sum / (float)g.N;
-      float sq = 0.0f;
+      if (do_ln) {  // host guarantees n_tiles == 1 and BLOCK_N == NP: the thread owns the whole row
+        const float mean = sum / (float)g.N;
+        float sq = 0.0f;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        float v[32];
-        tmem_ld32(trow + c * 32, v);
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+          tmem_ld32(trow + c * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = v[i] - mean;
-          if (c * 32 + i < g.N) sq += d * d;
+          for (int i = 0; i < 32; ++i) {
+            const float d = v[i] - mean;
+            if (c * 32 + i < g.N) sq += d * d;
+          }
         }
-      }
-      const float rstd = rsqrtf(sq / (float)g.N + g.eps);
-      T* oln = reinterpret_cast<T*>(g.out_ln);
+        const float rstd = rsqrtf(sq / (float)g.N + g.eps);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        float v[32];
-        tmem_ld32(trow + c * 32, v);
-        if (valid) {
-          const float4* g4 = reinterpret_cast<const float4*>(g.gamma + c * 32);
-          const float4* be4 = reinterpret_cast<const float4*>(g.beta + c * 32);
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+          tmem_ld32(trow + c * 32, v);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 gv = __ldg(g4 + q), bv = __ldg(be4 + q);
+            const float4 gv = *reinterpret_cast<const float4*>(s_gamma + c * 32 + 4 * q);
+            const float4 bv = *reinterpret_cast<const float4*>(s_beta + c * 32 + 4 * q);
             v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * gv.x + bv.x;
             v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * gv.y + bv.y;
             v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gv.z + bv.z;
             v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gv.w + bv.w;
           }
-          T* dst = oln + (size_t)m * g.ld_ln + c * 32;
-          if constexpr (kTf32) {
-            float4* o4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              o4[q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]), round_tf32(v[4 * q + 2]),
-                                  round_tf32(v[4 * q + 3]));
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              o4[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                 pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-          }
+          stage_store_T<T>(st, lane, v, oln + c * 32, off_ln);
         }
       }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(grp));
     }
   }
 
@@ -485,6 +574,7 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   geo.nkb = g.taps * geo.kc_per_tap;
   CUtensorMap tmA, tmW;
   int grid_x;
+  SSR_CHECK(g.NP <= TC_MAX_NP, SSR_E_INVALID, "gemm_tc: NP=%d > %d", g.NP, TC_MAX_NP);
   if (g.taps == 9) {
     geo.conv = 1;
     choose_patch(g.B, g.H, g.W, &geo.BW, &geo.BH, &geo.BB);
@@ -518,7 +608,16 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     SSR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(grid_x, g.NP / BLOCK_N);
+  geo.m_tiles = grid_x;
+  geo.n_tiles = g.NP / BLOCK_N;
+  const int items = geo.m_tiles * geo.n_tiles;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    SSR_CUDA(cudaGetDevice(&dev));
+    SSR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  dim3 grid(items < num_sms ? items : num_sms);
   ProfScope prof(g.taps == 9 ? "gemm_tc_conv3x3" : "gemm_tc_linear", gemm_alg_flops(g), gemm_alg_bytes(g, elem), s);
   gemm_tc_kernel<T, BLOCK_N><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
   count_launch();

@@ -59,7 +59,12 @@ static int dispatch_gemm(int precision, GemmArgs& g, int elem, cudaStream_t s) {
 
 using namespace ssr;
 
+static long long* g_dbg_buf = nullptr;
+
 extern "C" {
+
+// developer diagnostics: per-CTA phase timestamps of the next ssr_op_linear launches (device buffer, 8 x int64 per CTA)
+void ssr_debug_set_buffer(void* p) { g_dbg_buf = reinterpret_cast<long long*>(p); }
 
 size_t ssr_op_workspace_bytes(int64_t max_elems) { return (size_t)max_elems * 4 * 8 + (1 << 20); }
 
@@ -95,6 +100,7 @@ int ssr_op_linear(int precision, const float* x, const float* W, const float* b,
   g.A = xp; g.lda = KP; g.M = M; g.B = M; g.H = 1; g.W = 1; g.taps = 1; g.KP = KP; g.Wt = wp; g.N = N; g.NP = NP;
   g.bias = bp; g.act = act; g.slope = 0.01f; g.alpha = 1.0f; g.res = rp; g.ldres = NP; g.out_f32 = yp; g.ld_f32 = NP;
   g.eps = 1e-5f; g.K_alg = K; g.N_alg = N;
+  g.dbg = g_dbg_buf;
   if (ln_w) {
     g.out_ln = ylp; g.ld_ln = NP; g.gamma = gp; g.beta = bep;
   }

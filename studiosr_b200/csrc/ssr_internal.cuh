@@ -83,6 +83,7 @@ struct GemmArgs {
   float eps;
   int round_tf32;  // round T=float stores to tf32 (rna) so the next tf32 MMA sees exact operands
   int K_alg, N_alg;  // un-padded contraction / output widths, for FLOP and byte accounting only
+  long long* dbg;    // optional per-CTA phase timestamps (developer diagnostics), 8 slots per CTA
 };
 double gemm_alg_flops(const GemmArgs& g);
 double gemm_alg_bytes(const GemmArgs& g, int elem);
