@@ -179,9 +179,22 @@ constexpr size_t tc_smem_bytes() {
 
 // ---- per-warp transposing I/O: thread <-> row in registers, lanes <-> columns in global memory ----
 // The TMEM accumulator layout gives every thread one full row; writing rows straight from registers
-// makes each 16-byte store its own L2 request (measured: 6 cycles/request, 36k cycles per tile).  These
+// makes each 16-byte store its own L2 request (measured: ~6 cycles/request, 36k cycles per tile).  These
 // helpers bounce a 32x32 chunk through a padded shared tile so global accesses are 128 B (fp32) or
-// 64 B (bf16) contiguous per row, 4 / 8 rows per instruction.
+// 64 B (bf16) contiguous per row, 4 / 8 rows per instruction.  Row indices of the transposed view are
+// gathered once per work item (RowMap) so the per-chunk code is shuffle- and branch-free.
+struct RowMap {
+  int mf[8];  // fp32 view: row 4*i + (lane>>3) -> pixel index or -1
+  int mh[4];  // bf16 view: row 8*i + (lane>>2) -> pixel index or -1
+};
+__device__ __forceinline__ RowMap make_rowmap(int m_own, int lane) {
+  RowMap r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.mf[i] = __shfl_sync(0xffffffffu, m_own, 4 * i + (lane >> 3));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.mh[i] = __shfl_sync(0xffffffffu, m_own, 8 * i + (lane >> 2));
+  return r;
+}
 __device__ __forceinline__ void stage_put_f32(float* st, int lane, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q)
@@ -194,32 +207,37 @@ __device__ __forceinline__ void stage_get_f32(const float* st, int lane, float (
     v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
   }
 }
-// rows -> global fp32: `rowoff` is this thread's own row offset in elements (or -1 = row not stored)
-__device__ __forceinline__ void stage_store_f32(const float* st, int lane, float* base, long long rowoff) {
+// coalesced residual prefetch: 8 x float4 per lane covering the warp's 32 rows x 32 columns at column nb
+__device__ __forceinline__ void res_prefetch(float4 (&x)[8], const RowMap& rm, int lane, const float* res, int ldres, int nb) {
   const int c4 = (lane & 7) * 4;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + (lane >> 3);
-    const long long off = __shfl_sync(0xffffffffu, rowoff, r);
-    const float4 x = *reinterpret_cast<const float4*>(st + r * TC_STAGE_ROW + c4);
-    if (off >= 0) *reinterpret_cast<float4*>(base + off + c4) = x;
-  }
+  for (int i = 0; i < 8; ++i)
+    x[i] = rm.mf[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(res + (size_t)rm.mf[i] * ldres + nb + c4))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
 }
-__device__ __forceinline__ void stage_load_f32(float* st, int lane, const float* base, long long rowoff) {
+// transposed domain: st += residual (if any), optional coalesced fp32 store of the sum
+__device__ __forceinline__ void stage_add_store_f32(float* st, int lane, const RowMap& rm, const float4* resv, float* out,
+                                                    int ld_out, int nb) {
   const int c4 = (lane & 7) * 4;
   float4 x[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + (lane >> 3);
-    const long long off = __shfl_sync(0xffffffffu, rowoff, r);
-    x[i] = off >= 0 ? *reinterpret_cast<const float4*>(base + off + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + c4);
+  if (resv) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + c4) = x[i];
+    for (int i = 0; i < 8; ++i) {
+      x[i].x += resv[i].x; x[i].y += resv[i].y; x[i].z += resv[i].z; x[i].w += resv[i].w;
+      *reinterpret_cast<float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + c4) = x[i];
+    }
+  }
+  if (out) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (rm.mf[i] >= 0) *reinterpret_cast<float4*>(out + (size_t)rm.mf[i] * ld_out + nb + c4) = x[i];
+  }
 }
-// rows -> global bf16: staging rows hold 32 bf16 (64 B) at an 80-byte pitch
-__device__ __forceinline__ void stage_store_bf16(float* stf, int lane, const float (&v)[32], __nv_bfloat16* base,
-                                                 long long rowoff) {
+// rows -> global bf16: staging rows hold 32 bf16 (64 B) at an 80-byte pitch.  `dst_of(i)` = destination of row-view i.
+template <typename DstF>
+__device__ __forceinline__ void stage_store_bf16(float* stf, int lane, const float (&v)[32], DstF dst_of) {
   uint8_t* st = reinterpret_cast<uint8_t*>(stf);
 #pragma unroll
   for (int q = 0; q < 4; ++q)
@@ -227,27 +245,61 @@ __device__ __forceinline__ void stage_store_bf16(float* stf, int lane, const flo
         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
   __syncwarp();
-  const int c8 = (lane & 3) * 8;
+  uint4 x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const uint4*>(st + (8 * i + (lane >> 2)) * 80 + (lane & 3) * 16);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = 8 * i + (lane >> 2);
-    const long long off = __shfl_sync(0xffffffffu, rowoff, r);
-    const uint4 x = *reinterpret_cast<const uint4*>(st + r * 80 + (lane & 3) * 16);
-    if (off >= 0) *reinterpret_cast<uint4*>(base + off + c8) = x;
+    __nv_bfloat16* d = dst_of(i);
+    if (d) *reinterpret_cast<uint4*>(d + (lane & 3) * 8) = x[i];
   }
   __syncwarp();
 }
-template <typename T>
-__device__ __forceinline__ void stage_store_T(float* st, int lane, float (&v)[32], T* base, long long rowoff) {
-  if constexpr (sizeof(T) == 2) {
-    stage_store_bf16(st, lane, v, base, rowoff);
-  } else {
+template <typename DstF>
+__device__ __forceinline__ void stage_store_tf32(float* st, int lane, float (&v)[32], DstF dst_of) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
-    stage_put_f32(st, lane, v);
-    __syncwarp();
-    stage_store_f32(st, lane, reinterpret_cast<float*>(base), rowoff);
-    __syncwarp();
+  for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+  stage_put_f32(st, lane, v);
+  __syncwarp();
+  float4 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + (lane & 7) * 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float* d = dst_of(i);
+    if (d) *reinterpret_cast<float4*>(d + (lane & 7) * 4) = x[i];
+  }
+  __syncwarp();
+}
+
+// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26) on the SFU: 1 rcp + 1 ex2 + 6 FMA instead of
+// erff's ~40-instruction polynomial; used by the tensor-core epilogues (the fp32 CUDA-core path keeps erff).
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(e, x);
+}
+__device__ __forceinline__ void epilogue_act(float (&v)[32], int act, float slope, float alpha) {
+  // one uniform branch around each 32-element loop: a per-element switch gets if-converted by ptxas and
+  // then evaluates the erf polynomial for every element whatever `act` is (measured 2.5k cycles / chunk)
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + fast_erf(v[i] * 0.70710678118654752440f));
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * slope;
+  }
+  if (alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= alpha;
   }
 }
 
@@ -385,59 +437,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if ((il & 1) != grp) continue;
       const int mt = item / geo.n_tiles, nt = item - mt * geo.n_tiles;
       const int n0 = nt * BLOCK_N;
-      long long m = -1;  // this thread's row as a pixel / token index, -1 if outside the tensor
-      int pb = 0, py = 0, px = 0;
+      int m = -1;  // this thread's row as a pixel / token index, -1 if outside the tensor
       if (geo.conv) {
         int t = mt;
         const int tx0 = (t % geo.tiles_x) * geo.BW;
         t /= geo.tiles_x;
         const int ty0 = (t % geo.tiles_y) * geo.BH, tb0 = (t / geo.tiles_y) * geo.BB;
         const int ww = row % geo.BW, hh = (row / geo.BW) % geo.BH, bb = row / (geo.BW * geo.BH);
-        pb = tb0 + bb;
-        py = ty0 + hh;
-        px = tx0 + ww;
-        if (pb < g.B && py < g.H && px < g.W) m = ((long long)pb * g.H + py) * g.W + px;
+        const int pb = tb0 + bb, py = ty0 + hh, px = tx0 + ww;
+        if (pb < g.B && py < g.H && px < g.W) m = (pb * g.H + py) * g.W + px;
       } else {
-        const long long mm = (long long)mt * TC_BM + row;
-        if (mm < g.M) {
-          m = mm;
-          if (g.ps_r > 1) {
-            px = (int)(mm % g.W);
-            py = (int)((mm / g.W) % g.H);
-            pb = (int)(mm / ((long long)g.W * g.H));
-          }
-        }
+        const int mm = mt * TC_BM + row;
+        if (mm < g.M) m = mm;
       }
-      const long long off_res = m >= 0 ? m * g.ldres : -1;
-      const long long off_f32 = m >= 0 ? m * g.ld_f32 : -1;
-      const long long off_T = m >= 0 ? m * g.ld_T : -1;
-      const long long off_ln = m >= 0 ? m * g.ld_ln : -1;
+      const RowMap rm = make_rowmap(m, lane);
+      // destination of transposed-view row i for the T-typed outputs (plain rows or pixel-shuffled)
+      auto dstT = [&](T* base, int ld, int mi, int nb) -> T* {
+        if (mi < 0) return nullptr;
+        if (g.ps_r > 1) {
+          const int px = mi % g.W, py = (mi / g.W) % g.H, pb = mi / (g.W * g.H);
+          return base + ps_offset(pb, py, px, nb, g.H, g.W, g.ps_r, Cps, ld);
+        }
+        return base + (size_t)mi * ld + nb;
+      };
+      auto store_T = [&](float (&v)[32], T* base, int ld, int nb) {
+        if constexpr (sizeof(T) == 2) {
+          stage_store_bf16(st, lane, v, [&](int i) { return dstT(base, ld, rm.mh[i], nb); });
+        } else {
+          stage_store_tf32(st, lane, v, [&](int i) { return dstT(base, ld, rm.mf[i], nb); });
+        }
+      };
 
+      float4 resv[8];
+      if (g.res) res_prefetch(resv, rm, lane, g.res, g.ldres, n0);  // overlaps the wait for the accumulator
+
+      long long* dbg = (g.dbg && (ew & 3) == 0 && lane == 0 && il < 64) ? g.dbg + 16 * ((size_t)blockIdx.x * 64 + il) : nullptr;
+      if (dbg) dbg[0] = clock64();
       mbar_wait(tfull_bar(grp), (uint32_t)(il >> 1) & 1u);
       tc_fence_after();
+      if (dbg) dbg[1] = clock64();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BLOCK_N);
       float sum = 0.0f;
 
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int nb = n0 + c * 32;
-        if (g.res) stage_load_f32(st, lane, g.res + nb, off_res);  // coalesced rows -> staging tile
         float v[32];
+        if (dbg && c == 1) dbg[4] = clock64();
         tmem_ld32(trow + c * 32, v);
+        if (dbg && c == 1) dbg[5] = clock64();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bv = *reinterpret_cast<const float4*>(s_bias + nb + 4 * q);  // warp-wide broadcast
-          v[4 * q + 0] = apply_act(v[4 * q + 0] + bv.x, g.act, g.slope) * g.alpha;
-          v[4 * q + 1] = apply_act(v[4 * q + 1] + bv.y, g.act, g.slope) * g.alpha;
-          v[4 * q + 2] = apply_act(v[4 * q + 2] + bv.z, g.act, g.slope) * g.alpha;
-          v[4 * q + 3] = apply_act(v[4 * q + 3] + bv.w, g.act, g.slope) * g.alpha;
+          v[4 * q + 0] += bv.x;
+          v[4 * q + 1] += bv.y;
+          v[4 * q + 2] += bv.z;
+          v[4 * q + 3] += bv.w;
         }
-        if (g.res) {
+        epilogue_act(v, g.act, g.slope, g.alpha);
+        if (dbg && c == 1) dbg[6] = clock64();
+        if (g.res || g.out_f32) {
+          // transposed domain: add the (prefetched, coalesced) residual and store the fp32 stream
+          stage_put_f32(st, lane, v);
           __syncwarp();
-          float r[32];
-          stage_get_f32(st, lane, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += r[i];
+          stage_add_store_f32(st, lane, rm, g.res ? resv : nullptr, g.out_f32, g.ld_f32, nb);
+          if (g.res && c + 1 < BLOCK_N / 32) res_prefetch(resv, rm, lane, g.res, g.ldres, nb + 32);
+          __syncwarp();
+          if (g.res) stage_get_f32(st, lane, v);
           __syncwarp();
         }
         if (nb + 32 > g.N) {
@@ -445,27 +511,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; ++i)
             if (nb + i >= g.N) v[i] = 0.0f;
         }
-        if (g.out_f32) {
-          stage_put_f32(st, lane, v);
-          __syncwarp();
-          stage_store_f32(st, lane, g.out_f32 + nb, off_f32);
-          __syncwarp();
-        }
         if (do_ln) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) sum += v[i];
           tmem_st32(trow + c * 32, v);  // keep v for the two LayerNorm passes
         }
-        if (outT) {
-          if (g.ps_r > 1) {
-            // 32 consecutive GEMM columns stay inside one (i,j) sub-pixel because Cps % 32 == 0
-            const long long o = m >= 0 ? (long long)ps_offset(pb, py, px, nb, g.H, g.W, g.ps_r, Cps, g.ld_T) : -1;
-            stage_store_T<T>(st, lane, v, outT, o);
-          } else {
-            stage_store_T<T>(st, lane, v, outT + nb, off_T);
-          }
-        }
+        if (outT) store_T(v, outT, g.ld_T, nb);
+        if (dbg && c == 1) dbg[7] = clock64();
       }
+      if (dbg) dbg[2] = clock64();
 
       if (do_ln) {  // host guarantees n_tiles == 1 and BLOCK_N == NP: the thread owns the whole row
         const float mean = sum / (float)g.N;
@@ -494,9 +548,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * gv.z + bv.z;
             v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * gv.w + bv.w;
           }
-          stage_store_T<T>(st, lane, v, oln + c * 32, off_ln);
+          // LN output is always plain rows (never pixel-shuffled)
+          if constexpr (sizeof(T) == 2) {
+            stage_store_bf16(st, lane, v, [&](int i) { return rm.mh[i] >= 0 ? oln + (size_t)rm.mh[i] * g.ld_ln + c * 32 : nullptr; });
+          } else {
+            stage_store_tf32(st, lane, v, [&](int i) { return rm.mf[i] >= 0 ? oln + (size_t)rm.mf[i] * g.ld_ln + c * 32 : nullptr; });
+          }
         }
       }
+      if (dbg) dbg[3] = clock64();
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
       tc_fence_before();
       __syncwarp();
