@@ -153,6 +153,14 @@ int ssr_op_linear(int precision, const float* x, const float* W, const float* b,
 int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b, const float* res, float* y, int B,
                    int Cin, int Cout, int H, int Wd, int act, float alpha, int ps_r, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* Fused tail of a SwinTransformerBlock (swinir.py:103,171-172; common.py:184-194), bf16 tensor-core path:
+ *   t1 = o @ Wp^T + bp + res;  h = GELU(LN(t1; g2,be2) @ W1^T + b1);  y = t1 + h @ W2^T + b2;
+ *   y_ln = LN(y; g3,be3) (or, when g3 is NULL, y rounded to bf16).  o, res, y: [M, C] fp32; weights in PyTorch
+ *   layouts ([C,C], [hidden,C], [C,hidden]).  Only the C=180 / 6 heads / hidden=360 class of shapes. */
+int ssr_op_swin_mlp(const float* o, const float* res, const float* Wp, const float* bp, const float* g2, const float* be2,
+                    const float* W1, const float* b1, const float* W2, const float* b2, const float* g3, const float* be3,
+                    float* y, float* y_ln, int M, int C, int heads, int hidden, void* workspace, size_t workspace_bytes,
+                    void* stream);
 /* SwinIR (shifted-)window attention core, swinir.py:78-105 minus the two Linear layers, together with
  * the roll / window_partition / window_reverse / calculate_mask around it (swinir.py:154-168,
  * common.py:236-274): qkv [B,H,W,3*C] (q|k|v, each head-major, un-scaled) -> o [B,H,W,C]; q scaling,

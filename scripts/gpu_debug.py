@@ -165,6 +165,56 @@ def attn_bf16():
     _attn("bf16", 2, 24, 16, 60, 6, 4)
 
 
+def _swin_mlp(M, with_ln):
+    import ctypes
+
+    import torch
+
+    from oracle import sr_oracle as O
+    from studiosr_b200 import _lib
+    from tests import gpu_util as G
+
+    lib = _lib.load()
+    C, heads, hid = 180, 6, 360
+    g = torch.Generator().manual_seed(5)
+    o = torch.randn(M, C, generator=g)
+    res = torch.randn(M, C, generator=g)
+    Wp = torch.randn(C, C, generator=g) / C**0.5 * 0.5
+    bp = torch.randn(C, generator=g) * 0.1
+    g2 = 1 + 0.1 * torch.randn(C, generator=g); be2 = 0.1 * torch.randn(C, generator=g)
+    W1 = torch.randn(hid, C, generator=g) / C**0.5
+    b1 = torch.randn(hid, generator=g) * 0.1
+    W2 = torch.randn(C, hid, generator=g) / hid**0.5 * 0.5
+    b2 = torch.randn(C, generator=g) * 0.1
+    g3 = 1 + 0.1 * torch.randn(C, generator=g); be3 = 0.1 * torch.randn(C, generator=g)
+    t1 = o @ Wp.t() + bp + res
+    h = O.gelu(O.layer_norm(t1, g2, be2) @ W1.t() + b1)
+    y = t1 + h @ W2.t() + b2
+    yl = O.layer_norm(y, g3, be3) if with_ln else y
+    c = lambda t: t.cuda()
+    yo = torch.empty(M, C, device="cuda"); ylo = torch.empty(M, C, device="cuda")
+    ws = torch.empty(M * 192 * 16 + (1 << 22), dtype=torch.uint8, device="cuda")
+    args = [c(o), c(res), c(Wp), c(bp), c(g2), c(be2), c(W1), c(b1), c(W2), c(b2)]
+    args += [c(g3), c(be3)] if with_ln else [None, None]
+    ptrs = [None if t is None else t.data_ptr() for t in args]
+    _lib.check(lib.ssr_op_swin_mlp(*ptrs, yo.data_ptr(), ylo.data_ptr(), M, C, heads, hid, ws.data_ptr(), ws.numel(), G.stream()))
+    torch.cuda.synchronize()
+    _stats(f"swin_mlp M{M} ln{int(with_ln)}: y", yo, y)
+    _stats("   y_ln / bf16 copy", ylo, yl)
+
+
+@check
+def mlp_fused_small():
+    _swin_mlp(128, True)
+
+
+@check
+def mlp_fused():
+    _swin_mlp(300, True)
+    _swin_mlp(5184, False)
+    _swin_mlp(148 * 128 * 3 + 77, True)
+
+
 @check
 def model_tiny():
     import torch

@@ -9,146 +9,12 @@
 // warps 2..5 = epilogue (one TMEM lane quadrant each; thread <-> accumulator row).
 // Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
 // epilogue overlaps the other's TMA/MMA main loop.
-#include <cuda.h>
-
 #include <mutex>
 
-#include "ssr_device.cuh"
+#include "ssr_tc.cuh"
 
 namespace ssr {
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline bug must trap (-> CUDA error on the host), never hang the GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int kCols>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(kCols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int kCols>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool kTf32>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if constexpr (kTf32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  }
-}
-
-// 32 lanes x 32 columns of fp32: thread t of the warp gets lane (base_lane + t), columns [col, col+32)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-      "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])),
-      "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])),
-      "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
-      "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])),
-      "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor, K-major operand, 128B swizzle, rows of 128 bytes packed densely:
-// start>>4 | LBO(=1, unused for swizzled K-major) | SBO = 1024 B (8 rows) | version 1 | SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D fp32, A/B format (1 = bf16, 2 = tf32), both K-major, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------------------------
 struct TcGeom {
@@ -163,8 +29,6 @@ struct TcGeom {
 constexpr int TC_BM = 128;
 constexpr int TC_EPI_WARPS = 8;                      // two groups of 4 (one per TMEM accumulator buffer)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_STAGE_ROW = 36;                     // floats per staging row (32 + 4 pad: conflict-free 16 B access)
-constexpr int TC_STAGE_BYTES = 32 * TC_STAGE_ROW * 4;  // per-warp transpose staging tile
 constexpr int TC_MAX_NP = 2304;
 
 template <int BLOCK_N>
@@ -177,133 +41,6 @@ constexpr size_t tc_smem_bytes() {
          2 * 256 * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
 }
 
-// ---- per-warp transposing I/O: thread <-> row in registers, lanes <-> columns in global memory ----
-// The TMEM accumulator layout gives every thread one full row; writing rows straight from registers
-// makes each 16-byte store its own L2 request (measured: ~6 cycles/request, 36k cycles per tile).  These
-// helpers bounce a 32x32 chunk through a padded shared tile so global accesses are 128 B (fp32) or
-// 64 B (bf16) contiguous per row, 4 / 8 rows per instruction.  Row indices of the transposed view are
-// gathered once per work item (RowMap) so the per-chunk code is shuffle- and branch-free.
-struct RowMap {
-  int mf[8];  // fp32 view: row 4*i + (lane>>3) -> pixel index or -1
-  int mh[4];  // bf16 view: row 8*i + (lane>>2) -> pixel index or -1
-};
-__device__ __forceinline__ RowMap make_rowmap(int m_own, int lane) {
-  RowMap r;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r.mf[i] = __shfl_sync(0xffffffffu, m_own, 4 * i + (lane >> 3));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) r.mh[i] = __shfl_sync(0xffffffffu, m_own, 8 * i + (lane >> 2));
-  return r;
-}
-__device__ __forceinline__ void stage_put_f32(float* st, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(st + lane * TC_STAGE_ROW + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-}
-__device__ __forceinline__ void stage_get_f32(const float* st, int lane, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 x = *reinterpret_cast<const float4*>(st + lane * TC_STAGE_ROW + 4 * q);
-    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-  }
-}
-// coalesced residual prefetch: 8 x float4 per lane covering the warp's 32 rows x 32 columns at column nb
-__device__ __forceinline__ void res_prefetch(float4 (&x)[8], const RowMap& rm, int lane, const float* res, int ldres, int nb) {
-  const int c4 = (lane & 7) * 4;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    x[i] = rm.mf[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(res + (size_t)rm.mf[i] * ldres + nb + c4))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-}
-// transposed domain: st += residual (if any), optional coalesced fp32 store of the sum
-__device__ __forceinline__ void stage_add_store_f32(float* st, int lane, const RowMap& rm, const float4* resv, float* out,
-                                                    int ld_out, int nb) {
-  const int c4 = (lane & 7) * 4;
-  float4 x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + c4);
-  if (resv) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      x[i].x += resv[i].x; x[i].y += resv[i].y; x[i].z += resv[i].z; x[i].w += resv[i].w;
-      *reinterpret_cast<float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + c4) = x[i];
-    }
-  }
-  if (out) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (rm.mf[i] >= 0) *reinterpret_cast<float4*>(out + (size_t)rm.mf[i] * ld_out + nb + c4) = x[i];
-  }
-}
-// rows -> global bf16: staging rows hold 32 bf16 (64 B) at an 80-byte pitch.  `dst_of(i)` = destination of row-view i.
-template <typename DstF>
-__device__ __forceinline__ void stage_store_bf16(float* stf, int lane, const float (&v)[32], DstF dst_of) {
-  uint8_t* st = reinterpret_cast<uint8_t*>(stf);
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<uint4*>(st + lane * 80 + 16 * q) =
-        make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-  __syncwarp();
-  uint4 x[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const uint4*>(st + (8 * i + (lane >> 2)) * 80 + (lane & 3) * 16);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16* d = dst_of(i);
-    if (d) *reinterpret_cast<uint4*>(d + (lane & 3) * 8) = x[i];
-  }
-  __syncwarp();
-}
-template <typename DstF>
-__device__ __forceinline__ void stage_store_tf32(float* st, int lane, float (&v)[32], DstF dst_of) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
-  stage_put_f32(st, lane, v);
-  __syncwarp();
-  float4 x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(st + (4 * i + (lane >> 3)) * TC_STAGE_ROW + (lane & 7) * 4);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float* d = dst_of(i);
-    if (d) *reinterpret_cast<float4*>(d + (lane & 7) * 4) = x[i];
-  }
-  __syncwarp();
-}
-
-// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26) on the SFU: rcp.approx + ex2.approx + 7 FMA-class
-// ops instead of erff's branchy ~40-instruction polynomial (measured: GELU epilogue 19k -> 6k cycles / tile).
-// Used by the tensor-core epilogues only; the fp32 CUDA-core path keeps erff.
-__device__ __forceinline__ float fast_erf(float x) {
-  const float ax = fabsf(x);
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  return copysignf(fmaf(-p * t, e, 1.0f), x);
-}
-__device__ __forceinline__ void epilogue_act(float (&v)[32], int act, float slope, float alpha) {
-  // one uniform branch around each 32-element loop: a per-element switch gets if-converted by ptxas and
-  // then evaluates the erf polynomial for every element whatever `act` is (measured 2.5k cycles / chunk)
-  if (act == ACT_GELU) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + fast_erf(v[i] * 0.70710678118654752440f));
-  } else if (act == ACT_RELU) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-  } else if (act == ACT_LEAKY) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * slope;
-  }
-  if (alpha != 1.0f) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= alpha;
-  }
-}
 
 template <typename T, int BLOCK_N>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -594,7 +331,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_tmap(CUtensorMap* map, const void* base, int elem, int rank, const cuuint64_t* dims,
+int make_tmap(CUtensorMap* map, const void* base, int elem, int rank, const cuuint64_t* dims,
                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   SSR_CHECK(fn != nullptr, SSR_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -606,6 +343,16 @@ static int make_tmap(CUtensorMap* map, const void* base, int elem, int rank, con
   SSR_CHECK(r == CUDA_SUCCESS, SSR_E_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d base %p dims %llu,%llu", (int)r,
             rank, base, (unsigned long long)dims[0], (unsigned long long)dims[1]);
   return SSR_OK;
+}
+
+int num_sms_cached() {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      num_sms = 148;
+  }
+  return num_sms;
 }
 
 // choose a BW x BH x BB = 128 pixel patch that wastes the fewest out-of-image pixels
@@ -673,12 +420,7 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   geo.m_tiles = grid_x;
   geo.n_tiles = g.NP / BLOCK_N;
   const int items = geo.m_tiles * geo.n_tiles;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    SSR_CUDA(cudaGetDevice(&dev));
-    SSR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = num_sms_cached();
   dim3 grid(items < num_sms ? items : num_sms);
   ProfScope prof(g.taps == 9 ? "gemm_tc_conv3x3" : "gemm_tc_linear", gemm_alg_flops(g), gemm_alg_bytes(g, elem), s);
   gemm_tc_kernel<T, BLOCK_N><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);

@@ -647,6 +647,24 @@ int launch_unpack_heads(const void* o, int ld, int elem, float* out, int M, int 
   return SSR_OK;
 }
 
+// reference channel order [M][heads*d] -> padded head layout [M][ld] (column = head*DP + j), zero pads
+__global__ void pack_heads_kernel(const float* in, void* out, int M, int heads, int d, int DP, int ld, int elem, int rtf32) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * ld) return;
+  const int c = (int)(idx % ld);
+  const long long m = idx / ld;
+  const int h = c / DP, j = c % DP;
+  store_elem(out, (size_t)idx, elem, (h < heads && j < d) ? in[m * heads * d + h * d + j] : 0.0f, rtf32);
+}
+int launch_pack_heads(const float* in, void* out, int M, int heads, int d, int DP, int ld, int elem, int rtf32,
+                      cudaStream_t s) {
+  const long long total = (long long)M * ld;
+  pack_heads_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(in, out, M, heads, d, DP, ld, elem, rtf32);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* in, void* out, int B, int C, int H, int W, int ld, int elem, int rtf32) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * ld) return;

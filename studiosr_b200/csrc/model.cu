@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -630,9 +631,11 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
   }
   SSR_CUDA(cudaMemsetAsync(W.o, 0, (size_t)T * m->QPmax * e, s));
   const int nL = (int)m->layers.size();
+  static const bool no_fused = getenv("STUDIOSR_B200_NO_FUSED_MLP") != nullptr;
   for (int li = 0; li < nL; ++li) {
     const Layer& L = m->layers[li];
     const int depth = (int)L.blocks.size();
+    const bool fused_mlp = !no_fused && c.precision == SSR_PREC_BF16 && CP == 192 && m->HP == 384 && L.QP == 192;
     for (int bi = 0; bi < depth; ++bi) {
       const Block& blk = L.blocks[bi];
       {  // qkv projection (swinir.py:80); q scale folded into the packed weights
@@ -662,6 +665,25 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
           SSR_TRY(launch_attn_mma(a, s));
         else
           SSR_TRY(launch_attn_simt(a, s));
+      }
+      if (fused_mlp) {  // proj + res + LN2 + fc1 + GELU + fc2 + res (+ next norm1 | bf16 copy) in ONE kernel
+        MlpFusedArgs f;
+        memset(&f, 0, sizeof(f));
+        f.o = W.o; f.ld_o = L.QP; f.M = T; f.C = m->C; f.Hid = m->HID; f.CP = CP; f.HP = m->HP; f.QP = L.QP;
+        f.Wp = m->arena + blk.proj.w_off; f.W1 = m->arena + blk.fc1.w_off; f.W2 = m->arena + blk.fc2.w_off;
+        f.bp = m->dev<float>(blk.proj.b_off); f.b1 = m->dev<float>(blk.fc1.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
+        f.g2 = m->dev<float>(blk.norm2.g_off); f.be2 = m->dev<float>(blk.norm2.b_off);
+        f.res = bi == 0 ? W.g : W.t; f.ldres = CP;
+        f.eps = 1e-5f;
+        if (bi + 1 < depth) {
+          f.out_f32 = W.t; f.ld_f32 = CP;
+          f.out_ln = W.xn; f.ld_ln = CP;
+          f.g3 = m->dev<float>(L.blocks[bi + 1].norm1.g_off); f.be3 = m->dev<float>(L.blocks[bi + 1].norm1.b_off);
+        } else {
+          f.out_T = W.tb; f.ld_T = CP;
+        }
+        SSR_TRY(launch_mlp_fused(f, s));
+        continue;
       }
       {  // proj + residual (swinir.py:103,171) with norm2 fused into the epilogue
         GemmArgs g = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);

@@ -153,6 +153,61 @@ int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b
   return launch_nhwc_to_nchw(yp, ldo, elem, y, B, Cps, H * r, Wd * r, s);
 }
 
+int ssr_op_swin_mlp(const float* o, const float* res, const float* Wp, const float* bp, const float* g2, const float* be2,
+                    const float* W1, const float* b1, const float* W2, const float* b2, const float* g3, const float* be3,
+                    float* y, float* y_ln, int M, int C, int heads, int hidden, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  SSR_CHECK(o && res && Wp && W1 && W2 && y && workspace, SSR_E_INVALID, "ssr_op_swin_mlp: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = C / heads, DP = d <= 16 ? 16 : 32, QP = round_up(heads * DP, 64), CP = round_up(C, 64), HP = round_up(hidden, 64);
+  SSR_CHECK(CP == 192 && HP == 384 && QP == 192, SSR_E_INVALID, "ssr_op_swin_mlp: only C=180/heads=6/hidden=360-class shapes");
+  Carve c(workspace, workspace_bytes);
+  void* op = c.take((size_t)M * QP * 2);
+  float* rp = (float*)c.take((size_t)M * CP * 4);
+  void* wp = c.take((size_t)CP * QP * 2);
+  void* w1 = c.take((size_t)HP * CP * 2);
+  void* w2 = c.take((size_t)CP * HP * 2);
+  float* vec = (float*)c.take((size_t)(6 * CP + HP) * 4);
+  float* yp = (float*)c.take((size_t)M * CP * 4);
+  void* ylp = c.take((size_t)M * CP * 2);
+  float* wtmp = (float*)c.take((size_t)CP * QP * 4);
+  SSR_CHECK(wtmp, SSR_E_WORKSPACE, "ssr_op_swin_mlp: workspace too small (%zu B)", workspace_bytes);
+  SSR_TRY(launch_pack_heads(o, op, M, heads, d, DP, QP, 2, 0, s));
+  SSR_TRY(launch_pack_rows(res, M, C, rp, CP, 4, 0, s));
+  // Wproj [C][C]: remap the K index to the padded head layout (row by row = "M" = C rows), zero-pad rows to CP
+  SSR_CUDA(cudaMemsetAsync(wp, 0, (size_t)CP * QP * 2, s));
+  SSR_TRY(launch_pack_heads(Wp, wp, C, heads, d, DP, QP, 2, 0, s));
+  SSR_CUDA(cudaMemsetAsync(w1, 0, (size_t)HP * CP * 2, s));
+  SSR_TRY(launch_pack_rows(W1, hidden, C, w1, CP, 2, 0, s));
+  SSR_CUDA(cudaMemsetAsync(w2, 0, (size_t)CP * HP * 2, s));
+  SSR_TRY(launch_pack_rows(W2, C, hidden, w2, HP, 2, 0, s));
+  float *vbp = vec, *vb2 = vec + CP, *vg2 = vec + 2 * CP, *vbe2 = vec + 3 * CP, *vg3 = vec + 4 * CP, *vbe3 = vec + 5 * CP,
+        *vb1 = vec + 6 * CP;
+  SSR_TRY(launch_pack_rows(bp, 1, C, vbp, CP, 4, 0, s));
+  SSR_TRY(launch_pack_rows(b2, 1, C, vb2, CP, 4, 0, s));
+  SSR_TRY(launch_pack_rows(g2, 1, C, vg2, CP, 4, 0, s));
+  SSR_TRY(launch_pack_rows(be2, 1, C, vbe2, CP, 4, 0, s));
+  if (g3) {
+    SSR_TRY(launch_pack_rows(g3, 1, C, vg3, CP, 4, 0, s));
+    SSR_TRY(launch_pack_rows(be3, 1, C, vbe3, CP, 4, 0, s));
+  }
+  SSR_TRY(launch_pack_rows(b1, 1, hidden, vb1, HP, 4, 0, s));
+  MlpFusedArgs f;
+  memset(&f, 0, sizeof(f));
+  f.o = op; f.ld_o = QP; f.M = M; f.C = C; f.Hid = hidden; f.CP = CP; f.HP = HP; f.QP = QP;
+  f.Wp = wp; f.W1 = w1; f.W2 = w2; f.bp = vbp; f.b1 = vb1; f.b2 = vb2; f.g2 = vg2; f.be2 = vbe2;
+  f.res = rp; f.ldres = CP; f.out_f32 = yp; f.ld_f32 = CP; f.eps = 1e-5f;
+  if (g3) {
+    f.g3 = vg3; f.be3 = vbe3; f.out_ln = ylp; f.ld_ln = CP;
+  } else {
+    f.out_T = ylp; f.ld_T = CP;
+  }
+  SSR_TRY(launch_mlp_fused(f, s));
+  SSR_TRY(launch_unpack_rows(yp, CP, 4, y, M, C, s));
+  if (y_ln) SSR_TRY(launch_unpack_rows(ylp, CP, 2, y_ln, M, C, s));
+  return SSR_OK;
+}
+
 int ssr_op_window_attention(int precision, const float* qkv, const float* bias_table, float* o, int B, int H, int W, int C,
                             int heads, int ws, int shift, void* workspace, size_t workspace_bytes, void* stream) {
   SSR_CHECK(qkv && bias_table && o && workspace, SSR_E_INVALID, "ssr_op_window_attention: bad argument");

@@ -161,6 +161,27 @@ struct BlendArgs {
   float u8_scale;
 };
 
+// fused proj + residual + LN2 + fc1 + GELU + fc2 + residual (+ LN_next) of one Swin block (bf16, padded 192/384)
+struct MlpFusedArgs {
+  const void* o;  // bf16 [M][ld_o] attention output in the padded head layout
+  int ld_o;
+  int M, C, Hid, CP, HP, QP;
+  const void *Wp, *W1, *W2;  // packed bf16 [CP][QP], [HP][CP], [CP][HP]
+  const float *bp, *b1, *b2, *g2, *be2, *g3, *be3;  // padded fp32 vectors (g3/be3 may be null)
+  const float* res;
+  int ldres;
+  float* out_f32;
+  int ld_f32;
+  void* out_T;
+  int ld_T;
+  void* out_ln;
+  int ld_ln;
+  float eps;
+};
+int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t s);
+int launch_pack_heads(const float* in, void* out, int M, int heads, int d, int DP, int ld, int elem, int round_tf32,
+                      cudaStream_t s);
+
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s);
 int launch_attn_simt(const AttnArgs& a, cudaStream_t s);
