@@ -332,13 +332,17 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap(CUtensorMap* map, const void* base, int elem, int rank, const cuuint64_t* dims,
-                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+              const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   SSR_CHECK(fn != nullptr, SSR_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapDataType dt = elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SSR_CHECK(r == CUDA_SUCCESS, SSR_E_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d base %p dims %llu,%llu", (int)r,
             rank, base, (unsigned long long)dims[0], (unsigned long long)dims[1]);

@@ -57,6 +57,9 @@ static int dispatch_gemm(int precision, GemmArgs& g, int elem, cudaStream_t s) {
 
 }  // namespace ssr
 
+namespace ssr {
+extern long long* g_tail_dbg;
+}
 using namespace ssr;
 
 static long long* g_dbg_buf = nullptr;
@@ -64,7 +67,10 @@ static long long* g_dbg_buf = nullptr;
 extern "C" {
 
 // developer diagnostics: per-CTA phase timestamps of the next ssr_op_linear launches (device buffer, 8 x int64 per CTA)
-void ssr_debug_set_buffer(void* p) { g_dbg_buf = reinterpret_cast<long long*>(p); }
+void ssr_debug_set_buffer(void* p) {
+  g_dbg_buf = reinterpret_cast<long long*>(p);
+  ssr::g_tail_dbg = g_dbg_buf;
+}
 
 size_t ssr_op_workspace_bytes(int64_t max_elems) { return (size_t)max_elems * 4 * 8 + (1 << 20); }
 
