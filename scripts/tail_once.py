@@ -1,0 +1,21 @@
+"""Developer aid: launch the fused Swin tail kernel a few times on a large synthetic tile set (for ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from studiosr_b200 import _lib
+from tests import gpu_util as G
+
+lib = _lib.load()
+M, C, heads, hid = 148 * 128 * 12, 180, 6, 360
+g = torch.Generator().manual_seed(0)
+r = lambda *s: torch.randn(*s, generator=g).cuda()
+o, res = r(M, C), r(M, C)
+Wp, W1, W2 = r(C, C) / C**0.5, r(hid, C) / C**0.5, r(C, hid) / hid**0.5
+bp, b1, b2, g2, be2, g3, be3 = r(C), r(hid), r(C), r(C), r(C), r(C), r(C)
+yo = torch.empty(M, C, device="cuda"); ylo = torch.empty(M, C, device="cuda")
+ws = torch.empty(M * 192 * 16 + (1 << 22), dtype=torch.uint8, device="cuda")
+ptrs = [t.data_ptr() for t in (o, res, Wp, bp, g2, be2, W1, b1, W2, b2, g3, be3)]
+for it in range(3):
+    _lib.check(lib.ssr_op_swin_mlp(*ptrs, yo.data_ptr(), ylo.data_ptr(), M, C, heads, hid, ws.data_ptr(), ws.numel(), G.stream()))
+torch.cuda.synchronize()
+print("ok", float(yo.abs().mean()))

@@ -53,8 +53,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t A_BYTES = TC_BM * 128, W_BYTES = BLOCK_N * 128;
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2 : 1, TC_BM, BLOCK_N);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // pointer arithmetic (not an integer round trip) keeps the shared address space visible to the compiler: LDS/STS
+  // instead of generic LD/ST for every staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smA = smem;
   uint8_t* smW = smem + kStages * A_BYTES;
   float* stage_all = reinterpret_cast<float*>(smem + kStages * (A_BYTES + W_BYTES));

@@ -578,6 +578,35 @@ __global__ void pack_rows_kernel(const float* in, int rows, int cols, void* out,
   const long long r = idx / ld;
   store_elem(out, (size_t)idx, elem, c < cols ? in[r * cols + c] : 0.0f, rtf32);
 }
+// Fold a LayerNorm affine into the Linear that consumes it (op-level tests; the model does this on the host at
+// pack time): Wf[n][k] = W[n][k] * gamma[k],  bf[n] = b[n] + sum_k W[n][k] * beta[k].
+__global__ void fold_ln_linear_kernel(const float* W, const float* b, const float* gamma, const float* beta, float* Wf, float* bf,
+                                      int N, int K) {
+  const int n = blockIdx.x;
+  float acc = 0.0f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float w = W[(size_t)n * K + k];
+    Wf[(size_t)n * K + k] = w * gamma[k];
+    acc += w * beta[k];
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = b[n];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    bf[n] = t;
+  }
+}
+int launch_fold_ln_linear(const float* W, const float* b, const float* gamma, const float* beta, float* Wf, float* bf, int N, int K,
+                          cudaStream_t s) {
+  fold_ln_linear_kernel<<<N, 128, 0, s>>>(W, b, gamma, beta, Wf, bf, N, K);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 int launch_pack_rows(const float* in, int rows, int cols, void* out, int ld, int elem, int rtf32, cudaStream_t s) {
   const long long total = (long long)rows * ld;
   pack_rows_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(in, rows, cols, out, ld, elem, rtf32);

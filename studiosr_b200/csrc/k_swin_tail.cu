@@ -1,7 +1,7 @@
 // Fused tail of a Swin block (bf16, C=180 -> padded 192, hidden 360 -> 384), one persistent kernel:
 //
 //   t'  = o @ Wproj^T + bproj + res                (swinir.py:103,171)    [tcgen05 SS, acc in TMEM]
-//   xn2 = LayerNorm2(t')                           (swinir.py:172)        [epilogue -> smem A operand]
+//   xn2 = (t' - mean) * rstd                       (swinir.py:172; norm2's gamma/beta are folded into W1/b1 at pack time)
 //   h   = GELU(xn2 @ W1^T + b1)                    (common.py:185-186)    [3 chunks of 128 hidden units]
 //   t'' = t' + h @ W2^T + b2                       (common.py:188, swinir.py:172)
 //   out: t'' (fp32 residual stream), LayerNorm_next(t'') or a bf16 copy of t''
@@ -10,7 +10,7 @@
 //  * h never touches shared memory: the GELU epilogue packs it to bf16 and writes it back over its own fc1
 //    accumulator columns with tcgen05.st; fc2 consumes it as the TMEM A operand of a TS-mode tcgen05.mma.
 //  * Every bulk transfer is TMA.  The fp32 residual arrives in per-warp [32 x 32] SWIZZLE_128B boxes (thread <-> row
-//    reads are bank-conflict free) prefetched two chunks ahead; the outputs leave as per-warp TMA stores from a
+//    reads are bank-conflict free) loaded one tile ahead, as soon as the same per-warp buffers have been drained by the output stores; the outputs leave as per-warp TMA stores from a
 //    swizzled staging box.  No thread ever waits on a global load, and the ragged last tile is clipped by TMA.
 //  * A single producer thread sustains only one wait->issue round per ~500 cycles however deep the ring is, so the
 //    weight stream is split over two producer warps (even / odd ring entries) and the o tile has its own.
@@ -32,10 +32,10 @@ constexpr uint32_t ST_TILE = 16384;           // one [128 rows][128 B] k-block t
 constexpr uint32_t ST_WSLOT = 192 * 128;      // weight ring slot (fc1 entries use 128 rows of it)
 constexpr uint32_t ST_OFF_OX = 0;                                  // 3 tiles: o, later xn2
 constexpr uint32_t ST_OFF_W = ST_OFF_OX + 3 * ST_TILE;             // weight ring
-constexpr uint32_t ST_OFF_IO = ST_OFF_W + ST_WSLOTS * ST_WSLOT;    // per epilogue warp: R0, R1 (residual), S (staging)
+constexpr uint32_t ST_OFF_IO = ST_OFF_W + ST_WSLOTS * ST_WSLOT;    // per epilogue warp: B0, B1, B2 (residual in, outputs out)
 constexpr uint32_t ST_IO_WARP = 3 * 4096;
 constexpr uint32_t ST_OFF_PAR = ST_OFF_IO + 8 * ST_IO_WARP;        // fp32 parameters
-constexpr int ST_NPAR = 192 * 6 + 384;                             // bp b2 g2 be2 g3 be3 | b1
+constexpr int ST_NPAR = 192 * 4 + 384;                             // bp b2 g3 be3 | b1
 constexpr uint32_t ST_OFF_RED = ST_OFF_PAR + ST_NPAR * 4;          // [128][2] float2 cross-half reductions
 constexpr uint32_t ST_OFF_BAR = ST_OFF_RED + 128 * 2 * 8;
 constexpr uint32_t ST_SMEM = ST_OFF_BAR + 512 + 1024;
@@ -51,13 +51,13 @@ enum {  // mbarrier indices
   SB_XFULL,    // [2] fc1 chunk accumulator complete
   SB_HREADY = SB_XFULL + 2,  // [2] h chunk packed into TMEM (8 arrivals)
   SB_YFULL = SB_HREADY + 2,
-  SB_RFULL,    // [8 warps][2] residual chunk landed
-  SB_COUNT = SB_RFULL + 16
+  SB_RFULL,    // [8 warps][3] residual chunk landed
+  SB_COUNT = SB_RFULL + 24
 };
 
 struct TailArgs {
   int M, C, n_tiles;
-  const float *bp, *b1, *b2, *g2, *be2, *g3, *be3;
+  const float *bp, *b1, *b2, *g3, *be3;  // b1 (and W1) carry norm2's affine
   int has_f32;  // store t'' as fp32
   int has_bf;   // store a bf16 tensor: LayerNorm_next(t'') if do_ln else t''
   int do_ln;
@@ -73,29 +73,32 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// GELU(x) = x * Phi(x), Phi(x) ~ 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))): max |err| 1.3e-4 against the erf form
-// (relative 7.5e-4 for x > -3), one MUFU + 7 FMA-pipe instructions.  x^2 is clamped where the fit's x^4 term would
-// turn the polynomial around (|x| > 6: Phi is 0 / 1 to nine digits anyway).
-__device__ __forceinline__ float gelu_tanh3(float x) {
-  const float x2 = fminf(x * x, 36.0f);
-  float p = fmaf(x2, -3.99928615e-04f, 3.74196843e-02f);
-  p = fmaf(p, x2, 7.96738290e-01f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+// GELU(x) = x * Phi(x), Phi(x) ~ 0.5 (1 + tanh(x (c0 + c1 x^2))) with (c0, c1) least-squares fitted to the erf form
+// on [-8, 8]: max |err| 3.1e-4, far inside the bf16 rounding of h.  Two elements per call on the packed fp32x2 pipe:
+// 6 FFMA2-class instructions + 2 MUFU.TANH + 1 pack for a pair.
+__device__ __forceinline__ uint32_t gelu2_bf16(f32x2 x, f32x2 kC0, f32x2 kC1, f32x2 kHalf) {
+  const f32x2 x2 = f2_mul(x, x);
+  const f32x2 u = f2_mul(x, f2_fma(x2, kC1, kC0));
+  float ulo, uhi, tlo, thi;
+  f2_unpack(u, ulo, uhi);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tlo) : "f"(ulo));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(thi) : "f"(uhi));
+  const f32x2 hx = f2_mul(x, kHalf);
+  return f2_to_bf16x2(f2_fma(hx, f2_pack(tlo, thi), hx));
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
 swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWp,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                  const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmResPf,
-                 const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutB, const TailArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+                 const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutB,
+                 const __grid_constant__ CUtensorMap tmOutB2, const TailArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // pointer arithmetic (not an integer round trip) keeps the shared address space visible to the compiler: LDS/STS
+  // instead of generic LD/ST for every staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* par = reinterpret_cast<float*>(smem + ST_OFF_PAR);
-  float *s_bp = par, *s_b2 = par + 192, *s_g2 = par + 384, *s_be2 = par + 576, *s_g3 = par + 768, *s_be3 = par + 960,
-        *s_b1 = par + 1152;
+  float *s_bp = par, *s_b2 = par + 192, *s_g3 = par + 384, *s_be3 = par + 576, *s_b1 = par + 768;
   float2* red = reinterpret_cast<float2*>(smem + ST_OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + SB_COUNT);
@@ -107,8 +110,6 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
   for (int i = threadIdx.x; i < 192; i += ST_THREADS) {
     s_bp[i] = __ldg(a.bp + i);
     s_b2[i] = __ldg(a.b2 + i);
-    s_g2[i] = __ldg(a.g2 + i);
-    s_be2[i] = __ldg(a.be2 + i);
     s_g3[i] = a.g3 ? __ldg(a.g3 + i) : 0.f;
     s_be3[i] = a.be3 ? __ldg(a.be3 + i) : 0.f;
   }
@@ -122,6 +123,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
     prefetch_tmap(&tmResPf);
     prefetch_tmap(&tmOutF);
     prefetch_tmap(&tmOutB);
+    prefetch_tmap(&tmOutB2);
     for (int i = 0; i < SB_COUNT; ++i) {
       const bool epi8 = (i == SB_XNREADY) || (i >= SB_HREADY && i < SB_HREADY + 2);
       mbar_init(bar(i), epi8 ? 8 : 1);
@@ -254,37 +256,36 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint8_t* io = smem + ST_OFF_IO + ew * ST_IO_WARP;  // R0 | R1 | S
     const uint32_t io_s = smem_u32(io);
-    const int rbar = SB_RFULL + ew * 2;
+    const int rbar = SB_RFULL + ew * 3;
     uint32_t n_xfull[2] = {0, 0};
     const float invC = 1.0f / (float)a.C;
     const bool mask_tail = (hf == 1);  // this warp's last chunk holds the padded channels [C, 192)
 
-    // residual chunk q (running index over this CTA's tiles, 3 per tile) lives in R[q % 2]
-    uint32_t q = 0;
-    auto res_issue = [&](uint32_t qq) {  // lane 0 only
-      const int itl = (int)(qq / 3), c = (int)(qq % 3);
-      const long long tile = (long long)blockIdx.x + (long long)itl * gridDim.x;
+    // The warp's three 4 KB boxes B0..B2 carry the residual chunks [32 rows][32 cols] fp32 (SWIZZLE_128B) of the next
+    // tile from the moment the previous tile's output stores have drained them until the projection epilogue.
+    auto res_issue = [&](int c, long long tile) {  // lane 0 only
       if (tile < n_tiles) {
-        const uint32_t b = bar(rbar + (qq & 1));
+        const uint32_t b = bar(rbar + c);
         mbar_expect_tx(b, 4096);
-        tma_load_2d(io_s + (qq & 1) * 4096, &tmRes, b, hf * 96 + c * 32, (int)tile * 128 + quad * 32);
+        tma_load_2d(io_s + c * 4096, &tmRes, b, hf * 96 + c * 32, (int)tile * 128 + quad * 32);
       }
     };
     if (lane == 0) {
-      res_issue(0);
-      res_issue(1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) res_issue(c, blockIdx.x);
     }
 
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)it & 1u;
       const int row0 = tile * 128 + quad * 32;  // first row of this warp's boxes
-
       long long* dbg = (a.dbg && ew == 0 && lane == 0 && it < 32) ? a.dbg + 16 * ((size_t)blockIdx.x * 32 + it) : nullptr;
+      long long* dbg2 = dbg ? dbg + 16 * 148 * 32 : nullptr;  // second region: projection-epilogue detail
+
       // ---------------- projection epilogue: t' = acc + bp + res ; Y <- t' + b2 ; xn2 -> smem ----------------
-      float tv[3][32];
+      f32x2 tv[3][16];  // this thread's 96 values of the row, as (even, odd) column pairs
       if (dbg) dbg[0] = clock64();
-      mbar_wait(bar(SB_PFULL), ph);
+      mbar_wait_warp(bar(SB_PFULL), ph, lane);
       if (dbg) dbg[1] = clock64();
       tc_fence_after();
       {
@@ -292,87 +293,97 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tlane + 192 + hf * 96 + c * 32, raw[c]);
         tmem_wait_ld();
+        if (dbg2) dbg2[0] = clock64();
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tv[c][i] = __uint_as_float(raw[c][i]);
+          for (int i = 0; i < 16; ++i) tv[c][i] = f2_pack_u(raw[c][2 * i], raw[c][2 * i + 1]);
       }
-      float sum = 0.0f, sq = 0.0f;
+      f32x2 sm[4] = {0ull, 0ull, 0ull, 0ull}, sqv[4] = {0ull, 0ull, 0ull, 0ull};  // independent chains: no 96-deep FADD dependency
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int nb = hf * 96 + c * 32;
-        mbar_wait(bar(rbar + (q & 1)), (q >> 1) & 1u);
-        const uint8_t* rb = io + (q & 1) * 4096;
+        mbar_wait_warp(bar(rbar + c), ph, lane);
+        if (dbg2) dbg2[1 + 2 * c] = clock64();
+        const uint8_t* rb = io + c * 4096;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 r = *reinterpret_cast<const float4*>(rb + sw128_off(lane, j));
           const float4 b = *reinterpret_cast<const float4*>(s_bp + nb + 4 * j);
-          tv[c][4 * j + 0] += r.x + b.x;
-          tv[c][4 * j + 1] += r.y + b.y;
-          tv[c][4 * j + 2] += r.z + b.z;
-          tv[c][4 * j + 3] += r.w + b.w;
+          tv[c][2 * j] = f2_add(tv[c][2 * j], f2_add(f2_pack(r.x, r.y), f2_pack(b.x, b.y)));
+          tv[c][2 * j + 1] = f2_add(tv[c][2 * j + 1], f2_add(f2_pack(r.z, r.w), f2_pack(b.z, b.w)));
         }
-        __syncwarp();
-        if (lane == 0) res_issue(q + 2);  // refill this buffer two chunks ahead
-        ++q;
-        if (c == 2 && mask_tail) {
+        if (dbg2) dbg2[2 + 2 * c] = clock64();
+        if (c == 2 && mask_tail) {  // padded channels stay exact zeros
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i >= a.C) tv[c][i] = 0.0f;
+          for (int i = 0; i < 16; ++i) {
+            float lo, hi;
+            f2_unpack(tv[c][i], lo, hi);
+            tv[c][i] = f2_pack(nb + 2 * i < a.C ? lo : 0.0f, nb + 2 * i + 1 < a.C ? hi : 0.0f);
+          }
+        }
+        // Y = t' + b2: fc2 accumulates on top of the residual
+        {
+          uint32_t y[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = *reinterpret_cast<const float4*>(s_b2 + nb + 4 * j);
+            f2_unpack_u(f2_add(tv[c][2 * j], f2_pack(b.x, b.y)), y[4 * j], y[4 * j + 1]);
+            f2_unpack_u(f2_add(tv[c][2 * j + 1], f2_pack(b.z, b.w)), y[4 * j + 2], y[4 * j + 3]);
+          }
+          tmem_st32_u32(tlane + nb, y);
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          sum += tv[c][i];
-          sq = fmaf(tv[c][i], tv[c][i], sq);
+        for (int i = 0; i < 16; ++i) {
+          sm[i & 3] = f2_add(sm[i & 3], tv[c][i]);
+          sqv[i & 3] = f2_fma(tv[c][i], tv[c][i], sqv[i & 3]);
         }
       }
       if (dbg) dbg[2] = clock64();
-      red[row * 2 + hf] = make_float2(sum, sq);
-      // Y = t' + b2: fc2 accumulates on top of the residual (issued before the exchange so it overlaps the barrier)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int nb = hf * 96 + c * 32;
-        float y[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = tv[c][i] + s_b2[nb + i];
-        tmem_st32(tlane + nb, y);
-      }
+      red[row * 2 + hf] = make_float2(f2_hsum(f2_add(f2_add(sm[0], sm[1]), f2_add(sm[2], sm[3]))),
+                                      f2_hsum(f2_add(f2_add(sqv[0], sqv[1]), f2_add(sqv[2], sqv[3]))));
       named_bar_sync(1 + quad, 64);
       {
         const float2 r0 = red[row * 2], r1 = red[row * 2 + 1];
         const float mean = (r0.x + r1.x) * invC;
         const float var = fmaxf((r0.y + r1.y) * invC - mean * mean, 0.0f);
         const float rstd = rsqrtf(var + a.eps);
+        const f32x2 sc2 = f2_splat(rstd), sh2 = f2_splat(-mean * rstd);
         // the projection MMAs completed before SB_PFULL fired, so the o tile is dead: overwrite it with xn2 in the
-        // SWIZZLE_128B K-major layout TMA would have produced
+        // SWIZZLE_128B K-major layout TMA would have produced.  Padded channels must stay exact zeros.
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int nb = hf * 96 + c * 32;
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
-            float n[8];
+            uint32_t w[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int col = nb + 8 * qd + i;
-              n[i] = fmaf((tv[c][8 * qd + i] - mean) * rstd, s_g2[col], s_be2[col]);  // pads: gamma = beta = 0
+            for (int i = 0; i < 4; ++i) {
+              w[i] = f2_to_bf16x2(f2_fma(tv[c][4 * qd + i], sc2, sh2));
+              if (c == 2 && mask_tail) {
+                const int col = nb + 8 * qd + 2 * i;
+                w[i] = col >= a.C ? 0u : (col + 1 >= a.C ? (w[i] & 0xffffu) : w[i]);
+              }
             }
             const int col = nb + 8 * qd;
             *reinterpret_cast<uint4*>(smem + ST_OFF_OX + (col >> 6) * ST_TILE + sw128_off(row, (col & 63) >> 3)) =
-                make_uint4(pack_bf16x2(n[0], n[1]), pack_bf16x2(n[2], n[3]), pack_bf16x2(n[4], n[5]), pack_bf16x2(n[6], n[7]));
+                make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
-      tc_fence_before();    // orders the tcgen05.st of Y (tmem_st32 waits for completion) before the arrive
+      tmem_wait_st();
+      tc_fence_before();    // orders the tcgen05.st of Y before the arrive
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(SB_XNREADY));
       if (dbg) dbg[3] = clock64();
 
       // ---------------- fc1 chunk epilogues: h = GELU(acc + b1) -> packed bf16 over its own accumulator ----------------
+      const f32x2 kC0 = f2_splat(0.79973199f), kC1 = f2_splat(0.03489978f), kHalf = f2_splat(0.5f);
 #pragma unroll 1
       for (int ch = 0; ch < 3; ++ch) {
         const int b = ch & 1;
-        mbar_wait(bar(SB_XFULL + b), n_xfull[b] & 1u);
+        mbar_wait_warp(bar(SB_XFULL + b), n_xfull[b] & 1u, lane);
         ++n_xfull[b];
         tc_fence_after();
         if (dbg) dbg[4 + 2 * ch] = clock64();
@@ -381,13 +392,15 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
         tmem_ld32_nowait(tx, raw[0]);
         tmem_ld32_nowait(tx + 32, raw[1]);
         tmem_wait_ld();
+        if (dbg2 && ch == 0) dbg2[15] = clock64();
         uint32_t pk[32];
         const float* bb = s_b1 + ch * 128 + hf * 64;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x0 = __uint_as_float(raw[i >> 4][(2 * i) & 31]) + bb[2 * i];
-          const float x1 = __uint_as_float(raw[i >> 4][(2 * i + 1) & 31]) + bb[2 * i + 1];
-          pk[i] = pack_bf16x2(gelu_tanh3(x0), gelu_tanh3(x1));
+        for (int j = 0; j < 16; ++j) {
+          const float4 bv = *reinterpret_cast<const float4*>(bb + 4 * j);
+          const uint32_t* r4 = &raw[j >> 3][(4 * j) & 31];
+          pk[2 * j + 0] = gelu2_bf16(f2_add(f2_pack_u(r4[0], r4[1]), f2_pack(bv.x, bv.y)), kC0, kC1, kHalf);
+          pk[2 * j + 1] = gelu2_bf16(f2_add(f2_pack_u(r4[2], r4[3]), f2_pack(bv.z, bv.w)), kC0, kC1, kHalf);
         }
         tmem_st32_u32(tx, pk);  // K index 2i, 2i+1 of this half -> column i (low half = even k)
         tmem_wait_st();
@@ -398,7 +411,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
       }
 
       // ---------------- final epilogue: t'' = Y ; TMA stores + LayerNorm_next ----------------
-      mbar_wait(bar(SB_YFULL), ph);
+      mbar_wait_warp(bar(SB_YFULL), ph, lane);
       tc_fence_after();
       if (dbg) dbg[10] = clock64();
       {
@@ -406,87 +419,117 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tlane + hf * 96 + c * 32, raw[c]);
         tmem_wait_ld();
+        if (mask_tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (hf * 96 + 64 + i >= a.C) raw[2][i] = 0u;
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tv[c][i] = __uint_as_float(raw[c][i]);
+          for (int i = 0; i < 16; ++i) tv[c][i] = f2_pack_u(raw[c][2 * i], raw[c][2 * i + 1]);
       }
-      if (mask_tail) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (hf * 96 + 64 + i >= a.C) tv[2][i] = 0.0f;
-      }
-      if (a.do_ln) {
-        sum = 0.0f;
-        sq = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            sum += tv[c][i];
-            sq = fmaf(tv[c][i], tv[c][i], sq);
-          }
-        red[row * 2 + hf] = make_float2(sum, sq);
-      }
-      uint8_t* stg = io + 2 * 4096;
-      const uint32_t stg_s = io_s + 2 * 4096;
-      if (a.has_f32) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (lane == 0) bulk_wait_read<0>();  // the previous store has drained the staging box
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + sw128_off(lane, j)) =
-                make_float4(tv[c][4 * j], tv[c][4 * j + 1], tv[c][4 * j + 2], tv[c][4 * j + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOutF, stg_s, hf * 96 + c * 32, row0);
-            bulk_commit();
-          }
-        }
-      }
-      if (a.has_bf) {
-        float mean = 0.0f, rstd = 1.0f;
-        if (a.do_ln) {
-          named_bar_sync(1 + quad, 64);
-          const float2 r0 = red[row * 2], r1 = red[row * 2 + 1];
-          mean = (r0.x + r1.x) * invC;
-          const float var = fmaxf((r0.y + r1.y) * invC - mean * mean, 0.0f);
-          rstd = rsqrtf(var + a.eps);
-          named_bar_sync(1 + quad, 64);  // the partner has read `red` before the next tile's projection epilogue rewrites it
-        }
+      const long long next_tile = (long long)tile + gridDim.x;
+      auto drain = [&]() {  // every store issued so far has read its staging data
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
+      };
+      __syncwarp();  // every lane is done reading the residual boxes (projection epilogue of this tile)
+      if (dbg2) dbg2[8] = clock64();
+      if (a.has_f32) {  // all three fp32 chunks leave in one round: B_c <- chunk c
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int nb = hf * 96 + c * 32;
-          if (c == 2) {  // the first half-box is re-used
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-          }
-          uint8_t* sb = stg + (c & 1) * 2048;
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            float n[8];
+          for (int j = 0; j < 8; ++j) {
+            uint4 w;
+            f2_unpack_u(tv[c][2 * j], w.x, w.y);
+            f2_unpack_u(tv[c][2 * j + 1], w.z, w.w);
+            *reinterpret_cast<uint4*>(io + c * 4096 + sw128_off(lane, j)) = w;
+          }
+        if (dbg2) dbg2[9] = clock64();
+        fence_proxy_async();
+        if (dbg2) dbg2[10] = clock64();
+        __syncwarp();
+        if (dbg2) dbg2[11] = clock64();
+        if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int col = nb + 8 * qd + i;
-              const float v = tv[c][8 * qd + i];
-              n[i] = a.do_ln ? fmaf((v - mean) * rstd, s_g3[col], s_be3[col]) : v;
-            }
-            *reinterpret_cast<uint4*>(sb + sw64_off(lane, qd)) =
-                make_uint4(pack_bf16x2(n[0], n[1]), pack_bf16x2(n[2], n[3]), pack_bf16x2(n[4], n[5]), pack_bf16x2(n[6], n[7]));
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOutB, stg_s + (c & 1) * 2048, nb, row0);
-            bulk_commit();
-          }
+          for (int c = 0; c < 3; ++c) tma_store_2d(&tmOutF, io_s + c * 4096, hf * 96 + c * 32, row0);
+          bulk_commit();
         }
+        if (dbg2) dbg2[12] = clock64();
       }
+      if (dbg) dbg[13] = clock64();
+      float mean = 0.0f, rstd = 1.0f;
+      if (a.do_ln) {  // statistics overlap the stores' drain
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sm[i] = sqv[i] = 0ull;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            sm[i & 3] = f2_add(sm[i & 3], tv[c][i]);
+            sqv[i & 3] = f2_fma(tv[c][i], tv[c][i], sqv[i & 3]);
+          }
+        red[row * 2 + hf] = make_float2(f2_hsum(f2_add(f2_add(sm[0], sm[1]), f2_add(sm[2], sm[3]))),
+                                        f2_hsum(f2_add(f2_add(sqv[0], sqv[1]), f2_add(sqv[2], sqv[3]))));
+        if (dbg2) dbg2[13] = clock64();
+        named_bar_sync(1 + quad, 64);
+        if (dbg2) dbg2[14] = clock64();
+        const float2 r0 = red[row * 2], r1 = red[row * 2 + 1];
+        mean = (r0.x + r1.x) * invC;
+        const float var = fmaxf((r0.y + r1.y) * invC - mean * mean, 0.0f);
+        rstd = rsqrtf(var + a.eps);
+        named_bar_sync(1 + quad, 64);  // the partner has read `red` before the next tile's projection epilogue rewrites it
+      }
+      if (dbg) dbg[14] = clock64();
+      // bf16 word (two columns) i of chunk c: LayerNorm_next or a plain copy
+      const f32x2 sc2 = f2_splat(a.do_ln ? rstd : 1.0f), sh2 = f2_splat(a.do_ln ? -mean * rstd : 0.0f);
+      auto bf_quad = [&](int c, int j) -> uint4 {  // columns [4j*2 .. 4j*2+8) of chunk c -> 16 bytes
+        const int nb = hf * 96 + c * 32;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          f32x2 n0 = f2_fma(tv[c][4 * j + 2 * i], sc2, sh2), n1 = f2_fma(tv[c][4 * j + 2 * i + 1], sc2, sh2);
+          if (a.do_ln) {  // pads: gamma = beta = 0
+            const float4 gv = *reinterpret_cast<const float4*>(s_g3 + nb + 8 * j + 4 * i);
+            const float4 bv = *reinterpret_cast<const float4*>(s_be3 + nb + 8 * j + 4 * i);
+            n0 = f2_fma(n0, f2_pack(gv.x, gv.y), f2_pack(bv.x, bv.y));
+            n1 = f2_fma(n1, f2_pack(gv.z, gv.w), f2_pack(bv.z, bv.w));
+          }
+          w[2 * i] = f2_to_bf16x2(n0);
+          w[2 * i + 1] = f2_to_bf16x2(n1);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+      };
+      drain();  // fp32 boxes have been read
+      if (dbg) dbg[15] = clock64();
+      if (lane == 0) {  // B0, B1 take the next tile's residual right away; B2 stages the bf16 output first
+        res_issue(0, next_tile);
+        res_issue(1, next_tile);
+      }
+      if (a.has_bf) {
+        // columns [0,64) of this half: one [32 x 64] bf16 SWIZZLE_128B box; columns [64,96): a [32 x 32] SWIZZLE_64B box
+        uint8_t* stg = io + 2 * 4096;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(stg + sw128_off(lane, j)) = bf_quad(j >> 2, j & 3);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOutB2, io_s + 2 * 4096, hf * 96, row0);
+          bulk_commit();
+        }
+        drain();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + sw64_off(lane, j)) = bf_quad(2, j);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOutB, io_s + 2 * 4096, hf * 96 + 64, row0);
+          bulk_commit();
+        }
+        drain();
+      }
+      if (lane == 0) res_issue(2, next_tile);
       tc_fence_before();  // Y and the projection columns are re-written by this warp in the next tile (program order)
       if (dbg) dbg[11] = clock64();
     }
@@ -508,7 +551,7 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
             f.QP);
   SSR_CHECK(!(f.out_T && f.out_ln), SSR_E_INVALID, "swin_tail: at most one bf16 output");
   SSR_CHECK(f.ldres % 4 == 0 && (!f.out_f32 || f.ld_f32 % 4 == 0), SSR_E_INVALID, "swin_tail: fp32 leading dims must be 16-byte multiples");
-  CUtensorMap tmO, tmWp, tmW1, tmW2, tmRes, tmResPf, tmOutF, tmOutB;
+  CUtensorMap tmO, tmWp, tmW1, tmW2, tmRes, tmResPf, tmOutF, tmOutB, tmOutB2;
   auto map2d = [&](CUtensorMap* m, const void* base, int elem, int cols, int rows, int ld, int box_c, int box_r, int sw) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t str[1] = {(cuuint64_t)ld * elem};
@@ -528,12 +571,14 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
   if (outb) {
     SSR_CHECK(ldb % 8 == 0, SSR_E_INVALID, "swin_tail: bf16 leading dim must be a 16-byte multiple");
     SSR_TRY(map2d(&tmOutB, outb, 2, 192, f.M, ldb, 32, 32, 64));
+    SSR_TRY(map2d(&tmOutB2, outb, 2, 192, f.M, ldb, 64, 32, 128));
   } else {
     tmOutB = tmO;
+    tmOutB2 = tmO;
   }
   TailArgs a;
   a.M = f.M; a.C = f.C; a.n_tiles = (f.M + 127) / 128;
-  a.bp = f.bp; a.b1 = f.b1; a.b2 = f.b2; a.g2 = f.g2; a.be2 = f.be2; a.g3 = f.g3; a.be3 = f.be3;
+  a.bp = f.bp; a.b1 = f.b1; a.b2 = f.b2; a.g3 = f.g3; a.be3 = f.be3;
   a.has_f32 = f.out_f32 != nullptr;
   a.has_bf = outb != nullptr;
   a.do_ln = f.out_ln != nullptr;
@@ -549,7 +594,7 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
   const double bytes = (double)f.M * f.C * (2 + 4 + (f.out_f32 ? 4 : 0) + (f.out_T ? 2 : 0) + (f.out_ln ? 2 : 0));
   ProfScope prof("swin_tail", flops, bytes, s);
   swin_tail_kernel<<<a.n_tiles < sms ? a.n_tiles : sms, ST_THREADS, ST_SMEM, s>>>(tmO, tmWp, tmW1, tmW2, tmRes, tmResPf, tmOutF,
-                                                                                 tmOutB, a);
+                                                                                 tmOutB, tmOutB2, a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;

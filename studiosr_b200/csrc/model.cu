@@ -259,6 +259,31 @@ static int pack_conv_first(ssr_model* m, const std::string& name, int Cout, size
   return SSR_OK;
 }
 
+// The fused Swin tail kernel (k_swin_tail.cu) is used for bf16 models of the 180/6/360 class.
+static bool fused_tail(const ssr_model* m, const Layer& L) {
+  return m->cfg.precision == SSR_PREC_BF16 && m->CP == 192 && m->HP == 384 && L.QP == 192;
+}
+
+// Re-pack `lin` (already packed un-folded by pack_linear) with the preceding LayerNorm's affine folded in:
+// W'[n][k] = W[n][k] * gamma[k], b'[n] = b[n] + sum_k W[n][k] * beta[k]; the kernel then only normalises.
+static int fold_norm_into_linear(ssr_model* m, const std::string& norm, const std::string& lin, int N, int K, int KP, const Lin& out) {
+  const std::vector<float>* W = find_param(m, lin + ".weight", (size_t)N * K);
+  const std::vector<float>* B = find_param(m, lin + ".bias", (size_t)N);
+  const std::vector<float>* g = find_param(m, norm + ".weight", (size_t)K);
+  const std::vector<float>* be = find_param(m, norm + ".bias", (size_t)K);
+  if (!W || !B || !g || !be) return SSR_E_STATE;
+  for (int n = 0; n < N; ++n) {
+    double acc = (*B)[n];
+    for (int k = 0; k < K; ++k) {
+      const float w = (*W)[(size_t)n * K + k];
+      store_w(m, out.w_off, (size_t)n * KP + k, w * (*g)[k]);
+      acc += (double)w * (*be)[k];
+    }
+    reinterpret_cast<float*>(m->host_arena.data() + out.b_off)[n] = (float)acc;
+  }
+  return SSR_OK;
+}
+
 static int finalize_swinir(ssr_model* m) {
   const ssr_model_config& c = m->cfg;
   SSR_CHECK(c.n_colors == 3, SSR_E_INVALID, "n_colors must be 3");
@@ -311,6 +336,7 @@ static int finalize_swinir(ssr_model* m) {
       const int HID = m->HID;
       auto ident_h = [=](int k) { return k < HID ? k : -1; };
       SSR_TRY(pack_linear(m, p + ".mlp.fc1", HID, C, m->HP, m->CP, ident_h, ident_c, one, &B.fc1));
+      if (fused_tail(m, L)) SSR_TRY(fold_norm_into_linear(m, p + ".norm2", p + ".mlp.fc1", HID, C, m->CP, B.fc1));
       SSR_TRY(pack_linear(m, p + ".mlp.fc2", C, HID, m->CP, m->HP, ident_c, ident_h, one, &B.fc2));
       // relative position bias table [(2ws-1)^2][heads] -> [heads][(2ws-1)^2]
       const std::vector<float>* T = find_param(m, p + ".attn.relative_position_bias_table", (size_t)nb * heads);
@@ -631,11 +657,10 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
   }
   SSR_CUDA(cudaMemsetAsync(W.o, 0, (size_t)T * m->QPmax * e, s));
   const int nL = (int)m->layers.size();
-  static const bool no_fused = getenv("STUDIOSR_B200_NO_FUSED_MLP") != nullptr;
   for (int li = 0; li < nL; ++li) {
     const Layer& L = m->layers[li];
     const int depth = (int)L.blocks.size();
-    const bool fused_mlp = !no_fused && c.precision == SSR_PREC_BF16 && CP == 192 && m->HP == 384 && L.QP == 192;
+    const bool fused_mlp = fused_tail(m, L);
     for (int bi = 0; bi < depth; ++bi) {
       const Block& blk = L.blocks[bi];
       {  // qkv projection (swinir.py:80); q scale folded into the packed weights
@@ -672,7 +697,6 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
         f.o = W.o; f.ld_o = L.QP; f.M = T; f.C = m->C; f.Hid = m->HID; f.CP = CP; f.HP = m->HP; f.QP = L.QP;
         f.Wp = m->arena + blk.proj.w_off; f.W1 = m->arena + blk.fc1.w_off; f.W2 = m->arena + blk.fc2.w_off;
         f.bp = m->dev<float>(blk.proj.b_off); f.b1 = m->dev<float>(blk.fc1.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
-        f.g2 = m->dev<float>(blk.norm2.g_off); f.be2 = m->dev<float>(blk.norm2.b_off);
         f.res = bi == 0 ? W.g : W.t; f.ldres = CP;
         f.eps = 1e-5f;
         if (bi + 1 < depth) {

@@ -176,32 +176,32 @@ int ssr_op_swin_mlp(const float* o, const float* res, const float* Wp, const flo
   float* vec = (float*)c.take((size_t)(6 * CP + HP) * 4);
   float* yp = (float*)c.take((size_t)M * CP * 4);
   void* ylp = c.take((size_t)M * CP * 2);
-  float* wtmp = (float*)c.take((size_t)CP * QP * 4);
-  SSR_CHECK(wtmp, SSR_E_WORKSPACE, "ssr_op_swin_mlp: workspace too small (%zu B)", workspace_bytes);
+  float* w1f = (float*)c.take((size_t)hidden * C * 4);
+  float* b1f = (float*)c.take((size_t)hidden * 4);
+  SSR_CHECK(b1f, SSR_E_WORKSPACE, "ssr_op_swin_mlp: workspace too small (%zu B)", workspace_bytes);
+  SSR_CHECK(g2 && be2 && b1, SSR_E_INVALID, "ssr_op_swin_mlp: norm2 / fc1 parameters missing");
+  SSR_TRY(launch_fold_ln_linear(W1, b1, g2, be2, w1f, b1f, hidden, C, s));  // norm2's affine rides in fc1
   SSR_TRY(launch_pack_heads(o, op, M, heads, d, DP, QP, 2, 0, s));
   SSR_TRY(launch_pack_rows(res, M, C, rp, CP, 4, 0, s));
   // Wproj [C][C]: remap the K index to the padded head layout (row by row = "M" = C rows), zero-pad rows to CP
   SSR_CUDA(cudaMemsetAsync(wp, 0, (size_t)CP * QP * 2, s));
   SSR_TRY(launch_pack_heads(Wp, wp, C, heads, d, DP, QP, 2, 0, s));
   SSR_CUDA(cudaMemsetAsync(w1, 0, (size_t)HP * CP * 2, s));
-  SSR_TRY(launch_pack_rows(W1, hidden, C, w1, CP, 2, 0, s));
+  SSR_TRY(launch_pack_rows(w1f, hidden, C, w1, CP, 2, 0, s));
   SSR_CUDA(cudaMemsetAsync(w2, 0, (size_t)CP * HP * 2, s));
   SSR_TRY(launch_pack_rows(W2, C, hidden, w2, HP, 2, 0, s));
-  float *vbp = vec, *vb2 = vec + CP, *vg2 = vec + 2 * CP, *vbe2 = vec + 3 * CP, *vg3 = vec + 4 * CP, *vbe3 = vec + 5 * CP,
-        *vb1 = vec + 6 * CP;
+  float *vbp = vec, *vb2 = vec + CP, *vg3 = vec + 4 * CP, *vbe3 = vec + 5 * CP, *vb1 = vec + 6 * CP;
   SSR_TRY(launch_pack_rows(bp, 1, C, vbp, CP, 4, 0, s));
   SSR_TRY(launch_pack_rows(b2, 1, C, vb2, CP, 4, 0, s));
-  SSR_TRY(launch_pack_rows(g2, 1, C, vg2, CP, 4, 0, s));
-  SSR_TRY(launch_pack_rows(be2, 1, C, vbe2, CP, 4, 0, s));
   if (g3) {
     SSR_TRY(launch_pack_rows(g3, 1, C, vg3, CP, 4, 0, s));
     SSR_TRY(launch_pack_rows(be3, 1, C, vbe3, CP, 4, 0, s));
   }
-  SSR_TRY(launch_pack_rows(b1, 1, hidden, vb1, HP, 4, 0, s));
+  SSR_TRY(launch_pack_rows(b1f, 1, hidden, vb1, HP, 4, 0, s));
   MlpFusedArgs f;
   memset(&f, 0, sizeof(f));
   f.o = op; f.ld_o = QP; f.M = M; f.C = C; f.Hid = hidden; f.CP = CP; f.HP = HP; f.QP = QP;
-  f.Wp = wp; f.W1 = w1; f.W2 = w2; f.bp = vbp; f.b1 = vb1; f.b2 = vb2; f.g2 = vg2; f.be2 = vbe2;
+  f.Wp = wp; f.W1 = w1; f.W2 = w2; f.bp = vbp; f.b1 = vb1; f.b2 = vb2;
   f.res = rp; f.ldres = CP; f.out_f32 = yp; f.ld_f32 = CP; f.eps = 1e-5f;
   if (g3) {
     f.g3 = vg3; f.be3 = vbe3; f.out_ln = ylp; f.ld_ln = CP;

@@ -161,13 +161,14 @@ struct BlendArgs {
   float u8_scale;
 };
 
-// fused proj + residual + LN2 + fc1 + GELU + fc2 + residual (+ LN_next) of one Swin block (bf16, padded 192/384)
+// fused proj + residual + LN2 + fc1 + GELU + fc2 + residual (+ LN_next) of one Swin block (bf16, padded 192/384).
+// LN2's affine is NOT applied by the kernel: W1 / b1 must carry it (W1[n][k] * gamma2[k], b1 + W1 beta2).
 struct MlpFusedArgs {
   const void* o;  // bf16 [M][ld_o] attention output in the padded head layout
   int ld_o;
   int M, C, Hid, CP, HP, QP;
   const void *Wp, *W1, *W2;  // packed bf16 [CP][QP], [HP][CP], [CP][HP]
-  const float *bp, *b1, *b2, *g2, *be2, *g3, *be3;  // padded fp32 vectors (g3/be3 may be null)
+  const float *bp, *b1, *b2, *g3, *be3;  // padded fp32 vectors (g3/be3 may be null)
   const float* res;
   int ldres;
   float* out_f32;
@@ -179,6 +180,8 @@ struct MlpFusedArgs {
   float eps;
 };
 int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t s);
+int launch_fold_ln_linear(const float* W, const float* b, const float* gamma, const float* beta, float* Wf, float* bf, int N, int K,
+                          cudaStream_t s);
 int launch_pack_heads(const float* in, void* out, int M, int heads, int d, int DP, int ld, int elem, int round_tf32,
                       cudaStream_t s);
 

@@ -21,24 +21,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (prompt wake-up) or the
+// hint expires, instead of spinning.  A spinning waiter is not free: ncu showed the old loop (try_wait + clock64 +
+// branch) taking 45 % of all issued warp instructions of the fused kernels and, through CS2R, half of the XU pipe
+// that MUFU.TANH needs.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must trap (-> CUDA error on the host), never hang the GPU box.
+// Bounded wait: a pipeline bug must trap (-> CUDA error on the host), never hang the GPU box.  The clock is only
+// consulted once every 256 failed (i.e. timed-out) attempts.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if ((++spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 8000000000LL) __trap();
+    }
   }
+}
+// whole-warp wait: one lane polls, the warp re-converges behind it (32x less barrier traffic, one wake-up)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -188,6 +203,52 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // instruction descriptor: D fp32, A/B format (1 = bf16, 2 = tf32), both K-major, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): two lanes per issued instruction.  The fused
+// epilogues are issue-bound, not FMA-pipe bound, so this halves their cost. ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_pack_u(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 a, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+__device__ __forceinline__ void f2_unpack_u(f32x2 a, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(a));
+}
+__device__ __forceinline__ f32x2 f2_splat(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 a) {
+  float lo, hi;
+  f2_unpack(a, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float f2_hsum(f32x2 a) {
+  float lo, hi;
+  f2_unpack(a, lo, hi);
+  return lo + hi;
 }
 
 constexpr int TC_STAGE_ROW = 36;                     // floats per staging row (32 + 4 pad: conflict-free 16 B access)
