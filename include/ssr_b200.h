@@ -168,6 +168,11 @@ int ssr_op_swin_mlp(const float* o, const float* res, const float* Wp, const flo
 int ssr_op_window_attention(int precision, const float* qkv, const float* bias_table, float* o, int B, int H, int W,
                             int C, int heads, int ws, int shift, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* Fused qkv projection + (shifted-)window attention of a SwinTransformerBlock (swinir.py:78-102 and 154-168 without
+ * the output projection), bf16 tensor-core path: xn [B,H,W,C] (the LayerNorm1 output) -> o [B,H,W,C]; Wqkv [3C,C],
+ * bqkv [3C], bias_table [225, heads] in the reference's layouts; 8x8 windows, shift 0 or 4, C=180 / 6 heads class. */
+int ssr_op_swin_attn(const float* xn, const float* Wqkv, const float* bqkv, const float* bias_table, float* o, int B, int H,
+                     int W, int C, int heads, int shift, void* workspace, size_t workspace_bytes, void* stream);
 size_t ssr_op_workspace_bytes(int64_t max_elems);
 
 #ifdef __cplusplus

@@ -215,6 +215,89 @@ def mlp_fused():
     _swin_mlp(148 * 128 * 3 + 77, True)
 
 
+def _attn_fused(B, H, W, shift, C=180, heads=6):
+    import torch
+
+    from oracle import sr_oracle as O
+    from studiosr_b200 import _lib
+    from tests import gpu_util as G
+
+    lib = _lib.load()
+    ws, d = 8, C // heads
+    g = torch.Generator().manual_seed(B + H + W + shift)
+    xn = torch.randn(B, H, W, C, generator=g)
+    Wq = torch.randn(3 * C, C, generator=g) / C**0.5
+    bq = torch.randn(3 * C, generator=g) * 0.2
+    table = torch.randn(225, heads, generator=g) * 0.5
+    qkv = xn @ Wq.t() + bq
+    q = torch.roll(qkv, (-shift, -shift), (1, 2)) if shift else qkv
+    qw = O.to_windows(q, ws).reshape(-1, ws * ws, 3, heads, d)
+    Q = qw[:, :, 0].transpose(1, 2) * d**-0.5
+    K = qw[:, :, 1].transpose(1, 2)
+    V = qw[:, :, 2].transpose(1, 2)
+    s_ = Q @ K.transpose(-1, -2) + O.rel_pos_bias(table, ws)[None]
+    mask = O.shift_mask(H, W, ws, shift, torch.float32)
+    if mask is not None:
+        nW = mask.shape[0]
+        s_ = (s_.reshape(B, nW, heads, 64, 64) + mask[None, :, None]).reshape(-1, heads, 64, 64)
+    o = (torch.softmax(s_, -1) @ V).transpose(1, 2).reshape(-1, 64, C)
+    o = O.from_windows(o, ws, B, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    y = torch.empty(B, H, W, C, device="cuda")
+    wsb = torch.empty(B * H * W * 192 * 8 + (1 << 22), dtype=torch.uint8, device="cuda")
+    args = [t.cuda() for t in (xn, Wq, bq, table)]
+    _lib.check(lib.ssr_op_swin_attn(*[t.data_ptr() for t in args], y.data_ptr(), B, H, W, C, heads, shift, wsb.data_ptr(),
+                                    wsb.numel(), G.stream()))
+    torch.cuda.synchronize()
+    _stats(f"swin_attn fused B{B} {H}x{W} shift{shift}", y.reshape(-1, C), o.reshape(-1, C))
+
+
+@check
+def attn_fused_small():
+    _attn_fused(1, 8, 16, 0)
+
+
+@check
+def attn_fused():
+    _attn_fused(1, 16, 24, 0)
+    _attn_fused(2, 16, 24, 4)
+    _attn_fused(3, 8, 8, 4)
+    _attn_fused(1, 72, 72, 4)
+    _attn_fused(5, 72, 72, 0)
+
+
+@check
+def attn_fused_odd():
+    _attn_fused(1, 72, 72, 0)
+    _attn_fused(1, 24, 24, 0)
+    _attn_fused(1, 24, 24, 4)
+
+
+@check
+def model_cfg1():
+    import json, os
+    import numpy as np
+    import torch
+
+    from oracle import synth
+    from studiosr_b200.models import SwinIR
+
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "meta.json")))["cases"]["swinir_full_x4_eval_cfg1"]
+    cfg = meta["cfg"]
+    kw = {k: cfg[k] for k in ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size", "mlp_ratio", "upsampler")}
+    m = SwinIR(drop_path_rate=0.0, **kw)
+    m.load_state_dict(synth.swinir_weights(cfg, meta["wseed"]), strict=True)
+    m = m.cuda().eval()
+    m.precision = "bf16"
+    x = synth.image_batch(meta["shape"], meta["xseed"]).cuda()
+    ref = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "swinir_full_x4_eval_cfg1.npz"))["y"])
+    for rep in range(3):
+        with torch.no_grad():
+            y = m(x).float().cpu()
+        print("rep", rep, "nan", int(torch.isnan(y).sum()), "max err", float((y - ref).abs().nan_to_num(0).max()))
+
+
 @check
 def model_tiny():
     import torch

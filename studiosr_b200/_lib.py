@@ -55,6 +55,7 @@ SYMBOLS = {
     "ssr_op_swin_mlp": (c_int, [c_void_p] * 14 + [c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ssr_op_window_attention": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_int, c_void_p, c_size_t, c_void_p]),
+    "ssr_op_swin_attn": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ssr_op_workspace_bytes": (c_size_t, [c_int64]),
 }
 

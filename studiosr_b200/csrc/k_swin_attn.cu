@@ -1,0 +1,469 @@
+// Fused (shifted-)window attention of a Swin block (bf16, 8x8 windows, head_dim <= 32 padded to 32, C padded to 192):
+//
+//   qkv = xn @ Wqkv^T + b                  (swinir.py:80)            [tcgen05 SS, N = 192 per head pair]
+//   s   = q k^T * d^-1/2 + rel_pos_bias (+ shift mask)  (swinir.py:83-95)  [tcgen05 SS, scores in TMEM]
+//   p   = softmax(s)                       (swinir.py:97)            [registers; P written back over S as bf16]
+//   o   = p v                              (swinir.py:100)           [tcgen05 TS: A = P from TMEM, B = V MN-major]
+//
+// torch.roll, window_partition and window_reverse (swinir.py:154-168, common.py:236-247) are TMA tile addressing:
+// one work item is two windows = 128 tokens; every window is fetched as two [8 rows x 4 px x 64 ch] boxes (four when it
+// wraps around the bottom edge of the cyclically shifted image) straight out of the pixel-ordered NHWC activation, and
+// the result leaves through the same boxes.  That makes the token order inside a window
+//   r = (tx / 4) * 32 + ty * 4 + tx % 4
+// which only the (host-permuted) bias table and the mask have to know about.  The shift mask is -100 on whole 16-column
+// groups of that order (the 4x4 quadrants of the window), so it costs one predicated add per group.
+//
+// Work per item is software-pipelined over the three head pairs g: while the epilogue warps run the softmax of pair g
+// the tensor core already computes the QKV projection of pair g+1.  q is pre-scaled by d^-1/2 * log2(e) and the bias
+// table by log2(e) at pack time, so the softmax is a bare ex2.
+//
+// TMEM (512 columns): [0,192) QKV accumulator of the current pair (q h0 h1 | k h0 h1 | v h0 h1, 32 each);
+// [192,320) / [320,448) scores of head 0 / 1 of the pair over all 128 keys of the item (only the own window's 64 are
+// read), overwritten in place by P (packed bf16: 64 columns, the other window's half zeroed = block-diagonal P);
+// [448,512) O of the pair.
+// Warps: 0 = activation loads + output stores, 1,2 = weight producers, 3 = MMA issuer, 4..11 = epilogue
+// (lane quadrant = warp % 4; group = (warp - 4) / 4: column half in the QKV epilogue, head of the pair afterwards).
+#include "ssr_tc.cuh"
+
+namespace ssr {
+
+constexpr int SA_THREADS = 384;
+constexpr uint32_t SA_TILE = 16384;
+constexpr uint32_t SA_WSLOT = 192 * 128;
+constexpr int SA_WSLOTS = 2;
+constexpr uint32_t SA_OFF_XN = 0;                                  // 3 k-block tiles of the LayerNorm-ed input
+constexpr uint32_t SA_OFF_W = SA_OFF_XN + 3 * SA_TILE;             // weight ring
+constexpr uint32_t SA_OFF_Q = SA_OFF_W + SA_WSLOTS * SA_WSLOT;     // [128][64] bf16 SW128: q of the pair
+constexpr uint32_t SA_OFF_K = SA_OFF_Q + SA_TILE;                  // [128][64] bf16 SW128: k of the pair
+constexpr uint32_t SA_OFF_V = SA_OFF_K + SA_TILE;                  // 2 x [128 tokens][32] bf16 SW64 (MN-major B operand)
+constexpr uint32_t SA_OFF_BIAS = SA_OFF_V + SA_TILE;               // [6][64][64] bf16 relative-position bias
+constexpr uint32_t SA_BIAS_BYTES = 6 * 64 * 128;
+constexpr uint32_t SA_OFF_OST = SA_OFF_BIAS + SA_BIAS_BYTES;       // [128][64] bf16 SW128 output staging
+constexpr uint32_t SA_OFF_PAR = SA_OFF_OST + SA_TILE;              // fp32 qkv bias [3][192]
+constexpr uint32_t SA_OFF_BAR = SA_OFF_PAR + 3 * 192 * 4;
+constexpr uint32_t SA_SMEM = SA_OFF_BAR + 256 + 1024;
+static_assert(SA_SMEM <= 232448, "fused attention kernel exceeds the 227 KB shared-memory limit");
+
+enum {
+  AB_WFULL = 0,                      // [2]
+  AB_WEMPTY = AB_WFULL + SA_WSLOTS,  // [2]
+  AB_XNFULL = AB_WEMPTY + SA_WSLOTS,
+  AB_XNEMPTY,
+  AB_QKVFULL,   // accumulator of pair g complete
+  AB_OPREADY,   // q/k/v operands of pair g in smem, accumulator drained (8 arrivals)
+  AB_SFULL,     // [2] scores of head 0/1
+  AB_PREADY = AB_SFULL + 2,  // [2] P of head 0/1 in TMEM (4 arrivals)
+  AB_OFULL = AB_PREADY + 2,  // [2] O of head 0/1
+  AB_OSTAGED = AB_OFULL + 2, // output of pair g staged (8 arrivals)
+  AB_OSTFREE,                // staging drained by the TMA stores
+  AB_COUNT
+};
+
+struct AttnKArgs {
+  const float* bhp;      // [3][192] qkv bias in head-pair order (q part pre-scaled)
+  const uint4* bias_tab;  // [6][64][64] bf16, pi order, 16-byte chunks XOR-swizzled by (row & 7), times log2(e)
+  int B, H, W, shift;
+  int nwx, nwy, n_windows, n_tiles;
+};
+
+__device__ __forceinline__ uint32_t sa_sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t sa_sw64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+// MN-major B operand, SWIZZLE_64B: rows of 64 bytes (32 bf16 of N) per K index, 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+
+struct WinPos {
+  int valid, b, x0, y0, ywrap;
+};
+__device__ __forceinline__ WinPos win_pos(const AttnKArgs& a, int widx) {
+  WinPos p;
+  p.valid = widx < a.n_windows;
+  const int wx = widx % a.nwx, t = widx / a.nwx;
+  const int wy = t % a.nwy;
+  p.b = p.valid ? t / a.nwy : a.B;  // an out-of-range image index makes TMA zero-fill (loads) / drop (stores) the box
+  p.x0 = wx * 8 + a.shift;          // < W: shift < 8 and the last window starts at W - 8 ... the halves wrap separately
+  p.y0 = wy * 8 + a.shift;
+  p.ywrap = p.y0 + 8 > a.H;
+  return p;
+}
+
+__global__ void __launch_bounds__(SA_THREADS, 1)
+swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant__ CUtensorMap tmX4,
+                 const __grid_constant__ CUtensorMap tmO8, const __grid_constant__ CUtensorMap tmO4,
+                 const __grid_constant__ CUtensorMap tmW, const AttnKArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* s_bhp = reinterpret_cast<float*>(smem + SA_OFF_PAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AB_COUNT);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * 192; i += SA_THREADS) s_bhp[i] = __ldg(a.bhp + i);
+  for (int i = threadIdx.x; i < (int)(SA_BIAS_BYTES / 16); i += SA_THREADS)
+    reinterpret_cast<uint4*>(smem + SA_OFF_BIAS)[i] = __ldg(a.bias_tab + i);
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX8);
+    prefetch_tmap(&tmX4);
+    prefetch_tmap(&tmO8);
+    prefetch_tmap(&tmO4);
+    prefetch_tmap(&tmW);
+    for (int i = 0; i < AB_COUNT; ++i) {
+      int cnt = 1;
+      if (i == AB_OPREADY || i == AB_OSTAGED) cnt = 8;
+      if (i == AB_PREADY || i == AB_PREADY + 1) cnt = 4;
+      mbar_init(bar(i), cnt);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 3) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
+  const int G = 3 * my_tiles;                                                               // head-pair steps
+  constexpr uint32_t IDESC_QKV = umma_idesc(1, 128, 192), IDESC_S = umma_idesc(1, 128, 128);
+  constexpr uint32_t IDESC_PV = umma_idesc(1, 128, 32) | (1u << 16);  // B operand MN-major
+  const uint32_t tACC = tmem_base, tS[2] = {tmem_base + 192, tmem_base + 320}, tO = tmem_base + 448;
+
+  if (warp == 0) {
+    // =========================== activation loads + output stores ===========================
+    if (lane == 0) {
+      auto load_item = [&](int it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        mbar_expect_tx(bar(AB_XNFULL), 3 * SA_TILE);
+        for (int w = 0; w < 2; ++w) {
+          const WinPos p = win_pos(a, 2 * tile + w);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int x = (p.x0 + 4 * hh) % a.W;
+            const uint32_t row_off = (uint32_t)(64 * w + 32 * hh) * 128u;
+            for (int kb = 0; kb < 3; ++kb) {
+              const uint32_t dst = sbase + SA_OFF_XN + kb * SA_TILE + row_off;
+              if (!p.ywrap) {
+                tma_load_4d(dst, &tmX8, bar(AB_XNFULL), kb * 64, x, p.y0, p.b);
+              } else {  // rows ty 0..3 at the bottom edge, ty 4..7 wrapped to the top
+                tma_load_4d(dst, &tmX4, bar(AB_XNFULL), kb * 64, x, p.y0, p.b);
+                tma_load_4d(dst + 16 * 128, &tmX4, bar(AB_XNFULL), kb * 64, x, 0, p.b);
+              }
+            }
+          }
+        }
+      };
+      auto store_pair = [&](int it, int hp) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        for (int w = 0; w < 2; ++w) {
+          const WinPos p = win_pos(a, 2 * tile + w);
+          if (!p.valid) continue;
+          for (int hh = 0; hh < 2; ++hh) {
+            const int x = (p.x0 + 4 * hh) % a.W;
+            const uint32_t src = sbase + SA_OFF_OST + (uint32_t)(64 * w + 32 * hh) * 128u;
+            if (!p.ywrap) {
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO8), "r"(src),
+                           "r"(hp * 64), "r"(x), "r"(p.y0), "r"(p.b)
+                           : "memory");
+            } else {
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO4), "r"(src),
+                           "r"(hp * 64), "r"(x), "r"(p.y0), "r"(p.b)
+                           : "memory");
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO4),
+                           "r"(src + 16 * 128), "r"(hp * 64), "r"(x), "r"(0), "r"(p.b)
+                           : "memory");
+            }
+          }
+        }
+        bulk_commit();
+      };
+      if (my_tiles > 0) load_item(0);
+      for (int g = 0; g < G; ++g) {
+        const int it = g / 3, hp = g - 3 * it;
+        mbar_wait(bar(AB_OSTAGED), (uint32_t)g & 1u);
+        store_pair(it, hp);
+        bulk_wait_read<0>();
+        mbar_arrive(bar(AB_OSTFREE));
+        if (hp == 0 && it + 1 < my_tiles) {  // the QKV MMAs of the third pair release the input tile about now
+          mbar_wait(bar(AB_XNEMPTY), (uint32_t)it & 1u);
+          load_item(it + 1);
+        }
+      }
+      bulk_wait_all();
+    }
+  } else if (warp < 3) {
+    // =========================== weight producers (even / odd k-blocks) ===========================
+    if (lane == 0) {
+      for (int e = warp - 1; e < 3 * G; e += 2) {
+        const int g = e / 3, kb = e - 3 * g, hp = g % 3;
+        const int s = e & 1;
+        mbar_wait(bar(AB_WEMPTY + s), (((uint32_t)e >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(bar(AB_WFULL + s), SA_WSLOT);
+        tma_load_2d(sbase + SA_OFF_W + s * SA_WSLOT, &tmW, bar(AB_WFULL + s), kb * 64, hp * 192);
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0 && G > 0) {
+      uint32_t wk = 0;
+      auto proj = [&](int g) {  // QKV accumulator of pair g: [128 x 192] = xn [128 x 192] * Whp[g % 3]^T
+        for (int kb = 0; kb < 3; ++kb) {
+          const int s = wk & 1;
+          mbar_wait(bar(AB_WFULL + s), (wk >> 1) & 1u);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(sbase + SA_OFF_XN + kb * SA_TILE);
+          const uint64_t bdesc = umma_desc_sw128(sbase + SA_OFF_W + s * SA_WSLOT);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma<false>(tACC, adesc + 2 * k, bdesc + 2 * k, IDESC_QKV, (kb | k) ? 1u : 0u);
+          umma_commit(bar(AB_WEMPTY + s));
+          ++wk;
+        }
+        umma_commit(bar(AB_QKVFULL));
+        if (g % 3 == 2) umma_commit(bar(AB_XNEMPTY));  // last reader of this item's input tile
+      };
+      mbar_wait(bar(AB_XNFULL), 0);
+      tc_fence_after();
+      proj(0);
+      for (int g = 0; g < G; ++g) {
+        const uint32_t ph = (uint32_t)g & 1u;
+        mbar_wait(bar(AB_OPREADY), ph);  // q, k, v of pair g staged; accumulator drained
+        tc_fence_after();
+        const uint64_t qd = umma_desc_sw128(sbase + SA_OFF_Q), kd = umma_desc_sw128(sbase + SA_OFF_K);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // S_h = q_h k_h^T over all 128 keys of the item (K = 32: bytes [64h, 64h+64) of a row)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma<false>(tS[h], qd + 4 * h + 2 * k, kd + 4 * h + 2 * k, IDESC_S, k ? 1u : 0u);
+          umma_commit(bar(AB_SFULL + h));
+        }
+        if (g + 1 < G) {  // next pair's projection runs under this pair's softmax
+          if ((g + 1) % 3 == 0) {
+            mbar_wait(bar(AB_XNFULL), (uint32_t)((g + 1) / 3) & 1u);
+            tc_fence_after();
+          }
+          proj(g + 1);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // O_h = P_h v_h: A = P (TMEM, block-diagonal over the two windows), B = V_h MN-major
+          mbar_wait(bar(AB_PREADY + h), ph);
+          tc_fence_after();
+          const uint64_t vd = umma_desc_mn_sw64(sbase + SA_OFF_V + h * 8192);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // 16 keys per step: 8 packed columns of P, 16 rows (1 KB) of V
+            umma_ts(tO + 32 * h, tS[h] + 8 * k, vd + 64 * k, IDESC_PV, k ? 1u : 0u);
+          umma_commit(bar(AB_OFULL + h));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue (8 warps) ===========================
+    const int ew = warp - 4;
+    const int grp = ew >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // token row of the item
+    const int w = row >> 6;            // window of the item (warp-uniform)
+    const int ri = row & 63;           // token index inside the window (pi order)
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint8_t* sQ = smem + SA_OFF_Q;
+    uint8_t* sK = smem + SA_OFF_K;
+    uint8_t* sV = smem + SA_OFF_V;
+    uint8_t* sO = smem + SA_OFF_OST;
+    const uint4* sBias = reinterpret_cast<const uint4*>(smem + SA_OFF_BIAS);
+    constexpr float kMask = -100.0f * 1.4426950408889634f;
+    bool yflag = false, xflag = false;
+
+    for (int g = 0; g < G; ++g) {
+      const uint32_t ph = (uint32_t)g & 1u;
+      const int it = g / 3, hp = g - 3 * it;
+      if (hp == 0 && a.shift > 0) {  // which edges of the shifted image does this thread's window touch?
+        const int widx = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + w;
+        const int wx = widx % a.nwx, wy = (widx / a.nwx) % a.nwy;
+        yflag = wy == a.nwy - 1;
+        xflag = wx == a.nwx - 1;
+      }
+
+      // ---------------- QKV epilogue: + bias, bf16, operand tiles ----------------
+      mbar_wait_warp(bar(AB_QKVFULL), ph, lane);
+      tc_fence_after();
+      {
+        uint32_t raw[3][32];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tlane + grp * 96 + c * 32, raw[c]);
+        tmem_wait_ld();
+        const float* bb = s_bhp + hp * 192 + grp * 96;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16-byte chunk
+            const float4 b0 = *reinterpret_cast<const float4*>(bb + c * 32 + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(bb + c * 32 + 8 * j + 4);
+            const uint32_t* r8 = &raw[c][8 * j];
+            uint4 v;
+            v.x = f2_to_bf16x2(f2_add(f2_pack_u(r8[0], r8[1]), f2_pack(b0.x, b0.y)));
+            v.y = f2_to_bf16x2(f2_add(f2_pack_u(r8[2], r8[3]), f2_pack(b0.z, b0.w)));
+            v.z = f2_to_bf16x2(f2_add(f2_pack_u(r8[4], r8[5]), f2_pack(b1.x, b1.y)));
+            v.w = f2_to_bf16x2(f2_add(f2_pack_u(r8[6], r8[7]), f2_pack(b1.z, b1.w)));
+            const int col = grp * 96 + c * 32 + 8 * j;  // column of the pair's accumulator
+            uint8_t* dst;
+            if (col < 64) dst = sQ + sa_sw128(row, col >> 3);                       // q h0 | h1
+            else if (col < 128) dst = sK + sa_sw128(row, (col - 64) >> 3);          // k h0 | h1
+            else dst = sV + ((col - 128) >> 5) * 8192 + sa_sw64(row, ((col - 128) & 31) >> 3);  // v h0 / h1
+            *reinterpret_cast<uint4*>(dst) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(AB_OPREADY));
+
+      // ---------------- softmax of head `grp` of the pair ----------------
+      const int head = 2 * hp + grp;
+      mbar_wait_warp(bar(AB_SFULL + grp), ph, lane);
+      tc_fence_after();
+      float inv_l;
+      {
+        uint32_t raw[2][32];
+        tmem_ld32_nowait(tlane + (tS[grp] - tmem_base) + 64 * w, raw[0]);
+        tmem_ld32_nowait(tlane + (tS[grp] - tmem_base) + 64 * w + 32, raw[1]);
+        // bias row of this token: 64 bf16 = 8 chunks
+        const uint4* brow = sBias + (head * 64 + ri) * 8;
+        uint4 bq[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bq[c] = brow[c ^ (ri & 7)];
+        tmem_wait_ld();
+        f32x2 s[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t wds[4] = {bq[c].x, bq[c].y, bq[c].z, bq[c].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int p = 4 * c + i;  // pair index: key columns 2p, 2p+1
+            const f32x2 bias2 = f2_pack_u(wds[i] << 16, wds[i] & 0xffff0000u);
+            s[p] = f2_add(f2_pack_u(raw[p >> 4][(2 * p) & 31], raw[p >> 4][(2 * p + 1) & 31]), bias2);
+          }
+        }
+        if (yflag || xflag) {  // shift mask: -100 on the 16-key groups whose quadrant lies across the image seam
+          const int gi = ri >> 4;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const bool m = (xflag && ((gq >> 1) != (gi >> 1))) || (yflag && ((gq & 1) != (gi & 1)));
+            const f32x2 mv = f2_splat(m ? kMask : 0.0f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[8 * gq + i] = f2_add(s[8 * gq + i], mv);
+          }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+          float lo, hi;
+          f2_unpack(s[p], lo, hi);
+          mx = fmaxf(mx, fmaxf(lo, hi));
+        }
+        const f32x2 nm = f2_splat(-mx);
+        f32x2 acc2[2] = {0ull, 0ull};
+        uint32_t pk[32];
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+          float lo, hi;
+          f2_unpack(f2_add(s[p], nm), lo, hi);
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lo) : "f"(lo));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(hi));
+          const f32x2 e2 = f2_pack(lo, hi);
+          acc2[p & 1] = f2_add(acc2[p & 1], e2);
+          pk[p] = f2_to_bf16x2(e2);
+        }
+        inv_l = 1.0f / f2_hsum(f2_add(acc2[0], acc2[1]));
+        // P over the scores: own window's 64 keys -> 32 packed columns, the other window's half zeroed
+        uint32_t zero[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zero[i] = 0u;
+        tmem_st32_u32(tlane + (tS[grp] - tmem_base) + 32 * w, pk);
+        tmem_st32_u32(tlane + (tS[grp] - tmem_base) + 32 * (1 - w), zero);
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(AB_PREADY + grp));
+
+      // ---------------- output of head `grp`: O / l -> bf16 -> staging ----------------
+      mbar_wait_warp(bar(AB_OFULL + grp), ph, lane);
+      tc_fence_after();
+      {
+        uint32_t raw[32];
+        tmem_ld32_nowait(tlane + (tO - tmem_base) + 32 * grp, raw);
+        if (g > 0) mbar_wait_warp(bar(AB_OSTFREE), ((uint32_t)g & 1u) ^ 1u, lane);  // stores of pair g-1 have read the staging
+        tmem_wait_ld();
+        const f32x2 il = f2_splat(inv_l);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 0], raw[8 * j + 1]), il));
+          v.y = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 2], raw[8 * j + 3]), il));
+          v.z = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 4], raw[8 * j + 5]), il));
+          v.w = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 6], raw[8 * j + 7]), il));
+          *reinterpret_cast<uint4*>(sO + sa_sw128(row, 4 * grp + j)) = v;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(AB_OSTAGED));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int launch_swin_attn_fused(const AttnFusedArgs& f, cudaStream_t s) {
+  SSR_CHECK(f.H % 8 == 0 && f.W % 8 == 0, SSR_E_INVALID, "swin_attn: %dx%d not a multiple of the 8x8 window", f.H, f.W);
+  SSR_CHECK(f.shift == 0 || f.shift == 4, SSR_E_INVALID, "swin_attn: shift %d not in {0, 4}", f.shift);
+  SSR_CHECK(f.ld_x == 192 && f.ld_o == 192, SSR_E_INVALID, "swin_attn: leading dims must be 192 (got %d / %d)", f.ld_x, f.ld_o);
+  CUtensorMap tmX8, tmX4, tmO8, tmO4, tmW;
+  auto map4d = [&](CUtensorMap* m, const void* base, int ld, int bh) {
+    cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)f.W, (cuuint64_t)f.H, (cuuint64_t)f.B};
+    cuuint64_t str[3] = {(cuuint64_t)ld * 2, (cuuint64_t)f.W * ld * 2, (cuuint64_t)f.H * f.W * ld * 2};
+    cuuint32_t box[4] = {64, 4, (cuuint32_t)bh, 1};
+    return make_tmap(m, base, 2, 4, dims, str, box, 128);
+  };
+  SSR_TRY(map4d(&tmX8, f.xn, f.ld_x, 8));
+  SSR_TRY(map4d(&tmX4, f.xn, f.ld_x, 4));
+  SSR_TRY(map4d(&tmO8, f.o, f.ld_o, 8));
+  SSR_TRY(map4d(&tmO4, f.o, f.ld_o, 4));
+  {
+    cuuint64_t dims[2] = {192, 576};
+    cuuint64_t str[1] = {192 * 2};
+    cuuint32_t box[2] = {64, 192};
+    SSR_TRY(make_tmap(&tmW, f.Whp, 2, 2, dims, str, box, 128));
+  }
+  AttnKArgs a;
+  a.bhp = f.bhp;
+  a.bias_tab = reinterpret_cast<const uint4*>(f.bias_tab);
+  a.B = f.B; a.H = f.H; a.W = f.W; a.shift = f.shift;
+  a.nwx = f.W / 8; a.nwy = f.H / 8;
+  a.n_windows = f.B * a.nwx * a.nwy;
+  a.n_tiles = (a.n_windows + 1) / 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
+    attr_set = true;
+  }
+  const int sms = num_sms_cached();
+  const double T = (double)f.B * f.H * f.W;
+  const double flops = T * (2.0 * 3 * f.C * f.C + 4.0 * 64 * f.C);  // qkv projection + (q k^T, p v) over 64 keys
+  const double bytes = T * f.C * (2 + 2);
+  ProfScope prof("swin_attn", flops, bytes, s);
+  swin_attn_kernel<<<a.n_tiles < sms ? a.n_tiles : sms, SA_THREADS, SA_SMEM, s>>>(tmX8, tmX4, tmO8, tmO4, tmW, a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+}  // namespace ssr

@@ -88,6 +88,7 @@ struct Block {
   LNp norm1, norm2;
   Lin qkv, proj, fc1, fc2;
   size_t bias_off = 0;  // float [heads][(2ws-1)^2]
+  size_t whp_off = 0, bhp_off = 0, btab_off = 0;  // fused attention kernel operands (k_swin_attn.cu)
 };
 struct Layer {
   std::vector<Block> blocks;
@@ -264,6 +265,11 @@ static bool fused_tail(const ssr_model* m, const Layer& L) {
   return m->cfg.precision == SSR_PREC_BF16 && m->CP == 192 && m->HP == 384 && L.QP == 192;
 }
 
+// The fused QKV + window-attention kernel (k_swin_attn.cu): same class, 6 heads, 8x8 windows.
+static bool fused_attn(const ssr_model* m, const Layer& L) {
+  return fused_tail(m, L) && L.heads == 6 && L.DP == 32 && m->cfg.window_size == 8 && getenv("STUDIOSR_B200_UNFUSED_ATTN") == nullptr;
+}
+
 // Re-pack `lin` (already packed un-folded by pack_linear) with the preceding LayerNorm's affine folded in:
 // W'[n][k] = W[n][k] * gamma[k], b'[n] = b[n] + sum_k W[n][k] * beta[k]; the kernel then only normalises.
 static int fold_norm_into_linear(ssr_model* m, const std::string& norm, const std::string& lin, int N, int K, int KP, const Lin& out) {
@@ -281,6 +287,38 @@ static int fold_norm_into_linear(ssr_model* m, const std::string& norm, const st
     }
     reinterpret_cast<float*>(m->host_arena.data() + out.b_off)[n] = (float)acc;
   }
+  return SSR_OK;
+}
+
+int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* table, int C, int heads, void* Whp, float* bhp,
+                         void* bias_tab) {
+  SSR_CHECK(heads == 6 && C % heads == 0 && C / heads <= 32 && C <= 192, SSR_E_INVALID,
+            "fused attention packing: C=%d heads=%d unsupported", C, heads);
+  const int d = C / heads;
+  const float log2e = 1.4426950408889634f, qs = log2e / sqrtf((float)d);
+  __nv_bfloat16* W = reinterpret_cast<__nv_bfloat16*>(Whp);
+  for (int hp = 0; hp < 3; ++hp)
+    for (int n = 0; n < 192; ++n) {
+      const int sec = n / 64, hh = (n % 64) / 32, j = n % 32, head = 2 * hp + hh;
+      const bool real = j < d;
+      const int src = sec * C + head * d + j;
+      const float sc = sec == 0 ? qs : 1.0f;
+      bhp[hp * 192 + n] = real ? bqkv[src] * sc : 0.0f;
+      for (int k = 0; k < 192; ++k)
+        W[((size_t)hp * 192 + n) * 192 + k] = __float2bfloat16_rn(real && k < C ? Wqkv[(size_t)src * C + k] * sc : 0.0f);
+    }
+  // relative-position bias in the kernel's window-token order r = (tx / 4) * 32 + ty * 4 + tx % 4 (swinir.py:57-67, 92-95)
+  uint8_t* bt = reinterpret_cast<uint8_t*>(bias_tab);
+  for (int hd = 0; hd < heads; ++hd)
+    for (int ri = 0; ri < 64; ++ri) {
+      const int yi = (ri & 31) >> 2, xi = (ri >> 5) * 4 + (ri & 3);
+      for (int rj = 0; rj < 64; ++rj) {
+        const int yj = (rj & 31) >> 2, xj = (rj >> 5) * 4 + (rj & 3);
+        const float v = table[(size_t)((yi - yj + 7) * 15 + (xi - xj + 7)) * heads + hd] * log2e;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        memcpy(bt + (size_t)hd * 8192 + ri * 128 + ((((rj >> 3) ^ (ri & 7))) << 4) + (rj & 7) * 2, &h, 2);
+      }
+    }
   return SSR_OK;
 }
 
@@ -345,6 +383,17 @@ static int finalize_swinir(ssr_model* m) {
       float* bt = reinterpret_cast<float*>(m->host_arena.data() + B.bias_off);
       for (int h = 0; h < heads; ++h)
         for (int i = 0; i < nb; ++i) bt[h * nb + i] = (*T)[(size_t)i * heads + h];
+      if (fused_attn(m, L)) {  // operands of k_swin_attn.cu: head-pair ordered qkv weights, pi-ordered bias table
+        const std::vector<float>* Wq = find_param(m, p + ".attn.qkv.weight", (size_t)3 * C * C);
+        const std::vector<float>* Bq = find_param(m, p + ".attn.qkv.bias", (size_t)3 * C);
+        if (!Wq || !Bq) return SSR_E_STATE;
+        B.whp_off = arena_alloc(m, kAttnWhpBytes);
+        B.bhp_off = arena_alloc(m, kAttnBhpBytes);
+        B.btab_off = arena_alloc(m, kAttnBiasBytes);
+        uint8_t* base = m->host_arena.data();
+        SSR_TRY(pack_attn_fused_host(Wq->data(), Bq->data(), T->data(), C, heads, base + B.whp_off,
+                                     reinterpret_cast<float*>(base + B.bhp_off), base + B.btab_off));
+      }
       L.blocks.push_back(B);
     }
     char nm[64];
@@ -590,6 +639,43 @@ static int run_tail(ssr_model* m, const void* cur, int ch_ld, int B, int Hp, int
   return launch_conv_last(a, s);
 }
 
+// developer diagnostics (STUDIOSR_B200_DEBUG_NAN=1): count non-finite values of an activation buffer after a launch
+__global__ void count_nonfinite_kernel(const void* p, size_t n, int elem, unsigned long long* out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  unsigned long long c = 0;
+  for (; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = elem == 2 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+    if (!isfinite(v)) ++c;
+  }
+  if (c) atomicAdd(out, c);
+}
+static void debug_nonfinite(const char* what, int li, int bi, const void* p, size_t n, int elem, cudaStream_t s) {
+  static const bool on = getenv("STUDIOSR_B200_DEBUG_NAN") != nullptr;
+  if (!on) return;
+  unsigned long long* d;
+  cudaMalloc(&d, 8);
+  cudaMemsetAsync(d, 0, 8, s);
+  count_nonfinite_kernel<<<256, 256, 0, s>>>(p, n, elem, d);
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  fprintf(stderr, "[debug] layer %d block %d %-10s non-finite %llu of %zu (%s)\n", li, bi, what, h, n, cudaGetErrorString(e));
+  cudaFree(d);
+  if (h && elem == 2 && li == 0 && bi == 0) {  // pattern of the first bad buffer: per 32-column group, and the first bad rows
+    std::vector<__nv_bfloat16> hb(n);
+    cudaMemcpy(hb.data(), p, n * 2, cudaMemcpyDeviceToHost);
+    size_t rows = n / 192, colg[6] = {0, 0, 0, 0, 0, 0};
+    int printed = 0;
+    for (size_t r = 0; r < rows; ++r) {
+      int bad = 0;
+      for (int c = 0; c < 192; ++c)
+        if (!isfinite(__bfloat162float(hb[r * 192 + c]))) { ++bad; ++colg[c / 32]; }
+      if (bad && printed < 24) { fprintf(stderr, "   row %zu (y %zu x %zu): %d bad\n", r, r / 72, r % 72, bad); ++printed; }
+    }
+    fprintf(stderr, "   bad per head: %zu %zu %zu %zu %zu %zu\n", colg[0], colg[1], colg[2], colg[3], colg[4], colg[5]);
+  }
+}
+
 static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, int pad_mode,
                           void* ws, size_t ws_bytes, cudaStream_t s) {
   const ssr_model_config& c = m->cfg;
@@ -663,6 +749,22 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
     const bool fused_mlp = fused_tail(m, L);
     for (int bi = 0; bi < depth; ++bi) {
       const Block& blk = L.blocks[bi];
+      if (fused_attn(m, L)) {  // qkv projection + roll + partition + attention + reverse + roll in ONE kernel
+        AttnFusedArgs f;
+        memset(&f, 0, sizeof(f));
+        f.xn = W.xn; f.ld_x = CP; f.o = W.o; f.ld_o = L.QP;
+        f.Whp = m->arena + blk.whp_off; f.bhp = m->dev<float>(blk.bhp_off); f.bias_tab = m->arena + blk.btab_off;
+        f.B = B; f.H = Hp; f.W = Wp; f.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
+        f.C = m->C; f.d = L.d;
+        debug_nonfinite("xn", li, bi, W.xn, (size_t)T * CP, e, s);
+        if (li == 0 && bi == 0) {
+          debug_nonfinite("Whp", li, bi + 100, f.Whp, kAttnWhpBytes / 2, 2, s);
+          debug_nonfinite("bhp", li, bi + 100, f.bhp, kAttnBhpBytes / 4, 4, s);
+          debug_nonfinite("btab", li, bi + 100, f.bias_tab, kAttnBiasBytes / 2, 2, s);
+        }
+        SSR_TRY(launch_swin_attn_fused(f, s));
+        debug_nonfinite("o", li, bi, W.o, (size_t)T * L.QP, e, s);
+      } else {
       {  // qkv projection (swinir.py:80); q scale folded into the packed weights
         GemmArgs g = gemm_base(m, blk.qkv, W.xn, CP, B, Hp, Wp);
         g.out_T = W.qkv;
@@ -691,6 +793,7 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
         else
           SSR_TRY(launch_attn_simt(a, s));
       }
+      }
       if (fused_mlp) {  // proj + res + LN2 + fc1 + GELU + fc2 + res (+ next norm1 | bf16 copy) in ONE kernel
         MlpFusedArgs f;
         memset(&f, 0, sizeof(f));
@@ -707,6 +810,7 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
           f.out_T = W.tb; f.ld_T = CP;
         }
         SSR_TRY(launch_mlp_fused(f, s));
+        debug_nonfinite("t", li, bi, W.t, (size_t)T * CP, 4, s);
         continue;
       }
       {  // proj + residual (swinir.py:103,171) with norm2 fused into the epilogue
@@ -975,6 +1079,20 @@ int ssr_model_finalize(ssr_model_t* m) {
   if (!m->arena) {
     m->arena_bytes = m->host_arena.size();
     SSR_CUDA(cudaMalloc(&m->arena, m->arena_bytes));
+  }
+  if (getenv("STUDIOSR_B200_DEBUG_NAN") && m->cfg.arch == SSR_ARCH_SWINIR && !m->layers.empty() && m->layers[0].blocks[0].whp_off) {
+    const Block& b0 = m->layers[0].blocks[0];
+    auto scan = [&](const char* nm, size_t off, size_t n) {
+      size_t bad = 0, first = 0;
+      for (size_t i = 0; i < n; ++i) {
+        __nv_bfloat16 h;
+        memcpy(&h, m->host_arena.data() + off + 2 * i, 2);
+        if (!isfinite(__bfloat162float(h))) { if (!bad) first = i; ++bad; }
+      }
+      fprintf(stderr, "[debug] finalize: %s at arena+%zu: %zu non-finite of %zu (first at %zu)\n", nm, off, bad, n, first);
+    };
+    scan("Whp", b0.whp_off, kAttnWhpBytes / 2);
+    scan("btab", b0.btab_off, kAttnBiasBytes / 2);
   }
   SSR_CUDA(cudaMemcpy(m->arena, m->host_arena.data(), m->host_arena.size(), cudaMemcpyHostToDevice));
   m->host_arena.clear();

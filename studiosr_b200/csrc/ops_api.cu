@@ -4,6 +4,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "ssr_device.cuh"
 
 namespace ssr {
@@ -246,6 +248,45 @@ int ssr_op_window_attention(int precision, const float* qkv, const float* bias_t
   else
     SSR_TRY(launch_attn_simt(a, s));
   return launch_unpack_heads(op, QP, elem, o, (int)M, heads, d, DP, s);
+}
+
+int ssr_op_swin_attn(const float* xn, const float* Wqkv, const float* bqkv, const float* bias_table, float* o, int B, int H,
+                     int W, int C, int heads, int shift, void* workspace, size_t workspace_bytes, void* stream) {
+  SSR_CHECK(xn && Wqkv && bqkv && bias_table && o && workspace, SSR_E_INVALID, "ssr_op_swin_attn: bad argument");
+  SSR_CHECK(heads == 6 && C % heads == 0 && C / heads <= 32 && C > 128 && C <= 192, SSR_E_INVALID,
+            "ssr_op_swin_attn: only the C=180 / 6 heads class of shapes (C=%d heads=%d)", C, heads);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = C / heads;
+  const size_t M = (size_t)B * H * W;
+  Carve c(workspace, workspace_bytes);
+  void* xp = c.take(M * 192 * 2);
+  void* op = c.take(M * 192 * 2);
+  void* whp = c.take(kAttnWhpBytes);
+  float* bhp = (float*)c.take(kAttnBhpBytes);
+  void* btab = c.take(kAttnBiasBytes);
+  SSR_CHECK(btab, SSR_E_WORKSPACE, "ssr_op_swin_attn: workspace too small (%zu B)", workspace_bytes);
+  // test-only convenience: the operands are packed on the host exactly as ssr_model_finalize does
+  std::vector<float> hW((size_t)3 * C * C), hb((size_t)3 * C), ht((size_t)225 * heads);
+  SSR_CUDA(cudaMemcpyAsync(hW.data(), Wqkv, hW.size() * 4, cudaMemcpyDeviceToHost, s));
+  SSR_CUDA(cudaMemcpyAsync(hb.data(), bqkv, hb.size() * 4, cudaMemcpyDeviceToHost, s));
+  SSR_CUDA(cudaMemcpyAsync(ht.data(), bias_table, ht.size() * 4, cudaMemcpyDeviceToHost, s));
+  SSR_CUDA(cudaStreamSynchronize(s));
+  std::vector<uint8_t> pw(kAttnWhpBytes), pt(kAttnBiasBytes);
+  std::vector<float> pb(kAttnBhpBytes / 4);
+  SSR_TRY(pack_attn_fused_host(hW.data(), hb.data(), ht.data(), C, heads, pw.data(), pb.data(), pt.data()));
+  SSR_CUDA(cudaMemcpyAsync(whp, pw.data(), pw.size(), cudaMemcpyHostToDevice, s));
+  SSR_CUDA(cudaMemcpyAsync(bhp, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, s));
+  SSR_CUDA(cudaMemcpyAsync(btab, pt.data(), pt.size(), cudaMemcpyHostToDevice, s));
+  SSR_TRY(launch_pack_rows(xn, (int)M, C, xp, 192, 2, 0, s));
+  SSR_CUDA(cudaMemsetAsync(op, 0, M * 192 * 2, s));
+  AttnFusedArgs f;
+  memset(&f, 0, sizeof(f));
+  f.xn = xp; f.ld_x = 192; f.o = op; f.ld_o = 192; f.Whp = whp; f.bhp = bhp; f.bias_tab = btab;
+  f.B = B; f.H = H; f.W = W; f.shift = shift; f.C = C; f.d = d;
+  SSR_TRY(launch_swin_attn_fused(f, s));
+  SSR_TRY(launch_unpack_heads(op, 192, 2, o, (int)M, heads, d, 32, s));
+  SSR_CUDA(cudaStreamSynchronize(s));  // the host staging vectors die with this frame
+  return SSR_OK;
 }
 
 }  // extern "C"

@@ -53,3 +53,26 @@ def op_window_attention(prec, qkv, table, heads, ws_, shift):
                                            shift, _p(ws), ws.numel(), stream()))
     torch.cuda.synchronize()
     return o
+
+
+def op_swin_attn(xn, Wqkv, bqkv, table, heads, shift):
+    lib = _lib.load()
+    B, H, W, C = xn.shape
+    o = torch.empty(B, H, W, C, device="cuda")
+    ws = _ws(B * H * W * 192 * 8 + (1 << 22))
+    _lib.check(lib.ssr_op_swin_attn(_p(xn), _p(Wqkv), _p(bqkv), _p(table), _p(o), B, H, W, C, heads, shift, _p(ws),
+                                    ws.numel(), stream()))
+    torch.cuda.synchronize()
+    return o
+
+
+def op_swin_mlp(o, res, Wp, bp, g2, be2, W1, b1, W2, b2, g3, be3, heads, hidden):
+    lib = _lib.load()
+    M, C = o.shape
+    y = torch.empty(M, C, device="cuda")
+    y2 = torch.empty(M, C, device="cuda")
+    ws = _ws(M * 192 * 16 + (1 << 22))
+    _lib.check(lib.ssr_op_swin_mlp(_p(o), _p(res), _p(Wp), _p(bp), _p(g2), _p(be2), _p(W1), _p(b1), _p(W2), _p(b2), _p(g3),
+                                   _p(be3), _p(y), _p(y2), M, C, heads, hidden, _p(ws), ws.numel(), stream()))
+    torch.cuda.synchronize()
+    return y, y2

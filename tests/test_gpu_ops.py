@@ -112,3 +112,61 @@ def test_window_attention(prec, B, H, W, C, heads, shift):
         o = torch.roll(o, (shift, shift), (1, 2))
     y = G.op_window_attention(prec, qkv.cuda(), table.cuda(), heads, ws, shift)
     _close(y, o, prec, "window attention")
+
+
+def _attention_oracle(qkv, table, B, H, W, C, heads, shift):
+    """roll -> windows -> attention core -> reverse -> roll (swinir.py:83-102, 154-168), fp32."""
+    ws, d = 8, C // heads
+    q = torch.roll(qkv, (-shift, -shift), (1, 2)) if shift else qkv
+    qw = O.to_windows(q, ws).reshape(-1, ws * ws, 3, heads, d)
+    Q = qw[:, :, 0].transpose(1, 2) * d**-0.5
+    K = qw[:, :, 1].transpose(1, 2)
+    V = qw[:, :, 2].transpose(1, 2)
+    s = Q @ K.transpose(-1, -2) + O.rel_pos_bias(table, ws)[None]
+    mask = O.shift_mask(H, W, ws, shift, torch.float32)
+    nW = mask.shape[0]
+    s = (s.reshape(B, nW, heads, 64, 64) + mask[None, :, None]).reshape(-1, heads, 64, 64)
+    o = (torch.softmax(s, -1) @ V).transpose(1, 2).reshape(-1, 64, C)
+    o = O.from_windows(o, ws, B, H, W)
+    return torch.roll(o, (shift, shift), (1, 2)) if shift else o
+
+
+@pytest.mark.parametrize("B,H,W,shift", [
+    (1, 72, 72, 0),   # cfg1: 81 windows -> the last work item holds a single window
+    (1, 72, 72, 4),   # shifted: seam windows on the bottom row / right column / corner
+    (2, 16, 24, 4),
+    (3, 8, 8, 4),     # one window per image: every window touches both seams
+    (5, 24, 16, 0),
+])
+def test_swin_attn_fused(B, H, W, shift):
+    """k_swin_attn.cu: qkv projection + (shifted-)window attention in one tcgen05 kernel, bf16."""
+    C, heads = 180, 6
+    g = _gen(B + H + W + shift)
+    xn = torch.randn(B, H, W, C, generator=g)
+    Wq = torch.randn(3 * C, C, generator=g) / C**0.5
+    bq = torch.randn(3 * C, generator=g) * 0.2
+    table = torch.randn(225, heads, generator=g) * 0.5
+    ref = _attention_oracle(xn @ Wq.t() + bq, table, B, H, W, C, heads, shift)
+    y = G.op_swin_attn(xn.cuda(), Wq.cuda(), bq.cuda(), table.cuda(), heads, shift)
+    _close(y, ref, "bf16", "fused window attention")
+
+
+@pytest.mark.parametrize("M,with_ln", [(128, True), (300, True), (5184, False), (148 * 128 + 77, True)])
+def test_swin_tail_fused(M, with_ln):
+    """k_swin_tail.cu: proj + residual + LN2 + fc1 + GELU + fc2 + residual (+ next LN) in one tcgen05 kernel, bf16."""
+    C, heads, hid = 180, 6, 360
+    g = _gen(M)
+    r = lambda *s: torch.randn(*s, generator=g)
+    o, res = r(M, C), r(M, C)
+    Wp, W1, W2 = r(C, C) / C**0.5, r(hid, C) / C**0.5, r(C, hid) / hid**0.5
+    bp, b1, b2 = r(C) * 0.1, r(hid) * 0.1, r(C) * 0.1
+    g2, be2, g3, be3 = 1 + 0.1 * r(C), 0.1 * r(C), 1 + 0.1 * r(C), 0.1 * r(C)
+    t1 = o @ Wp.t() + bp + res
+    h = O.gelu(O.layer_norm(t1, g2, be2) @ W1.t() + b1)
+    y_ref = t1 + h @ W2.t() + b2
+    yl_ref = O.layer_norm(y_ref, g3, be3) if with_ln else y_ref
+    c = lambda t: t.cuda()
+    y, yl = G.op_swin_mlp(c(o), c(res), c(Wp), c(bp), c(g2), c(be2), c(W1), c(b1), c(W2), c(b2),
+                          c(g3) if with_ln else None, c(be3) if with_ln else None, heads, hid)
+    _close(y, y_ref, "bf16", "fused swin tail")
+    _close(yl, yl_ref, "bf16", "fused swin tail (second output)")
