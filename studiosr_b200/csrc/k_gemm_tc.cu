@@ -28,7 +28,7 @@ struct TcGeom {
 
 constexpr int TC_BM = 128;
 constexpr int TC_EPI_WARPS = 8;                      // two groups of 4 (one per TMEM accumulator buffer)
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 second TMA producer
 constexpr int TC_MAX_NP = 2304;
 
 template <int BLOCK_N>
@@ -101,8 +101,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   const int n_items = geo.m_tiles * geo.n_tiles;
 
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
+  if (warp == 0 || warp == 2 + TC_EPI_WARPS) {
+    // =========================== TMA producers ===========================
+    // One thread completes only one wait->issue round per ~500 cycles whatever the ring depth (measured,
+    // profiles/r01_micro_tc.txt), less than a k-block's MMAs take, so even and odd k-blocks get their own thread.
+    const uint32_t pid = warp == 0 ? 0u : 1u;
     if (lane == 0) {
       uint32_t kbg = 0;  // running k-block counter across items (ring position)
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -119,6 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           m0 = mt * TC_BM;
         }
         for (int kb = 0; kb < geo.nkb; ++kb, ++kbg) {
+          if ((kbg & 1u) != pid) continue;
           const int s = kbg % kStages;
           const uint32_t ph = (kbg / kStages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -161,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 2 + TC_EPI_WARPS) {
     // =========================== epilogue ===========================
     const int ew = warp - 2;
     const int grp = ew >> 2;    // accumulator buffer / item parity served by this warp
@@ -219,6 +223,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (dbg) dbg[1] = clock64();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BLOCK_N);
       float sum = 0.0f;
+
+      if (g.out3_f32 || g.out3_u8) {
+        // reconstruction conv (Cout = 3): bias + output affine + crop + fp32 NCHW / uint8 HWC store straight from the
+        // first three accumulator columns; consecutive lanes are consecutive pixels of a row, so the stores coalesce
+        float v[32];
+        tmem_ld32(trow, v);
+        if (m >= 0) {
+          const int px = m % g.W, py = (m / g.W) % g.H, pb = m / (g.W * g.H);
+          if (py < g.crop_h && px < g.crop_w) {
+            float r[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) r[c] = (v[c] + s_bias[c] + g.out_shift[c]) * g.out_scale;
+            if (g.out3_f32) {
+              const size_t plane = (size_t)g.crop_h * g.crop_w;
+              float* o = g.out3_f32 + (size_t)pb * 3 * plane + (size_t)py * g.crop_w + px;
+              o[0] = r[0];
+              o[plane] = r[1];
+              o[2 * plane] = r[2];
+            }
+            if (g.out3_u8) {
+              uint8_t* o = g.out3_u8 + ((size_t)(pb * g.crop_h + py) * g.crop_w + px) * 3;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) o[c] = (uint8_t)fminf(fmaxf(rintf(r[c] * g.u8_scale), 0.0f), 255.0f);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(grp));
+        continue;
+      }
 
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -428,7 +463,8 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   const int items = geo.m_tiles * geo.n_tiles;
   const int num_sms = num_sms_cached();
   dim3 grid(items < num_sms ? items : num_sms);
-  ProfScope prof(g.taps == 9 ? "gemm_tc_conv3x3" : "gemm_tc_linear", gemm_alg_flops(g), gemm_alg_bytes(g, elem), s);
+  ProfScope prof((g.out3_f32 || g.out3_u8) ? "gemm_tc_conv_last" : g.taps == 9 ? "gemm_tc_conv3x3" : "gemm_tc_linear", gemm_alg_flops(g),
+                 gemm_alg_bytes(g, elem), s);
   gemm_tc_kernel<T, BLOCK_N><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
   count_launch();
   SSR_CUDA(cudaGetLastError());

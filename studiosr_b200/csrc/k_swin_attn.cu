@@ -64,6 +64,7 @@ struct AttnKArgs {
   const uint4* bias_tab;  // [6][64][64] bf16, pi order, 16-byte chunks XOR-swizzled by (row & 7), times log2(e)
   int B, H, W, shift;
   int nwx, nwy, n_windows, n_tiles;
+  long long* dbg;  // optional phase timestamps (developer diagnostics): [CTA][g < 96][8]
 };
 
 __device__ __forceinline__ uint32_t sa_sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -284,8 +285,11 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         xflag = wx == a.nwx - 1;
       }
 
+      long long* dbg = (a.dbg && ew == 0 && lane == 0 && g < 96) ? a.dbg + 8 * ((size_t)blockIdx.x * 96 + g) : nullptr;
+      if (dbg) dbg[0] = clock64();
       // ---------------- QKV epilogue: + bias, bf16, operand tiles ----------------
       mbar_wait_warp(bar(AB_QKVFULL), ph, lane);
+      if (dbg) dbg[1] = clock64();
       tc_fence_after();
       {
         uint32_t raw[3][32];
@@ -318,10 +322,12 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(AB_OPREADY));
+      if (dbg) dbg[2] = clock64();
 
       // ---------------- softmax of head `grp` of the pair ----------------
       const int head = 2 * hp + grp;
       mbar_wait_warp(bar(AB_SFULL + grp), ph, lane);
+      if (dbg) dbg[3] = clock64();
       tc_fence_after();
       float inv_l;
       {
@@ -387,9 +393,11 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(AB_PREADY + grp));
+      if (dbg) dbg[4] = clock64();
 
       // ---------------- output of head `grp`: O / l -> bf16 -> staging ----------------
       mbar_wait_warp(bar(AB_OFULL + grp), ph, lane);
+      if (dbg) dbg[5] = clock64();
       tc_fence_after();
       {
         uint32_t raw[32];
@@ -411,6 +419,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(AB_OSTAGED));
+      if (dbg) dbg[6] = clock64();
     }
   }
 
@@ -421,6 +430,8 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
     tmem_dealloc<512>(tmem_base);
   }
 }
+
+extern long long* g_tail_dbg;
 
 int launch_swin_attn_fused(const AttnFusedArgs& f, cudaStream_t s) {
   SSR_CHECK(f.H % 8 == 0 && f.W % 8 == 0, SSR_E_INVALID, "swin_attn: %dx%d not a multiple of the 8x8 window", f.H, f.W);
@@ -450,6 +461,7 @@ int launch_swin_attn_fused(const AttnFusedArgs& f, cudaStream_t s) {
   a.nwx = f.W / 8; a.nwy = f.H / 8;
   a.n_windows = f.B * a.nwx * a.nwy;
   a.n_tiles = (a.n_windows + 1) / 2;
+  a.dbg = g_tail_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));

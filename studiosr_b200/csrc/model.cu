@@ -58,6 +58,8 @@ double gemm_alg_bytes(const GemmArgs& g, int elem) {
   if (g.out_f32) b += (double)g.M * g.N_alg * 4;
   if (g.out_T) b += (double)g.M * g.N_alg * elem;
   if (g.out_ln) b += (double)g.M * g.N_alg * elem;
+  if (g.out3_f32) b += (double)g.B * g.crop_h * g.crop_w * 3 * 4;
+  if (g.out3_u8) b += (double)g.B * g.crop_h * g.crop_w * 3;
   return b;
 }
 
@@ -120,6 +122,7 @@ struct ssr_model {
   size_t conv_last_w = 0;
   float conv_last_bias[3] = {0, 0, 0};
   int last_cin = 64;
+  Lin last_lin;  // the same conv packed for the tensor-core implicit GEMM (bf16 / tf32 models)
   // EDSR
   int F = 0, FP = 0;
   std::vector<Lin> res_a, res_b;
@@ -417,6 +420,7 @@ static int finalize_swinir(ssr_model* m) {
     }
     m->last_cin = 64;
     SSR_TRY(pack_conv_last(m, "conv_last", 64, &m->conv_last_w, m->conv_last_bias));
+    if (c.precision != SSR_PREC_FP32) SSR_TRY(pack_conv(m, "conv_last", 3, 64, 0, &m->last_lin));
   } else {
     // pixelshuffledirect: one conv C -> scale^2 * 3, stored un-shuffled; the shuffle happens in the finish kernel
     Lin L;
@@ -463,6 +467,7 @@ static int finalize_edsr(ssr_model* m) {
   }
   m->last_cin = m->F;
   SSR_TRY(pack_conv_last(m, "tail.1", m->F, &m->conv_last_w, m->conv_last_bias));
+  if (c.precision != SSR_PREC_FP32) SSR_TRY(pack_conv(m, "tail.1", 3, m->F, 0, &m->last_lin));
   return SSR_OK;
 }
 
@@ -615,6 +620,17 @@ static int run_tail(ssr_model* m, const void* cur, int ch_ld, int B, int Hp, int
     cur = bufs[i & 1];
     H *= L.ps_r;
     W *= L.ps_r;
+  }
+  if (m->cfg.precision != SSR_PREC_FP32) {  // tensor-core implicit GEMM (N padded 3 -> 64) with the reconstruction epilogue
+    GemmArgs g = gemm_base(m, m->last_lin, cur, ch_ld, B, H, W);
+    g.out3_f32 = out.out_f32;
+    g.out3_u8 = out.out_u8;
+    g.crop_h = h * m->cfg.scale;
+    g.crop_w = w * m->cfg.scale;
+    for (int i = 0; i < 3; ++i) g.out_shift[i] = out_shift[i];
+    g.out_scale = out_scale;
+    g.u8_scale = m->cfg.img_range == 1.0f ? 255.0f : 1.0f;
+    return run_gemm(m, g, s);
   }
   ConvLastArgs a;
   memset(&a, 0, sizeof(a));

@@ -82,6 +82,13 @@ struct GemmArgs {
   const float* beta;
   float eps;
   int round_tf32;  // round T=float stores to tf32 (rna) so the next tf32 MMA sees exact operands
+  // reconstruction-conv mode (tensor-core path only): v[0..2] -> (v + out_shift) * out_scale, cropped to crop_h x crop_w,
+  // stored as fp32 NCHW [B,3,crop_h,crop_w] and / or uint8 HWC (round-half-even, clip); all other outputs unused
+  float* out3_f32;
+  uint8_t* out3_u8;
+  int crop_h, crop_w;
+  float out_shift[3];
+  float out_scale, u8_scale;
   int K_alg, N_alg;  // un-padded contraction / output widths, for FLOP and byte accounting only
   long long* dbg;    // optional per-CTA phase timestamps (developer diagnostics), 8 slots per CTA
 };
