@@ -35,13 +35,13 @@ constexpr uint32_t SA_OFF_XN = 0;                                  // 3 k-block 
 constexpr uint32_t SA_OFF_W = SA_OFF_XN + 3 * SA_TILE;             // weight ring
 constexpr uint32_t SA_OFF_Q = SA_OFF_W + SA_WSLOTS * SA_WSLOT;     // [128][64] bf16 SW128: q of the pair
 constexpr uint32_t SA_OFF_K = SA_OFF_Q + SA_TILE;                  // [128][64] bf16 SW128: k of the pair
-constexpr uint32_t SA_OFF_V = SA_OFF_K + SA_TILE;                  // 2 x [128 tokens][32] bf16 SW64 (MN-major B operand)
-constexpr uint32_t SA_OFF_BIAS = SA_OFF_V + SA_TILE;               // [6][64][64] bf16 relative-position bias
+constexpr uint32_t SA_OFF_V = SA_OFF_K + SA_TILE;                  // 2 buffers x 2 heads x [128 tokens][32] bf16 SW64 (MN-major B operand)
+constexpr uint32_t SA_OFF_BIAS = SA_OFF_V + 2 * SA_TILE;           // [6][64][64] bf16 relative-position bias
 constexpr uint32_t SA_BIAS_BYTES = 6 * 64 * 128;
 constexpr uint32_t SA_OFF_OST = SA_OFF_BIAS + SA_BIAS_BYTES;       // [128][64] bf16 SW128 output staging
 constexpr uint32_t SA_OFF_PAR = SA_OFF_OST + SA_TILE;              // fp32 qkv bias [3][192]
 constexpr uint32_t SA_OFF_BAR = SA_OFF_PAR + 3 * 192 * 4;
-constexpr uint32_t SA_SMEM = SA_OFF_BAR + 256 + 1024;
+constexpr uint32_t SA_SMEM = SA_OFF_BAR + 256;  // the kernel has no static shared memory: the dynamic base is 1024-aligned (checked)
 static_assert(SA_SMEM <= 232448, "fused attention kernel exceeds the 227 KB shared-memory limit");
 
 enum {
@@ -95,7 +95,8 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
                  const __grid_constant__ CUtensorMap tmO8, const __grid_constant__ CUtensorMap tmO4,
                  const __grid_constant__ CUtensorMap tmW, const AttnKArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need the 1 KB alignment
   float* s_bhp = reinterpret_cast<float*>(smem + SA_OFF_PAR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA_OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AB_COUNT);
@@ -249,7 +250,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         for (int h = 0; h < 2; ++h) {  // O_h = P_h v_h: A = P (TMEM, block-diagonal over the two windows), B = V_h MN-major
           mbar_wait(bar(AB_PREADY + h), ph);
           tc_fence_after();
-          const uint64_t vd = umma_desc_mn_sw64(sbase + SA_OFF_V + h * 8192);
+          const uint64_t vd = umma_desc_mn_sw64(sbase + SA_OFF_V + (uint32_t)(g & 1) * SA_TILE + h * 8192);
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // 16 keys per step: 8 packed columns of P, 16 rows (1 KB) of V
             umma_ts(tO + 32 * h, tS[h] + 8 * k, vd + 64 * k, IDESC_PV, k ? 1u : 0u);
@@ -275,6 +276,42 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
     constexpr float kMask = -100.0f * 1.4426950408889634f;
     bool yflag = false, xflag = false;
 
+    // output of head `grp` of pair gg: O / l -> bf16 -> staging (runs one pair late, under the next pair's MMAs)
+    auto out_epilogue = [&](int gg, float inv_l) {
+      mbar_wait_warp(bar(AB_OFULL + grp), (uint32_t)gg & 1u, lane);
+      tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld32_nowait(tlane + (tO - tmem_base) + 32 * grp, raw);
+      if (gg > 0) mbar_wait_warp(bar(AB_OSTFREE), ((uint32_t)gg & 1u) ^ 1u, lane);  // stores of pair gg-1 have read the staging
+      tmem_wait_ld();
+      const f32x2 il = f2_splat(inv_l);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 0], raw[8 * j + 1]), il));
+        v.y = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 2], raw[8 * j + 3]), il));
+        v.z = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 4], raw[8 * j + 5]), il));
+        v.w = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 6], raw[8 * j + 7]), il));
+        *reinterpret_cast<uint4*>(sO + sa_sw128(row, 4 * grp + j)) = v;
+      }
+    };  // the caller publishes the staging (fence.proxy.async + arrive on AB_OSTAGED) together with its own smem writes
+    // QKV epilogue of one 32-column chunk: + bias, bf16, into the operand tile `dst_of(chunk j)` selects
+    auto qkv_chunk = [&](const uint32_t (&raw)[32], const float* bb, auto dst_of) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16-byte chunk
+        const float4 b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
+        const float4 b1 = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
+        const uint32_t* r8 = &raw[8 * j];
+        uint4 v;
+        v.x = f2_to_bf16x2(f2_add(f2_pack_u(r8[0], r8[1]), f2_pack(b0.x, b0.y)));
+        v.y = f2_to_bf16x2(f2_add(f2_pack_u(r8[2], r8[3]), f2_pack(b0.z, b0.w)));
+        v.z = f2_to_bf16x2(f2_add(f2_pack_u(r8[4], r8[5]), f2_pack(b1.x, b1.y)));
+        v.w = f2_to_bf16x2(f2_add(f2_pack_u(r8[6], r8[7]), f2_pack(b1.z, b1.w)));
+        *reinterpret_cast<uint4*>(dst_of(j)) = v;
+      }
+    };
+
+    float inv_l_prev = 1.0f;
     for (int g = 0; g < G; ++g) {
       const uint32_t ph = (uint32_t)g & 1u;
       const int it = g / 3, hp = g - 3 * it;
@@ -284,10 +321,10 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         yflag = wy == a.nwy - 1;
         xflag = wx == a.nwx - 1;
       }
-
       long long* dbg = (a.dbg && ew == 0 && lane == 0 && g < 96) ? a.dbg + 8 * ((size_t)blockIdx.x * 96 + g) : nullptr;
       if (dbg) dbg[0] = clock64();
-      // ---------------- QKV epilogue: + bias, bf16, operand tiles ----------------
+
+      // ---------------- QKV epilogue: + bias, bf16, operand tiles (V into buffer g & 1: P.V of pair g-1 may still run) ----------------
       mbar_wait_warp(bar(AB_QKVFULL), ph, lane);
       if (dbg) dbg[1] = clock64();
       tc_fence_after();
@@ -297,48 +334,45 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tlane + grp * 96 + c * 32, raw[c]);
         tmem_wait_ld();
         const float* bb = s_bhp + hp * 192 + grp * 96;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16-byte chunk
-            const float4 b0 = *reinterpret_cast<const float4*>(bb + c * 32 + 8 * j);
-            const float4 b1 = *reinterpret_cast<const float4*>(bb + c * 32 + 8 * j + 4);
-            const uint32_t* r8 = &raw[c][8 * j];
-            uint4 v;
-            v.x = f2_to_bf16x2(f2_add(f2_pack_u(r8[0], r8[1]), f2_pack(b0.x, b0.y)));
-            v.y = f2_to_bf16x2(f2_add(f2_pack_u(r8[2], r8[3]), f2_pack(b0.z, b0.w)));
-            v.z = f2_to_bf16x2(f2_add(f2_pack_u(r8[4], r8[5]), f2_pack(b1.x, b1.y)));
-            v.w = f2_to_bf16x2(f2_add(f2_pack_u(r8[6], r8[7]), f2_pack(b1.z, b1.w)));
-            const int col = grp * 96 + c * 32 + 8 * j;  // column of the pair's accumulator
-            uint8_t* dst;
-            if (col < 64) dst = sQ + sa_sw128(row, col >> 3);                       // q h0 | h1
-            else if (col < 128) dst = sK + sa_sw128(row, (col - 64) >> 3);          // k h0 | h1
-            else dst = sV + ((col - 128) >> 5) * 8192 + sa_sw64(row, ((col - 128) & 31) >> 3);  // v h0 / h1
-            *reinterpret_cast<uint4*>(dst) = v;
-          }
+        uint8_t* vbuf = sV + (g & 1) * SA_TILE;
+        if (grp == 0) {  // columns [0,96): q h0 | q h1 | k h0
+          qkv_chunk(raw[0], bb, [&](int j) { return sQ + sa_sw128(row, j); });
+          qkv_chunk(raw[1], bb + 32, [&](int j) { return sQ + sa_sw128(row, 4 + j); });
+          qkv_chunk(raw[2], bb + 64, [&](int j) { return sK + sa_sw128(row, j); });
+        } else {  // columns [96,192): k h1 | v h0 | v h1
+          qkv_chunk(raw[0], bb, [&](int j) { return sK + sa_sw128(row, 4 + j); });
+          qkv_chunk(raw[1], bb + 32, [&](int j) { return vbuf + sa_sw64(row, j); });
+          qkv_chunk(raw[2], bb + 64, [&](int j) { return vbuf + 8192 + sa_sw64(row, j); });
         }
       }
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(AB_OPREADY));
       if (dbg) dbg[2] = clock64();
+      // ---------------- output of the previous pair (its P.V ran under this pair's QKV epilogue) ----------------
+      if (g > 0) out_epilogue(g - 1, inv_l_prev);
+      tc_fence_before();
+      fence_proxy_async();  // one proxy fence publishes both the operand tiles and the output staging
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(AB_OPREADY));
+        if (g > 0) mbar_arrive(bar(AB_OSTAGED));
+      }
+      if (dbg) dbg[3] = clock64();
 
       // ---------------- softmax of head `grp` of the pair ----------------
       const int head = 2 * hp + grp;
+      // bias row of this token: 64 bf16 = 8 chunks (fetched while the score MMAs finish)
+      uint4 bq[8];
+      {
+        const uint4* brow = sBias + (head * 64 + ri) * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bq[c] = brow[c ^ (ri & 7)];
+      }
       mbar_wait_warp(bar(AB_SFULL + grp), ph, lane);
-      if (dbg) dbg[3] = clock64();
+      if (dbg) dbg[4] = clock64();
       tc_fence_after();
-      float inv_l;
       {
         uint32_t raw[2][32];
         tmem_ld32_nowait(tlane + (tS[grp] - tmem_base) + 64 * w, raw[0]);
         tmem_ld32_nowait(tlane + (tS[grp] - tmem_base) + 64 * w + 32, raw[1]);
-        // bias row of this token: 64 bf16 = 8 chunks
-        const uint4* brow = sBias + (head * 64 + ri) * 8;
-        uint4 bq[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) bq[c] = brow[c ^ (ri & 7)];
         tmem_wait_ld();
         f32x2 s[32];
 #pragma unroll
@@ -361,15 +395,15 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
             for (int i = 0; i < 8; ++i) s[8 * gq + i] = f2_add(s[8 * gq + i], mv);
           }
         }
-        float mx = -INFINITY;
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int p = 0; p < 32; ++p) {
           float lo, hi;
           f2_unpack(s[p], lo, hi);
-          mx = fmaxf(mx, fmaxf(lo, hi));
+          mx[p & 3] = fmaxf(mx[p & 3], fmaxf(lo, hi));
         }
-        const f32x2 nm = f2_splat(-mx);
-        f32x2 acc2[2] = {0ull, 0ull};
+        const f32x2 nm = f2_splat(-fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+        f32x2 acc2[4] = {0ull, 0ull, 0ull, 0ull};
         uint32_t pk[32];
 #pragma unroll
         for (int p = 0; p < 32; ++p) {
@@ -378,10 +412,10 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lo) : "f"(lo));
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(hi));
           const f32x2 e2 = f2_pack(lo, hi);
-          acc2[p & 1] = f2_add(acc2[p & 1], e2);
+          acc2[p & 3] = f2_add(acc2[p & 3], e2);
           pk[p] = f2_to_bf16x2(e2);
         }
-        inv_l = 1.0f / f2_hsum(f2_add(acc2[0], acc2[1]));
+        inv_l_prev = 1.0f / f2_hsum(f2_add(f2_add(acc2[0], acc2[1]), f2_add(acc2[2], acc2[3])));
         // P over the scores: own window's 64 keys -> 32 packed columns, the other window's half zeroed
         uint32_t zero[32];
 #pragma unroll
@@ -393,33 +427,14 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(AB_PREADY + grp));
-      if (dbg) dbg[4] = clock64();
-
-      // ---------------- output of head `grp`: O / l -> bf16 -> staging ----------------
-      mbar_wait_warp(bar(AB_OFULL + grp), ph, lane);
       if (dbg) dbg[5] = clock64();
-      tc_fence_after();
-      {
-        uint32_t raw[32];
-        tmem_ld32_nowait(tlane + (tO - tmem_base) + 32 * grp, raw);
-        if (g > 0) mbar_wait_warp(bar(AB_OSTFREE), ((uint32_t)g & 1u) ^ 1u, lane);  // stores of pair g-1 have read the staging
-        tmem_wait_ld();
-        const f32x2 il = f2_splat(inv_l);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v;
-          v.x = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 0], raw[8 * j + 1]), il));
-          v.y = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 2], raw[8 * j + 3]), il));
-          v.z = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 4], raw[8 * j + 5]), il));
-          v.w = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 6], raw[8 * j + 7]), il));
-          *reinterpret_cast<uint4*>(sO + sa_sw128(row, 4 * grp + j)) = v;
-        }
-      }
+    }
+    if (G > 0) {
+      out_epilogue(G - 1, inv_l_prev);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(AB_OSTAGED));
-      if (dbg) dbg[6] = clock64();
     }
   }
 
