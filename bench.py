@@ -272,8 +272,16 @@ def run_ours(args):
         top = max(prof, key=lambda k: prof[k]["ms"])
         v = prof[top]
         ach = v["flops"] / (v["ms"] / 1e3) / 1e12
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of this kernel (per token x tokens per launch)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                per_tok = json.load(f).get(top, {}).get("dram_bytes_per_token")
+            if per_tok:
+                traffic = per_tok * nt * PAD_TILE * PAD_TILE
+        except OSError:
+            pass
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sust"], "traffic": None,
+                    "frac": ach / pk["tf_sust"], "traffic": traffic,
                     "per_launch": {"flops": v["flops"] / v["launches"], "ms": v["ms"] / v["launches"]},
                     "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)"}
 
