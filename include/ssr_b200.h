@@ -40,7 +40,7 @@ enum {
   SSR_E_WORKSPACE = -5  /* workspace too small */
 };
 
-enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1 };
+enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1, SSR_ARCH_RCAN = 2 };
 
 /* arithmetic of the contractions */
 enum {
@@ -58,7 +58,7 @@ enum {
 #define SSR_MAX_LAYERS 16
 
 /* Mirrors the constructor arguments of studiosr.models.SwinIR (swinir.py:259-274) and
- * studiosr.models.EDSR (edsr.py:13-21). */
+ * studiosr.models.EDSR (edsr.py:13-21) and studiosr.models.RCAN (rcan.py:40-49). */
 typedef struct ssr_model_config {
   int arch;      /* SSR_ARCH_* */
   int precision; /* SSR_PREC_* */
@@ -77,6 +77,9 @@ typedef struct ssr_model_config {
   int n_feats;
   int n_resblocks;
   float res_scale;
+  /* RCAN (n_feats, n_resblocks as above) */
+  int n_resgroups;
+  int reduction;
 } ssr_model_config;
 
 typedef struct ssr_model ssr_model_t;

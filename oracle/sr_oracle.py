@@ -214,6 +214,35 @@ def edsr_forward(P: Dict, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
     return F.conv2d(y, P["add_mean.weight"], P["add_mean.bias"])
 
 
+# --------------------------------------------------------------------------- RCAN
+def channel_attention(P: Dict, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """common.py:156-170 -- x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2), 1x1 convs on the pooled [B,C,1,1]."""
+    y = x.mean(dim=(2, 3), keepdim=True)
+    y = torch.relu(F.conv2d(y, P[pre + ".conv_du.0.weight"], P[pre + ".conv_du.0.bias"]))
+    y = torch.sigmoid(F.conv2d(y, P[pre + ".conv_du.2.weight"], P[pre + ".conv_du.2.bias"]))
+    return x * y
+
+
+def rcan_forward(P: Dict, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
+    """rcan.py:68-77 with RCAB :11-24, ResidualGroup :27-36 and MeanShift common.py:108-121."""
+    dt = x.dtype
+    P = {k: v.to(dt) for k, v in P.items()}
+    x = F.conv2d(x, P["sub_mean.weight"], P["sub_mean.bias"])
+    x = conv3x3(P, "head.0", x)
+    g = x
+    nb, ng = cfg["n_resblocks"], cfg["n_resgroups"]
+    for gi in range(ng):
+        r = g
+        for bi in range(nb):
+            p = f"body.{gi}.body.{bi}.body"
+            t = conv3x3(P, p + ".2", torch.relu(conv3x3(P, p + ".0", r)))
+            r = channel_attention(P, p + ".3", t) + r
+        g = conv3x3(P, f"body.{gi}.body.{nb}", r) + g
+    r = conv3x3(P, f"body.{ng}", g) + x
+    y = conv3x3(P, "tail.1", _upsampler(P, "tail.0", r, cfg["scale"], cfg["n_feats"]))
+    return F.conv2d(y, P["add_mean.weight"], P["add_mean.bias"])
+
+
 # --------------------------------------------------------------------------- Model.inference + tiler
 def quantize_u8(y: torch.Tensor, img_range: float) -> torch.Tensor:
     """common.py:44-45 -- [3,H,W] float -> [H,W,3] uint8 (round half to even, clip)."""

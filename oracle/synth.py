@@ -149,6 +149,39 @@ def edsr_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
     return sd
 
 
+RCAN_DEFAULT = dict(scale=4, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=20, n_resgroups=10, reduction=16)
+RCAN_TINY = dict(scale=4, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=2, n_resgroups=2, reduction=16)
+
+
+def rcan_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of reference RCAN(**cfg) (rcan.py:39-66, RCAB :11-24, ResidualGroup :27-36,
+    ChannelAttention common.py:156-170), synthetic values."""
+    g = _gen(seed)
+    sd = OrderedDict()
+    F = cfg["n_feats"]
+    nc = cfg["n_colors"]
+    R = F // cfg["reduction"]
+    mean = torch.tensor(RGB_MEAN) * cfg["img_range"]
+    sd["sub_mean.weight"] = torch.eye(3).view(3, 3, 1, 1)
+    sd["sub_mean.bias"] = -mean
+    sd["add_mean.weight"] = torch.eye(3).view(3, 3, 1, 1)
+    sd["add_mean.bias"] = mean.clone()
+    _conv(g, sd, "head.0", F, nc)
+    for gi in range(cfg["n_resgroups"]):
+        for bi in range(cfg["n_resblocks"]):
+            p = f"body.{gi}.body.{bi}.body"
+            _conv(g, sd, p + ".0", F, F)
+            _conv(g, sd, p + ".2", F, F, gain=0.5)
+            _conv(g, sd, p + ".3.conv_du.0", R, F, k=1)
+            _conv(g, sd, p + ".3.conv_du.2", F, R, k=1, gain=2.0)
+        _conv(g, sd, f"body.{gi}.body.{cfg['n_resblocks']}", F, F, gain=0.5)
+    _conv(g, sd, f"body.{cfg['n_resgroups']}", F, F, gain=0.5)
+    for i, cout, _ in upsampler_convs(cfg["scale"], F):
+        _conv(g, sd, f"tail.0.{i}", cout, F)
+    _conv(g, sd, "tail.1", nc, F)
+    return sd
+
+
 def image_batch(shape, seed: int = 1234) -> torch.Tensor:
     """Synthetic LR input in [0,1] (torch.rand, seed 1234)."""
     return torch.rand(*shape, generator=_gen(seed), dtype=torch.float32)

@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssr_b200.so")
 
-SSR_ARCH_SWINIR, SSR_ARCH_EDSR = 0, 1
+SSR_ARCH_SWINIR, SSR_ARCH_EDSR, SSR_ARCH_RCAN = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
 PAD_EVAL, PAD_TRAIN = 0, 1
@@ -24,6 +24,7 @@ class ModelConfig(ctypes.Structure):
         ("embed_dim", c_int), ("n_layers", c_int), ("depths", c_int * SSR_MAX_LAYERS),
         ("num_heads", c_int * SSR_MAX_LAYERS), ("window_size", c_int), ("mlp_ratio", c_float), ("upsampler", c_int),
         ("n_feats", c_int), ("n_resblocks", c_int), ("res_scale", c_float),
+        ("n_resgroups", c_int), ("reduction", c_int),
     ]
 
 

@@ -578,6 +578,136 @@ __global__ void pack_rows_kernel(const float* in, int rows, int cols, void* out,
   const long long r = idx / ld;
   store_elem(out, (size_t)idx, elem, c < cols ? in[r * cols + c] : 0.0f, rtf32);
 }
+// =============================================================================================
+// RCAN channel attention (common.py:156-170) around the second conv of an RCAB (rcan.py:21-24):
+//   y = sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2);  out = res + t * y
+// Stage 1 reduces t over pixel slabs into partial[b][split][c] (deterministic, no atomics); stage 2
+// finishes the mean, evaluates the tiny MLP once per block and applies gate + residual.
+// =============================================================================================
+__global__ void __launch_bounds__(256) ca_pool_kernel(const float* t, int ld, int HW, int C, int nsplit, float* partial) {
+  __shared__ float red[256];
+  const int b = blockIdx.y, split = blockIdx.x;
+  const int chunk = (HW + nsplit - 1) / nsplit;
+  const int p0 = split * chunk, p1 = min(HW, p0 + chunk);
+  const int lanes = 256 / 64;  // pixel lanes per 64-channel slab
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
+    float acc = 0.0f;
+    if (c < C)
+      for (int p = p0 + pl; p < p1; p += lanes) acc += t[((size_t)b * HW + p) * ld + c];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < C)
+      partial[((size_t)b * nsplit + split) * C + c] = red[threadIdx.x] + red[threadIdx.x + 64] + red[threadIdx.x + 128] + red[threadIdx.x + 192];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) ca_apply_kernel(const CaArgs a) {
+  __shared__ float pooled[256], hid[64], gate[256];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float s = 0.0f;
+    for (int k = 0; k < a.nsplit; ++k) s += a.partial[((size_t)b * a.nsplit + k) * a.C + c];
+    pooled[c] = s / (float)a.HW;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < a.R; r += blockDim.x) {
+    float s = a.b1[r];
+    for (int c = 0; c < a.C; ++c) s = fmaf(a.W1[r * a.C + c], pooled[c], s);
+    hid[r] = fmaxf(s, 0.0f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.CP; c += blockDim.x) {
+    float g = 0.0f;
+    if (c < a.C) {
+      float s = a.b2[c];
+      for (int r = 0; r < a.R; ++r) s = fmaf(a.W2[c * a.R + r], hid[r], s);
+      g = 1.0f / (1.0f + expf(-s));
+    }
+    gate[c] = g;  // padded channels: t is zero there anyway
+  }
+  __syncthreads();
+  const int chunk = (a.HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * chunk, p1 = min(a.HW, p0 + chunk);
+  const int c4n = a.CP / 4;
+  for (int e = threadIdx.x; e < (p1 - p0) * c4n; e += blockDim.x) {
+    const int p = p0 + e / c4n, c = (e % c4n) * 4;
+    const size_t m = (size_t)b * a.HW + p;
+    const float4 tv = *reinterpret_cast<const float4*>(a.t + m * a.ld + c);
+    const float4 rv = *reinterpret_cast<const float4*>(a.res + m * a.ld + c);
+    float4 o;
+    o.x = fmaf(tv.x, gate[c], rv.x); o.y = fmaf(tv.y, gate[c + 1], rv.y);
+    o.z = fmaf(tv.z, gate[c + 2], rv.z); o.w = fmaf(tv.w, gate[c + 3], rv.w);
+    *reinterpret_cast<float4*>(a.out_f32 + m * a.ld + c) = o;
+    if (a.elem == 2) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out_T) + m * a.ld_T + c) = pk;
+    } else {
+      float4 q = o;
+      if (a.round_tf32) { q.x = round_tf32(q.x); q.y = round_tf32(q.y); q.z = round_tf32(q.z); q.w = round_tf32(q.w); }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out_T) + m * a.ld_T + c) = q;
+    }
+  }
+}
+
+int launch_channel_attention(const CaArgs& a, cudaStream_t s) {
+  SSR_CHECK(a.C <= 256 && a.R <= 64 && a.CP % 4 == 0 && a.nsplit >= 1, SSR_E_INVALID, "channel attention: C=%d R=%d", a.C, a.R);
+  const double px = (double)a.B * a.HW;
+  {
+    ProfScope prof("ca_pool", 0.0, px * a.C * 4, s);
+    ca_pool_kernel<<<dim3(a.nsplit, a.B), 256, 0, s>>>(a.t, a.ld, a.HW, a.C, a.nsplit, a.partial);
+    count_launch();
+  }
+  {
+    ProfScope prof("ca_apply", 0.0, px * a.C * (4 + 4 + 4 + a.elem), s);
+    const int blocks = a.HW >= 4096 ? 64 : (a.HW + 63) / 64;
+    ca_apply_kernel<<<dim3(blocks, a.B), 256, 0, s>>>(a);
+    count_launch();
+  }
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// "pixelshuffledirect" tail of the lightweight SwinIR (swinir.py:327-329, 367-372): the single conv C -> 3 s^2 leaves
+// fp32 rows [pixel][3 s^2]; this kernel is nn.PixelShuffle(s) + un-normalise + crop + fp32 NCHW / uint8 HWC store.
+__global__ void shuffle_finish_kernel(const float* in, int ld, int B, int Hp, int Wp, int scale, int ch, int cw, float s0, float s1,
+                                      float s2, float out_scale, float u8_scale, float* out_f32, uint8_t* out_u8) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * ch * cw) return;
+  const int X = (int)(idx % cw), Y = (int)((idx / cw) % ch), b = (int)(idx / ((long long)cw * ch));
+  const int y = Y / scale, x = X / scale, q = (Y % scale) * scale + X % scale, ss = scale * scale;
+  const float* row = in + ((size_t)(b * Hp + y) * Wp + x) * ld;
+  const float sh[3] = {s0, s1, s2};
+  float r[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) r[c] = (row[c * ss + q] + sh[c]) * out_scale;
+  if (out_f32) {
+    const size_t plane = (size_t)ch * cw;
+    float* o = out_f32 + (size_t)b * 3 * plane + (size_t)Y * cw + X;
+    o[0] = r[0];
+    o[plane] = r[1];
+    o[2 * plane] = r[2];
+  }
+  if (out_u8) {
+    uint8_t* o = out_u8 + ((size_t)(b * ch + Y) * cw + X) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = (uint8_t)fminf(fmaxf(rintf(r[c] * u8_scale), 0.0f), 255.0f);
+  }
+}
+int launch_shuffle_finish(const float* in, int ld, int B, int Hp, int Wp, int scale, int ch, int cw, const float* shift3,
+                          float out_scale, float u8_scale, float* out_f32, uint8_t* out_u8, cudaStream_t s) {
+  const long long total = (long long)B * ch * cw;
+  ProfScope prof("shuffle_finish", 0.0, (double)total * 3 * (4 + (out_f32 ? 4 : 1)), s);
+  shuffle_finish_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(in, ld, B, Hp, Wp, scale, ch, cw, shift3[0], shift3[1], shift3[2],
+                                                                  out_scale, u8_scale, out_f32, out_u8);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 // Fold a LayerNorm affine into the Linear that consumes it (op-level tests; the model does this on the host at
 // pack time): Wf[n][k] = W[n][k] * gamma[k],  bf[n] = b[n] + sum_k W[n][k] * beta[k].
 __global__ void fold_ln_linear_kernel(const float* W, const float* b, const float* gamma, const float* beta, float* Wf, float* bf,

@@ -128,6 +128,12 @@ struct ssr_model {
   std::vector<Lin> res_a, res_b;
   Lin body_tail;
   float sub_bias[3] = {0, 0, 0}, add_bias[3] = {0, 0, 0};
+  // RCAN: res_a / res_b hold the two convs of every RCAB (group-major), grp_tail the conv closing each group
+  std::vector<Lin> grp_tail;
+  struct CaP {
+    size_t w1 = 0, b1 = 0, w2 = 0, b2 = 0;  // fp32 [R][C], [R], [C][R], [C]
+  };
+  std::vector<CaP> ca;
 
   template <typename T>
   T* dev(size_t off) const { return reinterpret_cast<T*>(arena + off); }
@@ -471,6 +477,69 @@ static int finalize_edsr(ssr_model* m) {
   return SSR_OK;
 }
 
+static size_t pack_raw(ssr_model* m, const std::string& name, size_t numel) {
+  const std::vector<float>* v = find_param(m, name, numel);
+  if (!v) return (size_t)-1;
+  return pack_vec(m, *v, (int)numel);
+}
+
+static int finalize_rcan(ssr_model* m) {  // rcan.py:39-66
+  const ssr_model_config& c = m->cfg;
+  SSR_CHECK(c.n_colors == 3, SSR_E_INVALID, "n_colors must be 3");
+  m->F = c.n_feats;
+  m->FP = round_up(m->F, 64);
+  SSR_CHECK(m->FP <= 256, SSR_E_INVALID, "n_feats %d > 256 not supported", m->F);
+  SSR_CHECK(c.reduction > 0 && m->F % c.reduction == 0 && m->F / c.reduction <= 64, SSR_E_INVALID, "bad reduction %d", c.reduction);
+  SSR_CHECK(c.n_resgroups > 0 && c.n_resblocks > 0, SSR_E_INVALID, "bad RCAN depth %dx%d", c.n_resgroups, c.n_resblocks);
+  const int F = m->F, R = F / c.reduction;
+  SSR_TRY(pack_conv_first(m, "head.0", F, &m->conv_first_w, &m->conv_first_b));
+  const std::vector<float>* sb = find_param(m, "sub_mean.bias", 3);
+  const std::vector<float>* ab = find_param(m, "add_mean.bias", 3);
+  if (!sb || !ab) return SSR_E_STATE;
+  for (int i = 0; i < 3; ++i) {
+    m->sub_bias[i] = (*sb)[i];
+    m->add_bias[i] = (*ab)[i];
+  }
+  const int nblk = c.n_resgroups * c.n_resblocks;
+  m->res_a.assign(nblk, Lin());
+  m->res_b.assign(nblk, Lin());
+  m->ca.assign(nblk, ssr_model::CaP());
+  m->grp_tail.assign(c.n_resgroups, Lin());
+  char nm[96];
+  for (int g = 0; g < c.n_resgroups; ++g) {
+    for (int b = 0; b < c.n_resblocks; ++b) {
+      const int i = g * c.n_resblocks + b;
+      snprintf(nm, sizeof(nm), "body.%d.body.%d.body", g, b);
+      const std::string p(nm);
+      SSR_TRY(pack_conv(m, p + ".0", F, F, 0, &m->res_a[i]));
+      SSR_TRY(pack_conv(m, p + ".2", F, F, 0, &m->res_b[i]));
+      ssr_model::CaP& ca = m->ca[i];
+      ca.w1 = pack_raw(m, p + ".3.conv_du.0.weight", (size_t)R * F);
+      ca.b1 = pack_raw(m, p + ".3.conv_du.0.bias", (size_t)R);
+      ca.w2 = pack_raw(m, p + ".3.conv_du.2.weight", (size_t)F * R);
+      ca.b2 = pack_raw(m, p + ".3.conv_du.2.bias", (size_t)F);
+      if (ca.w1 == (size_t)-1 || ca.b1 == (size_t)-1 || ca.w2 == (size_t)-1 || ca.b2 == (size_t)-1) return SSR_E_STATE;
+    }
+    snprintf(nm, sizeof(nm), "body.%d.body.%d", g, c.n_resblocks);
+    SSR_TRY(pack_conv(m, nm, F, F, 0, &m->grp_tail[g]));
+  }
+  snprintf(nm, sizeof(nm), "body.%d", c.n_resgroups);
+  SSR_TRY(pack_conv(m, nm, F, F, 0, &m->body_tail));
+  std::vector<int> rs;
+  upsampler_plan(c.scale, &rs);
+  m->up.clear();
+  for (size_t i = 0; i < rs.size(); ++i) {
+    Lin L;
+    snprintf(nm, sizeof(nm), "tail.0.%d", (int)(2 * i));
+    SSR_TRY(pack_conv(m, nm, rs[i] * rs[i] * F, F, rs[i], &L));
+    m->up.push_back(L);
+  }
+  m->last_cin = F;
+  SSR_TRY(pack_conv_last(m, "tail.1", F, &m->conv_last_w, m->conv_last_bias));
+  if (c.precision != SSR_PREC_FP32) SSR_TRY(pack_conv(m, "tail.1", 3, F, 0, &m->last_lin));
+  return SSR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // workspace planning
 struct Carver {
@@ -526,10 +595,10 @@ static size_t plan_swinir(const ssr_model* m, void* base, int B, int Hp, int Wp,
     px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
     if (px * 64 > need[i & 1]) need[i & 1] = px * 64;
   }
-  if (m->cfg.upsampler == 1) need[0] = T * m->up[0].NP;
+  if (m->cfg.upsampler == 1) need[0] = T * m->up[0].NP;  // fp32 rows of the pixelshuffledirect conv
   for (int i = 0; i < 2; ++i) {
     w->hr_elems[i] = need[i];
-    w->hr[i] = need[i] ? c.take(need[i] * e) : nullptr;
+    w->hr[i] = need[i] ? c.take(need[i] * (m->cfg.upsampler == 1 ? 4 : e)) : nullptr;
   }
   return c.off + 1024;
 }
@@ -892,8 +961,13 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
     SSR_TRY(run_gemm(m, g, s));
     return run_tail(m, W.cbu, 64, B, Hp, Wp, W.hr[0], W.hr[1], h, w, shift, c.img_range, out, s);
   }
-  set_error("upsampler 'pixelshuffledirect' is not implemented yet");
-  return SSR_E_INVALID;
+  // lightweight SR ("pixelshuffledirect", swinir.py:327-329,367-369): one conv C -> 3 s^2, then shuffle + un-normalise + crop
+  GemmArgs g = gemm_base(m, m->up[0], W.tb, CP, B, Hp, Wp);
+  g.out_f32 = reinterpret_cast<float*>(W.hr[0]);
+  g.ld_f32 = m->up[0].NP;
+  SSR_TRY(run_gemm(m, g, s));
+  return launch_shuffle_finish(reinterpret_cast<float*>(W.hr[0]), m->up[0].NP, B, Hp, Wp, c.scale, h * c.scale, w * c.scale, shift,
+                               c.img_range, c.img_range == 1.0f ? 255.0f : 1.0f, out.out_f32, out.out_u8, s);
 }
 
 static int forward_edsr(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, void* ws,
@@ -961,6 +1035,101 @@ static int forward_edsr(ssr_model* m, const InputSpec& in, const OutputSpec& out
   return run_tail(m, W.tmp, FP, B, h, w, W.hr[0], W.hr[1], h, w, m->add_bias, 1.0f, out, s);
 }
 
+struct RcanWs {
+  float *x, *gin, *r, *t2, *partial;
+  void *rb, *tmp, *hr[2];
+  int nsplit;
+};
+static size_t plan_rcan(const ssr_model* m, void* base, int B, int H, int W, RcanWs* w) {
+  Carver c(base);
+  const size_t T = (size_t)B * H * W, e = m->elem;
+  const int HW = H * W;
+  w->nsplit = HW >= 16384 ? 64 : (HW + 255) / 256;
+  w->x = (float*)c.take(T * m->FP * 4);
+  w->gin = (float*)c.take(T * m->FP * 4);
+  w->r = (float*)c.take(T * m->FP * 4);
+  w->t2 = (float*)c.take(T * m->FP * 4);
+  w->partial = (float*)c.take((size_t)B * w->nsplit * m->F * 4);
+  w->rb = c.take(T * m->FP * e);
+  w->tmp = c.take(T * m->FP * e);
+  size_t need[2] = {0, 0};
+  size_t px = T;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
+    if (px * m->FP > need[i & 1]) need[i & 1] = px * m->FP;
+  }
+  for (int i = 0; i < 2; ++i) w->hr[i] = need[i] ? c.take(need[i] * e) : nullptr;
+  return c.off + 1024;
+}
+
+static int forward_rcan(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, void* ws,
+                        size_t ws_bytes, cudaStream_t s) {
+  const ssr_model_config& c = m->cfg;
+  RcanWs W;
+  const size_t need = plan_rcan(m, ws, B, h, w, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+  const int FP = m->FP, e = m->elem, R = m->F / c.reduction;
+  {  // sub_mean + head (rcan.py:69-70)
+    ConvFirstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in.in; a.in_u8 = in.in_u8; a.fh = in.fh; a.fw = in.fw;
+    a.tile_mode = in.tile_mode; a.tile = in.tile; a.stride = in.stride; a.tiles_x = in.tiles_x; a.tile_begin = in.tile_begin;
+    a.h = h; a.w = w; a.Hp = h; a.Wp = w; a.pad_mode = 2; a.B = B;
+    a.in_scale = (in.in_u8 && c.img_range == 1.0f) ? 1.0f / 255.0f : 1.0f;
+    for (int i = 0; i < 3; ++i) a.in_shift[i] = m->sub_bias[i];
+    a.Wc = m->dev<float>(m->conv_first_w);
+    a.bias = m->dev<float>(m->conv_first_b);
+    a.Cout = m->F;
+    a.out_f32 = W.x; a.ld_f32 = FP; a.out_T = W.rb; a.ld_T = FP; a.elem = e;
+    a.round_tf32 = c.precision == SSR_PREC_TF32;
+    SSR_TRY(launch_conv_first(a, s));
+  }
+  const float* gcur = W.x;  // input of the current residual group (fp32 stream)
+  for (int g = 0; g < c.n_resgroups; ++g) {
+    const float* rcur = gcur;  // input of the current RCAB
+    for (int b = 0; b < c.n_resblocks; ++b) {  // RCAB (rcan.py:21-24)
+      const int i = g * c.n_resblocks + b;
+      GemmArgs ga = gemm_base(m, m->res_a[i], W.rb, FP, B, h, w);
+      ga.act = ACT_RELU;
+      ga.out_T = W.tmp;
+      ga.ld_T = FP;
+      SSR_TRY(run_gemm(m, ga, s));
+      GemmArgs gb = gemm_base(m, m->res_b[i], W.tmp, FP, B, h, w);
+      gb.out_f32 = W.t2;
+      gb.ld_f32 = FP;
+      SSR_TRY(run_gemm(m, gb, s));
+      CaArgs ca;
+      memset(&ca, 0, sizeof(ca));
+      ca.t = W.t2; ca.res = rcur; ca.ld = FP; ca.B = B; ca.HW = h * w; ca.C = m->F; ca.CP = FP; ca.R = R;
+      ca.W1 = m->dev<float>(m->ca[i].w1); ca.b1 = m->dev<float>(m->ca[i].b1);
+      ca.W2 = m->dev<float>(m->ca[i].w2); ca.b2 = m->dev<float>(m->ca[i].b2);
+      ca.partial = W.partial; ca.nsplit = W.nsplit;
+      ca.out_f32 = W.r; ca.out_T = W.rb; ca.ld_T = FP; ca.elem = e; ca.round_tf32 = c.precision == SSR_PREC_TF32;
+      SSR_TRY(launch_channel_attention(ca, s));
+      rcur = W.r;
+    }
+    // group tail conv + group skip (rcan.py:33-36)
+    GemmArgs gt = gemm_base(m, m->grp_tail[g], W.rb, FP, B, h, w);
+    gt.res = gcur;
+    gt.ldres = FP;
+    gt.out_f32 = W.gin;
+    gt.ld_f32 = FP;
+    gt.out_T = W.rb;
+    gt.ld_T = FP;
+    SSR_TRY(run_gemm(m, gt, s));
+    gcur = W.gin;
+  }
+  {  // body tail conv + long skip (rcan.py:72-73)
+    GemmArgs g = gemm_base(m, m->body_tail, W.rb, FP, B, h, w);
+    g.res = W.x;
+    g.ldres = FP;
+    g.out_T = W.tmp;
+    g.ld_T = FP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  return run_tail(m, W.tmp, FP, B, h, w, W.hr[0], W.hr[1], h, w, m->add_bias, 1.0f, out, s);
+}
+
 static int check_ready(ssr_model* m) {
   SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
   SSR_CHECK(m->finalized, SSR_E_STATE, "model not finalised (call ssr_model_finalize)");
@@ -974,6 +1143,7 @@ static int forward_any(ssr_model* m, const InputSpec& in, const OutputSpec& out,
                        void* ws, size_t ws_bytes, cudaStream_t s) {
   SSR_CHECK(B > 0 && h > 0 && w > 0, SSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, h, w);
   if (m->cfg.arch == SSR_ARCH_SWINIR) return forward_swinir(m, in, out, B, h, w, pad_mode, ws, ws_bytes, s);
+  if (m->cfg.arch == SSR_ARCH_RCAN) return forward_rcan(m, in, out, B, h, w, ws, ws_bytes, s);
   return forward_edsr(m, in, out, B, h, w, ws, ws_bytes, s);
 }
 
@@ -983,6 +1153,10 @@ static size_t workspace_any(const ssr_model* m, int B, int H, int W, int pad_mod
     padded_size(m, H, W, pad_mode, &Hp, &Wp);
     SwinWs w;
     return plan_swinir(m, nullptr, B, Hp, Wp, &w);
+  }
+  if (m->cfg.arch == SSR_ARCH_RCAN) {
+    RcanWs w;
+    return plan_rcan(m, nullptr, B, H, W, &w);
   }
   EdsrWs w;
   return plan_edsr(m, nullptr, B, H, W, &w);
@@ -1061,7 +1235,8 @@ int ssr_device_check(int device) {
 
 int ssr_model_create(const ssr_model_config* cfg, int device, ssr_model_t** out) {
   SSR_CHECK(cfg && out, SSR_E_INVALID, "null argument");
-  SSR_CHECK(cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_EDSR, SSR_E_INVALID, "unknown arch %d", cfg->arch);
+  SSR_CHECK(cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_EDSR || cfg->arch == SSR_ARCH_RCAN, SSR_E_INVALID,
+            "unknown arch %d", cfg->arch);
   SSR_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SSR_E_INVALID, "unknown precision %d", cfg->precision);
   SSR_CHECK(cfg->scale >= 1 && cfg->scale <= 8, SSR_E_INVALID, "bad scale %d", cfg->scale);
   if (cfg->arch == SSR_ARCH_SWINIR)
@@ -1086,7 +1261,7 @@ int ssr_model_finalize(ssr_model_t* m) {
   SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
   SSR_CUDA(cudaSetDevice(m->device));
   m->host_arena.clear();
-  int r = m->cfg.arch == SSR_ARCH_SWINIR ? finalize_swinir(m) : finalize_edsr(m);
+  int r = m->cfg.arch == SSR_ARCH_SWINIR ? finalize_swinir(m) : m->cfg.arch == SSR_ARCH_RCAN ? finalize_rcan(m) : finalize_edsr(m);
   if (r != SSR_OK) return r;
   if (m->arena && m->arena_bytes < m->host_arena.size()) {
     cudaFree(m->arena);

@@ -211,6 +211,20 @@ int launch_fold_ln_linear(const float* W, const float* b, const float* gamma, co
 int launch_pack_heads(const float* in, void* out, int M, int heads, int d, int DP, int ld, int elem, int round_tf32,
                       cudaStream_t s);
 
+// RCAN channel-attention gate + RCAB residual: out = res + t * sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2)
+struct CaArgs {
+  const float* t;    // fp32 [B][HW][ld]: output of the RCAB's second conv
+  const float* res;  // fp32 [B][HW][ld]: RCAB input
+  int ld, B, HW, C, CP, R;
+  const float *W1, *b1, *W2, *b2;  // [R][C], [R], [C][R], [C] fp32
+  float* partial;                  // scratch [B][nsplit][C]
+  int nsplit;
+  float* out_f32;  // [B][HW][ld]
+  void* out_T;     // T-typed copy for the next conv
+  int ld_T, elem, round_tf32;
+};
+int launch_channel_attention(const CaArgs& a, cudaStream_t s);
+
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s);
 int launch_attn_simt(const AttnArgs& a, cudaStream_t s);
@@ -219,6 +233,8 @@ int launch_layernorm(const LnArgs& a, cudaStream_t s);
 int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s);
 int launch_conv_last(const ConvLastArgs& a, cudaStream_t s);
 int launch_blend(const BlendArgs& a, cudaStream_t s);
+int launch_shuffle_finish(const float* in, int ld, int B, int Hp, int Wp, int scale, int ch, int cw, const float* shift3,
+                          float out_scale, float u8_scale, float* out_f32, uint8_t* out_u8, cudaStream_t s);
 // fp32 [rows][cols] -> T [rows][ld] (zero pad), optional per-row-block scale; used by op-level tests
 int launch_pack_rows(const float* in, int rows, int cols, void* out, int ld, int elem, int round_tf32, cudaStream_t s);
 int launch_unpack_rows(const void* in, int ld, int elem, float* out, int rows, int cols, cudaStream_t s);

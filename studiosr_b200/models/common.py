@@ -213,3 +213,15 @@ class ResBlock(nn.Module):
         super().__init__()
         self.body = nn.Sequential(conv2d(n_feats, n_feats, kernel_size), nn.ReLU(True), conv2d(n_feats, n_feats, kernel_size))
         self.res_scale = res_scale
+
+
+class ChannelAttention(nn.Module):
+    """Parameter container with the reference's key names (common.py:156-170): avg-pool -> 1x1 conv -> ReLU ->
+    1x1 conv -> sigmoid gate.  The arithmetic runs in libssr_b200 (pool + gate kernels)."""
+
+    def __init__(self, channel: int, reduction: int = 16) -> None:
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.conv_du = nn.Sequential(nn.Conv2d(channel, channel // reduction, 1), nn.ReLU(True),
+                                     nn.Conv2d(channel // reduction, channel, 1), nn.Sigmoid())
+

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 SWINIR_CASES = [
     "swinir_tiny_x4_eval_2x20x28", "swinir_tiny_x4_eval_1x16x16", "swinir_tiny_x4_train_1x12x12",
     "swinir_tiny_x4_train_2x16x24", "swinir_tiny_x2_eval_1x12x12", "swinir_tiny_x3_eval_1x8x8",
-    "swinir_tiny_x8_eval_1x8x8", "swinir_full_x4_eval_cfg1",
+    "swinir_tiny_x8_eval_1x8x8", "swinir_full_x4_eval_cfg1", "swinir_light_x4_eval_1x12x20",
 ]
 EDSR_CASES = ["edsr_tiny_x4_2x12x20", "edsr_tiny_x2_1x9x11", "edsr_tiny_x3_1x8x8", "edsr_full_x4_1x24x24"]
 # "fp32" (CUDA-core FMA) carries the north-star fp32 claim (<= 1e-3; held to 1e-4 here).  "tf32" is an
@@ -86,6 +86,33 @@ def test_edsr_matches_reference_golden(name, prec, golden_meta):
         assert err <= ABS_TOL[prec], f"{name} [{prec}] max-abs {err:.3e}"
     else:
         assert err <= 6e-2 and _psnr_delta(y, ref) <= 0.01, f"{name} [bf16] max-abs {err:.3e}"
+
+
+RCAN_CASES = ["rcan_tiny_x4_2x12x20", "rcan_tiny_x2_1x9x11", "rcan_tiny_x3_1x8x8", "rcan_full_x4_1x24x24"]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("name", RCAN_CASES)
+def test_rcan_matches_reference_golden(name, prec, golden_meta):
+    """RCAN forward (rcan.py:68-77; 10 x 20 RCABs with channel attention) against the reference's own outputs."""
+    from studiosr_b200.models import RCAN
+
+    c = golden_meta[name]
+    m = RCAN(**c["cfg"])
+    m.load_state_dict(synth.rcan_weights(c["cfg"], c["wseed"]), strict=True)
+    m = m.cuda().eval()
+    m.precision = prec
+    x = synth.image_batch(c["shape"], c["xseed"]).cuda()
+    with torch.no_grad():
+        y = m(x).float().cpu()
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    err = (y - ref).abs().max().item()
+    if prec in ABS_TOL:
+        tol = ABS_TOL[prec] * (4 if "full" in name else 1)  # 400 convs deep: summation-order noise accumulates
+        assert err <= tol, f"{name} [{prec}] max-abs {err:.3e}"
+    else:
+        assert err <= 1e-1 and _psnr_delta(y, ref) <= 0.01, f"{name} [bf16] max-abs {err:.3e}"
 
 
 def test_inference_u8_matches_reference(golden_meta):
