@@ -214,6 +214,111 @@ def edsr_forward(P: Dict, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
     return F.conv2d(y, P["add_mean.weight"], P["add_mean.bias"])
 
 
+# --------------------------------------------------------------------------- HAT
+def _hat_window_attention(P, pre, xw, heads, ws, mask):
+    """hat.py:85-110 -- same arithmetic as SwinIR's WindowAttention with an explicit 16x16 rpi."""
+    B_, N, C = xw.shape
+    d = C // heads
+    qkv = (xw @ P[pre + ".qkv.weight"].t() + P[pre + ".qkv.bias"]).reshape(B_, N, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * d**-0.5, qkv[1], qkv[2]
+    attn = q @ k.transpose(-2, -1) + rel_pos_bias(P[pre + ".relative_position_bias_table"], ws)[None]
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = (attn.view(B_ // nW, nW, heads, N, N) + mask[None, :, None]).view(-1, heads, N, N)
+    x = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(B_, N, C)
+    return x @ P[pre + ".proj.weight"].t() + P[pre + ".proj.bias"]
+
+
+def _hat_cab(P, pre, x_nhwc):
+    """hat.py:41-52 (+ ChannelAttention :25-38) on NHWC input; returns NHWC."""
+    x = x_nhwc.permute(0, 3, 1, 2)
+    t = gelu(conv3x3(P, pre + ".cab.0", x))
+    t = conv3x3(P, pre + ".cab.2", t)
+    y = t.mean(dim=(2, 3), keepdim=True)
+    y = torch.relu(F.conv2d(y, P[pre + ".cab.3.attention.1.weight"], P[pre + ".cab.3.attention.1.bias"]))
+    y = torch.sigmoid(F.conv2d(y, P[pre + ".cab.3.attention.3.weight"], P[pre + ".cab.3.attention.3.bias"]))
+    return (t * y).permute(0, 2, 3, 1)
+
+
+def hat_hab(P, pre, x, heads, ws, shift, conv_scale):
+    """hat.py:154-195 on [B,H,W,C]."""
+    B, H, W, C = x.shape
+    y = layer_norm(x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
+    conv_x = _hat_cab(P, pre + ".conv_block", y)
+    if shift > 0:
+        y = torch.roll(y, (-shift, -shift), (1, 2))
+    mask = shift_mask(H, W, ws, shift, x.dtype) if shift > 0 else None  # hat.py:171: no mask on unshifted blocks
+    a = _hat_window_attention(P, pre + ".attn", to_windows(y, ws), heads, ws, mask)
+    y = from_windows(a, ws, B, H, W)
+    if shift > 0:
+        y = torch.roll(y, (shift, shift), (1, 2))
+    x = x + y + conv_x * conv_scale
+    y = layer_norm(x, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
+    y = gelu(y @ P[pre + ".mlp.fc1.weight"].t() + P[pre + ".mlp.fc1.bias"])
+    return x + y @ P[pre + ".mlp.fc2.weight"].t() + P[pre + ".mlp.fc2.bias"]
+
+
+def hat_ocab(P, pre, x, heads, ws, overlap_ratio):
+    """hat.py:240-293 on [B,H,W,C]: queries in ws x ws windows, keys / values in the (1 + overlap_ratio) ws windows
+    around them (nn.Unfold with zero padding: out-of-image keys are ZERO vectors that still take part in the softmax
+    with their bias term)."""
+    B, H, W, C = x.shape
+    d = C // heads
+    wse = ws + int(ws * overlap_ratio)
+    pad = (wse - ws) // 2
+    y = layer_norm(x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
+    qkv = y @ P[pre + ".qkv.weight"].t() + P[pre + ".qkv.bias"]  # [B,H,W,3C]
+    q = to_windows(qkv[..., :C], ws)  # [nW*B, ws*ws, C]
+    kv = F.pad(qkv[..., C:].permute(0, 3, 1, 2), (pad, pad, pad, pad))  # [B,2C,H+2p,W+2p], zeros
+    nwy, nwx = H // ws, W // ws
+    kw = kv.unfold(2, wse, ws).unfold(3, wse, ws)  # [B,2C,nwy,nwx,wse,wse]
+    kw = kw.permute(0, 2, 3, 4, 5, 1).reshape(B * nwy * nwx, wse * wse, 2 * C)
+    k, v = kw[..., :C], kw[..., C:]
+    B_ = q.shape[0]
+    qh = q.reshape(B_, ws * ws, heads, d).permute(0, 2, 1, 3) * d**-0.5
+    kh = k.reshape(B_, wse * wse, heads, d).permute(0, 2, 1, 3)
+    vh = v.reshape(B_, wse * wse, heads, d).permute(0, 2, 1, 3)
+    table = P[pre + ".relative_position_bias_table"]
+    o = torch.arange(ws * ws)
+    e = torch.arange(wse * wse)
+    dy = (e // wse)[None, :] - (o // ws)[:, None] + ws - 1
+    dx = (e % wse)[None, :] - (o % ws)[:, None] + ws - 1
+    bias = table[(dy * (ws + wse - 1) + dx).reshape(-1)].reshape(ws * ws, wse * wse, heads).permute(2, 0, 1)
+    attn = torch.softmax(qh @ kh.transpose(-2, -1) + bias[None], -1)
+    a = (attn @ vh).transpose(1, 2).reshape(B_, ws * ws, C)
+    y = from_windows(a, ws, B, H, W)
+    x = y @ P[pre + ".proj.weight"].t() + P[pre + ".proj.bias"] + x
+    y = layer_norm(x, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
+    y = gelu(y @ P[pre + ".mlp.fc1.weight"].t() + P[pre + ".mlp.fc1.bias"])
+    return x + y @ P[pre + ".mlp.fc2.weight"].t() + P[pre + ".mlp.fc2.bias"]
+
+
+def hat_forward(P: Dict, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
+    """hat.py:542-554 (forward), :519-540 (forward_features), RHAG :379-385, AttenBlocks :340-344.
+    Reflect padding to a multiple of the window in BOTH modes (common.py:277-282)."""
+    dt = x.dtype
+    P = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in P.items()}
+    h0, w0 = x.shape[2:]
+    ws, C, s = cfg["window_size"], cfg["embed_dim"], cfg["scale"]
+    x = pad_for_train(x, ws)
+    mean = torch.tensor([0.4488, 0.4371, 0.4040], dtype=dt).view(1, 3, 1, 1)
+    x = x / cfg["img_range"] - mean
+    x = conv3x3(P, "conv_first", x)
+    t = layer_norm(x.permute(0, 2, 3, 1), P["patch_embed.norm.weight"], P["patch_embed.norm.bias"])
+    for li, (depth, nh) in enumerate(zip(cfg["depths"], cfg["num_heads"])):
+        g = t
+        for bi in range(depth):
+            t = hat_hab(P, f"layers.{li}.residual_group.blocks.{bi}", t, nh, ws, 0 if bi % 2 == 0 else ws // 2, cfg["conv_scale"])
+        t = hat_ocab(P, f"layers.{li}.residual_group.overlap_attn", t, nh, ws, cfg["overlap_ratio"])
+        t = conv3x3(P, f"layers.{li}.conv", t.permute(0, 3, 1, 2)).permute(0, 2, 3, 1) + g
+    t = layer_norm(t, P["norm.weight"], P["norm.bias"])
+    y = conv3x3(P, "conv_after_body", t.permute(0, 3, 1, 2)) + x
+    y = F.leaky_relu(conv3x3(P, "conv_before_upsample.0", y), 0.01)
+    y = conv3x3(P, "conv_last", _upsampler(P, "upsample", y, s, 64))
+    y = (y + mean) * cfg["img_range"]
+    return y[:, :, : h0 * s, : w0 * s]
+
+
 # --------------------------------------------------------------------------- RCAN
 def channel_attention(P: Dict, pre: str, x: torch.Tensor) -> torch.Tensor:
     """common.py:156-170 -- x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2), 1x1 convs on the pooled [B,C,1,1]."""

@@ -149,6 +149,71 @@ def edsr_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
     return sd
 
 
+HAT_DEFAULT = dict(scale=4, n_colors=3, img_range=1.0, embed_dim=180, depths=[6] * 6, num_heads=[6] * 6, window_size=16,
+                   mlp_ratio=2.0, compress_ratio=3, squeeze_factor=30, conv_scale=0.01, overlap_ratio=0.5)
+HAT_TINY = dict(scale=4, n_colors=3, img_range=1.0, embed_dim=60, depths=[2, 2], num_heads=[6, 6], window_size=16,
+                mlp_ratio=2.0, compress_ratio=3, squeeze_factor=30, conv_scale=0.01, overlap_ratio=0.5)
+
+
+def hat_rpi_sa(ws: int) -> torch.Tensor:
+    """hat.py:475-488 restated: index = (dy + ws - 1) * (2 ws - 1) + (dx + ws - 1)."""
+    return relative_position_index(ws)
+
+
+def hat_rpi_oca(ws: int, overlap_ratio: float) -> torch.Tensor:
+    """hat.py:490-513 restated: query (yo, xo) in the ws x ws window, key (ye, xe) in the wse x wse window;
+    index = (ye - yo + ws - wse + 1 ... shifted to start at 0) * (ws + wse - 1) + (xe - xo + ...)."""
+    wse = ws + int(overlap_ratio * ws)
+    o = torch.arange(ws * ws)
+    e = torch.arange(wse * wse)
+    dy = (e // wse)[None, :] - (o // ws)[:, None] + ws - 1
+    dx = (e % wse)[None, :] - (o % ws)[:, None] + ws - 1
+    return (dy * (ws + wse - 1) + dx).to(torch.int64)
+
+
+def hat_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of reference HAT(**cfg) (hat.py:388-470), synthetic values; integer buffers restated."""
+    g = _gen(seed)
+    sd = OrderedDict()
+    C, ws, nc = cfg["embed_dim"], cfg["window_size"], cfg["n_colors"]
+    hid = int(C * cfg["mlp_ratio"])
+    wse = ws + int(cfg["overlap_ratio"] * ws)
+    sd["relative_position_index_SA"] = hat_rpi_sa(ws)
+    sd["relative_position_index_OCA"] = hat_rpi_oca(ws, cfg["overlap_ratio"])
+    _conv(g, sd, "conv_first", C, nc)
+    _ln(g, sd, "patch_embed.norm", C)
+    for li, (depth, nh) in enumerate(zip(cfg["depths"], cfg["num_heads"])):
+        for bi in range(depth):
+            p = f"layers.{li}.residual_group.blocks.{bi}"
+            _ln(g, sd, p + ".norm1", C)
+            sd[p + ".attn.relative_position_bias_table"] = _randn(g, (2 * ws - 1) ** 2, nh, std=0.5)
+            _linear(g, sd, p + ".attn.qkv", 3 * C, C)
+            _linear(g, sd, p + ".attn.proj", C, C, gain=0.5)
+            _conv(g, sd, p + ".conv_block.cab.0", C // cfg["compress_ratio"], C)
+            _conv(g, sd, p + ".conv_block.cab.2", C, C // cfg["compress_ratio"], gain=8.0)  # x conv_scale 0.01: keep it visible
+            _conv(g, sd, p + ".conv_block.cab.3.attention.1", C // cfg["squeeze_factor"], C, k=1)
+            _conv(g, sd, p + ".conv_block.cab.3.attention.3", C, C // cfg["squeeze_factor"], k=1, gain=2.0)
+            _ln(g, sd, p + ".norm2", C)
+            _linear(g, sd, p + ".mlp.fc1", hid, C)
+            _linear(g, sd, p + ".mlp.fc2", C, hid, gain=0.5)
+        p = f"layers.{li}.residual_group.overlap_attn"
+        sd[p + ".relative_position_bias_table"] = _randn(g, (ws + wse - 1) ** 2, nh, std=0.5)
+        _ln(g, sd, p + ".norm1", C)
+        _linear(g, sd, p + ".qkv", 3 * C, C)
+        _linear(g, sd, p + ".proj", C, C, gain=0.5)
+        _ln(g, sd, p + ".norm2", C)
+        _linear(g, sd, p + ".mlp.fc1", hid, C)
+        _linear(g, sd, p + ".mlp.fc2", C, hid, gain=0.5)
+        _conv(g, sd, f"layers.{li}.conv", C, C, gain=0.5)
+    _ln(g, sd, "norm", C)
+    _conv(g, sd, "conv_after_body", C, C, gain=0.5)
+    _conv(g, sd, "conv_before_upsample.0", 64, C)
+    for i, cout, _ in upsampler_convs(cfg["scale"], 64):
+        _conv(g, sd, f"upsample.{i}", cout, 64)
+    _conv(g, sd, "conv_last", nc, 64)
+    return sd
+
+
 RCAN_DEFAULT = dict(scale=4, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=20, n_resgroups=10, reduction=16)
 RCAN_TINY = dict(scale=4, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=2, n_resgroups=2, reduction=16)
 

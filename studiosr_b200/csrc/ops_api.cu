@@ -156,6 +156,7 @@ int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b
   } else {
     g.out_T = yp; g.ld_T = ldo;
   }
+  g.dbg = g_dbg_buf;
   SSR_TRY(dispatch_gemm(precision, g, elem, s));
   if (res) return launch_nhwc_to_nchw(yf, NP, 4, y, B, Cout, H, Wd, s);
   return launch_nhwc_to_nchw(yp, ldo, elem, y, B, Cps, H * r, Wd * r, s);

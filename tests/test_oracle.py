@@ -14,6 +14,8 @@ SWINIR_CASES = [
     "swinir_tiny_x8_eval_1x8x8", "swinir_light_x4_eval_1x12x20", "swinir_full_x4_eval_cfg1",
 ]
 EDSR_CASES = ["edsr_tiny_x4_2x12x20", "edsr_tiny_x2_1x9x11", "edsr_tiny_x3_1x8x8", "edsr_full_x4_1x24x24"]
+HAT_CASES = ["hat_tiny_x4_eval_2x20x40", "hat_tiny_x4_train_1x32x32", "hat_tiny_x2_eval_1x16x48", "hat_tiny_x3_eval_1x17x17",
+             "hat_full_x4_eval_1x64x64"]
 RCAN_CASES = ["rcan_tiny_x4_2x12x20", "rcan_tiny_x2_1x9x11", "rcan_tiny_x3_1x8x8", "rcan_full_x4_1x24x24"]
 
 
@@ -27,6 +29,19 @@ def test_swinir_oracle_matches_reference_golden(name, golden_meta):
     assert list(y.shape) == c["out_shape"]
     # same fp32 math, different op order: reference fp32-vs-fp64 noise is 3.6e-7
     assert (y - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name", HAT_CASES)
+def test_hat_oracle_matches_reference_golden(name, golden_meta):
+    """oracle/sr_oracle.py:hat_forward (HAB + CAB + OCAB, hat.py) vs the reference's own HAT forward
+    (fixtures: oracle/make_golden_hat.py; cfg3-class full model included)."""
+    c = golden_meta[name]
+    P = synth.hat_weights(c["cfg"], c["wseed"])
+    x = synth.image_batch(c["shape"], c["xseed"])
+    y = O.hat_forward(P, x, c["cfg"])
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    assert (y - ref).abs().max().item() <= 2e-5
 
 
 @pytest.mark.parametrize("name", RCAN_CASES)
