@@ -40,7 +40,7 @@ enum {
   SSR_E_WORKSPACE = -5  /* workspace too small */
 };
 
-enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1, SSR_ARCH_RCAN = 2 };
+enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1, SSR_ARCH_RCAN = 2, SSR_ARCH_HAT = 3 };
 
 /* arithmetic of the contractions */
 enum {
@@ -80,6 +80,11 @@ typedef struct ssr_model_config {
   /* RCAN (n_feats, n_resblocks as above) */
   int n_resgroups;
   int reduction;
+  /* HAT (hat.py:389-406; embed_dim, depths, num_heads, window_size, mlp_ratio as SwinIR) */
+  int compress_ratio;
+  int squeeze_factor;
+  float conv_scale;
+  float overlap_ratio;
 } ssr_model_config;
 
 typedef struct ssr_model ssr_model_t;

@@ -38,6 +38,11 @@ def main() -> None:
         doc["cases"][name] = dict(cfg=cfg, wseed=wseed, shape=list(shape), xseed=xseed, training=training,
                                   out_shape=list(y.shape), absmax=float(y.abs().max()))
         print(name, tuple(y.shape), float(y.abs().max()))
+    # the index buffers a freshly constructed reference model computes for itself (hat.py:475-513) -- the OCA one
+    # carries the negative-index quirk the restatement has to reproduce
+    fresh = models.HAT(embed_dim=60, depths=[2], num_heads=[6], window_size=16)
+    np.savez_compressed(os.path.join(OUT, "hat_ops.npz"), rpi_sa=fresh.relative_position_index_SA.numpy(),
+                        rpi_oca=fresh.relative_position_index_OCA.numpy())
     with open(os.path.join(OUT, "meta.json"), "w") as f:
         json.dump(doc, f, indent=1, sort_keys=True)
 

@@ -281,9 +281,11 @@ def hat_ocab(P, pre, x, heads, ws, overlap_ratio):
     table = P[pre + ".relative_position_bias_table"]
     o = torch.arange(ws * ws)
     e = torch.arange(wse * wse)
-    dy = (e // wse)[None, :] - (o // ws)[:, None] + ws - 1
-    dx = (e % wse)[None, :] - (o % ws)[:, None] + ws - 1
-    bias = table[(dy * (ws + wse - 1) + dx).reshape(-1)].reshape(ws * ws, wse * wse, heads).permute(2, 0, 1)
+    # hat.py:508-512: offsets are shifted by ws - wse + 1 (negative!), the table is read with negative-index wrap-around
+    dy = (e // wse)[None, :] - (o // ws)[:, None] + ws - wse + 1
+    dx = (e % wse)[None, :] - (o % ws)[:, None] + ws - wse + 1
+    idx = (dy * (ws + wse - 1) + dx).reshape(-1)
+    bias = table[idx % table.shape[0]].reshape(ws * ws, wse * wse, heads).permute(2, 0, 1)
     attn = torch.softmax(qh @ kh.transpose(-2, -1) + bias[None], -1)
     a = (attn @ vh).transpose(1, 2).reshape(B_, ws * ws, C)
     y = from_windows(a, ws, B, H, W)

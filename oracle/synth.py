@@ -161,13 +161,14 @@ def hat_rpi_sa(ws: int) -> torch.Tensor:
 
 
 def hat_rpi_oca(ws: int, overlap_ratio: float) -> torch.Tensor:
-    """hat.py:490-513 restated: query (yo, xo) in the ws x ws window, key (ye, xe) in the wse x wse window;
-    index = (ye - yo + ws - wse + 1 ... shifted to start at 0) * (ws + wse - 1) + (xe - xo + ...)."""
+    """hat.py:490-513 restated, quirk included: the reference shifts the (key - query) offsets by
+    ws - wse + 1 (= -7 for 16 / 24), NOT to zero, so the index runs over [-880, 640] and the bias table is
+    read with Python's negative indexing (table[i] == table[i + 1521] for i < 0)."""
     wse = ws + int(overlap_ratio * ws)
     o = torch.arange(ws * ws)
     e = torch.arange(wse * wse)
-    dy = (e // wse)[None, :] - (o // ws)[:, None] + ws - 1
-    dx = (e % wse)[None, :] - (o % ws)[:, None] + ws - 1
+    dy = (e // wse)[None, :] - (o // ws)[:, None] + ws - wse + 1
+    dx = (e % wse)[None, :] - (o % ws)[:, None] + ws - wse + 1
     return (dy * (ws + wse - 1) + dx).to(torch.int64)
 
 

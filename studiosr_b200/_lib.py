@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssr_b200.so")
 
-SSR_ARCH_SWINIR, SSR_ARCH_EDSR, SSR_ARCH_RCAN = 0, 1, 2
+SSR_ARCH_SWINIR, SSR_ARCH_EDSR, SSR_ARCH_RCAN, SSR_ARCH_HAT = 0, 1, 2, 3
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
 PAD_EVAL, PAD_TRAIN = 0, 1
@@ -25,6 +25,7 @@ class ModelConfig(ctypes.Structure):
         ("num_heads", c_int * SSR_MAX_LAYERS), ("window_size", c_int), ("mlp_ratio", c_float), ("upsampler", c_int),
         ("n_feats", c_int), ("n_resblocks", c_int), ("res_scale", c_float),
         ("n_resgroups", c_int), ("reduction", c_int),
+        ("compress_ratio", c_int), ("squeeze_factor", c_int), ("conv_scale", c_float), ("overlap_ratio", c_float),
     ]
 
 

@@ -1,6 +1,7 @@
 from .common import Model
 from .edsr import EDSR
+from .hat import HAT
 from .rcan import RCAN
 from .swinir import SwinIR
 
-__all__ = ["Model", "SwinIR", "EDSR", "RCAN"]
+__all__ = ["Model", "SwinIR", "HAT", "EDSR", "RCAN"]

@@ -44,6 +44,16 @@ def test_hat_oracle_matches_reference_golden(name, golden_meta):
     assert (y - ref).abs().max().item() <= 2e-5
 
 
+def test_hat_index_buffers_match_reference():
+    """relative_position_index_SA / _OCA as the reference computes them (the OCA one runs over [-880, 640])."""
+    g = load_golden("hat_ops")
+    assert (synth.hat_rpi_sa(16).numpy() == g["rpi_sa"]).all()
+    assert (synth.hat_rpi_oca(16, 0.5).numpy() == g["rpi_oca"]).all()
+    from studiosr_b200.models.hat import _rpi_oca
+
+    assert (_rpi_oca(16, 0.5).numpy() == g["rpi_oca"]).all()
+
+
 @pytest.mark.parametrize("name", RCAN_CASES)
 def test_rcan_oracle_matches_reference_golden(name, golden_meta):
     """oracle/sr_oracle.py:rcan_forward vs the reference's own RCAN forward (fixtures: oracle/make_golden_rcan.py)."""
