@@ -203,8 +203,7 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(const AttnArgs a) {
   const int wy = w % nwy;
   const int b = w / nwy;
   const int tid = threadIdx.x;
-  const float* qkv = reinterpret_cast<const float*>(a.qkv);
-  float* o = reinterpret_cast<float*>(a.o);
+  const int elem = a.elem ? a.elem : 4;  // 4: fp32 activations (fp32 / tf32 models), 2: bf16
   const int nb = 2 * a.ws - 1;
 
   for (int t = tid; t < N; t += blockDim.x) {
@@ -218,16 +217,16 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(const AttnArgs a) {
   for (int h = 0; h < a.heads; ++h) {
     for (int e = tid; e < N * a.DP; e += blockDim.x) {
       const int t = e / a.DP, j = e % a.DP;
-      const float* row = qkv + (size_t)pix[t] * a.ld_qkv + h * a.DP + j;
-      ks[t * DPp + j] = row[a.QP];
-      vs[t * DPp + j] = row[2 * a.QP];
+      const size_t row = (size_t)pix[t] * a.ld_qkv + h * a.DP + j;
+      ks[t * DPp + j] = load_elem(a.qkv, row + a.QP, elem);
+      vs[t * DPp + j] = load_elem(a.qkv, row + 2 * a.QP, elem);
     }
     const float* btab = a.bias + (size_t)h * nb * nb;
     for (int q0 = 0; q0 < N; q0 += 64) {
       __syncthreads();
       for (int e = tid; e < 64 * a.DP; e += blockDim.x) {
         const int t = e / a.DP, j = e % a.DP;
-        qs[t * DPp + j] = qkv[(size_t)pix[q0 + t] * a.ld_qkv + h * a.DP + j];
+        qs[t * DPp + j] = load_elem(a.qkv, (size_t)pix[q0 + t] * a.ld_qkv + h * a.DP + j, elem);
       }
       __syncthreads();
       for (int e = tid; e < 64 * N; e += blockDim.x) {
@@ -262,11 +261,118 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(const AttnArgs a) {
         float acc = 0.0f;
         if (c < a.d)
           for (int j = 0; j < N; ++j) acc = fmaf(S[i * (N + 1) + j], vs[j * DPp + c], acc);
-        o[(size_t)pix[q0 + i] * a.ld_o + h * a.DP + c] = acc;
+        store_elem(a.o, (size_t)pix[q0 + i] * a.ld_o + h * a.DP + c, elem, acc, 0);
       }
     }
     __syncthreads();
   }
+}
+
+// =============================================================================================
+// HAT overlapping cross-attention core (hat.py:257-284): queries = one ws x ws window, keys / values =
+// the kws x kws window around it (nn.Unfold: stride ws, zero padding (kws - ws) / 2 -- out-of-image keys
+// are ZERO vectors that still enter the softmax with their bias).  One CTA per window; per head the key
+// tile is staged once per 32-query block for the scores and replaced by the value tile for P.V.
+// Bias index = (ky - qy + ws - kws + 1) * nb + (kx - qx + ws - kws + 1), nb = ws + kws - 1, with the
+// reference's negative-index wrap-around (hat.py:508-512 + Python indexing).
+// =============================================================================================
+__global__ void __launch_bounds__(256) attn_oca_kernel(const AttnArgs a) {
+  extern __shared__ float smem[];
+  const int Nq = a.ws * a.ws, Nk = a.kws * a.kws;
+  const int DPp = a.DP + 1;
+  float* kv = smem;              // [Nk][DP+1]
+  float* qs = kv + Nk * DPp;     // [32][DP+1]
+  float* S = qs + 32 * DPp;      // [32][Nk+1]
+  int* kpix = reinterpret_cast<int*>(S + 32 * (Nk + 1));  // [Nk] source row or -1 (zero padding)
+  int* qpix = kpix + Nk;                                  // [Nq]
+  const int elem = a.elem ? a.elem : 4;
+  const int nwx = a.W / a.ws, nwy = a.H / a.ws;
+  int w = blockIdx.x;
+  const int wx = w % nwx;
+  w /= nwx;
+  const int wy = w % nwy;
+  const int b = w / nwy;
+  const int tid = threadIdx.x;
+  const int pad = (a.kws - a.ws) / 2;
+  const int nb = a.ws + a.kws - 1, off = a.ws - a.kws + 1;
+  for (int t = tid; t < Nk; t += blockDim.x) {
+    const int y = wy * a.ws - pad + t / a.kws, x = wx * a.ws - pad + t % a.kws;
+    kpix[t] = (y >= 0 && y < a.H && x >= 0 && x < a.W) ? (b * a.H + y) * a.W + x : -1;
+  }
+  for (int t = tid; t < Nq; t += blockDim.x) qpix[t] = (b * a.H + wy * a.ws + t / a.ws) * a.W + wx * a.ws + t % a.ws;
+  __syncthreads();
+  for (int h = 0; h < a.heads; ++h) {
+    const float* btab = a.bias + (size_t)h * nb * nb;
+    for (int q0 = 0; q0 < Nq; q0 += 32) {
+      __syncthreads();
+      for (int e = tid; e < Nk * a.DP; e += blockDim.x) {  // keys
+        const int t = e / a.DP, j = e % a.DP;
+        kv[t * DPp + j] = kpix[t] >= 0 ? load_elem(a.qkv, (size_t)kpix[t] * a.ld_qkv + a.QP + h * a.DP + j, elem) : 0.0f;
+      }
+      for (int e = tid; e < 32 * a.DP; e += blockDim.x) {
+        const int t = e / a.DP, j = e % a.DP;
+        qs[t * DPp + j] = load_elem(a.qkv, (size_t)qpix[q0 + t] * a.ld_qkv + h * a.DP + j, elem);
+      }
+      __syncthreads();
+      for (int e = tid; e < 32 * Nk; e += blockDim.x) {
+        const int i = e / Nk, j = e % Nk;
+        const int ti = q0 + i;
+        float sc = 0.0f;
+        for (int c = 0; c < a.d; ++c) sc = fmaf(qs[i * DPp + c], kv[j * DPp + c], sc);
+        int idx = (j / a.kws - ti / a.ws + off) * nb + (j % a.kws - ti % a.ws + off);
+        if (idx < 0) idx += nb * nb;
+        S[i * (Nk + 1) + j] = sc + __ldg(btab + idx);
+      }
+      __syncthreads();
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int i = warp; i < 32; i += 8) {
+        float mx = -INFINITY;
+        for (int j = lane; j < Nk; j += 32) mx = fmaxf(mx, S[i * (Nk + 1) + j]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < Nk; j += 32) {
+          const float p = expf(S[i * (Nk + 1) + j] - mx);
+          S[i * (Nk + 1) + j] = p;
+          sum += p;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < Nk; j += 32) S[i * (Nk + 1) + j] *= inv;
+      }
+      for (int e = tid; e < Nk * a.DP; e += blockDim.x) {  // values replace the keys (all score reads are done: the
+        const int t = e / a.DP, j = e % a.DP;              // softmax above touches S only, the barrier below orders the rest)
+        kv[t * DPp + j] = kpix[t] >= 0 ? load_elem(a.qkv, (size_t)kpix[t] * a.ld_qkv + 2 * a.QP + h * a.DP + j, elem) : 0.0f;
+      }
+      __syncthreads();
+      for (int e = tid; e < 32 * a.DP; e += blockDim.x) {
+        const int i = e / a.DP, c = e % a.DP;
+        float acc = 0.0f;
+        if (c < a.d)
+          for (int j = 0; j < Nk; ++j) acc = fmaf(S[i * (Nk + 1) + j], kv[j * DPp + c], acc);
+        store_elem(a.o, (size_t)qpix[q0 + i] * a.ld_o + h * a.DP + c, elem, acc, 0);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_attn_oca(const AttnArgs& a, cudaStream_t s) {
+  SSR_CHECK(a.H % a.ws == 0 && a.W % a.ws == 0, SSR_E_INVALID, "attn_oca: %dx%d not a multiple of ws=%d", a.H, a.W, a.ws);
+  SSR_CHECK(a.kws > a.ws && (a.kws - a.ws) % 2 == 0 && (a.ws * a.ws) % 32 == 0, SSR_E_INVALID, "attn_oca: windows %d / %d", a.ws, a.kws);
+  const int Nq = a.ws * a.ws, Nk = a.kws * a.kws;
+  const size_t smem = (size_t)(Nk * (a.DP + 1) + 32 * (a.DP + 1) + 32 * (Nk + 1)) * sizeof(float) + (size_t)(Nk + Nq) * sizeof(int);
+  SSR_CHECK(smem <= 227 * 1024, SSR_E_INVALID, "attn_oca: %zu B of shared memory", smem);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    SSR_CUDA(cudaFuncSetAttribute(attn_oca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int nwin = a.B * (a.H / a.ws) * (a.W / a.ws);
+  ProfScope prof("attn_oca", 4.0 * nwin * Nq * Nk * a.d * a.heads, (double)nwin * (Nq + 2.25 * Nq) * a.heads * a.d * (a.elem ? a.elem : 4), s);
+  attn_oca_kernel<<<nwin, 256, smem, s>>>(a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
 }
 
 int launch_attn_simt(const AttnArgs& a, cudaStream_t s) {
@@ -623,7 +729,7 @@ __global__ void __launch_bounds__(256) ca_apply_kernel(const CaArgs a) {
     if (c < a.C) {
       float s = a.b2[c];
       for (int r = 0; r < a.R; ++r) s = fmaf(a.W2[c * a.R + r], hid[r], s);
-      g = 1.0f / (1.0f + expf(-s));
+      g = a.scale / (1.0f + expf(-s));
     }
     gate[c] = g;  // padded channels: t is zero there anyway
   }
@@ -638,8 +744,9 @@ __global__ void __launch_bounds__(256) ca_apply_kernel(const CaArgs a) {
     const float4 rv = *reinterpret_cast<const float4*>(a.res + m * a.ld + c);
     float4 o;
     o.x = fmaf(tv.x, gate[c], rv.x); o.y = fmaf(tv.y, gate[c + 1], rv.y);
-    o.z = fmaf(tv.z, gate[c + 2], rv.z); o.w = fmaf(tv.w, gate[c + 3], rv.w);
+    o.z = fmaf(tv.z, gate[c + 2], rv.z); o.w = fmaf(tv.w, gate[c + 3], rv.w);  // gate already carries a.scale
     *reinterpret_cast<float4*>(a.out_f32 + m * a.ld + c) = o;
+    if (!a.out_T) continue;
     if (a.elem == 2) {
       uint2 pk;
       pk.x = pack_bf16x2(o.x, o.y);

@@ -91,11 +91,15 @@ struct Block {
   Lin qkv, proj, fc1, fc2;
   size_t bias_off = 0;  // float [heads][(2ws-1)^2]
   size_t whp_off = 0, bhp_off = 0, btab_off = 0;  // fused attention kernel operands (k_swin_attn.cu)
+  // HAT: channel attention block of a HAB (hat.py:41-52)
+  Lin cab0, cab2;
+  size_t ca_w1 = 0, ca_b1 = 0, ca_w2 = 0, ca_b2 = 0;
 };
 struct Layer {
   std::vector<Block> blocks;
   Lin conv;
   int heads = 0, d = 0, DP = 0, QP = 0;
+  Block ocab;  // HAT: overlapping cross-attention block closing the group (hat.py:198-293)
 };
 
 }  // namespace ssr
@@ -436,6 +440,112 @@ static int finalize_swinir(ssr_model* m) {
   return SSR_OK;
 }
 
+static size_t pack_raw(ssr_model* m, const std::string& name, size_t numel);
+
+// qkv / proj / fc1 / fc2 of one attention block in the padded-head layout of the un-fused GEMM path, plus the
+// relative-position bias table transposed to [heads][nbias] (shared by SwinIR's un-fused path and HAT)
+static int pack_attn_mlp(ssr_model* m, const std::string& pa, const std::string& pm, const std::string& ptab, const Layer& L,
+                         int nbias, Block* B) {
+  const int C = m->C, HID = m->HID, heads = L.heads, d = L.d, DP = L.DP, QP = L.QP;
+  const float qscale = 1.0f / sqrtf((float)d);
+  auto qkv_row = [=](int n) {
+    const int part = n / QP, hc = n % QP, h = hc / DP, j = hc % DP;
+    return (h < heads && j < d) ? part * C + h * d + j : -1;
+  };
+  auto qkv_scale = [=](int n) { return n < QP ? qscale : 1.0f; };
+  auto ident_c = [=](int k) { return k < C ? k : -1; };
+  auto one = [](int) { return 1.0f; };
+  SSR_TRY(pack_linear(m, pa + ".qkv", 3 * C, C, 3 * QP, m->CP, qkv_row, ident_c, qkv_scale, &B->qkv));
+  B->qkv.N = 3 * QP;
+  auto proj_col = [=](int k) {
+    const int h = k / DP, j = k % DP;
+    return (h < heads && j < d) ? h * d + j : -1;
+  };
+  SSR_TRY(pack_linear(m, pa + ".proj", C, C, m->CP, QP, ident_c, proj_col, one, &B->proj));
+  auto ident_h = [=](int k) { return k < HID ? k : -1; };
+  SSR_TRY(pack_linear(m, pm + ".fc1", HID, C, m->HP, m->CP, ident_h, ident_c, one, &B->fc1));
+  SSR_TRY(pack_linear(m, pm + ".fc2", C, HID, m->CP, m->HP, ident_c, ident_h, one, &B->fc2));
+  const std::vector<float>* T = find_param(m, ptab, (size_t)nbias * heads);
+  if (!T) return SSR_E_STATE;
+  B->bias_off = arena_alloc(m, (size_t)heads * nbias * 4);
+  float* bt = reinterpret_cast<float*>(m->host_arena.data() + B->bias_off);
+  for (int h = 0; h < heads; ++h)
+    for (int i = 0; i < nbias; ++i) bt[h * nbias + i] = (*T)[(size_t)i * heads + h];
+  return SSR_OK;
+}
+
+static int finalize_hat(ssr_model* m) {  // hat.py:388-470
+  const ssr_model_config& c = m->cfg;
+  SSR_CHECK(c.n_colors == 3, SSR_E_INVALID, "n_colors must be 3");
+  const int C = c.embed_dim, ws = c.window_size;
+  m->C = C;
+  m->CP = round_up(C, 64);
+  m->HID = (int)(C * c.mlp_ratio);
+  m->HP = round_up(m->HID, 64);
+  SSR_CHECK(m->CP <= 256, SSR_E_INVALID, "embed_dim %d > 256 not supported", C);
+  SSR_CHECK(c.compress_ratio > 0 && C % c.compress_ratio == 0 && c.squeeze_factor > 0 && C % c.squeeze_factor == 0, SSR_E_INVALID,
+            "embed_dim %d not divisible by compress_ratio %d / squeeze_factor %d", C, c.compress_ratio, c.squeeze_factor);
+  const int wse = ws + (int)(c.overlap_ratio * ws);
+  SSR_CHECK((ws * ws) % 64 == 0 && wse > ws && (wse - ws) % 2 == 0, SSR_E_INVALID, "window %d / overlap window %d unsupported", ws, wse);
+  const int R = C / c.squeeze_factor, Cc = C / c.compress_ratio;
+  SSR_TRY(pack_conv_first(m, "conv_first", C, &m->conv_first_w, &m->conv_first_b));
+  SSR_TRY(pack_ln(m, "patch_embed.norm", C, m->CP, &m->pe_norm));
+  m->layers.clear();
+  m->QPmax = 0;
+  for (int li = 0; li < c.n_layers; ++li) {
+    Layer L;
+    L.heads = c.num_heads[li];
+    SSR_CHECK(L.heads > 0 && C % L.heads == 0, SSR_E_INVALID, "embed_dim %d not divisible by heads %d", C, L.heads);
+    L.d = C / L.heads;
+    SSR_CHECK(L.d <= 32, SSR_E_INVALID, "head_dim %d > 32 not supported", L.d);
+    L.DP = L.d <= 16 ? 16 : 32;
+    L.QP = round_up(L.heads * L.DP, 64);
+    if (L.QP > m->QPmax) m->QPmax = L.QP;
+    char pre[128];
+    for (int bi = 0; bi < c.depths[li]; ++bi) {
+      Block B;
+      snprintf(pre, sizeof(pre), "layers.%d.residual_group.blocks.%d", li, bi);
+      const std::string p(pre);
+      SSR_TRY(pack_ln(m, p + ".norm1", C, m->CP, &B.norm1));
+      SSR_TRY(pack_ln(m, p + ".norm2", C, m->CP, &B.norm2));
+      SSR_TRY(pack_attn_mlp(m, p + ".attn", p + ".mlp", p + ".attn.relative_position_bias_table", L, (2 * ws - 1) * (2 * ws - 1), &B));
+      SSR_TRY(pack_conv(m, p + ".conv_block.cab.0", Cc, C, 0, &B.cab0));
+      SSR_TRY(pack_conv(m, p + ".conv_block.cab.2", C, Cc, 0, &B.cab2));
+      B.ca_w1 = pack_raw(m, p + ".conv_block.cab.3.attention.1.weight", (size_t)R * C);
+      B.ca_b1 = pack_raw(m, p + ".conv_block.cab.3.attention.1.bias", (size_t)R);
+      B.ca_w2 = pack_raw(m, p + ".conv_block.cab.3.attention.3.weight", (size_t)C * R);
+      B.ca_b2 = pack_raw(m, p + ".conv_block.cab.3.attention.3.bias", (size_t)C);
+      if (B.ca_w1 == (size_t)-1 || B.ca_b1 == (size_t)-1 || B.ca_w2 == (size_t)-1 || B.ca_b2 == (size_t)-1) return SSR_E_STATE;
+      L.blocks.push_back(B);
+    }
+    snprintf(pre, sizeof(pre), "layers.%d.residual_group.overlap_attn", li);
+    const std::string po(pre);
+    SSR_TRY(pack_ln(m, po + ".norm1", C, m->CP, &L.ocab.norm1));
+    SSR_TRY(pack_ln(m, po + ".norm2", C, m->CP, &L.ocab.norm2));
+    SSR_TRY(pack_attn_mlp(m, po, po + ".mlp", po + ".relative_position_bias_table", L, (ws + wse - 1) * (ws + wse - 1), &L.ocab));
+    snprintf(pre, sizeof(pre), "layers.%d.conv", li);
+    SSR_TRY(pack_conv(m, pre, C, C, 0, &L.conv));
+    m->layers.push_back(L);
+  }
+  SSR_TRY(pack_ln(m, "norm", C, m->CP, &m->final_norm));
+  SSR_TRY(pack_conv(m, "conv_after_body", C, C, 0, &m->conv_after_body));
+  std::vector<int> rs;
+  upsampler_plan(c.scale, &rs);
+  m->up.clear();
+  SSR_TRY(pack_conv(m, "conv_before_upsample.0", 64, C, 0, &m->conv_before_up));
+  for (size_t i = 0; i < rs.size(); ++i) {
+    Lin L;
+    char nm[64];
+    snprintf(nm, sizeof(nm), "upsample.%d", (int)(2 * i));
+    SSR_TRY(pack_conv(m, nm, rs[i] * rs[i] * 64, 64, rs[i], &L));
+    m->up.push_back(L);
+  }
+  m->last_cin = 64;
+  SSR_TRY(pack_conv_last(m, "conv_last", 64, &m->conv_last_w, m->conv_last_bias));
+  if (c.precision != SSR_PREC_FP32) SSR_TRY(pack_conv(m, "conv_last", 3, 64, 0, &m->last_lin));
+  return SSR_OK;
+}
+
 static int finalize_edsr(ssr_model* m) {
   const ssr_model_config& c = m->cfg;
   SSR_CHECK(c.n_colors == 3, SSR_E_INVALID, "n_colors must be 3");
@@ -555,7 +665,7 @@ struct Carver {
 };
 
 static void padded_size(const ssr_model* m, int H, int W, int pad_mode, int* Hp, int* Wp) {
-  if (m->cfg.arch != SSR_ARCH_SWINIR) {
+  if (m->cfg.arch != SSR_ARCH_SWINIR && m->cfg.arch != SSR_ARCH_HAT) {
     *Hp = H;
     *Wp = W;
     return;
@@ -1035,6 +1145,214 @@ static int forward_edsr(ssr_model* m, const InputSpec& in, const OutputSpec& out
   return run_tail(m, W.tmp, FP, B, h, w, W.hr[0], W.hr[1], h, w, m->add_bias, 1.0f, out, s);
 }
 
+struct HatWs {
+  float *x0, *g, *t, *t2, *partial;
+  void *xn, *qkv, *o, *hbuf, *tb, *cbu, *c1, *hr[2];
+  int nsplit;
+};
+static size_t plan_hat(const ssr_model* m, void* base, int B, int Hp, int Wp, HatWs* w) {
+  Carver c(base);
+  const size_t T = (size_t)B * Hp * Wp, e = m->elem;
+  const int HW = Hp * Wp;
+  w->nsplit = HW >= 16384 ? 64 : (HW + 255) / 256;
+  w->x0 = (float*)c.take(T * m->CP * 4);
+  w->g = (float*)c.take(T * m->CP * 4);
+  w->t = (float*)c.take(T * m->CP * 4);
+  w->t2 = (float*)c.take(T * m->CP * 4);
+  w->partial = (float*)c.take((size_t)B * w->nsplit * m->C * 4);
+  w->xn = c.take(T * m->CP * e);
+  w->qkv = c.take(T * 3 * m->QPmax * e);
+  w->o = c.take(T * m->QPmax * e);
+  w->hbuf = c.take(T * m->HP * e);
+  w->tb = c.take(T * m->CP * e);
+  w->cbu = c.take(T * 64 * e);
+  w->c1 = c.take(T * round_up(m->C / m->cfg.compress_ratio, 64) * e);
+  size_t need[2] = {0, 0};
+  size_t px = T;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
+    if (px * 64 > need[i & 1]) need[i & 1] = px * 64;
+  }
+  for (int i = 0; i < 2; ++i) w->hr[i] = need[i] ? c.take(need[i] * e) : nullptr;
+  return c.off + 1024;
+}
+
+// HAT forward (hat.py:542-554): the un-fused GEMM path of SwinIR with 16x16 windows, plus the channel-attention
+// block inside every HAB and the overlapping cross-attention block closing every group.
+static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, void* ws, size_t ws_bytes,
+                       cudaStream_t s) {
+  const ssr_model_config& c = m->cfg;
+  int Hp, Wp;
+  padded_size(m, h, w, SSR_PAD_TRAIN, &Hp, &Wp);  // hat.py:544: reflect pad in both modes
+  SSR_CHECK(Hp - h < h && Wp - w < w, SSR_E_INVALID, "reflect padding needs pad < size (%dx%d)", h, w);
+  HatWs W;
+  const size_t need = plan_hat(m, ws, B, Hp, Wp, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+  const int CP = m->CP, e = m->elem;
+  const int T = B * Hp * Wp;
+  const int rtf = c.precision == SSR_PREC_TF32;
+  const int wse = c.window_size + (int)(c.overlap_ratio * c.window_size);
+  const int R = m->C / c.squeeze_factor, CcP = round_up(m->C / c.compress_ratio, 64);
+
+  {  // reflect pad + normalise + conv_first (hat.py:544-548)
+    ConvFirstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in.in; a.in_u8 = in.in_u8; a.fh = in.fh; a.fw = in.fw;
+    a.tile_mode = in.tile_mode; a.tile = in.tile; a.stride = in.stride; a.tiles_x = in.tiles_x; a.tile_begin = in.tile_begin;
+    a.h = h; a.w = w; a.Hp = Hp; a.Wp = Wp; a.pad_mode = SSR_PAD_TRAIN; a.B = B;
+    const float u8s = (in.in_u8 && c.img_range == 1.0f) ? 1.0f / 255.0f : 1.0f;
+    a.in_scale = u8s / c.img_range;
+    for (int i = 0; i < 3; ++i) a.in_shift[i] = -kRgbMean[i];
+    a.Wc = m->dev<float>(m->conv_first_w);
+    a.bias = m->dev<float>(m->conv_first_b);
+    a.Cout = m->C;
+    a.out_f32 = W.x0; a.ld_f32 = CP; a.elem = e;
+    SSR_TRY(launch_conv_first(a, s));
+  }
+  auto layer_norm = [&](const float* src, const LNp& ln, float* dst_f32, const LNp* ln2, void* dst_T) {
+    LnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = src; a.ld_in = CP; a.M = T; a.C = m->C; a.CP = CP;
+    a.g1 = m->dev<float>(ln.g_off); a.b1 = m->dev<float>(ln.b_off);
+    a.out_f32 = dst_f32; a.ld_f32 = CP;
+    if (ln2) {
+      a.g2 = m->dev<float>(ln2->g_off);
+      a.b2 = m->dev<float>(ln2->b_off);
+    }
+    a.out_T = dst_T; a.ld_T = CP; a.elem = e; a.round_tf32 = rtf; a.eps = 1e-5f;
+    return launch_layernorm(a, s);
+  };
+  // patch_embed.norm -> g (residual stream), chained with layers.0.blocks.0.norm1 -> xn
+  SSR_TRY(layer_norm(W.x0, m->pe_norm, W.g, &m->layers[0].blocks[0].norm1, W.xn));
+  SSR_CUDA(cudaMemsetAsync(W.o, 0, (size_t)T * m->QPmax * e, s));
+  SSR_CUDA(cudaMemsetAsync(W.c1, 0, (size_t)T * CcP * e, s));
+  const int nL = (int)m->layers.size();
+
+  // shared tail of HAB / OCAB: norm2 -> fc1 + GELU -> fc2 + residual, epilogue = `next` LayerNorm into xn or a T copy into tb
+  auto mlp = [&](const Block& blk, bool ln2_fused, const LNp* next) -> int {
+    if (!ln2_fused) SSR_TRY(layer_norm(W.t, blk.norm2, nullptr, nullptr, W.xn));
+    {
+      GemmArgs g = gemm_base(m, blk.fc1, W.xn, CP, B, Hp, Wp);
+      g.act = ACT_GELU;
+      g.out_T = W.hbuf;
+      g.ld_T = m->HP;
+      SSR_TRY(run_gemm(m, g, s));
+    }
+    GemmArgs g = gemm_base(m, blk.fc2, W.hbuf, m->HP, B, Hp, Wp);
+    g.res = W.t;
+    g.ldres = CP;
+    if (next) {
+      g.out_f32 = W.t;
+      g.ld_f32 = CP;
+      set_ln(m, g, *next, W.xn, CP);
+    } else {
+      g.out_T = W.tb;
+      g.ld_T = CP;
+    }
+    return run_gemm(m, g, s);
+  };
+
+  for (int li = 0; li < nL; ++li) {
+    const Layer& L = m->layers[li];
+    const int depth = (int)L.blocks.size();
+    for (int bi = 0; bi < depth; ++bi) {  // HAB (hat.py:154-195); xn = norm1(x) on entry
+      const Block& blk = L.blocks[bi];
+      const float* shortcut = bi == 0 ? W.g : W.t;
+      {  // channel attention block on norm1(x): conv 3x3 -> GELU -> conv 3x3 (hat.py:44-49); the gate is applied below
+        GemmArgs g = gemm_base(m, blk.cab0, W.xn, CP, B, Hp, Wp);
+        g.act = ACT_GELU;
+        g.out_T = W.c1;
+        g.ld_T = CcP;
+        SSR_TRY(run_gemm(m, g, s));
+        GemmArgs g2 = gemm_base(m, blk.cab2, W.c1, CcP, B, Hp, Wp);
+        g2.out_f32 = W.t2;
+        g2.ld_f32 = CP;
+        SSR_TRY(run_gemm(m, g2, s));
+      }
+      {  // (S)W-MSA over 16x16 windows (hat.py:167-183)
+        GemmArgs g = gemm_base(m, blk.qkv, W.xn, CP, B, Hp, Wp);
+        g.out_T = W.qkv;
+        g.ld_T = 3 * L.QP;
+        SSR_TRY(run_gemm(m, g, s));
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.qkv = W.qkv; a.ld_qkv = 3 * L.QP; a.QP = L.QP; a.o = W.o; a.ld_o = L.QP;
+        a.bias = m->dev<float>(blk.bias_off);
+        a.B = B; a.H = Hp; a.W = Wp; a.ws = c.window_size; a.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
+        a.heads = L.heads; a.d = L.d; a.DP = L.DP; a.elem = e;
+        SSR_TRY(launch_attn_simt(a, s));
+        GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
+        gp.res = shortcut;
+        gp.ldres = CP;
+        gp.out_f32 = W.t;
+        gp.ld_f32 = CP;
+        SSR_TRY(run_gemm(m, gp, s));
+      }
+      {  // x = shortcut + attn + conv_scale * (t2 * sigmoid-gate(mean t2))  (hat.py:188, :25-38)
+        CaArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.t = W.t2; ca.res = W.t; ca.ld = CP; ca.B = B; ca.HW = Hp * Wp; ca.C = m->C; ca.CP = CP; ca.R = R;
+        ca.W1 = m->dev<float>(blk.ca_w1); ca.b1 = m->dev<float>(blk.ca_b1);
+        ca.W2 = m->dev<float>(blk.ca_w2); ca.b2 = m->dev<float>(blk.ca_b2);
+        ca.partial = W.partial; ca.nsplit = W.nsplit;
+        ca.out_f32 = W.t; ca.out_T = nullptr; ca.elem = e; ca.round_tf32 = rtf; ca.scale = c.conv_scale;
+        SSR_TRY(launch_channel_attention(ca, s));
+      }
+      SSR_TRY(mlp(blk, false, bi + 1 < depth ? &L.blocks[bi + 1].norm1 : &L.ocab.norm1));
+    }
+    {  // OCAB (hat.py:240-293); xn = ocab.norm1(x) on entry
+      const Block& blk = L.ocab;
+      GemmArgs g = gemm_base(m, blk.qkv, W.xn, CP, B, Hp, Wp);
+      g.out_T = W.qkv;
+      g.ld_T = 3 * L.QP;
+      SSR_TRY(run_gemm(m, g, s));
+      AttnArgs a;
+      memset(&a, 0, sizeof(a));
+      a.qkv = W.qkv; a.ld_qkv = 3 * L.QP; a.QP = L.QP; a.o = W.o; a.ld_o = L.QP;
+      a.bias = m->dev<float>(blk.bias_off);
+      a.B = B; a.H = Hp; a.W = Wp; a.ws = c.window_size; a.kws = wse; a.heads = L.heads; a.d = L.d; a.DP = L.DP; a.elem = e;
+      SSR_TRY(launch_attn_oca(a, s));
+      GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
+      gp.res = W.t;
+      gp.ldres = CP;
+      gp.out_f32 = W.t;
+      gp.ld_f32 = CP;
+      set_ln(m, gp, blk.norm2, W.xn, CP);
+      SSR_TRY(run_gemm(m, gp, s));
+      SSR_TRY(mlp(blk, true, nullptr));
+    }
+    {  // group conv + group residual (hat.py:385); epilogue = next group's first norm1 or the final norm
+      GemmArgs g = gemm_base(m, L.conv, W.tb, CP, B, Hp, Wp);
+      g.res = W.g;
+      g.ldres = CP;
+      if (li + 1 < nL) {
+        g.out_f32 = W.g;
+        g.ld_f32 = CP;
+        set_ln(m, g, m->layers[li + 1].blocks[0].norm1, W.xn, CP);
+      } else {
+        set_ln(m, g, m->final_norm, W.xn, CP);
+      }
+      SSR_TRY(run_gemm(m, g, s));
+    }
+  }
+  {  // conv_after_body + long skip (hat.py:549)
+    GemmArgs g = gemm_base(m, m->conv_after_body, W.xn, CP, B, Hp, Wp);
+    g.res = W.x0;
+    g.ldres = CP;
+    g.out_T = W.tb;
+    g.ld_T = CP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  float shift[3] = {kRgbMean[0], kRgbMean[1], kRgbMean[2]};
+  GemmArgs g = gemm_base(m, m->conv_before_up, W.tb, CP, B, Hp, Wp);
+  g.act = ACT_LEAKY;
+  g.slope = 0.01f;
+  g.out_T = W.cbu;
+  g.ld_T = 64;
+  SSR_TRY(run_gemm(m, g, s));
+  return run_tail(m, W.cbu, 64, B, Hp, Wp, W.hr[0], W.hr[1], h, w, shift, c.img_range, out, s);
+}
+
 struct RcanWs {
   float *x, *gin, *r, *t2, *partial;
   void *rb, *tmp, *hr[2];
@@ -1105,6 +1423,7 @@ static int forward_rcan(ssr_model* m, const InputSpec& in, const OutputSpec& out
       ca.W2 = m->dev<float>(m->ca[i].w2); ca.b2 = m->dev<float>(m->ca[i].b2);
       ca.partial = W.partial; ca.nsplit = W.nsplit;
       ca.out_f32 = W.r; ca.out_T = W.rb; ca.ld_T = FP; ca.elem = e; ca.round_tf32 = c.precision == SSR_PREC_TF32;
+      ca.scale = 1.0f;
       SSR_TRY(launch_channel_attention(ca, s));
       rcur = W.r;
     }
@@ -1144,6 +1463,7 @@ static int forward_any(ssr_model* m, const InputSpec& in, const OutputSpec& out,
   SSR_CHECK(B > 0 && h > 0 && w > 0, SSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, h, w);
   if (m->cfg.arch == SSR_ARCH_SWINIR) return forward_swinir(m, in, out, B, h, w, pad_mode, ws, ws_bytes, s);
   if (m->cfg.arch == SSR_ARCH_RCAN) return forward_rcan(m, in, out, B, h, w, ws, ws_bytes, s);
+  if (m->cfg.arch == SSR_ARCH_HAT) return forward_hat(m, in, out, B, h, w, ws, ws_bytes, s);
   return forward_edsr(m, in, out, B, h, w, ws, ws_bytes, s);
 }
 
@@ -1157,6 +1477,12 @@ static size_t workspace_any(const ssr_model* m, int B, int H, int W, int pad_mod
   if (m->cfg.arch == SSR_ARCH_RCAN) {
     RcanWs w;
     return plan_rcan(m, nullptr, B, H, W, &w);
+  }
+  if (m->cfg.arch == SSR_ARCH_HAT) {
+    int Hp, Wp;
+    padded_size(m, H, W, SSR_PAD_TRAIN, &Hp, &Wp);
+    HatWs w;
+    return plan_hat(m, nullptr, B, Hp, Wp, &w);
   }
   EdsrWs w;
   return plan_edsr(m, nullptr, B, H, W, &w);
@@ -1235,11 +1561,10 @@ int ssr_device_check(int device) {
 
 int ssr_model_create(const ssr_model_config* cfg, int device, ssr_model_t** out) {
   SSR_CHECK(cfg && out, SSR_E_INVALID, "null argument");
-  SSR_CHECK(cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_EDSR || cfg->arch == SSR_ARCH_RCAN, SSR_E_INVALID,
-            "unknown arch %d", cfg->arch);
+  SSR_CHECK(cfg->arch >= SSR_ARCH_SWINIR && cfg->arch <= SSR_ARCH_HAT, SSR_E_INVALID, "unknown arch %d", cfg->arch);
   SSR_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SSR_E_INVALID, "unknown precision %d", cfg->precision);
   SSR_CHECK(cfg->scale >= 1 && cfg->scale <= 8, SSR_E_INVALID, "bad scale %d", cfg->scale);
-  if (cfg->arch == SSR_ARCH_SWINIR)
+  if (cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_HAT)
     SSR_CHECK(cfg->n_layers > 0 && cfg->n_layers <= SSR_MAX_LAYERS, SSR_E_INVALID, "bad n_layers %d", cfg->n_layers);
   SSR_TRY(ssr_device_check(device));
   ssr_model* m = new ssr_model();
@@ -1261,7 +1586,10 @@ int ssr_model_finalize(ssr_model_t* m) {
   SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
   SSR_CUDA(cudaSetDevice(m->device));
   m->host_arena.clear();
-  int r = m->cfg.arch == SSR_ARCH_SWINIR ? finalize_swinir(m) : m->cfg.arch == SSR_ARCH_RCAN ? finalize_rcan(m) : finalize_edsr(m);
+  int r = m->cfg.arch == SSR_ARCH_SWINIR ? finalize_swinir(m)
+          : m->cfg.arch == SSR_ARCH_RCAN ? finalize_rcan(m)
+          : m->cfg.arch == SSR_ARCH_HAT  ? finalize_hat(m)
+                                         : finalize_edsr(m);
   if (r != SSR_OK) return r;
   if (m->arena && m->arena_bytes < m->host_arena.size()) {
     cudaFree(m->arena);

@@ -103,6 +103,8 @@ struct AttnArgs {
   int ld_o;
   const float* bias;  // [heads][(2ws-1)^2]
   int B, H, W, ws, shift, heads, d, DP;
+  int elem;  // bytes per activation element for the CUDA-core kernels (0 / 4: fp32, 2: bf16)
+  int kws;   // key / value window of the HAT overlapping cross-attention (launch_attn_oca)
 };
 
 struct LnArgs {
@@ -222,12 +224,14 @@ struct CaArgs {
   float* out_f32;  // [B][HW][ld]
   void* out_T;     // T-typed copy for the next conv
   int ld_T, elem, round_tf32;
+  float scale;  // out = res + t * gate * scale (1 for RCAN, conv_scale for HAT's CAB)
 };
 int launch_channel_attention(const CaArgs& a, cudaStream_t s);
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s);
 int launch_attn_simt(const AttnArgs& a, cudaStream_t s);
+int launch_attn_oca(const AttnArgs& a, cudaStream_t s);
 int launch_attn_mma(const AttnArgs& a, cudaStream_t s);
 int launch_layernorm(const LnArgs& a, cudaStream_t s);
 int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s);

@@ -88,6 +88,35 @@ def test_edsr_matches_reference_golden(name, prec, golden_meta):
         assert err <= 6e-2 and _psnr_delta(y, ref) <= 0.01, f"{name} [bf16] max-abs {err:.3e}"
 
 
+HAT_CASES = ["hat_tiny_x4_eval_2x20x40", "hat_tiny_x4_train_1x32x32", "hat_tiny_x2_eval_1x16x48", "hat_tiny_x3_eval_1x17x17",
+             "hat_full_x4_eval_1x64x64"]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("name", HAT_CASES)
+def test_hat_matches_reference_golden(name, prec, golden_meta):
+    """HAT forward (hat.py:542-554: HAB with channel attention, 16x16 (S)W-MSA, overlapping cross-attention) against the
+    reference's own outputs; the last case is the full BASELINE.json config-3 model on one 64x64 tile."""
+    from studiosr_b200.models import HAT
+
+    c = golden_meta[name]
+    m = HAT(drop_path_rate=0.0, **c["cfg"])
+    m.load_state_dict(synth.hat_weights(c["cfg"], c["wseed"]), strict=True)
+    m = m.cuda()
+    m.train(c["training"])
+    m.precision = prec
+    x = synth.image_batch(c["shape"], c["xseed"]).cuda()
+    with torch.no_grad():
+        y = m(x).float().cpu()
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    err = (y - ref).abs().max().item()
+    if prec in ABS_TOL:
+        assert err <= ABS_TOL[prec], f"{name} [{prec}] max-abs {err:.3e}"
+    else:
+        assert err <= 6e-2 and _psnr_delta(y, ref) <= 0.01, f"{name} [bf16] max-abs {err:.3e}"
+
+
 RCAN_CASES = ["rcan_tiny_x4_2x12x20", "rcan_tiny_x2_1x9x11", "rcan_tiny_x3_1x8x8", "rcan_full_x4_1x24x24"]
 
 
