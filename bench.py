@@ -104,6 +104,18 @@ def build_model(precision):
     return m
 
 
+def max_over_ranks(ms, dist, device):
+    """Multi-GPU numbers are the MAX over ranks of the device-side time (the frames are independent shards, the job is
+    done when the slowest rank is).  `dist` is torch.distributed (or None for a single process)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return ms
+    import torch
+
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
 def synthetic_frame(rank):
     from oracle.synth import smooth_image_u8
 
@@ -223,11 +235,7 @@ def run_ours(args):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+        ms = max_over_ranks(e0.elapsed_time(e1), dist, dev)
         barrier()
         return ms
 
