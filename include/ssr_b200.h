@@ -135,6 +135,25 @@ int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, u
                                     int tile, int overlap, int chunk_tiles, void* workspace, size_t workspace_bytes,
                                     void* stream);
 
+/* ---- training step (trainer.py:97-105: `out = model(x)` ... `loss.backward()`), bf16 tensor-core path ----------
+ * The reference differentiates the model with torch autograd; these two calls are that forward/backward pair for the
+ * whole model.  The fp32 master parameters and their gradients stay in caller-owned DEVICE memory:
+ *   ssr_model_train_bind     names the state_dict entries (weights AND biases, in any fixed order) once; the model must
+ *                            have been finalised (ssr_model_set_param + ssr_model_finalize) so the layouts exist.
+ *   ssr_model_train_forward  params[i] = DEVICE fp32 pointer of bound entry i (PyTorch layout).  Re-packs the weights on
+ *                            the device (forward and transposed/rotated dgrad operands), runs the training-mode forward
+ *                            x [B,3,H,W] -> y [B,3,sH,sW] (fp32 NCHW) and keeps every GEMM operand in `workspace`.
+ *   ssr_model_train_backward dy = dL/dy (DEVICE fp32 NCHW).  grads[i] = DEVICE fp32 buffer for dL/d(param i), overwritten
+ *                            (NULL: not wanted, e.g. frozen entries).  `workspace` must be the buffer, untouched, that
+ *                            the matching train_forward used.  dL/dx is not produced (the Trainer never asks for it).
+ * Forward/backward pairs on one handle must not interleave with another forward on the same handle. */
+int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const int64_t* numels);
+size_t ssr_model_train_workspace_bytes(const ssr_model_t* m, int B, int H, int W);
+int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const float* x, float* y, int B, int H, int W,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int ssr_model_train_backward(ssr_model_t* m, const float* dy, float* const* grads, int B, int H, int W, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 int64_t ssr_launch_count(void);
 /* Per-launch device timing for the roofline report: between begin and end every kernel launch is
@@ -161,6 +180,12 @@ int ssr_op_linear(int precision, const float* x, const float* W, const float* b,
 int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b, const float* res, float* y, int B,
                    int Cin, int Cout, int H, int Wd, int act, float alpha, int ps_r, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* Weight / bias gradient of nn.Conv2d(Cin, Cout, 3, 1, 1) (taps = 9) or of a 1x1 conv / nn.Linear over pixels (taps = 1) as
+ * torch autograd computes it for the reference (trainer.py:104), bf16 tensor-core path (k_wgrad_tc.cu):
+ *   dW[co][ci][ky][kx] = alpha * sum_{b,y,x} dy[b,co,y,x] * x[b,ci,y+ky-1,x+kx-1];   db[co] = alpha * sum dy[b,co,y,x]
+ * dy [B,Cout,H,W], x [B,Cin,H,W] fp32 NCHW; dW [Cout,Cin,3,3] (or [Cout,Cin]); db [Cout] or NULL. */
+int ssr_op_conv3x3_wgrad(const float* dy, const float* x, float* dW, float* db, int B, int Cin, int Cout, int H, int Wd, int taps,
+                         float alpha, void* workspace, size_t workspace_bytes, void* stream);
 /* Fused tail of a SwinTransformerBlock (swinir.py:103,171-172; common.py:184-194), bf16 tensor-core path:
  *   t1 = o @ Wp^T + bp + res;  h = GELU(LN(t1; g2,be2) @ W1^T + b1);  y = t1 + h @ W2^T + b2;
  *   y_ln = LN(y; g3,be3) (or, when g3 is NULL, y rounded to bf16).  o, res, y: [M, C] fp32; weights in PyTorch

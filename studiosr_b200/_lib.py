@@ -47,6 +47,12 @@ SYMBOLS = {
                                            c_size_t, c_void_p]),
     "ssr_model_upscale_tiled_u8_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                                 c_void_p, c_size_t, c_void_p]),
+    "ssr_model_train_bind": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int64)]),
+    "ssr_model_train_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "ssr_model_train_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                        c_size_t, c_void_p]),
+    "ssr_model_train_backward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_size_t,
+                                         c_void_p]),
     "ssr_launch_count": (c_int64, []),
     "ssr_profile_begin": (c_int, []),
     "ssr_profile_end": (c_int, [c_char_p, c_size_t]),
@@ -54,6 +60,8 @@ SYMBOLS = {
                               c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ssr_op_conv3x3": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "ssr_op_conv3x3_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_float, c_void_p, c_size_t, c_void_p]),
     "ssr_op_swin_mlp": (c_int, [c_void_p] * 14 + [c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ssr_op_window_attention": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_int, c_void_p, c_size_t, c_void_p]),

@@ -271,6 +271,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[4 * q + 3] += bv.w;
         }
         epilogue_act(v, g.act, g.slope, g.alpha);
+        if (g.mask) {  // activation backward (training dgrad): gate by the sign of the saved forward output
+          float mk[32];
+          if (m >= 0) {
+            const T* mp = reinterpret_cast<const T*>(g.mask) + (size_t)m * g.ld_mask + nb;
+            if constexpr (sizeof(T) == 2) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(mp) + q);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  mk[8 * q + 2 * j] = __uint_as_float(w4[j] << 16);
+                  mk[8 * q + 2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(mp) + q);
+                mk[4 * q] = u.x; mk[4 * q + 1] = u.y; mk[4 * q + 2] = u.z; mk[4 * q + 3] = u.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = mk[i] > 0.0f ? v[i] : v[i] * g.mask_slope;
+          }
+        }
         if (dbg && c == 1) dbg[6] = clock64();
         if (g.res || g.out_f32) {
           // transposed domain: add the (prefetched, coalesced) residual and store the fp32 stream

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "ssr_internal.cuh"
+#include "ssr_model.cuh"
 
 namespace ssr {
 
@@ -76,78 +76,15 @@ static inline float tf32_round_host(float x) {
   return x;
 }
 
-// ---------------------------------------------------------------------------------------------
-struct Lin {           // one packed (implicit-)GEMM layer
-  size_t w_off = 0;    // arena offset of T [NP][taps*KP]
-  size_t b_off = 0;    // arena offset of float [NP]
-  int K = 0, KP = 0, N = 0, NP = 0, taps = 1, ps_r = 0;
-  int N_alg = 0;       // un-padded output width (accounting)
-};
-struct LNp {
-  size_t g_off = 0, b_off = 0;
-};
-struct Block {
-  LNp norm1, norm2;
-  Lin qkv, proj, fc1, fc2;
-  size_t bias_off = 0;  // float [heads][(2ws-1)^2]
-  size_t whp_off = 0, bhp_off = 0, btab_off = 0;  // fused attention kernel operands (k_swin_attn.cu)
-  // HAT: channel attention block of a HAB (hat.py:41-52)
-  Lin cab0, cab2;
-  size_t ca_w1 = 0, ca_b1 = 0, ca_w2 = 0, ca_b2 = 0;
-};
-struct Layer {
-  std::vector<Block> blocks;
-  Lin conv;
-  int heads = 0, d = 0, DP = 0, QP = 0;
-  Block ocab;  // HAT: overlapping cross-attention block closing the group (hat.py:198-293)
-};
-
 }  // namespace ssr
 
 using namespace ssr;
-
-struct ssr_model {
-  ssr_model_config cfg;
-  int device = 0;
-  int elem = 4;  // bytes per activation / weight element
-  bool finalized = false;
-  std::map<std::string, std::vector<float>> params;
-  // packed
-  std::vector<uint8_t> host_arena;
-  uint8_t* arena = nullptr;
-  size_t arena_bytes = 0;
-  // SwinIR
-  int C = 0, CP = 0, HID = 0, HP = 0, QPmax = 0;
-  std::vector<Layer> layers;
-  LNp pe_norm, final_norm;
-  size_t conv_first_w = 0, conv_first_b = 0;
-  Lin conv_after_body, conv_before_up;
-  std::vector<Lin> up;  // upsample convs
-  size_t conv_last_w = 0;
-  float conv_last_bias[3] = {0, 0, 0};
-  int last_cin = 64;
-  Lin last_lin;  // the same conv packed for the tensor-core implicit GEMM (bf16 / tf32 models)
-  // EDSR
-  int F = 0, FP = 0;
-  std::vector<Lin> res_a, res_b;
-  Lin body_tail;
-  float sub_bias[3] = {0, 0, 0}, add_bias[3] = {0, 0, 0};
-  // RCAN: res_a / res_b hold the two convs of every RCAB (group-major), grp_tail the conv closing each group
-  std::vector<Lin> grp_tail;
-  struct CaP {
-    size_t w1 = 0, b1 = 0, w2 = 0, b2 = 0;  // fp32 [R][C], [R], [C][R], [C]
-  };
-  std::vector<CaP> ca;
-
-  template <typename T>
-  T* dev(size_t off) const { return reinterpret_cast<T*>(arena + off); }
-};
 
 namespace ssr {
 
 // ---------------------------------------------------------------------------------------------
 // packing helpers (host)
-static size_t arena_alloc(ssr_model* m, size_t bytes) {
+size_t arena_alloc(ssr_model* m, size_t bytes) {
   size_t off = (m->host_arena.size() + 255) & ~(size_t)255;
   m->host_arena.resize(off + bytes, 0);
   return off;
@@ -242,7 +179,7 @@ static int pack_ln(ssr_model* m, const std::string& name, int C, int CP, LNp* ou
   return SSR_OK;
 }
 
-static void upsampler_plan(int scale, std::vector<int>* rs) {  // common.py:124-137
+void upsampler_plan(int scale, std::vector<int>* rs) {  // common.py:124-137
   rs->clear();
   if ((scale & (scale - 1)) == 0) {
     for (int s = scale; s > 1; s >>= 1) rs->push_back(2);
@@ -652,18 +589,6 @@ static int finalize_rcan(ssr_model* m) {  // rcan.py:39-66
 
 // ---------------------------------------------------------------------------------------------
 // workspace planning
-struct Carver {
-  uint8_t* base;
-  size_t off = 0;
-  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
-  void* take(size_t bytes) {
-    off = (off + 1023) & ~(size_t)1023;
-    void* p = base ? base + off : nullptr;
-    off += bytes;
-    return p;
-  }
-};
-
 static void padded_size(const ssr_model* m, int H, int W, int pad_mode, int* Hp, int* Wp) {
   if (m->cfg.arch != SSR_ARCH_SWINIR && m->cfg.arch != SSR_ARCH_HAT) {
     *Hp = H;
@@ -736,13 +661,13 @@ static size_t plan_edsr(const ssr_model* m, void* base, int B, int H, int W, Eds
 
 // ---------------------------------------------------------------------------------------------
 // launch helpers
-static int run_gemm(const ssr_model* m, GemmArgs& g, cudaStream_t s) {
+int run_gemm(const ssr_model* m, GemmArgs& g, cudaStream_t s) {
   g.round_tf32 = m->cfg.precision == SSR_PREC_TF32;
   if (m->cfg.precision == SSR_PREC_FP32) return launch_gemm_simt(g, s);
   return launch_gemm_tc(g, m->elem, s);
 }
 
-static GemmArgs gemm_base(const ssr_model* m, const Lin& L, const void* A, int lda, int B, int H, int W) {
+GemmArgs gemm_base(const ssr_model* m, const Lin& L, const void* A, int lda, int B, int H, int W) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = A;
@@ -775,17 +700,6 @@ static void set_ln(const ssr_model* m, GemmArgs& g, const LNp& ln, void* out, in
 }
 
 // pixel-shuffle tail shared by SwinIR ("pixelshuffle") and EDSR: cur [B,H,W,ch] -> conv_last
-struct InputSpec {
-  const void* in;
-  int in_u8;
-  int fh, fw;  // frame / image size
-  int tile_mode, tile, stride, tiles_x, tile_begin;
-};
-struct OutputSpec {
-  float* out_f32;
-  uint8_t* out_u8;
-};
-
 static int run_tail(ssr_model* m, const void* cur, int ch_ld, int B, int Hp, int Wp, void* hr0, void* hr1, int h, int w,
                     const float* out_shift, float out_scale, const OutputSpec& out, cudaStream_t s) {
   int H = Hp, W = Wp;
@@ -1449,7 +1363,7 @@ static int forward_rcan(ssr_model* m, const InputSpec& in, const OutputSpec& out
   return run_tail(m, W.tmp, FP, B, h, w, W.hr[0], W.hr[1], h, w, m->add_bias, 1.0f, out, s);
 }
 
-static int check_ready(ssr_model* m) {
+int check_ready(ssr_model* m) {
   SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
   SSR_CHECK(m->finalized, SSR_E_STATE, "model not finalised (call ssr_model_finalize)");
   int dev = -1;
@@ -1622,6 +1536,7 @@ int ssr_model_finalize(ssr_model_t* m) {
 
 void ssr_model_destroy(ssr_model_t* m) {
   if (!m) return;
+  train_state_destroy(m);
   if (m->arena) cudaFree(m->arena);
   delete m;
 }

@@ -162,6 +162,30 @@ int ssr_op_conv3x3(int precision, const float* x, const float* W, const float* b
   return launch_nhwc_to_nchw(yp, ldo, elem, y, B, Cps, H * r, Wd * r, s);
 }
 
+int ssr_op_conv3x3_wgrad(const float* dy, const float* x, float* dW, float* db, int B, int Cin, int Cout, int H, int Wd, int taps,
+                         float alpha, void* workspace, size_t workspace_bytes, void* stream) {
+  SSR_CHECK(dy && x && dW && workspace && (taps == 1 || taps == 9), SSR_E_INVALID, "ssr_op_conv3x3_wgrad: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int KP = round_up(Cin, 64), NP = round_up(Cout, 64);
+  const size_t M = (size_t)B * H * Wd;
+  Carve c(workspace, workspace_bytes);
+  void* xp = c.take(M * KP * 2);
+  void* yp = c.take(M * NP * 2);
+  float* dwp = (float*)c.take((size_t)NP * taps * KP * 4);
+  SSR_CHECK(dwp, SSR_E_WORKSPACE, "ssr_op_conv3x3_wgrad: workspace too small (%zu B)", workspace_bytes);
+  SSR_TRY(launch_nchw_to_nhwc(x, xp, B, Cin, H, Wd, KP, 2, 0, s));
+  SSR_TRY(launch_nchw_to_nhwc(dy, yp, B, Cout, H, Wd, NP, 2, 0, s));
+  SSR_CUDA(cudaMemsetAsync(dwp, 0, (size_t)NP * taps * KP * 4, s));
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dY = yp; a.ldy = NP; a.X = xp; a.ldx = KP; a.B = B; a.H = H; a.W = Wd; a.M = (int)M; a.taps = taps; a.NoutP = NP; a.CinP = KP;
+  a.dWp = dwp; a.alpha = alpha; a.N_alg = Cout; a.K_alg = Cin;
+  SSR_TRY(launch_wgrad_tc(a, s));
+  SSR_TRY(launch_unpack_wgrad(dwp, dW, Cout, Cin, KP, taps, 0, s));
+  if (db) SSR_TRY(launch_colsum(yp, 2, NP, (int)M, Cout, 0, alpha, db, s));
+  return SSR_OK;
+}
+
 int ssr_op_swin_mlp(const float* o, const float* res, const float* Wp, const float* bp, const float* g2, const float* be2,
                     const float* W1, const float* b1, const float* W2, const float* b2, const float* g3, const float* be3,
                     float* y, float* y_ln, int M, int C, int heads, int hidden, void* workspace, size_t workspace_bytes,

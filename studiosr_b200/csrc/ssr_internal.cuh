@@ -90,6 +90,11 @@ struct GemmArgs {
   float out_shift[3];
   float out_scale, u8_scale;
   int K_alg, N_alg;  // un-padded contraction / output widths, for FLOP and byte accounting only
+  // backward of an activation folded into a dgrad epilogue (tensor-core path only): after alpha,
+  //   v = mask[m][n] > 0 ? v : v * mask_slope     (ReLU: slope 0 with mask = the forward OUTPUT; LeakyReLU likewise)
+  const void* mask;  // T [M][ld_mask] or null
+  int ld_mask;
+  float mask_slope;
   long long* dbg;    // optional per-CTA phase timestamps (developer diagnostics), 8 slots per CTA
 };
 double gemm_alg_flops(const GemmArgs& g);
@@ -227,6 +232,30 @@ struct CaArgs {
   float scale;  // out = res + t * gate * scale (1 for RCAN, conv_scale for HAT's CAB)
 };
 int launch_channel_attention(const CaArgs& a, cudaStream_t s);
+
+// weight gradient of a conv3x3 / linear layer (k_wgrad_tc.cu): dWp[n][tap][c] += alpha * sum_p dY[p][n] X[p+off(tap)][c]
+struct WgradArgs {
+  const void* dY;  // bf16 [B*H*W][ldy]
+  int ldy;
+  const void* X;  // bf16 [B*H*W][ldx]
+  int ldx;
+  int B, H, W, M;
+  int taps;
+  int NoutP, CinP;  // padded widths (multiples of 64) of dY / X that take part
+  float* dWp;       // fp32 [NoutP][taps][CinP], accumulated into (zero it first)
+  float alpha;
+  int N_alg, K_alg;  // un-padded widths (accounting)
+};
+int launch_wgrad_tc(const WgradArgs& a, cudaStream_t s);
+
+// k_train.cu: on-device (re)packing of the fp32 master parameters, gradient unpacking, small backward pieces
+int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int Cout, int Cin, int NP, int KP,
+                         int taps, int ps_r, cudaStream_t s);
+int launch_unpack_wgrad(const float* dWp, float* grad, int Cout, int Cin, int KP, int taps, int ps_r, cudaStream_t s);
+int launch_colsum(const void* dY, int elem, int ld, int M, int N, int ps_r, float alpha, float* out, cudaStream_t s);
+int launch_unshuffle(const void* in, void* out, int B, int H, int W, int C, int r, int ld_in, cudaStream_t s);
+int launch_nchw3_to_nhwc64(const float* in, void* out, int B, int H, int W, float scale, const float* shift3, cudaStream_t s);
+int launch_add_inplace(float* a, const float* b, void* out_bf, size_t n, cudaStream_t s);
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s);

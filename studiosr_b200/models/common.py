@@ -34,17 +34,34 @@ def converge_images(images: List[torch.Tensor]) -> torch.Tensor:
     return torch.mean(torch.stack(back), dim=0)
 
 
-class _NativeForward(torch.autograd.Function):
-    """Forward through libssr_b200; backward is not part of this round and fails loudly."""
+class _NativeTrainStep(torch.autograd.Function):
+    """`out = model(x)` / `loss.backward()` of the Trainer step (trainer.py:97-105) through libssr_b200:
+    forward keeps every GEMM operand in a workspace, backward produces all parameter gradients (fp32, PyTorch
+    layouts) with the tensor-core dgrad / wgrad kernels.  dL/dx is not produced."""
 
     @staticmethod
-    def forward(ctx, x, model, precision, pad_mode, *params):
-        return model._native(x.device, precision).forward(x, model.scale, pad_mode)
+    def forward(ctx, x, model, nat, names, *tensors):
+        y, ws = nat.train_forward(x, [t.detach() for t in tensors], model.scale)
+        ctx.nat, ctx.ws, ctx.shape = nat, ws, tuple(x.shape)
+        ctx.meta = [(t.shape, t.numel(), t.requires_grad) for t in tensors]
+        return y
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(
-            "studiosr_b200: the sm_100a backward kernels are not built yet (forward/inference only in this round)")
+    def backward(ctx, dy):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("studiosr_b200: the gradient with respect to the input image is not built")
+        total = sum(n for _, n, rg in ctx.meta if rg)
+        flat = torch.empty(total, dtype=torch.float32, device=dy.device)  # one flat buffer: grads are views into it
+        grads, off = [], 0
+        for shape, n, rg in ctx.meta:
+            if rg:
+                grads.append(flat[off:off + n].view(shape))
+                off += n
+            else:
+                grads.append(None)
+        ctx.nat.train_backward(dy, grads, ctx.shape, ctx.ws)
+        ctx.ws = None
+        return (None, None, None, None, *grads)
 
 
 class Model(nn.Module):
@@ -95,9 +112,26 @@ class Model(nn.Module):
         assert x.dim() == 4 and x.shape[1] == self.n_colors, "expected [B, n_colors, H, W]"
         precision = self._resolve_precision(x)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            params = [p for p in self.parameters() if p.requires_grad]
-            return _NativeForward.apply(x, self, precision, self._pad_mode(), *params)
+            return self._train_forward(x, precision)
         return self._native(x.device, precision).forward(x, self.scale, self._pad_mode())
+
+    def _train_forward(self, x: torch.Tensor, precision: str) -> torch.Tensor:
+        """Differentiable forward (the Trainer's `model(x)`, trainer.py:101-102)."""
+        if precision != "bf16":
+            raise NotImplementedError(
+                "studiosr_b200: the backward kernels are built for the bf16 tensor-core precision (the Trainer's default "
+                "`torch.autocast(dtype=torch.bfloat16)`, trainer.py:69,80); run under bf16 autocast or set model.precision = 'bf16'")
+        named = {k: v for k, v in self.state_dict(keep_vars=True).items() if v.is_floating_point()}
+        dev = torch.device(x.device)
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), precision, "train")
+        nat = self._natives.get(key)
+        if nat is None:
+            nat = NativeModel(self._native_config(_lib.PRECISIONS[precision]), dev)
+            nat.load_state(named, None)  # establishes the packed layouts; the values are re-packed on device every step
+            nat.train_bind(named)
+            self._natives[key] = nat
+        names = list(named.keys())
+        return _NativeTrainStep.apply(x, self, nat, names, *[named[k] for k in names])
 
     def _device(self) -> torch.device:
         return next(self.parameters()).device

@@ -66,6 +66,42 @@ class NativeModel:
                                                   ws.data_ptr(), ws.numel(), _stream_ptr(x.device)))
         return y
 
+    # -- training step (ssr_model_train_*): the fp32 master parameters stay in PyTorch's device memory -----------
+    def train_bind(self, named: Dict[str, torch.Tensor]) -> None:
+        """Name the state_dict entries once; pointers are passed per call (parameters may be re-allocated)."""
+        self._train_names = list(named.keys())
+        n = len(self._train_names)
+        names = (_lib.c_char_p * n)(*[k.encode() for k in self._train_names])
+        numels = (_lib.c_int64 * n)(*[int(named[k].numel()) for k in self._train_names])
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.ssr_model_train_bind(self.handle, n, names, numels))
+
+    def _ptr_array(self, tensors):
+        arr = (_lib.c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            arr[i] = None if t is None else t.data_ptr()
+        return arr
+
+    def train_forward(self, x: torch.Tensor, params, scale: int):
+        """x fp32 [B,3,H,W]; params: tensors in bound order.  Returns (y, workspace) -- the workspace holds the saved
+        activations and must reach train_backward untouched."""
+        B, C, H, W = x.shape
+        x = x.detach().to(torch.float32).contiguous()
+        y = torch.empty((B, C, H * scale, W * scale), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.index):
+            need = self.lib.ssr_model_train_workspace_bytes(self.handle, B, H, W)
+            ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
+            _lib.check(self.lib.ssr_model_train_forward(self.handle, self._ptr_array(params), x.data_ptr(), y.data_ptr(), B, H, W,
+                                                        ws.data_ptr(), ws.numel(), _stream_ptr(x.device)))
+        return y, ws
+
+    def train_backward(self, dy: torch.Tensor, grads, shape, ws: torch.Tensor) -> None:
+        B, _, H, W = shape
+        dy = dy.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.ssr_model_train_backward(self.handle, dy.data_ptr(), self._ptr_array(grads), B, H, W,
+                                                         ws.data_ptr(), ws.numel(), _stream_ptr(dy.device)))
+
     def upscale_u8(self, img: torch.Tensor, scale: int) -> torch.Tensor:
         """img: uint8 [B,H,W,3] on the device -> uint8 [B,sH,sW,3]."""
         B, H, W, _ = img.shape

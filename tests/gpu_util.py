@@ -76,3 +76,18 @@ def op_swin_mlp(o, res, Wp, bp, g2, be2, W1, b1, W2, b2, g3, be3, heads, hidden)
                                    _p(be3), _p(y), _p(y2), M, C, heads, hidden, _p(ws), ws.numel(), stream()))
     torch.cuda.synchronize()
     return y, y2
+
+
+def op_conv_wgrad(dy, x, taps=9, alpha=1.0, want_bias=True):
+    """dy [B,Cout,H,W], x [B,Cin,H,W] -> (dW [Cout,Cin,3,3] or [Cout,Cin], db [Cout])"""
+    lib = _lib.load()
+    B, Cout, H, Wd = dy.shape
+    Cin = x.shape[1]
+    dW = torch.empty((Cout, Cin, 3, 3) if taps == 9 else (Cout, Cin), device="cuda")
+    db = torch.empty(Cout, device="cuda") if want_bias else None
+    elems = B * H * Wd * (Cin + Cout + 128) + 2 * (Cout + 64) * taps * (Cin + 64) + 4096
+    ws = _ws(lib.ssr_op_workspace_bytes(elems))
+    _lib.check(lib.ssr_op_conv3x3_wgrad(_p(dy), _p(x), _p(dW), _p(db), B, Cin, Cout, H, Wd, taps, alpha, _p(ws), ws.numel(),
+                                        stream()))
+    torch.cuda.synchronize()
+    return dW, db

@@ -1,0 +1,125 @@
+"""-m gpu: parity of the training path -- the tcgen05 weight-gradient kernel at op level and the whole
+EDSR forward+backward through the drop-in module -- against torch autograd over the oracle restatement (which is what the
+reference's `loss.backward()` computes, trainer.py:104) on the same seeded weights and inputs.
+Tolerance (bf16 operands, fp32 accumulation, same dtype policy as the reference under bf16 autocast): the per-parameter
+relative L2 error of the gradient against the fp32 oracle must not exceed 2e-2, or 2x the error the oracle itself makes
+when it runs under the reference's own policy (torch.autocast(bfloat16), trainer.py:69,80), whichever is larger."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sr_oracle as O
+from oracle import synth
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,taps", [
+    (2, 64, 64, 16, 16, 9),
+    (1, 64, 128, 8, 8, 9),
+    (3, 180, 180, 24, 24, 9),    # SwinIR RSTB conv (padded 192)
+    (2, 256, 256, 48, 48, 9),    # EDSR ResBlock conv at the cfg2 patch size
+    (1, 64, 256, 13, 9, 9),      # ragged image, pixel-shuffle-class width
+    (2, 3, 64, 12, 20, 9),       # head conv (3 -> F)
+    (2, 64, 3, 12, 20, 9),       # reconstruction conv (F -> 3)
+    (1, 64, 1024, 10, 10, 9),    # upsampler conv
+    (1, 180, 360, 50, 7, 1),     # nn.Linear over tokens (fc1)
+    (1, 360, 180, 33, 5, 1),     # fc2: two column blocks
+])
+def test_conv_wgrad(B, Cin, Cout, H, W, taps):
+    g = torch.Generator().manual_seed(B * 1000 + Cin + Cout + H)
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    dy = _bf(torch.randn(B, Cout, H, W, generator=g))
+    w = torch.zeros(Cout, Cin, 3, 3) if taps == 9 else torch.zeros(Cout, Cin, 1, 1)
+    w.requires_grad_(True)
+    b = torch.zeros(Cout, requires_grad=True)
+    y = F.conv2d(x.double(), w.double(), b.double(), padding=taps // 6)
+    gw, gb = torch.autograd.grad(y, (w, b), dy.double())
+    dW, db = G.op_conv_wgrad(dy.cuda(), x.cuda(), taps=taps, alpha=0.5)
+    ref_w = 0.5 * gw.float().reshape(dW.shape)
+    assert _rel(dW.cpu(), ref_w) < 1e-4, f"dW rel err {_rel(dW.cpu(), ref_w):.3e}"
+    assert _rel(db.cpu(), 0.5 * gb.float()) < 1e-4, f"db rel err {_rel(db.cpu(), 0.5 * gb.float()):.3e}"
+
+
+def _edsr_case(cfg, B, H, W, wseed, xseed):
+    from studiosr_b200.models import EDSR
+
+    P = synth.edsr_weights(cfg, wseed)
+    x = synth.image_batch((B, 3, H, W), xseed)
+    tgt = synth.image_batch((B, 3, H * cfg["scale"], W * cfg["scale"]), xseed + 1)
+    # oracle: fp32 autograd over the restated forward with an L1 loss (trainer.py:45,102)
+    Pr = {k: v.clone().requires_grad_(v.is_floating_point() and "mean" not in k) for k, v in P.items()}
+    loss_ref = F.l1_loss(O.edsr_forward(Pr, x, cfg), tgt)
+    loss_ref.backward()
+    # the same oracle under the reference's bf16 autocast policy: how far bf16 itself moves each gradient
+    Pa = {k: v.clone().requires_grad_(v.is_floating_point() and "mean" not in k) for k, v in P.items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        loss_a = F.l1_loss(O.edsr_forward(Pa, x, cfg), tgt)
+    loss_a.backward()
+    model = EDSR(**cfg)
+    model.load_state_dict(P, strict=True)
+    model = model.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = model(x.cuda())
+        loss = F.l1_loss(out, tgt.cuda())
+    loss.backward()
+    return model, Pr, Pa, loss.item(), loss_ref.item()
+
+
+@pytest.mark.parametrize("name,cfg,B,H,W", [
+    ("tiny", synth.EDSR_TINY, 2, 24, 20),
+    ("x2", dict(synth.EDSR_TINY, scale=2, n_resblocks=2), 1, 16, 16),
+    ("x3", dict(synth.EDSR_TINY, scale=3, n_resblocks=1), 1, 12, 16),
+    ("wide", dict(synth.EDSR_DEFAULT, n_resblocks=4), 2, 48, 48),  # cfg2 width and patch size, fewer blocks
+])
+def test_edsr_backward(name, cfg, B, H, W):
+    model, Pr, Pa, loss, loss_ref = _edsr_case(cfg, B, H, W, 5, 77)
+    assert abs(loss - loss_ref) < 2e-3 * max(1.0, abs(loss_ref)), (loss, loss_ref)
+    report = []
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        e = _rel(p.grad.cpu(), Pr[k].grad)
+        e_ref = _rel(Pa[k].grad.float(), Pr[k].grad)
+        report.append((e / max(2e-2, 2.0 * e_ref), e, e_ref, k))
+    worst = max(report)
+    print(f"EDSR {name}: worst gradient rel err {worst[1]:.3e} (reference under bf16 autocast: {worst[2]:.3e}) at {worst[3]}")
+    assert worst[0] <= 1.0, f"EDSR {name}: gradient rel err {worst[1]:.3e} vs reference-bf16 {worst[2]:.3e} at {worst[3]}"
+
+
+def test_edsr_train_step_updates_weights():
+    """Two optimiser steps through the unchanged torch.optim.Adam: the device-side re-pack must pick up the new weights."""
+    from studiosr_b200.models import EDSR
+
+    cfg = synth.EDSR_TINY
+    model = EDSR(**cfg)
+    model.load_state_dict(synth.edsr_weights(cfg, 3), strict=True)
+    model = model.cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x = synth.image_batch((2, 3, 16, 16), 9).cuda()
+    tgt = synth.image_batch((2, 3, 64, 64), 10).cuda()
+    losses = []
+    for _ in range(6):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.l1_loss(model(x), tgt)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses
