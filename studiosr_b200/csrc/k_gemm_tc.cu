@@ -270,6 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[4 * q + 2] += bv.z;
           v[4 * q + 3] += bv.w;
         }
+        if (g.out_pre) store_T(v, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
         epilogue_act(v, g.act, g.slope, g.alpha);
         if (g.mask) {  // activation backward (training dgrad): gate by the sign of the saved forward output
           float mk[32];
@@ -294,7 +295,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = mk[i] > 0.0f ? v[i] : v[i] * g.mask_slope;
+            for (int i = 0; i < 32; ++i) {
+              if (g.mask_mode == 1) {  // d/du [u Phi(u)] = Phi(u) + u phi(u)
+                const float u = mk[i];
+                const float cdf = 0.5f * (1.0f + fast_erf(u * 0.70710678118654752440f));
+                v[i] *= fmaf(u * 0.3989422804014327f, __expf(-0.5f * u * u), cdf);
+              } else {
+                v[i] = mk[i] > 0.0f ? v[i] : v[i] * g.mask_slope;
+              }
+            }
           }
         }
         if (dbg && c == 1) dbg[6] = clock64();

@@ -146,4 +146,254 @@ int launch_add_inplace(float* a, const float* b, void* out_bf, size_t n, cudaStr
   return SSR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// nn.Linear maps (model.cu finalize_swinir): source (n, k) -> packed (np, kp) and the row scale
+__device__ __forceinline__ void lin_map(const LinMap& m, int n, int k, int* np, int* kp, float* scale) {
+  *np = n;
+  *kp = k;
+  *scale = 1.0f;
+  if (m.mode == 1) {
+    const int part = n / m.C, r = n - part * m.C, h = r / m.d, j = r - h * m.d;
+    *np = part * m.QP + h * m.DP + j;
+    if (part == 0) *scale = m.qscale;
+  } else if (m.mode == 2) {
+    const int h = k / m.d, j = k - h * m.d;
+    *kp = h * m.DP + j;
+  }
+}
+
+// W fp32 [N][K] -> Wf bf16 [NP][KP] (forward), Wd bf16 [KP][NP] (dgrad: dX = dY Wd^T ... rows = input feature), bias
+__global__ void pack_linear_dev_kernel(const float* __restrict__ W, const float* __restrict__ b, __nv_bfloat16* Wf, float* bf,
+                                       __nv_bfloat16* Wd, int N, int K, int NP, int KP, const LinMap map) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx - n * K;
+  int np, kp;
+  float sc;
+  lin_map(map, n, k, &np, &kp, &sc);
+  const __nv_bfloat16 v = __float2bfloat16_rn(W[idx] * sc);
+  if (Wf) Wf[(size_t)np * KP + kp] = v;
+  if (Wd) Wd[(size_t)kp * NP + np] = v;
+  if (k == 0 && bf && b) bf[np] = b[n] * sc;
+}
+int launch_pack_linear_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int N, int K, int NP, int KP,
+                           const LinMap& map, cudaStream_t s) {
+  pack_linear_dev_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(W, b, (__nv_bfloat16*)Wf, bf, (__nv_bfloat16*)Wd, N, K, NP, KP, map);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// packed fp32 gradient dWp [NP][KP] -> grad [N][K]; the q-row scale of the pack is the chain-rule factor of the raw weight
+__global__ void unpack_linear_grad_kernel(const float* __restrict__ dWp, float* grad, int N, int K, int KP, const LinMap map) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx - n * K;
+  int np, kp;
+  float sc;
+  lin_map(map, n, k, &np, &kp, &sc);
+  grad[idx] = dWp[(size_t)np * KP + kp] * sc;
+}
+int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int KP, const LinMap& map, cudaStream_t s) {
+  unpack_linear_grad_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(dWp, grad, N, K, KP, map);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// bias gradient of a linear layer: out[n] = scale(n) * sum_m dY[m][np(n)]   (out zeroed here, atomics over row strips)
+__global__ void colsum_map_kernel(const void* __restrict__ dY, int elem, int ld, int M, int N, const LinMap map, float* out,
+                                  int rows_per_block) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    int np, kp;
+    float sc;
+    lin_map(map, n, 0, &np, &kp, &sc);
+    float acc = 0.0f;
+    for (int r = r0; r < r1; ++r) acc += load_elem(dY, (size_t)r * ld + np, elem);
+    atomicAdd(out + n, acc * sc);
+  }
+}
+int launch_colsum_map(const void* dY, int elem, int ld, int M, int N, const LinMap& map, float* out, cudaStream_t s) {
+  const int blocks = min((M + 63) / 64, 4 * 148);
+  const int rpb = (M + blocks - 1) / blocks;
+  SSR_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 4, s));
+  colsum_map_kernel<<<(M + rpb - 1) / rpb, 256, 0, s>>>(dY, elem, ld, M, N, map, out, rpb);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// relative_position_bias_table [nb][heads] -> [heads][nb] (the layout the attention kernels read)
+__global__ void bias_table_to_head_major_kernel(const float* __restrict__ t, float* out, int nb, int heads) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nb * heads) return;
+  const int h = idx / nb, i = idx - h * nb;
+  out[idx] = t[(size_t)i * heads + h];
+}
+int launch_transpose_table(const float* table, float* out, int nb, int heads, cudaStream_t s) {
+  bias_table_to_head_major_kernel<<<(nb * heads + 255) / 256, 256, 0, s>>>(table, out, nb, heads);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward, one warp per row (rows strided over all warps so dgamma / dbeta partials live in registers):
+//   xhat = (x - mean) rstd;  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  __shared__ float red[2][8][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * 8 + wib, nwarps = gridDim.x * 8;
+  float dg[8], db[8], gam[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dg[j] = db[j] = 0.0f;
+    const int n = lane + 32 * j;
+    gam[j] = n < a.C ? __ldg(a.gamma + n) : 0.0f;
+  }
+  const float invC = 1.0f / (float)a.C;
+  for (int row = warp; row < a.M; row += nwarps) {
+    const float* x = a.x + (size_t)row * a.ldx;
+    float v[8], dy[8];
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = lane + 32 * j;
+      v[j] = n < a.C ? x[n] : 0.0f;
+      dy[j] = n < a.C ? load_elem(a.dy, (size_t)row * a.ld_dy + n, a.elem_dy) : 0.0f;
+      s += v[j];
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (lane + 32 * j < a.C) q += (v[j] - mean) * (v[j] - mean);
+    const float rstd = rsqrtf(warp_sum(q) * invC + a.eps);
+    float sg = 0.0f, sgx = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = (lane + 32 * j < a.C) ? (v[j] - mean) * rstd : 0.0f;  // xhat
+      dg[j] = fmaf(dy[j], v[j], dg[j]);
+      db[j] += dy[j];
+      dy[j] *= gam[j];
+      sg += dy[j];
+      sgx = fmaf(dy[j], v[j], sgx);
+    }
+    sg = warp_sum(sg) * invC;
+    sgx = warp_sum(sgx) * invC;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = lane + 32 * j;
+      if (n >= a.CP) continue;
+      float dx = n < a.C ? rstd * (dy[j] - sg - v[j] * sgx) : 0.0f;
+      const size_t o = (size_t)row * a.ldg + n;
+      if (a.Gin && n < a.C) dx += a.Gin[o];
+      a.Gout[o] = dx;
+      if (a.Gb) reinterpret_cast<__nv_bfloat16*>(a.Gb)[o] = __float2bfloat16_rn(dx);
+    }
+  }
+  if (!a.dgamma) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][wib][lane + 32 * j] = dg[j];
+    red[1][wib][lane + 32 * j] = db[j];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < a.C; n += 256) {
+    float g = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      g += red[0][w][n];
+      b += red[1][w][n];
+    }
+    atomicAdd(a.dgamma + n, g);
+    atomicAdd(a.dbeta + n, b);
+  }
+}
+int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s) {
+  SSR_CHECK(a.C <= 256 && a.CP <= 256, SSR_E_INVALID, "ln_bwd: C=%d", a.C);
+  if (a.dgamma) {
+    SSR_CUDA(cudaMemsetAsync(a.dgamma, 0, (size_t)a.C * 4, s));
+    SSR_CUDA(cudaMemsetAsync(a.dbeta, 0, (size_t)a.C * 4, s));
+  }
+  const int blocks = min((a.M + 7) / 8, 4 * 148);
+  ln_bwd_kernel<<<blocks, 256, 0, s>>>(a);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// network input for the first conv's weight gradient: pad (training flavour: reflect, common.py:277-282) + normalise
+// fp32 NCHW [B,3,h,w] -> bf16 NHWC [B,Hp,Wp,64], lanes 0..2 = x * scale + shift[c], rest zero
+__global__ void input_nhwc64_kernel(const float* __restrict__ in, __nv_bfloat16* out, int B, int h, int w, int Hp, int Wp,
+                                    float scale, float s0, float s1, float s2) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)B * Hp * Wp) return;
+  const int x = (int)(p % Wp), y = (int)((p / Wp) % Hp), b = (int)(p / ((long long)Wp * Hp));
+  const int sy = y < h ? y : 2 * (h - 1) - y, sx = x < w ? x : 2 * (w - 1) - x;
+  const size_t plane = (size_t)h * w;
+  const float* src = in + (size_t)b * 3 * plane + (size_t)sy * w + sx;
+  uint4 z = make_uint4(0, 0, 0, 0);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)p * 64);
+  uint4 first = z;
+  first.x = pack_bf16x2(src[0] * scale + s0, src[plane] * scale + s1);
+  first.y = pack_bf16x2(src[2 * plane] * scale + s2, 0.0f);
+  dst[0] = first;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) dst[i] = z;
+}
+int launch_input_nhwc64(const float* x, void* out, int B, int h, int w, int Hp, int Wp, float scale, const float* shift3,
+                        cudaStream_t s) {
+  const long long total = (long long)B * Hp * Wp;
+  input_nhwc64_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(x, (__nv_bfloat16*)out, B, h, w, Hp, Wp, scale, shift3[0],
+                                                                 shift3[1], shift3[2]);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// output gradient fp32 NCHW [B,3,ch,cw] (the cropped image) -> bf16 NHWC [B,Hs,Ws,64] of the un-cropped reconstruction
+// conv output: lanes 0..2 = dy * scale inside the crop, zero outside and in the pad lanes
+__global__ void grad_nhwc64_kernel(const float* __restrict__ dy, __nv_bfloat16* out, int B, int ch, int cw, int Hs, int Ws,
+                                   float scale) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)B * Hs * Ws) return;
+  const int x = (int)(p % Ws), y = (int)((p / Ws) % Hs), b = (int)(p / ((long long)Ws * Hs));
+  uint4 z = make_uint4(0, 0, 0, 0);
+  uint4 first = z;
+  if (y < ch && x < cw) {
+    const size_t plane = (size_t)ch * cw;
+    const float* src = dy + (size_t)b * 3 * plane + (size_t)y * cw + x;
+    first.x = pack_bf16x2(src[0] * scale, src[plane] * scale);
+    first.y = pack_bf16x2(src[2 * plane] * scale, 0.0f);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)p * 64);
+  dst[0] = first;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) dst[i] = z;
+}
+int launch_grad_nhwc64(const float* dy, void* out, int B, int ch, int cw, int Hs, int Ws, float scale, cudaStream_t s) {
+  const long long total = (long long)B * Hs * Ws;
+  grad_nhwc64_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(dy, (__nv_bfloat16*)out, B, ch, cw, Hs, Ws, scale);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* out, size_t n4) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = reinterpret_cast<const float4*>(in)[i];
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+}
+int launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s) {
+  SSR_CHECK(n % 4 == 0, SSR_E_INVALID, "f32_to_bf16: n %% 4");
+  f32_to_bf16_kernel<<<(int)((n / 4 + 255) / 256), 256, 0, s>>>(in, (__nv_bfloat16*)out, n / 4);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 }  // namespace ssr

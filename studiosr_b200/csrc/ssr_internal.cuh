@@ -92,9 +92,13 @@ struct GemmArgs {
   int K_alg, N_alg;  // un-padded contraction / output widths, for FLOP and byte accounting only
   // backward of an activation folded into a dgrad epilogue (tensor-core path only): after alpha,
   //   v = mask[m][n] > 0 ? v : v * mask_slope     (ReLU: slope 0 with mask = the forward OUTPUT; LeakyReLU likewise)
+  // mask_mode 1 (GELU backward): v *= gelu'(mask[m][n]) with mask = the saved PRE-activation
   const void* mask;  // T [M][ld_mask] or null
   int ld_mask;
   float mask_slope;
+  int mask_mode;
+  void* out_pre;  // T [M][ld_pre]: copy of (acc + bias) BEFORE the activation (kept for the backward), or null
+  int ld_pre;
   long long* dbg;    // optional per-CTA phase timestamps (developer diagnostics), 8 slots per CTA
 };
 double gemm_alg_flops(const GemmArgs& g);
@@ -247,6 +251,52 @@ struct WgradArgs {
   int N_alg, K_alg;  // un-padded widths (accounting)
 };
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t s);
+
+// backward of the window-attention core (k_attn_bwd.cu), bf16, 8x8 windows
+struct AttnBwdArgs {
+  const void* qkv;  // bf16 [B*H*W][ld_qkv]: q | k | v, each [heads][DP], q pre-scaled (as the forward reads it)
+  int ld_qkv, QP;
+  const void* d_o;  // bf16 [B*H*W][ld_do]: gradient of the attention output, channel = head*DP + j
+  int ld_do;
+  void* dqkv;         // bf16 [B*H*W][ld_qkv]: gradient of qkv (w.r.t. the pre-scaled q); pad lanes must be pre-zeroed
+  const float* bias;  // [heads][225]
+  float* dB;          // scratch fp32 [heads][64][64]
+  float* dtable;      // fp32 [225][heads] = d(relative_position_bias_table), overwritten (or null)
+  int B, H, W, shift, heads, d, DP;
+};
+int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t s);
+
+// row / column maps between a PyTorch nn.Linear [N][K] and its padded pack (model.cu finalize_swinir)
+struct LinMap {
+  int mode;  // 0: identity; 1: qkv rows n = part*C + h*d + j -> part*QP + h*DP + j (q rows scaled); 2: proj columns k = h*d + j -> h*DP + j
+  int C, d, DP, QP;
+  float qscale;
+};
+// LayerNorm backward (one warp per row): G_out = G_in + dLN(x; dy, gamma), dgamma += sum dy*xhat, dbeta += sum dy
+struct LnBwdArgs {
+  const float* x;  // fp32 [M][ldx]: LayerNorm input
+  int ldx;
+  const void* dy;  // gradient w.r.t. the LayerNorm output, [M][ld_dy], elem_dy = 2 (bf16) or 4 (fp32)
+  int ld_dy, elem_dy;
+  const float* gamma;  // [C]
+  const float* Gin;    // fp32 [M][ldg] residual-stream gradient to add, or null
+  float* Gout;         // fp32 [M][ldg]
+  void* Gb;            // bf16 copy of Gout [M][ldg], or null
+  int ldg;
+  int M, C, CP;
+  float eps;
+  float *dgamma, *dbeta;  // [C], accumulated with atomics (zero them first), or null
+};
+int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s);
+int launch_pack_linear_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int N, int K, int NP, int KP,
+                           const LinMap& map, cudaStream_t s);
+int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int KP, const LinMap& map, cudaStream_t s);
+int launch_colsum_map(const void* dY, int elem, int ld, int M, int N, const LinMap& map, float* out, cudaStream_t s);
+int launch_transpose_table(const float* table, float* out, int nb, int heads, cudaStream_t s);
+int launch_input_nhwc64(const float* x, void* out, int B, int h, int w, int Hp, int Wp, float scale, const float* shift3,
+                        cudaStream_t s);
+int launch_grad_nhwc64(const float* dy, void* out, int B, int ch, int cw, int Hs, int Ws, float scale, cudaStream_t s);
+int launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s);
 
 // k_train.cu: on-device (re)packing of the fp32 master parameters, gradient unpacking, small backward pieces
 int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int Cout, int Cin, int NP, int KP,

@@ -2,7 +2,10 @@
 // the C ABI, bf16 tensor-core path.  Replaces what `loss.backward()` (trainer.py:104) runs through torch autograd for
 // the model: the reference has no hand-written backward, so every formula below is the adjoint of the cited forward.
 // The fp32 master parameters stay in PyTorch-owned device memory; each train_forward re-packs them on the device.
+#include <math.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "ssr_model.cuh"
 
@@ -16,6 +19,25 @@ struct ConvT {       // a trainable conv3x3 executed by the implicit-GEMM kernel
   int Cout = 0, Cin = 0;
   size_t dg_off = 0;     // dgrad pack in train->arena2: bf16 [KP][9*NP]
   size_t dwp_off = 0;    // packed fp32 weight gradient [NP][9][KP] (float offset into the dwp workspace block)
+};
+
+struct LinT {  // a trainable nn.Linear executed by the GEMM kernels
+  const Lin* fwd = nullptr;
+  int wi = -1, bi = -1;
+  int N = 0, K = 0;  // PyTorch [N][K]
+  LinMap map{};
+  size_t dg_off = 0;   // dgrad pack in arena2: bf16 [KP][NP]
+  size_t dwp_off = 0;  // packed fp32 weight gradient [NP][KP]
+};
+struct LnT {
+  const LNp* p = nullptr;
+  int gi = -1, bi = -1;
+};
+struct BlockT {
+  LnT n1, n2;
+  LinT qkv, proj, fc1, fc2;
+  int table_i = -1;
+  size_t bias_off = 0;  // head-major table in m->arena
 };
 
 }  // namespace ssr
@@ -34,6 +56,11 @@ struct ssr_train_state {
   size_t head_dwp = 0;
   std::vector<int> e_res_a, e_res_b, e_up;  // indices into convs
   int e_body_tail = -1, e_last = -1;
+  // SwinIR
+  std::vector<std::vector<BlockT>> s_blocks;
+  std::vector<int> s_conv;  // RSTB convs
+  LnT s_pe, s_fin;
+  int s_cab = -1, s_cbu = -1;
 };
 
 namespace ssr {
@@ -413,6 +440,638 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
   return SSR_OK;
 }
 
+
+// =============================================================================================
+// SwinIR (swinir.py:353-372) training executor
+// =============================================================================================
+static int add_linear(ssr_train_state* t, const std::string& name, const Lin* fwd, int N, int K, const LinMap& map, size_t* a2,
+                      LinT* out) {
+  out->fwd = fwd;
+  out->N = N;
+  out->K = K;
+  out->map = map;
+  out->wi = find_idx(t, name + ".weight", (int64_t)N * K);
+  out->bi = find_idx(t, name + ".bias", N);
+  if (out->wi < 0 || out->bi < 0) return SSR_E_STATE;
+  *a2 = (*a2 + 255) & ~(size_t)255;
+  out->dg_off = *a2;
+  *a2 += (size_t)fwd->KP * fwd->NP * 2;
+  out->dwp_off = t->dwp_floats;
+  t->dwp_floats += (size_t)fwd->NP * fwd->KP;
+  return SSR_OK;
+}
+static int add_ln(ssr_train_state* t, const std::string& name, const LNp* p, int C, LnT* out) {
+  out->p = p;
+  out->gi = find_idx(t, name + ".weight", C);
+  out->bi = find_idx(t, name + ".bias", C);
+  return (out->gi < 0 || out->bi < 0) ? SSR_E_STATE : SSR_OK;
+}
+
+static int bind_swinir(ssr_model* m) {
+  ssr_train_state* t = m->train;
+  const ssr_model_config& c = m->cfg;
+  SSR_CHECK(c.upsampler == 0, SSR_E_INVALID, "training path: only the 'pixelshuffle' upsampler is built");
+  SSR_CHECK(c.window_size == 8, SSR_E_INVALID, "training path: window_size 8 only");
+  const int C = m->C;
+  size_t a2 = 0;
+  t->zero_bias_off = a2;
+  a2 += 4096 * 4;
+  t->head_w = find_idx(t, "conv_first.weight", (int64_t)C * 27);
+  t->head_b = find_idx(t, "conv_first.bias", C);
+  if (t->head_w < 0 || t->head_b < 0) return SSR_E_STATE;
+  t->head_dwp = t->dwp_floats;
+  t->dwp_floats += (size_t)m->CP * 9 * 64;
+  SSR_TRY(add_ln(t, "patch_embed.norm", &m->pe_norm, C, &t->s_pe));
+  t->s_blocks.resize(m->layers.size());
+  for (size_t li = 0; li < m->layers.size(); ++li) {
+    const Layer& L = m->layers[li];
+    LinMap ident{0, C, L.d, L.DP, L.QP, 1.0f};
+    LinMap mq{1, C, L.d, L.DP, L.QP, 1.0f / sqrtf((float)L.d)};
+    LinMap mp{2, C, L.d, L.DP, L.QP, 1.0f};
+    for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
+      const Block& B = L.blocks[bi];
+      BlockT bt;
+      char pre[128];
+      snprintf(pre, sizeof(pre), "layers.%d.residual_group.blocks.%d", (int)li, (int)bi);
+      const std::string p(pre);
+      SSR_TRY(add_ln(t, p + ".norm1", &B.norm1, C, &bt.n1));
+      SSR_TRY(add_ln(t, p + ".norm2", &B.norm2, C, &bt.n2));
+      SSR_TRY(add_linear(t, p + ".attn.qkv", &B.qkv, 3 * C, C, mq, &a2, &bt.qkv));
+      SSR_TRY(add_linear(t, p + ".attn.proj", &B.proj, C, C, mp, &a2, &bt.proj));
+      SSR_TRY(add_linear(t, p + ".mlp.fc1", &B.fc1, m->HID, C, ident, &a2, &bt.fc1));
+      SSR_TRY(add_linear(t, p + ".mlp.fc2", &B.fc2, C, m->HID, ident, &a2, &bt.fc2));
+      bt.table_i = find_idx(t, p + ".attn.relative_position_bias_table", (int64_t)225 * L.heads);
+      if (bt.table_i < 0) return SSR_E_STATE;
+      bt.bias_off = B.bias_off;
+      t->s_blocks[li].push_back(bt);
+    }
+    char nm[64];
+    snprintf(nm, sizeof(nm), "layers.%d.conv", (int)li);
+    const int ic = add_conv(t, nm, &L.conv, C, C, &a2);
+    if (ic < 0) return SSR_E_STATE;
+    t->s_conv.push_back(ic);
+  }
+  SSR_TRY(add_ln(t, "norm", &m->final_norm, C, &t->s_fin));
+  t->s_cab = add_conv(t, "conv_after_body", &m->conv_after_body, C, C, &a2);
+  t->s_cbu = add_conv(t, "conv_before_upsample.0", &m->conv_before_up, 64, C, &a2);
+  if (t->s_cab < 0 || t->s_cbu < 0) return SSR_E_STATE;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "upsample.%d", (int)(2 * i));
+    const int iu = add_conv(t, nm, &m->up[i], m->up[i].N, 64, &a2);
+    if (iu < 0) return SSR_E_STATE;
+    t->e_up.push_back(iu);
+  }
+  t->e_last = add_conv(t, "conv_last", &m->last_lin, 3, 64, &a2);
+  if (t->e_last < 0) return SSR_E_STATE;
+  t->arena2_bytes = a2 + 1024;
+  SSR_CUDA(cudaMalloc(&t->arena2, t->arena2_bytes));
+  SSR_CUDA(cudaMemset(t->arena2, 0, t->arena2_bytes));
+  return SSR_OK;
+}
+
+struct SwinBlockWs {
+  const float* tin;  // fp32 LN1 input (layer input or the previous block's output)
+  float* tmid;       // fp32 after the attention residual
+  float* tout;       // fp32 block output (null for the last block of a layer: only the bf16 copy is needed)
+  void *xn1, *qkv, *o, *xn2, *u, *h;
+};
+struct SwinTrainWs {
+  void* xin64;
+  float* x0;
+  std::vector<float*> g;  // n_layers + 1
+  std::vector<std::vector<SwinBlockWs>> blk;
+  std::vector<void*> tb;
+  void *xnf, *tbf, *cbu;
+  std::vector<void*> hr, ghr;
+  void *dy64, *gU, *dcbu;
+  float *G, *Gt, *Gres, *dB;
+  void *Gb, *Gtb, *dH, *dXn, *dO, *dQKV;
+  float* dwp;
+};
+
+static size_t plan_swin_train(const ssr_model* m, void* base, int B, int Hp, int Wp, SwinTrainWs* w) {
+  Carver c(base);
+  const size_t T = (size_t)B * Hp * Wp;
+  const int CP = m->CP, HP = m->HP;
+  const size_t nL = m->layers.size();
+  w->xin64 = c.take(T * 64 * 2);
+  w->x0 = (float*)c.take(T * CP * 4);
+  w->g.resize(nL + 1);
+  for (size_t i = 0; i <= nL; ++i) w->g[i] = (float*)c.take(T * CP * 4);
+  w->blk.resize(nL);
+  w->tb.resize(nL);
+  int QPmax = 0, heads_max = 0;
+  for (size_t li = 0; li < nL; ++li) {
+    const Layer& L = m->layers[li];
+    QPmax = std::max(QPmax, L.QP);
+    heads_max = std::max(heads_max, L.heads);
+    w->blk[li].resize(L.blocks.size());
+    for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
+      SwinBlockWs& b = w->blk[li][bi];
+      b.tin = bi == 0 ? w->g[li] : w->blk[li][bi - 1].tout;
+      b.xn1 = c.take(T * CP * 2);
+      b.qkv = c.take(T * 3 * L.QP * 2);
+      b.o = c.take(T * L.QP * 2);
+      b.tmid = (float*)c.take(T * CP * 4);
+      b.xn2 = c.take(T * CP * 2);
+      b.u = c.take(T * HP * 2);
+      b.h = c.take(T * HP * 2);
+      b.tout = bi + 1 < L.blocks.size() ? (float*)c.take(T * CP * 4) : nullptr;
+    }
+    w->tb[li] = c.take(T * CP * 2);
+  }
+  w->xnf = c.take(T * CP * 2);
+  w->tbf = c.take(T * CP * 2);
+  w->cbu = c.take(T * 64 * 2);
+  w->dcbu = c.take(T * 64 * 2);
+  size_t px = T, gu_max = 0;
+  w->hr.resize(m->up.size());
+  w->ghr.resize(m->up.size());
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    gu_max = std::max(gu_max, px * (size_t)m->up[i].NP);
+    px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
+    w->hr[i] = c.take(px * 64 * 2);
+    w->ghr[i] = c.take(px * 64 * 2);
+  }
+  w->dy64 = c.take(px * 64 * 2);
+  w->gU = c.take(gu_max * 2);
+  w->G = (float*)c.take(T * CP * 4);
+  w->Gt = (float*)c.take(T * CP * 4);
+  w->Gres = (float*)c.take(T * CP * 4);
+  w->Gb = c.take(T * CP * 2);
+  w->Gtb = c.take(T * CP * 2);
+  w->dH = c.take(T * HP * 2);
+  w->dXn = c.take(T * CP * 2);
+  w->dO = c.take(T * QPmax * 2);
+  w->dQKV = c.take(T * 3 * QPmax * 2);
+  w->dB = (float*)c.take((size_t)heads_max * 64 * 64 * 4);
+  w->dwp = (float*)c.take(m->train->dwp_floats * 4);
+  return c.off + 1024;
+}
+
+static int repack_linear(ssr_model* m, const LinT& l, const float* const* params, cudaStream_t s) {
+  const Lin& L = *l.fwd;
+  return launch_pack_linear_dev(params[l.wi], params[l.bi], m->arena + L.w_off, m->dev<float>(L.b_off), m->train->arena2 + l.dg_off,
+                                l.N, l.K, L.NP, L.KP, l.map, s);
+}
+static int repack_ln(ssr_model* m, const LnT& l, const float* const* params, int C, cudaStream_t s) {
+  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(l.p->g_off), params[l.gi], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(l.p->b_off), params[l.bi], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  return SSR_OK;
+}
+
+static void train_padded(const ssr_model* m, int h, int w, int* Hp, int* Wp) {
+  const int ws = m->cfg.window_size;
+  *Hp = (h + ws - 1) / ws * ws;
+  *Wp = (w + ws - 1) / ws * ws;
+}
+
+static const float kMean3[3] = {0.4488f, 0.4371f, 0.4040f};  // common.py:223
+
+static int train_forward_swinir(ssr_model* m, const float* const* params, const float* x, float* y, int B, int h, int w, void* ws,
+                                size_t ws_bytes, cudaStream_t s) {
+  ssr_train_state* t = m->train;
+  const ssr_model_config& c = m->cfg;
+  int Hp, Wp;
+  train_padded(m, h, w, &Hp, &Wp);
+  SSR_CHECK(Hp - h < h && Wp - w < w, SSR_E_INVALID, "reflect padding needs pad < size (%dx%d)", h, w);
+  SwinTrainWs W;
+  const size_t need = plan_swin_train(m, ws, B, Hp, Wp, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "train workspace %zu B < required %zu B", ws_bytes, need);
+  const int C = m->C, CP = m->CP, HP = m->HP;
+  const int T = B * Hp * Wp;
+  // ---- re-pack the fp32 master parameters ----
+  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(m->conv_first_w), params[t->head_w], (size_t)C * 27 * 4, cudaMemcpyDeviceToDevice, s));
+  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(m->conv_first_b), params[t->head_b], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  SSR_TRY(repack_ln(m, t->s_pe, params, C, s));
+  SSR_TRY(repack_ln(m, t->s_fin, params, C, s));
+  for (size_t li = 0; li < t->s_blocks.size(); ++li)
+    for (const BlockT& b : t->s_blocks[li]) {
+      SSR_TRY(repack_ln(m, b.n1, params, C, s));
+      SSR_TRY(repack_ln(m, b.n2, params, C, s));
+      SSR_TRY(repack_linear(m, b.qkv, params, s));
+      SSR_TRY(repack_linear(m, b.proj, params, s));
+      SSR_TRY(repack_linear(m, b.fc1, params, s));
+      SSR_TRY(repack_linear(m, b.fc2, params, s));
+      SSR_TRY(launch_transpose_table(params[b.table_i], m->dev<float>(b.bias_off), 225, m->layers[li].heads, s));
+    }
+  for (const ConvT& cv : t->convs) SSR_TRY(repack_conv(m, cv, params, s));
+  // ---- forward (swinir.py:353-372, training branch: reflect pad), un-fused so that every GEMM operand is kept ----
+  const float in_scale = 1.0f / c.img_range;
+  float in_shift[3] = {-kMean3[0], -kMean3[1], -kMean3[2]};
+  SSR_TRY(launch_input_nhwc64(x, W.xin64, B, h, w, Hp, Wp, in_scale, in_shift, s));
+  {
+    ConvFirstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = x;
+    a.fh = h;
+    a.fw = w;
+    a.h = h;
+    a.w = w;
+    a.Hp = Hp;
+    a.Wp = Wp;
+    a.pad_mode = SSR_PAD_TRAIN;
+    a.B = B;
+    a.in_scale = in_scale;
+    for (int i = 0; i < 3; ++i) a.in_shift[i] = in_shift[i];
+    a.Wc = m->dev<float>(m->conv_first_w);
+    a.bias = m->dev<float>(m->conv_first_b);
+    a.Cout = C;
+    a.out_f32 = W.x0;
+    a.ld_f32 = CP;
+    a.elem = 2;
+    SSR_TRY(launch_conv_first(a, s));
+  }
+  {
+    LnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = W.x0;
+    a.ld_in = CP;
+    a.M = T;
+    a.C = C;
+    a.CP = CP;
+    a.g1 = m->dev<float>(m->pe_norm.g_off);
+    a.b1 = m->dev<float>(m->pe_norm.b_off);
+    a.out_f32 = W.g[0];
+    a.ld_f32 = CP;
+    const Block& b0 = m->layers[0].blocks[0];
+    a.g2 = m->dev<float>(b0.norm1.g_off);
+    a.b2 = m->dev<float>(b0.norm1.b_off);
+    a.out_T = W.blk[0][0].xn1;
+    a.ld_T = CP;
+    a.elem = 2;
+    a.eps = 1e-5f;
+    SSR_TRY(launch_layernorm(a, s));
+  }
+  const int nL = (int)m->layers.size();
+  for (int li = 0; li < nL; ++li) {
+    const Layer& L = m->layers[li];
+    const int depth = (int)L.blocks.size();
+    for (int bi = 0; bi < depth; ++bi) {
+      const Block& blk = L.blocks[bi];
+      SwinBlockWs& bw = W.blk[li][bi];
+      {
+        GemmArgs g = gemm_base(m, blk.qkv, bw.xn1, CP, B, Hp, Wp);
+        g.out_T = bw.qkv;
+        g.ld_T = 3 * L.QP;
+        SSR_TRY(run_gemm(m, g, s));
+      }
+      {
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.qkv = bw.qkv;
+        a.ld_qkv = 3 * L.QP;
+        a.QP = L.QP;
+        a.o = bw.o;
+        a.ld_o = L.QP;
+        a.bias = m->dev<float>(blk.bias_off);
+        a.B = B;
+        a.H = Hp;
+        a.W = Wp;
+        a.ws = c.window_size;
+        a.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
+        a.heads = L.heads;
+        a.d = L.d;
+        a.DP = L.DP;
+        SSR_CUDA(cudaMemsetAsync(bw.o, 0, (size_t)T * L.QP * 2, s));
+        SSR_TRY(launch_attn_mma(a, s));
+      }
+      {
+        GemmArgs g = gemm_base(m, blk.proj, bw.o, L.QP, B, Hp, Wp);
+        g.res = bw.tin;
+        g.ldres = CP;
+        g.out_f32 = bw.tmid;
+        g.ld_f32 = CP;
+        g.out_ln = bw.xn2;
+        g.ld_ln = CP;
+        g.gamma = m->dev<float>(blk.norm2.g_off);
+        g.beta = m->dev<float>(blk.norm2.b_off);
+        SSR_TRY(run_gemm(m, g, s));
+      }
+      {
+        GemmArgs g = gemm_base(m, blk.fc1, bw.xn2, CP, B, Hp, Wp);
+        g.act = ACT_GELU;
+        g.out_pre = bw.u;
+        g.ld_pre = HP;
+        g.out_T = bw.h;
+        g.ld_T = HP;
+        SSR_TRY(run_gemm(m, g, s));
+      }
+      {
+        GemmArgs g = gemm_base(m, blk.fc2, bw.h, HP, B, Hp, Wp);
+        g.res = bw.tmid;
+        g.ldres = CP;
+        if (bi + 1 < depth) {
+          g.out_f32 = bw.tout;
+          g.ld_f32 = CP;
+          g.out_ln = W.blk[li][bi + 1].xn1;
+          g.ld_ln = CP;
+          g.gamma = m->dev<float>(L.blocks[bi + 1].norm1.g_off);
+          g.beta = m->dev<float>(L.blocks[bi + 1].norm1.b_off);
+        } else {
+          g.out_T = W.tb[li];
+          g.ld_T = CP;
+        }
+        SSR_TRY(run_gemm(m, g, s));
+      }
+    }
+    {
+      GemmArgs g = gemm_base(m, L.conv, W.tb[li], CP, B, Hp, Wp);
+      g.res = W.g[li];
+      g.ldres = CP;
+      g.out_f32 = W.g[li + 1];
+      g.ld_f32 = CP;
+      const LNp& nx = li + 1 < nL ? m->layers[li + 1].blocks[0].norm1 : m->final_norm;
+      g.out_ln = li + 1 < nL ? W.blk[li + 1][0].xn1 : W.xnf;
+      g.ld_ln = CP;
+      g.gamma = m->dev<float>(nx.g_off);
+      g.beta = m->dev<float>(nx.b_off);
+      SSR_TRY(run_gemm(m, g, s));
+    }
+  }
+  {
+    GemmArgs g = gemm_base(m, m->conv_after_body, W.xnf, CP, B, Hp, Wp);
+    g.res = W.x0;
+    g.ldres = CP;
+    g.out_T = W.tbf;
+    g.ld_T = CP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  {
+    GemmArgs g = gemm_base(m, m->conv_before_up, W.tbf, CP, B, Hp, Wp);
+    g.act = ACT_LEAKY;
+    g.slope = 0.01f;
+    g.out_T = W.cbu;
+    g.ld_T = 64;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  const void* cur = W.cbu;
+  int H = Hp, Wd = Wp;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    GemmArgs g = gemm_base(m, m->up[i], cur, 64, B, H, Wd);
+    g.out_T = W.hr[i];
+    g.ld_T = 64;
+    SSR_TRY(run_gemm(m, g, s));
+    cur = W.hr[i];
+    H *= m->up[i].ps_r;
+    Wd *= m->up[i].ps_r;
+  }
+  GemmArgs g = gemm_base(m, m->last_lin, cur, 64, B, H, Wd);
+  g.out3_f32 = y;
+  g.crop_h = h * c.scale;
+  g.crop_w = w * c.scale;
+  for (int i = 0; i < 3; ++i) g.out_shift[i] = kMean3[i];
+  g.out_scale = c.img_range;
+  g.u8_scale = 1.0f;
+  return run_gemm(m, g, s);
+}
+
+// dgrad of a linear layer: dX[M][K] = dY[M][N] W[N][K] -> the forward GEMM kernel on the transposed pack
+static GemmArgs dgrad_lin(const ssr_model* m, const LinT& l, const void* dY, int M) {
+  const Lin& L = *l.fwd;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = dY;
+  g.lda = L.NP;
+  g.B = 1;
+  g.H = 1;
+  g.W = M;
+  g.M = M;
+  g.taps = 1;
+  g.KP = L.NP;
+  g.Wt = m->train->arena2 + l.dg_off;
+  g.N = L.KP;  // every padded column is produced (pads are exact zeros): downstream kernels read whole rows
+  g.NP = L.KP;
+  g.bias = reinterpret_cast<const float*>(m->train->arena2 + m->train->zero_bias_off);
+  g.alpha = 1.0f;
+  g.eps = 1e-5f;
+  g.K_alg = l.N;
+  g.N_alg = l.K;
+  return g;
+}
+static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const void* X, int M, float* dwp, float* const* grads,
+                     cudaStream_t s) {
+  const Lin& L = *l.fwd;
+  if (grads[l.wi]) {
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dY = dY;
+    a.ldy = L.NP;
+    a.X = X;
+    a.ldx = L.KP;
+    a.B = 1;
+    a.H = 1;
+    a.W = M;
+    a.M = M;
+    a.taps = 1;
+    a.NoutP = L.NP;
+    a.CinP = L.KP;
+    a.dWp = dwp + l.dwp_off;
+    a.alpha = 1.0f;
+    a.N_alg = l.N;
+    a.K_alg = l.K;
+    SSR_TRY(launch_wgrad_tc(a, s));
+    SSR_TRY(launch_unpack_linear_grad(dwp + l.dwp_off, grads[l.wi], l.N, l.K, L.KP, l.map, s));
+  }
+  if (grads[l.bi]) SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, l.N, l.map, grads[l.bi], s));
+  return SSR_OK;
+}
+static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, const void* dy, int elem_dy, const float* Gin, float* Gout,
+                       void* Gb, int M, int C, int CP, float* const* grads, cudaStream_t s) {
+  LnBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x;
+  a.ldx = CP;
+  a.dy = dy;
+  a.ld_dy = CP;
+  a.elem_dy = elem_dy;
+  a.gamma = gamma_dev;
+  a.Gin = Gin;
+  a.Gout = Gout;
+  a.Gb = Gb;
+  a.ldg = CP;
+  a.M = M;
+  a.C = C;
+  a.CP = CP;
+  a.eps = 1e-5f;
+  if (grads[l.gi] && grads[l.bi]) {
+    a.dgamma = grads[l.gi];
+    a.dbeta = grads[l.bi];
+  }
+  return launch_ln_bwd(a, s);
+}
+
+static int train_backward_swinir(ssr_model* m, const float* dy, float* const* grads, int B, int h, int w, void* ws, size_t ws_bytes,
+                                 cudaStream_t s) {
+  ssr_train_state* t = m->train;
+  const ssr_model_config& c = m->cfg;
+  int Hp, Wp;
+  train_padded(m, h, w, &Hp, &Wp);
+  SwinTrainWs W;
+  const size_t need = plan_swin_train(m, ws, B, Hp, Wp, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "train workspace %zu B < required %zu B", ws_bytes, need);
+  const int C = m->C, CP = m->CP;
+  const int T = B * Hp * Wp;
+  SSR_CUDA(cudaMemsetAsync(W.dwp, 0, t->dwp_floats * 4, s));
+  int H = Hp * c.scale, Wd = Wp * c.scale;
+  // y = (conv_last(.) + mean) * img_range, cropped (swinir.py:366-372): dL/d(conv_last output) = dy * img_range inside the crop
+  SSR_TRY(launch_grad_nhwc64(dy, W.dy64, B, h * c.scale, w * c.scale, H, Wd, c.img_range, s));
+  const int nup = (int)m->up.size();
+  {
+    const ConvT& cv = t->convs[t->e_last];
+    SSR_TRY(wgrad_conv(m, cv, W.dy64, nup ? W.hr[nup - 1] : W.cbu, 64, B, H, Wd, 1.0f, W.dwp, grads, s));
+    GemmArgs g = dgrad_base(m, cv, W.dy64, B, H, Wd);
+    g.out_T = nup ? W.ghr[nup - 1] : W.dcbu;
+    g.ld_T = 64;
+    if (!nup) {
+      g.mask = W.cbu;
+      g.ld_mask = 64;
+      g.mask_slope = 0.01f;
+    }
+    SSR_TRY(launch_gemm_tc(g, 2, s));
+  }
+  for (int k = nup - 1; k >= 0; --k) {
+    const ConvT& cv = t->convs[t->e_up[k]];
+    const int r = m->up[k].ps_r;
+    H /= r;
+    Wd /= r;
+    SSR_TRY(launch_unshuffle(W.ghr[k], W.gU, B, H, Wd, 64, r, 64, s));
+    SSR_TRY(wgrad_conv(m, cv, W.gU, k ? W.hr[k - 1] : W.cbu, 64, B, H, Wd, 1.0f, W.dwp, grads, s));
+    GemmArgs g = dgrad_base(m, cv, W.gU, B, H, Wd);
+    g.out_T = k ? W.ghr[k - 1] : W.dcbu;
+    g.ld_T = 64;
+    if (k == 0) {  // LeakyReLU(0.01) of conv_before_upsample (swinir.py:321-324): gate by the sign of its output
+      g.mask = W.cbu;
+      g.ld_mask = 64;
+      g.mask_slope = 0.01f;
+    }
+    SSR_TRY(launch_gemm_tc(g, 2, s));
+  }
+  {  // conv_before_upsample.0
+    const ConvT& cv = t->convs[t->s_cbu];
+    SSR_TRY(wgrad_conv(m, cv, W.dcbu, W.tbf, CP, B, Hp, Wp, 1.0f, W.dwp, grads, s));
+    GemmArgs g = dgrad_base(m, cv, W.dcbu, B, Hp, Wp);
+    g.out_f32 = W.Gres;
+    g.ld_f32 = CP;
+    g.out_T = W.Gb;
+    g.ld_T = CP;
+    SSR_TRY(launch_gemm_tc(g, 2, s));
+  }
+  {  // conv_after_body(norm(features)) + x0 (swinir.py:362): Gres also flows to x0 through the long skip
+    const ConvT& cv = t->convs[t->s_cab];
+    SSR_TRY(wgrad_conv(m, cv, W.Gb, W.xnf, CP, B, Hp, Wp, 1.0f, W.dwp, grads, s));
+    GemmArgs g = dgrad_base(m, cv, W.Gb, B, Hp, Wp);
+    g.out_T = W.dXn;
+    g.ld_T = CP;
+    SSR_TRY(launch_gemm_tc(g, 2, s));
+  }
+  const int nL = (int)m->layers.size();
+  SSR_TRY(ln_backward(t->s_fin, m->dev<float>(m->final_norm.g_off), W.g[nL], W.dXn, 2, nullptr, W.G, W.Gb, T, C, CP, grads, s));
+  for (int li = nL - 1; li >= 0; --li) {
+    const Layer& L = m->layers[li];
+    const int depth = (int)L.blocks.size();
+    {  // RSTB: g' = g + conv(t_last) (swinir.py:245-246); G = dL/dg' keeps flowing through the skip
+      const ConvT& cv = t->convs[t->s_conv[li]];
+      SSR_TRY(wgrad_conv(m, cv, W.Gb, W.tb[li], CP, B, Hp, Wp, 1.0f, W.dwp, grads, s));
+      GemmArgs g = dgrad_base(m, cv, W.Gb, B, Hp, Wp);
+      g.out_f32 = W.Gt;
+      g.ld_f32 = CP;
+      g.out_T = W.Gtb;
+      g.ld_T = CP;
+      SSR_TRY(launch_gemm_tc(g, 2, s));
+    }
+    for (int bi = depth - 1; bi >= 0; --bi) {
+      const Block& blk = L.blocks[bi];
+      const BlockT& bt = t->s_blocks[li][bi];
+      const SwinBlockWs& bw = W.blk[li][bi];
+      // ---- MLP: t_out = t_mid + fc2(GELU(fc1(LN2(t_mid))))  (swinir.py:172, common.py:184-194) ----
+      SSR_TRY(wgrad_lin(m, bt.fc2, W.Gtb, bw.h, T, W.dwp, grads, s));
+      {
+        GemmArgs g = dgrad_lin(m, bt.fc2, W.Gtb, T);
+        g.mask = bw.u;  // GELU backward on the saved pre-activation
+        g.ld_mask = m->HP;
+        g.mask_mode = 1;
+        g.out_T = W.dH;
+        g.ld_T = m->HP;
+        SSR_TRY(launch_gemm_tc(g, 2, s));
+      }
+      SSR_TRY(wgrad_lin(m, bt.fc1, W.dH, bw.xn2, T, W.dwp, grads, s));
+      {
+        GemmArgs g = dgrad_lin(m, bt.fc1, W.dH, T);
+        g.out_T = W.dXn;
+        g.ld_T = CP;
+        SSR_TRY(launch_gemm_tc(g, 2, s));
+      }
+      SSR_TRY(ln_backward(bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, grads, s));
+      // ---- attention: t_mid = t_in + proj(W-MSA(LN1(t_in)))  (swinir.py:149-171) ----
+      SSR_TRY(wgrad_lin(m, bt.proj, W.Gtb, bw.o, T, W.dwp, grads, s));
+      {
+        GemmArgs g = dgrad_lin(m, bt.proj, W.Gtb, T);
+        g.out_T = W.dO;
+        g.ld_T = L.QP;
+        SSR_TRY(launch_gemm_tc(g, 2, s));
+      }
+      {
+        AttnBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.qkv = bw.qkv;
+        a.ld_qkv = 3 * L.QP;
+        a.QP = L.QP;
+        a.d_o = W.dO;
+        a.ld_do = L.QP;
+        a.dqkv = W.dQKV;
+        a.bias = m->dev<float>(blk.bias_off);
+        a.dB = W.dB;
+        a.dtable = grads[bt.table_i];
+        a.B = B;
+        a.H = Hp;
+        a.W = Wp;
+        a.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
+        a.heads = L.heads;
+        a.d = L.d;
+        a.DP = L.DP;
+        if (L.heads * L.DP < L.QP) SSR_CUDA(cudaMemsetAsync(W.dQKV, 0, (size_t)T * 3 * L.QP * 2, s));
+        SSR_TRY(launch_attn_bwd(a, s));
+      }
+      SSR_TRY(wgrad_lin(m, bt.qkv, W.dQKV, bw.xn1, T, W.dwp, grads, s));
+      {
+        GemmArgs g = dgrad_lin(m, bt.qkv, W.dQKV, T);
+        g.out_T = W.dXn;
+        g.ld_T = CP;
+        SSR_TRY(launch_gemm_tc(g, 2, s));
+      }
+      SSR_TRY(ln_backward(bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, grads, s));
+    }
+    SSR_TRY(launch_add_inplace(W.G, W.Gt, W.Gb, (size_t)T * CP, s));  // blocks' path joins the group skip
+  }
+  // g0 = patch_embed.norm(x0) (swinir.py:22-32, 343-344); x0 also receives the long skip Gres
+  SSR_TRY(ln_backward(t->s_pe, m->dev<float>(m->pe_norm.g_off), W.x0, W.G, 4, W.Gres, W.Gt, W.Gtb, T, C, CP, grads, s));
+  if (grads[t->head_w]) {
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dY = W.Gtb;
+    a.ldy = CP;
+    a.X = W.xin64;
+    a.ldx = 64;
+    a.B = B;
+    a.H = Hp;
+    a.W = Wp;
+    a.M = T;
+    a.taps = 9;
+    a.NoutP = CP;
+    a.CinP = 64;
+    a.dWp = W.dwp + t->head_dwp;
+    a.alpha = 1.0f;
+    a.N_alg = C;
+    a.K_alg = 3;
+    SSR_TRY(launch_wgrad_tc(a, s));
+    SSR_TRY(launch_unpack_wgrad(W.dwp + t->head_dwp, grads[t->head_w], C, 3, 64, 9, 0, s));
+  }
+  if (grads[t->head_b]) SSR_TRY(launch_colsum(W.Gtb, 2, CP, T, C, 0, 1.0f, grads[t->head_b], s));
+  return SSR_OK;
+}
+
 }  // namespace ssr
 
 // =============================================================================================
@@ -421,7 +1080,8 @@ extern "C" {
 int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const int64_t* numels) {
   SSR_TRY(check_ready(m));
   SSR_CHECK(m->cfg.precision == SSR_PREC_BF16, SSR_E_INVALID, "the training path is built for the bf16 tensor-core precision only");
-  SSR_CHECK(m->cfg.arch == SSR_ARCH_EDSR, SSR_E_INVALID, "the training path is built for EDSR so far");
+  SSR_CHECK(m->cfg.arch == SSR_ARCH_EDSR || m->cfg.arch == SSR_ARCH_SWINIR, SSR_E_INVALID,
+            "the training path is built for EDSR and SwinIR (HAT / RCAN are inference-only)");
   train_state_destroy(m);
   m->train = new ssr_train_state();
   for (int i = 0; i < n; ++i) {
@@ -429,13 +1089,19 @@ int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const 
     m->train->numels.push_back(numels[i]);
     m->train->index[names[i]] = i;
   }
-  int r = bind_edsr(m);
+  int r = m->cfg.arch == SSR_ARCH_EDSR ? bind_edsr(m) : bind_swinir(m);
   if (r != SSR_OK) train_state_destroy(m);
   return r;
 }
 
 size_t ssr_model_train_workspace_bytes(const ssr_model_t* m, int B, int H, int W) {
   if (!m || !m->train) return 0;
+  if (m->cfg.arch == SSR_ARCH_SWINIR) {
+    int Hp, Wp;
+    train_padded(m, H, W, &Hp, &Wp);
+    SwinTrainWs w;
+    return plan_swin_train(m, nullptr, B, Hp, Wp, &w);
+  }
   EdsrTrainWs w;
   return plan_edsr_train(m, nullptr, B, H, W, &w);
 }
@@ -445,6 +1111,8 @@ int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const fl
   SSR_TRY(check_ready(m));
   SSR_CHECK(m->train != nullptr, SSR_E_STATE, "ssr_model_train_bind has not been called");
   SSR_CHECK(params && x && y && B > 0 && H > 0 && W > 0, SSR_E_INVALID, "train_forward: bad argument");
+  if (m->cfg.arch == SSR_ARCH_SWINIR)
+    return train_forward_swinir(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_forward_edsr(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -453,6 +1121,8 @@ int ssr_model_train_backward(ssr_model_t* m, const float* dy, float* const* grad
   SSR_TRY(check_ready(m));
   SSR_CHECK(m->train != nullptr, SSR_E_STATE, "ssr_model_train_bind has not been called");
   SSR_CHECK(dy && grads && B > 0 && H > 0 && W > 0, SSR_E_INVALID, "train_backward: bad argument");
+  if (m->cfg.arch == SSR_ARCH_SWINIR)
+    return train_backward_swinir(m, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_backward_edsr(m, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

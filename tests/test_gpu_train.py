@@ -123,3 +123,55 @@ def test_edsr_train_step_updates_weights():
         opt.zero_grad(set_to_none=True)
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+def _swin_case(cfg, B, H, W, wseed, xseed):
+    from studiosr_b200.models import SwinIR
+
+    P = synth.swinir_weights(cfg, wseed)
+    x = synth.image_batch((B, 3, H, W), xseed)
+    tgt = synth.image_batch((B, 3, H * cfg["scale"], W * cfg["scale"]), xseed + 1)
+
+    def oracle_grads(autocast):
+        Q = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
+        if autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                loss = F.l1_loss(O.swinir_forward(Q, x, cfg, training=True), tgt)
+        else:
+            loss = F.l1_loss(O.swinir_forward(Q, x, cfg, training=True), tgt)
+        loss.backward()
+        return Q, loss.item()
+
+    Pr, loss_ref = oracle_grads(False)
+    Pa, _ = oracle_grads(True)
+    kw = {k: cfg[k] for k in ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size", "mlp_ratio",
+                              "upsampler")}
+    model = SwinIR(drop_path_rate=0.0, **kw)
+    model.load_state_dict(P, strict=True)
+    model = model.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = F.l1_loss(model(x.cuda()), tgt.cuda())
+    loss.backward()
+    return model, Pr, Pa, loss.item(), loss_ref
+
+
+@pytest.mark.parametrize("name,over,B,H,W", [
+    ("tiny", dict(synth.SWINIR_TINY), 2, 16, 24),
+    ("tiny-reflect-pad", dict(synth.SWINIR_TINY), 1, 20, 28),                       # padded to 24x32 (common.py:277-282)
+    ("c180", dict(embed_dim=180, depths=[2, 2], num_heads=[6, 6], scale=4), 1, 16, 16),  # the 180 / 6-head class (cfg4 widths)
+    ("x2", dict(synth.SWINIR_TINY, scale=2), 1, 16, 16),
+])
+def test_swinir_backward(name, over, B, H, W):
+    cfg = synth.swinir_config(**over)
+    model, Pr, Pa, loss, loss_ref = _swin_case(cfg, B, H, W, 11, 101)
+    assert abs(loss - loss_ref) < 5e-3 * max(1.0, abs(loss_ref)), (loss, loss_ref)
+    report = []
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        e = _rel(p.grad.cpu(), Pr[k].grad)
+        e_ref = _rel(Pa[k].grad.float(), Pr[k].grad)
+        report.append((e / max(2e-2, 2.0 * e_ref), e, e_ref, k))
+    worst = max(report)
+    print(f"SwinIR {name}: worst gradient rel err {worst[1]:.3e} (reference under bf16 autocast: {worst[2]:.3e}) at {worst[3]}")
+    bad = sorted(r for r in report if r[0] > 1.0)
+    assert not bad, f"SwinIR {name}: " + "; ".join(f"{k}: {e:.3e} (ref-bf16 {er:.3e})" for _, e, er, k in bad[-8:])
