@@ -58,22 +58,85 @@ int launch_unpack_wgrad(const float* dWp, float* grad, int Cout, int Cin, int KP
   return SSR_OK;
 }
 
-// bias gradient: out[sn(n)] = alpha * sum_m dY[m][n]; out must be zeroed (atomics over row strips)
-__global__ void colsum_kernel(const void* __restrict__ dY, int elem, int ld, int M, int N, int Cout, int ps_r, float alpha,
-                              float* out, int rows_per_block) {
+// Column sums run in two stages -- per-strip partial sums, then one thread per column adds the strips -- so that no
+// address sees hundreds of same-address atomics (measured: the single-stage atomic version cost 5x the data movement) and
+// the result is deterministic.  `partial` is scratch of at least kColsumStrips * N floats.
+constexpr int kColsumStrips = 592;
+// stage 1: bf16 [M][ld] -> partial[strip][NP]; a thread owns 8 consecutive columns (one 16-byte load per row), RY row
+// lanes of a CTA walk the strip's rows in parallel and meet in shared memory
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ dY, int ld, int M, int NP, float* partial,
+                                                             int rows_per_block, int VX, int RY) {
+  extern __shared__ float cs_red[];  // [RY][NP]
+  const int V = NP / 8;
+  const int vx = threadIdx.x % VX, ry = threadIdx.x / VX;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float acc = 0.0f;
-    for (int r = r0; r < r1; ++r) acc += load_elem(dY, (size_t)r * ld + n, elem);
-    atomicAdd(out + ps_src_row(n, Cout, ps_r), acc * alpha);
+  if (ry < RY) {
+    for (int v = vx; v < V; v += VX) {
+      float acc[8], acc2[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = acc2[e] = 0.0f;
+      const __nv_bfloat16* base = dY + v * 8;
+      int r = r0 + ry;
+      for (; r + RY < r1; r += 2 * RY) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * ld));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(r + RY) * ld));
+        const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += __uint_as_float(wa[e] << 16);
+          acc[2 * e + 1] += __uint_as_float(wa[e] & 0xffff0000u);
+          acc2[2 * e] += __uint_as_float(wb[e] << 16);
+          acc2[2 * e + 1] += __uint_as_float(wb[e] & 0xffff0000u);
+        }
+      }
+      if (r < r1) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * ld));
+        const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += __uint_as_float(wa[e] << 16);
+          acc[2 * e + 1] += __uint_as_float(wa[e] & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cs_red[(size_t)ry * NP + v * 8 + e] = acc[e] + acc2[e];
+    }
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < NP; n += blockDim.x) {
+    float t = 0.0f;
+    for (int y = 0; y < RY; ++y) t += cs_red[(size_t)y * NP + n];
+    partial[(size_t)blockIdx.x * NP + n] = t;
   }
 }
-int launch_colsum(const void* dY, int elem, int ld, int M, int N, int ps_r, float alpha, float* out, cudaStream_t s) {
-  const int blocks = min((M + 63) / 64, 4 * 148);
+// bias gradient of a conv: out[sn(n)] = alpha * sum_m dY[m][n]
+__global__ void colsum_final_conv_kernel(const float* __restrict__ partial, int strips, int NP, int Cout, int ps_r, float alpha,
+                                         float* out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Cout) return;
+  float acc = 0.0f;
+  for (int b = 0; b < strips; ++b) acc += partial[(size_t)b * NP + n];
+  out[ps_src_row(n, Cout, ps_r)] = acc * alpha;
+}
+static int colsum_stage1(const void* dY, int elem, int ld, int M, int NP, float* partial, int* strips, cudaStream_t s) {
+  SSR_CHECK(elem == 2 && NP % 8 == 0 && ld % 8 == 0 && NP <= 2304, SSR_E_INVALID, "colsum: bf16 rows with NP %% 8 == 0 (NP=%d ld=%d)", NP, ld);
+  const int blocks = min((M + 63) / 64, kColsumStrips);
   const int rpb = (M + blocks - 1) / blocks;
-  SSR_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 4, s));
-  colsum_kernel<<<(M + rpb - 1) / rpb, 256, 0, s>>>(dY, elem, ld, M, N, N, ps_r, alpha, out, rpb);
+  *strips = (M + rpb - 1) / rpb;
+  const int V = NP / 8, VX = V < 256 ? V : 256, RY = 256 / VX;
+  ProfScope prof("bias_grad_colsum", 0.0, (double)M * NP * elem, s);
+  colsum_partial_kernel<<<*strips, 256, (size_t)RY * NP * 4, s>>>((const __nv_bfloat16*)dY, ld, M, NP, partial, rpb, VX, RY);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+// dY: bf16 [M][ld] of packed width NP (multiple of 8); out[sn(n)] for n < Cout
+int launch_colsum(const void* dY, int elem, int ld, int M, int NP, int Cout, int ps_r, float alpha, float* out, float* partial,
+                  cudaStream_t s) {
+  int strips;
+  SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, partial, &strips, s));
+  colsum_final_conv_kernel<<<(Cout + 127) / 128, 128, 0, s>>>(partial, strips, NP, Cout, ps_r, alpha, out);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;
@@ -201,25 +264,22 @@ int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int K
   return SSR_OK;
 }
 
-// bias gradient of a linear layer: out[n] = scale(n) * sum_m dY[m][np(n)]   (out zeroed here, atomics over row strips)
-__global__ void colsum_map_kernel(const void* __restrict__ dY, int elem, int ld, int M, int N, const LinMap map, float* out,
-                                  int rows_per_block) {
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(M, r0 + rows_per_block);
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    int np, kp;
-    float sc;
-    lin_map(map, n, 0, &np, &kp, &sc);
-    float acc = 0.0f;
-    for (int r = r0; r < r1; ++r) acc += load_elem(dY, (size_t)r * ld + np, elem);
-    atomicAdd(out + n, acc * sc);
-  }
+// bias gradient of a linear layer: out[n] = scale(n) * sum_m dY[m][np(n)]  (NP = packed width of dY)
+__global__ void colsum_final_map_kernel(const float* __restrict__ partial, int strips, int NP, int N, const LinMap map, float* out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int np, kp;
+  float sc;
+  lin_map(map, n, 0, &np, &kp, &sc);
+  float acc = 0.0f;
+  for (int b = 0; b < strips; ++b) acc += partial[(size_t)b * NP + np];
+  out[n] = acc * sc;
 }
-int launch_colsum_map(const void* dY, int elem, int ld, int M, int N, const LinMap& map, float* out, cudaStream_t s) {
-  const int blocks = min((M + 63) / 64, 4 * 148);
-  const int rpb = (M + blocks - 1) / blocks;
-  SSR_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 4, s));
-  colsum_map_kernel<<<(M + rpb - 1) / rpb, 256, 0, s>>>(dY, elem, ld, M, N, map, out, rpb);
+int launch_colsum_map(const void* dY, int elem, int ld, int M, int NP, int N, const LinMap& map, float* out, float* partial,
+                      cudaStream_t s) {
+  int strips;
+  SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, partial, &strips, s));
+  colsum_final_map_kernel<<<(N + 127) / 128, 128, 0, s>>>(partial, strips, NP, N, map, out);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;
@@ -242,39 +302,70 @@ int launch_transpose_table(const float* table, float* out, int nb, int heads, cu
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward, one warp per row (rows strided over all warps so dgamma / dbeta partials live in registers):
 //   xhat = (x - mean) rstd;  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float red[2][8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = blockIdx.x * 8 + wib, nwarps = gridDim.x * 8;
+  // a lane owns the float4 slots `lane` and `lane + 32` of a row: columns col(j) = 4 * (lane + 32 * (j / 4)) + j % 4
+  const int Q = a.CP / 4;
+  const bool has1 = lane + 32 < Q;
   float dg[8], db[8], gam[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     dg[j] = db[j] = 0.0f;
-    const int n = lane + 32 * j;
+    const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
     gam[j] = n < a.C ? __ldg(a.gamma + n) : 0.0f;
   }
   const float invC = 1.0f / (float)a.C;
   for (int row = warp; row < a.M; row += nwarps) {
-    const float* x = a.x + (size_t)row * a.ldx;
-    float v[8], dy[8];
+    float v[8], dy[8], gi[8];
+    {
+      const float4* x4 = reinterpret_cast<const float4*>(a.x + (size_t)row * a.ldx);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 x0 = lane < Q ? x4[lane] : z, x1 = has1 ? x4[lane + 32] : z;
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      if (a.elem_dy == 2) {
+        const uint2* d2 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.dy) + (size_t)row * a.ld_dy);
+        const uint2 zz = make_uint2(0, 0);
+        const uint2 d0 = lane < Q ? d2[lane] : zz, d1 = has1 ? d2[lane + 32] : zz;
+        dy[0] = __uint_as_float(d0.x << 16); dy[1] = __uint_as_float(d0.x & 0xffff0000u);
+        dy[2] = __uint_as_float(d0.y << 16); dy[3] = __uint_as_float(d0.y & 0xffff0000u);
+        dy[4] = __uint_as_float(d1.x << 16); dy[5] = __uint_as_float(d1.x & 0xffff0000u);
+        dy[6] = __uint_as_float(d1.y << 16); dy[7] = __uint_as_float(d1.y & 0xffff0000u);
+      } else {
+        const float4* d4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.dy) + (size_t)row * a.ld_dy);
+        const float4 d0 = lane < Q ? d4[lane] : z, d1 = has1 ? d4[lane + 32] : z;
+        dy[0] = d0.x; dy[1] = d0.y; dy[2] = d0.z; dy[3] = d0.w; dy[4] = d1.x; dy[5] = d1.y; dy[6] = d1.z; dy[7] = d1.w;
+      }
+      if (a.Gin) {
+        const float4* g4 = reinterpret_cast<const float4*>(a.Gin + (size_t)row * a.ldg);
+        const float4 g0 = lane < Q ? g4[lane] : z, g1 = has1 ? g4[lane + 32] : z;
+        gi[0] = g0.x; gi[1] = g0.y; gi[2] = g0.z; gi[3] = g0.w; gi[4] = g1.x; gi[5] = g1.y; gi[6] = g1.z; gi[7] = g1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gi[j] = 0.0f;
+      }
+    }
     float s = 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int n = lane + 32 * j;
-      v[j] = n < a.C ? x[n] : 0.0f;
-      dy[j] = n < a.C ? load_elem(a.dy, (size_t)row * a.ld_dy + n, a.elem_dy) : 0.0f;
+      const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
+      if (n >= a.C) v[j] = dy[j] = gi[j] = 0.0f;
       s += v[j];
     }
     const float mean = warp_sum(s) * invC;
     float q = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (lane + 32 * j < a.C) q += (v[j] - mean) * (v[j] - mean);
+    for (int j = 0; j < 8; ++j) {
+      const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
+      if (n < a.C) q += (v[j] - mean) * (v[j] - mean);
+    }
     const float rstd = rsqrtf(warp_sum(q) * invC + a.eps);
     float sg = 0.0f, sgx = 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[j] = (lane + 32 * j < a.C) ? (v[j] - mean) * rstd : 0.0f;  // xhat
+      const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
+      v[j] = n < a.C ? (v[j] - mean) * rstd : 0.0f;  // xhat
       dg[j] = fmaf(dy[j], v[j], dg[j]);
       db[j] += dy[j];
       dy[j] *= gam[j];
@@ -283,22 +374,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     }
     sg = warp_sum(sg) * invC;
     sgx = warp_sum(sgx) * invC;
+    float dx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int n = lane + 32 * j;
-      if (n >= a.CP) continue;
-      float dx = n < a.C ? rstd * (dy[j] - sg - v[j] * sgx) : 0.0f;
-      const size_t o = (size_t)row * a.ldg + n;
-      if (a.Gin && n < a.C) dx += a.Gin[o];
-      a.Gout[o] = dx;
-      if (a.Gb) reinterpret_cast<__nv_bfloat16*>(a.Gb)[o] = __float2bfloat16_rn(dx);
+      const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
+      dx[j] = n < a.C ? rstd * (dy[j] - sg - v[j] * sgx) + gi[j] : 0.0f;
+    }
+    float4* o4 = reinterpret_cast<float4*>(a.Gout + (size_t)row * a.ldg);
+    if (lane < Q) o4[lane] = make_float4(dx[0], dx[1], dx[2], dx[3]);
+    if (has1) o4[lane + 32] = make_float4(dx[4], dx[5], dx[6], dx[7]);
+    if (a.Gb) {
+      uint2* b2 = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.Gb) + (size_t)row * a.ldg);
+      if (lane < Q) b2[lane] = make_uint2(pack_bf16x2(dx[0], dx[1]), pack_bf16x2(dx[2], dx[3]));
+      if (has1) b2[lane + 32] = make_uint2(pack_bf16x2(dx[4], dx[5]), pack_bf16x2(dx[6], dx[7]));
     }
   }
   if (!a.dgamma) return;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[0][wib][lane + 32 * j] = dg[j];
-    red[1][wib][lane + 32 * j] = db[j];
+    const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
+    red[0][wib][n] = dg[j];
+    red[1][wib][n] = db[j];
   }
   __syncthreads();
   for (int n = threadIdx.x; n < a.C; n += 256) {
@@ -308,20 +404,32 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
       g += red[0][w][n];
       b += red[1][w][n];
     }
-    atomicAdd(a.dgamma + n, g);
-    atomicAdd(a.dbeta + n, b);
+    a.partial[((size_t)blockIdx.x * 2) * a.C + n] = g;
+    a.partial[((size_t)blockIdx.x * 2 + 1) * a.C + n] = b;
   }
 }
+__global__ void ln_bwd_final_kernel(const float* __restrict__ partial, int blocks, int C, float* dgamma, float* dbeta) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= 2 * C) return;
+  const int which = n / C, c = n - which * C;
+  float acc = 0.0f;
+  for (int b = 0; b < blocks; ++b) acc += partial[((size_t)b * 2 + which) * C + c];
+  (which ? dbeta : dgamma)[c] = acc;
+}
 int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s) {
-  SSR_CHECK(a.C <= 256 && a.CP <= 256, SSR_E_INVALID, "ln_bwd: C=%d", a.C);
-  if (a.dgamma) {
-    SSR_CUDA(cudaMemsetAsync(a.dgamma, 0, (size_t)a.C * 4, s));
-    SSR_CUDA(cudaMemsetAsync(a.dbeta, 0, (size_t)a.C * 4, s));
-  }
-  const int blocks = min((a.M + 7) / 8, 4 * 148);
+  SSR_CHECK(a.C <= 256 && a.CP <= 256 && a.CP % 4 == 0 && a.ldx % 4 == 0 && a.ldg % 4 == 0 && a.ld_dy % 4 == 0, SSR_E_INVALID,
+            "ln_bwd: C=%d CP=%d", a.C, a.CP);
+  SSR_CHECK(!a.dgamma || a.partial, SSR_E_INVALID, "ln_bwd: partial scratch missing");
+  const int blocks = min((a.M + 7) / 8, kColsumStrips);
+  ProfScope prof("ln_bwd", 0.0, (double)a.M * a.C * (4 + a.elem_dy + (a.Gin ? 4 : 0) + 4 + (a.Gb ? 2 : 0)), s);
   ln_bwd_kernel<<<blocks, 256, 0, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
+  if (a.dgamma) {
+    ln_bwd_final_kernel<<<(2 * a.C + 127) / 128, 128, 0, s>>>(a.partial, blocks, a.C, a.dgamma, a.dbeta);
+    count_launch();
+    SSR_CUDA(cudaGetLastError());
+  }
   return SSR_OK;
 }
 

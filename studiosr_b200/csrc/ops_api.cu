@@ -172,7 +172,8 @@ int ssr_op_conv3x3_wgrad(const float* dy, const float* x, float* dW, float* db, 
   void* xp = c.take(M * KP * 2);
   void* yp = c.take(M * NP * 2);
   float* dwp = (float*)c.take((size_t)NP * taps * KP * 4);
-  SSR_CHECK(dwp, SSR_E_WORKSPACE, "ssr_op_conv3x3_wgrad: workspace too small (%zu B)", workspace_bytes);
+  float* partial = (float*)c.take(kTrainPartialFloats * 4);
+  SSR_CHECK(dwp && partial, SSR_E_WORKSPACE, "ssr_op_conv3x3_wgrad: workspace too small (%zu B)", workspace_bytes);
   SSR_TRY(launch_nchw_to_nhwc(x, xp, B, Cin, H, Wd, KP, 2, 0, s));
   SSR_TRY(launch_nchw_to_nhwc(dy, yp, B, Cout, H, Wd, NP, 2, 0, s));
   SSR_CUDA(cudaMemsetAsync(dwp, 0, (size_t)NP * taps * KP * 4, s));
@@ -182,7 +183,7 @@ int ssr_op_conv3x3_wgrad(const float* dy, const float* x, float* dW, float* db, 
   a.dWp = dwp; a.alpha = alpha; a.N_alg = Cout; a.K_alg = Cin;
   SSR_TRY(launch_wgrad_tc(a, s));
   SSR_TRY(launch_unpack_wgrad(dwp, dW, Cout, Cin, KP, taps, 0, s));
-  if (db) SSR_TRY(launch_colsum(yp, 2, NP, (int)M, Cout, 0, alpha, db, s));
+  if (db) SSR_TRY(launch_colsum(yp, 2, NP, (int)M, NP, Cout, 0, alpha, db, partial, s));
   return SSR_OK;
 }
 

@@ -285,13 +285,16 @@ struct LnBwdArgs {
   int ldg;
   int M, C, CP;
   float eps;
-  float *dgamma, *dbeta;  // [C], accumulated with atomics (zero them first), or null
+  float *dgamma, *dbeta;  // [C], overwritten, or null
+  float* partial;         // scratch, >= kTrainPartialFloats floats (per-CTA partial sums)
 };
 int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s);
 int launch_pack_linear_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int N, int K, int NP, int KP,
                            const LinMap& map, cudaStream_t s);
 int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int KP, const LinMap& map, cudaStream_t s);
-int launch_colsum_map(const void* dY, int elem, int ld, int M, int N, const LinMap& map, float* out, cudaStream_t s);
+int launch_colsum_map(const void* dY, int elem, int ld, int M, int NP, int N, const LinMap& map, float* out, float* partial,
+                      cudaStream_t s);
+constexpr size_t kTrainPartialFloats = (size_t)592 * 2304;  // column-sum strips x widest packed row
 int launch_transpose_table(const float* table, float* out, int nb, int heads, cudaStream_t s);
 int launch_input_nhwc64(const float* x, void* out, int B, int h, int w, int Hp, int Wp, float scale, const float* shift3,
                         cudaStream_t s);
@@ -302,7 +305,8 @@ int launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s);
 int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int Cout, int Cin, int NP, int KP,
                          int taps, int ps_r, cudaStream_t s);
 int launch_unpack_wgrad(const float* dWp, float* grad, int Cout, int Cin, int KP, int taps, int ps_r, cudaStream_t s);
-int launch_colsum(const void* dY, int elem, int ld, int M, int N, int ps_r, float alpha, float* out, cudaStream_t s);
+int launch_colsum(const void* dY, int elem, int ld, int M, int NP, int Cout, int ps_r, float alpha, float* out, float* partial,
+                  cudaStream_t s);
 int launch_unshuffle(const void* in, void* out, int B, int H, int W, int C, int r, int ld_in, cudaStream_t s);
 int launch_nchw3_to_nhwc64(const float* in, void* out, int B, int H, int W, float scale, const float* shift3, cudaStream_t s);
 int launch_add_inplace(float* a, const float* b, void* out_bf, size_t n, cudaStream_t s);

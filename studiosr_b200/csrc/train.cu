@@ -152,6 +152,7 @@ struct EdsrTrainWs {
   float *G, *Gt;
   void *Gb, *Dh;
   float* dwp;
+  float* partial;
 };
 
 static size_t plan_edsr_train(const ssr_model* m, void* base, int B, int H, int W, EdsrTrainWs* w) {
@@ -182,6 +183,7 @@ static size_t plan_edsr_train(const ssr_model* m, void* base, int B, int H, int 
   w->Gb = c.take(T * FP * 2);
   w->Dh = c.take(T * FP * 2);
   w->dwp = (float*)c.take(m->train->dwp_floats * 4);
+  w->partial = (float*)c.take(kTrainPartialFloats * 4);
   return c.off + 1024;
 }
 
@@ -301,7 +303,7 @@ static GemmArgs dgrad_base(const ssr_model* m, const ConvT& c, const void* dY, i
 }
 
 static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const void* X, int ldx, int B, int H, int W, float alpha,
-                      float* dwp, float* const* grads, cudaStream_t s) {
+                      float* dwp, float* partial, float* const* grads, cudaStream_t s) {
   const Lin& L = *c.fwd;
   if (grads[c.wi]) {
     WgradArgs a;
@@ -324,7 +326,7 @@ static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const 
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_wgrad(dwp + c.dwp_off, grads[c.wi], c.Cout, c.Cin, L.KP, 9, L.ps_r, s));
   }
-  if (grads[c.bi]) SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, c.Cout, L.ps_r, alpha, grads[c.bi], s));
+  if (grads[c.bi]) SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s));
   return SSR_OK;
 }
 
@@ -345,7 +347,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
   {  // tail.1 (edsr.py:37,46)
     const ConvT& cv = t->convs[t->e_last];
     const void* X = nup ? W.hr[nup - 1] : W.bt;
-    SSR_TRY(wgrad_conv(m, cv, W.dy64, X, FP, B, H, Wd, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cv, W.dy64, X, FP, B, H, Wd, 1.0f, W.dwp, W.partial, grads, s));
     GemmArgs g = dgrad_base(m, cv, W.dy64, B, H, Wd);
     if (nup) {
       g.out_T = W.ghr[nup - 1];
@@ -365,7 +367,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     Wd /= r;
     SSR_TRY(launch_unshuffle(W.ghr[k], W.gU, B, H, Wd, m->F, r, FP, s));
     const void* X = k ? W.hr[k - 1] : W.bt;
-    SSR_TRY(wgrad_conv(m, cv, W.gU, X, FP, B, H, Wd, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cv, W.gU, X, FP, B, H, Wd, 1.0f, W.dwp, W.partial, grads, s));
     GemmArgs g = dgrad_base(m, cv, W.gU, B, H, Wd);
     if (k) {
       g.out_T = W.ghr[k - 1];
@@ -380,7 +382,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
   }
   {  // res = body(x) + x (edsr.py:43-44): Gt = dL/d(res) feeds the body's last conv and, through the skip, the head output
     const ConvT& cv = t->convs[t->e_body_tail];
-    SSR_TRY(wgrad_conv(m, cv, W.Gb, W.rb[nb], FP, B, h, w, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cv, W.Gb, W.rb[nb], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
     GemmArgs g = dgrad_base(m, cv, W.Gb, B, h, w);
     g.out_f32 = W.G;
     g.ld_f32 = FP;
@@ -393,7 +395,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
   for (int i = nb - 1; i >= 0; --i) {  // ResBlock: r' = r + res_scale * conv_b(relu(conv_a(r)))  (common.py:150-153)
     const ConvT& ca = t->convs[t->e_res_a[i]];
     const ConvT& cb = t->convs[t->e_res_b[i]];
-    SSR_TRY(wgrad_conv(m, cb, Gb, W.tmp[i], FP, B, h, w, c.res_scale, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cb, Gb, W.tmp[i], FP, B, h, w, c.res_scale, W.dwp, W.partial, grads, s));
     GemmArgs gb = dgrad_base(m, cb, Gb, B, h, w);
     gb.alpha = c.res_scale;
     gb.mask = W.tmp[i];  // ReLU backward: gate by the saved ReLU output
@@ -402,7 +404,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     gb.out_T = Dh;
     gb.ld_T = FP;
     SSR_TRY(launch_gemm_tc(gb, 2, s));
-    SSR_TRY(wgrad_conv(m, ca, Dh, W.rb[i], FP, B, h, w, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, ca, Dh, W.rb[i], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
     if (i == 0) SSR_TRY(launch_add_inplace(W.G, W.Gt, nullptr, T * FP, s));  // long skip joins at the head output
     GemmArgs ga = dgrad_base(m, ca, Dh, B, h, w);
     ga.res = W.G;
@@ -436,7 +438,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_wgrad(W.dwp + t->head_dwp, grads[t->head_w], m->F, 3, 64, 9, 0, s));
   }
-  if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, m->F, 0, 1.0f, grads[t->head_b], s));
+  if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, FP, m->F, 0, 1.0f, grads[t->head_b], W.partial, s));
   return SSR_OK;
 }
 
@@ -548,6 +550,7 @@ struct SwinTrainWs {
   float *G, *Gt, *Gres, *dB;
   void *Gb, *Gtb, *dH, *dXn, *dO, *dQKV;
   float* dwp;
+  float* partial;
 };
 
 static size_t plan_swin_train(const ssr_model* m, void* base, int B, int Hp, int Wp, SwinTrainWs* w) {
@@ -607,6 +610,7 @@ static size_t plan_swin_train(const ssr_model* m, void* base, int B, int Hp, int
   w->dQKV = c.take(T * 3 * QPmax * 2);
   w->dB = (float*)c.take((size_t)heads_max * 64 * 64 * 4);
   w->dwp = (float*)c.take(m->train->dwp_floats * 4);
+  w->partial = (float*)c.take(kTrainPartialFloats * 4);
   return c.off + 1024;
 }
 
@@ -850,8 +854,8 @@ static GemmArgs dgrad_lin(const ssr_model* m, const LinT& l, const void* dY, int
   g.N_alg = l.K;
   return g;
 }
-static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const void* X, int M, float* dwp, float* const* grads,
-                     cudaStream_t s) {
+static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const void* X, int M, float* dwp, float* partial,
+                     float* const* grads, cudaStream_t s) {
   const Lin& L = *l.fwd;
   if (grads[l.wi]) {
     WgradArgs a;
@@ -874,11 +878,11 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_linear_grad(dwp + l.dwp_off, grads[l.wi], l.N, l.K, L.KP, l.map, s));
   }
-  if (grads[l.bi]) SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, l.N, l.map, grads[l.bi], s));
+  if (grads[l.bi]) SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, L.NP, l.N, l.map, grads[l.bi], partial, s));
   return SSR_OK;
 }
 static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, const void* dy, int elem_dy, const float* Gin, float* Gout,
-                       void* Gb, int M, int C, int CP, float* const* grads, cudaStream_t s) {
+                       void* Gb, int M, int C, int CP, float* partial, float* const* grads, cudaStream_t s) {
   LnBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x;
@@ -895,6 +899,7 @@ static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, con
   a.C = C;
   a.CP = CP;
   a.eps = 1e-5f;
+  a.partial = partial;
   if (grads[l.gi] && grads[l.bi]) {
     a.dgamma = grads[l.gi];
     a.dbeta = grads[l.bi];
@@ -920,7 +925,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
   const int nup = (int)m->up.size();
   {
     const ConvT& cv = t->convs[t->e_last];
-    SSR_TRY(wgrad_conv(m, cv, W.dy64, nup ? W.hr[nup - 1] : W.cbu, 64, B, H, Wd, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cv, W.dy64, nup ? W.hr[nup - 1] : W.cbu, 64, B, H, Wd, 1.0f, W.dwp, W.partial, grads, s));
     GemmArgs g = dgrad_base(m, cv, W.dy64, B, H, Wd);
     g.out_T = nup ? W.ghr[nup - 1] : W.dcbu;
     g.ld_T = 64;
@@ -937,7 +942,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
     H /= r;
     Wd /= r;
     SSR_TRY(launch_unshuffle(W.ghr[k], W.gU, B, H, Wd, 64, r, 64, s));
-    SSR_TRY(wgrad_conv(m, cv, W.gU, k ? W.hr[k - 1] : W.cbu, 64, B, H, Wd, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cv, W.gU, k ? W.hr[k - 1] : W.cbu, 64, B, H, Wd, 1.0f, W.dwp, W.partial, grads, s));
     GemmArgs g = dgrad_base(m, cv, W.gU, B, H, Wd);
     g.out_T = k ? W.ghr[k - 1] : W.dcbu;
     g.ld_T = 64;
@@ -950,7 +955,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
   }
   {  // conv_before_upsample.0
     const ConvT& cv = t->convs[t->s_cbu];
-    SSR_TRY(wgrad_conv(m, cv, W.dcbu, W.tbf, CP, B, Hp, Wp, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cv, W.dcbu, W.tbf, CP, B, Hp, Wp, 1.0f, W.dwp, W.partial, grads, s));
     GemmArgs g = dgrad_base(m, cv, W.dcbu, B, Hp, Wp);
     g.out_f32 = W.Gres;
     g.ld_f32 = CP;
@@ -960,20 +965,20 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
   }
   {  // conv_after_body(norm(features)) + x0 (swinir.py:362): Gres also flows to x0 through the long skip
     const ConvT& cv = t->convs[t->s_cab];
-    SSR_TRY(wgrad_conv(m, cv, W.Gb, W.xnf, CP, B, Hp, Wp, 1.0f, W.dwp, grads, s));
+    SSR_TRY(wgrad_conv(m, cv, W.Gb, W.xnf, CP, B, Hp, Wp, 1.0f, W.dwp, W.partial, grads, s));
     GemmArgs g = dgrad_base(m, cv, W.Gb, B, Hp, Wp);
     g.out_T = W.dXn;
     g.ld_T = CP;
     SSR_TRY(launch_gemm_tc(g, 2, s));
   }
   const int nL = (int)m->layers.size();
-  SSR_TRY(ln_backward(t->s_fin, m->dev<float>(m->final_norm.g_off), W.g[nL], W.dXn, 2, nullptr, W.G, W.Gb, T, C, CP, grads, s));
+  SSR_TRY(ln_backward(t->s_fin, m->dev<float>(m->final_norm.g_off), W.g[nL], W.dXn, 2, nullptr, W.G, W.Gb, T, C, CP, W.partial, grads, s));
   for (int li = nL - 1; li >= 0; --li) {
     const Layer& L = m->layers[li];
     const int depth = (int)L.blocks.size();
     {  // RSTB: g' = g + conv(t_last) (swinir.py:245-246); G = dL/dg' keeps flowing through the skip
       const ConvT& cv = t->convs[t->s_conv[li]];
-      SSR_TRY(wgrad_conv(m, cv, W.Gb, W.tb[li], CP, B, Hp, Wp, 1.0f, W.dwp, grads, s));
+      SSR_TRY(wgrad_conv(m, cv, W.Gb, W.tb[li], CP, B, Hp, Wp, 1.0f, W.dwp, W.partial, grads, s));
       GemmArgs g = dgrad_base(m, cv, W.Gb, B, Hp, Wp);
       g.out_f32 = W.Gt;
       g.ld_f32 = CP;
@@ -986,7 +991,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
       const BlockT& bt = t->s_blocks[li][bi];
       const SwinBlockWs& bw = W.blk[li][bi];
       // ---- MLP: t_out = t_mid + fc2(GELU(fc1(LN2(t_mid))))  (swinir.py:172, common.py:184-194) ----
-      SSR_TRY(wgrad_lin(m, bt.fc2, W.Gtb, bw.h, T, W.dwp, grads, s));
+      SSR_TRY(wgrad_lin(m, bt.fc2, W.Gtb, bw.h, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.fc2, W.Gtb, T);
         g.mask = bw.u;  // GELU backward on the saved pre-activation
@@ -996,16 +1001,16 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
         g.ld_T = m->HP;
         SSR_TRY(launch_gemm_tc(g, 2, s));
       }
-      SSR_TRY(wgrad_lin(m, bt.fc1, W.dH, bw.xn2, T, W.dwp, grads, s));
+      SSR_TRY(wgrad_lin(m, bt.fc1, W.dH, bw.xn2, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.fc1, W.dH, T);
         g.out_T = W.dXn;
         g.ld_T = CP;
         SSR_TRY(launch_gemm_tc(g, 2, s));
       }
-      SSR_TRY(ln_backward(bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, grads, s));
+      SSR_TRY(ln_backward(bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
       // ---- attention: t_mid = t_in + proj(W-MSA(LN1(t_in)))  (swinir.py:149-171) ----
-      SSR_TRY(wgrad_lin(m, bt.proj, W.Gtb, bw.o, T, W.dwp, grads, s));
+      SSR_TRY(wgrad_lin(m, bt.proj, W.Gtb, bw.o, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.proj, W.Gtb, T);
         g.out_T = W.dO;
@@ -1034,19 +1039,19 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
         if (L.heads * L.DP < L.QP) SSR_CUDA(cudaMemsetAsync(W.dQKV, 0, (size_t)T * 3 * L.QP * 2, s));
         SSR_TRY(launch_attn_bwd(a, s));
       }
-      SSR_TRY(wgrad_lin(m, bt.qkv, W.dQKV, bw.xn1, T, W.dwp, grads, s));
+      SSR_TRY(wgrad_lin(m, bt.qkv, W.dQKV, bw.xn1, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.qkv, W.dQKV, T);
         g.out_T = W.dXn;
         g.ld_T = CP;
         SSR_TRY(launch_gemm_tc(g, 2, s));
       }
-      SSR_TRY(ln_backward(bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, grads, s));
+      SSR_TRY(ln_backward(bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
     }
     SSR_TRY(launch_add_inplace(W.G, W.Gt, W.Gb, (size_t)T * CP, s));  // blocks' path joins the group skip
   }
   // g0 = patch_embed.norm(x0) (swinir.py:22-32, 343-344); x0 also receives the long skip Gres
-  SSR_TRY(ln_backward(t->s_pe, m->dev<float>(m->pe_norm.g_off), W.x0, W.G, 4, W.Gres, W.Gt, W.Gtb, T, C, CP, grads, s));
+  SSR_TRY(ln_backward(t->s_pe, m->dev<float>(m->pe_norm.g_off), W.x0, W.G, 4, W.Gres, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
   if (grads[t->head_w]) {
     WgradArgs a;
     memset(&a, 0, sizeof(a));
@@ -1068,7 +1073,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_wgrad(W.dwp + t->head_dwp, grads[t->head_w], C, 3, 64, 9, 0, s));
   }
-  if (grads[t->head_b]) SSR_TRY(launch_colsum(W.Gtb, 2, CP, T, C, 0, 1.0f, grads[t->head_b], s));
+  if (grads[t->head_b]) SSR_TRY(launch_colsum(W.Gtb, 2, CP, T, CP, C, 0, 1.0f, grads[t->head_b], W.partial, s));
   return SSR_OK;
 }
 

@@ -85,7 +85,7 @@ def op_conv_wgrad(dy, x, taps=9, alpha=1.0, want_bias=True):
     Cin = x.shape[1]
     dW = torch.empty((Cout, Cin, 3, 3) if taps == 9 else (Cout, Cin), device="cuda")
     db = torch.empty(Cout, device="cuda") if want_bias else None
-    elems = B * H * Wd * (Cin + Cout + 128) + 2 * (Cout + 64) * taps * (Cin + 64) + 4096
+    elems = B * H * Wd * (Cin + Cout + 128) + 2 * (Cout + 64) * taps * (Cin + 64) + 4096 + 2 * 592 * 2304
     ws = _ws(lib.ssr_op_workspace_bytes(elems))
     _lib.check(lib.ssr_op_conv3x3_wgrad(_p(dy), _p(x), _p(dW), _p(db), B, Cin, Cout, H, Wd, taps, alpha, _p(ws), ws.numel(),
                                         stream()))
