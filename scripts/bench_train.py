@@ -38,9 +38,18 @@ def main():
         model, B, H, W = SwinIR(scale=4), 32, 64, 64
         step_flops = 32 * 321.30e9
         name = "SwinIR-x4 Trainer step, batch 32 of 64x64 LR patches per GPU, bf16 autocast, L1 loss"
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     model = model.cuda().train()
+    dist = None
+    if world > 1:  # data-parallel replicas, gradient all-reduce by DDP over NCCL (trainer.py:89-91)
+        import torch.distributed as dist
+        from torch.nn.parallel import DistributedDataParallel as DDP
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        model = DDP(model, device_ids=[local], output_device=local)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99))
-    g = torch.Generator().manual_seed(1234)
+    g = torch.Generator().manual_seed(1234 + rank)
     x = torch.rand(B, 3, H, W, generator=g).cuda()
     y = torch.rand(B, 3, 4 * H, 4 * W, generator=g).cuda()
     lib = _lib.load()
@@ -57,6 +66,9 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
     l0 = lib.ssr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -65,7 +77,16 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    if dist is not None:  # max over ranks of the device-side time
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
     launches = (lib.ssr_launch_count() - l0) // args.steps
+    if rank != 0:  # the profiled step below still all-reduces: every rank takes part, rank 0 reports
+        step()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        return
     lib.ssr_profile_begin()
     step()
     buf = _lib.ctypes.create_string_buffer(1 << 16)
@@ -74,12 +95,16 @@ def main():
     kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["ms"] > 0 else 0.0,
                    "gbs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] > 0 else 0.0} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     pk = peaks()
+    step_flops *= world
     tf = step_flops / (ms / 1e3) / 1e12
     print(json.dumps({
-        "metric": f"{args.workload}_train_step", "ms_per_step": ms, "achieved_tflops": tf, "frac_of_sustained_peak": tf / pk["tf_sust"],
-        "output_mpix_per_s": B * 16 * H * W / 1e6 / (ms / 1e3), "alg_tflop_per_step": step_flops / 1e12, "loss": float(loss),
+        "metric": f"{args.workload}_train_step", "n_gpus": world, "ms_per_step": ms, "achieved_tflops": tf,
+        "frac_of_sustained_peak": tf / pk["tf_sust"] / world, "scaling": "weak",
+        "output_mpix_per_s": world * B * 16 * H * W / 1e6 / (ms / 1e3), "alg_tflop_per_step": step_flops / 1e12, "loss": float(loss.detach()),
         "launches_per_step": int(launches), "optimizer_in_step": not args.no_optimizer, "config": {"workload": name},
         "profiled_kernel_ms": sum(v["ms"] for v in prof.values()), "kernels": kernels}))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

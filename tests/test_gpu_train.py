@@ -175,3 +175,87 @@ def test_swinir_backward(name, over, B, H, W):
     print(f"SwinIR {name}: worst gradient rel err {worst[1]:.3e} (reference under bf16 autocast: {worst[2]:.3e}) at {worst[3]}")
     bad = sorted(r for r in report if r[0] > 1.0)
     assert not bad, f"SwinIR {name}: " + "; ".join(f"{k}: {e:.3e} (ref-bf16 {er:.3e})" for _, e, er, k in bad[-8:])
+
+
+@pytest.mark.parametrize("name", ["train_edsr_tiny_x4_2x24x20", "train_swinir_tiny_x4_pad_1x20x28", "train_swinir_c180_x4_1x16x16"])
+def test_backward_against_reference_golden_gradients(name):
+    """CUDA gradients directly against gradients the reference's own loss.backward() produced (oracle/make_golden_train.py)."""
+    from studiosr_b200.models import EDSR, SwinIR
+
+    with open(os.path.join(GOLD, "meta_train.json")) as f:
+        c = json.load(f)["cases"][name]
+    cfg, shape = c["cfg"], tuple(c["shape"])
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    x = synth.image_batch(shape, c["xseed"]).cuda()
+    tgt = synth.image_batch((shape[0], 3, shape[2] * cfg["scale"], shape[3] * cfg["scale"]), c["xseed"] + 1).cuda()
+    if c["arch"] == "edsr":
+        model = EDSR(**cfg)
+        model.load_state_dict(synth.edsr_weights(cfg, c["wseed"]), strict=True)
+    else:
+        kw = {k: cfg[k] for k in ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size",
+                                  "mlp_ratio", "upsampler")}
+        model = SwinIR(drop_path_rate=0.0, **kw)
+        model.load_state_dict(synth.swinir_weights(cfg, c["wseed"]), strict=True)
+    model = model.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = F.l1_loss(model(x), tgt)
+    loss.backward()
+    assert abs(loss.item() - float(gold["loss"][0])) < 5e-3
+    for k, p in model.named_parameters():
+        if k + "::norm" not in gold.files:
+            continue
+        ref = torch.from_numpy(gold[k + "::sample"])
+        got = p.grad.flatten()[::c["stride"]].cpu()
+        # the bias-table gradient is a sum of dS entries with heavy cancellation: the reference's own bf16 autocast run is
+        # off by the same 5-10 % there (see test_swinir_backward, which bounds it by 2x that error)
+        tol = 0.15 if k.endswith("relative_position_bias_table") else 6e-2
+        assert _rel(got, ref) < tol, f"{k}: rel err {_rel(got, ref):.3e}"
+        assert abs(p.grad.norm().item() - float(gold[k + "::norm"][0])) < 3e-2 * float(gold[k + "::norm"][0]) + 1e-9, k
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from studiosr_b200.models import EDSR
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = synth.EDSR_TINY
+    model = EDSR(**cfg)
+    model.load_state_dict(synth.edsr_weights(cfg, 3), strict=True)
+    model = model.cuda().train()
+    xs = [synth.image_batch((2, 3, 16, 16), 40 + r).cuda() for r in range(world)]
+    ts = [synth.image_batch((2, 3, 64, 64), 50 + r).cuda() for r in range(world)]
+    # expected: mean over ranks of the single-process gradients (what DDP's all-reduce must produce, trainer.py:89-91)
+    want = None
+    for r in range(world):
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            F.l1_loss(model(xs[r]), ts[r]).backward()
+        g = [p.grad.clone() for p in model.parameters() if p.requires_grad]
+        want = g if want is None else [a + b for a, b in zip(want, g)]
+    want = [w / world for w in want]
+    model.zero_grad(set_to_none=True)
+    ddp = DDP(model, device_ids=[rank], output_device=rank)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        F.l1_loss(ddp(xs[rank]), ts[rank]).backward()
+    got = [p.grad for p in model.parameters() if p.requires_grad]
+    worst = max(_rel(a.float().cpu(), b.float().cpu()) for a, b in zip(got, want))
+    if rank == 0:
+        with open(out, "w") as f:
+            f.write(repr(worst))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (data-parallel gradient all-reduce over NCCL)")
+def test_ddp_gradient_allreduce_two_gpus(tmp_path):
+    """DistributedDataParallel around the drop-in module (trainer.py:89-91): the native backward's gradients must reach
+    DDP's reducer and come back as the mean over ranks."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "worst.txt")
+    mp.spawn(_ddp_worker, args=(2, 29611, out), nprocs=2, join=True)
+    worst = float(open(out).read())
+    assert worst < 1e-5, worst

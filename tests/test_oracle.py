@@ -1,5 +1,8 @@
 """CPU: pin the oracle restatement (oracle/sr_oracle.py) against fixtures produced by
 executing the unmodified reference (oracle/make_golden.py)."""
+import json
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -125,3 +128,44 @@ def test_tiler_identity_and_tile_starts():
     up = lambda t: t.repeat_interleave(4, 2).repeat_interleave(4, 3)
     y = O.tiled_upscale(up, x, 4, tile=64, overlap=16)
     assert (y - up(x)).abs().max().item() < 1e-6
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- training step: the oracle's autograd against gradients produced by the reference's own loss.backward() ----
+def _train_meta():
+    with open(os.path.join(GOLD, "meta_train.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("name", sorted(_train_meta().keys()))
+def test_oracle_backward_matches_reference_gradients(name):
+    import torch.nn.functional as F
+
+    c = _train_meta()[name]
+    cfg, shape = c["cfg"], tuple(c["shape"])
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    x = synth.image_batch(shape, c["xseed"])
+    tgt = synth.image_batch((shape[0], 3, shape[2] * cfg["scale"], shape[3] * cfg["scale"]), c["xseed"] + 1)
+    if c["arch"] == "edsr":
+        P = synth.edsr_weights(cfg, c["wseed"])
+        Q = {k: v.clone().requires_grad_(v.is_floating_point() and "mean" not in k) for k, v in P.items()}
+        loss = F.l1_loss(O.edsr_forward(Q, x, cfg), tgt)
+    else:
+        P = synth.swinir_weights(cfg, c["wseed"])
+        Q = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
+        loss = F.l1_loss(O.swinir_forward(Q, x, cfg, training=True), tgt)
+    loss.backward()
+    assert abs(loss.item() - float(gold["loss"][0])) < 1e-5
+    checked = 0
+    for k, v in Q.items():
+        if k + "::norm" not in gold.files:
+            continue
+        g = v.grad.flatten()
+        ref_norm = float(gold[k + "::norm"][0])
+        assert abs(g.norm().item() - ref_norm) <= 2e-4 * ref_norm + 1e-9, k
+        ref = torch.from_numpy(gold[k + "::sample"])
+        assert (g[::c["stride"]] - ref).norm().item() <= 2e-4 * ref.norm().item() + 1e-9, k
+        checked += 1
+    assert checked == c["n_params"]
