@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Secondary benchmark lines (not the driver's headline): training steps of BASELINE.json configs 2 and 4 on one GPU.
+"""Secondary benchmark lines (not the driver's headline): BASELINE.json configs 2, 3 and 4.
 
-  python scripts/bench_train.py --workload cfg2   # EDSR-x4 fwd+bwd, 16 x 3x48x48, bf16 autocast, L1 loss (+ Adam step)
-  python scripts/bench_train.py --workload cfg4   # SwinIR-x4 Trainer step, 32 x 3x64x64 per GPU
+  python scripts/bench_extra.py --workload cfg2   # EDSR-x4 fwd+bwd, 16 x 3x48x48, bf16 autocast, L1 loss (+ Adam step)
+  python scripts/bench_extra.py --workload cfg3   # HAT-x4 bf16 inference, batch 32 of 64x64 LR tiles
+  python scripts/bench_extra.py --workload cfg4   # SwinIR-x4 Trainer step, 32 x 3x64x64 per GPU (torchrun: DDP)
 
 Prints one JSON line: ms per step (CUDA events, after warm-up), algorithmic TFLOP/s (SURVEY 8d FLOP counts) as a
 fraction of the measured bf16 peak, output Mpix/s, and the per-kernel-class profile from ssr_profile_begin/end."""
@@ -17,7 +18,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-optimizer", action="store_true")
@@ -27,22 +28,29 @@ def main():
 
     from bench import peaks
     from studiosr_b200 import _lib
-    from studiosr_b200.models import EDSR, SwinIR
+    from studiosr_b200.models import EDSR, HAT, SwinIR
 
     torch.manual_seed(0)
     if args.workload == "cfg2":
         model, B, H, W = EDSR(scale=4), 16, 48, 48
         step_flops = 16 * 694.66e9  # fwd+bwd per 48x48 patch
         name = "EDSR-x4 forward+backward (+Adam), batch 16 of 48x48 LR patches, bf16 autocast, L1 loss"
+    elif args.workload == "cfg3":
+        model, B, H, W = HAT(scale=4), 32, 64, 64
+        step_flops = 32 * 207.76e9  # forward per 64x64 tile
+        name = "HAT-x4 bf16 inference, batch 32 of 64x64 LR tiles (overlapping cross-attention + channel attention)"
     else:
         model, B, H, W = SwinIR(scale=4), 32, 64, 64
         step_flops = 32 * 321.30e9
         name = "SwinIR-x4 Trainer step, batch 32 of 64x64 LR patches per GPU, bf16 autocast, L1 loss"
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    model = model.cuda().train()
+    infer = args.workload == "cfg3"
+    model = model.cuda().eval() if infer else model.cuda().train()
+    if infer:
+        model.precision = "bf16"
     dist = None
-    if world > 1:  # data-parallel replicas, gradient all-reduce by DDP over NCCL (trainer.py:89-91)
+    if world > 1 and not infer:  # data-parallel replicas, gradient all-reduce by DDP over NCCL (trainer.py:89-91)
         import torch.distributed as dist
         from torch.nn.parallel import DistributedDataParallel as DDP
 
@@ -55,6 +63,9 @@ def main():
     lib = _lib.load()
 
     def step():
+        if infer:
+            with torch.inference_mode():
+                return model(x).sum()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = F.l1_loss(model(x), y)
         loss.backward()
@@ -98,10 +109,10 @@ def main():
     step_flops *= world
     tf = step_flops / (ms / 1e3) / 1e12
     print(json.dumps({
-        "metric": f"{args.workload}_train_step", "n_gpus": world, "ms_per_step": ms, "achieved_tflops": tf,
+        "metric": f"{args.workload}_{'inference' if infer else 'train'}_step", "n_gpus": world, "ms_per_step": ms, "achieved_tflops": tf,
         "frac_of_sustained_peak": tf / pk["tf_sust"] / world, "scaling": "weak",
         "output_mpix_per_s": world * B * 16 * H * W / 1e6 / (ms / 1e3), "alg_tflop_per_step": step_flops / 1e12, "loss": float(loss.detach()),
-        "launches_per_step": int(launches), "optimizer_in_step": not args.no_optimizer, "config": {"workload": name},
+        "launches_per_step": int(launches), "optimizer_in_step": (not args.no_optimizer) and not infer, "config": {"workload": name},
         "profiled_kernel_ms": sum(v["ms"] for v in prof.values()), "kernels": kernels}))
     if dist is not None:
         dist.destroy_process_group()

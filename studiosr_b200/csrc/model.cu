@@ -1194,7 +1194,10 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
         a.bias = m->dev<float>(blk.bias_off);
         a.B = B; a.H = Hp; a.W = Wp; a.ws = c.window_size; a.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
         a.heads = L.heads; a.d = L.d; a.DP = L.DP; a.elem = e;
-        SSR_TRY(launch_attn_simt(a, s));
+        if (e == 2 && (a.DP == 16 || a.DP == 32) && (a.ws * a.ws) % 64 == 0)
+          SSR_TRY(launch_attn_flash(a, 0, s));  // bf16: mma.sync tiles with an online softmax over key chunks
+        else
+          SSR_TRY(launch_attn_simt(a, s));
         GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
         gp.res = shortcut;
         gp.ldres = CP;
@@ -1225,7 +1228,10 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
       a.qkv = W.qkv; a.ld_qkv = 3 * L.QP; a.QP = L.QP; a.o = W.o; a.ld_o = L.QP;
       a.bias = m->dev<float>(blk.bias_off);
       a.B = B; a.H = Hp; a.W = Wp; a.ws = c.window_size; a.kws = wse; a.heads = L.heads; a.d = L.d; a.DP = L.DP; a.elem = e;
-      SSR_TRY(launch_attn_oca(a, s));
+      if (e == 2 && (a.DP == 16 || a.DP == 32) && (a.ws * a.ws) % 64 == 0 && (a.kws * a.kws) % 64 == 0)
+        SSR_TRY(launch_attn_flash(a, 1, s));  // bf16: mma.sync tiles with an online softmax over key chunks
+      else
+        SSR_TRY(launch_attn_oca(a, s));
       GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
       gp.res = W.t;
       gp.ldres = CP;

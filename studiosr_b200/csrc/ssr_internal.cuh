@@ -316,6 +316,7 @@ int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s);
 int launch_attn_simt(const AttnArgs& a, cudaStream_t s);
 int launch_attn_oca(const AttnArgs& a, cudaStream_t s);
 int launch_attn_mma(const AttnArgs& a, cudaStream_t s);
+int launch_attn_flash(const AttnArgs& a, int oca, cudaStream_t s);  // bf16, large windows (HAT): k_attn_flash.cu
 int launch_layernorm(const LnArgs& a, cudaStream_t s);
 int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s);
 int launch_conv_last(const ConvLastArgs& a, cudaStream_t s);
