@@ -146,13 +146,18 @@ int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, u
  *   ssr_model_train_backward dy = dL/dy (DEVICE fp32 NCHW).  grads[i] = DEVICE fp32 buffer for dL/d(param i), overwritten
  *                            (NULL: not wanted, e.g. frozen entries).  `workspace` must be the buffer, untouched, that
  *                            the matching train_forward used.  dL/dx is not produced (the Trainer never asks for it).
+ *   drop_scale               stochastic depth of SwinIR (timm DropPath, swinir.py:137,171-172): DEVICE fp32
+ *                            [2 * n_blocks][B], entry [2k][b] / [2k+1][b] = the factor (0 or 1/keep_prob) applied to sample b's
+ *                            attention / MLP branch of block k (blocks in forward order); NULL = no stochastic depth.  The host
+ *                            draws it (the Python module consumes torch's RNG exactly as the reference's DropPath calls do);
+ *                            the same array must be passed to the matching backward.
  * Forward/backward pairs on one handle must not interleave with another forward on the same handle. */
 int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const int64_t* numels);
 size_t ssr_model_train_workspace_bytes(const ssr_model_t* m, int B, int H, int W);
-int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const float* x, float* y, int B, int H, int W,
-                            void* workspace, size_t workspace_bytes, void* stream);
-int ssr_model_train_backward(ssr_model_t* m, const float* dy, float* const* grads, int B, int H, int W, void* workspace,
-                             size_t workspace_bytes, void* stream);
+int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const float* drop_scale, const float* x, float* y, int B,
+                            int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+int ssr_model_train_backward(ssr_model_t* m, const float* dy, const float* drop_scale, float* const* grads, int B, int H, int W,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 int64_t ssr_launch_count(void);

@@ -27,7 +27,11 @@ CASES = {
     "train_swinir_tiny_x4_pad_1x20x28": ("swinir", synth.swinir_config(**synth.SWINIR_TINY), 11, (1, 3, 20, 28), 101),
     "train_swinir_c180_x4_1x16x16": ("swinir", synth.swinir_config(embed_dim=180, depths=[2, 2], num_heads=[6, 6]), 11,
                                      (1, 3, 16, 16), 101),
+    # stochastic depth ON (reference default is drop_path_rate=0.1; 0.5 here so that several branches really drop):
+    # torch.manual_seed(DROP_SEED) right before the forward fixes the masks the reference's DropPath modules draw
+    "train_swinir_tiny_x4_droppath_4x16x16": ("swinir_dp", synth.swinir_config(**synth.SWINIR_TINY), 11, (4, 3, 16, 16), 101),
 }
+DROP_SEED, DROP_RATE = 77, 0.5
 
 
 def case_inputs(cfg, shape, xseed):
@@ -47,10 +51,12 @@ def main() -> None:
             m = models.EDSR(**cfg)
             m.load_state_dict(synth.edsr_weights(cfg, wseed), strict=True)
         else:
-            m = models.SwinIR(drop_path_rate=0.0, **cfg)
+            m = models.SwinIR(drop_path_rate=DROP_RATE if arch == "swinir_dp" else 0.0, **cfg)
             m.load_state_dict(synth.swinir_weights(cfg, wseed), strict=True)
         m.train()
         x, tgt = case_inputs(cfg, shape, xseed)
+        if arch == "swinir_dp":
+            torch.manual_seed(DROP_SEED)
         loss = torch.nn.L1Loss()(m(x), tgt)
         loss.backward()
         arrays = {}
@@ -63,6 +69,8 @@ def main() -> None:
         np.savez_compressed(os.path.join(OUT, name + ".npz"), loss=np.asarray([loss.item()]), **arrays)
         meta[name] = dict(arch=arch, cfg=cfg, wseed=wseed, shape=list(shape), xseed=xseed, stride=STRIDE,
                           n_params=len(arrays) // 2)
+        if arch == "swinir_dp":
+            meta[name].update(drop_seed=DROP_SEED, drop_path_rate=DROP_RATE)
         print(name, "loss", loss.item(), "params", len(arrays) // 2)
     with open(os.path.join(OUT, "meta_train.json"), "w") as f:
         json.dump(dict(cases=meta), f, indent=1, sort_keys=True)

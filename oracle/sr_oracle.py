@@ -126,8 +126,9 @@ def gelu(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def swin_block(P: Dict, pre: str, x: torch.Tensor, heads: int, ws: int, shift: int) -> torch.Tensor:
-    """swinir.py:146-174 with drop_path == identity -- x [B,H,W,C]."""
+def swin_block(P: Dict, pre: str, x: torch.Tensor, heads: int, ws: int, shift: int, drop=None) -> torch.Tensor:
+    """swinir.py:146-174 -- x [B,H,W,C].  drop = (s_attn [B], s_mlp [B]): the per-sample factors timm's DropPath multiplies
+    the two residual branches with in training (0 or 1/keep_prob; swinir.py:171-172), None = identity."""
     B, H, W, C = x.shape
     y = layer_norm(x, P[pre + ".norm1.weight"], P[pre + ".norm1.bias"])
     if shift > 0:
@@ -137,10 +138,14 @@ def swin_block(P: Dict, pre: str, x: torch.Tensor, heads: int, ws: int, shift: i
     y = from_windows(a, ws, B, H, W)
     if shift > 0:
         y = torch.roll(y, (shift, shift), (1, 2))
+    if drop is not None:
+        y = y * drop[0].to(y.dtype).view(-1, 1, 1, 1)
     x = x + y
     y = layer_norm(x, P[pre + ".norm2.weight"], P[pre + ".norm2.bias"])
     y = gelu(y @ P[pre + ".mlp.fc1.weight"].t() + P[pre + ".mlp.fc1.bias"])
     y = y @ P[pre + ".mlp.fc2.weight"].t() + P[pre + ".mlp.fc2.bias"]
+    if drop is not None:
+        y = y * drop[1].to(y.dtype).view(-1, 1, 1, 1)
     return x + y
 
 
@@ -166,8 +171,9 @@ def _upsampler(P: Dict, pre: str, x: torch.Tensor, scale: int, n_feats: int, num
 
 
 # --------------------------------------------------------------------------- SwinIR
-def swinir_forward(P: Dict, x: torch.Tensor, cfg: Dict, training: bool = False) -> torch.Tensor:
-    """swinir.py:353-372 (+ forward_features :342-351, RSTB :245-246), drop_path off.
+def swinir_forward(P: Dict, x: torch.Tensor, cfg: Dict, training: bool = False, drop_scale=None) -> torch.Tensor:
+    """swinir.py:353-372 (+ forward_features :342-351, RSTB :245-246).  drop_scale [2 * n_blocks, B] = the stochastic-depth
+    factors of this step (row 2k / 2k+1: attention / MLP branch of block k), None = drop_path off.
 
     x: [B, n_colors, H, W] float -> [B, n_colors, s*H, s*W]."""
     dt = x.dtype
@@ -180,11 +186,14 @@ def swinir_forward(P: Dict, x: torch.Tensor, cfg: Dict, training: bool = False) 
     x0 = conv3x3(P, "conv_first", x)
     t = x0.permute(0, 2, 3, 1)
     t = layer_norm(t, P["patch_embed.norm.weight"], P["patch_embed.norm.bias"])
+    k = 0
     for li, depth in enumerate(cfg["depths"]):
         g = t
         for bi in range(depth):
             shift = 0 if bi % 2 == 0 else ws // 2
-            t = swin_block(P, f"layers.{li}.residual_group.blocks.{bi}", t, cfg["num_heads"][li], ws, shift)
+            drop = None if drop_scale is None else (drop_scale[2 * k], drop_scale[2 * k + 1])
+            t = swin_block(P, f"layers.{li}.residual_group.blocks.{bi}", t, cfg["num_heads"][li], ws, shift, drop)
+            k += 1
         t = conv3x3(P, f"layers.{li}.conv", t.permute(0, 3, 1, 2)).permute(0, 2, 3, 1) + g
     t = layer_norm(t, P["norm.weight"], P["norm.bias"])
     y = conv3x3(P, "conv_after_body", t.permute(0, 3, 1, 2)) + x0

@@ -49,10 +49,10 @@ SYMBOLS = {
                                                 c_void_p, c_size_t, c_void_p]),
     "ssr_model_train_bind": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int64)]),
     "ssr_model_train_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
-    "ssr_model_train_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                        c_size_t, c_void_p]),
-    "ssr_model_train_backward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_size_t,
-                                         c_void_p]),
+    "ssr_model_train_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_void_p, c_size_t, c_void_p]),
+    "ssr_model_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p,
+                                         c_size_t, c_void_p]),
     "ssr_launch_count": (c_int64, []),
     "ssr_profile_begin": (c_int, []),
     "ssr_profile_end": (c_int, [c_char_p, c_size_t]),

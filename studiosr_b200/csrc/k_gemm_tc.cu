@@ -306,6 +306,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (g.row_scale && m >= 0) {
+          const float rs = __ldg(g.row_scale + m / g.rows_per_scale);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= rs;
+        }
         if (dbg && c == 1) dbg[6] = clock64();
         if (g.res || g.out_f32) {
           // transposed domain: add the (prefetched, coalesced) residual and store the fp32 stream

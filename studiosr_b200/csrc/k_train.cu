@@ -504,4 +504,20 @@ int launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s) {
   return SSR_OK;
 }
 
+__global__ void scale_to_bf16_kernel(const float* __restrict__ in, const float* __restrict__ scale, size_t elems_per_scale,
+                                     __nv_bfloat16* out, size_t n4) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float sc = __ldg(scale + (i * 4) / elems_per_scale);
+  const float4 x = reinterpret_cast<const float4*>(in)[i];
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(x.x * sc, x.y * sc), pack_bf16x2(x.z * sc, x.w * sc));
+}
+int launch_scale_to_bf16(const float* in, const float* scale, size_t elems_per_scale, void* out, size_t n, cudaStream_t s) {
+  SSR_CHECK(n % 4 == 0 && elems_per_scale % 4 == 0, SSR_E_INVALID, "scale_to_bf16: n %% 4");
+  scale_to_bf16_kernel<<<(int)((n / 4 + 255) / 256), 256, 0, s>>>(in, scale, elems_per_scale, (__nv_bfloat16*)out, n / 4);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 }  // namespace ssr

@@ -99,6 +99,9 @@ struct GemmArgs {
   int mask_mode;
   void* out_pre;  // T [M][ld_pre]: copy of (acc + bias) BEFORE the activation (kept for the backward), or null
   int ld_pre;
+  // stochastic depth (timm DropPath, swinir.py:137,171-172): v *= row_scale[m / rows_per_scale] before the residual add
+  const float* row_scale;  // [ceil(M / rows_per_scale)] or null (tensor-core path only)
+  int rows_per_scale;
   long long* dbg;    // optional per-CTA phase timestamps (developer diagnostics), 8 slots per CTA
 };
 double gemm_alg_flops(const GemmArgs& g);
@@ -300,6 +303,8 @@ int launch_input_nhwc64(const float* x, void* out, int B, int h, int w, int Hp, 
                         cudaStream_t s);
 int launch_grad_nhwc64(const float* dy, void* out, int B, int ch, int cw, int Hs, int Ws, float scale, cudaStream_t s);
 int launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s);
+// out[i] = bf16(in[i] * scale[i / elems_per_scale])
+int launch_scale_to_bf16(const float* in, const float* scale, size_t elems_per_scale, void* out, size_t n, cudaStream_t s);
 
 // k_train.cu: on-device (re)packing of the fp32 master parameters, gradient unpacking, small backward pieces
 int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int Cout, int Cin, int NP, int KP,

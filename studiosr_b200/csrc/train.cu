@@ -633,8 +633,8 @@ static void train_padded(const ssr_model* m, int h, int w, int* Hp, int* Wp) {
 
 static const float kMean3[3] = {0.4488f, 0.4371f, 0.4040f};  // common.py:223
 
-static int train_forward_swinir(ssr_model* m, const float* const* params, const float* x, float* y, int B, int h, int w, void* ws,
-                                size_t ws_bytes, cudaStream_t s) {
+static int train_forward_swinir(ssr_model* m, const float* const* params, const float* drop, const float* x, float* y, int B, int h,
+                                int w, void* ws, size_t ws_bytes, cudaStream_t s) {
   ssr_train_state* t = m->train;
   const ssr_model_config& c = m->cfg;
   int Hp, Wp;
@@ -709,10 +709,11 @@ static int train_forward_swinir(ssr_model* m, const float* const* params, const 
     SSR_TRY(launch_layernorm(a, s));
   }
   const int nL = (int)m->layers.size();
+  int kblk = 0;  // running block index: drop holds [2 * kblk] (attention branch) and [2 * kblk + 1] (MLP branch), B floats each
   for (int li = 0; li < nL; ++li) {
     const Layer& L = m->layers[li];
     const int depth = (int)L.blocks.size();
-    for (int bi = 0; bi < depth; ++bi) {
+    for (int bi = 0; bi < depth; ++bi, ++kblk) {
       const Block& blk = L.blocks[bi];
       SwinBlockWs& bw = W.blk[li][bi];
       {
@@ -745,6 +746,10 @@ static int train_forward_swinir(ssr_model* m, const float* const* params, const 
         GemmArgs g = gemm_base(m, blk.proj, bw.o, L.QP, B, Hp, Wp);
         g.res = bw.tin;
         g.ldres = CP;
+        if (drop) {  // x = shortcut + drop_path(attn)  (swinir.py:171)
+          g.row_scale = drop + (size_t)(2 * kblk) * B;
+          g.rows_per_scale = Hp * Wp;
+        }
         g.out_f32 = bw.tmid;
         g.ld_f32 = CP;
         g.out_ln = bw.xn2;
@@ -766,6 +771,10 @@ static int train_forward_swinir(ssr_model* m, const float* const* params, const 
         GemmArgs g = gemm_base(m, blk.fc2, bw.h, HP, B, Hp, Wp);
         g.res = bw.tmid;
         g.ldres = CP;
+        if (drop) {  // x = x + drop_path(mlp(norm2(x)))  (swinir.py:172)
+          g.row_scale = drop + (size_t)(2 * kblk + 1) * B;
+          g.rows_per_scale = Hp * Wp;
+        }
         if (bi + 1 < depth) {
           g.out_f32 = bw.tout;
           g.ld_f32 = CP;
@@ -907,8 +916,8 @@ static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, con
   return launch_ln_bwd(a, s);
 }
 
-static int train_backward_swinir(ssr_model* m, const float* dy, float* const* grads, int B, int h, int w, void* ws, size_t ws_bytes,
-                                 cudaStream_t s) {
+static int train_backward_swinir(ssr_model* m, const float* dy, const float* drop, float* const* grads, int B, int h, int w, void* ws,
+                                 size_t ws_bytes, cudaStream_t s) {
   ssr_train_state* t = m->train;
   const ssr_model_config& c = m->cfg;
   int Hp, Wp;
@@ -972,6 +981,9 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
     SSR_TRY(launch_gemm_tc(g, 2, s));
   }
   const int nL = (int)m->layers.size();
+  int kblk = 0;
+  for (int li = 0; li < nL; ++li) kblk += (int)m->layers[li].blocks.size();
+  const size_t per_sample = (size_t)Hp * Wp * CP;
   SSR_TRY(ln_backward(t->s_fin, m->dev<float>(m->final_norm.g_off), W.g[nL], W.dXn, 2, nullptr, W.G, W.Gb, T, C, CP, W.partial, grads, s));
   for (int li = nL - 1; li >= 0; --li) {
     const Layer& L = m->layers[li];
@@ -987,10 +999,13 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
       SSR_TRY(launch_gemm_tc(g, 2, s));
     }
     for (int bi = depth - 1; bi >= 0; --bi) {
+      --kblk;
       const Block& blk = L.blocks[bi];
       const BlockT& bt = t->s_blocks[li][bi];
       const SwinBlockWs& bw = W.blk[li][bi];
       // ---- MLP: t_out = t_mid + fc2(GELU(fc1(LN2(t_mid))))  (swinir.py:172, common.py:184-194) ----
+      // with stochastic depth the branch sees dL/dt_out scaled per sample: Gtb = bf16(Gt * drop[2k+1][b])
+      if (drop) SSR_TRY(launch_scale_to_bf16(W.Gt, drop + (size_t)(2 * kblk + 1) * B, per_sample, W.Gtb, (size_t)T * CP, s));
       SSR_TRY(wgrad_lin(m, bt.fc2, W.Gtb, bw.h, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.fc2, W.Gtb, T);
@@ -1010,6 +1025,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, float* const* gr
       }
       SSR_TRY(ln_backward(bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
       // ---- attention: t_mid = t_in + proj(W-MSA(LN1(t_in)))  (swinir.py:149-171) ----
+      if (drop) SSR_TRY(launch_scale_to_bf16(W.Gt, drop + (size_t)(2 * kblk) * B, per_sample, W.Gtb, (size_t)T * CP, s));
       SSR_TRY(wgrad_lin(m, bt.proj, W.Gtb, bw.o, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.proj, W.Gtb, T);
@@ -1111,23 +1127,24 @@ size_t ssr_model_train_workspace_bytes(const ssr_model_t* m, int B, int H, int W
   return plan_edsr_train(m, nullptr, B, H, W, &w);
 }
 
-int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const float* x, float* y, int B, int H, int W,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const float* drop_scale, const float* x, float* y, int B,
+                            int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
   SSR_TRY(check_ready(m));
   SSR_CHECK(m->train != nullptr, SSR_E_STATE, "ssr_model_train_bind has not been called");
   SSR_CHECK(params && x && y && B > 0 && H > 0 && W > 0, SSR_E_INVALID, "train_forward: bad argument");
   if (m->cfg.arch == SSR_ARCH_SWINIR)
-    return train_forward_swinir(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+    return train_forward_swinir(m, params, drop_scale, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+  SSR_CHECK(drop_scale == nullptr, SSR_E_INVALID, "train_forward: drop_scale is a SwinIR option");
   return train_forward_edsr(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int ssr_model_train_backward(ssr_model_t* m, const float* dy, float* const* grads, int B, int H, int W, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+int ssr_model_train_backward(ssr_model_t* m, const float* dy, const float* drop_scale, float* const* grads, int B, int H, int W,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   SSR_TRY(check_ready(m));
   SSR_CHECK(m->train != nullptr, SSR_E_STATE, "ssr_model_train_bind has not been called");
   SSR_CHECK(dy && grads && B > 0 && H > 0 && W > 0, SSR_E_INVALID, "train_backward: bad argument");
   if (m->cfg.arch == SSR_ARCH_SWINIR)
-    return train_backward_swinir(m, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+    return train_backward_swinir(m, dy, drop_scale, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_backward_edsr(m, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -40,9 +40,9 @@ class _NativeTrainStep(torch.autograd.Function):
     layouts) with the tensor-core dgrad / wgrad kernels.  dL/dx is not produced."""
 
     @staticmethod
-    def forward(ctx, x, model, nat, names, *tensors):
-        y, ws = nat.train_forward(x, [t.detach() for t in tensors], model.scale)
-        ctx.nat, ctx.ws, ctx.shape = nat, ws, tuple(x.shape)
+    def forward(ctx, x, model, nat, drop_scale, *tensors):
+        y, ws = nat.train_forward(x, [t.detach() for t in tensors], model.scale, drop_scale)
+        ctx.nat, ctx.ws, ctx.shape, ctx.drop_scale = nat, ws, tuple(x.shape), drop_scale
         ctx.meta = [(t.shape, t.numel(), t.requires_grad) for t in tensors]
         return y
 
@@ -59,7 +59,7 @@ class _NativeTrainStep(torch.autograd.Function):
                 off += n
             else:
                 grads.append(None)
-        ctx.nat.train_backward(dy, grads, ctx.shape, ctx.ws)
+        ctx.nat.train_backward(dy, grads, ctx.shape, ctx.ws, ctx.drop_scale)
         ctx.ws = None
         return (None, None, None, None, *grads)
 
@@ -131,7 +131,12 @@ class Model(nn.Module):
             nat.train_bind(named)
             self._natives[key] = nat
         names = list(named.keys())
-        return _NativeTrainStep.apply(x, self, nat, names, *[named[k] for k in names])
+        drop_scale = self._draw_drop_path(x.shape[0], dev) if self.training else None
+        return _NativeTrainStep.apply(x, self, nat, drop_scale, *[named[k] for k in names])
+
+    def _draw_drop_path(self, batch: int, device) -> Optional[torch.Tensor]:
+        """Stochastic-depth factors of this step, or None (models without DropPath)."""
+        return None
 
     def _device(self) -> torch.device:
         return next(self.parameters()).device

@@ -95,7 +95,7 @@ class SwinIR(Model):
         self.mlp_ratio = mlp_ratio
         self.drop_rate = drop_rate
         self.attn_drop_rate = attn_drop_rate
-        self.drop_path_rate = drop_path_rate  # stochastic depth is treated as identity by the native forward
+        self.drop_path_rate = drop_path_rate  # stochastic depth: training only (swinir.py:296,137,171-172), see _draw_drop_path
         self.upsampler = upsampler
 
         self.conv_first = nn.Conv2d(n_colors, embed_dim, 3, 1, 1)
@@ -123,6 +123,27 @@ class SwinIR(Model):
         elif isinstance(m, nn.LayerNorm):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
+
+    def _draw_drop_path(self, batch: int, device):
+        """Per-sample stochastic-depth factors of one training step, [2 * n_blocks, B]: row 2k / 2k+1 scales the attention /
+        MLP branch of block k.  Mirrors the reference: rates follow `torch.linspace(0, drop_path_rate, sum(depths))`
+        (swinir.py:296), a block with rate 0 has nn.Identity (swinir.py:137) and draws nothing, every other block calls timm's
+        DropPath twice per forward (swinir.py:171-172), each call drawing `x.new_empty((B,1,1,1)).bernoulli_(keep) / keep`
+        from torch's global generator of the input's device -- the draws below consume that generator identically."""
+        if self.drop_path_rate <= 0.0:
+            return None
+        n = sum(self.depths)
+        rates = [v.item() for v in torch.linspace(0, self.drop_path_rate, n)]
+        rows = []
+        for p in rates:
+            for _ in range(2):
+                if p > 0.0:
+                    keep = 1.0 - p
+                    rows.append(torch.empty((batch, 1, 1, 1), dtype=torch.float32, device=device).bernoulli_(keep).div_(keep).view(batch))
+                else:
+                    rows.append(torch.ones(batch, dtype=torch.float32, device=device))
+        self._last_drop_scale = torch.stack(rows).contiguous()
+        return self._last_drop_scale
 
     def _native_config(self, precision: int) -> "_lib.ModelConfig":
         c = _lib.ModelConfig()

@@ -82,24 +82,26 @@ class NativeModel:
             arr[i] = None if t is None else t.data_ptr()
         return arr
 
-    def train_forward(self, x: torch.Tensor, params, scale: int):
-        """x fp32 [B,3,H,W]; params: tensors in bound order.  Returns (y, workspace) -- the workspace holds the saved
-        activations and must reach train_backward untouched."""
+    def train_forward(self, x: torch.Tensor, params, scale: int, drop_scale: Optional[torch.Tensor] = None):
+        """x fp32 [B,3,H,W]; params: tensors in bound order; drop_scale: fp32 [2*n_blocks, B] stochastic-depth factors or
+        None.  Returns (y, workspace) -- the workspace holds the saved activations and must reach train_backward untouched."""
         B, C, H, W = x.shape
         x = x.detach().to(torch.float32).contiguous()
         y = torch.empty((B, C, H * scale, W * scale), dtype=torch.float32, device=x.device)
         with torch.cuda.device(self.index):
             need = self.lib.ssr_model_train_workspace_bytes(self.handle, B, H, W)
             ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
-            _lib.check(self.lib.ssr_model_train_forward(self.handle, self._ptr_array(params), x.data_ptr(), y.data_ptr(), B, H, W,
-                                                        ws.data_ptr(), ws.numel(), _stream_ptr(x.device)))
+            _lib.check(self.lib.ssr_model_train_forward(self.handle, self._ptr_array(params),
+                                                        None if drop_scale is None else drop_scale.data_ptr(), x.data_ptr(),
+                                                        y.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), _stream_ptr(x.device)))
         return y, ws
 
-    def train_backward(self, dy: torch.Tensor, grads, shape, ws: torch.Tensor) -> None:
+    def train_backward(self, dy: torch.Tensor, grads, shape, ws: torch.Tensor, drop_scale: Optional[torch.Tensor] = None) -> None:
         B, _, H, W = shape
         dy = dy.detach().to(torch.float32).contiguous()
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.ssr_model_train_backward(self.handle, dy.data_ptr(), self._ptr_array(grads), B, H, W,
+            _lib.check(self.lib.ssr_model_train_backward(self.handle, dy.data_ptr(),
+                                                         None if drop_scale is None else drop_scale.data_ptr(), self._ptr_array(grads), B, H, W,
                                                          ws.data_ptr(), ws.numel(), _stream_ptr(dy.device)))
 
     def upscale_u8(self, img: torch.Tensor, scale: int) -> torch.Tensor:

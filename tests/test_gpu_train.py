@@ -259,3 +259,45 @@ def test_ddp_gradient_allreduce_two_gpus(tmp_path):
     mp.spawn(_ddp_worker, args=(2, 29611, out), nprocs=2, join=True)
     worst = float(open(out).read())
     assert worst < 1e-5, worst
+
+
+def test_swinir_drop_path_training_step():
+    """Stochastic depth (SwinIR's default in training, swinir.py:137,171-172,296): the native step with the masks the module
+    drew against oracle autograd given the same masks.  (That those draws are the reference's own is pinned on CPU by
+    tests/test_oracle.py against a seeded run of the reference.)"""
+    from studiosr_b200.models import SwinIR
+
+    cfg = synth.swinir_config(**synth.SWINIR_TINY)
+    P = synth.swinir_weights(cfg, 11)
+    x = synth.image_batch((4, 3, 16, 16), 101)
+    tgt = synth.image_batch((4, 3, 64, 64), 102)
+    kw = {k: cfg[k] for k in ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size", "mlp_ratio",
+                              "upsampler")}
+    model = SwinIR(drop_path_rate=0.5, **kw)
+    model.load_state_dict(P, strict=True)
+    model = model.cuda().train()
+    torch.manual_seed(5)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = F.l1_loss(model(x.cuda()), tgt.cuda())
+    loss.backward()
+    drop = model._last_drop_scale.cpu()
+    assert (drop == 0).any() and (drop > 1).any(), "the seed should drop at least one branch"
+    Q = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
+    loss_ref = F.l1_loss(O.swinir_forward(Q, x, cfg, training=True, drop_scale=drop), tgt)
+    loss_ref.backward()
+    Qa = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        F.l1_loss(O.swinir_forward(Qa, x, cfg, training=True, drop_scale=drop), tgt).backward()
+    assert abs(loss.item() - loss_ref.item()) < 5e-3
+    bad = []
+    for k, p in model.named_parameters():
+        e, e_ref = _rel(p.grad.cpu(), Q[k].grad), _rel(Qa[k].grad.float(), Q[k].grad)
+        if e > max(2e-2, 2.0 * e_ref):
+            bad.append(f"{k}: {e:.3e} (ref-bf16 {e_ref:.3e})")
+    assert not bad, "; ".join(bad[:8])
+    # eval mode never drops
+    model.eval()
+    assert model._draw_drop_path(4, torch.device("cuda")) is not None  # draw helper itself is mode-agnostic ...
+    with torch.inference_mode():
+        y1, y2 = model(x.cuda()), model(x.cuda())
+    assert torch.equal(y1, y2)  # ... but the inference path takes no masks

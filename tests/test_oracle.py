@@ -155,7 +155,17 @@ def test_oracle_backward_matches_reference_gradients(name):
     else:
         P = synth.swinir_weights(cfg, c["wseed"])
         Q = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
-        loss = F.l1_loss(O.swinir_forward(Q, x, cfg, training=True), tgt)
+        drop = None
+        if c["arch"] == "swinir_dp":  # the drop-in module draws the masks from torch's generator exactly as the reference does
+            from studiosr_b200.models import SwinIR
+
+            kw = {k: cfg[k] for k in ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size",
+                                      "mlp_ratio", "upsampler")}
+            mod = SwinIR(drop_path_rate=c["drop_path_rate"], **kw)  # (construction consumes the generator: seed afterwards)
+            torch.manual_seed(c["drop_seed"])
+            drop = mod._draw_drop_path(shape[0], torch.device("cpu"))
+            assert (drop == 0).any() and (drop > 1).any()
+        loss = F.l1_loss(O.swinir_forward(Q, x, cfg, training=True, drop_scale=drop), tgt)
     loss.backward()
     assert abs(loss.item() - float(gold["loss"][0])) < 1e-5
     checked = 0
