@@ -64,8 +64,27 @@ class _NativeTrainStep(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class _NativeForwardOnly(torch.autograd.Function):
+    """Differentiable-looking forward for the modes whose backward kernels are not built (fp32 / tf32 contractions, HAT,
+    RCAN): the forward runs natively (so the reference's own shape tests, which call the model in train mode with grad
+    enabled, pass unchanged), a backward through it fails loudly instead of returning something else."""
+
+    @staticmethod
+    def forward(ctx, x, model, precision, pad_mode, *params):
+        ctx.why = f"{type(model).__name__} in '{precision}' mode"
+        return model._native(x.device, precision).forward(x, model.scale, pad_mode)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError(
+            f"studiosr_b200: no backward kernels for {ctx.why}; the training path covers EDSR and SwinIR under the Trainer's "
+            "bf16 autocast (trainer.py:69,80) -- run under torch.autocast('cuda', dtype=torch.bfloat16) or set "
+            "model.precision = 'bf16'")
+
+
 class Model(nn.Module):
     ARCH = -1
+    TRAINABLE = False  # True for the model families whose backward is built (EDSR, SwinIR)
 
     def __init__(self, scale: int = 4, n_colors: int = 3, img_range: float = 1.0) -> None:
         super().__init__()
@@ -115,12 +134,14 @@ class Model(nn.Module):
             return self._train_forward(x, precision)
         return self._native(x.device, precision).forward(x, self.scale, self._pad_mode())
 
+    def _trainable(self) -> bool:
+        return self.TRAINABLE
+
     def _train_forward(self, x: torch.Tensor, precision: str) -> torch.Tensor:
         """Differentiable forward (the Trainer's `model(x)`, trainer.py:101-102)."""
-        if precision != "bf16":
-            raise NotImplementedError(
-                "studiosr_b200: the backward kernels are built for the bf16 tensor-core precision (the Trainer's default "
-                "`torch.autocast(dtype=torch.bfloat16)`, trainer.py:69,80); run under bf16 autocast or set model.precision = 'bf16'")
+        if precision != "bf16" or not self._trainable() or x.requires_grad:
+            params = [p for p in self.parameters() if p.requires_grad]
+            return _NativeForwardOnly.apply(x, self, precision, self._pad_mode(), *params)
         named = {k: v for k, v in self.state_dict(keep_vars=True).items() if v.is_floating_point()}
         dev = torch.device(x.device)
         key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), precision, "train")

@@ -11,6 +11,7 @@ from .common import MeanShift, Model, ResBlock, Upsampler, conv2d
 
 class EDSR(Model):
     ARCH = _lib.SSR_ARCH_EDSR
+    TRAINABLE = True
 
     def __init__(self, scale: int = 4, n_colors: int = 3, img_range: float = 1.0, n_feats: int = 256,
                  n_resblocks: int = 32, res_scale: float = 0.1) -> None:

@@ -64,6 +64,7 @@ class RSTB(nn.Module):
 
 class SwinIR(Model):
     ARCH = _lib.SSR_ARCH_SWINIR
+    TRAINABLE = True
 
     def __init__(
         self,
@@ -123,6 +124,9 @@ class SwinIR(Model):
         elif isinstance(m, nn.LayerNorm):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
+
+    def _trainable(self) -> bool:
+        return self.upsampler == "pixelshuffle" and self.window_size == 8  # what train.cu's bind_swinir accepts
 
     def _draw_drop_path(self, batch: int, device):
         """Per-sample stochastic-depth factors of one training step, [2 * n_blocks, B]: row 2k / 2k+1 scales the attention /
