@@ -381,8 +381,8 @@ static size_t pack_raw(ssr_model* m, const std::string& name, size_t numel);
 
 // qkv / proj / fc1 / fc2 of one attention block in the padded-head layout of the un-fused GEMM path, plus the
 // relative-position bias table transposed to [heads][nbias] (shared by SwinIR's un-fused path and HAT)
-static int pack_attn_mlp(ssr_model* m, const std::string& pa, const std::string& pm, const std::string& ptab, const Layer& L,
-                         int nbias, Block* B) {
+static int pack_attn_mlp(ssr_model* m, const std::string& pa, const std::string& pm, const std::string& ptab, const std::string& pn2,
+                         const Layer& L, int nbias, Block* B) {
   const int C = m->C, HID = m->HID, heads = L.heads, d = L.d, DP = L.DP, QP = L.QP;
   const float qscale = 1.0f / sqrtf((float)d);
   auto qkv_row = [=](int n) {
@@ -401,6 +401,7 @@ static int pack_attn_mlp(ssr_model* m, const std::string& pa, const std::string&
   SSR_TRY(pack_linear(m, pa + ".proj", C, C, m->CP, QP, ident_c, proj_col, one, &B->proj));
   auto ident_h = [=](int k) { return k < HID ? k : -1; };
   SSR_TRY(pack_linear(m, pm + ".fc1", HID, C, m->HP, m->CP, ident_h, ident_c, one, &B->fc1));
+  if (fused_tail(m, L)) SSR_TRY(fold_norm_into_linear(m, pn2, pm + ".fc1", HID, C, m->CP, B->fc1));  // k_swin_tail.cu applies no LN2 affine
   SSR_TRY(pack_linear(m, pm + ".fc2", C, HID, m->CP, m->HP, ident_c, ident_h, one, &B->fc2));
   const std::vector<float>* T = find_param(m, ptab, (size_t)nbias * heads);
   if (!T) return SSR_E_STATE;
@@ -445,7 +446,8 @@ static int finalize_hat(ssr_model* m) {  // hat.py:388-470
       const std::string p(pre);
       SSR_TRY(pack_ln(m, p + ".norm1", C, m->CP, &B.norm1));
       SSR_TRY(pack_ln(m, p + ".norm2", C, m->CP, &B.norm2));
-      SSR_TRY(pack_attn_mlp(m, p + ".attn", p + ".mlp", p + ".attn.relative_position_bias_table", L, (2 * ws - 1) * (2 * ws - 1), &B));
+      SSR_TRY(pack_attn_mlp(m, p + ".attn", p + ".mlp", p + ".attn.relative_position_bias_table", p + ".norm2", L,
+                            (2 * ws - 1) * (2 * ws - 1), &B));
       SSR_TRY(pack_conv(m, p + ".conv_block.cab.0", Cc, C, 0, &B.cab0));
       SSR_TRY(pack_conv(m, p + ".conv_block.cab.2", C, Cc, 0, &B.cab2));
       B.ca_w1 = pack_raw(m, p + ".conv_block.cab.3.attention.1.weight", (size_t)R * C);
@@ -459,7 +461,8 @@ static int finalize_hat(ssr_model* m) {  // hat.py:388-470
     const std::string po(pre);
     SSR_TRY(pack_ln(m, po + ".norm1", C, m->CP, &L.ocab.norm1));
     SSR_TRY(pack_ln(m, po + ".norm2", C, m->CP, &L.ocab.norm2));
-    SSR_TRY(pack_attn_mlp(m, po, po + ".mlp", po + ".relative_position_bias_table", L, (ws + wse - 1) * (ws + wse - 1), &L.ocab));
+    SSR_TRY(pack_attn_mlp(m, po, po + ".mlp", po + ".relative_position_bias_table", po + ".norm2", L, (ws + wse - 1) * (ws + wse - 1),
+                          &L.ocab));
     snprintf(pre, sizeof(pre), "layers.%d.conv", li);
     SSR_TRY(pack_conv(m, pre, C, C, 0, &L.conv));
     m->layers.push_back(L);
@@ -1169,6 +1172,7 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
   for (int li = 0; li < nL; ++li) {
     const Layer& L = m->layers[li];
     const int depth = (int)L.blocks.size();
+    const bool fused = fused_tail(m, L);  // same predicate finalize_hat used to fold norm2 into fc1
     for (int bi = 0; bi < depth; ++bi) {  // HAB (hat.py:154-195); xn = norm1(x) on entry
       const Block& blk = L.blocks[bi];
       const float* shortcut = bi == 0 ? W.g : W.t;
@@ -1198,24 +1202,40 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
           SSR_TRY(launch_attn_flash(a, 0, s));  // bf16: mma.sync tiles with an online softmax over key chunks
         else
           SSR_TRY(launch_attn_simt(a, s));
-        GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
-        gp.res = shortcut;
-        gp.ldres = CP;
-        gp.out_f32 = W.t;
-        gp.ld_f32 = CP;
-        SSR_TRY(run_gemm(m, gp, s));
+        if (!fused) {
+          GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
+          gp.res = shortcut;
+          gp.ldres = CP;
+          gp.out_f32 = W.t;
+          gp.ld_f32 = CP;
+          SSR_TRY(run_gemm(m, gp, s));
+        }
       }
-      {  // x = shortcut + attn + conv_scale * (t2 * sigmoid-gate(mean t2))  (hat.py:188, :25-38)
+      {  // x = shortcut + attn + conv_scale * (t2 * sigmoid-gate(mean t2))  (hat.py:188, :25-38); in the fused path the
+         // channel-attention term joins the shortcut first and the projection is part of the tail kernel
         CaArgs ca;
         memset(&ca, 0, sizeof(ca));
-        ca.t = W.t2; ca.res = W.t; ca.ld = CP; ca.B = B; ca.HW = Hp * Wp; ca.C = m->C; ca.CP = CP; ca.R = R;
+        ca.t = W.t2; ca.res = fused ? shortcut : W.t; ca.ld = CP; ca.B = B; ca.HW = Hp * Wp; ca.C = m->C; ca.CP = CP; ca.R = R;
         ca.W1 = m->dev<float>(blk.ca_w1); ca.b1 = m->dev<float>(blk.ca_b1);
         ca.W2 = m->dev<float>(blk.ca_w2); ca.b2 = m->dev<float>(blk.ca_b2);
         ca.partial = W.partial; ca.nsplit = W.nsplit;
         ca.out_f32 = W.t; ca.out_T = nullptr; ca.elem = e; ca.round_tf32 = rtf; ca.scale = c.conv_scale;
         SSR_TRY(launch_channel_attention(ca, s));
       }
-      SSR_TRY(mlp(blk, false, bi + 1 < depth ? &L.blocks[bi + 1].norm1 : &L.ocab.norm1));
+      const LNp* next = bi + 1 < depth ? &L.blocks[bi + 1].norm1 : &L.ocab.norm1;
+      if (fused) {  // proj + residual + LN2 + fc1 + GELU + fc2 + residual + next norm1 in ONE kernel (k_swin_tail.cu)
+        MlpFusedArgs f;
+        memset(&f, 0, sizeof(f));
+        f.o = W.o; f.ld_o = L.QP; f.M = T; f.C = m->C; f.Hid = m->HID; f.CP = CP; f.HP = m->HP; f.QP = L.QP;
+        f.Wp = m->arena + blk.proj.w_off; f.W1 = m->arena + blk.fc1.w_off; f.W2 = m->arena + blk.fc2.w_off;
+        f.bp = m->dev<float>(blk.proj.b_off); f.b1 = m->dev<float>(blk.fc1.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
+        f.res = W.t; f.ldres = CP; f.eps = 1e-5f;
+        f.out_f32 = W.t; f.ld_f32 = CP; f.out_ln = W.xn; f.ld_ln = CP;
+        f.g3 = m->dev<float>(next->g_off); f.be3 = m->dev<float>(next->b_off);
+        SSR_TRY(launch_mlp_fused(f, s));
+      } else {
+        SSR_TRY(mlp(blk, false, next));
+      }
     }
     {  // OCAB (hat.py:240-293); xn = ocab.norm1(x) on entry
       const Block& blk = L.ocab;
@@ -1232,14 +1252,25 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
         SSR_TRY(launch_attn_flash(a, 1, s));  // bf16: mma.sync tiles with an online softmax over key chunks
       else
         SSR_TRY(launch_attn_oca(a, s));
-      GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
-      gp.res = W.t;
-      gp.ldres = CP;
-      gp.out_f32 = W.t;
-      gp.ld_f32 = CP;
-      set_ln(m, gp, blk.norm2, W.xn, CP);
-      SSR_TRY(run_gemm(m, gp, s));
-      SSR_TRY(mlp(blk, true, nullptr));
+      if (fused) {
+        MlpFusedArgs f;
+        memset(&f, 0, sizeof(f));
+        f.o = W.o; f.ld_o = L.QP; f.M = T; f.C = m->C; f.Hid = m->HID; f.CP = CP; f.HP = m->HP; f.QP = L.QP;
+        f.Wp = m->arena + blk.proj.w_off; f.W1 = m->arena + blk.fc1.w_off; f.W2 = m->arena + blk.fc2.w_off;
+        f.bp = m->dev<float>(blk.proj.b_off); f.b1 = m->dev<float>(blk.fc1.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
+        f.res = W.t; f.ldres = CP; f.eps = 1e-5f;
+        f.out_T = W.tb; f.ld_T = CP;
+        SSR_TRY(launch_mlp_fused(f, s));
+      } else {
+        GemmArgs gp = gemm_base(m, blk.proj, W.o, L.QP, B, Hp, Wp);
+        gp.res = W.t;
+        gp.ldres = CP;
+        gp.out_f32 = W.t;
+        gp.ld_f32 = CP;
+        set_ln(m, gp, blk.norm2, W.xn, CP);
+        SSR_TRY(run_gemm(m, gp, s));
+        SSR_TRY(mlp(blk, true, nullptr));
+      }
     }
     {  // group conv + group residual (hat.py:385); epilogue = next group's first norm1 or the final norm
       GemmArgs g = gemm_base(m, L.conv, W.tb, CP, B, Hp, Wp);
