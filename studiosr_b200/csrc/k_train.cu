@@ -302,7 +302,7 @@ int launch_transpose_table(const float* table, float* out, int nb, int heads, cu
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward, one warp per row (rows strided over all warps so dgamma / dbeta partials live in registers):
 //   xhat = (x - mean) rstd;  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
-__global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float red[2][8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = blockIdx.x * 8 + wib, nwarps = gridDim.x * 8;

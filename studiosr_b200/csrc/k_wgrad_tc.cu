@@ -225,8 +225,9 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t s) {
     }
   }
   const int tiles = geo.m_blocks * a.taps * geo.n_blocks;
+  // one CTA per SM is resident (192 KB of operand stages): aim at exactly two full waves, never a third partial one
   const int target = 2 * num_sms_cached();
-  geo.splits = (target + tiles - 1) / tiles;
+  geo.splits = target / tiles;
   if (geo.splits > geo.n_chunks) geo.splits = geo.n_chunks;
   if (geo.splits < 1) geo.splits = 1;
   static bool attr_set = false;
