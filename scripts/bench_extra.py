@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Secondary benchmark lines (not the driver's headline): BASELINE.json configs 2, 3 and 4.
 
+  python scripts/bench_extra.py --workload cfg1   # SwinIR-x4 single 64x64 image latency (bf16)
   python scripts/bench_extra.py --workload cfg2   # EDSR-x4 fwd+bwd, 16 x 3x48x48, bf16 autocast, L1 loss (+ Adam step)
   python scripts/bench_extra.py --workload cfg3   # HAT-x4 bf16 inference, batch 32 of 64x64 LR tiles
   python scripts/bench_extra.py --workload cfg4   # SwinIR-x4 Trainer step, 32 x 3x64x64 per GPU (torchrun: DDP)
@@ -18,7 +19,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-optimizer", action="store_true")
@@ -35,6 +36,10 @@ def main():
         model, B, H, W = EDSR(scale=4), 16, 48, 48
         step_flops = 16 * 694.66e9  # fwd+bwd per 48x48 patch
         name = "EDSR-x4 forward+backward (+Adam), batch 16 of 48x48 LR patches, bf16 autocast, L1 loss"
+    elif args.workload == "cfg1":
+        model, B, H, W = SwinIR(scale=4), 1, 64, 64
+        step_flops = 135.56e9  # one 64x64 image, padded to 72x72 by the eval forward
+        name = "SwinIR-x4 inference latency, one 3x64x64 LR image (BASELINE config 1, the reference's CPU-runnable case), bf16"
     elif args.workload == "cfg3":
         model, B, H, W = HAT(scale=4), 32, 64, 64
         step_flops = 32 * 207.76e9  # forward per 64x64 tile
@@ -45,7 +50,7 @@ def main():
         name = "SwinIR-x4 Trainer step, batch 32 of 64x64 LR patches per GPU, bf16 autocast, L1 loss"
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    infer = args.workload == "cfg3"
+    infer = args.workload in ("cfg1", "cfg3")
     model = model.cuda().eval() if infer else model.cuda().train()
     if infer:
         model.precision = "bf16"

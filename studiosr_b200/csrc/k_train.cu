@@ -17,26 +17,37 @@ __device__ __forceinline__ int ps_src_row(int n, int Cout, int ps_r) {
 
 // W fp32 [Cout][Cin][taps] -> Wf bf16 [NP][taps*KP] (k = tap*KP + c), Wd bf16 [KP][taps*NP] (dgrad: rows = input
 // channel, k' = tap'*NP + n with tap' = taps-1-tap, i.e. the 180-degree rotated kernel), bias -> bf [NP].
-__global__ void pack_conv_dev_kernel(const float* __restrict__ W, const float* __restrict__ b, __nv_bfloat16* Wf, float* bf,
-                                     __nv_bfloat16* Wd, int Cout, int Cin, int NP, int KP, int taps, int ps_r) {
+// Two passes so that BOTH packs are written with consecutive threads on consecutive elements (a single pass left the
+// dgrad pack as 2-byte stores 9*NP*2 bytes apart: 5M scattered sector writes per 256x256 conv).
+__global__ void pack_conv_fwd_kernel(const float* __restrict__ W, const float* __restrict__ b, __nv_bfloat16* Wf, float* bf, int Cout,
+                                     int Cin, int KP, int taps, int ps_r) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * Cin) return;
-  const int n = idx / Cin, c = idx - n * Cin;
+  const int n = idx / Cin, c = idx - n * Cin;  // c fastest: Wf[n][t*KP + c]
   const int sn = ps_src_row(n, Cout, ps_r);
   const float* src = W + ((size_t)sn * Cin + c) * taps;
-  for (int t = 0; t < taps; ++t) {
-    const __nv_bfloat16 v = __float2bfloat16_rn(src[t]);
-    if (Wf) Wf[(size_t)n * taps * KP + (size_t)t * KP + c] = v;
-    if (Wd) Wd[(size_t)c * taps * NP + (size_t)(taps - 1 - t) * NP + n] = v;
-  }
+  for (int t = 0; t < taps; ++t) Wf[(size_t)n * taps * KP + (size_t)t * KP + c] = __float2bfloat16_rn(src[t]);
   if (c == 0 && bf && b) bf[n] = b[sn];
+}
+__global__ void pack_conv_dg_kernel(const float* __restrict__ W, __nv_bfloat16* Wd, int Cout, int Cin, int NP, int taps, int ps_r) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * Cin) return;
+  const int c = idx / Cout, n = idx - c * Cout;  // n fastest: Wd[c][t'*NP + n]
+  const int sn = ps_src_row(n, Cout, ps_r);
+  const float* src = W + ((size_t)sn * Cin + c) * taps;
+  for (int t = 0; t < taps; ++t) Wd[(size_t)c * taps * NP + (size_t)(taps - 1 - t) * NP + n] = __float2bfloat16_rn(src[t]);
 }
 int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int Cout, int Cin, int NP, int KP,
                          int taps, int ps_r, cudaStream_t s) {
   const int total = Cout * Cin;
-  pack_conv_dev_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, b, (__nv_bfloat16*)Wf, bf, (__nv_bfloat16*)Wd, Cout, Cin, NP, KP,
-                                                           taps, ps_r);
-  count_launch();
+  if (Wf) {
+    pack_conv_fwd_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, b, (__nv_bfloat16*)Wf, bf, Cout, Cin, KP, taps, ps_r);
+    count_launch();
+  }
+  if (Wd) {
+    pack_conv_dg_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, (__nv_bfloat16*)Wd, Cout, Cin, NP, taps, ps_r);
+    count_launch();
+  }
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;
 }
@@ -227,22 +238,32 @@ __device__ __forceinline__ void lin_map(const LinMap& m, int n, int k, int* np, 
 
 // W fp32 [N][K] -> Wf bf16 [NP][KP] (forward), Wd bf16 [KP][NP] (dgrad: dX = dY Wd^T ... rows = input feature), bias
 __global__ void pack_linear_dev_kernel(const float* __restrict__ W, const float* __restrict__ b, __nv_bfloat16* Wf, float* bf,
-                                       __nv_bfloat16* Wd, int N, int K, int NP, int KP, const LinMap map) {
+                                       __nv_bfloat16* Wd, int N, int K, int NP, int KP, const LinMap map, int transposed) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * K) return;
-  const int n = idx / K, k = idx - n * K;
+  // pass 0 writes Wf with k fastest, pass 1 writes Wd with n fastest: both store streams are coalesced
+  const int n = transposed ? idx % N : idx / K, k = transposed ? idx / N : idx % K;
   int np, kp;
   float sc;
   lin_map(map, n, k, &np, &kp, &sc);
-  const __nv_bfloat16 v = __float2bfloat16_rn(W[idx] * sc);
-  if (Wf) Wf[(size_t)np * KP + kp] = v;
-  if (Wd) Wd[(size_t)kp * NP + np] = v;
-  if (k == 0 && bf && b) bf[np] = b[n] * sc;
+  const __nv_bfloat16 v = __float2bfloat16_rn(W[(size_t)n * K + k] * sc);
+  if (!transposed) {
+    Wf[(size_t)np * KP + kp] = v;
+    if (k == 0 && bf && b) bf[np] = b[n] * sc;
+  } else {
+    Wd[(size_t)kp * NP + np] = v;
+  }
 }
 int launch_pack_linear_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int N, int K, int NP, int KP,
                            const LinMap& map, cudaStream_t s) {
-  pack_linear_dev_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(W, b, (__nv_bfloat16*)Wf, bf, (__nv_bfloat16*)Wd, N, K, NP, KP, map);
-  count_launch();
+  if (Wf) {
+    pack_linear_dev_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(W, b, (__nv_bfloat16*)Wf, bf, nullptr, N, K, NP, KP, map, 0);
+    count_launch();
+  }
+  if (Wd) {
+    pack_linear_dev_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(W, b, nullptr, nullptr, (__nv_bfloat16*)Wd, N, K, NP, KP, map, 1);
+    count_launch();
+  }
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;
 }

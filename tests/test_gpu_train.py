@@ -85,6 +85,8 @@ def _edsr_case(cfg, B, H, W, wseed, xseed):
     ("x2", dict(synth.EDSR_TINY, scale=2, n_resblocks=2), 1, 16, 16),
     ("x3", dict(synth.EDSR_TINY, scale=3, n_resblocks=1), 1, 12, 16),
     ("wide", dict(synth.EDSR_DEFAULT, n_resblocks=4), 2, 48, 48),  # cfg2 width and patch size, fewer blocks
+    ("ragged", synth.EDSR_TINY, 3, 13, 9),                          # odd sizes: TMA boxes clip at the image edge
+    ("single-pixel-rows", dict(synth.EDSR_TINY, n_resblocks=1), 1, 1, 7),
 ])
 def test_edsr_backward(name, cfg, B, H, W):
     model, Pr, Pa, loss, loss_ref = _edsr_case(cfg, B, H, W, 5, 77)
@@ -160,6 +162,7 @@ def _swin_case(cfg, B, H, W, wseed, xseed):
     ("tiny-reflect-pad", dict(synth.SWINIR_TINY), 1, 20, 28),                       # padded to 24x32 (common.py:277-282)
     ("c180", dict(embed_dim=180, depths=[2, 2], num_heads=[6, 6], scale=4), 1, 16, 16),  # the 180 / 6-head class (cfg4 widths)
     ("x2", dict(synth.SWINIR_TINY, scale=2), 1, 16, 16),
+    ("x3-batch3", dict(synth.SWINIR_TINY, scale=3, depths=[3], num_heads=[6]), 3, 8, 16),  # odd depth (last block shifted), PS3
 ])
 def test_swinir_backward(name, over, B, H, W):
     cfg = synth.swinir_config(**over)
@@ -301,3 +304,26 @@ def test_swinir_drop_path_training_step():
     with torch.inference_mode():
         y1, y2 = model(x.cuda()), model(x.cuda())
     assert torch.equal(y1, y2)  # ... but the inference path takes no masks
+
+
+def test_training_modes_without_backward_fail_loudly():
+    """fp32-mode training, HAT / RCAN training and dL/dx are not built: the forward still runs (the reference's own shape
+    tests call the model in train mode), the backward raises instead of returning something else."""
+    from studiosr_b200.models import EDSR, RCAN
+
+    x = synth.image_batch((1, 3, 8, 8), 3).cuda()
+    m = EDSR(**synth.EDSR_TINY).cuda().train()
+    y = m(x)  # fp32 mode (no autocast)
+    assert y.shape == (1, 3, 32, 32) and y.requires_grad
+    with pytest.raises(NotImplementedError, match="no backward kernels"):
+        y.sum().backward()
+    xr = x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(xr)
+    with pytest.raises(NotImplementedError):
+        y.sum().backward()
+    r = RCAN(scale=2, n_feats=64, n_resblocks=1, n_resgroups=1, reduction=16).cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = r(x)
+    with pytest.raises(NotImplementedError, match="no backward kernels"):
+        y.sum().backward()
