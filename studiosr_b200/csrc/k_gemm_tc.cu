@@ -283,8 +283,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[4 * q + 2] += bv.z;
           v[4 * q + 3] += bv.w;
         }
-        if (g.out_pre) store_T(v, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
-        epilogue_act(v, g.act, g.slope, g.alpha);
+        if (g.out_pre && g.pre_mode == 1) {  // GELU and its derivative in one pass (training forward of fc1)
+          float gp[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = v[i], ax = fabsf(x) * 0.70710678118654752440f;
+            float t, e;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));  // exp(-x^2 / 2)
+            float p = fmaf(1.061405429f, t, -1.453152027f);
+            p = fmaf(p, t, 1.421413741f);
+            p = fmaf(p, t, -0.284496736f);
+            p = fmaf(p, t, 0.254829592f);
+            const float cdf = 0.5f * (1.0f + copysignf(fmaf(-p * t, e, 1.0f), x));
+            gp[i] = fmaf(x * 0.3989422804014327f, e, cdf);
+            v[i] = x * cdf * g.alpha;
+          }
+          store_T(gp, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
+        } else {
+          if (g.out_pre) store_T(v, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
+          epilogue_act(v, g.act, g.slope, g.alpha);
+        }
         if (g.mask) {  // activation backward (training dgrad): gate by the sign of the saved forward output
           float mk[32];
           if (m >= 0) {
@@ -311,7 +330,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (c + 1 < BLOCK_N / 32) mask_fetch(nb + 32);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              if (g.mask_mode == 1) {  // d/du [u Phi(u)] = Phi(u) + u phi(u)
+              if (g.mask_mode == 2) {
+                v[i] *= mk[i];
+              } else if (g.mask_mode == 1) {  // d/du [u Phi(u)] = Phi(u) + u phi(u)
                 const float u = mk[i];
                 const float cdf = 0.5f * (1.0f + fast_erf(u * 0.70710678118654752440f));
                 v[i] *= fmaf(u * 0.3989422804014327f, __expf(-0.5f * u * u), cdf);

@@ -121,14 +121,34 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
     partial[(size_t)blockIdx.x * NP + n] = t;
   }
 }
+// second stage of the two-stage reductions: 32 columns x 8 strip lanes per CTA, 4 independent accumulators per thread so
+// that 32 strip loads are in flight per column (one thread walking 592 strips serially took 42 us per launch)
+__device__ __forceinline__ float strip_sum(const float* __restrict__ col, int strips, size_t stride, float (*red)[33]) {
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  int b = threadIdx.y;
+  for (; b + 24 < strips; b += 32) {
+    a0 += col[(size_t)b * stride];
+    a1 += col[(size_t)(b + 8) * stride];
+    a2 += col[(size_t)(b + 16) * stride];
+    a3 += col[(size_t)(b + 24) * stride];
+  }
+  for (; b < strips; b += 8) a0 += col[(size_t)b * stride];
+  red[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  float t = 0.0f;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+  }
+  return t;
+}
 // bias gradient of a conv: out[sn(n)] = alpha * sum_m dY[m][n]
-__global__ void colsum_final_conv_kernel(const float* __restrict__ partial, int strips, int NP, int Cout, int ps_r, float alpha,
-                                         float* out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= Cout) return;
-  float acc = 0.0f;
-  for (int b = 0; b < strips; ++b) acc += partial[(size_t)b * NP + n];
-  out[ps_src_row(n, Cout, ps_r)] = acc * alpha;
+__global__ void __launch_bounds__(256) colsum_final_conv_kernel(const float* __restrict__ partial, int strips, int NP, int Cout,
+                                                                int ps_r, float alpha, float* out) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const float t = strip_sum(partial + min(n, NP - 1), strips, (size_t)NP, red);
+  if (threadIdx.y == 0 && n < Cout) out[ps_src_row(n, Cout, ps_r)] = t * alpha;
 }
 static int colsum_stage1(const void* dY, int elem, int ld, int M, int NP, float* partial, int* strips, cudaStream_t s) {
   SSR_CHECK(elem == 2 && NP % 8 == 0 && ld % 8 == 0 && NP <= 2304, SSR_E_INVALID, "colsum: bf16 rows with NP %% 8 == 0 (NP=%d ld=%d)", NP, ld);
@@ -147,7 +167,7 @@ int launch_colsum(const void* dY, int elem, int ld, int M, int NP, int Cout, int
                   cudaStream_t s) {
   int strips;
   SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, partial, &strips, s));
-  colsum_final_conv_kernel<<<(Cout + 127) / 128, 128, 0, s>>>(partial, strips, NP, Cout, ps_r, alpha, out);
+  colsum_final_conv_kernel<<<(Cout + 31) / 32, dim3(32, 8), 0, s>>>(partial, strips, NP, Cout, ps_r, alpha, out);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;
@@ -286,21 +306,21 @@ int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int K
 }
 
 // bias gradient of a linear layer: out[n] = scale(n) * sum_m dY[m][np(n)]  (NP = packed width of dY)
-__global__ void colsum_final_map_kernel(const float* __restrict__ partial, int strips, int NP, int N, const LinMap map, float* out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  int np, kp;
-  float sc;
-  lin_map(map, n, 0, &np, &kp, &sc);
-  float acc = 0.0f;
-  for (int b = 0; b < strips; ++b) acc += partial[(size_t)b * NP + np];
-  out[n] = acc * sc;
+__global__ void __launch_bounds__(256) colsum_final_map_kernel(const float* __restrict__ partial, int strips, int NP, int N,
+                                                               const LinMap map, float* out) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  int np = 0, kp;
+  float sc = 0.0f;
+  if (n < N) lin_map(map, n, 0, &np, &kp, &sc);
+  const float t = strip_sum(partial + np, strips, (size_t)NP, red);
+  if (threadIdx.y == 0 && n < N) out[n] = t * sc;
 }
 int launch_colsum_map(const void* dY, int elem, int ld, int M, int NP, int N, const LinMap& map, float* out, float* partial,
                       cudaStream_t s) {
   int strips;
   SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, partial, &strips, s));
-  colsum_final_map_kernel<<<(N + 127) / 128, 128, 0, s>>>(partial, strips, NP, N, map, out);
+  colsum_final_map_kernel<<<(N + 31) / 32, dim3(32, 8), 0, s>>>(partial, strips, NP, N, map, out);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;
@@ -405,6 +425,11 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs a) {
     if (lane < Q) o4[lane] = make_float4(dx[0], dx[1], dx[2], dx[3]);
     if (has1) o4[lane + 32] = make_float4(dx[4], dx[5], dx[6], dx[7]);
     if (a.Gb) {
+      if (a.gb_scale) {
+        const float sc = __ldg(a.gb_scale + row / a.rows_per_scale);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] *= sc;
+      }
       uint2* b2 = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.Gb) + (size_t)row * a.ldg);
       if (lane < Q) b2[lane] = make_uint2(pack_bf16x2(dx[0], dx[1]), pack_bf16x2(dx[2], dx[3]));
       if (has1) b2[lane + 32] = make_uint2(pack_bf16x2(dx[4], dx[5]), pack_bf16x2(dx[6], dx[7]));
@@ -429,13 +454,13 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs a) {
     a.partial[((size_t)blockIdx.x * 2 + 1) * a.C + n] = b;
   }
 }
-__global__ void ln_bwd_final_kernel(const float* __restrict__ partial, int blocks, int C, float* dgamma, float* dbeta) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= 2 * C) return;
-  const int which = n / C, c = n - which * C;
-  float acc = 0.0f;
-  for (int b = 0; b < blocks; ++b) acc += partial[((size_t)b * 2 + which) * C + c];
-  (which ? dbeta : dgamma)[c] = acc;
+__global__ void __launch_bounds__(256) ln_bwd_final_kernel(const float* __restrict__ partial, int blocks, int C, float* dgamma,
+                                                           float* dbeta) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;  // n in [0, 2C): dgamma columns, then dbeta columns
+  const int which = n >= C ? 1 : 0, c = min(n - which * C, C - 1);
+  const float t = strip_sum(partial + (size_t)which * C + c, blocks, (size_t)2 * C, red);
+  if (threadIdx.y == 0 && n < 2 * C) (which ? dbeta : dgamma)[c] = t;
 }
 int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s) {
   SSR_CHECK(a.C <= 256 && a.CP <= 256 && a.CP % 4 == 0 && a.ldx % 4 == 0 && a.ldg % 4 == 0 && a.ld_dy % 4 == 0, SSR_E_INVALID,
@@ -447,7 +472,7 @@ int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s) {
   count_launch();
   SSR_CUDA(cudaGetLastError());
   if (a.dgamma) {
-    ln_bwd_final_kernel<<<(2 * a.C + 127) / 128, 128, 0, s>>>(a.partial, blocks, a.C, a.dgamma, a.dbeta);
+    ln_bwd_final_kernel<<<(2 * a.C + 31) / 32, dim3(32, 8), 0, s>>>(a.partial, blocks, a.C, a.dgamma, a.dbeta);
     count_launch();
     SSR_CUDA(cudaGetLastError());
   }

@@ -93,12 +93,15 @@ struct GemmArgs {
   // backward of an activation folded into a dgrad epilogue (tensor-core path only): after alpha,
   //   v = mask[m][n] > 0 ? v : v * mask_slope     (ReLU: slope 0 with mask = the forward OUTPUT; LeakyReLU likewise)
   // mask_mode 1 (GELU backward): v *= gelu'(mask[m][n]) with mask = the saved PRE-activation
+  // mask_mode 2: v *= mask[m][n] (mask = the activation's derivative, saved by the forward with pre_mode 1)
   const void* mask;  // T [M][ld_mask] or null
   int ld_mask;
   float mask_slope;
   int mask_mode;
   void* out_pre;  // T [M][ld_pre]: copy of (acc + bias) BEFORE the activation (kept for the backward), or null
   int ld_pre;
+  int pre_mode;   // 0: out_pre = pre-activation u; 1 (act == GELU only): out_pre = gelu'(u) = Phi(u) + u phi(u), which shares the
+                  // exponential of the erf evaluation, so the backward's epilogue is one multiply
   // stochastic depth (timm DropPath, swinir.py:137,171-172): v *= row_scale[m / rows_per_scale] before the residual add
   const float* row_scale;  // [ceil(M / rows_per_scale)] or null (tensor-core path only)
   int rows_per_scale;
@@ -285,6 +288,8 @@ struct LnBwdArgs {
   const float* Gin;    // fp32 [M][ldg] residual-stream gradient to add, or null
   float* Gout;         // fp32 [M][ldg]
   void* Gb;            // bf16 copy of Gout [M][ldg], or null
+  const float* gb_scale;  // optional per-sample factor of the bf16 copy only (stochastic depth of the next branch): [M / rows_per_scale]
+  int rows_per_scale;
   int ldg;
   int M, C, CP;
   float eps;

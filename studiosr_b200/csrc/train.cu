@@ -761,8 +761,9 @@ static int train_forward_swinir(ssr_model* m, const float* const* params, const 
       {
         GemmArgs g = gemm_base(m, blk.fc1, bw.xn2, CP, B, Hp, Wp);
         g.act = ACT_GELU;
-        g.out_pre = bw.u;
+        g.out_pre = bw.u;  // holds gelu'(u), not u: the dgrad of fc2 only multiplies by it
         g.ld_pre = HP;
+        g.pre_mode = 1;
         g.out_T = bw.h;
         g.ld_T = HP;
         SSR_TRY(run_gemm(m, g, s));
@@ -891,7 +892,8 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
   return SSR_OK;
 }
 static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, const void* dy, int elem_dy, const float* Gin, float* Gout,
-                       void* Gb, int M, int C, int CP, float* partial, float* const* grads, cudaStream_t s) {
+                       void* Gb, int M, int C, int CP, float* partial, float* const* grads, cudaStream_t s,
+                       const float* gb_scale = nullptr, int rows_per_scale = 1) {
   LnBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x;
@@ -909,6 +911,8 @@ static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, con
   a.CP = CP;
   a.eps = 1e-5f;
   a.partial = partial;
+  a.gb_scale = gb_scale;
+  a.rows_per_scale = rows_per_scale;
   if (grads[l.gi] && grads[l.bi]) {
     a.dgamma = grads[l.gi];
     a.dbeta = grads[l.bi];
@@ -1005,13 +1009,15 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
       const SwinBlockWs& bw = W.blk[li][bi];
       // ---- MLP: t_out = t_mid + fc2(GELU(fc1(LN2(t_mid))))  (swinir.py:172, common.py:184-194) ----
       // with stochastic depth the branch sees dL/dt_out scaled per sample: Gtb = bf16(Gt * drop[2k+1][b])
-      if (drop) SSR_TRY(launch_scale_to_bf16(W.Gt, drop + (size_t)(2 * kblk + 1) * B, per_sample, W.Gtb, (size_t)T * CP, s));
+      // (for the other blocks the LN1 backward of the block after this one already wrote the scaled copy)
+      if (drop && bi == depth - 1)
+        SSR_TRY(launch_scale_to_bf16(W.Gt, drop + (size_t)(2 * kblk + 1) * B, per_sample, W.Gtb, (size_t)T * CP, s));
       SSR_TRY(wgrad_lin(m, bt.fc2, W.Gtb, bw.h, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.fc2, W.Gtb, T);
-        g.mask = bw.u;  // GELU backward on the saved pre-activation
+        g.mask = bw.u;  // GELU backward: the forward saved gelu'(u)
         g.ld_mask = m->HP;
-        g.mask_mode = 1;
+        g.mask_mode = 2;
         g.out_T = W.dH;
         g.ld_T = m->HP;
         SSR_TRY(launch_gemm_tc(g, 2, s));
@@ -1023,9 +1029,11 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
         g.ld_T = CP;
         SSR_TRY(launch_gemm_tc(g, 2, s));
       }
-      SSR_TRY(ln_backward(bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
+      // the bf16 copy feeds the attention branch: scaled by its stochastic-depth factor
+      SSR_TRY(ln_backward(bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
+                          drop ? drop + (size_t)(2 * kblk) * B : nullptr, Hp * Wp));
       // ---- attention: t_mid = t_in + proj(W-MSA(LN1(t_in)))  (swinir.py:149-171) ----
-      if (drop) SSR_TRY(launch_scale_to_bf16(W.Gt, drop + (size_t)(2 * kblk) * B, per_sample, W.Gtb, (size_t)T * CP, s));
+
       SSR_TRY(wgrad_lin(m, bt.proj, W.Gtb, bw.o, T, W.dwp, W.partial, grads, s));
       {
         GemmArgs g = dgrad_lin(m, bt.proj, W.Gtb, T);
@@ -1062,7 +1070,9 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
         g.ld_T = CP;
         SSR_TRY(launch_gemm_tc(g, 2, s));
       }
-      SSR_TRY(ln_backward(bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
+      // the bf16 copy feeds the MLP branch of the previous block (unused for the first block of a layer)
+      SSR_TRY(ln_backward(bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
+                          (drop && bi > 0) ? drop + (size_t)(2 * (kblk - 1) + 1) * B : nullptr, Hp * Wp));
     }
     SSR_TRY(launch_add_inplace(W.G, W.Gt, W.Gb, (size_t)T * CP, s));  // blocks' path joins the group skip
   }
