@@ -32,6 +32,11 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_fast(float x) {  // MUFU.EX2 only (exp2f adds range handling around it)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 }  // namespace
 
 template <int DP>
@@ -144,8 +149,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdArgs a) {
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        s[nt][e] = exp2f((s[nt][e] - m0) * LOG2E);
-        s[nt][2 + e] = exp2f((s[nt][2 + e] - m1) * LOG2E);
+        s[nt][e] = ex2_fast((s[nt][e] - m0) * LOG2E);
+        s[nt][2 + e] = ex2_fast((s[nt][2 + e] - m1) * LOG2E);
         l0 += s[nt][e];
         l1 += s[nt][2 + e];
       }

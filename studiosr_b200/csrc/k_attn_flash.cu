@@ -33,6 +33,11 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_fast(float x) {  // MUFU.EX2 only (exp2f adds range handling around it)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 }  // namespace
 
 // oca = 0: keys = the query window itself (roll by `shift`, region mask); oca = 1: keys = kws x kws unfold window
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a, const
       c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1));
       c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
       const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);
-      const float f0 = exp2f((m0 - n0) * LOG2E), f1 = exp2f((m1 - n1) * LOG2E);  // exp2(-inf) = 0 on the first chunk
+      const float f0 = ex2_fast((m0 - n0) * LOG2E), f1 = ex2_fast((m1 - n1) * LOG2E);  // exp2(-inf) = 0 on the first chunk
       m0 = n0;
       m1 = n1;
       float r0 = 0.0f, r1 = 0.0f;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a, const
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float p0 = exp2f(fmaf(s[nt][e], LOG2E, -nb0)), p1 = exp2f(fmaf(s[nt][2 + e], LOG2E, -nb1));
+          const float p0 = ex2_fast(fmaf(s[nt][e], LOG2E, -nb0)), p1 = ex2_fast(fmaf(s[nt][2 + e], LOG2E, -nb1));
           s[nt][e] = p0;
           s[nt][2 + e] = p1;
           r0 += p0;
