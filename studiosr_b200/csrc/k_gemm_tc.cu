@@ -9,12 +9,19 @@
 // warps 2..5 = epilogue (one TMEM lane quadrant each; thread <-> accumulator row).
 // Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
 // epilogue overlaps the other's TMA/MMA main loop.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "ssr_tc.cuh"
 
 namespace ssr {
 
+#ifdef SSR_TC_POLL
+#define TC_ROLE_WAIT mbar_wait_poll
+#else
+#define TC_ROLE_WAIT mbar_wait
+#endif
 
 // ---------------------------------------------------------------------------------------------
 struct TcGeom {
@@ -30,10 +37,20 @@ constexpr int TC_BM = 128;
 constexpr int TC_EPI_WARPS = 8;                      // two groups of 4 (one per TMEM accumulator buffer)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 second TMA producer
 constexpr int TC_MAX_NP = 2304;
+// "Halo" mode of the 3x3 conv (bf16): the 128-pixel tile is an 8 x 16 patch and ONE TMA box of (8+2) x (16+2) pixels x 64
+// channels serves all nine taps -- the tap's A operand is the same shared-memory tile read from a start address shifted by
+// ((dy+1) * 10 + (dx+1)) rows with an 8-row-group stride of 10 rows.  That is legal because the tensor core derives the
+// 128B-swizzle phase from absolute shared-memory address bits, exactly like TMA (measured for every shift / pitch:
+// scripts/micro_halo.cu, profiles/r01_micro_halo_descriptor.txt).  The conv kernels were bound by the SM's shared-memory
+// fill rate (~58-60 B/clk/SM at 40-48 KB per k-block); the halo tile cuts the A-operand fill 6x.
+constexpr int TC_HALO_BW = 8, TC_HALO_BH = 16;
+constexpr int TC_HALO_PITCH = TC_HALO_BW + 2;                                   // pixels per halo row
+constexpr uint32_t TC_HALO_BYTES = (TC_HALO_BH + 2) * TC_HALO_PITCH * 128;      // 23040
+constexpr uint32_t TC_HALO_SLOT = 24576;                                        // 1 KB aligned slot per halo tile
 
 template <int BLOCK_N>
 constexpr int tc_stages() {
-  return BLOCK_N >= 256 ? 3 : 4;  // stage = 16 KB (A) + BLOCK_N*128 B (W)
+  return BLOCK_N >= 256 ? 3 : BLOCK_N <= 64 ? 6 : 4;  // stage = 16 KB (A) + BLOCK_N*128 B (W); small stages need a deeper ring
 }
 template <int BLOCK_N>
 constexpr size_t tc_smem_bytes() {
@@ -42,8 +59,8 @@ constexpr size_t tc_smem_bytes() {
 }
 
 
-template <typename T, int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <typename T, int BLOCK_N, bool kHalo>
+__global__ void __launch_bounds__(TC_THREADS + (kHalo ? 32 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g,
                const TcGeom geo) {
   constexpr bool kTf32 = sizeof(T) == 4;
@@ -65,7 +82,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_beta = s_gamma + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + 256);
   // bars: [0,kStages) full, [kStages,2kStages) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base address
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  // halo mode: + full[2], empty[2] of the two halo-tile slots (they live in the A region of the stage ring)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -73,10 +91,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
+  auto afull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 4 + b); };
+  auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 6 + b); };
+  static_assert(!kHalo || (2 * TC_HALO_SLOT <= kStages * A_BYTES), "two halo tiles must fit the A region of the ring");
 
-  for (int i = threadIdx.x; i < g.NP; i += TC_THREADS) s_bias[i] = __ldg(g.bias + i);
+  for (int i = threadIdx.x; i < g.NP; i += blockDim.x) s_bias[i] = __ldg(g.bias + i);
   if (g.out_ln)
-    for (int i = threadIdx.x; i < g.NP; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < g.NP; i += blockDim.x) {
       s_gamma[i] = __ldg(g.gamma + i);
       s_beta[i] = __ldg(g.beta + i);
     }
@@ -90,6 +111,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 4);  // one arrival per epilogue warp of the group
+      mbar_init(afull_bar(b), 1);
+      mbar_init(aempty_bar(b), 1);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -125,17 +148,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if ((kbg & 1u) != pid) continue;
           const int s = kbg % kStages;
           const uint32_t ph = (kbg / kStages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), A_BYTES + W_BYTES);
-          const int tap = kb / geo.kc_per_tap, kc = kb - tap * geo.kc_per_tap;
+          TC_ROLE_WAIT(empty_bar(s), ph ^ 1u);
           const uint32_t dstA = smem_u32(smA + s * A_BYTES), dstW = smem_u32(smW + s * W_BYTES);
-          if (geo.conv) {
-            const int dy = (g.taps == 9) ? tap / 3 - 1 : 0, dx = (g.taps == 9) ? tap % 3 - 1 : 0;
-            tma_load_4d(dstA, &tmA, full_bar(s), kc * BK, tx0 + dx, ty0 + dy, tb0);
+          if constexpr (kHalo) {
+            // k-blocks run channel-block major (cb, tap): the halo tile of a channel block lasts nine k-blocks, only W streams
+            const int cb = kb / 9, tap = kb - cb * 9;
+            mbar_expect_tx(full_bar(s), W_BYTES);
+            tma_load_2d(dstW, &tmW, full_bar(s), (tap * geo.kc_per_tap + cb) * BK, n0);
           } else {
-            tma_load_2d(dstA, &tmA, full_bar(s), kc * BK, m0);
+            mbar_expect_tx(full_bar(s), A_BYTES + W_BYTES);
+            const int tap = kb / geo.kc_per_tap, kc = kb - tap * geo.kc_per_tap;
+            if (geo.conv) {
+              const int dy = (g.taps == 9) ? tap / 3 - 1 : 0, dx = (g.taps == 9) ? tap % 3 - 1 : 0;
+              tma_load_4d(dstA, &tmA, full_bar(s), kc * BK, tx0 + dx, ty0 + dy, tb0);
+            } else {
+              tma_load_2d(dstA, &tmA, full_bar(s), kc * BK, m0);
+            }
+            tma_load_2d(dstW, &tmW, full_bar(s), kb * BK, n0);
           }
-          tma_load_2d(dstW, &tmW, full_bar(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (kHalo && warp == 3 + TC_EPI_WARPS) {
+    // =========================== halo-tile producer (halo mode only) ===========================
+    if (lane == 0) {
+      uint32_t ag = 0;  // running halo-tile counter (slot = ag & 1)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int t = item / geo.n_tiles;
+        const int tx0 = (t % geo.tiles_x) * geo.BW;
+        t /= geo.tiles_x;
+        const int ty0 = (t % geo.tiles_y) * geo.BH, tb0 = t / geo.tiles_y;
+        for (int cb = 0; cb < geo.kc_per_tap; ++cb, ++ag) {
+          const int sa = ag & 1;
+          TC_ROLE_WAIT(aempty_bar(sa), ((ag >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(afull_bar(sa), TC_HALO_BYTES);
+          tma_load_4d(smem_u32(smA + sa * TC_HALO_SLOT), &tmA, afull_bar(sa), cb * BK, tx0 - 1, ty0 - 1, tb0);
         }
       }
     }
@@ -143,24 +190,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       uint32_t kbg = 0;
+      uint32_t ag0 = 0;  // halo mode: running halo-tile counter at the start of the item
       int il = 0;  // local item index
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++il) {
         const int b = il & 1;
-        mbar_wait(tempty_bar(b), ((uint32_t)(il >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        TC_ROLE_WAIT(tempty_bar(b), ((uint32_t)(il >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(b * BLOCK_N);
         for (int kb = 0; kb < geo.nkb; ++kb, ++kbg) {
           const int s = kbg % kStages;
           const uint32_t ph = (kbg / kStages) & 1u;
-          mbar_wait(full_bar(s), ph);
+          uint64_t adesc;
+          if constexpr (kHalo) {
+            const int cb = kb / 9, tap = kb - cb * 9;
+            const uint32_t ag = ag0 + (uint32_t)cb;
+            const int sa = ag & 1;
+            if (tap == 0) TC_ROLE_WAIT(afull_bar(sa), (ag >> 1) & 1u);
+            // same tile, start shifted by (dy+1) halo rows and (dx+1) pixels; 8-row groups (= patch rows) 10 pixels apart
+            const uint32_t a_addr = smem_u32(smA + sa * TC_HALO_SLOT) + (uint32_t)((tap / 3) * TC_HALO_PITCH + tap % 3) * 128u;
+            adesc = (uint64_t)((a_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((TC_HALO_PITCH * 128) >> 4) << 32) | (1ull << 46) |
+                    (2ull << 61);
+          } else {
+            adesc = umma_desc_sw128(smem_u32(smA + s * A_BYTES));
+          }
+          TC_ROLE_WAIT(full_bar(s), ph);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smA + s * A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smW + s * W_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per 128-byte row: +2 in the (addr >> 4) field
             umma<kTf32>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          if constexpr (kHalo) {
+            if (kb % 9 == 8) umma_commit(aempty_bar((ag0 + (uint32_t)(kb / 9)) & 1u));  // the halo tile has served its nine taps
+          }
         }
+        if constexpr (kHalo) ag0 += (uint32_t)geo.kc_per_tap;
         umma_commit(tfull_bar(b));  // accumulator complete
       }
     }
@@ -501,15 +565,33 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   CUtensorMap tmA, tmW;
   int grid_x;
   SSR_CHECK(g.NP <= TC_MAX_NP, SSR_E_INVALID, "gemm_tc: NP=%d > %d", g.NP, TC_MAX_NP);
+  bool halo = false;
   if (g.taps == 9) {
     geo.conv = 1;
     choose_patch(g.B, g.H, g.W, &geo.BW, &geo.BH, &geo.BB);
     geo.tiles_x = (g.W + geo.BW - 1) / geo.BW;
     geo.tiles_y = (g.H + geo.BH - 1) / geo.BH;
     grid_x = geo.tiles_x * geo.tiles_y * ((g.B + geo.BB - 1) / geo.BB);
+    if (elem == 2 && getenv("STUDIOSR_B200_HALO")) {  // opt-in: measured neutral-to-slower, kept for the record
+      // halo mode needs the 8 x 16 patch; take it unless it wastes > 25 % more out-of-image rows than the best free patch
+      const long long hx = (g.W + TC_HALO_BW - 1) / TC_HALO_BW, hy = (g.H + TC_HALO_BH - 1) / TC_HALO_BH;
+      if (hx * hy * g.B * 4 <= (long long)grid_x * 5) {
+        halo = true;
+        geo.BW = TC_HALO_BW;
+        geo.BH = TC_HALO_BH;
+        geo.BB = 1;
+        geo.tiles_x = (int)hx;
+        geo.tiles_y = (int)hy;
+        grid_x = (int)(hx * hy * g.B);
+      }
+    }
     cuuint64_t dims[4] = {(cuuint64_t)g.lda, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
     cuuint64_t str[3] = {(cuuint64_t)g.lda * elem, (cuuint64_t)g.W * g.lda * elem, (cuuint64_t)g.H * g.W * g.lda * elem};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)geo.BW, (cuuint32_t)geo.BH, (cuuint32_t)geo.BB};
+    if (halo) {  // one box = the patch plus its one-pixel halo; out-of-image pixels are zero-filled (= the conv padding)
+      box[1] = TC_HALO_BW + 2;
+      box[2] = TC_HALO_BH + 2;
+    }
     SSR_TRY(make_tmap(&tmA, g.A, elem, 4, dims, str, box));
   } else {
     geo.conv = 0;
@@ -531,7 +613,9 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = tc_smem_bytes<BLOCK_N>();
   static bool attr_set = false;
   if (!attr_set) {
-    SSR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (elem == 2)
+      SSR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   geo.m_tiles = grid_x;
@@ -541,7 +625,14 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   dim3 grid(items < num_sms ? items : num_sms);
   ProfScope prof((g.out3_f32 || g.out3_u8) ? "gemm_tc_conv_last" : g.taps == 9 ? "gemm_tc_conv3x3" : "gemm_tc_linear", gemm_alg_flops(g),
                  gemm_alg_bytes(g, elem), s);
-  gemm_tc_kernel<T, BLOCK_N><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
+  if constexpr (elem == 2) {
+    if (halo)
+      gemm_tc_kernel<T, BLOCK_N, true><<<grid, TC_THREADS + 32, smem, s>>>(tmA, tmW, g, geo);
+    else
+      gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
+  } else {
+    gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
+  }
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;

@@ -50,6 +50,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Polling wait (mbarrier.test_wait in a tight loop): for single-thread roles (TMA producer, MMA issuer) whose wake-up latency
+// is on the critical path of a software pipeline; a suspended try_wait wakes up late.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xfffffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 8000000000LL) __trap();
+    }
+  }
+}
 // whole-warp wait: one lane polls, the warp re-converges behind it (32x less barrier traffic, one wake-up)
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
   if (lane == 0) mbar_wait(bar, parity);
