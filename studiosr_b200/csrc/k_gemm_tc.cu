@@ -572,7 +572,12 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     geo.tiles_x = (g.W + geo.BW - 1) / geo.BW;
     geo.tiles_y = (g.H + geo.BH - 1) / geo.BH;
     grid_x = geo.tiles_x * geo.tiles_y * ((g.B + geo.BB - 1) / geo.BB);
-    if (elem == 2 && getenv("STUDIOSR_B200_HALO")) {  // opt-in: measured neutral-to-slower, kept for the record
+    // Halo mode pays where the kernel is shared-memory-fill bound: wide tiles (BLOCK_N = 256: EDSR body / upsampler convs,
+    // +8 % measured) whose images tile exactly into 8 x 16 patches.  Narrower tiles are epilogue- or latency-bound and got
+    // slower; STUDIOSR_B200_HALO=1 / =0 forces it on / off for experiments.
+    const char* henv = getenv("STUDIOSR_B200_HALO");
+    const bool halo_auto = BLOCK_N == 256 && g.W % TC_HALO_BW == 0 && g.H % TC_HALO_BH == 0;
+    if (elem == 2 && (henv ? henv[0] == '1' : halo_auto)) {
       // halo mode needs the 8 x 16 patch; take it unless it wastes > 25 % more out-of-image rows than the best free patch
       const long long hx = (g.W + TC_HALO_BW - 1) / TC_HALO_BW, hy = (g.H + TC_HALO_BH - 1) / TC_HALO_BH;
       if (hx * hy * g.B * 4 <= (long long)grid_x * 5) {
