@@ -576,7 +576,7 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     // +8 % measured) whose images tile exactly into 8 x 16 patches.  Narrower tiles are epilogue- or latency-bound and got
     // slower; STUDIOSR_B200_HALO=1 / =0 forces it on / off for experiments.
     const char* henv = getenv("STUDIOSR_B200_HALO");
-    const bool halo_auto = BLOCK_N == 256 && g.W % TC_HALO_BW == 0 && g.H % TC_HALO_BH == 0;
+    const bool halo_auto = BLOCK_N == 256 && g.KP >= 128 && g.W % TC_HALO_BW == 0 && g.H % TC_HALO_BH == 0;
     if (elem == 2 && (henv ? henv[0] == '1' : halo_auto)) {
       // halo mode needs the 8 x 16 patch; take it unless it wastes > 25 % more out-of-image rows than the best free patch
       const long long hx = (g.W + TC_HALO_BW - 1) / TC_HALO_BW, hy = (g.H + TC_HALO_BH - 1) / TC_HALO_BH;
