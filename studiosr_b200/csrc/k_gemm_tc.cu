@@ -299,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       if (dbg) dbg[1] = clock64();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BLOCK_N);
-      float sum = 0.0f;
+      float sum = 0.0f, sumsq = 0.0f;
 
       if (g.out3_f32 || g.out3_u8) {
         // reconstruction conv (Cout = 3): bias + output affine + crop + fp32 NCHW / uint8 HWC store straight from the
@@ -427,10 +427,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; ++i)
             if (nb + i >= g.N) v[i] = 0.0f;
         }
-        if (do_ln) {
+        if (do_ln) {  // one-pass statistics (pad columns are exact zeros and add nothing)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum += v[i];
-          tmem_st32(trow + c * 32, v);  // keep v for the two LayerNorm passes
+          for (int i = 0; i < 32; ++i) {
+            sum += v[i];
+            sumsq = fmaf(v[i], v[i], sumsq);
+          }
+          tmem_st32(trow + c * 32, v);  // keep v for the normalisation pass
         }
         if (outT) store_T(v, outT, g.ld_T, nb);
         if (dbg && c == 1) dbg[7] = clock64();
@@ -439,17 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if (do_ln) {  // host guarantees n_tiles == 1 and BLOCK_N == NP: the thread owns the whole row
         const float mean = sum / (float)g.N;
-        float sq = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          float v[32];
-          tmem_ld32(trow + c * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float d = v[i] - mean;
-            if (c * 32 + i < g.N) sq += d * d;
-          }
-        }
+        const float sq = fmaxf(sumsq - sum * mean, 0.0f);  // sum (v - mean)^2
         const float rstd = rsqrtf(sq / (float)g.N + g.eps);
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {

@@ -468,7 +468,7 @@ __device__ __forceinline__ int mirror_index(int i, int n, int pad_mode) {
 }
 
 __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstArgs a) {
-  __shared__ float patch[CF_PIX][28];
+  __shared__ __align__(16) float patch[CF_PIX][28];  // 27 taps + 1 pad: a pixel's patch is seven 16-byte broadcast loads
   const int tid = threadIdx.x;
   const int M = a.B * a.Hp * a.Wp;
   const int m0 = blockIdx.x * CF_PIX;
@@ -521,8 +521,15 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstArgs a) 
     const int m = m0 + p;
     if (m >= M) break;
     float acc = bias;
+    const float4* pp = reinterpret_cast<const float4*>(patch[p]);  // LDS.128 x 7 instead of LDS.32 x 27: the kernel was LDS-bound
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc = fmaf(patch[p][k], w[k], acc);
+    for (int q = 0; q < 7; ++q) {
+      const float4 v = pp[q];
+      acc = fmaf(v.x, w[4 * q], acc);
+      if (4 * q + 1 < 27) acc = fmaf(v.y, w[4 * q + 1], acc);
+      if (4 * q + 2 < 27) acc = fmaf(v.z, w[4 * q + 2], acc);
+      if (4 * q + 3 < 27) acc = fmaf(v.w, w[4 * q + 3], acc);
+    }
     if (a.out_f32 && c < a.ld_f32) a.out_f32[(size_t)m * a.ld_f32 + c] = acc;
     if (a.out_T && c < a.ld_T) store_elem(a.out_T, (size_t)m * a.ld_T + c, a.elem, acc, a.round_tf32);
   }
