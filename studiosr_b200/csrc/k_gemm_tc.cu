@@ -337,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nb = n0 + c * 32;
         float v[32];
         if (dbg && c == 1) dbg[4] = clock64();
-        tmem_ld32(trow + c * 32, v);
+        tmem_ld32(trow + c * 32, v);  // (requesting chunk c + 1 here, ahead of its use, was measured 30 % SLOWER: DESIGN.md 5.3)
         if (dbg && c == 1) dbg[5] = clock64();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
