@@ -65,12 +65,15 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a, const
   w /= nwx;
   const int wy = w % nwy, b = w / nwy;
   const int shift = oca ? 0 : a.shift;
+  const int rid_first = shift > 0 ? 3 * shift_region(wy * a.ws, a.H, a.ws, shift) + shift_region(wx * a.ws, a.W, a.ws, shift) : 0;
+  int any_mixed = 0;  // does this window straddle shift-mask regions?  (only the last window row / column does)
   for (int t = tid; t < Nq; t += 128) {
     const int qy = t / a.ws, qx = t % a.ws;
     const int sy = wy * a.ws + qy, sx = wx * a.ws + qx;
     const int yy = (sy + shift) % a.H, xx = (sx + shift) % a.W;
     qpix[t] = (b * a.H + yy) * a.W + xx;
     const int rid = shift > 0 ? 3 * shift_region(sy, a.H, a.ws, shift) + shift_region(sx, a.W, a.ws, shift) : 0;
+    any_mixed |= rid != rid_first;
     qinfo[t] = (qy * nb + qx) | (rid << 16);
     if (!oca) {
       kpix[t] = qpix[t];
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a, const
     }
   }
   for (int e = tid; e < nb * nb; e += 128) btab[e] = __ldg(a.bias + (size_t)h * nb * nb + e);
-  __syncthreads();
+  const bool mixed = __syncthreads_or(any_mixed) != 0;
 
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(a.qkv);
   const uint32_t sK = (uint32_t)__cvta_generic_to_shared(tK), sV = (uint32_t)__cvta_generic_to_shared(tV);
@@ -102,7 +105,10 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a, const
   }
 
   const int g = lane >> 2, t4 = lane & 3;
-  const bool masked = shift > 0;
+  const bool masked = shift > 0 && mixed;  // a window inside one region needs no mask at all
+  // 16x16 self-attention: key j of a chunk sits at (ky, kx) = (kc / 16 + nt / 2, (nt & 1) * 8 + 2 t + e), so the bias index
+  // q - k is a per-chunk base minus a compile-time offset: one LDS with an immediate per score instead of two LDS + index math
+  const bool fast16 = !oca && a.ws == 16;
   constexpr float LOG2E = 1.4426950408889634f;
   // bias index: self-attention (q - k + ws - 1) * nb + ..., OCA (k - q + ws - kws + 1) * nb + ... wrapped when negative
   const int qoff = oca ? -(a.ws - kws + 1) * (nb + 1) : (a.ws - 1) * (nb + 1);
@@ -145,6 +151,22 @@ __global__ void __launch_bounds__(128) attn_flash_kernel(const AttnArgs a, const
         }
       }
       float c0 = -INFINITY, c1 = -INFINITY;
+      if (fast16 && !masked) {
+        const float* bt0 = btab + (qb0 - (kc >> 4) * 31 - 2 * t4);
+        const float* bt1 = btab + (qb1 - (kc >> 4) * 31 - 2 * t4);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int off = (nt >> 1) * 31 + (nt & 1) * 8 + e;
+            const float v0 = s[nt][e] + bt0[-off], v1 = s[nt][2 + e] + bt1[-off];
+            s[nt][e] = v0;
+            s[nt][2 + e] = v1;
+            c0 = fmaxf(c0, v0);
+            c1 = fmaxf(c1, v1);
+          }
+        }
+      } else
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
