@@ -10,6 +10,7 @@
 // Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
 // epilogue overlaps the other's TMA/MMA main loop.
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -61,8 +62,8 @@ constexpr size_t tc_smem_bytes() {
 
 template <typename T, int BLOCK_N, bool kHalo>
 __global__ void __launch_bounds__(TC_THREADS + (kHalo ? 32 : 0), 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g,
-               const TcGeom geo) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const GemmArgs g, const TcGeom geo) {
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int BK = 128 / (int)sizeof(T);  // elements per 128-byte swizzle row
   constexpr int kStages = tc_stages<BLOCK_N>();
@@ -277,6 +278,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
 
+      // plain-rows bf16 outputs (linear layers): pack the chunk into a SWIZZLE_64B box [32 rows][32 cols] of this warp's staging
+      // area and let TMA write it (rows beyond M are clipped); no read-back, no per-lane global stores.  Two boxes per warp.
+      auto tma_store_chunk = [&](const float (&v)[32], const CUtensorMap* map, int buf, int nb_) {
+        uint8_t* box = reinterpret_cast<uint8_t*>(st) + buf * 2048;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(box + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                         pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(map, smem_u32(box), nb_, mt * TC_BM + quad * 32);
+          bulk_commit();
+        }
+      };
       float4 resv[8];
       if (g.res) res_prefetch(resv, rm, lane, g.res, g.ldres, n0);  // overlaps the wait for the accumulator
       // activation-backward mask (training dgrad): this thread's row, 32 columns = 4 x 16 B (bf16), fetched one chunk ahead
@@ -363,9 +380,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             gp[i] = fmaf(x * 0.3989422804014327f, e, cdf);
             v[i] = x * cdf * g.alpha;
           }
-          store_T(gp, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
+          if (g.tma_store) {
+            if (lane == 0) bulk_wait_read<0>();  // both boxes of the previous chunk have been read by TMA
+            __syncwarp();
+            tma_store_chunk(gp, &tmP, 0, nb);
+          } else {
+            store_T(gp, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
+          }
         } else {
-          if (g.out_pre) store_T(v, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
+          if (g.out_pre) {
+            if (g.tma_store) {
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+              tma_store_chunk(v, &tmP, 0, nb);
+            } else {
+              store_T(v, reinterpret_cast<T*>(g.out_pre), g.ld_pre, nb);
+            }
+          }
           epilogue_act(v, g.act, g.slope, g.alpha);
         }
         if (g.mask) {  // activation backward (training dgrad): gate by the sign of the saved forward output
@@ -435,7 +466,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tmem_st32(trow + c * 32, v);  // keep v for the normalisation pass
         }
-        if (outT) store_T(v, outT, g.ld_T, nb);
+        if (outT) {
+          if (g.tma_store) {
+            if (g.out_pre) {
+              tma_store_chunk(v, &tmO, 1, nb);  // box 0 holds out_pre of this chunk (waited for above)
+            } else {
+              if (lane == 0) bulk_wait_read<1>();  // the box written two chunks ago is free again
+              __syncwarp();
+              tma_store_chunk(v, &tmO, c & 1, nb);
+            }
+          } else {
+            store_T(v, outT, g.ld_T, nb);
+          }
+        }
         if (dbg && c == 1) dbg[7] = clock64();
       }
       if (dbg) dbg[2] = clock64();
@@ -471,6 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(grp));
     }
+    if (g.tma_store && lane == 0) bulk_wait_all();  // the staging boxes must outlive their TMA stores
   }
 
   tc_fence_before();
@@ -608,6 +652,27 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BLOCK_N};
     SSR_TRY(make_tmap(&tmW, g.Wt, elem, 2, dims, str, box));
   }
+  // TMA-store epilogue: bf16 plain-row outputs of linear layers without residual / LayerNorm / fp32 outputs
+  GemmArgs ga = g;
+  CUtensorMap tmO, tmP;
+  memset(&tmO, 0, sizeof(tmO));
+  memset(&tmP, 0, sizeof(tmP));
+  ga.tma_store = 0;
+  if (elem == 2 && g.taps == 1 && g.out_T && !g.out_f32 && !g.res && !g.out_ln && g.ps_r <= 1 && !g.out3_f32 && !g.out3_u8 &&
+      g.ld_T % 8 == 0 && (!g.out_pre || g.ld_pre % 8 == 0) && !getenv("STUDIOSR_B200_NO_TMA_STORE")) {
+    cuuint32_t box[2] = {32, 32};
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)g.NP, (cuuint64_t)g.M};
+      cuuint64_t str[1] = {(cuuint64_t)g.ld_T * 2};
+      SSR_TRY(make_tmap(&tmO, g.out_T, 2, 2, dims, str, box, 64));
+    }
+    if (g.out_pre) {
+      cuuint64_t dims[2] = {(cuuint64_t)g.NP, (cuuint64_t)g.M};
+      cuuint64_t str[1] = {(cuuint64_t)g.ld_pre * 2};
+      SSR_TRY(make_tmap(&tmP, g.out_pre, 2, 2, dims, str, box, 64));
+    }
+    ga.tma_store = 1;
+  }
   constexpr size_t smem = tc_smem_bytes<BLOCK_N>();
   static bool attr_set = false;
   if (!attr_set) {
@@ -625,11 +690,11 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
                  gemm_alg_bytes(g, elem), s);
   if constexpr (elem == 2) {
     if (halo)
-      gemm_tc_kernel<T, BLOCK_N, true><<<grid, TC_THREADS + 32, smem, s>>>(tmA, tmW, g, geo);
+      gemm_tc_kernel<T, BLOCK_N, true><<<grid, TC_THREADS + 32, smem, s>>>(tmA, tmW, tmO, tmP, ga, geo);
     else
-      gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
+      gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, tmO, tmP, ga, geo);
   } else {
-    gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, g, geo);
+    gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, tmO, tmP, ga, geo);
   }
   count_launch();
   SSR_CUDA(cudaGetLastError());

@@ -90,6 +90,7 @@ struct GemmArgs {
   float out_shift[3];
   float out_scale, u8_scale;
   int K_alg, N_alg;  // un-padded contraction / output widths, for FLOP and byte accounting only
+  int tma_store;     // set by the launcher: out_T (and out_pre) leave through TMA stores of swizzled 32 x 32 boxes
   // backward of an activation folded into a dgrad epilogue (tensor-core path only): after alpha,
   //   v = mask[m][n] > 0 ? v : v * mask_slope     (ReLU: slope 0 with mask = the forward OUTPUT; LeakyReLU likewise)
   // mask_mode 1 (GELU backward): v *= gelu'(mask[m][n]) with mask = the saved PRE-activation
