@@ -181,10 +181,17 @@ class Model(nn.Module):
         dev = self._device()
         scale = 255.0 if self.img_range == 1.0 else 1.0
         img = torch.from_numpy(image.astype(np.float32) / scale).to(dev)
-        outs = []
-        for im in diverge_images(img):
-            x = im.permute(2, 0, 1).unsqueeze(0).contiguous()
-            outs.append(self.forward(x)[0].permute(1, 2, 0))
+        # the 8 rot / flip variants come in at most two shapes (HxW and WxH): one batched native forward per shape instead of
+        # eight launches sequences; samples of a batch are independent, so the result is unchanged
+        variants = [im.permute(2, 0, 1).contiguous() for im in diverge_images(img)]
+        outs = [None] * len(variants)
+        by_shape = {}
+        for i, v in enumerate(variants):
+            by_shape.setdefault(tuple(v.shape), []).append(i)
+        for idx in by_shape.values():
+            y = self.forward(torch.stack([variants[i] for i in idx]))
+            for k, i in enumerate(idx):
+                outs[i] = y[k].permute(1, 2, 0)
         out = converge_images(outs) * scale
         return out.round().clip(0, 255).to(torch.uint8).cpu().numpy()
 
