@@ -524,6 +524,9 @@ def run_extra(args):
 
 
 def main():
+    # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION (the GPU boxes set it)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
