@@ -139,7 +139,9 @@ class Model(nn.Module):
 
     def _train_forward(self, x: torch.Tensor, precision: str) -> torch.Tensor:
         """Differentiable forward (the Trainer's `model(x)`, trainer.py:101-102)."""
-        if precision != "bf16" or not self._trainable() or x.requires_grad:
+        # the backward kernels mirror the TRAINING branch of the forward (reflect padding, stochastic depth); a differentiable
+        # call in eval mode keeps the eval forward and fails loudly on backward
+        if precision != "bf16" or not self._trainable() or x.requires_grad or not self.training:
             params = [p for p in self.parameters() if p.requires_grad]
             return _NativeForwardOnly.apply(x, self, precision, self._pad_mode(), *params)
         named = {k: v for k, v in self.state_dict(keep_vars=True).items() if v.is_floating_point()}
