@@ -248,11 +248,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = item / geo.n_tiles, nt = item - mt * geo.n_tiles;
       const int n0 = nt * BLOCK_N;
       int m = -1;  // this thread's row as a pixel / token index, -1 if outside the tensor
+      int tx0 = 0, ty0 = 0, tb0 = 0;  // patch origin (conv)
       if (geo.conv) {
         int t = mt;
-        const int tx0 = (t % geo.tiles_x) * geo.BW;
+        tx0 = (t % geo.tiles_x) * geo.BW;
         t /= geo.tiles_x;
-        const int ty0 = (t % geo.tiles_y) * geo.BH, tb0 = (t / geo.tiles_y) * geo.BB;
+        ty0 = (t % geo.tiles_y) * geo.BH;
+        tb0 = (t / geo.tiles_y) * geo.BB;
         const int ww = row % geo.BW, hh = (row / geo.BW) % geo.BH, bb = row / (geo.BW * geo.BH);
         const int pb = tb0 + bb, py = ty0 + hh, px = tx0 + ww;
         if (pb < g.B && py < g.H && px < g.W) m = (pb * g.H + py) * g.W + px;
@@ -290,7 +292,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(map, smem_u32(box), nb_, mt * TC_BM + quad * 32);
+          if (g.tma_store == 2) {
+            // nn.PixelShuffle folded into the store: the warp's 32 pixels are a (bw x bh) sub-patch, the 32 columns one (i, j)
+            // sub-position and half of its channels; the output is addressed as (c, j, x, i, b*H + y) -- a 5-D tensor map
+            const int Cps_ = g.N / (g.ps_r * g.ps_r), q_ = nb_ / Cps_, r0_ = quad * 32;
+            tma_store_5d(map, smem_u32(box), nb_ - q_ * Cps_, q_ % g.ps_r, tx0 + r0_ % geo.BW, q_ / g.ps_r,
+                         tb0 * g.H + ty0 + r0_ / geo.BW);
+          } else {
+            tma_store_2d(map, smem_u32(box), nb_, mt * TC_BM + quad * 32);
+          }
           bulk_commit();
         }
       };
@@ -613,7 +623,7 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     // +8 % measured) whose images tile exactly into 8 x 16 patches.  Narrower tiles are epilogue- or latency-bound and got
     // slower; STUDIOSR_B200_HALO=1 / =0 forces it on / off for experiments.
     const char* henv = getenv("STUDIOSR_B200_HALO");
-    const bool halo_auto = BLOCK_N == 256 && g.KP >= 128 && g.W % TC_HALO_BW == 0 && g.H % TC_HALO_BH == 0;
+    const bool halo_auto = BLOCK_N == 256 && g.W % TC_HALO_BW == 0 && g.H % TC_HALO_BH == 0;
     if (elem == 2 && (henv ? henv[0] == '1' : halo_auto)) {
       // halo mode needs the 8 x 16 patch; take it unless it wastes > 25 % more out-of-image rows than the best free patch
       const long long hx = (g.W + TC_HALO_BW - 1) / TC_HALO_BW, hy = (g.H + TC_HALO_BH - 1) / TC_HALO_BH;
@@ -672,6 +682,17 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
       SSR_TRY(make_tmap(&tmP, g.out_pre, 2, 2, dims, str, box, 64));
     }
     ga.tma_store = 1;
+  } else if (elem == 2 && g.taps == 9 && g.ps_r > 1 && g.out_T && !g.out_f32 && !g.res && !g.out_ln && !g.out_pre && geo.BB == 1 &&
+             g.H % geo.BH == 0 && g.ld_T % 8 == 0 && !getenv("STUDIOSR_B200_NO_TMA_STORE")) {
+    // pixel-shuffled output [B][H r][W r][ld] seen as (c, j, x, i, t = b*H + y); a warp stores a (32 ch, 1, bw, 1, bh) box
+    const int r = g.ps_r, Cps = g.N / (r * r);
+    const int bwp = geo.BW < 32 ? geo.BW : 32, bhp = 32 / bwp;
+    const cuuint64_t ldb = (cuuint64_t)g.ld_T * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)Cps, (cuuint64_t)r, (cuuint64_t)g.W, (cuuint64_t)r, (cuuint64_t)g.B * g.H};
+    cuuint64_t str[4] = {ldb, ldb * r, ldb * r * g.W, ldb * r * g.W * r};
+    cuuint32_t box[5] = {32, 1, (cuuint32_t)bwp, 1, (cuuint32_t)bhp};
+    SSR_TRY(make_tmap(&tmO, g.out_T, 2, 5, dims, str, box, 64));
+    ga.tma_store = 2;
   }
   constexpr size_t smem = tc_smem_bytes<BLOCK_N>();
   static bool attr_set = false;
