@@ -3,6 +3,8 @@
 // transposed / rotated (dgrad) copies --, the inverse (packed fp32 weight gradients -> PyTorch layouts), PixelShuffle
 // backward, bias gradients (column sums) and small elementwise pieces.  All memory-bound; none is on the
 // inference path.
+#include <string.h>
+
 #include "ssr_device.cuh"
 
 namespace ssr {
@@ -163,10 +165,23 @@ static int colsum_stage1(const void* dY, int elem, int ld, int M, int NP, float*
   return SSR_OK;
 }
 // dY: bf16 [M][ld] of packed width NP (multiple of 8); out[sn(n)] for n < Cout
+static float* red_take(DeferredRed* dr, size_t floats) {
+  if (!dr || dr->used + floats > dr->pool_floats || dr->n >= dr->cap) return nullptr;
+  float* p = dr->pool + dr->used;
+  dr->used += (floats + 63) & ~(size_t)63;
+  return p;
+}
 int launch_colsum(const void* dY, int elem, int ld, int M, int NP, int Cout, int ps_r, float alpha, float* out, float* partial,
-                  cudaStream_t s) {
+                  cudaStream_t s, DeferredRed* dr) {
   int strips;
-  SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, partial, &strips, s));
+  float* mine = red_take(dr, (size_t)kColsumStrips * NP);
+  SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, mine ? mine : partial, &strips, s));
+  if (mine) {
+    RedEntry& e = dr->host[dr->n++];
+    memset(&e, 0, sizeof(e));
+    e.partial = mine; e.out = out; e.strips = strips; e.stride = NP; e.N = Cout; e.mode = 0; e.Cout = Cout; e.ps_r = ps_r; e.alpha = alpha;
+    return SSR_OK;
+  }
   colsum_final_conv_kernel<<<(Cout + 31) / 32, dim3(32, 8), 0, s>>>(partial, strips, NP, Cout, ps_r, alpha, out);
   count_launch();
   SSR_CUDA(cudaGetLastError());
@@ -317,12 +332,55 @@ __global__ void __launch_bounds__(256) colsum_final_map_kernel(const float* __re
   if (threadIdx.y == 0 && n < N) out[n] = t * sc;
 }
 int launch_colsum_map(const void* dY, int elem, int ld, int M, int NP, int N, const LinMap& map, float* out, float* partial,
-                      cudaStream_t s) {
+                      cudaStream_t s, DeferredRed* dr) {
   int strips;
-  SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, partial, &strips, s));
+  float* mine = red_take(dr, (size_t)kColsumStrips * NP);
+  SSR_TRY(colsum_stage1(dY, elem, ld, M, NP, mine ? mine : partial, &strips, s));
+  if (mine) {
+    RedEntry& e = dr->host[dr->n++];
+    memset(&e, 0, sizeof(e));
+    e.partial = mine; e.out = out; e.strips = strips; e.stride = NP; e.N = N; e.mode = 1; e.map = map; e.alpha = 1.0f;
+    return SSR_OK;
+  }
   colsum_final_map_kernel<<<(N + 31) / 32, dim3(32, 8), 0, s>>>(partial, strips, NP, N, map, out);
   count_launch();
   SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// all deferred second stages in one launch: blockIdx.y = entry, blockIdx.x = block of 32 output columns
+__global__ void __launch_bounds__(256) deferred_reductions_kernel(const RedEntry* __restrict__ entries) {
+  __shared__ float red[8][33];
+  const RedEntry e = entries[blockIdx.y];
+  if ((int)blockIdx.x * 32 >= e.N) return;
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  int col = 0, dst = 0;
+  float sc = 0.0f;
+  if (n < e.N) {
+    if (e.mode == 1) {
+      int kp;
+      lin_map(e.map, n, 0, &col, &kp, &sc);
+      dst = n;
+    } else {
+      col = n;
+      dst = e.mode == 0 ? ps_src_row(n, e.Cout, e.ps_r) : n;
+      sc = e.mode == 0 ? e.alpha : 1.0f;
+    }
+  }
+  const float t = strip_sum(e.partial + col, e.strips, (size_t)e.stride, red);
+  if (threadIdx.y == 0 && n < e.N) e.out[dst] = t * sc;
+}
+int launch_deferred_reductions(DeferredRed* dr, cudaStream_t s) {
+  if (!dr || dr->n == 0) return SSR_OK;
+  int maxN = 0;
+  for (int i = 0; i < dr->n; ++i) maxN = dr->host[i].N > maxN ? dr->host[i].N : maxN;
+  SSR_CUDA(cudaMemcpyAsync(dr->dev, dr->host, (size_t)dr->n * sizeof(RedEntry), cudaMemcpyHostToDevice, s));
+  ProfScope prof("deferred_reductions", 0.0, 0.0, s);
+  deferred_reductions_kernel<<<dim3((maxN + 31) / 32, dr->n), dim3(32, 8), 0, s>>>(dr->dev);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  dr->n = 0;
+  dr->used = 0;
   return SSR_OK;
 }
 
@@ -462,16 +520,26 @@ __global__ void __launch_bounds__(256) ln_bwd_final_kernel(const float* __restri
   const float t = strip_sum(partial + (size_t)which * C + c, blocks, (size_t)2 * C, red);
   if (threadIdx.y == 0 && n < 2 * C) (which ? dbeta : dgamma)[c] = t;
 }
-int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s) {
+int launch_ln_bwd(const LnBwdArgs& a0, cudaStream_t s, DeferredRed* dr) {
+  LnBwdArgs a = a0;
   SSR_CHECK(a.C <= 256 && a.CP <= 256 && a.CP % 4 == 0 && a.ldx % 4 == 0 && a.ldg % 4 == 0 && a.ld_dy % 4 == 0, SSR_E_INVALID,
             "ln_bwd: C=%d CP=%d", a.C, a.CP);
   SSR_CHECK(!a.dgamma || a.partial, SSR_E_INVALID, "ln_bwd: partial scratch missing");
   const int blocks = min((a.M + 7) / 8, kColsumStrips);
+  float* mine = a.dgamma && dr && dr->n + 2 <= dr->cap ? red_take(dr, (size_t)blocks * 2 * a.C) : nullptr;
+  if (mine) a.partial = mine;
   ProfScope prof("ln_bwd", 0.0, (double)a.M * a.C * (4 + a.elem_dy + (a.Gin ? 4 : 0) + 4 + (a.Gb ? 2 : 0)), s);
   ln_bwd_kernel<<<blocks, 256, 0, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
-  if (a.dgamma) {
+  if (mine) {
+    for (int which = 0; which < 2; ++which) {
+      RedEntry& e = dr->host[dr->n++];
+      memset(&e, 0, sizeof(e));
+      e.partial = mine + (size_t)which * a.C; e.out = which ? a.dbeta : a.dgamma; e.strips = blocks; e.stride = 2 * a.C; e.N = a.C;
+      e.mode = 2; e.alpha = 1.0f;
+    }
+  } else if (a.dgamma) {
     ln_bwd_final_kernel<<<(2 * a.C + 31) / 32, dim3(32, 8), 0, s>>>(a.partial, blocks, a.C, a.dgamma, a.dbeta);
     count_launch();
     SSR_CUDA(cudaGetLastError());

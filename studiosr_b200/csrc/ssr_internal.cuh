@@ -279,6 +279,27 @@ struct LinMap {
   int C, d, DP, QP;
   float qscale;
 };
+// Second stages of the two-stage reductions of a backward pass can be DEFERRED: every first stage writes its strips into
+// its own slice of a pool, and one batched kernel at the end of the backward finishes all of them (hundreds of 5-15 us
+// latency-bound launches become one).  dr == nullptr keeps the immediate behaviour.
+struct RedEntry {  // out[dst(n)] = scale(n) * sum_b partial[b * stride + col(n)],  n < N
+  const float* partial;
+  float* out;
+  int strips, stride, N;
+  int mode;  // 0: conv bias (dst = pixel-shuffle source row, scale = alpha); 1: linear bias (LinMap); 2: plain
+  int Cout, ps_r;
+  float alpha;
+  LinMap map;
+};
+struct DeferredRed {
+  float* pool = nullptr;  // device scratch for the strips
+  size_t pool_floats = 0, used = 0;
+  RedEntry* dev = nullptr;  // device copy of the entries
+  int cap = 0;
+  RedEntry* host = nullptr;  // host entries (owned by the caller, >= cap)
+  int n = 0;
+};
+int launch_deferred_reductions(DeferredRed* dr, cudaStream_t s);
 // LayerNorm backward (one warp per row): G_out = G_in + dLN(x; dy, gamma), dgamma += sum dy*xhat, dbeta += sum dy
 struct LnBwdArgs {
   const float* x;  // fp32 [M][ldx]: LayerNorm input
@@ -297,12 +318,12 @@ struct LnBwdArgs {
   float *dgamma, *dbeta;  // [C], overwritten, or null
   float* partial;         // scratch, >= kTrainPartialFloats floats (per-CTA partial sums)
 };
-int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s);
+int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s, DeferredRed* dr = nullptr);
 int launch_pack_linear_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int N, int K, int NP, int KP,
                            const LinMap& map, cudaStream_t s);
 int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int KP, const LinMap& map, cudaStream_t s);
 int launch_colsum_map(const void* dY, int elem, int ld, int M, int NP, int N, const LinMap& map, float* out, float* partial,
-                      cudaStream_t s);
+                      cudaStream_t s, DeferredRed* dr = nullptr);
 constexpr size_t kTrainPartialFloats = (size_t)592 * 2304;  // column-sum strips x widest packed row
 int launch_transpose_table(const float* table, float* out, int nb, int heads, cudaStream_t s);
 int launch_input_nhwc64(const float* x, void* out, int B, int h, int w, int Hp, int Wp, float scale, const float* shift3,
@@ -317,7 +338,7 @@ int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, vo
                          int taps, int ps_r, cudaStream_t s);
 int launch_unpack_wgrad(const float* dWp, float* grad, int Cout, int Cin, int KP, int taps, int ps_r, cudaStream_t s);
 int launch_colsum(const void* dY, int elem, int ld, int M, int NP, int Cout, int ps_r, float alpha, float* out, float* partial,
-                  cudaStream_t s);
+                  cudaStream_t s, DeferredRed* dr = nullptr);
 int launch_unshuffle(const void* in, void* out, int B, int H, int W, int C, int r, int ld_in, cudaStream_t s);
 int launch_nchw3_to_nhwc64(const float* in, void* out, int B, int H, int W, float scale, const float* shift3, cudaStream_t s);
 int launch_add_inplace(float* a, const float* b, void* out_bf, size_t n, cudaStream_t s);

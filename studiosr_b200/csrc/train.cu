@@ -51,6 +51,10 @@ struct ssr_train_state {
   size_t zero_bias_off = 0;
   std::vector<ConvT> convs;
   size_t dwp_floats = 0;
+  size_t red_floats = 0;  // pool for the strips of every deferred reduction of one backward
+  int red_entries = 0;
+  std::vector<RedEntry> red_host;
+  DeferredRed red;
   // EDSR
   int head_w = -1, head_b = -1;
   size_t head_dwp = 0;
@@ -99,6 +103,8 @@ static int add_conv(ssr_train_state* t, const std::string& name, const Lin* fwd,
   *a2 += (size_t)fwd->KP * 9 * fwd->NP * 2;
   c.dwp_off = t->dwp_floats;
   t->dwp_floats += (size_t)fwd->NP * 9 * fwd->KP;
+  t->red_floats += (size_t)592 * fwd->NP + 64;
+  t->red_entries += 1;
   t->convs.push_back(c);
   return (int)t->convs.size() - 1;
 }
@@ -114,6 +120,8 @@ static int bind_edsr(ssr_model* m) {
   if (t->head_w < 0 || t->head_b < 0) return SSR_E_STATE;
   t->head_dwp = t->dwp_floats;
   t->dwp_floats += (size_t)m->FP * 9 * 64;
+  t->red_floats += (size_t)592 * m->FP + 64;
+  t->red_entries += 1;
   char nm[64];
   for (int i = 0; i < c.n_resblocks; ++i) {
     snprintf(nm, sizeof(nm), "body.%d.body.0", i);
@@ -153,6 +161,8 @@ struct EdsrTrainWs {
   void *Gb, *Dh;
   float* dwp;
   float* partial;
+  float* red_pool;
+  RedEntry* red_dev;
 };
 
 static size_t plan_edsr_train(const ssr_model* m, void* base, int B, int H, int W, EdsrTrainWs* w) {
@@ -184,6 +194,8 @@ static size_t plan_edsr_train(const ssr_model* m, void* base, int B, int H, int 
   w->Dh = c.take(T * FP * 2);
   w->dwp = (float*)c.take(m->train->dwp_floats * 4);
   w->partial = (float*)c.take(kTrainPartialFloats * 4);
+  w->red_pool = (float*)c.take(m->train->red_floats * 4);
+  w->red_dev = (RedEntry*)c.take((size_t)(m->train->red_entries + 8) * sizeof(RedEntry));
   return c.off + 1024;
 }
 
@@ -276,6 +288,18 @@ static int train_forward_edsr(ssr_model* m, const float* const* params, const fl
   return run_gemm(m, g, s);
 }
 
+static DeferredRed* red_begin(ssr_train_state* t, float* pool, RedEntry* dev) {
+  t->red_host.resize((size_t)t->red_entries + 8);
+  t->red.pool = pool;
+  t->red.pool_floats = t->red_floats;
+  t->red.used = 0;
+  t->red.dev = dev;
+  t->red.cap = t->red_entries + 8;
+  t->red.host = t->red_host.data();
+  t->red.n = 0;
+  return &t->red;
+}
+
 // dgrad of a conv: dX[p][c] = sum_{tap',n} dY[p + off(tap')][n] * Wd[c][tap'*NP + n]  (the forward kernel on the rotated pack)
 static GemmArgs dgrad_base(const ssr_model* m, const ConvT& c, const void* dY, int B, int H, int W) {
   const Lin& L = *c.fwd;
@@ -326,7 +350,7 @@ static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const 
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_wgrad(dwp + c.dwp_off, grads[c.wi], c.Cout, c.Cin, L.KP, 9, L.ps_r, s));
   }
-  if (grads[c.bi]) SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s));
+  if (grads[c.bi]) SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s, &m->train->red));
   return SSR_OK;
 }
 
@@ -339,6 +363,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
   SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "train workspace %zu B < required %zu B", ws_bytes, need);
   const int FP = m->FP, nb = c.n_resblocks;
   const size_t T = (size_t)B * h * w;
+  red_begin(t, W.red_pool, W.red_dev);
   SSR_CUDA(cudaMemsetAsync(W.dwp, 0, t->dwp_floats * 4, s));
   int H = h * c.scale, Wd = w * c.scale;
   // add_mean is a frozen identity-weight 1x1 conv (common.py:108-121): dL/d(tail.1 output) = dy
@@ -438,8 +463,8 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_wgrad(W.dwp + t->head_dwp, grads[t->head_w], m->F, 3, 64, 9, 0, s));
   }
-  if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, FP, m->F, 0, 1.0f, grads[t->head_b], W.partial, s));
-  return SSR_OK;
+  if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, FP, m->F, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  return launch_deferred_reductions(&t->red, s);  // every bias gradient's second stage, one launch
 }
 
 
@@ -460,12 +485,16 @@ static int add_linear(ssr_train_state* t, const std::string& name, const Lin* fw
   *a2 += (size_t)fwd->KP * fwd->NP * 2;
   out->dwp_off = t->dwp_floats;
   t->dwp_floats += (size_t)fwd->NP * fwd->KP;
+  t->red_floats += (size_t)592 * fwd->NP + 64;
+  t->red_entries += 1;
   return SSR_OK;
 }
 static int add_ln(ssr_train_state* t, const std::string& name, const LNp* p, int C, LnT* out) {
   out->p = p;
   out->gi = find_idx(t, name + ".weight", C);
   out->bi = find_idx(t, name + ".bias", C);
+  t->red_floats += (size_t)592 * 2 * C + 64;
+  t->red_entries += 2;
   return (out->gi < 0 || out->bi < 0) ? SSR_E_STATE : SSR_OK;
 }
 
@@ -483,6 +512,8 @@ static int bind_swinir(ssr_model* m) {
   if (t->head_w < 0 || t->head_b < 0) return SSR_E_STATE;
   t->head_dwp = t->dwp_floats;
   t->dwp_floats += (size_t)m->CP * 9 * 64;
+  t->red_floats += (size_t)592 * m->CP + 64;
+  t->red_entries += 1;
   SSR_TRY(add_ln(t, "patch_embed.norm", &m->pe_norm, C, &t->s_pe));
   t->s_blocks.resize(m->layers.size());
   for (size_t li = 0; li < m->layers.size(); ++li) {
@@ -551,6 +582,8 @@ struct SwinTrainWs {
   void *Gb, *Gtb, *dH, *dXn, *dO, *dQKV;
   float* dwp;
   float* partial;
+  float* red_pool;
+  RedEntry* red_dev;
 };
 
 static size_t plan_swin_train(const ssr_model* m, void* base, int B, int Hp, int Wp, SwinTrainWs* w) {
@@ -611,6 +644,8 @@ static size_t plan_swin_train(const ssr_model* m, void* base, int B, int Hp, int
   w->dB = (float*)c.take((size_t)heads_max * 64 * 64 * 4);
   w->dwp = (float*)c.take(m->train->dwp_floats * 4);
   w->partial = (float*)c.take(kTrainPartialFloats * 4);
+  w->red_pool = (float*)c.take(m->train->red_floats * 4);
+  w->red_dev = (RedEntry*)c.take((size_t)(m->train->red_entries + 8) * sizeof(RedEntry));
   return c.off + 1024;
 }
 
@@ -888,10 +923,10 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_linear_grad(dwp + l.dwp_off, grads[l.wi], l.N, l.K, L.KP, l.map, s));
   }
-  if (grads[l.bi]) SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, L.NP, l.N, l.map, grads[l.bi], partial, s));
+  if (grads[l.bi]) SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, L.NP, l.N, l.map, grads[l.bi], partial, s, &m->train->red));
   return SSR_OK;
 }
-static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, const void* dy, int elem_dy, const float* Gin, float* Gout,
+static int ln_backward(ssr_train_state* ts, const LnT& l, const float* gamma_dev, const float* x, const void* dy, int elem_dy, const float* Gin, float* Gout,
                        void* Gb, int M, int C, int CP, float* partial, float* const* grads, cudaStream_t s,
                        const float* gb_scale = nullptr, int rows_per_scale = 1) {
   LnBwdArgs a;
@@ -917,7 +952,7 @@ static int ln_backward(const LnT& l, const float* gamma_dev, const float* x, con
     a.dgamma = grads[l.gi];
     a.dbeta = grads[l.bi];
   }
-  return launch_ln_bwd(a, s);
+  return launch_ln_bwd(a, s, &ts->red);
 }
 
 static int train_backward_swinir(ssr_model* m, const float* dy, const float* drop, float* const* grads, int B, int h, int w, void* ws,
@@ -931,6 +966,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
   SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "train workspace %zu B < required %zu B", ws_bytes, need);
   const int C = m->C, CP = m->CP;
   const int T = B * Hp * Wp;
+  red_begin(t, W.red_pool, W.red_dev);
   SSR_CUDA(cudaMemsetAsync(W.dwp, 0, t->dwp_floats * 4, s));
   int H = Hp * c.scale, Wd = Wp * c.scale;
   // y = (conv_last(.) + mean) * img_range, cropped (swinir.py:366-372): dL/d(conv_last output) = dy * img_range inside the crop
@@ -988,7 +1024,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
   int kblk = 0;
   for (int li = 0; li < nL; ++li) kblk += (int)m->layers[li].blocks.size();
   const size_t per_sample = (size_t)Hp * Wp * CP;
-  SSR_TRY(ln_backward(t->s_fin, m->dev<float>(m->final_norm.g_off), W.g[nL], W.dXn, 2, nullptr, W.G, W.Gb, T, C, CP, W.partial, grads, s));
+  SSR_TRY(ln_backward(t, t->s_fin, m->dev<float>(m->final_norm.g_off), W.g[nL], W.dXn, 2, nullptr, W.G, W.Gb, T, C, CP, W.partial, grads, s));
   for (int li = nL - 1; li >= 0; --li) {
     const Layer& L = m->layers[li];
     const int depth = (int)L.blocks.size();
@@ -1030,7 +1066,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
         SSR_TRY(launch_gemm_tc(g, 2, s));
       }
       // the bf16 copy feeds the attention branch: scaled by its stochastic-depth factor
-      SSR_TRY(ln_backward(bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
+      SSR_TRY(ln_backward(t, bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
                           drop ? drop + (size_t)(2 * kblk) * B : nullptr, Hp * Wp));
       // ---- attention: t_mid = t_in + proj(W-MSA(LN1(t_in)))  (swinir.py:149-171) ----
 
@@ -1071,13 +1107,13 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
         SSR_TRY(launch_gemm_tc(g, 2, s));
       }
       // the bf16 copy feeds the MLP branch of the previous block (unused for the first block of a layer)
-      SSR_TRY(ln_backward(bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
+      SSR_TRY(ln_backward(t, bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
                           (drop && bi > 0) ? drop + (size_t)(2 * (kblk - 1) + 1) * B : nullptr, Hp * Wp));
     }
     SSR_TRY(launch_add_inplace(W.G, W.Gt, W.Gb, (size_t)T * CP, s));  // blocks' path joins the group skip
   }
   // g0 = patch_embed.norm(x0) (swinir.py:22-32, 343-344); x0 also receives the long skip Gres
-  SSR_TRY(ln_backward(t->s_pe, m->dev<float>(m->pe_norm.g_off), W.x0, W.G, 4, W.Gres, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
+  SSR_TRY(ln_backward(t, t->s_pe, m->dev<float>(m->pe_norm.g_off), W.x0, W.G, 4, W.Gres, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s));
   if (grads[t->head_w]) {
     WgradArgs a;
     memset(&a, 0, sizeof(a));
@@ -1099,8 +1135,8 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
     SSR_TRY(launch_wgrad_tc(a, s));
     SSR_TRY(launch_unpack_wgrad(W.dwp + t->head_dwp, grads[t->head_w], C, 3, 64, 9, 0, s));
   }
-  if (grads[t->head_b]) SSR_TRY(launch_colsum(W.Gtb, 2, CP, T, CP, C, 0, 1.0f, grads[t->head_b], W.partial, s));
-  return SSR_OK;
+  if (grads[t->head_b]) SSR_TRY(launch_colsum(W.Gtb, 2, CP, T, CP, C, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  return launch_deferred_reductions(&t->red, s);  // bias / LayerNorm-parameter gradients: all second stages, one launch
 }
 
 }  // namespace ssr
