@@ -634,4 +634,69 @@ int launch_scale_to_bf16(const float* in, const float* scale, size_t elems_per_s
   return SSR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched re-pack: blockIdx.y = table entry, blockIdx.z = pass (0: forward pack, source-order threads; 1: dgrad pack,
+// transposed thread order so that its stores are coalesced too), blockIdx.x = block of 256 elements
+__global__ void __launch_bounds__(256) pack_batched_kernel(const PackEntry* __restrict__ entries) {
+  const PackEntry e = entries[blockIdx.y];
+  const int pass = blockIdx.z;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (e.kind == 2) {  // plain copy
+    if (pass == 0 && idx < e.N) reinterpret_cast<float*>(e.Wf)[idx] = e.W[idx];
+    return;
+  }
+  if (e.kind == 3) {  // [N][K] -> [K][N]
+    if (pass == 0 && idx < e.N * e.K) {
+      const int k = idx / e.N, n = idx - k * e.N;
+      reinterpret_cast<float*>(e.Wf)[idx] = e.W[(size_t)n * e.K + k];
+    }
+    return;
+  }
+  if (idx >= e.N * e.K) return;
+  if (pass == 1 && !e.Wd) return;
+  if (e.kind == 0) {
+    if (pass == 0) {
+      const int n = idx / e.K, c = idx - n * e.K;
+      const int sn = ps_src_row(n, e.N, e.ps_r);
+      const float* src = e.W + ((size_t)sn * e.K + c) * e.taps;
+      __nv_bfloat16* Wf = reinterpret_cast<__nv_bfloat16*>(e.Wf);
+      for (int t = 0; t < e.taps; ++t) Wf[(size_t)n * e.taps * e.KP + (size_t)t * e.KP + c] = __float2bfloat16_rn(src[t]);
+      if (c == 0 && e.bf && e.b) e.bf[n] = e.b[sn];
+    } else {
+      const int c = idx / e.N, n = idx - c * e.N;
+      const int sn = ps_src_row(n, e.N, e.ps_r);
+      const float* src = e.W + ((size_t)sn * e.K + c) * e.taps;
+      __nv_bfloat16* Wd = reinterpret_cast<__nv_bfloat16*>(e.Wd);
+      for (int t = 0; t < e.taps; ++t) Wd[(size_t)c * e.taps * e.NP + (size_t)(e.taps - 1 - t) * e.NP + n] = __float2bfloat16_rn(src[t]);
+    }
+    return;
+  }
+  // linear
+  const int n = pass ? idx % e.N : idx / e.K, k = pass ? idx / e.N : idx % e.K;
+  int np, kp;
+  float sc;
+  lin_map(e.map, n, k, &np, &kp, &sc);
+  const __nv_bfloat16 v = __float2bfloat16_rn(e.W[(size_t)n * e.K + k] * sc);
+  if (!pass) {
+    reinterpret_cast<__nv_bfloat16*>(e.Wf)[(size_t)np * e.KP + kp] = v;
+    if (k == 0 && e.bf && e.b) e.bf[np] = e.b[n] * sc;
+  } else {
+    reinterpret_cast<__nv_bfloat16*>(e.Wd)[(size_t)kp * e.NP + np] = v;
+  }
+}
+int launch_pack_batched(const PackEntry* host, PackEntry* dev, int n, cudaStream_t s) {
+  if (n == 0) return SSR_OK;
+  long long max_elems = 1;
+  for (int i = 0; i < n; ++i) {
+    const long long el = host[i].kind == 2 ? host[i].N : (long long)host[i].N * host[i].K;
+    max_elems = el > max_elems ? el : max_elems;
+  }
+  SSR_CUDA(cudaMemcpyAsync(dev, host, (size_t)n * sizeof(PackEntry), cudaMemcpyHostToDevice, s));
+  ProfScope prof("weight_repack", 0.0, 0.0, s);
+  pack_batched_kernel<<<dim3((unsigned)((max_elems + 255) / 256), n, 2), 256, 0, s>>>(dev);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 }  // namespace ssr

@@ -300,6 +300,19 @@ struct DeferredRed {
   int n = 0;
 };
 int launch_deferred_reductions(DeferredRed* dr, cudaStream_t s);
+// One launch re-packs every parameter of a model (train_forward): conv / linear packs (forward + dgrad operands), plain
+// vector copies (LayerNorm affine, first-conv weights) and the bias-table transposition, driven by a device table.
+struct PackEntry {
+  const float* W;   // source (PyTorch layout)
+  const float* b;   // bias source or null
+  void* Wf;         // forward pack (bf16) / copy destination (fp32) / transposed table (fp32)
+  float* bf;        // packed bias or null
+  void* Wd;         // dgrad pack (bf16) or null
+  int kind;         // 0 conv [N][K][taps], 1 linear [N][K] with LinMap, 2 plain copy of N floats, 3 table [N][K] -> [K][N]
+  int N, K, NP, KP, taps, ps_r;
+  LinMap map;
+};
+int launch_pack_batched(const PackEntry* host, PackEntry* dev, int n, cudaStream_t s);
 // LayerNorm backward (one warp per row): G_out = G_in + dLN(x; dy, gamma), dgamma += sum dy*xhat, dbeta += sum dy
 struct LnBwdArgs {
   const float* x;  // fp32 [M][ldx]: LayerNorm input

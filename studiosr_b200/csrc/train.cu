@@ -55,6 +55,7 @@ struct ssr_train_state {
   int red_entries = 0;
   std::vector<RedEntry> red_host;
   DeferredRed red;
+  std::vector<PackEntry> pack_host;
   // EDSR
   int head_w = -1, head_b = -1;
   size_t head_dwp = 0;
@@ -163,6 +164,7 @@ struct EdsrTrainWs {
   float* partial;
   float* red_pool;
   RedEntry* red_dev;
+  PackEntry* pack_dev;
 };
 
 static size_t plan_edsr_train(const ssr_model* m, void* base, int B, int H, int W, EdsrTrainWs* w) {
@@ -196,13 +198,38 @@ static size_t plan_edsr_train(const ssr_model* m, void* base, int B, int H, int 
   w->partial = (float*)c.take(kTrainPartialFloats * 4);
   w->red_pool = (float*)c.take(m->train->red_floats * 4);
   w->red_dev = (RedEntry*)c.take((size_t)(m->train->red_entries + 8) * sizeof(RedEntry));
+  w->pack_dev = (PackEntry*)c.take((size_t)(2 * m->train->red_entries + 16) * sizeof(PackEntry));
   return c.off + 1024;
 }
 
-static int repack_conv(ssr_model* m, const ConvT& c, const float* const* params, cudaStream_t s) {
+static void push_copy(ssr_train_state* t, const float* src, float* dst, int n) {
+  PackEntry e;
+  memset(&e, 0, sizeof(e));
+  e.W = src;
+  e.Wf = dst;
+  e.kind = 2;
+  e.N = n;
+  e.K = 1;
+  t->pack_host.push_back(e);
+}
+static int repack_conv(ssr_model* m, const ConvT& c, const float* const* params, cudaStream_t) {
   const Lin& L = *c.fwd;
-  return launch_pack_conv_dev(params[c.wi], params[c.bi], m->arena + L.w_off, m->dev<float>(L.b_off), m->train->arena2 + c.dg_off,
-                              c.Cout, c.Cin, L.NP, L.KP, 9, L.ps_r, s);
+  PackEntry e;
+  memset(&e, 0, sizeof(e));
+  e.W = params[c.wi];
+  e.b = params[c.bi];
+  e.Wf = m->arena + L.w_off;
+  e.bf = m->dev<float>(L.b_off);
+  e.Wd = m->train->arena2 + c.dg_off;
+  e.kind = 0;
+  e.N = c.Cout;
+  e.K = c.Cin;
+  e.NP = L.NP;
+  e.KP = L.KP;
+  e.taps = 9;
+  e.ps_r = L.ps_r;
+  m->train->pack_host.push_back(e);
+  return SSR_OK;
 }
 
 static int train_forward_edsr(ssr_model* m, const float* const* params, const float* x, float* y, int B, int h, int w, void* ws,
@@ -214,9 +241,11 @@ static int train_forward_edsr(ssr_model* m, const float* const* params, const fl
   SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "train workspace %zu B < required %zu B", ws_bytes, need);
   const int FP = m->FP;
   // ---- re-pack the (updated) fp32 master weights: forward + dgrad operand layouts ----
-  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(m->conv_first_w), params[t->head_w], (size_t)m->F * 27 * 4, cudaMemcpyDeviceToDevice, s));
-  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(m->conv_first_b), params[t->head_b], (size_t)m->F * 4, cudaMemcpyDeviceToDevice, s));
+  t->pack_host.clear();
+  push_copy(t, params[t->head_w], m->dev<float>(m->conv_first_w), m->F * 27);
+  push_copy(t, params[t->head_b], m->dev<float>(m->conv_first_b), m->F);
   for (const ConvT& cv : t->convs) SSR_TRY(repack_conv(m, cv, params, s));
+  SSR_TRY(launch_pack_batched(t->pack_host.data(), W.pack_dev, (int)t->pack_host.size(), s));
   // ---- forward (edsr.py:39-48), every GEMM operand kept for the backward ----
   SSR_TRY(launch_nchw3_to_nhwc64(x, W.xin64, B, h, w, 1.0f, m->sub_bias, s));
   {
@@ -584,6 +613,7 @@ struct SwinTrainWs {
   float* partial;
   float* red_pool;
   RedEntry* red_dev;
+  PackEntry* pack_dev;
 };
 
 static size_t plan_swin_train(const ssr_model* m, void* base, int B, int Hp, int Wp, SwinTrainWs* w) {
@@ -646,18 +676,43 @@ static size_t plan_swin_train(const ssr_model* m, void* base, int B, int Hp, int
   w->partial = (float*)c.take(kTrainPartialFloats * 4);
   w->red_pool = (float*)c.take(m->train->red_floats * 4);
   w->red_dev = (RedEntry*)c.take((size_t)(m->train->red_entries + 8) * sizeof(RedEntry));
+  w->pack_dev = (PackEntry*)c.take((size_t)(2 * m->train->red_entries + 16) * sizeof(PackEntry));
   return c.off + 1024;
 }
 
-static int repack_linear(ssr_model* m, const LinT& l, const float* const* params, cudaStream_t s) {
+static int repack_linear(ssr_model* m, const LinT& l, const float* const* params, cudaStream_t) {
   const Lin& L = *l.fwd;
-  return launch_pack_linear_dev(params[l.wi], params[l.bi], m->arena + L.w_off, m->dev<float>(L.b_off), m->train->arena2 + l.dg_off,
-                                l.N, l.K, L.NP, L.KP, l.map, s);
-}
-static int repack_ln(ssr_model* m, const LnT& l, const float* const* params, int C, cudaStream_t s) {
-  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(l.p->g_off), params[l.gi], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
-  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(l.p->b_off), params[l.bi], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  PackEntry e;
+  memset(&e, 0, sizeof(e));
+  e.W = params[l.wi];
+  e.b = params[l.bi];
+  e.Wf = m->arena + L.w_off;
+  e.bf = m->dev<float>(L.b_off);
+  e.Wd = m->train->arena2 + l.dg_off;
+  e.kind = 1;
+  e.N = l.N;
+  e.K = l.K;
+  e.NP = L.NP;
+  e.KP = L.KP;
+  e.taps = 1;
+  e.map = l.map;
+  m->train->pack_host.push_back(e);
   return SSR_OK;
+}
+static int repack_ln(ssr_model* m, const LnT& l, const float* const* params, int C, cudaStream_t) {
+  push_copy(m->train, params[l.gi], m->dev<float>(l.p->g_off), C);
+  push_copy(m->train, params[l.bi], m->dev<float>(l.p->b_off), C);
+  return SSR_OK;
+}
+static void repack_table(ssr_model* m, const float* table, float* dst, int nb, int heads) {
+  PackEntry e;
+  memset(&e, 0, sizeof(e));
+  e.W = table;  // [nb][heads]
+  e.Wf = dst;   // [heads][nb]
+  e.kind = 3;  // out[k * N + n] = W[n * K + k]: N = nb rows of the source, K = heads
+  e.N = nb;
+  e.K = heads;
+  m->train->pack_host.push_back(e);
 }
 
 static void train_padded(const ssr_model* m, int h, int w, int* Hp, int* Wp) {
@@ -681,8 +736,9 @@ static int train_forward_swinir(ssr_model* m, const float* const* params, const 
   const int C = m->C, CP = m->CP, HP = m->HP;
   const int T = B * Hp * Wp;
   // ---- re-pack the fp32 master parameters ----
-  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(m->conv_first_w), params[t->head_w], (size_t)C * 27 * 4, cudaMemcpyDeviceToDevice, s));
-  SSR_CUDA(cudaMemcpyAsync(m->dev<float>(m->conv_first_b), params[t->head_b], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  t->pack_host.clear();
+  push_copy(t, params[t->head_w], m->dev<float>(m->conv_first_w), C * 27);
+  push_copy(t, params[t->head_b], m->dev<float>(m->conv_first_b), C);
   SSR_TRY(repack_ln(m, t->s_pe, params, C, s));
   SSR_TRY(repack_ln(m, t->s_fin, params, C, s));
   for (size_t li = 0; li < t->s_blocks.size(); ++li)
@@ -693,9 +749,10 @@ static int train_forward_swinir(ssr_model* m, const float* const* params, const 
       SSR_TRY(repack_linear(m, b.proj, params, s));
       SSR_TRY(repack_linear(m, b.fc1, params, s));
       SSR_TRY(repack_linear(m, b.fc2, params, s));
-      SSR_TRY(launch_transpose_table(params[b.table_i], m->dev<float>(b.bias_off), 225, m->layers[li].heads, s));
+      repack_table(m, params[b.table_i], m->dev<float>(b.bias_off), 225, m->layers[li].heads);
     }
   for (const ConvT& cv : t->convs) SSR_TRY(repack_conv(m, cv, params, s));
+  SSR_TRY(launch_pack_batched(t->pack_host.data(), W.pack_dev, (int)t->pack_host.size(), s));
   // ---- forward (swinir.py:353-372, training branch: reflect pad), un-fused so that every GEMM operand is kept ----
   const float in_scale = 1.0f / c.img_range;
   float in_shift[3] = {-kMean3[0], -kMean3[1], -kMean3[2]};
