@@ -5,6 +5,8 @@
 // inference path.
 #include <string.h>
 
+#include <algorithm>
+
 #include "ssr_device.cuh"
 
 namespace ssr {
@@ -694,6 +696,35 @@ int launch_pack_batched(const PackEntry* host, PackEntry* dev, int n, cudaStream
   SSR_CUDA(cudaMemcpyAsync(dev, host, (size_t)n * sizeof(PackEntry), cudaMemcpyHostToDevice, s));
   ProfScope prof("weight_repack", 0.0, 0.0, s);
   pack_batched_kernel<<<dim3((unsigned)((max_elems + 255) / 256), n, 2), 256, 0, s>>>(dev);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+__global__ void __launch_bounds__(256) unpack_batched_kernel(const PackEntry* __restrict__ entries) {
+  const PackEntry e = entries[blockIdx.y];
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= e.N * e.K) return;
+  const int n = idx / e.K, k = idx - n * e.K;
+  float* grad = reinterpret_cast<float*>(e.Wf);
+  if (e.kind == 0) {
+    const int sn = ps_src_row(n, e.N, e.ps_r);
+    float* dst = grad + ((size_t)sn * e.K + k) * e.taps;
+    for (int t = 0; t < e.taps; ++t) dst[t] = e.W[((size_t)n * e.taps + t) * e.KP + k];
+  } else {
+    int np, kp;
+    float sc;
+    lin_map(e.map, n, k, &np, &kp, &sc);
+    grad[idx] = e.W[(size_t)np * e.KP + kp] * sc;
+  }
+}
+int launch_unpack_batched(const PackEntry* host, PackEntry* dev, int n, cudaStream_t s) {
+  if (n == 0) return SSR_OK;
+  long long max_elems = 1;
+  for (int i = 0; i < n; ++i) max_elems = std::max(max_elems, (long long)host[i].N * host[i].K);
+  SSR_CUDA(cudaMemcpyAsync(dev, host, (size_t)n * sizeof(PackEntry), cudaMemcpyHostToDevice, s));
+  ProfScope prof("wgrad_unpack", 0.0, 0.0, s);
+  unpack_batched_kernel<<<dim3((unsigned)((max_elems + 255) / 256), n), 256, 0, s>>>(dev);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;

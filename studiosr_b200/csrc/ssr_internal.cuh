@@ -313,6 +313,9 @@ struct PackEntry {
   LinMap map;
 };
 int launch_pack_batched(const PackEntry* host, PackEntry* dev, int n, cudaStream_t s);
+// ... and one launch un-packs every packed fp32 weight gradient into the PyTorch layouts at the end of the backward
+// (PackEntry re-used: W = packed gradient, Wf = destination, kind 0 conv / 1 linear)
+int launch_unpack_batched(const PackEntry* host, PackEntry* dev, int n, cudaStream_t s);
 // LayerNorm backward (one warp per row): G_out = G_in + dLN(x; dy, gamma), dgamma += sum dy*xhat, dbeta += sum dy
 struct LnBwdArgs {
   const float* x;  // fp32 [M][ldx]: LayerNorm input

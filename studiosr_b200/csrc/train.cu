@@ -55,7 +55,7 @@ struct ssr_train_state {
   int red_entries = 0;
   std::vector<RedEntry> red_host;
   DeferredRed red;
-  std::vector<PackEntry> pack_host;
+  std::vector<PackEntry> pack_host, unpack_host;
   // EDSR
   int head_w = -1, head_b = -1;
   size_t head_dwp = 0;
@@ -326,6 +326,7 @@ static DeferredRed* red_begin(ssr_train_state* t, float* pool, RedEntry* dev) {
   t->red.cap = t->red_entries + 8;
   t->red.host = t->red_host.data();
   t->red.n = 0;
+  t->unpack_host.clear();
   return &t->red;
 }
 
@@ -377,7 +378,17 @@ static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const 
     a.N_alg = c.Cout;
     a.K_alg = c.Cin;
     SSR_TRY(launch_wgrad_tc(a, s));
-    SSR_TRY(launch_unpack_wgrad(dwp + c.dwp_off, grads[c.wi], c.Cout, c.Cin, L.KP, 9, L.ps_r, s));
+    PackEntry e;  // un-packed with all the others by one launch at the end of the backward
+    memset(&e, 0, sizeof(e));
+    e.W = dwp + c.dwp_off;
+    e.Wf = grads[c.wi];
+    e.kind = 0;
+    e.N = c.Cout;
+    e.K = c.Cin;
+    e.KP = L.KP;
+    e.taps = 9;
+    e.ps_r = L.ps_r;
+    m->train->unpack_host.push_back(e);
   }
   if (grads[c.bi]) SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s, &m->train->red));
   return SSR_OK;
@@ -490,9 +501,19 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     a.N_alg = m->F;
     a.K_alg = 3;
     SSR_TRY(launch_wgrad_tc(a, s));
-    SSR_TRY(launch_unpack_wgrad(W.dwp + t->head_dwp, grads[t->head_w], m->F, 3, 64, 9, 0, s));
+    PackEntry e;
+    memset(&e, 0, sizeof(e));
+    e.W = W.dwp + t->head_dwp;
+    e.Wf = grads[t->head_w];
+    e.kind = 0;
+    e.N = m->F;
+    e.K = 3;
+    e.KP = 64;
+    e.taps = 9;
+    t->unpack_host.push_back(e);
   }
   if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, FP, m->F, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  SSR_TRY(launch_unpack_batched(t->unpack_host.data(), W.pack_dev, (int)t->unpack_host.size(), s));
   return launch_deferred_reductions(&t->red, s);  // every bias gradient's second stage, one launch
 }
 
@@ -978,7 +999,17 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
     a.N_alg = l.N;
     a.K_alg = l.K;
     SSR_TRY(launch_wgrad_tc(a, s));
-    SSR_TRY(launch_unpack_linear_grad(dwp + l.dwp_off, grads[l.wi], l.N, l.K, L.KP, l.map, s));
+    PackEntry e;
+    memset(&e, 0, sizeof(e));
+    e.W = dwp + l.dwp_off;
+    e.Wf = grads[l.wi];
+    e.kind = 1;
+    e.N = l.N;
+    e.K = l.K;
+    e.KP = L.KP;
+    e.taps = 1;
+    e.map = l.map;
+    m->train->unpack_host.push_back(e);
   }
   if (grads[l.bi]) SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, L.NP, l.N, l.map, grads[l.bi], partial, s, &m->train->red));
   return SSR_OK;
@@ -1190,9 +1221,19 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
     a.N_alg = C;
     a.K_alg = 3;
     SSR_TRY(launch_wgrad_tc(a, s));
-    SSR_TRY(launch_unpack_wgrad(W.dwp + t->head_dwp, grads[t->head_w], C, 3, 64, 9, 0, s));
+    PackEntry e;
+    memset(&e, 0, sizeof(e));
+    e.W = W.dwp + t->head_dwp;
+    e.Wf = grads[t->head_w];
+    e.kind = 0;
+    e.N = C;
+    e.K = 3;
+    e.KP = 64;
+    e.taps = 9;
+    t->unpack_host.push_back(e);
   }
   if (grads[t->head_b]) SSR_TRY(launch_colsum(W.Gtb, 2, CP, T, CP, C, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  SSR_TRY(launch_unpack_batched(t->unpack_host.data(), W.pack_dev, (int)t->unpack_host.size(), s));
   return launch_deferred_reductions(&t->red, s);  // bias / LayerNorm-parameter gradients: all second stages, one launch
 }
 
