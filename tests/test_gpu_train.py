@@ -87,6 +87,7 @@ def _edsr_case(cfg, B, H, W, wseed, xseed):
     ("wide", dict(synth.EDSR_DEFAULT, n_resblocks=4), 2, 48, 48),  # cfg2 width and patch size, fewer blocks
     ("ragged", synth.EDSR_TINY, 3, 13, 9),                          # odd sizes: TMA boxes clip at the image edge
     ("single-pixel-rows", dict(synth.EDSR_TINY, n_resblocks=1), 1, 1, 7),
+    ("full-cfg2-model", synth.EDSR_DEFAULT, 1, 48, 48),  # the default 32-block model at the cfg2 patch size (one sample)
 ])
 def test_edsr_backward(name, cfg, B, H, W):
     model, Pr, Pa, loss, loss_ref = _edsr_case(cfg, B, H, W, 5, 77)
@@ -163,6 +164,7 @@ def _swin_case(cfg, B, H, W, wseed, xseed):
     ("c180", dict(embed_dim=180, depths=[2, 2], num_heads=[6, 6], scale=4), 1, 16, 16),  # the 180 / 6-head class (cfg4 widths)
     ("x2", dict(synth.SWINIR_TINY, scale=2), 1, 16, 16),
     ("x3-batch3", dict(synth.SWINIR_TINY, scale=3, depths=[3], num_heads=[6]), 3, 8, 16),  # odd depth (last block shifted), PS3
+    ("full-cfg4-model", dict(), 1, 64, 64),  # the default 36-block model at the cfg4 patch size (one sample)
 ])
 def test_swinir_backward(name, over, B, H, W):
     cfg = synth.swinir_config(**over)
