@@ -84,7 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + 256);
   // bars: [0,kStages) full, [kStages,2kStages) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base address
   // halo mode: + full[2], empty[2] of the two halo-tile slots (they live in the A region of the stage ring)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -92,9 +92,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
+  // halo tiles live in the A region of the stage ring: as many slots as fit (narrow tiles have 6 stages -> 4 slots, which
+  // they need: nine N=64 k-blocks last only ~1.7k cycles, less than one TMA round trip)
+  constexpr int kHaloSlots = (kStages * A_BYTES) / TC_HALO_SLOT >= 4 ? 4 : 2;
   auto afull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 4 + b); };
-  auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 6 + b); };
-  static_assert(!kHalo || (2 * TC_HALO_SLOT <= kStages * A_BYTES), "two halo tiles must fit the A region of the ring");
+  auto aempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 8 + b); };
+  static_assert(!kHalo || (kHaloSlots * TC_HALO_SLOT <= kStages * A_BYTES), "the halo tiles must fit the A region of the ring");
 
   for (int i = threadIdx.x; i < g.NP; i += blockDim.x) s_bias[i] = __ldg(g.bias + i);
   if (g.out_ln)
@@ -112,6 +115,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 4);  // one arrival per epilogue warp of the group
+    }
+    for (int b = 0; b < 4; ++b) {
       mbar_init(afull_bar(b), 1);
       mbar_init(aempty_bar(b), 1);
     }
@@ -180,8 +185,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         t /= geo.tiles_x;
         const int ty0 = (t % geo.tiles_y) * geo.BH, tb0 = t / geo.tiles_y;
         for (int cb = 0; cb < geo.kc_per_tap; ++cb, ++ag) {
-          const int sa = ag & 1;
-          TC_ROLE_WAIT(aempty_bar(sa), ((ag >> 1) & 1u) ^ 1u);
+          const int sa = ag % kHaloSlots;
+          TC_ROLE_WAIT(aempty_bar(sa), ((ag / kHaloSlots) & 1u) ^ 1u);
           mbar_expect_tx(afull_bar(sa), TC_HALO_BYTES);
           tma_load_4d(smem_u32(smA + sa * TC_HALO_SLOT), &tmA, afull_bar(sa), cb * BK, tx0 - 1, ty0 - 1, tb0);
         }
@@ -205,8 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (kHalo) {
             const int cb = kb / 9, tap = kb - cb * 9;
             const uint32_t ag = ag0 + (uint32_t)cb;
-            const int sa = ag & 1;
-            if (tap == 0) TC_ROLE_WAIT(afull_bar(sa), (ag >> 1) & 1u);
+            const int sa = ag % kHaloSlots;
+            if (tap == 0) TC_ROLE_WAIT(afull_bar(sa), (ag / kHaloSlots) & 1u);
             // same tile, start shifted by (dy+1) halo rows and (dx+1) pixels; 8-row groups (= patch rows) 10 pixels apart
             const uint32_t a_addr = smem_u32(smA + sa * TC_HALO_SLOT) + (uint32_t)((tap / 3) * TC_HALO_PITCH + tap % 3) * 128u;
             adesc = (uint64_t)((a_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((TC_HALO_PITCH * 128) >> 4) << 32) | (1ull << 46) |
@@ -222,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma<kTf32>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
           if constexpr (kHalo) {
-            if (kb % 9 == 8) umma_commit(aempty_bar((ag0 + (uint32_t)(kb / 9)) & 1u));  // the halo tile has served its nine taps
+            if (kb % 9 == 8) umma_commit(aempty_bar((ag0 + (uint32_t)(kb / 9)) % kHaloSlots));  // the halo tile has served its nine taps
           }
         }
         if constexpr (kHalo) ag0 += (uint32_t)geo.kc_per_tap;
