@@ -697,7 +697,7 @@ __global__ void pack_rows_kernel(const float* in, int rows, int cols, void* out,
 // Stage 1 reduces t over pixel slabs into partial[b][split][c] (deterministic, no atomics); stage 2
 // finishes the mean, evaluates the tiny MLP once per block and applies gate + residual.
 // =============================================================================================
-__global__ void __launch_bounds__(256) ca_pool_kernel(const float* t, int ld, int HW, int C, int nsplit, float* partial) {
+__global__ void __launch_bounds__(256) ca_pool_kernel(const void* t, int elem_t, int ld, int HW, int C, int nsplit, float* partial) {
   __shared__ float red[256];
   const int b = blockIdx.y, split = blockIdx.x;
   const int chunk = (HW + nsplit - 1) / nsplit;
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(256) ca_pool_kernel(const float* t, int ld, in
     const int c = c0 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
     float acc = 0.0f;
     if (c < C)
-      for (int p = p0 + pl; p < p1; p += lanes) acc += t[((size_t)b * HW + p) * ld + c];
+      for (int p = p0 + pl; p < p1; p += lanes) acc += load_elem(t, ((size_t)b * HW + p) * ld + c, elem_t == 2 ? 2 : 4);
     red[threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.x < 64 && c < C)
@@ -747,7 +747,14 @@ __global__ void __launch_bounds__(256) ca_apply_kernel(const CaArgs a) {
   for (int e = threadIdx.x; e < (p1 - p0) * c4n; e += blockDim.x) {
     const int p = p0 + e / c4n, c = (e % c4n) * 4;
     const size_t m = (size_t)b * a.HW + p;
-    const float4 tv = *reinterpret_cast<const float4*>(a.t + m * a.ld + c);
+    float4 tv;
+    if (a.elem_t == 2) {
+      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.t) + m * a.ld + c);
+      tv = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+    } else {
+      tv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.t) + m * a.ld + c);
+    }
     const float4 rv = *reinterpret_cast<const float4*>(a.res + m * a.ld + c);
     float4 o;
     o.x = fmaf(tv.x, gate[c], rv.x); o.y = fmaf(tv.y, gate[c + 1], rv.y);
@@ -771,12 +778,12 @@ int launch_channel_attention(const CaArgs& a, cudaStream_t s) {
   SSR_CHECK(a.C <= 256 && a.R <= 64 && a.CP % 4 == 0 && a.nsplit >= 1, SSR_E_INVALID, "channel attention: C=%d R=%d", a.C, a.R);
   const double px = (double)a.B * a.HW;
   {
-    ProfScope prof("ca_pool", 0.0, px * a.C * 4, s);
-    ca_pool_kernel<<<dim3(a.nsplit, a.B), 256, 0, s>>>(a.t, a.ld, a.HW, a.C, a.nsplit, a.partial);
+    ProfScope prof("ca_pool", 0.0, px * a.C * (a.elem_t == 2 ? 2 : 4), s);
+    ca_pool_kernel<<<dim3(a.nsplit, a.B), 256, 0, s>>>(a.t, a.elem_t, a.ld, a.HW, a.C, a.nsplit, a.partial);
     count_launch();
   }
   {
-    ProfScope prof("ca_apply", 0.0, px * a.C * (4 + 4 + 4 + a.elem), s);
+    ProfScope prof("ca_apply", 0.0, px * a.C * ((a.elem_t == 2 ? 2 : 4) + 4 + 4 + (a.out_T ? a.elem : 0)), s);
     const int blocks = a.HW >= 4096 ? 64 : (a.HW + 63) / 64;
     ca_apply_kernel<<<dim3(blocks, a.B), 256, 0, s>>>(a);
     count_launch();

@@ -1183,8 +1183,13 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
         g.ld_T = CcP;
         SSR_TRY(run_gemm(m, g, s));
         GemmArgs g2 = gemm_base(m, blk.cab2, W.c1, CcP, B, Hp, Wp);
-        g2.out_f32 = W.t2;
-        g2.ld_f32 = CP;
+        if (e == 2) {  // bf16 path: the channel-attention input stays bf16 (half the bytes for the conv store, pool and gate)
+          g2.out_T = W.t2;
+          g2.ld_T = CP;
+        } else {
+          g2.out_f32 = W.t2;
+          g2.ld_f32 = CP;
+        }
         SSR_TRY(run_gemm(m, g2, s));
       }
       {  // (S)W-MSA over 16x16 windows (hat.py:167-183)
@@ -1215,7 +1220,7 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
          // channel-attention term joins the shortcut first and the projection is part of the tail kernel
         CaArgs ca;
         memset(&ca, 0, sizeof(ca));
-        ca.t = W.t2; ca.res = fused ? shortcut : W.t; ca.ld = CP; ca.B = B; ca.HW = Hp * Wp; ca.C = m->C; ca.CP = CP; ca.R = R;
+        ca.t = W.t2; ca.elem_t = e == 2 ? 2 : 4; ca.res = fused ? shortcut : W.t; ca.ld = CP; ca.B = B; ca.HW = Hp * Wp; ca.C = m->C; ca.CP = CP; ca.R = R;
         ca.W1 = m->dev<float>(blk.ca_w1); ca.b1 = m->dev<float>(blk.ca_b1);
         ca.W2 = m->dev<float>(blk.ca_w2); ca.b2 = m->dev<float>(blk.ca_b2);
         ca.partial = W.partial; ca.nsplit = W.nsplit;

@@ -231,7 +231,8 @@ int launch_pack_heads(const float* in, void* out, int M, int heads, int d, int D
 
 // RCAN channel-attention gate + RCAB residual: out = res + t * sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2)
 struct CaArgs {
-  const float* t;    // fp32 [B][HW][ld]: output of the RCAB's second conv
+  const void* t;     // [B][HW][ld]: output of the second conv, fp32 (elem_t 0 / 4) or bf16 (elem_t 2: HAT's bf16 path)
+  int elem_t;
   const float* res;  // fp32 [B][HW][ld]: RCAB input
   int ld, B, HW, C, CP, R;
   const float *W1, *b1, *W2, *b2;  // [R][C], [R], [C][R], [C] fp32
