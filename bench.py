@@ -105,6 +105,26 @@ def build_model(precision):
     return m
 
 
+def init_dist_quiet(local):
+    """torch.distributed over NCCL with fd 1 pointed at stderr while the communicator comes up: NCCL writes its version
+    banner to stdout at that moment, and stdout must carry the ONE JSON line only."""
+    import torch
+    import torch.distributed as dist
+
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return dist
+
+
 def max_over_ranks(ms, dist, device):
     """Multi-GPU numbers are the MAX over ranks of the device-side time (the frames are independent shards, the job is
     done when the slowest rank is).  `dist` is torch.distributed (or None for a single process)."""
@@ -211,9 +231,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = init_dist_quiet(local)
     lib = _lib.load()
     precision = args.precision
     model = build_model(precision)
@@ -417,9 +435,7 @@ def run_extra(args):
         model.precision = "bf16"
     dist = None
     if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
+        dist = init_dist_quiet(local)
         if training:  # data-parallel replicas, gradient all-reduce by DDP over NCCL (trainer.py:89-91)
             from torch.nn.parallel import DistributedDataParallel as DDP
 
