@@ -19,43 +19,6 @@ __device__ __forceinline__ int ps_src_row(int n, int Cout, int ps_r) {
   return c * rr + q;
 }
 
-// W fp32 [Cout][Cin][taps] -> Wf bf16 [NP][taps*KP] (k = tap*KP + c), Wd bf16 [KP][taps*NP] (dgrad: rows = input
-// channel, k' = tap'*NP + n with tap' = taps-1-tap, i.e. the 180-degree rotated kernel), bias -> bf [NP].
-// Two passes so that BOTH packs are written with consecutive threads on consecutive elements (a single pass left the
-// dgrad pack as 2-byte stores 9*NP*2 bytes apart: 5M scattered sector writes per 256x256 conv).
-__global__ void pack_conv_fwd_kernel(const float* __restrict__ W, const float* __restrict__ b, __nv_bfloat16* Wf, float* bf, int Cout,
-                                     int Cin, int KP, int taps, int ps_r) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Cout * Cin) return;
-  const int n = idx / Cin, c = idx - n * Cin;  // c fastest: Wf[n][t*KP + c]
-  const int sn = ps_src_row(n, Cout, ps_r);
-  const float* src = W + ((size_t)sn * Cin + c) * taps;
-  for (int t = 0; t < taps; ++t) Wf[(size_t)n * taps * KP + (size_t)t * KP + c] = __float2bfloat16_rn(src[t]);
-  if (c == 0 && bf && b) bf[n] = b[sn];
-}
-__global__ void pack_conv_dg_kernel(const float* __restrict__ W, __nv_bfloat16* Wd, int Cout, int Cin, int NP, int taps, int ps_r) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Cout * Cin) return;
-  const int c = idx / Cout, n = idx - c * Cout;  // n fastest: Wd[c][t'*NP + n]
-  const int sn = ps_src_row(n, Cout, ps_r);
-  const float* src = W + ((size_t)sn * Cin + c) * taps;
-  for (int t = 0; t < taps; ++t) Wd[(size_t)c * taps * NP + (size_t)(taps - 1 - t) * NP + n] = __float2bfloat16_rn(src[t]);
-}
-int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int Cout, int Cin, int NP, int KP,
-                         int taps, int ps_r, cudaStream_t s) {
-  const int total = Cout * Cin;
-  if (Wf) {
-    pack_conv_fwd_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, b, (__nv_bfloat16*)Wf, bf, Cout, Cin, KP, taps, ps_r);
-    count_launch();
-  }
-  if (Wd) {
-    pack_conv_dg_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, (__nv_bfloat16*)Wd, Cout, Cin, NP, taps, ps_r);
-    count_launch();
-  }
-  SSR_CUDA(cudaGetLastError());
-  return SSR_OK;
-}
-
 // packed fp32 gradient dWp [NP][taps][KP] -> grad fp32 [Cout][Cin][taps] (PyTorch layout)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dWp, float* grad, int Cout, int Cin, int KP, int taps, int ps_r) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,55 +236,6 @@ __device__ __forceinline__ void lin_map(const LinMap& m, int n, int k, int* np, 
   }
 }
 
-// W fp32 [N][K] -> Wf bf16 [NP][KP] (forward), Wd bf16 [KP][NP] (dgrad: dX = dY Wd^T ... rows = input feature), bias
-__global__ void pack_linear_dev_kernel(const float* __restrict__ W, const float* __restrict__ b, __nv_bfloat16* Wf, float* bf,
-                                       __nv_bfloat16* Wd, int N, int K, int NP, int KP, const LinMap map, int transposed) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * K) return;
-  // pass 0 writes Wf with k fastest, pass 1 writes Wd with n fastest: both store streams are coalesced
-  const int n = transposed ? idx % N : idx / K, k = transposed ? idx / N : idx % K;
-  int np, kp;
-  float sc;
-  lin_map(map, n, k, &np, &kp, &sc);
-  const __nv_bfloat16 v = __float2bfloat16_rn(W[(size_t)n * K + k] * sc);
-  if (!transposed) {
-    Wf[(size_t)np * KP + kp] = v;
-    if (k == 0 && bf && b) bf[np] = b[n] * sc;
-  } else {
-    Wd[(size_t)kp * NP + np] = v;
-  }
-}
-int launch_pack_linear_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int N, int K, int NP, int KP,
-                           const LinMap& map, cudaStream_t s) {
-  if (Wf) {
-    pack_linear_dev_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(W, b, (__nv_bfloat16*)Wf, bf, nullptr, N, K, NP, KP, map, 0);
-    count_launch();
-  }
-  if (Wd) {
-    pack_linear_dev_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(W, b, nullptr, nullptr, (__nv_bfloat16*)Wd, N, K, NP, KP, map, 1);
-    count_launch();
-  }
-  SSR_CUDA(cudaGetLastError());
-  return SSR_OK;
-}
-
-// packed fp32 gradient dWp [NP][KP] -> grad [N][K]; the q-row scale of the pack is the chain-rule factor of the raw weight
-__global__ void unpack_linear_grad_kernel(const float* __restrict__ dWp, float* grad, int N, int K, int KP, const LinMap map) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * K) return;
-  const int n = idx / K, k = idx - n * K;
-  int np, kp;
-  float sc;
-  lin_map(map, n, k, &np, &kp, &sc);
-  grad[idx] = dWp[(size_t)np * KP + kp] * sc;
-}
-int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int KP, const LinMap& map, cudaStream_t s) {
-  unpack_linear_grad_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(dWp, grad, N, K, KP, map);
-  count_launch();
-  SSR_CUDA(cudaGetLastError());
-  return SSR_OK;
-}
-
 // bias gradient of a linear layer: out[n] = scale(n) * sum_m dY[m][np(n)]  (NP = packed width of dY)
 __global__ void __launch_bounds__(256) colsum_final_map_kernel(const float* __restrict__ partial, int strips, int NP, int N,
                                                                const LinMap map, float* out) {
@@ -383,20 +297,6 @@ int launch_deferred_reductions(DeferredRed* dr, cudaStream_t s) {
   SSR_CUDA(cudaGetLastError());
   dr->n = 0;
   dr->used = 0;
-  return SSR_OK;
-}
-
-// relative_position_bias_table [nb][heads] -> [heads][nb] (the layout the attention kernels read)
-__global__ void bias_table_to_head_major_kernel(const float* __restrict__ t, float* out, int nb, int heads) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nb * heads) return;
-  const int h = idx / nb, i = idx - h * nb;
-  out[idx] = t[(size_t)i * heads + h];
-}
-int launch_transpose_table(const float* table, float* out, int nb, int heads, cudaStream_t s) {
-  bias_table_to_head_major_kernel<<<(nb * heads + 255) / 256, 256, 0, s>>>(table, out, nb, heads);
-  count_launch();
-  SSR_CUDA(cudaGetLastError());
   return SSR_OK;
 }
 
@@ -601,20 +501,6 @@ __global__ void grad_nhwc64_kernel(const float* __restrict__ dy, __nv_bfloat16* 
 int launch_grad_nhwc64(const float* dy, void* out, int B, int ch, int cw, int Hs, int Ws, float scale, cudaStream_t s) {
   const long long total = (long long)B * Hs * Ws;
   grad_nhwc64_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(dy, (__nv_bfloat16*)out, B, ch, cw, Hs, Ws, scale);
-  count_launch();
-  SSR_CUDA(cudaGetLastError());
-  return SSR_OK;
-}
-
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* out, size_t n4) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const float4 x = reinterpret_cast<const float4*>(in)[i];
-  reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-}
-int launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s) {
-  SSR_CHECK(n % 4 == 0, SSR_E_INVALID, "f32_to_bf16: n %% 4");
-  f32_to_bf16_kernel<<<(int)((n / 4 + 255) / 256), 256, 0, s>>>(in, (__nv_bfloat16*)out, n / 4);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;

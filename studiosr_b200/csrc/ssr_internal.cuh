@@ -336,23 +336,16 @@ struct LnBwdArgs {
   float* partial;         // scratch, >= kTrainPartialFloats floats (per-CTA partial sums)
 };
 int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s, DeferredRed* dr = nullptr);
-int launch_pack_linear_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int N, int K, int NP, int KP,
-                           const LinMap& map, cudaStream_t s);
-int launch_unpack_linear_grad(const float* dWp, float* grad, int N, int K, int KP, const LinMap& map, cudaStream_t s);
 int launch_colsum_map(const void* dY, int elem, int ld, int M, int NP, int N, const LinMap& map, float* out, float* partial,
                       cudaStream_t s, DeferredRed* dr = nullptr);
 constexpr size_t kTrainPartialFloats = (size_t)592 * 2304;  // column-sum strips x widest packed row
-int launch_transpose_table(const float* table, float* out, int nb, int heads, cudaStream_t s);
 int launch_input_nhwc64(const float* x, void* out, int B, int h, int w, int Hp, int Wp, float scale, const float* shift3,
                         cudaStream_t s);
 int launch_grad_nhwc64(const float* dy, void* out, int B, int ch, int cw, int Hs, int Ws, float scale, cudaStream_t s);
-int launch_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t s);
 // out[i] = bf16(in[i] * scale[i / elems_per_scale])
 int launch_scale_to_bf16(const float* in, const float* scale, size_t elems_per_scale, void* out, size_t n, cudaStream_t s);
 
 // k_train.cu: on-device (re)packing of the fp32 master parameters, gradient unpacking, small backward pieces
-int launch_pack_conv_dev(const float* W, const float* b, void* Wf, float* bf, void* Wd, int Cout, int Cin, int NP, int KP,
-                         int taps, int ps_r, cudaStream_t s);
 int launch_unpack_wgrad(const float* dWp, float* grad, int Cout, int Cin, int KP, int taps, int ps_r, cudaStream_t s);
 int launch_colsum(const void* dY, int elem, int ld, int M, int NP, int Cout, int ps_r, float alpha, float* out, float* partial,
                   cudaStream_t s, DeferredRed* dr = nullptr);
