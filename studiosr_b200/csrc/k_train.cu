@@ -304,16 +304,16 @@ int launch_deferred_reductions(DeferredRed* dr, cudaStream_t s) {
 // LayerNorm backward, one warp per row (rows strided over all warps so dgamma / dbeta partials live in registers):
 //   xhat = (x - mean) rstd;  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
 __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs a) {
-  __shared__ float red[2][8][256];
+  __shared__ float red[3][8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = blockIdx.x * 8 + wib, nwarps = gridDim.x * 8;
   // a lane owns the float4 slots `lane` and `lane + 32` of a row: columns col(j) = 4 * (lane + 32 * (j / 4)) + j % 4
   const int Q = a.CP / 4;
   const bool has1 = lane + 32 < Q;
-  float dg[8], db[8], gam[8];
+  float dg[8], db[8], ds[8], gam[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    dg[j] = db[j] = 0.0f;
+    dg[j] = db[j] = ds[j] = 0.0f;
     const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
     gam[j] = n < a.C ? __ldg(a.gamma + n) : 0.0f;
   }
@@ -390,6 +390,8 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dx[j] *= sc;
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ds[j] += dx[j];  // column sums of Gb: the consumer Linear layer's bias gradient
       uint2* b2 = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.Gb) + (size_t)row * a.ldg);
       if (lane < Q) b2[lane] = make_uint2(pack_bf16x2(dx[0], dx[1]), pack_bf16x2(dx[2], dx[3]));
       if (has1) b2[lane + 32] = make_uint2(pack_bf16x2(dx[4], dx[5]), pack_bf16x2(dx[6], dx[7]));
@@ -401,17 +403,21 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_kernel(const LnBwdArgs a) {
     const int n = 4 * (lane + 32 * (j >> 2)) + (j & 3);
     red[0][wib][n] = dg[j];
     red[1][wib][n] = db[j];
+    red[2][wib][n] = ds[j];
   }
   __syncthreads();
   for (int n = threadIdx.x; n < a.C; n += 256) {
-    float g = 0.0f, b = 0.0f;
+    float g = 0.0f, b = 0.0f, c = 0.0f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       g += red[0][w][n];
       b += red[1][w][n];
+      c += red[2][w][n];
     }
-    a.partial[((size_t)blockIdx.x * 2) * a.C + n] = g;
-    a.partial[((size_t)blockIdx.x * 2 + 1) * a.C + n] = b;
+    const int nacc = a.gb_colsum ? 3 : 2;  // strips: [block][nacc][C]
+    a.partial[((size_t)blockIdx.x * nacc) * a.C + n] = g;
+    a.partial[((size_t)blockIdx.x * nacc + 1) * a.C + n] = b;
+    if (a.gb_colsum) a.partial[((size_t)blockIdx.x * nacc + 2) * a.C + n] = c;
   }
 }
 __global__ void __launch_bounds__(256) ln_bwd_final_kernel(const float* __restrict__ partial, int blocks, int C, float* dgamma,
@@ -428,17 +434,20 @@ int launch_ln_bwd(const LnBwdArgs& a0, cudaStream_t s, DeferredRed* dr) {
             "ln_bwd: C=%d CP=%d", a.C, a.CP);
   SSR_CHECK(!a.dgamma || a.partial, SSR_E_INVALID, "ln_bwd: partial scratch missing");
   const int blocks = min((a.M + 7) / 8, kColsumStrips);
-  float* mine = a.dgamma && dr && dr->n + 2 <= dr->cap ? red_take(dr, (size_t)blocks * 2 * a.C) : nullptr;
+  const int nacc = a.gb_colsum ? 3 : 2;
+  float* mine = a.dgamma && dr && dr->n + nacc <= dr->cap ? red_take(dr, (size_t)blocks * nacc * a.C) : nullptr;
   if (mine) a.partial = mine;
+  SSR_CHECK(!a.gb_colsum || (mine && a.Gb), SSR_E_INVALID, "ln_bwd: gb_colsum needs Gb, dgamma and a deferred-reduction pool");
   ProfScope prof("ln_bwd", 0.0, (double)a.M * a.C * (4 + a.elem_dy + (a.Gin ? 4 : 0) + 4 + (a.Gb ? 2 : 0)), s);
   ln_bwd_kernel<<<blocks, 256, 0, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   if (mine) {
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < nacc; ++which) {
       RedEntry& e = dr->host[dr->n++];
       memset(&e, 0, sizeof(e));
-      e.partial = mine + (size_t)which * a.C; e.out = which ? a.dbeta : a.dgamma; e.strips = blocks; e.stride = 2 * a.C; e.N = a.C;
+      e.partial = mine + (size_t)which * a.C; e.out = which == 0 ? a.dgamma : which == 1 ? a.dbeta : a.gb_colsum; e.strips = blocks;
+      e.stride = nacc * a.C; e.N = a.C;
       e.mode = 2; e.alpha = 1.0f;
     }
   } else if (a.dgamma) {

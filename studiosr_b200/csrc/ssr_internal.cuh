@@ -333,6 +333,8 @@ struct LnBwdArgs {
   int M, C, CP;
   float eps;
   float *dgamma, *dbeta;  // [C], overwritten, or null
+  float* gb_colsum;       // [C] or null: column sums of the values written to Gb = the bias gradient of the Linear layer that
+                          // consumes Gb as its output gradient (needs dgamma and a DeferredRed)
   float* partial;         // scratch, >= kTrainPartialFloats floats (per-CTA partial sums)
 };
 int launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s, DeferredRed* dr = nullptr);

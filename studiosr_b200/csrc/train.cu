@@ -543,8 +543,8 @@ static int add_ln(ssr_train_state* t, const std::string& name, const LNp* p, int
   out->p = p;
   out->gi = find_idx(t, name + ".weight", C);
   out->bi = find_idx(t, name + ".bias", C);
-  t->red_floats += (size_t)592 * 2 * C + 64;
-  t->red_entries += 2;
+  t->red_floats += (size_t)592 * 3 * C + 64;
+  t->red_entries += 3;
   return (out->gi < 0 || out->bi < 0) ? SSR_E_STATE : SSR_OK;
 }
 
@@ -978,7 +978,7 @@ static GemmArgs dgrad_lin(const ssr_model* m, const LinT& l, const void* dY, int
   return g;
 }
 static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const void* X, int M, float* dwp, float* partial,
-                     float* const* grads, cudaStream_t s) {
+                     float* const* grads, cudaStream_t s, bool bias_done = false) {
   const Lin& L = *l.fwd;
   if (grads[l.wi]) {
     WgradArgs a;
@@ -1011,12 +1011,13 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
     e.map = l.map;
     m->train->unpack_host.push_back(e);
   }
-  if (grads[l.bi]) SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, L.NP, l.N, l.map, grads[l.bi], partial, s, &m->train->red));
+  if (grads[l.bi] && !bias_done)  // bias_done: the LayerNorm backward that produced dY already summed its columns
+    SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, L.NP, l.N, l.map, grads[l.bi], partial, s, &m->train->red));
   return SSR_OK;
 }
 static int ln_backward(ssr_train_state* ts, const LnT& l, const float* gamma_dev, const float* x, const void* dy, int elem_dy, const float* Gin, float* Gout,
                        void* Gb, int M, int C, int CP, float* partial, float* const* grads, cudaStream_t s,
-                       const float* gb_scale = nullptr, int rows_per_scale = 1) {
+                       const float* gb_scale = nullptr, int rows_per_scale = 1, float* gb_colsum = nullptr) {
   LnBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x;
@@ -1036,6 +1037,7 @@ static int ln_backward(ssr_train_state* ts, const LnT& l, const float* gamma_dev
   a.partial = partial;
   a.gb_scale = gb_scale;
   a.rows_per_scale = rows_per_scale;
+  a.gb_colsum = (grads[l.gi] && grads[l.bi]) ? gb_colsum : nullptr;
   if (grads[l.gi] && grads[l.bi]) {
     a.dgamma = grads[l.gi];
     a.dbeta = grads[l.bi];
@@ -1130,13 +1132,22 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
       --kblk;
       const Block& blk = L.blocks[bi];
       const BlockT& bt = t->s_blocks[li][bi];
+      // proj / fc2 bias gradients ride in the LayerNorm backward kernels (column sums of the bf16 gradient copy they write):
+      // LN2 backward of block b -> proj bias of b; LN1 backward of block b (b > 0) -> fc2 bias of block b - 1
+      auto sums_ok = [&](int b_) {
+        const BlockT& q = t->s_blocks[li][b_];
+        return grads[q.n1.gi] && grads[q.n1.bi] && grads[q.n2.gi] && grads[q.n2.bi];
+      };
+      const bool ln_sums = sums_ok(bi);
+      const bool fc2_bias_done = bi + 1 < depth && sums_ok(bi + 1);
       const SwinBlockWs& bw = W.blk[li][bi];
       // ---- MLP: t_out = t_mid + fc2(GELU(fc1(LN2(t_mid))))  (swinir.py:172, common.py:184-194) ----
       // with stochastic depth the branch sees dL/dt_out scaled per sample: Gtb = bf16(Gt * drop[2k+1][b])
       // (for the other blocks the LN1 backward of the block after this one already wrote the scaled copy)
       if (drop && bi == depth - 1)
         SSR_TRY(launch_scale_to_bf16(W.Gt, drop + (size_t)(2 * kblk + 1) * B, per_sample, W.Gtb, (size_t)T * CP, s));
-      SSR_TRY(wgrad_lin(m, bt.fc2, W.Gtb, bw.h, T, W.dwp, W.partial, grads, s));
+      // (the bias gradient of fc2 = column sums of Gtb came with the LN1 backward of the block after this one)
+      SSR_TRY(wgrad_lin(m, bt.fc2, W.Gtb, bw.h, T, W.dwp, W.partial, grads, s, fc2_bias_done));
       {
         GemmArgs g = dgrad_lin(m, bt.fc2, W.Gtb, T);
         g.mask = bw.u;  // GELU backward: the forward saved gelu'(u)
@@ -1155,10 +1166,10 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
       }
       // the bf16 copy feeds the attention branch: scaled by its stochastic-depth factor
       SSR_TRY(ln_backward(t, bt.n2, m->dev<float>(blk.norm2.g_off), bw.tmid, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
-                          drop ? drop + (size_t)(2 * kblk) * B : nullptr, Hp * Wp));
+                          drop ? drop + (size_t)(2 * kblk) * B : nullptr, Hp * Wp, ln_sums ? grads[bt.proj.bi] : nullptr));
       // ---- attention: t_mid = t_in + proj(W-MSA(LN1(t_in)))  (swinir.py:149-171) ----
 
-      SSR_TRY(wgrad_lin(m, bt.proj, W.Gtb, bw.o, T, W.dwp, W.partial, grads, s));
+      SSR_TRY(wgrad_lin(m, bt.proj, W.Gtb, bw.o, T, W.dwp, W.partial, grads, s, ln_sums));
       {
         GemmArgs g = dgrad_lin(m, bt.proj, W.Gtb, T);
         g.out_T = W.dO;
@@ -1196,7 +1207,8 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
       }
       // the bf16 copy feeds the MLP branch of the previous block (unused for the first block of a layer)
       SSR_TRY(ln_backward(t, bt.n1, m->dev<float>(blk.norm1.g_off), bw.tin, W.dXn, 2, W.Gt, W.Gt, W.Gtb, T, C, CP, W.partial, grads, s,
-                          (drop && bi > 0) ? drop + (size_t)(2 * (kblk - 1) + 1) * B : nullptr, Hp * Wp));
+                          (drop && bi > 0) ? drop + (size_t)(2 * (kblk - 1) + 1) * B : nullptr, Hp * Wp,
+                          (ln_sums && bi > 0) ? grads[t->s_blocks[li][bi - 1].fc2.bi] : nullptr));
     }
     SSR_TRY(launch_add_inplace(W.G, W.Gt, W.Gb, (size_t)T * CP, s));  // blocks' path joins the group skip
   }
