@@ -181,8 +181,10 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdArgs a) {
       dp[nt][1] = s[nt][1] * (dp[nt][1] - d0);
       dp[nt][2] = s[nt][2] * (dp[nt][2] - d1);
       dp[nt][3] = s[nt][3] * (dp[nt][3] - d1);
-      float2* b0p = reinterpret_cast<float2*>(dB + i0 * 64 + j);
-      float2* b1p = reinterpret_cast<float2*>(dB + i1 * 64 + j);
+      // column index XOR-swizzled by the row (i0 & 7 == i1 & 7 == g): the 8 rows a warp touches per access would all sit in
+      // the same banks (row pitch 256 B) -- 8-way conflicts on 64 read-modify-writes per window
+      float2* b0p = reinterpret_cast<float2*>(dB + i0 * 64 + (j ^ (g << 3)));
+      float2* b1p = reinterpret_cast<float2*>(dB + i1 * 64 + (j ^ (g << 3)));
       float2 x = *b0p, y = *b1p;
       x.x += dp[nt][0]; x.y += dp[nt][1]; y.x += dp[nt][2]; y.y += dp[nt][3];
       *b0p = x;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdArgs a) {
   }
   __syncthreads();
   float* out = a.dB + (size_t)h * 64 * 64;
-  for (int e = tid; e < 64 * 64; e += 128) atomicAdd(out + e, dB[e]);
+  for (int e = tid; e < 64 * 64; e += 128) atomicAdd(out + e, dB[(e & ~63) + ((e & 63) ^ (((e >> 6) & 7) << 3))]);
 }
 
 // dB [heads][64][64] -> d(relative_position_bias_table) [225][heads] (swinir.py:57-67, 92-95): entries (i, j) with the
