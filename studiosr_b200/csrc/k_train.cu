@@ -602,15 +602,18 @@ __global__ void __launch_bounds__(256) unpack_batched_kernel(const PackEntry* __
   if (idx >= e.N * e.K) return;
   const int n = idx / e.K, k = idx - n * e.K;
   float* grad = reinterpret_cast<float*>(e.Wf);
+  float* gbias = const_cast<float*>(e.b);  // destination of the bias gradient (its packed source is e.bf), or null
   if (e.kind == 0) {
     const int sn = ps_src_row(n, e.N, e.ps_r);
     float* dst = grad + ((size_t)sn * e.K + k) * e.taps;
     for (int t = 0; t < e.taps; ++t) dst[t] = e.W[((size_t)n * e.taps + t) * e.KP + k];
+    if (k == 0 && gbias && e.bf) gbias[sn] = e.bf[n];
   } else {
     int np, kp;
     float sc;
     lin_map(e.map, n, k, &np, &kp, &sc);
     grad[idx] = e.W[(size_t)np * e.KP + kp] * sc;
+    if (k == 0 && gbias && e.bf) gbias[n] = e.bf[np] * sc;
   }
 }
 int launch_unpack_batched(const PackEntry* host, PackEntry* dev, int n, cudaStream_t s) {

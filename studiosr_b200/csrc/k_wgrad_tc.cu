@@ -56,12 +56,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   auto empty_bar = [&](int s) { return bar0 + 8u * (WG_STAGES + s); };
   const uint32_t done_bar = bar0 + 8u * (2 * WG_STAGES);
 
+  // bias gradient: the CTAs of the centre tap (tap 0 of a Linear) and the first column block also sum the columns of the dY
+  // tiles; their four epilogue warps, idle during the main loop, read each stage and co-sign its release
+  const bool do_bias = a.dBp != nullptr && (blockIdx.x / geo.splits) % geo.n_blocks == 0 &&
+                       ((blockIdx.x / geo.splits) / geo.n_blocks) % a.taps == (a.taps == 9 ? 4 : 0);
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmY);
     prefetch_tmap(&tmX);
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), do_bias ? 5 : 1);
     }
     mbar_init(done_bar, 1);
     fence_barrier_init();
@@ -137,6 +141,48 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   } else if (warp < 6) {
     const int quad = warp & 3;
     const int row = m0 + quad * 32 + lane;
+    if (do_bias) {
+      // 128 threads = 16 column groups (8 channels = one 16-byte chunk) x 8 row lanes; a thread adds rows rl, rl + 8, ... of its
+      // chunk with LDS.128 (the 8 row lanes of a quarter-warp hit 8 different swizzled chunks: conflict-free) into 8 fp32
+      // accumulators; the row lanes meet by shuffles after the last stage.  te = thread index among the epilogue warps.
+      const int te = (warp - 2) * 32 + lane;
+      const int cg = te >> 3, rl = te & 7;  // column group 0..15 (block = cg >> 3), row lane
+      const uint8_t* gbase = smem + (cg >> 3) * 8192;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % WG_STAGES;
+        mbar_wait_warp(full_bar(s), (uint32_t)(it / WG_STAGES) & 1u, lane);
+        const uint8_t* tile = gbase + s * WG_STAGE;
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const int r = r8 * 8 + rl;  // r & 7 == rl
+          const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + ((((cg & 7)) ^ rl) << 4));
+          acc[0] += __uint_as_float(u.x << 16); acc[1] += __uint_as_float(u.x & 0xffff0000u);
+          acc[2] += __uint_as_float(u.y << 16); acc[3] += __uint_as_float(u.y & 0xffff0000u);
+          acc[4] += __uint_as_float(u.z << 16); acc[5] += __uint_as_float(u.z & 0xffff0000u);
+          acc[6] += __uint_as_float(u.w << 16); acc[7] += __uint_as_float(u.w & 0xffff0000u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+      }
+      if (rl == 0 && n_iter > 0) {
+        const int colb = cg * 8;  // first of this thread's 8 channels within the 128-row block
+        const bool blk_valid = colb < 64 || m1 == m0 + 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rrow = m0 + colb + i;
+          if (blk_valid && rrow < a.NoutP) atomicAdd(a.dBp + rrow, acc[i] * a.alpha);
+        }
+      }
+    }
     mbar_wait_warp(done_bar, 0, lane);
     tc_fence_after();
     if (n_iter > 0) {

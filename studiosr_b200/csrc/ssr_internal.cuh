@@ -255,6 +255,8 @@ struct WgradArgs {
   int taps;
   int NoutP, CinP;  // padded widths (multiples of 64) of dY / X that take part
   float* dWp;       // fp32 [NoutP][taps][CinP], accumulated into (zero it first)
+  float* dBp;       // fp32 [NoutP] or null: packed bias gradient alpha * sum_p dY[p][n], accumulated into (zero it first) --
+                    // the column sums of the dY tiles that stream through shared memory anyway, by the otherwise idle epilogue warps
   float alpha;
   int N_alg, K_alg;  // un-padded widths (accounting)
 };

@@ -20,6 +20,7 @@ struct ConvT {       // a trainable conv3x3 executed by the implicit-GEMM kernel
   int Cout = 0, Cin = 0;
   size_t dg_off = 0;     // dgrad pack in train->arena2: bf16 [KP][9*NP]
   size_t dwp_off = 0;    // packed fp32 weight gradient [NP][9][KP] (float offset into the dwp workspace block)
+  size_t dbp_off = 0;    // packed fp32 bias gradient [NP] (same block)
 };
 
 struct LinT {  // a trainable nn.Linear executed by the GEMM kernels
@@ -29,6 +30,7 @@ struct LinT {  // a trainable nn.Linear executed by the GEMM kernels
   LinMap map{};
   size_t dg_off = 0;   // dgrad pack in arena2: bf16 [KP][NP]
   size_t dwp_off = 0;  // packed fp32 weight gradient [NP][KP]
+  size_t dbp_off = 0;  // packed fp32 bias gradient [NP]
 };
 struct LnT {
   const LNp* p = nullptr;
@@ -59,7 +61,7 @@ struct ssr_train_state {
   std::vector<PackEntry> pack_host, unpack_host;
   // EDSR
   int head_w = -1, head_b = -1;
-  size_t head_dwp = 0;
+  size_t head_dwp = 0, head_dbp = 0;
   std::vector<int> e_res_a, e_res_b, e_up;  // indices into convs
   int e_body_tail = -1, e_last = -1;
   // SwinIR
@@ -105,6 +107,8 @@ static int add_conv(ssr_train_state* t, const std::string& name, const Lin* fwd,
   *a2 += (size_t)fwd->KP * 9 * fwd->NP * 2;
   c.dwp_off = t->dwp_floats;
   t->dwp_floats += (size_t)fwd->NP * 9 * fwd->KP;
+  c.dbp_off = t->dwp_floats;
+  t->dwp_floats += (size_t)fwd->NP;
   t->red_floats += (size_t)592 * fwd->NP + 64;
   t->red_entries += 1;
   t->convs.push_back(c);
@@ -122,6 +126,8 @@ static int bind_edsr(ssr_model* m) {
   if (t->head_w < 0 || t->head_b < 0) return SSR_E_STATE;
   t->head_dwp = t->dwp_floats;
   t->dwp_floats += (size_t)m->FP * 9 * 64;
+  t->head_dbp = t->dwp_floats;
+  t->dwp_floats += (size_t)m->FP;
   t->red_floats += (size_t)592 * m->FP + 64;
   t->red_entries += 1;
   char nm[64];
@@ -375,6 +381,9 @@ static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const 
     a.NoutP = L.NP;
     a.CinP = L.KP;
     a.dWp = dwp + c.dwp_off;
+    // (the in-kernel bias gradient is a Linear-layer feature: with nine taps only the centre-tap CTAs would carry the extra
+    // column sums and become the critical path of the launch -- measured +0.9 ms on cfg2 against 0.64 ms of column sums saved)
+    a.dBp = nullptr;
     a.alpha = alpha;
     a.N_alg = c.Cout;
     a.K_alg = c.Cin;
@@ -383,6 +392,8 @@ static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const 
     memset(&e, 0, sizeof(e));
     e.W = dwp + c.dwp_off;
     e.Wf = grads[c.wi];
+    e.bf = a.dBp;
+    e.b = grads[c.bi];
     e.kind = 0;
     e.N = c.Cout;
     e.K = c.Cin;
@@ -391,7 +402,8 @@ static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const 
     e.ps_r = L.ps_r;
     m->train->unpack_host.push_back(e);
   }
-  if (grads[c.bi]) SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s, &m->train->red));
+  if (grads[c.bi])
+    SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s, &m->train->red));
   return SSR_OK;
 }
 
@@ -498,6 +510,7 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     a.NoutP = FP;
     a.CinP = 64;
     a.dWp = W.dwp + t->head_dwp;
+    a.dBp = nullptr;
     a.alpha = 1.0f;
     a.N_alg = m->F;
     a.K_alg = 3;
@@ -506,6 +519,8 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     memset(&e, 0, sizeof(e));
     e.W = W.dwp + t->head_dwp;
     e.Wf = grads[t->head_w];
+    e.bf = a.dBp;
+    e.b = grads[t->head_b];
     e.kind = 0;
     e.N = m->F;
     e.K = 3;
@@ -536,6 +551,8 @@ static int add_linear(ssr_train_state* t, const std::string& name, const Lin* fw
   *a2 += (size_t)fwd->KP * fwd->NP * 2;
   out->dwp_off = t->dwp_floats;
   t->dwp_floats += (size_t)fwd->NP * fwd->KP;
+  out->dbp_off = t->dwp_floats;
+  t->dwp_floats += (size_t)fwd->NP;
   t->red_floats += (size_t)592 * fwd->NP + 64;
   t->red_entries += 1;
   return SSR_OK;
@@ -563,6 +580,8 @@ static int bind_swinir(ssr_model* m) {
   if (t->head_w < 0 || t->head_b < 0) return SSR_E_STATE;
   t->head_dwp = t->dwp_floats;
   t->dwp_floats += (size_t)m->CP * 9 * 64;
+  t->head_dbp = t->dwp_floats;
+  t->dwp_floats += (size_t)m->CP;
   t->red_floats += (size_t)592 * m->CP + 64;
   t->red_entries += 1;
   SSR_TRY(add_ln(t, "patch_embed.norm", &m->pe_norm, C, &t->s_pe));
@@ -996,6 +1015,7 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
     a.NoutP = L.NP;
     a.CinP = L.KP;
     a.dWp = dwp + l.dwp_off;
+    a.dBp = (grads[l.bi] && !bias_done) ? dwp + l.dbp_off : nullptr;
     a.alpha = 1.0f;
     a.N_alg = l.N;
     a.K_alg = l.K;
@@ -1004,6 +1024,8 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
     memset(&e, 0, sizeof(e));
     e.W = dwp + l.dwp_off;
     e.Wf = grads[l.wi];
+    e.bf = a.dBp;
+    e.b = a.dBp ? grads[l.bi] : nullptr;
     e.kind = 1;
     e.N = l.N;
     e.K = l.K;
@@ -1012,7 +1034,7 @@ static int wgrad_lin(const ssr_model* m, const LinT& l, const void* dY, const vo
     e.map = l.map;
     m->train->unpack_host.push_back(e);
   }
-  if (grads[l.bi] && !bias_done)  // bias_done: the LayerNorm backward that produced dY already summed its columns
+  if (grads[l.bi] && !bias_done && !grads[l.wi])  // bias_done: the LayerNorm backward that produced dY already summed its columns
     SSR_TRY(launch_colsum_map(dY, 2, L.NP, M, L.NP, l.N, l.map, grads[l.bi], partial, s, &m->train->red));
   return SSR_OK;
 }
@@ -1230,6 +1252,7 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
     a.NoutP = CP;
     a.CinP = 64;
     a.dWp = W.dwp + t->head_dwp;
+    a.dBp = nullptr;
     a.alpha = 1.0f;
     a.N_alg = C;
     a.K_alg = 3;
@@ -1238,6 +1261,8 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
     memset(&e, 0, sizeof(e));
     e.W = W.dwp + t->head_dwp;
     e.Wf = grads[t->head_w];
+    e.bf = a.dBp;
+    e.b = grads[t->head_b];
     e.kind = 0;
     e.N = C;
     e.K = 3;
