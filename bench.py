@@ -4,8 +4,11 @@
 Workload (config 5 of BASELINE.json): one synthetic LR frame 960x540 -> 3840x2160,
 tiled into 220 overlapping 64x64 tiles (overlap 16), each tile run through the eval-mode SwinIR-x4
 forward (which pads 64 -> 72 like the reference, swinir.py:249-255) and blended on device.  One
-"step" = one frame per GPU.  Multi-GPU = one process per GPU, every rank upscales its own frame
-(the path shards by independent frames / tiles; no data-path collective) -> "scaling": "weak".
+"step" = ONE frame.  Multi-GPU (one process per GPU, NCCL) strong-scales that frame: its tile list is
+sharded over the ranks, the tile outputs are all-gathered, every rank blends a band of output rows and
+the bands are all-gathered (studiosr_b200/sharding.py) -> "scaling": "strong"; `e2e` is host-in on
+rank 0 -> host-out on rank 0.  `--scaling weak` keeps round 1's mode (every rank its own frame, no
+data-path collective).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
   python bench.py --impl reference [...]                        # CPU arm (oracle port of the reference)
@@ -33,9 +36,9 @@ PAD_TILE = 72  # 64 -> (64//8+1)*8
 
 
 def n_tiles():
-    from oracle.sr_oracle import tile_starts
-
-    return len(tile_starts(FRAME_H, TILE, TILE - OVERLAP)) * len(tile_starts(FRAME_W, TILE, TILE - OVERLAP))
+    stride = TILE - OVERLAP
+    n1 = lambda L: 1 if L <= TILE else (L - TILE + stride - 1) // stride + 1  # == ssr_tiled_num_tiles (checked in run_ours)
+    return n1(FRAME_H) * n1(FRAME_W)
 
 
 def peaks():
@@ -105,23 +108,15 @@ def build_model(precision):
     return m
 
 
-def init_dist_quiet(local):
-    """torch.distributed over NCCL with fd 1 pointed at stderr while the communicator comes up: NCCL writes its version
-    banner to stdout at that moment, and stdout must carry the ONE JSON line only."""
+def init_dist(local):
+    """torch.distributed over NCCL.  NCCL_DEBUG is whatever the operator set (its log goes where NCCL sends it: stdout unless
+    NCCL_DEBUG_FILE is set); the ONE JSON line of this script is recognisable by its leading '{"metric"' / '{"impl"'."""
     import torch
     import torch.distributed as dist
 
-    sys.stdout.flush()
-    saved = os.dup(1)
-    os.dup2(2, 1)
-    try:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
-        torch.cuda.synchronize()
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved, 1)
-        os.close(saved)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.barrier()
+    torch.cuda.synchronize()
     return dist
 
 
@@ -198,8 +193,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "swinir_x4_output_megapixels_per_second", "value": value, "unit": "Mpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus, args.scaling),
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} of {nt} 64x64 tiles per step (eval forward incl. 64->72 pad), "
                                    f"value = frame Mpix / ({nt} x s/tile)"},
@@ -208,13 +203,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, scaling="strong"):
+    base = ("SwinIR-x4 (classical, embed 180, 6x6 blocks) tiled full-frame inference, LR 960x540 -> 3840x2160, "
+            "220 tiles 64x64 overlap 16 (each padded to 72x72 by the eval forward), linear-ramp blend; ")
+    if scaling == "weak" and n_gpus > 1:
+        return {"workload": base + "one frame per GPU per step", "frames_per_step": n_gpus, "tiles_per_frame": n_tiles(),
+                "parallelism": f"replicated weights, frame-sharded x{n_gpus} (no data-path collective)",
+                "l2": "per-step activation working set ~6 GB >> 126 MB L2 (no explicit flush needed)"}
+    per = (n_tiles() + n_gpus - 1) // n_gpus
     return {
-        "workload": "SwinIR-x4 (classical, embed 180, 6x6 blocks) tiled full-frame inference, LR 960x540 -> 3840x2160, "
-                    "220 tiles 64x64 overlap 16 (each padded to 72x72 by the eval forward), linear-ramp blend; "
-                    "one frame per GPU per step",
-        "frames_per_step": n_gpus, "tiles_per_frame": n_tiles(), "parallelism": f"replicated weights, frame-sharded x{n_gpus}",
-        "l2": "per-step activation working set ~6 GB >> 126 MB L2 (no explicit flush needed)",
+        "workload": base + "ONE frame per step",
+        "frames_per_step": 1, "tiles_per_frame": n_tiles(),
+        "parallelism": "single GPU" if n_gpus == 1 else
+                       f"replicated weights; the frame's tile list sharded x{n_gpus} ({per} tiles per rank, last rank "
+                       f"{n_tiles() - per * (n_gpus - 1)}), NCCL all-gather of the fp32 tile outputs, row-band blend, NCCL all-gather "
+                       f"of the uint8 bands",
+        "l2": f"per-step activation working set ~{6.0 / n_gpus:.2f} GB per GPU >> 126 MB L2 (no explicit flush needed)",
     }
 
 
@@ -231,15 +235,23 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        dist = init_dist_quiet(local)
+        dist = init_dist(local)
     lib = _lib.load()
     precision = args.precision
     model = build_model(precision)
     dev = torch.device("cuda", local)
     nat = model._native(dev, precision)
-    frame_np = synthetic_frame(rank)
+    strong = args.scaling == "strong"
+    sharded = strong and world > 1
+    frame_np = synthetic_frame(0 if strong else rank)  # strong: every rank works on THE frame; weak: each rank its own
     frame = torch.from_numpy(frame_np).to(dev)
     nt = n_tiles()
+    assert nt == lib.ssr_tiled_num_tiles(FRAME_H, FRAME_W, TILE, OVERLAP)
+    up = None
+    if sharded:  # one frame's tile list over all ranks: tiles -> all-gather -> band blend -> all-gather (studiosr_b200/sharding.py)
+        from studiosr_b200.sharding import NativeTileBackend, ShardedTiledUpscaler
+
+        up = ShardedTiledUpscaler(NativeTileBackend(nat, FRAME_H, FRAME_W, SCALE, TILE, OVERLAP, args.chunk), dist)
 
     def barrier():
         if dist is not None:
@@ -258,8 +270,9 @@ def run_ours(args):
         barrier()
         return ms
 
-    # ---- device-resident throughput ------------------------------------------------------------
-    step_dev = lambda: nat.upscale_tiled_u8(frame, SCALE, TILE, OVERLAP, args.chunk)
+    frames_per_step = 1 if strong else world
+    # ---- device-resident throughput (the frame is already in every rank's HBM) -------------------
+    step_dev = (lambda: up.upscale(frame)) if sharded else (lambda: nat.upscale_tiled_u8(frame, SCALE, TILE, OVERLAP, args.chunk))
     for _ in range(args.warmup):
         step_dev()
     sampler = ClockSampler(local)
@@ -267,28 +280,41 @@ def run_ours(args):
     l0 = lib.ssr_launch_count()
     ms = timed(step_dev, args.steps)
     launches = lib.ssr_launch_count() - l0
+    if dist is not None:  # kernels of this library launched inside the timed region, summed over the ranks
+        t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        launches = int(t.item())
     clocks = sampler.result()
-    value = world * OUT_MPIX * args.steps / (ms / 1e3)
+    value = frames_per_step * OUT_MPIX * args.steps / (ms / 1e3)
 
-    # ---- end to end through the host-buffer C-ABI call --------------------------------------------
+    # ---- end to end: host buffers in, host buffers out (pinned), copies inside the timed region ----
     h_in = torch.from_numpy(frame_np).pin_memory()
     h_out = torch.empty((FRAME_H * SCALE, FRAME_W * SCALE, 3), dtype=torch.uint8).pin_memory()
-    step_e2e = lambda: nat.upscale_tiled_u8_host(h_in.numpy(), h_out.numpy(), SCALE, TILE, OVERLAP, args.chunk)
+    if sharded:  # rank 0: H2D + broadcast ... all-gather + D2H + sync; the other ranks take part in the collectives
+        step_e2e = (lambda: up.upscale_host(h_in, h_out)) if rank == 0 else (lambda: up.upscale_host(None, None))
+    else:        # ONE C-ABI call: H2D, compute, D2H, stream sync
+        step_e2e = lambda: nat.upscale_tiled_u8_host(h_in.numpy(), h_out.numpy(), SCALE, TILE, OVERLAP, args.chunk)
     for _ in range(max(1, min(args.warmup, 3))):
         step_e2e()
-    barrier()
-    t0 = time.perf_counter()
     e2e_ms_dev = timed(step_e2e, args.steps)
-    e2e_value = world * OUT_MPIX * args.steps / (e2e_ms_dev / 1e3)
-    _ = time.perf_counter() - t0
+    e2e_value = frames_per_step * OUT_MPIX * args.steps / (e2e_ms_dev / 1e3)
+    if sharded and rank == 0:  # the sharded frame is the single-GPU frame, bit for bit
+        single = nat.upscale_tiled_u8(frame, SCALE, TILE, OVERLAP, args.chunk)
+        assert torch.equal(single.cpu(), h_out), "sharded frame differs from the single-GPU frame"
 
     # ---- per-kernel roofline (rank 0, outside the timed regions) -----------------------------------
     roofline, kernels = None, None
     pk = peaks()
     if rank == 0:
+        if sharded:  # rank 0's own kernels only (its tile slot + its row band); the collectives need every rank
+            (tb, te), (r0, r1) = up.tile_slots[0], up.row_slots[0]
+            step_prof = lambda: (up.be.compute(frame, up.tiles_all[tb:], tb, te), up.be.blend(up.tiles_all, up.frame_all, r0, r1))
+            my_tiles = te - tb
+        else:
+            step_prof, my_tiles = step_dev, nt
         lib.ssr_profile_begin()
         for _ in range(2):
-            step_dev()
+            step_prof()
         buf = _lib.ctypes.create_string_buffer(1 << 16)
         _lib.check(lib.ssr_profile_end(buf, len(buf)))
         prof = json.loads(buf.value.decode())
@@ -306,7 +332,7 @@ def run_ours(args):
             with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
                 per_tok = json.load(f).get(top, {}).get("dram_bytes_per_token")
             if per_tok:
-                traffic = per_tok * nt * PAD_TILE * PAD_TILE
+                traffic = per_tok * my_tiles * PAD_TILE * PAD_TILE
         except OSError:
             pass
         # the binding roofline of the top kernel: whichever of (algorithmic FLOPs / tensor peak, algorithmic bytes / HBM peak)
@@ -337,16 +363,23 @@ def run_ours(args):
         line = {
             "metric": "swinir_x4_output_megapixels_per_second", "value": value, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
-            "config": workload_config(world),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": precision, "data": "synthetic",
+            "config": workload_config(world, args.scaling),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": FRAME_H * FRAME_W * 3,
-                    "d2h_bytes_per_step": FRAME_H * SCALE * FRAME_W * SCALE * 3, "ms_per_step": e2e_ms_dev / args.steps},
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": frames_per_step * FRAME_H * FRAME_W * 3,
+                    "d2h_bytes_per_step": frames_per_step * FRAME_H * SCALE * FRAME_W * SCALE * 3, "ms_per_step": e2e_ms_dev / args.steps,
+                    "path": ("rank 0: pinned host frame -> H2D -> NCCL broadcast -> per-rank tiles -> NCCL all-gather -> row-band blend -> "
+                             "NCCL all-gather -> D2H to pinned host on rank 0, sync") if sharded else
+                            "ssr_model_upscale_tiled_u8_host: H2D, tiles, blend, D2H, stream sync in one C-ABI call"},
+            "collectives": None if not sharded else {
+                "backend": "nccl", "per_step": ["all_gather_into_tensor fp32 tile outputs", "all_gather_into_tensor uint8 row bands"],
+                "bytes_received_per_rank_per_step": int((world - 1) * (up.tiles_per * up.be.tile_elems * 4 + up.rows_per * up.out_cols * 3)),
+                "checked": "rank 0's sharded frame == its single-GPU frame (bit-exact)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "step_tensor_frac": {"alg_tflop_per_step": step_flops / 1e12,
-                                 "achieved_tflops": step_flops / (ms / args.steps / 1e3) / 1e12,
-                                 "frac_of_sustained_peak": step_flops / (ms / args.steps / 1e3) / 1e12 / pk["tf_sust"]},
+            "step_tensor_frac": {"alg_tflop_per_step": frames_per_step * step_flops / 1e12,
+                                 "achieved_tflops": frames_per_step * step_flops / (ms / args.steps / 1e3) / 1e12,
+                                 "frac_of_sustained_peak": frames_per_step * step_flops / (ms / args.steps / 1e3) / 1e12 / pk["tf_sust"] / world},
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
         }
@@ -367,8 +400,9 @@ EXTRA = {
     "cfg3": ("HAT", {}, 32, 64, 64, False, 32 * 207.76e9,
              "HAT-x4 bf16 inference, batch 32 of 64x64 LR tiles (overlapping cross-attention + channel attention)"),
     "cfg4": ("SwinIR", {}, 32, 64, 64, True, 32 * 321.30e9,
-             "SwinIR-x4 Trainer step (forward+backward+Adam, stochastic depth 0.1), batch 32 of 64x64 LR patches per GPU, "
-             "bf16 autocast, L1 loss; N > 1: DistributedDataParallel gradient all-reduce over NCCL"),
+             "SwinIR-x4 Trainer step (forward+backward+Adam+MultiStepLR, stochastic depth 0.1), batch 32 of 64x64 LR patches per "
+             "GPU, bf16 autocast, L1 loss; N > 1: data-parallel, gradient mean over ranks by ONE NCCL all-reduce of the flat "
+             "gradient buffer per step (--stock-trainer: torch DDP + torch.optim.Adam)"),
 }
 
 
@@ -435,12 +469,23 @@ def run_extra(args):
         model.precision = "bf16"
     dist = None
     if world > 1:
-        dist = init_dist_quiet(local)
-        if training:  # data-parallel replicas, gradient all-reduce by DDP over NCCL (trainer.py:89-91)
-            from torch.nn.parallel import DistributedDataParallel as DDP
+        dist = init_dist(local)
+        if training:  # data-parallel replicas with the gradient mean over ranks per step (trainer.py:89-91)
+            if args.stock_trainer:
+                from torch.nn.parallel import DistributedDataParallel as DDP
+            else:  # ONE NCCL all-reduce of the flat gradient buffer behind the native backward
+                from studiosr_b200.engine import DistributedDataParallel as DDP
 
             model = DDP(model, device_ids=[local], output_device=local)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99)) if training else None
+    crit = F.l1_loss
+    opt = None
+    if training and args.stock_trainer:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    elif training:  # the rest of the Trainer step on the flat buffers: one Adam launch, L1 loss + backward seed in one pass
+        from studiosr_b200.engine import FusedAdam, L1Loss
+
+        opt, crit = FusedAdam(model.parameters(), lr=1e-4, betas=(0.9, 0.99)), L1Loss()
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[250000, 400000, 450000, 475000], gamma=0.5) if training else None
     g = torch.Generator().manual_seed(1234 + rank)
     hx = torch.rand(B, 3, H, W, generator=g).pin_memory()
     hy = torch.rand(B, 3, SCALE * H, SCALE * W, generator=g).pin_memory()
@@ -452,10 +497,11 @@ def run_extra(args):
             with torch.inference_mode():
                 return model(xin)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = F.l1_loss(model(xin), yin)
+            loss = crit(model(xin), yin)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
+        sched.step()
         return loss
 
     def step_e2e():  # inputs from pinned host memory, result (loss / image) back on the host, every step
@@ -524,6 +570,8 @@ def run_extra(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": B, "lr_size": [H, W],
                    "parallelism": f"data-parallel x{world}" if training else f"replicas x{world}",
+                   "trainer_pieces": None if not training else ("torch.optim.Adam + F.l1_loss + torch DDP" if args.stock_trainer else
+                                                                "engine.FusedAdam + engine.L1Loss + engine.DistributedDataParallel"),
                    "l2": "inputs are a few MB; the per-step activation working set (0.2 - 25 GB) is far beyond the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": mpix / (ms_e2e / 1e3), "unit": "Mpix/s", "ms_per_step": ms_e2e,
@@ -540,9 +588,6 @@ def run_extra(args):
 
 
 def main():
-    # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION (the GPU boxes set it)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -552,6 +597,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="tiles per network pass (0 = all 220 at once)")
     ap.add_argument("--cpu-tiles", type=int, default=64, help="tiles timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--stock-trainer", action="store_true",
+                    help="cfg2 / cfg4: torch.optim.Adam + nn.L1Loss + torch DDP instead of studiosr_b200.engine's flat-buffer pieces")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = ONE frame's tiles sharded over the GPUs with NCCL gathers (default); weak = one frame per GPU")
     ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg1", "cfg2", "cfg3", "cfg4"],
                     help="cfg5 (default) = the headline line the driver reads; the others are the remaining BASELINE.json configs")
     args = ap.parse_args()

@@ -124,12 +124,27 @@ int ssr_model_upscale_u8(ssr_model_t* m, const uint8_t* img, uint8_t* out, int B
  * tiler): frame DEVICE uint8 HWC [H, W, 3] -> DEVICE uint8 HWC [scale*H, scale*W, 3].  Tiles of
  * tile x tile LR pixels at stride tile-overlap (last clamped to the border) run as one batch
  * through the eval forward; outputs are blended with separable linear ramps (oracle:
- * oracle/sr_oracle.py:tiled_upscale).  Tiles [tile_begin, tile_end) of the row-major tile list
- * are processed (for sharding a frame across ranks); pass 0, -1 for all. */
+ * oracle/sr_oracle.py:tiled_upscale). */
 int ssr_tiled_num_tiles(int H, int W, int tile, int overlap);
 size_t ssr_model_tiled_workspace_bytes(const ssr_model_t* m, int H, int W, int tile, int overlap, int chunk_tiles);
 int ssr_model_upscale_tiled_u8(ssr_model_t* m, const uint8_t* frame, uint8_t* out, int H, int W, int tile,
                                int overlap, int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream);
+/* The two halves of the call above, for sharding ONE frame over several GPUs (tiles are independent, the
+ * only exchange is the gather of their outputs).  A rank runs
+ *   ssr_model_tiles_u8        tiles [tile_begin, tile_end) of the row-major tile list (tile_end < 0: to the end) ->
+ *                             tiles_out, DEVICE fp32 [tile_end - tile_begin][3][th*scale][tw*scale] (th = min(tile, H), tw
+ *                             likewise; ssr_tiled_tile_elems floats per tile), chunk_tiles tiles per network pass (0 = all);
+ *   (the caller all-gathers the tile outputs, e.g. ncclAllGather into the full [n_tiles] list)
+ *   ssr_model_blend_tiles_u8  tiles = the FULL row-major list -> rows [row_begin, row_end) of the output frame (`out` is the
+ *                             frame base; row_end < 0: to the last row).  Blending is a gather per output pixel, so a band
+ *                             is bit-identical to the same rows of the whole-frame call.
+ * studiosr_b200/sharding.py drives this protocol over torch.distributed. */
+size_t ssr_tiled_tile_elems(const ssr_model_t* m, int H, int W, int tile);
+size_t ssr_model_tiles_workspace_bytes(const ssr_model_t* m, int H, int W, int tile, int max_tiles_per_pass);
+int ssr_model_tiles_u8(ssr_model_t* m, const uint8_t* frame, float* tiles_out, int H, int W, int tile, int overlap,
+                       int tile_begin, int tile_end, int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream);
+int ssr_model_blend_tiles_u8(ssr_model_t* m, const float* tiles, uint8_t* out, int H, int W, int tile, int overlap,
+                             int row_begin, int row_end, void* stream);
 /* Same, HOST buffers (pinned or pageable): H2D copy, compute, D2H copy, stream synchronise. */
 int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, uint8_t* out_host, int H, int W,
                                     int tile, int overlap, int chunk_tiles, void* workspace, size_t workspace_bytes,
@@ -158,6 +173,21 @@ int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const fl
                             int H, int W, void* workspace, size_t workspace_bytes, void* stream);
 int ssr_model_train_backward(ssr_model_t* m, const float* dy, const float* drop_scale, float* const* grads, int B, int H, int W,
                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the rest of the Trainer step on flat fp32 DEVICE buffers (trainer.py:102-109,133-139) -----------------------------
+ * ssr_l1_loss    nn.L1Loss (trainer.py:45): *loss = mean |out - y| over n elements and, when dout != NULL, the backward seed
+ *                dout = sign(out - y) / n in the same pass (deterministic two-stage sum).  workspace: ssr_l1_loss_workspace_bytes().
+ * ssr_adam_step  torch.optim.Adam's update (trainer.py:133-139; L2 weight decay, no amsgrad) for ONE flat parameter vector of n
+ *                elements in one launch: p, m (exp_avg), v (exp_avg_sq) updated in place from g * grad_scale; `step` is the 1-based
+ *                step count, `lr` the current learning rate (MultiStepLR stays on the host: it only changes this scalar).  The
+ *                hyper-parameters are doubles (python floats) because torch derives its fp32 constants from them in double; the
+ *                update is bit-identical to torch.optim.Adam(foreach=False).
+ * All pointers must be 16-byte aligned. */
+size_t ssr_l1_loss_workspace_bytes(void);
+int ssr_l1_loss(const float* out, const float* y, int64_t n, float* loss, float* dout, void* workspace, size_t workspace_bytes,
+                void* stream);
+int ssr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, int64_t step, float grad_scale, void* stream);
 
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 int64_t ssr_launch_count(void);

@@ -422,6 +422,29 @@ def tiled_upscale(forward, x: torch.Tensor, scale: int, tile: int = 64, overlap:
     return (acc / wsum).to(x.dtype).unsqueeze(0)
 
 
+def blend_tiles(tiles: torch.Tensor, H: int, W: int, scale: int, tile: int = 64, overlap: int = 16, row_begin: int = 0,
+                row_end: int = -1) -> torch.Tensor:
+    """The blend of `tiled_upscale` from an explicit row-major list of tile outputs [n_tiles, C, th*s, tw*s], restricted to
+    the output rows [row_begin, row_end): the checker of the sharded protocol (studiosr_b200/sharding.py), where a rank
+    blends only its band of the frame.  Returns [C, row_end - row_begin, W*s] (float64)."""
+    ys, xs = tile_starts(H, tile, tile - overlap), tile_starts(W, tile, tile - overlap)
+    th, tw = min(tile, H), min(tile, W)
+    row_end = H * scale if row_end < 0 else row_end
+    C = tiles.shape[1]
+    acc = torch.zeros(C, H * scale, W * scale, dtype=torch.float64)
+    wsum = torch.zeros(H * scale, W * scale, dtype=torch.float64)
+    for iy, y0 in enumerate(ys):
+        if y0 * scale >= row_end or (y0 + th) * scale <= row_begin:
+            continue
+        wy = ramp_weight(th, min(overlap, th), iy == 0, iy == len(ys) - 1, scale)
+        for ix, x0 in enumerate(xs):
+            wx = ramp_weight(tw, min(overlap, tw), ix == 0, ix == len(xs) - 1, scale)
+            w2 = wy[:, None] * wx[None, :]
+            acc[:, y0 * scale : (y0 + th) * scale, x0 * scale : (x0 + tw) * scale] += tiles[iy * len(xs) + ix].to(torch.float64) * w2
+            wsum[y0 * scale : (y0 + th) * scale, x0 * scale : (x0 + tw) * scale] += w2
+    return acc[:, row_begin:row_end] / wsum[row_begin:row_end]
+
+
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 255.0) -> float:
     """utils/metrics.py:36-49 on already-cropped arrays (no Y conversion)."""
     mse = ((a.double() - b.double()) ** 2).mean().item()

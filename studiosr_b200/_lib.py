@@ -5,7 +5,7 @@ sm_100 part, importing / calling raises.  Build the library with `python __graft
 (or `make -C studiosr_b200/csrc`)."""
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssr_b200.so")
@@ -47,12 +47,21 @@ SYMBOLS = {
                                            c_size_t, c_void_p]),
     "ssr_model_upscale_tiled_u8_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                                 c_void_p, c_size_t, c_void_p]),
+    "ssr_tiled_tile_elems": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "ssr_model_tiles_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
+    "ssr_model_tiles_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_size_t, c_void_p]),
+    "ssr_model_blend_tiles_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ssr_model_train_bind": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int64)]),
     "ssr_model_train_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "ssr_model_train_forward": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_void_p, c_size_t, c_void_p]),
     "ssr_model_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p,
                                          c_size_t, c_void_p]),
+    "ssr_l1_loss_workspace_bytes": (c_size_t, []),
+    "ssr_l1_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ssr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_double,
+                              c_int64, c_float, c_void_p]),
     "ssr_launch_count": (c_int64, []),
     "ssr_profile_begin": (c_int, []),
     "ssr_profile_end": (c_int, [c_char_p, c_size_t]),

@@ -639,10 +639,10 @@ __device__ __forceinline__ float ramp_w(int p, int n, int o, bool first, bool la
 }
 
 __global__ void __launch_bounds__(256) blend_kernel(const BlendArgs a) {
-  const int OW = a.W * a.scale, OH = a.H * a.scale;
+  const int OW = a.W * a.scale;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)OW * OH) return;
-  const int X = (int)(idx % OW), Y = (int)(idx / OW);
+  if (idx >= (long long)OW * (a.row_end - a.row_begin)) return;
+  const int X = (int)(idx % OW), Y = a.row_begin + (int)(idx / OW);
   const int th = a.tile < a.H ? a.tile : a.H, tw = a.tile < a.W ? a.tile : a.W;
   const int stride = a.tile - a.overlap;
   const int ts_h = th * a.scale, ts_w = tw * a.scale;
@@ -673,8 +673,12 @@ __global__ void __launch_bounds__(256) blend_kernel(const BlendArgs a) {
 }
 
 int launch_blend(const BlendArgs& a, cudaStream_t s) {
-  const long long total = (long long)a.W * a.scale * a.H * a.scale;
-  ProfScope prof("blend", 0.0, (double)total * 3 + (double)a.tiles_x * a.tiles_y * 3 * 4 * a.tile * a.tile * a.scale * a.scale, s);
+  SSR_CHECK(a.row_begin >= 0 && a.row_end <= a.H * a.scale && a.row_begin <= a.row_end, SSR_E_INVALID, "blend: bad row band [%d, %d)",
+            a.row_begin, a.row_end);
+  const long long total = (long long)a.W * a.scale * (a.row_end - a.row_begin);
+  if (total == 0) return SSR_OK;
+  const double frac = (double)(a.row_end - a.row_begin) / (a.H * a.scale);
+  ProfScope prof("blend", 0.0, (double)total * 3 + frac * a.tiles_x * a.tiles_y * 3 * 4 * a.tile * a.tile * a.scale * a.scale, s);
   blend_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());

@@ -1633,40 +1633,77 @@ size_t ssr_model_tiled_workspace_bytes(const ssr_model_t* m, int H, int W, int t
   return tiled_layout(m, H, W, tile, overlap, chunk_tiles, &a, &b, &c);
 }
 
-int ssr_model_upscale_tiled_u8(ssr_model_t* m, const uint8_t* frame, uint8_t* outp, int H, int W, int tile, int overlap,
-                               int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream) {
+size_t ssr_tiled_tile_elems(const ssr_model_t* m, int H, int W, int tile) {
+  if (!m || tile <= 0) return 0;
+  const int th = tile < H ? tile : H, tw = tile < W ? tile : W, s = m->cfg.scale;
+  return (size_t)3 * th * s * tw * s;
+}
+
+size_t ssr_model_tiles_workspace_bytes(const ssr_model_t* m, int H, int W, int tile, int max_tiles_per_pass) {
+  if (!m || !m->finalized || tile <= 0 || max_tiles_per_pass <= 0) return 0;
+  const int th = tile < H ? tile : H, tw = tile < W ? tile : W;
+  return workspace_any(m, max_tiles_per_pass, th, tw, SSR_PAD_EVAL);
+}
+
+int ssr_model_tiles_u8(ssr_model_t* m, const uint8_t* frame, float* tiles_out, int H, int W, int tile, int overlap, int tile_begin,
+                       int tile_end, int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream) {
   SSR_TRY(check_ready(m));
-  SSR_CHECK(frame && outp && workspace, SSR_E_INVALID, "null buffer");
+  SSR_CHECK(frame && tiles_out && workspace, SSR_E_INVALID, "null buffer");
   SSR_CHECK(tile > overlap && overlap >= 0, SSR_E_INVALID, "tile %d must exceed overlap %d", tile, overlap);
-  cudaStream_t s = (cudaStream_t)stream;
-  size_t tiles_off, in_off, out_off;
-  const size_t need = tiled_layout(m, H, W, tile, overlap, chunk_tiles, &tiles_off, &in_off, &out_off);
-  SSR_CHECK(need <= workspace_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
   const int th = tile < H ? tile : H, tw = tile < W ? tile : W, stride = tile - overlap;
   const int tiles_x = num_tiles_1d(W, tile, stride), tiles_y = num_tiles_1d(H, tile, stride);
   const int nt = tiles_x * tiles_y;
+  if (tile_end < 0) tile_end = nt;
+  SSR_CHECK(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= nt, SSR_E_INVALID, "tile range [%d, %d) outside [0, %d)", tile_begin,
+            tile_end, nt);
+  const int n = tile_end - tile_begin;
+  if (n == 0) return SSR_OK;
   int chunk = chunk_tiles;
-  if (chunk <= 0 || chunk > nt) chunk = nt;
-  const int sc = m->cfg.scale;
-  float* tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + tiles_off);
-  for (int t0 = 0; t0 < nt; t0 += chunk) {
-    const int nb = nt - t0 < chunk ? nt - t0 : chunk;
-    InputSpec in{frame, 1, H, W, 1, tile, stride, tiles_x, t0};
-    OutputSpec out{tiles + (size_t)t0 * 3 * th * sc * tw * sc, nullptr};
-    SSR_TRY(forward_any(m, in, out, nb, th, tw, SSR_PAD_EVAL, workspace, tiles_off, s));
+  if (chunk <= 0 || chunk > n) chunk = n;
+  const size_t need = workspace_any(m, chunk, th, tw, SSR_PAD_EVAL);
+  SSR_CHECK(need <= workspace_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  const size_t elems = ssr_tiled_tile_elems(m, H, W, tile);
+  for (int t0 = 0; t0 < n; t0 += chunk) {
+    const int nb = n - t0 < chunk ? n - t0 : chunk;
+    InputSpec in{frame, 1, H, W, 1, tile, stride, tiles_x, tile_begin + t0};
+    OutputSpec out{tiles_out + (size_t)t0 * elems, nullptr};
+    SSR_TRY(forward_any(m, in, out, nb, th, tw, SSR_PAD_EVAL, workspace, workspace_bytes, (cudaStream_t)stream));
   }
+  return SSR_OK;
+}
+
+int ssr_model_blend_tiles_u8(ssr_model_t* m, const float* tiles, uint8_t* outp, int H, int W, int tile, int overlap, int row_begin,
+                             int row_end, void* stream) {
+  SSR_CHECK(m && tiles && outp, SSR_E_INVALID, "null argument");
+  SSR_CHECK(tile > overlap && overlap >= 0, SSR_E_INVALID, "tile %d must exceed overlap %d", tile, overlap);
+  const int stride = tile - overlap;
   BlendArgs b;
   b.tiles = tiles;
   b.out = outp;
   b.H = H;
   b.W = W;
-  b.scale = sc;
+  b.scale = m->cfg.scale;
   b.tile = tile;
   b.overlap = overlap;
-  b.tiles_x = tiles_x;
-  b.tiles_y = tiles_y;
+  b.tiles_x = num_tiles_1d(W, tile, stride);
+  b.tiles_y = num_tiles_1d(H, tile, stride);
   b.u8_scale = m->cfg.img_range == 1.0f ? 255.0f : 1.0f;
-  return launch_blend(b, s);
+  b.row_begin = row_begin;
+  b.row_end = row_end < 0 ? H * m->cfg.scale : row_end;
+  return launch_blend(b, (cudaStream_t)stream);
+}
+
+int ssr_model_upscale_tiled_u8(ssr_model_t* m, const uint8_t* frame, uint8_t* outp, int H, int W, int tile, int overlap,
+                               int chunk_tiles, void* workspace, size_t workspace_bytes, void* stream) {
+  SSR_TRY(check_ready(m));
+  SSR_CHECK(frame && outp && workspace, SSR_E_INVALID, "null buffer");
+  SSR_CHECK(tile > overlap && overlap >= 0, SSR_E_INVALID, "tile %d must exceed overlap %d", tile, overlap);
+  size_t tiles_off, in_off, out_off;
+  const size_t need = tiled_layout(m, H, W, tile, overlap, chunk_tiles, &tiles_off, &in_off, &out_off);
+  SSR_CHECK(need <= workspace_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  float* tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + tiles_off);
+  SSR_TRY(ssr_model_tiles_u8(m, frame, tiles, H, W, tile, overlap, 0, -1, chunk_tiles, workspace, tiles_off, stream));
+  return ssr_model_blend_tiles_u8(m, tiles, outp, H, W, tile, overlap, 0, -1, stream);
 }
 
 int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, uint8_t* out_host, int H, int W, int tile,

@@ -184,6 +184,7 @@ struct BlendArgs {
   uint8_t* out;        // [H*s][W*s][3]
   int H, W, scale, tile, overlap, tiles_x, tiles_y;
   float u8_scale;
+  int row_begin, row_end;  // output rows [row_begin, row_end) are written (a rank's band of a sharded frame)
 };
 
 // fused proj + residual + LN2 + fc1 + GELU + fc2 + residual (+ LN_next) of one Swin block (bf16, padded 192/384).

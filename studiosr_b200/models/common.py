@@ -13,6 +13,7 @@ from ..native import NativeModel
 
 # precision of the fp32 (non-autocast) forward: "fp32" = CUDA-core FMA, "tf32" = tcgen05 kind::tf32
 DEFAULT_FP32_MODE = os.environ.get("STUDIOSR_B200_FP32_MODE", "fp32")
+TRUST_PARAM_VERSIONS = os.environ.get("STUDIOSR_B200_TRUST_PARAM_VERSIONS", "0") == "1"
 
 
 def diverge_images(image: torch.Tensor) -> List[torch.Tensor]:
@@ -42,7 +43,7 @@ class _NativeTrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, model, nat, drop_scale, *tensors):
         y, ws = nat.train_forward(x, [t.detach() for t in tensors], model.scale, drop_scale)
-        ctx.nat, ctx.ws, ctx.shape, ctx.drop_scale = nat, ws, tuple(x.shape), drop_scale
+        ctx.nat, ctx.ws, ctx.shape, ctx.drop_scale, ctx.model = nat, ws, tuple(x.shape), drop_scale, model
         ctx.meta = [(t.shape, t.numel(), t.requires_grad) for t in tensors]
         return y
 
@@ -50,17 +51,22 @@ class _NativeTrainStep(torch.autograd.Function):
     def backward(ctx, dy):
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("studiosr_b200: the gradient with respect to the input image is not built")
-        total = sum(n for _, n, rg in ctx.meta if rg)
-        flat = torch.empty(total, dtype=torch.float32, device=dy.device)  # one flat buffer: grads are views into it
+        # one flat buffer: grads are views into it, every slice on a 16-byte boundary -- the layout engine.FusedAdam keeps its
+        # parameters in, so the optimizer update is one launch and a data-parallel exchange one all-reduce
+        total = sum((n + 3) // 4 * 4 for _, n, rg in ctx.meta if rg)
+        flat = torch.zeros(total, dtype=torch.float32, device=dy.device)
         grads, off = [], 0
         for shape, n, rg in ctx.meta:
             if rg:
                 grads.append(flat[off:off + n].view(shape))
-                off += n
+                off += (n + 3) // 4 * 4
             else:
                 grads.append(None)
         ctx.nat.train_backward(dy, grads, ctx.shape, ctx.ws, ctx.drop_scale)
         ctx.ws = None
+        sync = getattr(ctx.model, "_grad_sync", None)  # engine.DistributedDataParallel: the gradient mean over ranks
+        if sync is not None:
+            sync(flat)
         return (None, None, None, None, *grads)
 
 
@@ -93,13 +99,47 @@ class Model(nn.Module):
         self.img_range: float = img_range
         self.precision: Optional[str] = None  # None = auto: bf16 under bf16 autocast, else DEFAULT_FP32_MODE
         self._natives: Dict = {}
+        # True skips the per-forward checksum (one device sync) of the packed-weight cache key: safe when parameters are only
+        # changed through autograd-visible ops / load_state_dict, or when invalidate_native() is called after `.data` writes
+        self.trust_param_versions: bool = False
 
     # ---- native plumbing ------------------------------------------------------------------
     def _native_config(self, precision: int) -> "_lib.ModelConfig":
         raise NotImplementedError
 
     def _param_version(self):
-        return tuple((id(t), t._version) for t in self.state_dict(keep_vars=True).values() if t.is_floating_point())
+        """Key of the packed-weight cache.  `_version` alone misses writes through `.data` (p.data.mul_(), p.data.copy_(),
+        p.data = ...), so the storage pointer and one cheap on-device checksum per call (sum and sum of |x| over all
+        parameters, a single foreach reduction) are part of the key; `invalidate_native()` forces a re-pack explicitly."""
+        ts = [t for t in self.state_dict(keep_vars=True).values() if t.is_floating_point()]
+        key = tuple((id(t), t._version, t.data_ptr()) for t in ts)
+        cuda = [t.detach() for t in ts if t.is_cuda]
+        if cuda and not (self.trust_param_versions or TRUST_PARAM_VERSIONS):
+            with torch.no_grad():
+                n1 = torch.stack(torch._foreach_norm(cuda, 1)).double()
+                n2 = torch.stack(torch._foreach_norm(cuda, 2)).double()
+                key += (float(n1.sum()), float((n2 * torch.arange(1, len(cuda) + 1, device=n2.device)).sum()))
+        return key
+
+    def invalidate_native(self) -> None:
+        """Drop the packed native copies of the weights (they are rebuilt by the next forward)."""
+        self._natives = {}
+
+    # ctypes handles cannot be copied or pickled: EMA copies (copy.deepcopy), torch.save(model) and DDP's module pickling
+    # carry the parameters only and rebuild the native side lazily
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_natives"] = {}
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_natives" else copy.deepcopy(v, memo)
+        return new
 
     def _native(self, device, precision: str) -> NativeModel:
         device = torch.device(device)
@@ -210,6 +250,19 @@ class Model(nn.Module):
         nat = self._native(dev, precision or self.precision or DEFAULT_FP32_MODE)
         return nat.upscale_tiled_u8_host(np.ascontiguousarray(image), out, self.scale, tile, overlap)
 
+    def sharded_tiler(self, H: int, W: int, tile: int = 64, overlap: int = 16, precision: Optional[str] = None, group=None,
+                      chunk: int = 0):
+        """One frame's tile list strong-scaled over the ranks of a torch.distributed group (BASELINE.json config 5 at
+        N > 1): returns a studiosr_b200.sharding.ShardedTiledUpscaler bound to this model's packed weights on
+        this rank's device.  `upscale_host(frame, out)` on it is the multi-GPU form of `inference_tiled`."""
+        import torch.distributed as dist
+
+        from ..sharding import NativeTileBackend, ShardedTiledUpscaler
+
+        self.eval()
+        nat = self._native(self._device(), precision or self.precision or DEFAULT_FP32_MODE)
+        return ShardedTiledUpscaler(NativeTileBackend(nat, H, W, self.scale, tile, overlap, chunk), dist, group)
+
     def get_model_config(self) -> Dict:
         return dict(scale=self.scale, n_colors=self.n_colors, img_range=self.img_range)
 
@@ -218,7 +271,16 @@ class Model(nn.Module):
 
     @classmethod
     def from_pretrained(cls, scale: int = 4) -> "Model":
-        return cls(scale=scale)
+        """Every model family overrides this with the reference's signature and file naming; the base class must not hand
+        back a randomly initialised model as if it were pretrained (the CLI would write garbage images)."""
+        raise NotImplementedError(f"{cls.__name__}.from_pretrained: no pretrained weights are defined for this class")
+
+    @staticmethod
+    def _load_pretrained_file(path: str):
+        """torch.load of a weight file that must already exist (downloads are outside the native path, no network here)."""
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not found (downloads are outside the native path; place the file there)")
+        return torch.load(path, map_location="cpu")
 
     def export(self, path: Optional[str] = None, input_shape: List[int] = [1, 3, 256, 256], format: str = "onnx") -> str:
         raise NotImplementedError("ONNX export of the native path is out of scope (SURVEY.md §2, common.py:84-98)")

@@ -1,6 +1,7 @@
 """Drop-in for studiosr.models.EDSR (reference edsr.py:12-111): identical constructor and
 state_dict; forward = implicit-GEMM conv chain in libssr_b200 (MeanShift folded into the first /
 last kernels, ReLU / res_scale / residual adds in the GEMM epilogues, PixelShuffle in the store)."""
+import os
 from typing import Dict
 
 import torch.nn as nn
@@ -42,3 +43,16 @@ class EDSR(Model):
     def get_training_config(self) -> Dict:
         return dict(batch_size=16, learning_rate=0.0001, beta1=0.9, beta2=0.99, weight_decay=0.0, max_iters=1000000,
                     gamma=0.5, milestones=[200000, 400000, 600000, 800000])
+
+    @classmethod
+    def from_pretrained(cls, scale: int = 4, dataset: str = "DIV2K") -> "EDSR":
+        """Signature, file names and the img_range=255 of the DIV2K weights as edsr.py:77-111; the file must already be
+        under ./pretrained."""
+        assert scale in [2, 3, 4]
+        assert dataset in ["DIV2K", "DF2K"]
+        if dataset == "DIV2K":
+            model, file_name = cls(scale=scale, img_range=255.0), f"r32f256x{scale}.pth"
+        else:
+            model, file_name = cls(scale=scale), f"EDSRx{scale}.pth"
+        model.load_state_dict(cls._load_pretrained_file(os.path.join("pretrained", file_name)), strict=False)
+        return model

@@ -1,6 +1,7 @@
 """Drop-in for studiosr.models.RCAN (reference rcan.py:11-122): identical constructor and state_dict;
 forward = implicit-GEMM conv chain in libssr_b200 with the channel-attention gate (global average pool ->
 64 -> 4 -> 64 MLP -> sigmoid, common.py:156-170) and both residual adds fused into two small kernels per RCAB."""
+import os
 from typing import Dict
 
 import torch.nn as nn
@@ -58,3 +59,11 @@ class RCAN(Model):
     def get_training_config(self) -> Dict:
         return dict(batch_size=16, learning_rate=0.0001, beta1=0.9, beta2=0.99, weight_decay=0.0, max_iters=1000000,
                     gamma=0.5, milestones=[200000, 400000, 600000, 800000])
+
+    @classmethod
+    def from_pretrained(cls, scale: int = 4) -> "RCAN":
+        """File layout and img_range=255 as rcan.py:107-119; the archive must already be extracted under ./pretrained."""
+        path = os.path.join("pretrained", "models_ECCV2018RCAN", f"RCAN_BIX{scale}.pt")
+        model = cls(scale=scale, img_range=255.0)
+        model.load_state_dict(cls._load_pretrained_file(path), False)
+        return model
