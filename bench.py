@@ -108,9 +108,30 @@ def build_model(precision):
     return m
 
 
+_JSON_FD = None
+
+
+def own_stdout_for_json():
+    """stdout carries the ONE JSON line and nothing else: fd 1 is pointed at stderr for the whole run (NCCL writes its banner and,
+    with NCCL_DEBUG=INFO, its whole log to fd 1 -- all of that stays visible, on stderr) and `emit` writes the line to the saved
+    descriptor.  NCCL_DEBUG itself is never touched."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def init_dist(local):
-    """torch.distributed over NCCL.  NCCL_DEBUG is whatever the operator set (its log goes where NCCL sends it: stdout unless
-    NCCL_DEBUG_FILE is set); the ONE JSON line of this script is recognisable by its leading '{"metric"' / '{"impl"'."""
+    """torch.distributed over NCCL; NCCL_DEBUG is whatever the operator set."""
     import torch
     import torch.distributed as dist
 
@@ -200,7 +221,7 @@ def run_reference(args):
                                    f"value = frame Mpix / ({nt} x s/tile)"},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus, scaling="strong"):
@@ -383,7 +404,7 @@ def run_ours(args):
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -582,12 +603,13 @@ def run_extra(args):
                              "frac_of_sustained_peak": tf / pk["tf_sust"] / world},
         "kernels": kernels, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    own_stdout_for_json()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

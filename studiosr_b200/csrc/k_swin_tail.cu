@@ -2,38 +2,56 @@
 //
 //   t'  = o @ Wproj^T + bproj + res                (swinir.py:103,171)    [tcgen05 SS, acc in TMEM]
 //   xn2 = (t' - mean) * rstd                       (swinir.py:172; norm2's gamma/beta are folded into W1/b1 at pack time)
-//   h   = GELU(xn2 @ W1^T + b1)                    (common.py:185-186)    [3 chunks of 128 hidden units]
+//   h   = GELU(xn2 @ W1^T + b1)                    (common.py:185-186)    [6 chunks of 64 hidden units]
 //   t'' = t' + h @ W2^T + b2                       (common.py:188, swinir.py:172)
 //   out: t'' (fp32 residual stream), LayerNorm_next(t'') or a bf16 copy of t''
+//
+// Round 2: TWO TILES IN FLIGHT.  Round 1 ran a tile's phases back to back on one set of 8 epilogue warps (21k cycles per
+// 128-token tile: projection epilogue 4.3k, MLP 9.3k + 1.8k, final epilogue 7k -- the tensor pipe idle during 11k of them).
+// Now the residual-stream accumulator Y is double-buffered in TMEM and the epilogue is split into two roles that work on
+// different tiles at the same time:
+//   IO warps   (8): E1(j) = projection epilogue of tile j (residual add, LayerNorm statistics, xn2 -> smem), then
+//                   E3(j-1) = final epilogue of tile j-1 (fp32 stream + LayerNorm_next / bf16 copy -> TMA stores);
+//   GELU warps (8): the six fc1-chunk epilogues of tile j;
+//   MMA issuer    : fc1 / fc2 chunks of tile j with the projection of tile j+1 slotted in after the first two fc1 chunks.
+// So the memory-bound phases of one tile run under the tensor-bound MLP of the other.
 //
 // Design notes (all measured on B200, profiles/r01_micro_tc.txt):
 //  * h never touches shared memory: the GELU epilogue packs it to bf16 and writes it back over its own fc1
 //    accumulator columns with tcgen05.st; fc2 consumes it as the TMEM A operand of a TS-mode tcgen05.mma.
 //  * Every bulk transfer is TMA.  The fp32 residual arrives in per-warp [32 x 32] SWIZZLE_128B boxes (thread <-> row
-//    reads are bank-conflict free) loaded one tile ahead, as soon as the same per-warp buffers have been drained by the output stores; the outputs leave as per-warp TMA stores from a
-//    swizzled staging box.  No thread ever waits on a global load, and the ragged last tile is clipped by TMA.
-//  * A single producer thread sustains only one wait->issue round per ~500 cycles however deep the ring is, so the
-//    weight stream is split over two producer warps (even / odd ring entries) and the o tile has its own.
+//    reads are bank-conflict free); the outputs leave as per-warp TMA stores from the same boxes.  No thread ever waits on
+//    a global load, and the ragged last tile is clipped by TMA.
+//  * The o tile streams through the weight ring (it is only needed by the three projection k-blocks), so the only
+//    tile-sized operand buffer is xn2; two producer threads fill the ring (a single thread sustains one wait -> issue round
+//    per ~500 cycles).
 //  * LayerNorm statistics are one-pass (sum, sum of squares in fp32) on values held in registers.
 //
-// TMEM (512 columns): Y = [0,192) fc2 accumulator (pre-loaded with t' + b2); [192,384) projection accumulator,
-// re-used as the fc1 chunk accumulators X0 = [192,320), X1 = [320,448).
-// Warps: 0,1 = weight TMA producers, 2 = o-tile producer + L2 prefetch of the next residual tile, 3 = MMA issuer,
-// 4..11 = epilogue; epilogue warp w owns TMEM lane quadrant (w % 4) and column half (w - 4) / 4.
+// TMEM (512 columns): Y0 = [0,192), Y1 = [192,384): projection accumulator -> t' + b2 -> fc2 accumulator of tiles with even /
+// odd local index; X0 = [384,448), X1 = [448,512): fc1 chunk accumulators, overwritten in place by the packed bf16 h.
+// Warps (20, registers re-balanced with setmaxnreg): 0,1,2 = ring producers (+ L2 prefetch of the residual rows), 3 = MMA
+// issuer, 4..11 = IO warps, 12..19 = GELU warps; warp w owns TMEM lane quadrant w % 4 and column half ((w - 4) % 8) / 4.
 #include "ssr_tc.cuh"
 
 namespace ssr {
 
-constexpr int ST_THREADS = 384;
-constexpr int ST_EPI_WARP0 = 4;
-constexpr int ST_WSLOTS = 3;
-constexpr int ST_WENTRIES = 18;               // weight ring entries per tile
+constexpr int ST_THREADS = 640;
+constexpr int ST_IO_WARP0 = 4, ST_GELU_WARP0 = 12;
+// register budgets after setmaxnreg (the CTA's pool is 640 x 96 = 61440 registers)
+#ifndef ST_REGS_WG0
+#define ST_REGS_WG0 40
+#define ST_REGS_IO 152
+#define ST_REGS_GELU 64
+#endif
+static_assert(128 * ST_REGS_WG0 + 256 * ST_REGS_IO + 256 * ST_REGS_GELU <= 640 * 96, "setmaxnreg budgets exceed the CTA's register pool");
+constexpr int ST_WSLOTS = 4;
+constexpr int ST_NCHUNK = 6;                  // fc1 / fc2 chunks of 64 hidden units
 constexpr uint32_t ST_TILE = 16384;           // one [128 rows][128 B] k-block tile
-constexpr uint32_t ST_WSLOT = 192 * 128;      // weight ring slot (fc1 entries use 128 rows of it)
-constexpr uint32_t ST_OFF_OX = 0;                                  // 3 tiles: o, later xn2
-constexpr uint32_t ST_OFF_W = ST_OFF_OX + 3 * ST_TILE;             // weight ring
-constexpr uint32_t ST_OFF_IO = ST_OFF_W + ST_WSLOTS * ST_WSLOT;    // per epilogue warp: B0, B1, B2 (residual in, outputs out)
-constexpr uint32_t ST_IO_WARP = 3 * 4096;
+constexpr uint32_t ST_WSLOT = 192 * 128;      // ring slot: Wproj / W2 k-block [192 x 64], W1 chunk 3 x [64 x 64], o k-block [128 x 64]
+constexpr uint32_t ST_OFF_XN = 0;                                  // 3 k-block tiles of xn2 (A operand of fc1)
+constexpr uint32_t ST_OFF_W = ST_OFF_XN + 3 * ST_TILE;             // ring
+constexpr uint32_t ST_OFF_IO = ST_OFF_W + ST_WSLOTS * ST_WSLOT;    // per IO warp: B0, B1 (residual in, outputs out)
+constexpr uint32_t ST_IO_WARP = 2 * 4096;
 constexpr uint32_t ST_OFF_PAR = ST_OFF_IO + 8 * ST_IO_WARP;        // fp32 parameters
 constexpr int ST_NPAR = 192 * 4 + 384;                             // bp b2 g3 be3 | b1
 constexpr uint32_t ST_OFF_RED = ST_OFF_PAR + ST_NPAR * 4;          // [128][2] float2 cross-half reductions
@@ -44,16 +62,17 @@ static_assert(ST_SMEM <= 232448, "fused tail kernel exceeds the 227 KB shared-me
 enum {  // mbarrier indices
   SB_WFULL = 0,                       // [ST_WSLOTS]
   SB_WEMPTY = SB_WFULL + ST_WSLOTS,   // [ST_WSLOTS]
-  SB_OFULL = SB_WEMPTY + ST_WSLOTS,
-  SB_OEMPTY,
-  SB_PFULL,    // projection accumulator complete
-  SB_XNREADY,  // xn2 in smem + Y initialised (8 arrivals)
-  SB_XFULL,    // [2] fc1 chunk accumulator complete
-  SB_HREADY = SB_XFULL + 2,  // [2] h chunk packed into TMEM (8 arrivals)
-  SB_YFULL = SB_HREADY + 2,
-  SB_RFULL,    // [8 warps][3] residual chunk landed
-  SB_COUNT = SB_RFULL + 24
+  SB_PFULL = SB_WEMPTY + ST_WSLOTS,   // [2] projection accumulator in Y0 / Y1 complete
+  SB_XNREADY = SB_PFULL + 2,          // xn2 in smem + Y = t' + b2 (8 arrivals: IO warps)
+  SB_XNFREE,                          // every fc1 MMA of the tile has read xn2
+  SB_XFULL,                           // [2] fc1 chunk accumulator X0 / X1 complete
+  SB_HREADY = SB_XFULL + 2,           // [2] h chunk packed into TMEM (8 arrivals: GELU warps)
+  SB_YFULL = SB_HREADY + 2,           // [2] fc2 of the tile complete
+  SB_YFREE = SB_YFULL + 2,            // [2] the final epilogue holds Y in registers (8 arrivals: IO warps)
+  SB_RFULL = SB_YFREE + 2,            // [8 warps][2] residual chunk landed in B0 / B1
+  SB_COUNT = SB_RFULL + 16
 };
+static_assert(SB_COUNT * 8 + 8 <= 512, "barrier area");
 
 struct TailArgs {
   int M, C, n_tiles;
@@ -62,7 +81,7 @@ struct TailArgs {
   int has_bf;   // store a bf16 tensor: LayerNorm_next(t'') if do_ln else t''
   int do_ln;
   float eps;
-  long long* dbg;  // optional phase timestamps (developer diagnostics): [CTA][tile < 32][16]
+  long long* dbg;  // optional phase timestamps (developer diagnostics): 3 regions of [CTA][tile < 32][16]
 };
 
 // byte offset of (row r, 16-byte chunk j) inside a [rows][128 B] SWIZZLE_128B box / [rows][64 B] SWIZZLE_64B box
@@ -85,6 +104,30 @@ __device__ __forceinline__ uint32_t gelu2_bf16(f32x2 x, f32x2 kC0, f32x2 kC1, f3
   asm("tanh.approx.f32 %0, %1;" : "=f"(thi) : "f"(uhi));
   const f32x2 hx = f2_mul(x, kHalf);
   return f2_to_bf16x2(f2_fma(hx, f2_pack(tlo, thi), hx));
+}
+
+// The ring entries of one CTA in the order the MMA issuer consumes them.  `f(kind, tile_it, idx)`: kind 0 = o k-block idx of
+// local tile tile_it, 1 = Wproj k-block idx, 2 = W1 chunk idx, 3 = W2 chunk idx.
+template <typename F>
+__device__ __forceinline__ void for_each_ring_entry(int my_tiles, F f) {
+  if (my_tiles <= 0) return;
+  for (int kb = 0; kb < 3; ++kb) {
+    f(0, 0, kb);
+    f(1, 0, kb);
+  }
+  for (int it = 0; it < my_tiles; ++it) {
+    f(2, it, 0);
+    f(2, it, 1);
+    if (it + 1 < my_tiles)
+      for (int kb = 0; kb < 3; ++kb) {
+        f(0, it + 1, kb);
+        f(1, it + 1, kb);
+      }
+    for (int c = 0; c < ST_NCHUNK; ++c) {
+      f(3, it, c);
+      if (c + 2 < ST_NCHUNK) f(2, it, c + 2);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
@@ -125,8 +168,8 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
     prefetch_tmap(&tmOutB);
     prefetch_tmap(&tmOutB2);
     for (int i = 0; i < SB_COUNT; ++i) {
-      const bool epi8 = (i == SB_XNREADY) || (i >= SB_HREADY && i < SB_HREADY + 2);
-      mbar_init(bar(i), epi8 ? 8 : 1);
+      const bool cnt8 = i == SB_XNREADY || (i >= SB_HREADY && i < SB_HREADY + 2) || (i >= SB_YFREE && i < SB_YFREE + 2);
+      mbar_init(bar(i), cnt8 ? 8 : 1);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -137,163 +180,177 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_tiles = a.n_tiles;
-  constexpr uint32_t IDESC_192 = umma_idesc(1, 128, 192), IDESC_128 = umma_idesc(1, 128, 128);
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  constexpr uint32_t IDESC_192 = umma_idesc(1, 128, 192), IDESC_64 = umma_idesc(1, 128, 64);
+  constexpr uint32_t TY = 0, TX = 384;  // Y_s = TY + 192 s, X_b = TX + 64 b
 
-  if (warp < 2) {
-    // =========================== weight producers (even / odd ring entries) ===========================
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        for (int e = warp; e < ST_WENTRIES; e += 2) {
-          // ring entries in exactly the order the MMA warp consumes them:
-          //  0-2 proj | 3-5 fc1 c0 | 6-8 fc1 c1 | 9-10 fc2 c0 | 11-13 fc1 c2 | 14-15 fc2 c1 | 16-17 fc2 c2
-          const CUtensorMap* map;
-          uint32_t bytes;
-          int c0, c1;
-          if (e < 3) {
-            map = &tmWp; bytes = 192 * 128; c0 = e * 64; c1 = 0;
-          } else if (e < 9) {
-            map = &tmW1; bytes = 128 * 128; c0 = ((e - 3) % 3) * 64; c1 = ((e - 3) / 3) * 128;
-          } else if (e < 11) {
-            map = &tmW2; bytes = 192 * 128; c0 = (e - 9) * 64; c1 = 0;
-          } else if (e < 14) {
-            map = &tmW1; bytes = 128 * 128; c0 = (e - 11) * 64; c1 = 256;
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_WG0));
+    if (warp < 3) {
+      // =========================== ring producers: entry e is loaded by warp e % 3 ===========================
+      if (lane == 0) {
+        uint32_t k = 0;
+        for_each_ring_entry(my_tiles, [&](int kind, int it, int idx) {
+          const uint32_t e = k++;
+          if ((int)(e % 3u) != warp) return;
+          const int s = e % ST_WSLOTS;
+          mbar_wait(bar(SB_WEMPTY + s), ((e / ST_WSLOTS) & 1u) ^ 1u);
+          const uint32_t dst = sbase + ST_OFF_W + s * ST_WSLOT, fb = bar(SB_WFULL + s);
+          if (kind == 0) {
+            const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128;
+            mbar_expect_tx(fb, ST_TILE);
+            tma_load_2d(dst, &tmO, fb, idx * 64, row0);
+            // pull the tile's residual rows into L2 (the IO warps fetch them into smem about one tile from now)
+            if (it >= 2) {
+              tma_prefetch_2d(&tmResPf, idx * 64, row0);
+              tma_prefetch_2d(&tmResPf, idx * 64 + 32, row0);
+            }
+          } else if (kind == 1) {
+            mbar_expect_tx(fb, ST_WSLOT);
+            tma_load_2d(dst, &tmWp, fb, idx * 64, 0);
+          } else if (kind == 2) {
+            mbar_expect_tx(fb, ST_WSLOT);
+            for (int kb = 0; kb < 3; ++kb) tma_load_2d(dst + kb * 8192, &tmW1, fb, kb * 64, idx * 64);
           } else {
-            map = &tmW2; bytes = 192 * 128; c0 = 128 + (e - 14) * 64; c1 = 0;
+            mbar_expect_tx(fb, ST_WSLOT);
+            tma_load_2d(dst, &tmW2, fb, idx * 64, 0);
           }
-          const uint32_t k = (uint32_t)it * ST_WENTRIES + e;
-          const int s = k % ST_WSLOTS;
-          mbar_wait(bar(SB_WEMPTY + s), ((k / ST_WSLOTS) & 1u) ^ 1u);
-          mbar_expect_tx(bar(SB_WFULL + s), bytes);
-          tma_load_2d(sbase + ST_OFF_W + s * ST_WSLOT, map, bar(SB_WFULL + s), c0, c1);
-        }
+        });
       }
-    }
-  } else if (warp == 2) {
-    // =========================== o-tile producer ===========================
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        // the buffer is free once the previous tile's last fc1 chunk has consumed xn2
-        mbar_wait(bar(SB_OEMPTY), ((uint32_t)it & 1u) ^ 1u);
-        mbar_expect_tx(bar(SB_OFULL), 3 * ST_TILE);
-        for (int kb = 0; kb < 3; ++kb) tma_load_2d(sbase + ST_OFF_OX + kb * ST_TILE, &tmO, bar(SB_OFULL), kb * 64, tile * 128);
-        // pull the residual rows of the tile after this one into L2 (they are fetched to smem ~1 tile from now)
-        const int nt = tile + gridDim.x;
-        if (nt < n_tiles)
-          for (int c = 0; c < 6; ++c) tma_prefetch_2d(&tmResPf, c * 32, nt * 128);
-      }
-    }
-  } else if (warp == 3) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      uint32_t wk = 0;  // weight ring position
-      uint32_t n_hready[2] = {0, 0};
-      const uint32_t tY = tmem_base, tP = tmem_base + 192, tX[2] = {tmem_base + 192, tmem_base + 320};
-      auto w_wait = [&]() -> uint32_t {
-        const int s = wk % ST_WSLOTS;
-        mbar_wait(bar(SB_WFULL + s), (wk / ST_WSLOTS) & 1u);
-        tc_fence_after();
-        return sbase + ST_OFF_W + s * ST_WSLOT;
-      };
-      auto w_release = [&]() {
-        umma_commit(bar(SB_WEMPTY + (wk % ST_WSLOTS)));
-        ++wk;
-      };
-      // one k-block, both operands in smem: A tile at `a_addr`, W from the ring, 4 UMMAs of K=16
-      auto kblock_ss = [&](uint32_t a_addr, uint32_t tmem_d, uint32_t idesc, bool first_clears) {
-        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(w_wait());
+    } else {
+      // =========================== MMA issuer ===========================
+      if (lane == 0 && my_tiles > 0) {
+        uint32_t wk = 0;  // ring position
+        uint32_t n_hready[2] = {0, 0};
+        // `opaque`: keeps ptxas from hoisting descriptors / TMEM addresses out of the loops (they would be spilled on this
+        // warpgroup's small register budget)
+        auto opaque = [](uint32_t v) {
+          asm volatile("" : "+r"(v));
+          return v;
+        };
+        auto w_wait = [&]() -> uint32_t {
+          const int s = wk % ST_WSLOTS;
+          mbar_wait(bar(SB_WFULL + s), (wk / ST_WSLOTS) & 1u);
+          tc_fence_after();
+          return opaque(sbase) + ST_OFF_W + s * ST_WSLOT;
+        };
+        auto w_release = [&]() {
+          umma_commit(bar(SB_WEMPTY + (wk % ST_WSLOTS)));
+          ++wk;
+        };
+        auto proj = [&](int it) {  // Y_s = o(it) Wproj^T ; s = it & 1
+          const uint32_t tY = opaque(tmem_base) + TY + 192u * (uint32_t)(it & 1);
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint32_t o_addr = w_wait();
+            const int so = wk % ST_WSLOTS;
+            ++wk;  // the o slot is released together with the weight slot below
+            const uint32_t w_addr = w_wait();
+            const uint64_t adesc = umma_desc_sw128(o_addr), bdesc = umma_desc_sw128(w_addr);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma<false>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (first_clears && k == 0) ? 0u : 1u);
-        w_release();
-      };
-      auto fc1_chunk = [&](int c) {
-        const int b = c & 1;
-        for (int kb = 0; kb < 3; ++kb) kblock_ss(sbase + ST_OFF_OX + kb * ST_TILE, tX[b], IDESC_128, kb == 0);
-        umma_commit(bar(SB_XFULL + b));
-      };
-      auto fc2_chunk = [&](int c) {
-        const int b = c & 1;
-        mbar_wait(bar(SB_HREADY + b), n_hready[b] & 1u);
-        ++n_hready[b];
-        tc_fence_after();
-        for (int kb = 0; kb < 2; ++kb) {
-          // h of hidden units [kb*64, kb*64+64) of this chunk: packed bf16 pairs in X_b columns [kb*64, kb*64+32)
-          const uint64_t bdesc = umma_desc_sw128(w_wait());
+            for (int k = 0; k < 4; ++k) umma<false>(tY, adesc + 2 * k, bdesc + 2 * k, IDESC_192, (kb | k) ? 1u : 0u);
+            umma_commit(bar(SB_WEMPTY + so));
+            w_release();
+          }
+          umma_commit(bar(SB_PFULL + (it & 1)));
+        };
+        auto fc1_chunk = [&](int c) {  // X_b = xn2 W1[64c : 64c+64]^T
+          const int b = c & 1;
+          const uint32_t w_addr = w_wait();
+          const uint32_t tX = opaque(tmem_base) + TX + 64u * (uint32_t)b;
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint64_t adesc = umma_desc_sw128(opaque(sbase) + ST_OFF_XN + kb * ST_TILE), bdesc = umma_desc_sw128(w_addr + kb * 8192);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ts(tY, tX[b] + (uint32_t)(kb * 64 + k * 8), bdesc + 2 * k, IDESC_192, 1u);
+            for (int k = 0; k < 4; ++k) umma<false>(tX, adesc + 2 * k, bdesc + 2 * k, IDESC_64, (kb | k) ? 1u : 0u);
+          }
           w_release();
+          umma_commit(bar(SB_XFULL + b));
+        };
+        auto fc2_chunk = [&](int it, int c) {  // Y_s += h_c W2[:, 64c : 64c+64]^T, h_c = packed bf16 in X_b columns [0,16) and [32,48)
+          const int b = c & 1;
+          mbar_wait(bar(SB_HREADY + b), n_hready[b] & 1u);
+          ++n_hready[b];
+          tc_fence_after();
+          const uint64_t bdesc = umma_desc_sw128(w_wait());
+          const uint32_t tb = opaque(tmem_base);
+          const uint32_t tY = tb + TY + 192u * (uint32_t)(it & 1), tX = tb + TX + 64u * (uint32_t)b;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ts(tY, tX + (uint32_t)((k >> 1) * 32 + (k & 1) * 8), bdesc + 2 * k, IDESC_192, 1u);
+          w_release();
+        };
+        proj(0);
+        for (int it = 0; it < my_tiles; ++it) {
+          const uint32_t ph = (uint32_t)it & 1u;
+          long long* dbg = (a.dbg && it < 32) ? a.dbg + 16 * ((size_t)(2 * gridDim.x + blockIdx.x) * 32 + it) : nullptr;
+          if (dbg) dbg[0] = clock64();
+          mbar_wait(bar(SB_XNREADY), ph);  // xn2 of tile `it` in smem, Y_s = t' + b2
+          tc_fence_after();
+          if (dbg) dbg[1] = clock64();
+          fc1_chunk(0);
+          fc1_chunk(1);
+          if (dbg) dbg[2] = clock64();
+          if (it + 1 < my_tiles) {  // projection of the next tile into the other Y: its final-epilogue reader is tile it-1
+            if (it >= 1) {
+              mbar_wait(bar(SB_YFREE + (ph ^ 1u)), ((uint32_t)(it - 1) >> 1) & 1u);
+              tc_fence_after();
+            }
+            proj(it + 1);
+          }
+          if (dbg) dbg[3] = clock64();
+          for (int c = 0; c < ST_NCHUNK; ++c) {
+            fc2_chunk(it, c);
+            if (c + 2 < ST_NCHUNK) fc1_chunk(c + 2);
+            if (c + 2 == ST_NCHUNK - 1) umma_commit(bar(SB_XNFREE));  // all reads of xn2 are done once this commit fires
+            if (dbg && c < 6) dbg[4 + c] = clock64();
+          }
+          umma_commit(bar(SB_YFULL + ph));
         }
-      };
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t ph = (uint32_t)it & 1u;
-        // projection into [192,384): everything that read X0/X1 of the previous tile was either waited for (GELU
-        // epilogues, via HREADY) or is an earlier tcgen05.mma of this thread (fc2's TS reads; MMAs execute in order)
-        mbar_wait(bar(SB_OFULL), ph);
-        tc_fence_after();
-        for (int kb = 0; kb < 3; ++kb) kblock_ss(sbase + ST_OFF_OX + kb * ST_TILE, tP, IDESC_192, kb == 0);
-        umma_commit(bar(SB_PFULL));
-        mbar_wait(bar(SB_XNREADY), ph);  // xn2 written over the o tile, Y = t' + b2
-        tc_fence_after();
-        fc1_chunk(0);
-        fc1_chunk(1);
-        fc2_chunk(0);
-        fc1_chunk(2);
-        umma_commit(bar(SB_OEMPTY));  // all reads of xn2 are done once this commit fires
-        fc2_chunk(1);
-        fc2_chunk(2);
-        umma_commit(bar(SB_YFULL));
       }
+      __syncwarp();
     }
-    __syncwarp();
-  } else {
-    // =========================== epilogue (8 warps) ===========================
-    const int ew = warp - ST_EPI_WARP0;
-    const int hf = ew >> 2;     // column half of every accumulator
+  } else if (warp < ST_GELU_WARP0) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ST_REGS_IO));
+    // =========================== IO warps (8): E1(j), E3(j-1), E1(j+1), ... ===========================
+    const int ew = warp - ST_IO_WARP0;
+    const int hf = ew >> 2;     // column half of Y
     const int quad = warp & 3;  // TMEM lane quadrant
     const int row = quad * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint8_t* io = smem + ST_OFF_IO + ew * ST_IO_WARP;  // R0 | R1 | S
+    uint8_t* io = smem + ST_OFF_IO + ew * ST_IO_WARP;  // B0 | B1
     const uint32_t io_s = smem_u32(io);
-    const int rbar = SB_RFULL + ew * 3;
-    uint32_t n_xfull[2] = {0, 0};
+    const int rbar = SB_RFULL + ew * 2;
     const float invC = 1.0f / (float)a.C;
     const bool mask_tail = (hf == 1);  // this warp's last chunk holds the padded channels [C, 192)
+    uint32_t n_res[2] = {0, 0};        // completed uses of this warp's two residual barriers
 
-    // The warp's three 4 KB boxes B0..B2 carry the residual chunks [32 rows][32 cols] fp32 (SWIZZLE_128B) of the next
-    // tile from the moment the previous tile's output stores have drained them until the projection epilogue.
-    auto res_issue = [&](int c, long long tile) {  // lane 0 only
-      if (tile < n_tiles) {
-        const uint32_t b = bar(rbar + c);
+    // The warp's two 4 KB boxes carry residual chunks [32 rows][32 cols] fp32 (SWIZZLE_128B): chunks 0 and 1 of a tile sit in
+    // B0 / B1 from the moment the previous output stores have drained them until that tile's projection epilogue, chunk 2
+    // follows into B0 as soon as chunk 0 has been consumed.
+    auto res_issue = [&](int c, int it) {  // lane 0 only; chunk c -> box c & 1
+      if (it < my_tiles) {
+        const uint32_t b = bar(rbar + (c & 1));
         mbar_expect_tx(b, 4096);
-        tma_load_2d(io_s + c * 4096, &tmRes, b, hf * 96 + c * 32, (int)tile * 128 + quad * 32);
+        tma_load_2d(io_s + (c & 1) * 4096, &tmRes, b, hf * 96 + c * 32, ((int)blockIdx.x + it * (int)gridDim.x) * 128 + quad * 32);
       }
     };
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) res_issue(c, blockIdx.x);
-    }
+    auto drain = [&]() {  // every store issued so far has read its staging data
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    };
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t ph = (uint32_t)it & 1u;
-      const int row0 = tile * 128 + quad * 32;  // first row of this warp's boxes
+    // ---------------- E1: projection epilogue of local tile `it`: t' = acc + bp + res ; Y <- t' + b2 ; xn2 -> smem ----------------
+    auto E1 = [&](int it) {
+      const uint32_t tY = tlane + TY + 192u * (uint32_t)(it & 1) + (uint32_t)hf * 96u;
       long long* dbg = (a.dbg && ew == 0 && lane == 0 && it < 32) ? a.dbg + 16 * ((size_t)blockIdx.x * 32 + it) : nullptr;
-      long long* dbg2 = dbg ? dbg + 16 * 148 * 32 : nullptr;  // second region: projection-epilogue detail
-
-      // ---------------- projection epilogue: t' = acc + bp + res ; Y <- t' + b2 ; xn2 -> smem ----------------
       f32x2 tv[3][16];  // this thread's 96 values of the row, as (even, odd) column pairs
       if (dbg) dbg[0] = clock64();
-      mbar_wait_warp(bar(SB_PFULL), ph, lane);
+      mbar_wait_warp(bar(SB_PFULL + (it & 1)), ((uint32_t)it >> 1) & 1u, lane);
       if (dbg) dbg[1] = clock64();
       tc_fence_after();
       {
         uint32_t raw[3][32];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tlane + 192 + hf * 96 + c * 32, raw[c]);
+        for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tY + c * 32, raw[c]);
         tmem_wait_ld();
-        if (dbg2) dbg2[0] = clock64();
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -303,9 +360,9 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int nb = hf * 96 + c * 32;
-        mbar_wait_warp(bar(rbar + c), ph, lane);
-        if (dbg2) dbg2[1 + 2 * c] = clock64();
-        const uint8_t* rb = io + c * 4096;
+        mbar_wait_warp(bar(rbar + (c & 1)), n_res[c & 1] & 1u, lane);
+        ++n_res[c & 1];
+        const uint8_t* rb = io + (c & 1) * 4096;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 r = *reinterpret_cast<const float4*>(rb + sw128_off(lane, j));
@@ -313,7 +370,10 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
           tv[c][2 * j] = f2_add(tv[c][2 * j], f2_add(f2_pack(r.x, r.y), f2_pack(b.x, b.y)));
           tv[c][2 * j + 1] = f2_add(tv[c][2 * j + 1], f2_add(f2_pack(r.z, r.w), f2_pack(b.z, b.w)));
         }
-        if (dbg2) dbg2[2 + 2 * c] = clock64();
+        if (c == 0) {  // B0 is free again: fetch the third chunk while the second is processed
+          __syncwarp();
+          if (lane == 0) res_issue(2, it);
+        }
         if (c == 2 && mask_tail) {  // padded channels stay exact zeros
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -331,7 +391,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
             f2_unpack_u(f2_add(tv[c][2 * j], f2_pack(b.x, b.y)), y[4 * j], y[4 * j + 1]);
             f2_unpack_u(f2_add(tv[c][2 * j + 1], f2_pack(b.z, b.w)), y[4 * j + 2], y[4 * j + 3]);
           }
-          tmem_st32_u32(tlane + nb, y);
+          tmem_st32_u32(tY + c * 32, y);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -343,32 +403,32 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
       red[row * 2 + hf] = make_float2(f2_hsum(f2_add(f2_add(sm[0], sm[1]), f2_add(sm[2], sm[3]))),
                                       f2_hsum(f2_add(f2_add(sqv[0], sqv[1]), f2_add(sqv[2], sqv[3]))));
       named_bar_sync(1 + quad, 64);
-      {
-        const float2 r0 = red[row * 2], r1 = red[row * 2 + 1];
-        const float mean = (r0.x + r1.x) * invC;
-        const float var = fmaxf((r0.y + r1.y) * invC - mean * mean, 0.0f);
-        const float rstd = rsqrtf(var + a.eps);
-        const f32x2 sc2 = f2_splat(rstd), sh2 = f2_splat(-mean * rstd);
-        // the projection MMAs completed before SB_PFULL fired, so the o tile is dead: overwrite it with xn2 in the
-        // SWIZZLE_128B K-major layout TMA would have produced.  Padded channels must stay exact zeros.
+      const float2 r0 = red[row * 2], r1 = red[row * 2 + 1];
+      const float mean = (r0.x + r1.x) * invC;
+      const float var = fmaxf((r0.y + r1.y) * invC - mean * mean, 0.0f);
+      const float rstd = rsqrtf(var + a.eps);
+      const f32x2 sc2 = f2_splat(rstd), sh2 = f2_splat(-mean * rstd);
+      // the xn2 tile is shared by consecutive tiles: the fc1 MMAs of the previous tile must have read it
+      if (it > 0) mbar_wait_warp(bar(SB_XNFREE), (uint32_t)(it - 1) & 1u, lane);
+      if (dbg) dbg[3] = clock64();
+      // xn2 in the SWIZZLE_128B K-major layout TMA would have produced.  Padded channels must stay exact zeros.
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int nb = hf * 96 + c * 32;
+      for (int c = 0; c < 3; ++c) {
+        const int nb = hf * 96 + c * 32;
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint32_t w[4];
+        for (int qd = 0; qd < 4; ++qd) {
+          uint32_t w[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              w[i] = f2_to_bf16x2(f2_fma(tv[c][4 * qd + i], sc2, sh2));
-              if (c == 2 && mask_tail) {
-                const int col = nb + 8 * qd + 2 * i;
-                w[i] = col >= a.C ? 0u : (col + 1 >= a.C ? (w[i] & 0xffffu) : w[i]);
-              }
+          for (int i = 0; i < 4; ++i) {
+            w[i] = f2_to_bf16x2(f2_fma(tv[c][4 * qd + i], sc2, sh2));
+            if (c == 2 && mask_tail) {
+              const int col = nb + 8 * qd + 2 * i;
+              w[i] = col >= a.C ? 0u : (col + 1 >= a.C ? (w[i] & 0xffffu) : w[i]);
             }
-            const int col = nb + 8 * qd;
-            *reinterpret_cast<uint4*>(smem + ST_OFF_OX + (col >> 6) * ST_TILE + sw128_off(row, (col & 63) >> 3)) =
-                make_uint4(w[0], w[1], w[2], w[3]);
           }
+          const int col = nb + 8 * qd;
+          *reinterpret_cast<uint4*>(smem + ST_OFF_XN + (col >> 6) * ST_TILE + sw128_off(row, (col & 63) >> 3)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       tmem_wait_st();
@@ -376,49 +436,27 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(SB_XNREADY));
-      if (dbg) dbg[3] = clock64();
+      if (dbg) dbg[4] = clock64();
+    };
 
-      // ---------------- fc1 chunk epilogues: h = GELU(acc + b1) -> packed bf16 over its own accumulator ----------------
-      const f32x2 kC0 = f2_splat(0.79973199f), kC1 = f2_splat(0.03489978f), kHalf = f2_splat(0.5f);
-#pragma unroll 1
-      for (int ch = 0; ch < 3; ++ch) {
-        const int b = ch & 1;
-        mbar_wait_warp(bar(SB_XFULL + b), n_xfull[b] & 1u, lane);
-        ++n_xfull[b];
-        tc_fence_after();
-        if (dbg) dbg[4 + 2 * ch] = clock64();
-        const uint32_t tx = tlane + 192 + b * 128 + hf * 64;  // this warp's 64 hidden columns of the chunk
-        uint32_t raw[2][32];
-        tmem_ld32_nowait(tx, raw[0]);
-        tmem_ld32_nowait(tx + 32, raw[1]);
-        tmem_wait_ld();
-        if (dbg2 && ch == 0) dbg2[15] = clock64();
-        uint32_t pk[32];
-        const float* bb = s_b1 + ch * 128 + hf * 64;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 bv = *reinterpret_cast<const float4*>(bb + 4 * j);
-          const uint32_t* r4 = &raw[j >> 3][(4 * j) & 31];
-          pk[2 * j + 0] = gelu2_bf16(f2_add(f2_pack_u(r4[0], r4[1]), f2_pack(bv.x, bv.y)), kC0, kC1, kHalf);
-          pk[2 * j + 1] = gelu2_bf16(f2_add(f2_pack_u(r4[2], r4[3]), f2_pack(bv.z, bv.w)), kC0, kC1, kHalf);
-        }
-        tmem_st32_u32(tx, pk);  // K index 2i, 2i+1 of this half -> column i (low half = even k)
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(SB_HREADY + b));
-        if (dbg) dbg[5 + 2 * ch] = clock64();
-      }
-
-      // ---------------- final epilogue: t'' = Y ; TMA stores + LayerNorm_next ----------------
-      mbar_wait_warp(bar(SB_YFULL), ph, lane);
+    // ---------------- E3: final epilogue of local tile `it`: t'' = Y ; TMA stores + LayerNorm_next; refill the boxes ----------------
+    auto E3 = [&](int it, int it_refill) {
+      const uint32_t tY = tlane + TY + 192u * (uint32_t)(it & 1) + (uint32_t)hf * 96u;
+      const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128 + quad * 32;  // first row of this warp's boxes
+      long long* dbg = (a.dbg && ew == 0 && lane == 0 && it < 32) ? a.dbg + 16 * ((size_t)blockIdx.x * 32 + it) : nullptr;
+      f32x2 tv[3][16];
+      if (dbg) dbg[8] = clock64();
+      mbar_wait_warp(bar(SB_YFULL + (it & 1)), ((uint32_t)it >> 1) & 1u, lane);
       tc_fence_after();
-      if (dbg) dbg[10] = clock64();
+      if (dbg) dbg[9] = clock64();
       {
         uint32_t raw[3][32];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tlane + hf * 96 + c * 32, raw[c]);
+        for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tY + c * 32, raw[c]);
         tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(SB_YFREE + (it & 1)));  // Y_s may take the projection of tile it + 2
         if (mask_tail) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -429,40 +467,30 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) tv[c][i] = f2_pack_u(raw[c][2 * i], raw[c][2 * i + 1]);
       }
-      const long long next_tile = (long long)tile + gridDim.x;
-      auto drain = [&]() {  // every store issued so far has read its staging data
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
+      auto stage_f32 = [&](int c, int box) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 w;
+          f2_unpack_u(tv[c][2 * j], w.x, w.y);
+          f2_unpack_u(tv[c][2 * j + 1], w.z, w.w);
+          *reinterpret_cast<uint4*>(io + box * 4096 + sw128_off(lane, j)) = w;
+        }
       };
-      __syncwarp();  // every lane is done reading the residual boxes (projection epilogue of this tile)
-      if (dbg2) dbg2[8] = clock64();
-      if (a.has_f32) {  // all three fp32 chunks leave in one round: B_c <- chunk c
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 w;
-            f2_unpack_u(tv[c][2 * j], w.x, w.y);
-            f2_unpack_u(tv[c][2 * j + 1], w.z, w.w);
-            *reinterpret_cast<uint4*>(io + c * 4096 + sw128_off(lane, j)) = w;
-          }
-        if (dbg2) dbg2[9] = clock64();
+      if (a.has_f32) {  // round 1: chunks 0, 1 -> B0, B1
+        stage_f32(0, 0);
+        stage_f32(1, 1);
         fence_proxy_async();
-        if (dbg2) dbg2[10] = clock64();
         __syncwarp();
-        if (dbg2) dbg2[11] = clock64();
         if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) tma_store_2d(&tmOutF, io_s + c * 4096, hf * 96 + c * 32, row0);
+          tma_store_2d(&tmOutF, io_s, hf * 96, row0);
+          tma_store_2d(&tmOutF, io_s + 4096, hf * 96 + 32, row0);
           bulk_commit();
         }
-        if (dbg2) dbg2[12] = clock64();
       }
-      if (dbg) dbg[13] = clock64();
+      if (dbg) dbg[10] = clock64();
       float mean = 0.0f, rstd = 1.0f;
       if (a.do_ln) {  // statistics overlap the stores' drain
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sm[i] = sqv[i] = 0ull;
+        f32x2 sm[4] = {0ull, 0ull, 0ull, 0ull}, sqv[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -470,18 +498,17 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
             sm[i & 3] = f2_add(sm[i & 3], tv[c][i]);
             sqv[i & 3] = f2_fma(tv[c][i], tv[c][i], sqv[i & 3]);
           }
+        named_bar_sync(1 + quad, 64);  // the partner has read E1's entries of `red`
         red[row * 2 + hf] = make_float2(f2_hsum(f2_add(f2_add(sm[0], sm[1]), f2_add(sm[2], sm[3]))),
                                         f2_hsum(f2_add(f2_add(sqv[0], sqv[1]), f2_add(sqv[2], sqv[3]))));
-        if (dbg2) dbg2[13] = clock64();
         named_bar_sync(1 + quad, 64);
-        if (dbg2) dbg2[14] = clock64();
         const float2 r0 = red[row * 2], r1 = red[row * 2 + 1];
         mean = (r0.x + r1.x) * invC;
         const float var = fmaxf((r0.y + r1.y) * invC - mean * mean, 0.0f);
         rstd = rsqrtf(var + a.eps);
-        named_bar_sync(1 + quad, 64);  // the partner has read `red` before the next tile's projection epilogue rewrites it
+        named_bar_sync(1 + quad, 64);  // the partner has read `red` before the next E1 rewrites it
       }
-      if (dbg) dbg[14] = clock64();
+      if (dbg) dbg[11] = clock64();
       // bf16 word (two columns) i of chunk c: LayerNorm_next or a plain copy
       const f32x2 sc2 = f2_splat(a.do_ln ? rstd : 1.0f), sh2 = f2_splat(a.do_ln ? -mean * rstd : 0.0f);
       auto bf_quad = [&](int c, int j) -> uint4 {  // columns [4j*2 .. 4j*2+8) of chunk c -> 16 bytes
@@ -501,39 +528,92 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
         }
         return make_uint4(w[0], w[1], w[2], w[3]);
       };
-      drain();  // fp32 boxes have been read
-      if (dbg) dbg[15] = clock64();
-      if (lane == 0) {  // B0, B1 take the next tile's residual right away; B2 stages the bf16 output first
-        res_issue(0, next_tile);
-        res_issue(1, next_tile);
-      }
+      drain();  // round 1 has been read
+      if (dbg) dbg[12] = clock64();
+      // round 2: fp32 chunk 2 -> B0 ; bf16 columns [0,64) of this half (one [32 x 64] SWIZZLE_128B box) -> B1
+      if (a.has_f32) stage_f32(2, 0);
       if (a.has_bf) {
-        // columns [0,64) of this half: one [32 x 64] bf16 SWIZZLE_128B box; columns [64,96): a [32 x 32] SWIZZLE_64B box
-        uint8_t* stg = io + 2 * 4096;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(stg + sw128_off(lane, j)) = bf_quad(j >> 2, j & 3);
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(io + 4096 + sw128_off(lane, j)) = bf_quad(j >> 2, j & 3);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (a.has_f32) tma_store_2d(&tmOutF, io_s, hf * 96 + 64, row0);
+        if (a.has_bf) tma_store_2d(&tmOutB2, io_s + 4096, hf * 96, row0);
+        bulk_commit();
+      }
+      drain();
+      // round 3: bf16 columns [64,96): a [32 x 32] SWIZZLE_64B box -> B0 ; B1 already takes the refill tile's residual
+      if (lane == 0) res_issue(1, it_refill);
+      if (a.has_bf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(io + sw64_off(lane, j)) = bf_quad(2, j);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmOutB2, io_s + 2 * 4096, hf * 96, row0);
-          bulk_commit();
-        }
-        drain();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + sw64_off(lane, j)) = bf_quad(2, j);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmOutB, io_s + 2 * 4096, hf * 96 + 64, row0);
+          tma_store_2d(&tmOutB, io_s, hf * 96 + 64, row0);
           bulk_commit();
         }
         drain();
       }
-      if (lane == 0) res_issue(2, next_tile);
-      tc_fence_before();  // Y and the projection columns are re-written by this warp in the next tile (program order)
-      if (dbg) dbg[11] = clock64();
+      if (lane == 0) res_issue(0, it_refill);
+      if (dbg) dbg[13] = clock64();
+    };
+
+    if (my_tiles > 0) {
+      if (lane == 0)
+        for (int c = 0; c < 2; ++c) res_issue(c, 0);
+      E1(0);
+      __syncwarp();
+      if (lane == 0)  // no final epilogue runs between the first two projection epilogues: refill the boxes here
+        for (int c = 0; c < 2; ++c) res_issue(c, 1);
+      for (int it = 1; it < my_tiles; ++it) {
+        E1(it);
+        E3(it - 1, it + 1);
+      }
+      E3(my_tiles - 1, my_tiles);
+      if (lane == 0) bulk_wait_all();  // every store of this warp has landed before the CTA may exit
     }
-    if (lane == 0) bulk_wait_all();  // every store of this warp has landed before the CTA may exit
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ST_REGS_GELU));  // below the launch value of 96: a release
+    // =========================== GELU warps (8): h = GELU(acc + b1) -> packed bf16 over its own accumulator ===========================
+    const int ew = warp - ST_GELU_WARP0;
+    const int hf = ew >> 2;     // 32-column half of the 64-unit chunk
+    const int quad = warp & 3;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const f32x2 kC0 = f2_splat(0.79973199f), kC1 = f2_splat(0.03489978f), kHalf = f2_splat(0.5f);
+    uint32_t n_xfull[2] = {0, 0};
+    for (int it = 0; it < my_tiles; ++it) {
+      long long* dbg = (a.dbg && ew == 0 && lane == 0 && it < 32) ? a.dbg + 16 * ((size_t)(gridDim.x + blockIdx.x) * 32 + it) : nullptr;
+#pragma unroll 1
+      for (int ch = 0; ch < ST_NCHUNK; ++ch) {
+        const int b = ch & 1;
+        if (dbg) dbg[2 * ch] = clock64();
+        mbar_wait_warp(bar(SB_XFULL + b), n_xfull[b] & 1u, lane);
+        ++n_xfull[b];
+        tc_fence_after();
+        if (dbg) dbg[2 * ch + 1] = clock64();
+        const uint32_t tx = tlane + TX + 64u * (uint32_t)b + 32u * (uint32_t)hf;  // this warp's 32 hidden columns of the chunk
+        uint32_t raw[32];
+        tmem_ld32_nowait(tx, raw);
+        tmem_wait_ld();
+        uint32_t pk[16];
+        const float* bb = s_b1 + ch * 64 + hf * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bv = *reinterpret_cast<const float4*>(bb + 4 * j);
+          pk[2 * j + 0] = gelu2_bf16(f2_add(f2_pack_u(raw[4 * j], raw[4 * j + 1]), f2_pack(bv.x, bv.y)), kC0, kC1, kHalf);
+          pk[2 * j + 1] = gelu2_bf16(f2_add(f2_pack_u(raw[4 * j + 2], raw[4 * j + 3]), f2_pack(bv.z, bv.w)), kC0, kC1, kHalf);
+        }
+        tmem_st16_u32(tx, pk);  // K index 2i, 2i+1 of this half -> column i (low half = even k)
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(SB_HREADY + b));
+      }
+      if (dbg) dbg[12] = clock64();
+    }
   }
 
   tc_fence_before();
@@ -560,7 +640,7 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
   };
   SSR_TRY(map2d(&tmO, f.o, 2, f.ld_o, f.M, f.ld_o, 64, 128, 128));
   SSR_TRY(map2d(&tmWp, f.Wp, 2, 192, 192, 192, 64, 192, 128));
-  SSR_TRY(map2d(&tmW1, f.W1, 2, 192, 384, 192, 64, 128, 128));
+  SSR_TRY(map2d(&tmW1, f.W1, 2, 192, 384, 192, 64, 64, 128));
   SSR_TRY(map2d(&tmW2, f.W2, 2, 384, 192, 384, 64, 192, 128));
   SSR_TRY(map2d(&tmRes, f.res, 4, 192, f.M, f.ldres, 32, 32, 128));
   SSR_TRY(map2d(&tmResPf, f.res, 4, 192, f.M, f.ldres, 32, 128, 128));
