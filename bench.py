@@ -487,7 +487,7 @@ def run_extra(args):
     model = getattr(M, name)(scale=SCALE, **kw).cuda()
     model = model.train() if training else model.eval()
     if not training:
-        model.precision = "bf16"
+        model.precision = args.precision
     dist = None
     if world > 1:
         dist = init_dist(local)
@@ -588,7 +588,7 @@ def run_extra(args):
     line = {
         "metric": f"{name.lower()}_x4_{'train' if training else 'inference'}_output_megapixels_per_second", "value": mpix / (ms / 1e3),
         "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if training else args.precision, "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": B, "lr_size": [H, W],
                    "parallelism": f"data-parallel x{world}" if training else f"replicas x{world}",
                    "trainer_pieces": None if not training else ("torch.optim.Adam + F.l1_loss + torch DDP" if args.stock_trainer else
