@@ -488,6 +488,9 @@ def run_extra(args):
     model = model.train() if training else model.eval()
     if not training:
         model.precision = args.precision
+        model.trust_param_versions = bool(args.trust_params)
+        if args.no_graph:
+            model.cuda_graphs = False
     dist = None
     if world > 1:
         dist = init_dist(local)
@@ -561,6 +564,8 @@ def run_extra(args):
         if dist is not None:
             dist.destroy_process_group()
         return
+    inner = model.module if hasattr(model, "module") else model
+    inner.cuda_graphs = False  # the per-kernel profile brackets every launch with events: eager launches
     lib.ssr_profile_begin()
     step()
     buf = _lib.ctypes.create_string_buffer(1 << 16)
@@ -591,6 +596,9 @@ def run_extra(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if training else args.precision, "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": B, "lr_size": [H, W],
                    "parallelism": f"data-parallel x{world}" if training else f"replicas x{world}",
+                   "host_path": None if training else ("CUDA-graph replay" if not args.no_graph else "eager launches") +
+                                (", packed-weight cache keyed on versions only" if args.trust_params else
+                                 ", packed-weight cache keyed on versions + a per-forward device checksum (one 16-byte sync)"),
                    "trainer_pieces": None if not training else ("torch.optim.Adam + F.l1_loss + torch DDP" if args.stock_trainer else
                                                                 "engine.FusedAdam + engine.L1Loss + engine.DistributedDataParallel"),
                    "l2": "inputs are a few MB; the per-step activation working set (0.2 - 25 GB) is far beyond the 126 MB L2"},
@@ -619,6 +627,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="tiles per network pass (0 = all 220 at once)")
     ap.add_argument("--cpu-tiles", type=int, default=64, help="tiles timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--trust-params", action="store_true",
+                    help="inference workloads: skip the per-forward checksum of the packed-weight cache key (model.trust_param_versions)")
+    ap.add_argument("--no-graph", action="store_true", help="inference workloads: no CUDA-graph replay of the launch sequence")
     ap.add_argument("--stock-trainer", action="store_true",
                     help="cfg2 / cfg4: torch.optim.Adam + nn.L1Loss + torch DDP instead of studiosr_b200.engine's flat-buffer pieces")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],

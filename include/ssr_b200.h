@@ -189,8 +189,38 @@ int ssr_l1_loss(const float* out, const float* y, int64_t n, float* loss, float*
 int ssr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
                   double weight_decay, int64_t step, float grad_scale, void* stream);
 
+/* ---- device-side evaluation metric and training augmentation -------------------------------------------------
+ * ssr_psnr_mse_u8       compute_psnr (utils/metrics.py:36-49) up to its last line: im1 [h1,w1,3], im2 [h2,w2,3] DEVICE uint8 HWC are
+ *                       cropped to the common size (trailing rows / columns), `crop_border` pixels are cut from every side, the
+ *                       squared error of the BT.601 luma (y_only != 0, metrics.py:11-17) or of the three channels is averaged
+ *                       into *dev_mse (DEVICE double); PSNR = 20 log10(255 / sqrt(mse)), inf for mse == 0.
+ * ssr_augment_pairs_u8  the training transform of dataset.py:50-58 + array2tensor (transforms.py:8-68) for n_pairs (LR, HR) pairs
+ *                       in one launch: x_out DEVICE fp32 [n_pairs,3,size,size], y_out [n_pairs,3,size*scale,size*scale], values / 255.
+ *                       dev_pairs: DEVICE array of ssr_aug_pair; the HOST draws xs, ys and the flags (the reference uses python's
+ *                       `random`, so its seeded sequence can be reproduced draw for draw). */
+typedef struct ssr_aug_pair {
+  const uint8_t* lq; /* DEVICE uint8 HWC LR image */
+  const uint8_t* gt; /* DEVICE uint8 HWC HR image (scale x larger) */
+  int lq_w, gt_w;    /* image widths in pixels */
+  int xs, ys;        /* crop origin in the LR image (paired_random_crop, transforms.py:8-22) */
+  int flags;         /* bit 0: fliplr, bit 1: flipud, bit 2: rot90 (np.rot90, counter-clockwise) -- applied in that order */
+  int pad;
+} ssr_aug_pair;
+size_t ssr_psnr_workspace_bytes(void);
+int ssr_psnr_mse_u8(const uint8_t* im1, int h1, int w1, const uint8_t* im2, int h2, int w2, int crop_border, int y_only,
+                    double* dev_mse, void* workspace, size_t workspace_bytes, void* stream);
+int ssr_augment_pairs_u8(const void* dev_pairs, int n_pairs, int size, int scale, float* x_out, float* y_out, void* stream);
+
+/* Checksum of n fp32 DEVICE tensors in two launches (the Python boundary keys its packed-weight cache on it: writes through
+ * `tensor.data` do not bump torch's version counters).  dev_ptrs / dev_numels: DEVICE int64 [n] (addresses, element counts);
+ * dev_partial: DEVICE double [2n] scratch; dev_out2: DEVICE double [2]. */
+int ssr_tensors_checksum(const int64_t* dev_ptrs, const int64_t* dev_numels, int n, double* dev_partial, double* dev_out2, void* stream);
+
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 int64_t ssr_launch_count(void);
+/* A host that captured calls of this library into a CUDA graph reports each replay here (kernels = the count's increase during
+ * the capture), so that ssr_launch_count keeps meaning "kernels of this library that ran". */
+void ssr_note_graph_replay(int64_t kernels);
 /* Per-launch device timing for the roofline report: between begin and end every kernel launch is
  * bracketed by CUDA events on its own stream.  ssr_profile_end synchronises the device and writes a
  * JSON object {"<kernel class>": {"launches", "ms", "flops", "bytes"}} (algorithmic FLOPs / bytes

@@ -445,6 +445,51 @@ def blend_tiles(tiles: torch.Tensor, H: int, W: int, scale: int, tile: int = 64,
     return acc[:, row_begin:row_end] / wsum[row_begin:row_end]
 
 
+def to_y(image):
+    """utils/metrics.py:11-17: BT.601 luma of an HWC image (uint8 -> float32 / 255 first), float64 result."""
+    import numpy as np
+
+    if not (image.ndim == 3 and image.shape[-1] == 3):
+        return image
+    if image.dtype == np.uint8:
+        image = image.astype(np.float32) / 255.0
+    return np.dot(image, [65.481, 128.553, 24.966]) + 16.0
+
+
+def compute_psnr(im1, im2, y_only: bool = False, crop_border: int = 0) -> float:
+    """utils/metrics.py:20-49 (crop_img_to_equal + compute_psnr) on numpy HWC images."""
+    import numpy as np
+
+    h, w = min(im1.shape[0], im2.shape[0]), min(im1.shape[1], im2.shape[1])
+    im1, im2 = im1[:h, :w], im2[:h, :w]
+    if crop_border:
+        im1 = im1[crop_border:-crop_border, crop_border:-crop_border]
+        im2 = im2[crop_border:-crop_border, crop_border:-crop_border]
+    if y_only:
+        im1, im2 = to_y(im1), to_y(im2)
+    elif im1.dtype != np.uint8:
+        im1, im2 = im1 * 255.0, im2 * 255.0
+    error = np.mean((im1.astype(np.float32) - im2.astype(np.float32)) ** 2)
+    return float("inf") if error == 0 else float(20 * np.log10(255.0 / np.sqrt(error)))
+
+
+def augment_pair(lq, gt, size: int, scale: int, xs: int, ys: int, flags: int):
+    """data/transforms.py:8-68 with the random draws made explicit: crop at (xs, ys), then fliplr (flags & 1), flipud (flags & 2),
+    np.rot90 (flags & 4) in the order of dataset.py:50-58, then array2tensor (CHW float32 / 255)."""
+    import numpy as np
+
+    a = lq[ys:ys + size, xs:xs + size]
+    b = gt[ys * scale:(ys + size) * scale, xs * scale:(xs + size) * scale]
+    if flags & 1:
+        a, b = np.fliplr(a), np.fliplr(b)
+    if flags & 2:
+        a, b = np.flipud(a), np.flipud(b)
+    if flags & 4:
+        a, b = np.rot90(a), np.rot90(b)
+    f = lambda t: np.ascontiguousarray(t.transpose(2, 0, 1)).astype(np.float32) / 255
+    return f(a), f(b)
+
+
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 255.0) -> float:
     """utils/metrics.py:36-49 on already-cropped arrays (no Y conversion)."""
     mse = ((a.double() - b.double()) ** 2).mean().item()

@@ -62,7 +62,12 @@ SYMBOLS = {
     "ssr_l1_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_double,
                               c_int64, c_float, c_void_p]),
+    "ssr_psnr_workspace_bytes": (c_size_t, []),
+    "ssr_psnr_mse_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ssr_augment_pairs_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ssr_tensors_checksum": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ssr_launch_count": (c_int64, []),
+    "ssr_note_graph_replay": (None, [c_int64]),
     "ssr_profile_begin": (c_int, []),
     "ssr_profile_end": (c_int, [c_char_p, c_size_t]),
     "ssr_op_linear": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

@@ -97,6 +97,51 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
   }
 }
 
+// Checksum of a set of fp32 tensors (the packed-weight cache key of the Python boundary): one block per tensor sums x and
+// x * (1 + (i & 1023)) in double in a fixed order; a second launch folds the per-tensor pairs with tensor-dependent weights.
+__global__ void __launch_bounds__(256) checksum_tensors_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ numels,
+                                                               double* __restrict__ partial) {
+  __shared__ double r0[8], r1[8];
+  const float* x = reinterpret_cast<const float*>(ptrs[blockIdx.x]);
+  const long long n = numels[blockIdx.x];
+  double a = 0.0, b = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = (double)__ldg(x + i);
+    a += v;
+    b += v * (double)(1 + (int)(i & 1023));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    r0[threadIdx.x >> 5] = a;
+    r1[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sa = 0.0, sb = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      sa += r0[w];
+      sb += r1[w];
+    }
+    partial[2 * blockIdx.x] = sa;
+    partial[2 * blockIdx.x + 1] = sb;
+  }
+}
+__global__ void checksum_fold_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < n; ++i) {
+      a += partial[2 * i] * (double)(1 + (i % 61));
+      b += partial[2 * i + 1] * (double)(1 + (i % 67));
+    }
+    out[0] = a;
+    out[1] = b;
+  }
+}
+
 }  // namespace ssr
 
 using namespace ssr;
@@ -120,6 +165,17 @@ int ssr_l1_loss(const float* out, const float* y, int64_t n, float* loss, float*
     l1_final_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const double*>(workspace), (int)blocks, loss, 1.0 / (double)n);
     count_launch(2);
   }
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+int ssr_tensors_checksum(const int64_t* dev_ptrs, const int64_t* dev_numels, int n, double* dev_partial, double* dev_out2, void* stream) {
+  SSR_CHECK(dev_ptrs && dev_numels && dev_partial && dev_out2 && n > 0, SSR_E_INVALID, "ssr_tensors_checksum: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  checksum_tensors_kernel<<<n, 256, 0, s>>>(reinterpret_cast<const long long*>(dev_ptrs), reinterpret_cast<const long long*>(dev_numels),
+                                           dev_partial);
+  checksum_fold_kernel<<<1, 32, 0, s>>>(dev_partial, n, dev_out2);
+  count_launch(2);
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;
 }

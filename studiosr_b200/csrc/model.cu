@@ -1459,6 +1459,7 @@ extern "C" {
 int ssr_version(void) { return SSR_VERSION; }
 const char* ssr_last_error(void) { return g_err; }
 int64_t ssr_launch_count(void) { return (int64_t)g_launches.load(); }
+void ssr_note_graph_replay(int64_t kernels) { g_launches.fetch_add((long long)kernels, std::memory_order_relaxed); }
 
 int ssr_profile_begin(void) {
   for (ProfRec* r : g_prof) {

@@ -15,6 +15,28 @@ from ..native import NativeModel
 DEFAULT_FP32_MODE = os.environ.get("STUDIOSR_B200_FP32_MODE", "fp32")
 TRUST_PARAM_VERSIONS = os.environ.get("STUDIOSR_B200_TRUST_PARAM_VERSIONS", "0") == "1"
 
+GRAPH_MAX_LR_PIXELS = int(os.environ.get("STUDIOSR_B200_GRAPH_MAX_LR_PIXELS", str(4 * 96 * 96)))
+
+# bumped whenever any nn.Module registers a parameter / buffer / submodule: validates the per-model tensor-list caches in O(1)
+_STRUCT_VERSION = [0]
+
+
+def _bump_struct_version(*_args):
+    _STRUCT_VERSION[0] += 1
+    return None
+
+
+try:
+    from torch.nn.modules.module import (register_module_buffer_registration_hook, register_module_module_registration_hook,
+                                         register_module_parameter_registration_hook)
+
+    register_module_parameter_registration_hook(_bump_struct_version)
+    register_module_buffer_registration_hook(_bump_struct_version)
+    register_module_module_registration_hook(_bump_struct_version)
+    _HAVE_REG_HOOKS = True
+except ImportError:  # no hooks: every call re-walks the module tree
+    _HAVE_REG_HOOKS = False
+
 
 def diverge_images(image: torch.Tensor) -> List[torch.Tensor]:
     """The 8 rot90 / fliplr variants of an HWC image, in the order of common.py:10-16."""
@@ -102,23 +124,47 @@ class Model(nn.Module):
         # True skips the per-forward checksum (one device sync) of the packed-weight cache key: safe when parameters are only
         # changed through autograd-visible ops / load_state_dict, or when invalidate_native() is called after `.data` writes
         self.trust_param_versions: bool = False
+        # CUDA-graph replay of the inference launch sequence: None = automatic (small inputs, where ~90 launches of 10-20 us
+        # kernels are launch-bound: up to GRAPH_MAX_LR_PIXELS LR pixels per call), True / False = always / never
+        self.cuda_graphs: Optional[bool] = None
 
     # ---- native plumbing ------------------------------------------------------------------
     def _native_config(self, precision: int) -> "_lib.ModelConfig":
         raise NotImplementedError
 
+    def _float_tensors(self):
+        """The floating-point state_dict tensors, cached: walking ~500 modules costs 1.4 ms per forward.  The cache is dropped
+        whenever ANY module registers a parameter, buffer or submodule (global registration hooks bump _STRUCT_VERSION)."""
+        c = self.__dict__.get("_ft_cache") if _HAVE_REG_HOOKS else None
+        if c is None or c[0] != _STRUCT_VERSION[0]:
+            c = (_STRUCT_VERSION[0], [t for t in self.state_dict(keep_vars=True).values() if t.is_floating_point()])
+            self.__dict__["_ft_cache"] = c
+        return c[1]
+
     def _param_version(self):
         """Key of the packed-weight cache.  `_version` alone misses writes through `.data` (p.data.mul_(), p.data.copy_(),
-        p.data = ...), so the storage pointer and one cheap on-device checksum per call (sum and sum of |x| over all
-        parameters, a single foreach reduction) are part of the key; `invalidate_native()` forces a re-pack explicitly."""
-        ts = [t for t in self.state_dict(keep_vars=True).values() if t.is_floating_point()]
-        key = tuple((id(t), t._version, t.data_ptr()) for t in ts)
-        cuda = [t.detach() for t in ts if t.is_cuda]
-        if cuda and not (self.trust_param_versions or TRUST_PARAM_VERSIONS):
-            with torch.no_grad():
-                n1 = torch.stack(torch._foreach_norm(cuda, 1)).double()
-                n2 = torch.stack(torch._foreach_norm(cuda, 2)).double()
-                key += (float(n1.sum()), float((n2 * torch.arange(1, len(cuda) + 1, device=n2.device)).sum()))
+        p.data = ...), so the storage pointers and a checksum of the parameter values (ssr_tensors_checksum: two launches over a
+        cached device pointer table + one 16-byte read-back, ~50 us) are part of the key; `trust_param_versions` skips the
+        checksum, `invalidate_native()` forces a re-pack explicitly."""
+        ts = self._float_tensors()
+        key = tuple((t._version, t.data_ptr()) for t in ts)
+        if self.trust_param_versions or TRUST_PARAM_VERSIONS:
+            return key
+        cuda = [t for t in ts if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()]
+        if cuda:
+            dev = cuda[0].device
+            ptrs = tuple(t.data_ptr() for t in cuda)
+            tab = self.__dict__.get("_ck_table")
+            if tab is None or tab[0] != ptrs:
+                n = len(cuda)
+                tab = (ptrs, torch.tensor(ptrs, dtype=torch.int64, device=dev), torch.tensor([t.numel() for t in cuda], dtype=torch.int64, device=dev),
+                       torch.empty(2 * n, dtype=torch.float64, device=dev), torch.empty(2, dtype=torch.float64, device=dev))
+                self.__dict__["_ck_table"] = tab
+            lib = _lib.load()
+            with torch.cuda.device(dev):
+                _lib.check(lib.ssr_tensors_checksum(tab[1].data_ptr(), tab[2].data_ptr(), len(cuda), tab[3].data_ptr(), tab[4].data_ptr(),
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+            key += tuple(tab[4].tolist())
         return key
 
     def invalidate_native(self) -> None:
@@ -130,6 +176,8 @@ class Model(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_natives"] = {}
+        state.pop("_ft_cache", None)
+        state.pop("_ck_table", None)
         return state
 
     def __deepcopy__(self, memo):
@@ -138,6 +186,8 @@ class Model(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k in ("_ft_cache", "_ck_table"):
+                continue
             new.__dict__[k] = {} if k == "_natives" else copy.deepcopy(v, memo)
         return new
 
@@ -172,7 +222,12 @@ class Model(nn.Module):
         precision = self._resolve_precision(x)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._train_forward(x, precision)
-        return self._native(x.device, precision).forward(x, self.scale, self._pad_mode())
+        return self._native(x.device, precision).forward(x, self.scale, self._pad_mode(), graph=self._use_graph(x.shape[0] * x.shape[2] * x.shape[3]))
+
+    def _use_graph(self, lr_pixels: int) -> bool:
+        if self.cuda_graphs is not None:
+            return bool(self.cuda_graphs)
+        return lr_pixels <= GRAPH_MAX_LR_PIXELS and not torch.cuda.is_current_stream_capturing()
 
     def _trainable(self) -> bool:
         return self.TRAINABLE
@@ -213,7 +268,7 @@ class Model(nn.Module):
         dev = self._device()
         img = torch.from_numpy(np.ascontiguousarray(image)).to(dev)
         precision = self.precision or DEFAULT_FP32_MODE
-        out = self._native(dev, precision).upscale_u8(img.unsqueeze(0), self.scale)[0]
+        out = self._native(dev, precision).upscale_u8(img.unsqueeze(0), self.scale, graph=self._use_graph(img.shape[0] * img.shape[1]))[0]
         return out.cpu().numpy()
 
     @torch.inference_mode()

@@ -27,6 +27,7 @@ class NativeModel:
         _lib.check(self.lib.ssr_model_create(_lib.ctypes.byref(cfg), idx, _lib.ctypes.byref(self.handle)))
         self.version = None
         self._ws: Optional[torch.Tensor] = None
+        self._graphs: Dict = {}  # (entry, B, C, H, W, pad_mode) -> (CUDAGraph, static input, static output, workspace)
 
     def __del__(self):
         try:
@@ -46,6 +47,7 @@ class NativeModel:
                 _lib.check(self.lib.ssr_model_set_param(self.handle, name.encode(), h.data_ptr(), h.numel()))
             _lib.check(self.lib.ssr_model_finalize(self.handle))
         self.version = version
+        self._graphs.clear()  # finalize may have moved the packed weights: captured graphs hold their old addresses
 
     # -- workspace ----------------------------------------------------------------------------
     def workspace(self, nbytes: int) -> torch.Tensor:
@@ -55,9 +57,44 @@ class NativeModel:
         return self._ws
 
     # -- entry points -------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, scale: int, pad_mode: int) -> torch.Tensor:
+    def _graphed(self, key, x: torch.Tensor, out_shape, out_dtype, need_bytes: int, call):
+        """Replay (capture on first use) the launch sequence of one entry point at one shape as a CUDA graph: at batch 1 a
+        SwinIR forward is ~87 launches of 10-20 us kernels and the host launch path dominates (BASELINE.json config 1).
+        `call(x_static, y_static, ws)` must enqueue everything on the current stream and touch no other memory."""
+        g = self._graphs.get(key)
+        if g is None:
+            xs, ys = torch.empty_like(x), torch.empty(out_shape, dtype=out_dtype, device=x.device)
+            ws = torch.empty(int(need_bytes), dtype=torch.uint8, device=x.device)  # owned by the graph: never re-allocated
+            xs.copy_(x)
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                call(xs, ys, ws)  # eager warm-up on the side stream: one-time cudaFuncSetAttribute calls happen outside the capture
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            l0 = self.lib.ssr_launch_count()
+            with torch.cuda.graph(graph):
+                call(xs, ys, ws)
+            g = (graph, xs, ys, ws, self.lib.ssr_launch_count() - l0)
+            self._graphs[key] = g
+        graph, xs, ys, _, kernels = g
+        xs.copy_(x, non_blocking=True)
+        graph.replay()
+        self.lib.ssr_note_graph_replay(kernels)
+        return ys.clone()
+
+    def forward(self, x: torch.Tensor, scale: int, pad_mode: int, graph: bool = False) -> torch.Tensor:
         B, C, H, W = x.shape
         x = x.detach().to(torch.float32).contiguous()
+        if graph:
+            with torch.cuda.device(self.index):
+                need = self.lib.ssr_model_workspace_bytes(self.handle, B, H, W, pad_mode)
+
+                def call(xs, ys, ws):
+                    _lib.check(self.lib.ssr_model_forward(self.handle, xs.data_ptr(), ys.data_ptr(), B, H, W, pad_mode, ws.data_ptr(),
+                                                          ws.numel(), _stream_ptr(x.device)))
+
+                return self._graphed(("fwd", B, C, H, W, pad_mode), x, (B, C, H * scale, W * scale), torch.float32, need, call)
         y = torch.empty((B, C, H * scale, W * scale), dtype=torch.float32, device=x.device)
         with torch.cuda.device(self.index):
             need = self.lib.ssr_model_workspace_bytes(self.handle, B, H, W, pad_mode)
@@ -104,9 +141,19 @@ class NativeModel:
                                                          None if drop_scale is None else drop_scale.data_ptr(), self._ptr_array(grads), B, H, W,
                                                          ws.data_ptr(), ws.numel(), _stream_ptr(dy.device)))
 
-    def upscale_u8(self, img: torch.Tensor, scale: int) -> torch.Tensor:
+    def upscale_u8(self, img: torch.Tensor, scale: int, graph: bool = False) -> torch.Tensor:
         """img: uint8 [B,H,W,3] on the device -> uint8 [B,sH,sW,3]."""
         B, H, W, _ = img.shape
+        if graph:
+            img = img.contiguous()
+            with torch.cuda.device(self.index):
+                need = self.lib.ssr_model_workspace_bytes(self.handle, B, H, W, _lib.PAD_EVAL)
+
+                def call(xs, ys, ws):
+                    _lib.check(self.lib.ssr_model_upscale_u8(self.handle, xs.data_ptr(), ys.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(),
+                                                             _stream_ptr(img.device)))
+
+                return self._graphed(("u8", B, 3, H, W, 0), img, (B, H * scale, W * scale, 3), torch.uint8, need, call)
         out = torch.empty((B, H * scale, W * scale, 3), dtype=torch.uint8, device=img.device)
         with torch.cuda.device(self.index):
             need = self.lib.ssr_model_workspace_bytes(self.handle, B, H, W, _lib.PAD_EVAL)

@@ -3,6 +3,8 @@ on the same seeded inputs.  Tolerances: fp32 CUDA-core path ~1e-5 (summation ord
 tf32 / bf16 tensor-core paths are judged relative to the output scale."""
 import math
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -170,3 +172,38 @@ def test_swin_tail_fused(M, with_ln):
                           c(g3) if with_ln else None, c(be3) if with_ln else None, heads, hid)
     _close(y, y_ref, "bf16", "fused swin tail")
     _close(yl, yl_ref, "bf16", "fused swin tail (second output)")
+
+
+def test_device_psnr_and_augmentation_match_reference():
+    """studiosr_b200.data (k_data.cu) against the reference's own outputs (tests/golden/data_ops.npz, made by
+    oracle/make_golden_data.py) and the oracle restatement: compute_psnr incl. y_only / crop_border / unequal sizes, and the
+    batched crop + flip + rot90 + array2tensor kernel with the reference's seeded draws."""
+    import random
+
+    from tests.conftest import load_golden
+    from studiosr_b200.data import PairedAugment, compute_psnr
+
+    g = load_golden("data_ops")
+    gt, sr, big = g["psnr_gt"], g["psnr_sr"], g["psnr_big"]
+    vals = []
+    for a, b in ((sr, gt), (big, gt)):
+        a_d, b_d = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        for y_only in (False, True):
+            for cb in (0, 4):
+                vals.append(compute_psnr(a_d, b_d, y_only=y_only, crop_border=cb))
+    assert np.allclose(vals, g["psnr_values"], rtol=0, atol=1e-4), (vals, g["psnr_values"])
+    assert compute_psnr(gt, gt) == float("inf")
+    lq, hr = g["aug_lq"], g["aug_gt"]
+    lq_d, hr_d = torch.from_numpy(lq).cuda(), torch.from_numpy(hr).cuda()
+    seeds = [int(s) for s in g["aug_seeds"]]
+    aug = PairedAugment(size=12, scale=4)
+    params = [PairedAugment(size=12, scale=4, rng=random.Random(s)).draw(lq.shape[0], lq.shape[1]) for s in seeds]
+    assert len({p[2] for p in params}) > 3  # the seeds cover several flip / rotation combinations
+    x, y = aug([lq_d] * len(seeds), [hr_d] * len(seeds), params=params)
+    assert torch.equal(x.cpu(), torch.from_numpy(g["aug_x"])) and torch.equal(y.cpu(), torch.from_numpy(g["aug_y"]))
+    # every flag combination against the oracle, on a non-square source
+    combos = [(3, 5, f) for f in range(8)]
+    x, y = aug([lq_d] * 8, [hr_d] * 8, params=combos)
+    for i, (xs, ys, f) in enumerate(combos):
+        xo, yo = O.augment_pair(lq, hr, 12, 4, xs, ys, f)
+        assert np.array_equal(x[i].cpu().numpy(), xo) and np.array_equal(y[i].cpu().numpy(), yo), f

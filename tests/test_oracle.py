@@ -179,3 +179,30 @@ def test_oracle_backward_matches_reference_gradients(name):
         assert (g[::c["stride"]] - ref).norm().item() <= 2e-4 * ref.norm().item() + 1e-9, k
         checked += 1
     assert checked == c["n_params"]
+
+
+def test_oracle_psnr_and_augmentation_match_reference_goldens():
+    """oracle.compute_psnr / augment_pair against values and patches produced by the unmodified reference
+    (oracle/make_golden_data.py): utils/metrics.py:11-49, data/transforms.py:8-68 with dataset.py:50-58's transform order."""
+    import random
+
+    import numpy as np
+
+    g = load_golden("data_ops")
+    gt, sr, big = g["psnr_gt"], g["psnr_sr"], g["psnr_big"]
+    vals = []
+    for a, b in ((sr, gt), (big, gt)):
+        for y_only in (False, True):
+            for cb in (0, 4):
+                vals.append(O.compute_psnr(a, b, y_only=y_only, crop_border=cb))
+    assert np.allclose(vals, g["psnr_values"], rtol=0, atol=1e-5)
+    assert O.compute_psnr(gt, gt) == float("inf") and np.isinf(g["psnr_identical"][0])
+    # the host-side draw sequence of studiosr_b200.data.PairedAugment is the reference's: seeded runs cut the same patches
+    from studiosr_b200.data import PairedAugment
+
+    lq, hr = g["aug_lq"], g["aug_gt"]
+    for i, seed in enumerate(g["aug_seeds"]):
+        rng = random.Random(int(seed))
+        xs, ys, flags = PairedAugment(size=12, scale=4, rng=rng, device="cpu").draw(lq.shape[0], lq.shape[1])
+        x, y = O.augment_pair(lq, hr, 12, 4, xs, ys, flags)
+        assert np.array_equal(x, g["aug_x"][i]) and np.array_equal(y, g["aug_y"][i]), seed
