@@ -547,6 +547,186 @@ int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s) {
 }
 
 // =============================================================================================
+// First conv + patch-embed LayerNorm + first block's norm1 in ONE pass (SwinIR, swinir.py:358-361,344-346,151):
+//   x0 = conv_first(pad(normalise(x)))  ->  g = LN(x0; patch_embed.norm)  ->  xn = LN(g; layers.0.blocks.0.norm1)
+// The three outputs are the whole cost (12 B + sizeof(T) per channel and pixel written, 3 bytes read): an HBM stream.  The
+// two-kernel version wrote x0, read it back and ran its conv with one thread per channel (15 % / 57 % of the HBM roofline).
+// A warp owns 8 pixels at a time; lane l holds channels (2l, 2l+1) + 64 i of every pixel, so weights are LDS.64 from a
+// [tap][channel] table, the input patch is a broadcast LDS and every store is a full 128- / 256-byte line per warp.
+// =============================================================================================
+constexpr int CFL_WARPS = 8, CFL_PX = 8;  // 64 pixels per CTA pass
+
+template <int NG>  // channel groups of 64: CP = 64 * NG
+__global__ void __launch_bounds__(32 * CFL_WARPS) conv_first_ln_kernel(const ConvFirstArgs a, int n_groups_px) {
+  extern __shared__ __align__(16) float cfl_smem[];
+  float* s_w = cfl_smem;                       // [27][64 NG]
+  float* s_bias = s_w + 27 * 64 * NG;          // [64 NG]
+  float* s_g1 = s_bias + 64 * NG;
+  float* s_b1 = s_g1 + 64 * NG;
+  float* s_g2 = s_b1 + 64 * NG;
+  float* s_b2 = s_g2 + 64 * NG;
+  float* s_patch = s_b2 + 64 * NG;             // [CFL_WARPS][CFL_PX][28]
+  constexpr int CP = 64 * NG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < 27 * CP; e += blockDim.x) {
+    const int k = e / CP, c = e - k * CP;
+    s_w[e] = c < a.Cout ? __ldg(a.Wc + c * 27 + k) : 0.0f;
+  }
+  for (int c = tid; c < CP; c += blockDim.x) {
+    s_bias[c] = c < a.Cout ? __ldg(a.bias + c) : 0.0f;
+    s_g1[c] = __ldg(a.g1 + c);
+    s_b1[c] = __ldg(a.b1 + c);
+    s_g2[c] = a.g2 ? __ldg(a.g2 + c) : 0.0f;
+    s_b2[c] = a.g2 ? __ldg(a.b2 + c) : 0.0f;
+  }
+  __syncthreads();
+  const int M = a.B * a.Hp * a.Wp;
+  const float invC = 1.0f / (float)a.Cout;
+  float* patch = s_patch + warp * (CFL_PX * 28);
+  for (int grp = blockIdx.x * CFL_WARPS + warp; grp < n_groups_px; grp += gridDim.x * CFL_WARPS) {
+    const int m0 = grp * CFL_PX;
+    // ---- the 8 pixels' 3x3x3 input patches (pad + normalise + tile addressing as conv_first_kernel) ----
+    __syncwarp();
+    for (int e = lane; e < CFL_PX * 27; e += 32) {
+      const int p = e / 27, k = e - p * 27;
+      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+      const int m = m0 + p;
+      float v = 0.0f;
+      if (m < M) {
+        const int x = m % a.Wp, y = (m / a.Wp) % a.Hp, b = m / (a.Wp * a.Hp);
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        if (yy >= 0 && yy < a.Hp && xx >= 0 && xx < a.Wp) {
+          int sy = mirror_index(yy, a.h, a.pad_mode), sx = mirror_index(xx, a.w, a.pad_mode);
+          int img = b;
+          if (a.tile_mode) {
+            const int t = a.tile_begin + b;
+            const int ty = t / a.tiles_x, tx = t % a.tiles_x;
+            int y0 = ty * a.stride, x0 = tx * a.stride;
+            if (y0 > a.fh - a.h) y0 = a.fh - a.h;
+            if (x0 > a.fw - a.w) x0 = a.fw - a.w;
+            sy += y0;
+            sx += x0;
+            img = 0;
+          }
+          float raw;
+          if (a.in_u8)
+            raw = (float)reinterpret_cast<const uint8_t*>(a.in)[((size_t)(img * a.fh + sy) * a.fw + sx) * 3 + ci];
+          else
+            raw = reinterpret_cast<const float*>(a.in)[((size_t)(img * 3 + ci) * a.fh + sy) * a.fw + sx];
+          v = raw * a.in_scale + a.in_shift[ci];
+        }
+      }
+      patch[p * 28 + k] = v;
+    }
+    __syncwarp();
+    // ---- conv: acc[p][g] = (channels 64 g + 2 lane, + 1) of pixel p ----
+    float2 acc[CFL_PX][NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float2 bv = *reinterpret_cast<const float2*>(s_bias + 64 * g + 2 * lane);
+#pragma unroll
+      for (int p = 0; p < CFL_PX; ++p) acc[p][g] = bv;
+    }
+#pragma unroll 3
+    for (int k = 0; k < 27; ++k) {
+      float2 w[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) w[g] = *reinterpret_cast<const float2*>(s_w + k * CP + 64 * g + 2 * lane);
+#pragma unroll
+      for (int p = 0; p < CFL_PX; ++p) {
+        const float xv = patch[p * 28 + k];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          acc[p][g].x = fmaf(xv, w[g].x, acc[p][g].x);
+          acc[p][g].y = fmaf(xv, w[g].y, acc[p][g].y);
+        }
+      }
+    }
+    // ---- per pixel: store x0, LN -> g, LN -> xn ----
+#pragma unroll
+    for (int p = 0; p < CFL_PX; ++p) {
+      const int m = m0 + p;
+      if (m >= M) break;  // warp-uniform
+      if (a.out_f32) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) *reinterpret_cast<float2*>(a.out_f32 + (size_t)m * a.ld_f32 + 64 * g + 2 * lane) = acc[p][g];
+      }
+      float2 v[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) v[g] = acc[p][g];
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {  // pass 0: patch_embed.norm (g1, b1); pass 1: norm1 of the first block (g2, b2)
+        if (pass == 1 && !a.g2) break;
+        float sum = 0.0f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) sum += v[g].x + v[g].y;  // padded channels are exact zeros
+        const float mean = warp_sum(sum) * invC;
+        float sq = 0.0f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int c = 64 * g + 2 * lane;
+          const float dx = c < a.Cout ? v[g].x - mean : 0.0f, dy = c + 1 < a.Cout ? v[g].y - mean : 0.0f;
+          sq += dx * dx + dy * dy;
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * invC + a.eps);
+        const float* gam = pass == 0 ? s_g1 : s_g2;
+        const float* bet = pass == 0 ? s_b1 : s_b2;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int c = 64 * g + 2 * lane;
+          const float2 gv = *reinterpret_cast<const float2*>(gam + c), bv = *reinterpret_cast<const float2*>(bet + c);
+          v[g].x = c < a.Cout ? (v[g].x - mean) * rstd * gv.x + bv.x : 0.0f;
+          v[g].y = c + 1 < a.Cout ? (v[g].y - mean) * rstd * gv.y + bv.y : 0.0f;
+        }
+        if (pass == 0 && a.out_g) {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) *reinterpret_cast<float2*>(a.out_g + (size_t)m * a.ld_g + 64 * g + 2 * lane) = v[g];
+        }
+      }
+      if (a.out_T) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const size_t idx = (size_t)m * a.ld_T + 64 * g + 2 * lane;
+          if (a.elem == 2) {
+            reinterpret_cast<uint32_t*>(a.out_T)[idx >> 1] = pack_bf16x2(v[g].x, v[g].y);
+          } else {
+            float2 o = v[g];
+            if (a.round_tf32) {
+              o.x = round_tf32(o.x);
+              o.y = round_tf32(o.y);
+            }
+            *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.out_T) + idx) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+int launch_conv_first_ln(const ConvFirstArgs& a, int CP, cudaStream_t s) {
+  SSR_CHECK(CP % 64 == 0 && CP >= 64 && CP <= 192 && a.Cout <= CP, SSR_E_INVALID, "conv_first_ln: padded channels %d not in {64, 128, 192}", CP);
+  SSR_CHECK(a.g1 && a.b1, SSR_E_INVALID, "conv_first_ln: missing LayerNorm parameters");
+  const int M = a.B * a.Hp * a.Wp;
+  const int n_groups = (M + CFL_PX - 1) / CFL_PX;
+  const size_t smem = (size_t)(27 * CP + 5 * CP + CFL_WARPS * CFL_PX * 28) * sizeof(float);
+  int blocks = (n_groups + CFL_WARPS - 1) / CFL_WARPS;
+  const int cap = 148 * 4;  // B200: 148 SMs (sm_100a only)
+  if (blocks > cap) blocks = cap;
+  ProfScope prof("conv_first_ln", 2.0 * M * 27 * a.Cout,
+                 (double)M * (3 * (a.in_u8 ? 1 : 4) + a.Cout * ((a.out_f32 ? 4 : 0) + (a.out_g ? 4 : 0) + (a.out_T ? a.elem : 0))), s);
+  const int ng = CP / 64;
+  if (ng == 1)
+    conv_first_ln_kernel<1><<<blocks, 32 * CFL_WARPS, smem, s>>>(a, n_groups);
+  else if (ng == 2)
+    conv_first_ln_kernel<2><<<blocks, 32 * CFL_WARPS, smem, s>>>(a, n_groups);
+  else
+    conv_first_ln_kernel<3><<<blocks, 32 * CFL_WARPS, smem, s>>>(a, n_groups);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// =============================================================================================
 // Last conv: Cin -> 3 with fused bias / affine / crop / (fp32 NCHW | uint8 HWC) store.
 // One thread per output pixel; weights staged in shared memory as [tap][ci][4].
 // =============================================================================================

@@ -198,6 +198,16 @@ static int pack_conv_last(ssr_model* m, const std::string& name, int Cin, size_t
     for (int c = 0; c < Cin; ++c)
       for (int co = 0; co < 3; ++co) dst[((size_t)tap * Cin + c) * 4 + co] = (*W)[((size_t)co * Cin + c) * 9 + tap];
   for (int i = 0; i < 3; ++i) bias3[i] = (*B)[i];
+  m->last_w27 = 0;
+  if (Cin == 64 && m->cfg.precision == SSR_PREC_BF16) {  // taps-in-N operand of k_conv_last.cu
+    m->last_w27 = arena_alloc(m, 32 * 64 * 2);
+    for (int n = 0; n < 32; ++n)
+      for (int c = 0; c < 64; ++c) {
+        const float v = n < 27 ? (*W)[((size_t)(n % 3) * Cin + c) * 9 + n / 3] : 0.0f;
+        const __nv_bfloat16 h = __float2bfloat16(v);
+        memcpy(m->host_arena.data() + m->last_w27 + ((size_t)n * 64 + c) * 2, &h, 2);
+      }
+  }
   return SSR_OK;
 }
 
@@ -717,6 +727,11 @@ static int run_tail(ssr_model* m, const void* cur, int ch_ld, int B, int Hp, int
     H *= L.ps_r;
     W *= L.ps_r;
   }
+  if (m->last_w27 && ch_ld >= 64) {  // bf16, 64 input channels: one K = 64 GEMM with the nine taps in N + a shared-memory gather
+    return launch_conv_last_tapn(cur, ch_ld, m->arena + m->last_w27, m->conv_last_bias, out_shift, out_scale,
+                                 m->cfg.img_range == 1.0f ? 255.0f : 1.0f, B, H, W, h * m->cfg.scale, w * m->cfg.scale, out.out_f32,
+                                 out.out_u8, s);
+  }
   if (m->cfg.precision != SSR_PREC_FP32) {  // tensor-core implicit GEMM (N padded 3 -> 64) with the reconstruction epilogue
     GemmArgs g = gemm_base(m, m->last_lin, cur, ch_ld, B, H, W);
     g.out3_f32 = out.out_f32;
@@ -829,9 +844,24 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
     a.out_f32 = W.x0;
     a.ld_f32 = CP;
     a.elem = e;
-    SSR_TRY(launch_conv_first(a, s));
+    if (CP <= 192) {  // + patch_embed.norm -> g (residual stream) and layers.0.blocks.0.norm1 -> xn in the same pass
+      const Block& b0 = m->layers[0].blocks[0];
+      a.g1 = m->dev<float>(m->pe_norm.g_off);
+      a.b1 = m->dev<float>(m->pe_norm.b_off);
+      a.g2 = m->dev<float>(b0.norm1.g_off);
+      a.b2 = m->dev<float>(b0.norm1.b_off);
+      a.out_g = W.g;
+      a.ld_g = CP;
+      a.out_T = W.xn;
+      a.ld_T = CP;
+      a.round_tf32 = rtf;
+      a.eps = 1e-5f;
+      SSR_TRY(launch_conv_first_ln(a, CP, s));
+    } else {
+      SSR_TRY(launch_conv_first(a, s));
+    }
   }
-  {  // patch_embed.norm -> g (residual stream), chained with layers.0.blocks.0.norm1 -> xn
+  if (CP > 192) {  // patch_embed.norm -> g (residual stream), chained with layers.0.blocks.0.norm1 -> xn
     LnArgs a;
     memset(&a, 0, sizeof(a));
     a.in = W.x0;
@@ -1571,6 +1601,9 @@ int ssr_model_finalize(ssr_model_t* m) {
     scan("btab", b0.btab_off, kAttnBiasBytes / 2);
   }
   SSR_CUDA(cudaMemcpy(m->arena, m->host_arena.data(), m->host_arena.size(), cudaMemcpyHostToDevice));
+  // a pageable-memory cudaMemcpy may return before its DMA has landed and only the legacy stream is ordered behind it: callers
+  // launch on non-blocking streams (CUDA-graph capture streams, torch side streams)
+  SSR_CUDA(cudaDeviceSynchronize());
   m->host_arena.clear();
   m->host_arena.shrink_to_fit();
   m->finalized = true;

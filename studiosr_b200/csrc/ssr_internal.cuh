@@ -161,7 +161,16 @@ struct ConvFirstArgs {
   int ld_T;
   int elem;
   int round_tf32;
+  // fused patch-embed LayerNorm chain (launch_conv_first_ln, SwinIR): g = LN(conv; g1, b1) -> out_g (fp32), LN(g; g2, b2) -> out_T
+  const float *g1, *b1, *g2, *b2;  // padded fp32 vectors [CP]
+  float* out_g;
+  int ld_g;
+  float eps;
 };
+int launch_conv_first_ln(const ConvFirstArgs& a, int CP, cudaStream_t s);
+// reconstruction conv 64 -> 3 with the taps in N (k_conv_last.cu); x bf16 NHWC, w27 bf16 [32][64] (row = tap * 3 + c)
+int launch_conv_last_tapn(const void* x, int ld, const void* w27, const float* bias3, const float* out_shift, float out_scale, float u8_scale,
+                          int B, int H, int W, int crop_h, int crop_w, float* out_f32, uint8_t* out_u8, cudaStream_t s);
 
 // last conv (Cin -> 3) fused with bias, output affine (un-normalise / MeanShift), crop and either
 // fp32 NCHW store or uint8 HWC quantisation (round-half-even, clip).

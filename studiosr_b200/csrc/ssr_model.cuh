@@ -60,6 +60,7 @@ struct ssr_model {
   float conv_last_bias[3] = {0, 0, 0};
   int last_cin = 64;
   Lin last_lin;  // the same conv packed for the tensor-core implicit GEMM (bf16 / tf32 models)
+  size_t last_w27 = 0;  // bf16 models with 64 input channels: [32][64] bf16, row = tap * 3 + c (k_conv_last.cu); 0 = not packed
   // EDSR
   int F = 0, FP = 0;
   std::vector<Lin> res_a, res_b;
