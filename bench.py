@@ -183,6 +183,30 @@ def cpu_port_tiles_per_s(n_sample, threads=None):
     return done / dt, torch.get_num_threads(), done
 
 
+def torch_eager_b200_tiles_per_s(batch=20, reps=3):
+    """Context line (not a target, not the product path): the oracle port -- plain PyTorch ops, i.e. cuBLAS / cuDNN / ATen eager
+    kernels -- on THIS B200 under stock bf16 autocast, `batch` tiles per forward.  Places the hand-written path against what the
+    reference's own code would reach on the same box ("same-box bar")."""
+    import torch
+
+    from oracle import sr_oracle as O
+    from oracle import synth
+
+    cfg = synth.swinir_config()
+    P = {k: v.cuda() for k, v in synth.swinir_weights(cfg, 0).items()}
+    x = synth.image_batch((batch, 3, TILE, TILE), 1234).cuda()
+    with torch.device("cuda"), torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        O.swinir_forward(P, x, cfg)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            O.swinir_forward(P, x, cfg)
+        e1.record()
+        torch.cuda.synchronize()
+    return batch * reps / (e0.elapsed_time(e1) / 1e3)
+
+
 def run_reference(args):
     """CPU arm: the reference's algorithm (oracle port; the reference itself is PyTorch-on-CPU and is
     not present on the GPU box) on all host threads.  Each step = `sample` tiles of the 220-tile frame;
@@ -378,6 +402,12 @@ def run_ours(args):
         cpu_baseline = {"value": OUT_MPIX / (nt / tps), "unit": "Mpix/s", "cores": cores, "kind": "port",
                         "sample": f"{done} of {nt} 64x64 tiles through the oracle port (fp32, eval forward incl. "
                                   f"64->72 pad); value = frame Mpix / ({nt} x s/tile)"}
+        try:  # same-box context: the same port as stock torch eager (cuBLAS / cuDNN) on this GPU under bf16 autocast
+            eager_tps = torch_eager_b200_tiles_per_s()
+            cpu_baseline["torch_eager_b200"] = {"value": OUT_MPIX / (nt / eager_tps), "unit": "Mpix/s", "dtype": "bf16 autocast",
+                                                "sample": "3 x 20 tiles per forward through the oracle port on cuda:0 (context only)"}
+        except Exception as exc:  # never let the context line break the bench
+            cpu_baseline["torch_eager_b200"] = {"unavailable": repr(exc)[:200]}
 
     if rank == 0:
         step_flops = nt * PAD_TILE * PAD_TILE * FLOP_PER_PADDED_PX
@@ -623,7 +653,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--chunk", type=int, default=0, help="tiles per network pass (0 = all 220 at once)")
     ap.add_argument("--cpu-tiles", type=int, default=64, help="tiles timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")

@@ -46,7 +46,10 @@ enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1, SSR_ARCH_RCAN = 2, SSR_ARCH_HAT =
 enum {
   SSR_PREC_FP32 = 0, /* CUDA-core fp32 FMA (bit-faithful to the reference's fp32 semantics up to summation order) */
   SSR_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 activations, fp32 accumulate */
-  SSR_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate, fp32 residual stream / LN / softmax */
+  SSR_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate, fp32 residual stream / LN / softmax */
+  SSR_PREC_TF32X3 = 3 /* tcgen05 kind::tf32, every operand split into a tf32 head + tail and three MMAs per k-step (a_hi w_hi +
+                         a_lo w_hi + a_hi w_lo): fp32-level accuracy (~1e-6) on the tensor cores; fp32 activations, fp32
+                         attention / LN / softmax.  Model entry points only (the ssr_op_* calls take 0..2). */
 };
 
 /* padding applied before the network, i.e. which reference branch of SwinIR.forward is mirrored */

@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssr_b200.so")
 
 SSR_ARCH_SWINIR, SSR_ARCH_EDSR, SSR_ARCH_RCAN, SSR_ARCH_HAT = 0, 1, 2, 3
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_TF32X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "tf32x3": PREC_TF32X3}
 PAD_EVAL, PAD_TRAIN = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU = 0, 1, 2, 3
 SSR_MAX_LAYERS = 16

@@ -60,15 +60,28 @@ constexpr size_t tc_smem_bytes() {
 }
 
 
-template <typename T, int BLOCK_N, bool kHalo>
-__global__ void __launch_bounds__(TC_THREADS + (kHalo ? 32 : 0), 1)
+// 3xTF32 ("tf32x3" precision, fp32 activations and weights): every operand is split into a tf32 head and a tf32 tail,
+//   a = a_hi + a_lo (+ O(2^-22 a)),  w = w_hi + w_lo;   D += a_hi w_hi + a_lo w_hi + a_hi w_lo    (three tcgen05.mma per k-step)
+// which carries the fp32 claim of the north star (max-abs <= 1e-3; measured ~1e-6) on the tensor cores -- a single tf32 pass sits
+// AT that tolerance (1.05e-3).  The weight tails are packed next to the heads (rows [NP, 2 NP) of the packed matrix); the
+// activation tile is split in shared memory by four extra warps between TMA arrival and the MMAs (in place: head; second tile:
+// tail), so the activations stay un-rounded fp32 in HBM and no producer kernel has to know about the mode.
+template <int BLOCK_N>
+constexpr size_t tc_smem_bytes_split() {
+  return (size_t)2 * (2 * 16384 + 2 * BLOCK_N * 128) + TC_EPI_WARPS * TC_STAGE_BYTES + TC_MAX_NP * 4 + 2 * 256 * 4 + 256 + 1024;
+}
+
+template <typename T, int BLOCK_N, bool kHalo, bool kSplit = false>
+__global__ void __launch_bounds__(TC_THREADS + (kHalo ? 32 : 0) + (kSplit ? 128 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const GemmArgs g, const TcGeom geo) {
   constexpr bool kTf32 = sizeof(T) == 4;
   constexpr int BK = 128 / (int)sizeof(T);  // elements per 128-byte swizzle row
-  constexpr int kStages = tc_stages<BLOCK_N>();
+  static_assert(!kSplit || (sizeof(T) == 4 && !kHalo), "the 3xTF32 split exists for fp32 operands only");
+  constexpr int kStages = kSplit ? 2 : tc_stages<BLOCK_N>();
   constexpr int kTmemCols = 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128 : 2 * BLOCK_N <= 256 ? 256 : 512;
-  constexpr uint32_t A_BYTES = TC_BM * 128, W_BYTES = BLOCK_N * 128;
+  constexpr uint32_t A_BYTES = TC_BM * 128 * (kSplit ? 2 : 1), W_BYTES = BLOCK_N * 128 * (kSplit ? 2 : 1);  // split: head | tail
+  constexpr uint32_t A_HALF = TC_BM * 128, W_HALF = BLOCK_N * 128;
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2 : 1, TC_BM, BLOCK_N);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -117,7 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tempty_bar(b), 4);  // one arrival per epilogue warp of the group
     }
     for (int b = 0; b < 4; ++b) {
-      mbar_init(afull_bar(b), 1);
+      mbar_init(afull_bar(b), kSplit ? 4 : 1);  // split mode: "stage b has been split" (one arrival per splitter warp)
       mbar_init(aempty_bar(b), 1);
     }
     fence_barrier_init();
@@ -162,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(full_bar(s), W_BYTES);
             tma_load_2d(dstW, &tmW, full_bar(s), (tap * geo.kc_per_tap + cb) * BK, n0);
           } else {
-            mbar_expect_tx(full_bar(s), A_BYTES + W_BYTES);
+            mbar_expect_tx(full_bar(s), A_HALF + W_BYTES);
             const int tap = kb / geo.kc_per_tap, kc = kb - tap * geo.kc_per_tap;
             if (geo.conv) {
               const int dy = (g.taps == 9) ? tap / 3 - 1 : 0, dx = (g.taps == 9) ? tap % 3 - 1 : 0;
@@ -171,8 +184,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d(dstA, &tmA, full_bar(s), kc * BK, m0);
             }
             tma_load_2d(dstW, &tmW, full_bar(s), kb * BK, n0);
+            if constexpr (kSplit) tma_load_2d(dstW + W_HALF, &tmW, full_bar(s), kb * BK, g.NP + n0);  // the tf32 tails of the weights
           }
         }
+      }
+    }
+  } else if (kSplit && warp >= 3 + TC_EPI_WARPS) {
+    // =========================== activation splitter (3xTF32 only): a -> (tf32 head in place, tf32 tail) ===========================
+    const int t = threadIdx.x - 32 * (3 + TC_EPI_WARPS);  // 0..127 = tile row
+    uint32_t kbg = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int kb = 0; kb < geo.nkb; ++kb, ++kbg) {
+        const int s = kbg % kStages;
+        mbar_wait_warp(full_bar(s), (kbg / kStages) & 1u, lane);
+        uint8_t* hi = smA + s * A_BYTES + t * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = (j ^ (t & 7)) * 16;  // rows are 128 bytes apart: rotate the chunk order so a quarter-warp hits 8 bank groups
+          float4 v = *reinterpret_cast<float4*>(hi + c);
+          float4 h4 = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+          float4 l4 = make_float4(round_tf32(v.x - h4.x), round_tf32(v.y - h4.y), round_tf32(v.z - h4.z), round_tf32(v.w - h4.w));
+          *reinterpret_cast<float4*>(hi + c) = h4;
+          *reinterpret_cast<float4*>(hi + A_HALF + c) = l4;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(afull_bar(s));
       }
     }
   } else if (kHalo && warp == 3 + TC_EPI_WARPS) {
@@ -220,11 +257,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             adesc = umma_desc_sw128(smem_u32(smA + s * A_BYTES));
           }
           TC_ROLE_WAIT(full_bar(s), ph);
+          if constexpr (kSplit) TC_ROLE_WAIT(afull_bar(s), ph);  // the splitter warps have written head and tail
           tc_fence_after();
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smW + s * W_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per 128-byte row: +2 in the (addr >> 4) field
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte row: +2 in the (addr >> 4) field
             umma<kTf32>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kSplit) {  // small terms: a_lo w_hi and a_hi w_lo
+              const uint64_t adesc_lo = umma_desc_sw128(smem_u32(smA + s * A_BYTES + A_HALF));
+              const uint64_t bdesc_lo = umma_desc_sw128(smem_u32(smW + s * W_BYTES + W_HALF));
+              umma<kTf32>(tmem_d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+              umma<kTf32>(tmem_d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1u);
+            }
+          }
           umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
           if constexpr (kHalo) {
             if (kb % 9 == 8) umma_commit(aempty_bar((ag0 + (uint32_t)(kb / 9)) % kHaloSlots));  // the halo tile has served its nine taps
@@ -281,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (sizeof(T) == 2) {
           stage_store_bf16(st, lane, v, [&](int i) { return dstT(base, ld, rm.mh[i], nb); });
         } else {
-          stage_store_tf32(st, lane, v, [&](int i) { return dstT(base, ld, rm.mf[i], nb); });
+          stage_store_tf32(st, lane, v, [&](int i) { return dstT(base, ld, rm.mf[i], nb); }, !kSplit);
         }
       };
 
@@ -519,7 +564,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (sizeof(T) == 2) {
             stage_store_bf16(st, lane, v, [&](int i) { return rm.mh[i] >= 0 ? oln + (size_t)rm.mh[i] * g.ld_ln + c * 32 : nullptr; });
           } else {
-            stage_store_tf32(st, lane, v, [&](int i) { return rm.mf[i] >= 0 ? oln + (size_t)rm.mf[i] * g.ld_ln + c * 32 : nullptr; });
+            stage_store_tf32(st, lane, v, [&](int i) { return rm.mf[i] >= 0 ? oln + (size_t)rm.mf[i] * g.ld_ln + c * 32 : nullptr; }, !kSplit);
           }
         }
       }
@@ -606,7 +651,7 @@ static void choose_patch(int B, int H, int W, int* bw, int* bh, int* bb) {
     }
 }
 
-template <typename T, int BLOCK_N>
+template <typename T, int BLOCK_N, bool kSplit = false>
 static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   constexpr int elem = (int)sizeof(T);
   constexpr int BK = 128 / elem;
@@ -662,7 +707,7 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
   }
   {
     const cuuint64_t Ktot = (cuuint64_t)g.taps * g.KP;
-    cuuint64_t dims[2] = {Ktot, (cuuint64_t)g.NP};
+    cuuint64_t dims[2] = {Ktot, (cuuint64_t)g.NP * (kSplit ? 2 : 1)};  // split: rows [NP, 2 NP) hold the tf32 tails
     cuuint64_t str[1] = {Ktot * elem};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BLOCK_N};
     SSR_TRY(make_tmap(&tmW, g.Wt, elem, 2, dims, str, box));
@@ -699,10 +744,11 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     SSR_TRY(make_tmap(&tmO, g.out_T, 2, 5, dims, str, box, 64));
     ga.tma_store = 2;
   }
-  constexpr size_t smem = tc_smem_bytes<BLOCK_N>();
+  constexpr size_t smem = kSplit ? tc_smem_bytes_split<BLOCK_N>() : tc_smem_bytes<BLOCK_N>();
+  static_assert(smem <= 232448, "gemm_tc: shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    SSR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BLOCK_N, false, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if constexpr (elem == 2)
       SSR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<T, BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -720,7 +766,7 @@ static int launch_tc_bn(const GemmArgs& g, cudaStream_t s) {
     else
       gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, tmO, tmP, ga, geo);
   } else {
-    gemm_tc_kernel<T, BLOCK_N, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, tmO, tmP, ga, geo);
+    gemm_tc_kernel<T, BLOCK_N, false, kSplit><<<grid, TC_THREADS + (kSplit ? 128 : 0), smem, s>>>(tmA, tmW, tmO, tmP, ga, geo);
   }
   count_launch();
   SSR_CUDA(cudaGetLastError());
@@ -750,8 +796,29 @@ static int launch_tc_t(const GemmArgs& g, cudaStream_t s) {
   return launch_tc_bn<T, 64>(g, s);
 }
 
+// 3xTF32: tiles of at most 192 columns (two stages of head + tail operands must fit the shared memory)
+static int launch_tc_split(const GemmArgs& g, cudaStream_t s) {
+  SSR_CHECK(g.NP % 64 == 0, SSR_E_INVALID, "gemm_tc: NP=%d must be a multiple of 64", g.NP);
+  if (g.ps_r > 1) {
+    const int Cps = g.N / (g.ps_r * g.ps_r);
+    SSR_CHECK(Cps % 32 == 0 && g.N == g.NP, SSR_E_INVALID, "gemm_tc: pixel-shuffle store needs N/r^2 %% 32 == 0 (N=%d r=%d)", g.N, g.ps_r);
+  }
+  if (g.out_ln) {
+    SSR_CHECK(g.NP <= 192, SSR_E_INVALID, "gemm_tc (tf32x3): fused LayerNorm needs NP<=192 (NP=%d)", g.NP);
+    switch (g.NP) {
+      case 64: return launch_tc_bn<float, 64, true>(g, s);
+      case 128: return launch_tc_bn<float, 128, true>(g, s);
+      case 192: return launch_tc_bn<float, 192, true>(g, s);
+    }
+  }
+  if (g.NP % 192 == 0) return launch_tc_bn<float, 192, true>(g, s);
+  if (g.NP % 128 == 0) return launch_tc_bn<float, 128, true>(g, s);
+  return launch_tc_bn<float, 64, true>(g, s);
+}
+
 int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s) {
   if (elem == 2) return launch_tc_t<__nv_bfloat16>(g, s);
+  if (g.split_tf32) return launch_tc_split(g, s);
   return launch_tc_t<float>(g, s);
 }
 

@@ -183,7 +183,8 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t s) {
 }
 
 // =============================================================================================
-// fp32 (shifted-)window attention: one CTA per window, loops heads and 64-query row blocks.
+// fp32 (shifted-)window attention: one CTA per (window, head) -- at batch 1 a grid of windows alone leaves half the SMs idle
+// and serialises the heads -- looping over 64-query row blocks.
 // =============================================================================================
 __global__ void __launch_bounds__(256) attn_simt_kernel(const AttnArgs a) {
   extern __shared__ float smem[];
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(const AttnArgs a) {
   }
   __syncthreads();
 
-  for (int h = 0; h < a.heads; ++h) {
+  {
+    const int h = blockIdx.y;
     for (int e = tid; e < N * a.DP; e += blockDim.x) {
       const int t = e / a.DP, j = e % a.DP;
       const size_t row = (size_t)pix[t] * a.ld_qkv + h * a.DP + j;
@@ -387,7 +389,7 @@ int launch_attn_simt(const AttnArgs& a, cudaStream_t s) {
   }
   const int nwin = a.B * (a.H / a.ws) * (a.W / a.ws);
   ProfScope prof("attn_fp32", 4.0 * nwin * N * N * a.d * a.heads, 4.0 * nwin * N * a.heads * a.d * 4, s);
-  attn_simt_kernel<<<nwin, 256, smem, s>>>(a);
+  attn_simt_kernel<<<dim3(nwin, a.heads), 256, smem, s>>>(a);
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;

@@ -90,15 +90,22 @@ size_t arena_alloc(ssr_model* m, size_t bytes) {
   return off;
 }
 
-static void store_w(ssr_model* m, size_t off, size_t idx, float v) {
+// element `idx` of a packed weight matrix of `total` elements; the 3xTF32 mode stores the tf32 head there and the tf32 tail
+// `total` elements further on (the second half of a double-size allocation, see w_bytes)
+static void store_w(ssr_model* m, size_t off, size_t idx, float v, size_t total) {
   if (m->elem == 2) {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     memcpy(m->host_arena.data() + off + idx * 2, &h, 2);
+  } else if (m->cfg.precision == SSR_PREC_TF32X3) {
+    const float hi = tf32_round_host(v), lo = tf32_round_host(v - hi);
+    memcpy(m->host_arena.data() + off + idx * 4, &hi, 4);
+    memcpy(m->host_arena.data() + off + (total + idx) * 4, &lo, 4);
   } else {
     if (m->cfg.precision == SSR_PREC_TF32) v = tf32_round_host(v);
     memcpy(m->host_arena.data() + off + idx * 4, &v, 4);
   }
 }
+static size_t w_bytes(const ssr_model* m, size_t elems) { return elems * m->elem * (m->cfg.precision == SSR_PREC_TF32X3 ? 2 : 1); }
 
 static const std::vector<float>* find_param(ssr_model* m, const std::string& name, size_t numel) {
   auto it = m->params.find(name);
@@ -128,7 +135,7 @@ static int pack_linear(ssr_model* m, const std::string& name, int N, int K, int 
   const std::vector<float>* B = find_param(m, name + ".bias", (size_t)N);
   if (!W || !B) return SSR_E_STATE;
   out->K = K; out->KP = KP; out->N = N; out->NP = NP; out->taps = 1; out->ps_r = 0; out->N_alg = N;
-  out->w_off = arena_alloc(m, (size_t)NP * KP * m->elem);
+  out->w_off = arena_alloc(m, w_bytes(m, (size_t)NP * KP));
   out->b_off = arena_alloc(m, (size_t)NP * 4);
   float* bd = reinterpret_cast<float*>(m->host_arena.data() + out->b_off);
   for (int n = 0; n < NP; ++n) {
@@ -139,7 +146,7 @@ static int pack_linear(ssr_model* m, const std::string& name, int N, int K, int 
     bd[n] = (*B)[sn] * sc;
     for (int k = 0; k < KP; ++k) {
       const int sk = col_src(k);
-      if (sk >= 0) store_w(m, out->w_off, (size_t)n * KP + k, (*W)[(size_t)sn * K + sk] * sc);
+      if (sk >= 0) store_w(m, out->w_off, (size_t)n * KP + k, (*W)[(size_t)sn * K + sk] * sc, (size_t)NP * KP);
     }
   }
   return SSR_OK;
@@ -153,7 +160,7 @@ static int pack_conv(ssr_model* m, const std::string& name, int Cout, int Cin, i
   if (!W || !B) return SSR_E_STATE;
   const int NP = round_up(Cout, 64), KP = round_up(Cin, 64);
   out->K = Cin; out->KP = KP; out->N = Cout; out->NP = NP; out->taps = 9; out->ps_r = ps_r; out->N_alg = Cout;
-  out->w_off = arena_alloc(m, (size_t)NP * 9 * KP * m->elem);
+  out->w_off = arena_alloc(m, w_bytes(m, (size_t)NP * 9 * KP));
   out->b_off = arena_alloc(m, (size_t)NP * 4);
   const int rr = ps_r > 1 ? ps_r * ps_r : 1, Cps = Cout / rr;
   for (int n = 0; n < Cout; ++n) {
@@ -165,7 +172,7 @@ static int pack_conv(ssr_model* m, const std::string& name, int Cout, int Cin, i
     reinterpret_cast<float*>(m->host_arena.data() + out->b_off)[n] = (*B)[sn];
     for (int tap = 0; tap < 9; ++tap)
       for (int c = 0; c < Cin; ++c)
-        store_w(m, out->w_off, (size_t)n * 9 * KP + (size_t)tap * KP + c, (*W)[((size_t)sn * Cin + c) * 9 + tap]);
+        store_w(m, out->w_off, (size_t)n * 9 * KP + (size_t)tap * KP + c, (*W)[((size_t)sn * Cin + c) * 9 + tap], (size_t)NP * 9 * KP);
   }
   return SSR_OK;
 }
@@ -242,7 +249,7 @@ static int fold_norm_into_linear(ssr_model* m, const std::string& norm, const st
     double acc = (*B)[n];
     for (int k = 0; k < K; ++k) {
       const float w = (*W)[(size_t)n * K + k];
-      store_w(m, out.w_off, (size_t)n * KP + k, w * (*g)[k]);
+      store_w(m, out.w_off, (size_t)n * KP + k, w * (*g)[k], (size_t)out.NP * KP);  // bf16 fused path only
       acc += (double)w * (*be)[k];
     }
     reinterpret_cast<float*>(m->host_arena.data() + out.b_off)[n] = (float)acc;
@@ -676,6 +683,7 @@ static size_t plan_edsr(const ssr_model* m, void* base, int B, int H, int W, Eds
 // launch helpers
 int run_gemm(const ssr_model* m, GemmArgs& g, cudaStream_t s) {
   g.round_tf32 = m->cfg.precision == SSR_PREC_TF32;
+  g.split_tf32 = m->cfg.precision == SSR_PREC_TF32X3;
   if (m->cfg.precision == SSR_PREC_FP32) return launch_gemm_simt(g, s);
   return launch_gemm_tc(g, m->elem, s);
 }
@@ -1549,7 +1557,7 @@ int ssr_device_check(int device) {
 int ssr_model_create(const ssr_model_config* cfg, int device, ssr_model_t** out) {
   SSR_CHECK(cfg && out, SSR_E_INVALID, "null argument");
   SSR_CHECK(cfg->arch >= SSR_ARCH_SWINIR && cfg->arch <= SSR_ARCH_HAT, SSR_E_INVALID, "unknown arch %d", cfg->arch);
-  SSR_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SSR_E_INVALID, "unknown precision %d", cfg->precision);
+  SSR_CHECK(cfg->precision >= 0 && cfg->precision <= 3, SSR_E_INVALID, "unknown precision %d", cfg->precision);
   SSR_CHECK(cfg->scale >= 1 && cfg->scale <= 8, SSR_E_INVALID, "bad scale %d", cfg->scale);
   if (cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_HAT)
     SSR_CHECK(cfg->n_layers > 0 && cfg->n_layers <= SSR_MAX_LAYERS, SSR_E_INVALID, "bad n_layers %d", cfg->n_layers);

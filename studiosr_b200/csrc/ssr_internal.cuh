@@ -82,6 +82,7 @@ struct GemmArgs {
   const float* beta;
   float eps;
   int round_tf32;  // round T=float stores to tf32 (rna) so the next tf32 MMA sees exact operands
+  int split_tf32;  // 3xTF32: Wt holds [2 NP] rows (tf32 heads, then tails); activations are full fp32 and split in the kernel
   // reconstruction-conv mode (tensor-core path only): v[0..2] -> (v + out_shift) * out_scale, cropped to crop_h x crop_w,
   // stored as fp32 NCHW [B,3,crop_h,crop_w] and / or uint8 HWC (round-half-even, clip); all other outputs unused
   float* out3_f32;

@@ -385,9 +385,11 @@ __device__ __forceinline__ void stage_store_bf16(float* stf, int lane, const flo
   __syncwarp();
 }
 template <typename DstF>
-__device__ __forceinline__ void stage_store_tf32(float* st, int lane, float (&v)[32], DstF dst_of) {
+__device__ __forceinline__ void stage_store_tf32(float* st, int lane, float (&v)[32], DstF dst_of, bool round = true) {
+  if (round) {  // single-pass tf32 consumers read exact operands; the 3xTF32 mode keeps full fp32 activations
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+  }
   stage_put_f32(st, lane, v);
   __syncwarp();
   float4 x[8];

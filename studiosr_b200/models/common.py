@@ -11,8 +11,9 @@ import torch.nn as nn
 from .. import _lib
 from ..native import NativeModel
 
-# precision of the fp32 (non-autocast) forward: "fp32" = CUDA-core FMA, "tf32" = tcgen05 kind::tf32
-DEFAULT_FP32_MODE = os.environ.get("STUDIOSR_B200_FP32_MODE", "fp32")
+# precision of the fp32 (non-autocast) forward: "tf32x3" = tcgen05 kind::tf32 with head / tail operand splits (three MMAs per
+# k-step, fp32-level accuracy: 5e-5 max-abs on the cfg1 golden), "fp32" = CUDA-core FMA, "tf32" = single-pass tcgen05 kind::tf32
+DEFAULT_FP32_MODE = os.environ.get("STUDIOSR_B200_FP32_MODE", "tf32x3")
 TRUST_PARAM_VERSIONS = os.environ.get("STUDIOSR_B200_TRUST_PARAM_VERSIONS", "0") == "1"
 
 GRAPH_MAX_LR_PIXELS = int(os.environ.get("STUDIOSR_B200_GRAPH_MAX_LR_PIXELS", str(4 * 96 * 96)))
