@@ -374,7 +374,7 @@ def run_ours(args):
         ach = v["flops"] / (v["ms"] / 1e3) / 1e12
         traffic = None  # DRAM bytes per launch from the committed ncu capture of this kernel (per token x tokens per launch)
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
                 per_tok = json.load(f).get(top, {}).get("dram_bytes_per_token")
             if per_tok:
                 traffic = per_tok * my_tiles * PAD_TILE * PAD_TILE
