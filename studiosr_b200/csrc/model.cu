@@ -1241,8 +1241,11 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
         a.bias = m->dev<float>(blk.bias_off);
         a.B = B; a.H = Hp; a.W = Wp; a.ws = c.window_size; a.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
         a.heads = L.heads; a.d = L.d; a.DP = L.DP; a.elem = e;
-        if (e == 2 && (a.DP == 16 || a.DP == 32) && (a.ws * a.ws) % 64 == 0)
-          SSR_TRY(launch_attn_flash(a, 0, s));  // bf16: mma.sync tiles with an online softmax over key chunks
+        static const bool no_tc = getenv("STUDIOSR_B200_HAT_ATTN_MMA") != nullptr;  // experiments: force the mma.sync kernel
+        if (e == 2 && a.DP == 32 && a.ws == 16 && !no_tc)
+          SSR_TRY(launch_attn_tc(a, 0, s));  // bf16, 16x16 windows: tcgen05 / TMEM two-pass softmax (k_attn_tc.cu)
+        else if (e == 2 && (a.DP == 16 || a.DP == 32) && (a.ws * a.ws) % 64 == 0)
+          SSR_TRY(launch_attn_flash(a, 0, s));  // other bf16 shapes: mma.sync tiles with an online softmax over key chunks
         else
           SSR_TRY(launch_attn_simt(a, s));
         if (!fused) {
@@ -1291,8 +1294,11 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
       a.qkv = W.qkv; a.ld_qkv = 3 * L.QP; a.QP = L.QP; a.o = W.o; a.ld_o = L.QP;
       a.bias = m->dev<float>(blk.bias_off);
       a.B = B; a.H = Hp; a.W = Wp; a.ws = c.window_size; a.kws = wse; a.heads = L.heads; a.d = L.d; a.DP = L.DP; a.elem = e;
-      if (e == 2 && (a.DP == 16 || a.DP == 32) && (a.ws * a.ws) % 64 == 0 && (a.kws * a.kws) % 64 == 0)
-        SSR_TRY(launch_attn_flash(a, 1, s));  // bf16: mma.sync tiles with an online softmax over key chunks
+      static const bool no_tc = getenv("STUDIOSR_B200_HAT_ATTN_MMA") != nullptr;
+      if (e == 2 && a.DP == 32 && a.ws == 16 && a.kws == 24 && !no_tc)
+        SSR_TRY(launch_attn_tc(a, 1, s));  // bf16: tcgen05 / TMEM, the 24x24 key window is one zero-filled TMA box
+      else if (e == 2 && (a.DP == 16 || a.DP == 32) && (a.ws * a.ws) % 64 == 0 && (a.kws * a.kws) % 64 == 0)
+        SSR_TRY(launch_attn_flash(a, 1, s));  // other bf16 shapes: mma.sync tiles with an online softmax over key chunks
       else
         SSR_TRY(launch_attn_oca(a, s));
       if (fused) {

@@ -374,6 +374,8 @@ int launch_attn_simt(const AttnArgs& a, cudaStream_t s);
 int launch_attn_oca(const AttnArgs& a, cudaStream_t s);
 int launch_attn_mma(const AttnArgs& a, cudaStream_t s);
 int launch_attn_flash(const AttnArgs& a, int oca, cudaStream_t s);  // bf16, large windows (HAT): k_attn_flash.cu
+// tcgen05 / TMEM form of the two HAT attention cores (k_attn_tc.cu): 16x16 windows (shift 0 / 8), 24x24 key windows, DP = 32, bf16
+int launch_attn_tc(const AttnArgs& a, int oca, cudaStream_t s);
 int launch_layernorm(const LnArgs& a, cudaStream_t s);
 int launch_conv_first(const ConvFirstArgs& a, cudaStream_t s);
 int launch_conv_last(const ConvLastArgs& a, cudaStream_t s);
