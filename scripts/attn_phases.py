@@ -27,3 +27,8 @@ d = dbg.view(148, 96, 8).cpu().double()[:, 6:90]
 f = lambda a, b: (d[:, :, a] - d[:, :, b]).mean().item()
 print("per head pair (cycles): wait QKV %.0f | QKV epilogue %.0f | previous pair's output %.0f | wait S %.0f | softmax %.0f | pair period %.0f (x3 per 128-token item)"
       % (f(1, 0), f(2, 1), f(3, 2), f(4, 3), f(5, 4), (d[:, 1:, 0] - d[:, :-1, 0]).mean().item()))
+
+for hp in range(3):
+    dd = d[:, hp::3]
+    ff = lambda a, b: (dd[:, :, a] - dd[:, :, b]).mean().item()
+    print("  head pair %d of the item: wait QKV %.0f | QKV epilogue %.0f | output %.0f | wait S %.0f | softmax %.0f" % (hp, ff(1, 0), ff(2, 1), ff(3, 2), ff(4, 3), ff(5, 4)))

@@ -677,8 +677,9 @@ __global__ void __launch_bounds__(32 * CFL_WARPS) conv_first_ln_kernel(const Con
         for (int g = 0; g < NG; ++g) {
           const int c = 64 * g + 2 * lane;
           const float2 gv = *reinterpret_cast<const float2*>(gam + c), bv = *reinterpret_cast<const float2*>(bet + c);
-          v[g].x = c < a.Cout ? (v[g].x - mean) * rstd * gv.x + bv.x : 0.0f;
-          v[g].y = c + 1 < a.Cout ? (v[g].y - mean) * rstd * gv.y + bv.y : 0.0f;
+          // pad channels take the (padded) beta: 0, or the 1.0 that carries the qkv bias of the fused attention kernel
+          v[g].x = c < a.Cout ? (v[g].x - mean) * rstd * gv.x + bv.x : bv.x;
+          v[g].y = c + 1 < a.Cout ? (v[g].y - mean) * rstd * gv.y + bv.y : bv.y;
         }
         if (pass == 0 && a.out_g) {
 #pragma unroll

@@ -28,19 +28,22 @@
 namespace ssr {
 
 constexpr int SA_THREADS = 384;
+constexpr int SA_POLY_DEFAULT = 4;  // every 4th pair of exponentials runs on the FMA pipe (0 = all on MUFU.EX2)
 constexpr uint32_t SA_TILE = 16384;
 constexpr uint32_t SA_WSLOT = 192 * 128;
-constexpr int SA_WSLOTS = 2;
+constexpr int SA_WSLOTS = 3;  // one per k-block of a pair's projection: the next pair's weights are complete before its MMAs start
 constexpr uint32_t SA_OFF_XN = 0;                                  // 3 k-block tiles of the LayerNorm-ed input
 constexpr uint32_t SA_OFF_W = SA_OFF_XN + 3 * SA_TILE;             // weight ring
 constexpr uint32_t SA_OFF_Q = SA_OFF_W + SA_WSLOTS * SA_WSLOT;     // [128][64] bf16 SW128: q of the pair
 constexpr uint32_t SA_OFF_K = SA_OFF_Q + SA_TILE;                  // [128][64] bf16 SW128: k of the pair
 constexpr uint32_t SA_OFF_V = SA_OFF_K + SA_TILE;                  // 2 buffers x 2 heads x [128 tokens][32] bf16 SW64 (MN-major B operand)
-constexpr uint32_t SA_OFF_BIAS = SA_OFF_V + 2 * SA_TILE;           // [6][64][64] bf16 relative-position bias
-constexpr uint32_t SA_BIAS_BYTES = 6 * 64 * 128;
-constexpr uint32_t SA_OFF_OST = SA_OFF_BIAS + SA_BIAS_BYTES;       // [128][64] bf16 SW128 output staging
-constexpr uint32_t SA_OFF_PAR = SA_OFF_OST + SA_TILE;              // fp32 qkv bias [3][192]
-constexpr uint32_t SA_OFF_BAR = SA_OFF_PAR + 3 * 192 * 4;
+constexpr uint32_t SA_OFF_OST = SA_OFF_V + 2 * SA_TILE;            // [128][64] bf16 SW128 output staging
+// relative-position bias, compact: per head 4 copies (one per 8-byte alignment of a window row's start) of the reversed
+// 15 x 15 table, row pitch 20 bf16: the 64 values of a token row are 16 aligned runs of 4 (one per key quad)
+constexpr uint32_t SA_BT_PITCH = 20, SA_BT_COPY = 15 * SA_BT_PITCH * 2, SA_BT_HEAD = 4 * SA_BT_COPY;
+constexpr uint32_t SA_BIAS_BYTES = 6 * SA_BT_HEAD;
+constexpr uint32_t SA_OFF_BIAS = SA_OFF_OST + SA_TILE;
+constexpr uint32_t SA_OFF_BAR = SA_OFF_BIAS + SA_BIAS_BYTES;
 constexpr uint32_t SA_SMEM = SA_OFF_BAR + 256;  // the kernel has no static shared memory: the dynamic base is 1024-aligned (checked)
 static_assert(SA_SMEM <= 232448, "fused attention kernel exceeds the 227 KB shared-memory limit");
 
@@ -60,8 +63,7 @@ enum {
 };
 
 struct AttnKArgs {
-  const float* bhp;      // [3][192] qkv bias in head-pair order (q part pre-scaled)
-  const uint4* bias_tab;  // [6][64][64] bf16, pi order, 16-byte chunks XOR-swizzled by (row & 7), times log2(e)
+  const uint4* bias_tab;  // [6 heads][4 copies][15][20] bf16 (pack_attn_fused_host), times log2(e)
   int B, H, W, shift;
   int nwx, nwy, n_windows, n_tiles;
   long long* dbg;  // optional phase timestamps (developer diagnostics): [CTA][g < 96][8]
@@ -90,6 +92,9 @@ __device__ __forceinline__ WinPos win_pos(const AttnKArgs& a, int widx) {
   return p;
 }
 
+// CL = CTAs per cluster: with CL = 2 each CTA fetches half of every Wqkv k-block and TMA-multicasts it into the ring slot of
+// both (the 221 KB of weights per 128-token item are 2/3 of the kernel's L2 reads); both CTAs walk the same item count.
+template <int SA_POLY_EVERY, int CL>
 __global__ void __launch_bounds__(SA_THREADS, 1)
 swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant__ CUtensorMap tmX4,
                  const __grid_constant__ CUtensorMap tmO8, const __grid_constant__ CUtensorMap tmO4,
@@ -97,7 +102,6 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need the 1 KB alignment
-  float* s_bhp = reinterpret_cast<float*>(smem + SA_OFF_PAR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SA_OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AB_COUNT);
   const uint32_t sbase = smem_u32(smem);
@@ -105,7 +109,6 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
   auto bar = [&](int i) { return bar0 + 8u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 3 * 192; i += SA_THREADS) s_bhp[i] = __ldg(a.bhp + i);
   for (int i = threadIdx.x; i < (int)(SA_BIAS_BYTES / 16); i += SA_THREADS)
     reinterpret_cast<uint4*>(smem + SA_OFF_BIAS)[i] = __ldg(a.bias_tab + i);
   if (threadIdx.x == 0) {
@@ -118,6 +121,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       int cnt = 1;
       if (i == AB_OPREADY || i == AB_OSTAGED) cnt = 8;
       if (i == AB_PREADY || i == AB_PREADY + 1) cnt = 4;
+      if (i >= AB_WEMPTY && i < AB_WEMPTY + SA_WSLOTS) cnt = CL;  // released by the MMA issuer of every CTA of the cluster
       mbar_init(bar(i), cnt);
     }
     fence_barrier_init();
@@ -126,9 +130,15 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
   if (warp == 3) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
+  // items of this CTA; in a cluster every CTA takes the same number (item indices >= n_tiles are dummies: zero-filled loads,
+  // no stores)
+  const int my_tiles = CL > 1 ? (a.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x
+                              : (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
   const int G = 3 * my_tiles;                                                               // head-pair steps
   constexpr uint32_t IDESC_QKV = umma_idesc(1, 128, 192), IDESC_S = umma_idesc(1, 128, 128);
   constexpr uint32_t IDESC_PV = umma_idesc(1, 128, 32) | (1u << 16);  // B operand MN-major
@@ -200,10 +210,14 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
     if (lane == 0) {
       for (int e = warp - 1; e < 3 * G; e += 2) {
         const int g = e / 3, kb = e - 3 * g, hp = g % 3;
-        const int s = e & 1;
-        mbar_wait(bar(AB_WEMPTY + s), (((uint32_t)e >> 1) & 1u) ^ 1u);
+        const int s = e % SA_WSLOTS;
+        mbar_wait(bar(AB_WEMPTY + s), (((uint32_t)e / SA_WSLOTS) & 1u) ^ 1u);
         mbar_expect_tx(bar(AB_WFULL + s), SA_WSLOT);
-        tma_load_2d(sbase + SA_OFF_W + s * SA_WSLOT, &tmW, bar(AB_WFULL + s), kb * 64, hp * 192);
+        if (CL > 1)  // own rows of the k-block -> both CTAs; the slot completes with the peer's part
+          tma_load_2d_mc(sbase + SA_OFF_W + s * SA_WSLOT + crank * (192u / CL) * 128u, &tmW, bar(AB_WFULL + s), kb * 64,
+                         hp * 192 + (int)crank * (192 / CL), kClMask);
+        else
+          tma_load_2d(sbase + SA_OFF_W + s * SA_WSLOT, &tmW, bar(AB_WFULL + s), kb * 64, hp * 192);
       }
     }
   } else if (warp == 3) {
@@ -212,14 +226,17 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       uint32_t wk = 0;
       auto proj = [&](int g) {  // QKV accumulator of pair g: [128 x 192] = xn [128 x 192] * Whp[g % 3]^T
         for (int kb = 0; kb < 3; ++kb) {
-          const int s = wk & 1;
-          mbar_wait(bar(AB_WFULL + s), (wk >> 1) & 1u);
+          const int s = wk % SA_WSLOTS;
+          mbar_wait(bar(AB_WFULL + s), (wk / SA_WSLOTS) & 1u);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(sbase + SA_OFF_XN + kb * SA_TILE);
           const uint64_t bdesc = umma_desc_sw128(sbase + SA_OFF_W + s * SA_WSLOT);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma<false>(tACC, adesc + 2 * k, bdesc + 2 * k, IDESC_QKV, (kb | k) ? 1u : 0u);
-          umma_commit(bar(AB_WEMPTY + s));
+          if (CL > 1)
+            umma_commit_mc(bar(AB_WEMPTY + s), kClMask);
+          else
+            umma_commit(bar(AB_WEMPTY + s));
           ++wk;
         }
         umma_commit(bar(AB_QKVFULL));
@@ -272,7 +289,10 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
     uint8_t* sK = smem + SA_OFF_K;
     uint8_t* sV = smem + SA_OFF_V;
     uint8_t* sO = smem + SA_OFF_OST;
-    const uint4* sBias = reinterpret_cast<const uint4*>(smem + SA_OFF_BIAS);
+    // this token's window coordinates (order r = (tx / 4) * 32 + ty * 4 + tx % 4) and its copy of the bias table
+    const int yi = (ri & 31) >> 2, xi = (ri >> 5) * 4 + (ri & 3);
+    const int bt_s = (7 - xi) & 3;
+    const uint8_t* sBiasRow = smem + SA_OFF_BIAS + bt_s * SA_BT_COPY + (7 - yi) * (SA_BT_PITCH * 2) + (7 - xi + ((4 - bt_s) & 3)) * 2;
     constexpr float kMask = -100.0f * 1.4426950408889634f;
     bool yflag = false, xflag = false;
 
@@ -295,18 +315,18 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         *reinterpret_cast<uint4*>(sO + sa_sw128(row, 4 * grp + j)) = v;
       }
     };  // the caller publishes the staging (fence.proxy.async + arrive on AB_OSTAGED) together with its own smem writes
-    // QKV epilogue of one 32-column chunk: + bias, bf16, into the operand tile `dst_of(chunk j)` selects
-    auto qkv_chunk = [&](const uint32_t (&raw)[32], const float* bb, auto dst_of) {
+    // QKV epilogue of one 32-column chunk: bf16 into the operand tile `dst_of(chunk j)` selects.  The qkv bias is already in
+    // the accumulator: norm1's output carries 1.0 in the two pad channels C, C+1 and the packed weight holds the bias there
+    // (hi + lo bf16 parts), so there is no shared-memory bias fetch in front of every store.
+    auto qkv_chunk = [&](const uint32_t (&raw)[32], auto dst_of) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16-byte chunk
-        const float4 b0 = *reinterpret_cast<const float4*>(bb + 8 * j);
-        const float4 b1 = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
         const uint32_t* r8 = &raw[8 * j];
         uint4 v;
-        v.x = f2_to_bf16x2(f2_add(f2_pack_u(r8[0], r8[1]), f2_pack(b0.x, b0.y)));
-        v.y = f2_to_bf16x2(f2_add(f2_pack_u(r8[2], r8[3]), f2_pack(b0.z, b0.w)));
-        v.z = f2_to_bf16x2(f2_add(f2_pack_u(r8[4], r8[5]), f2_pack(b1.x, b1.y)));
-        v.w = f2_to_bf16x2(f2_add(f2_pack_u(r8[6], r8[7]), f2_pack(b1.z, b1.w)));
+        v.x = pack_bf16x2(__uint_as_float(r8[0]), __uint_as_float(r8[1]));
+        v.y = pack_bf16x2(__uint_as_float(r8[2]), __uint_as_float(r8[3]));
+        v.z = pack_bf16x2(__uint_as_float(r8[4]), __uint_as_float(r8[5]));
+        v.w = pack_bf16x2(__uint_as_float(r8[6]), __uint_as_float(r8[7]));
         *reinterpret_cast<uint4*>(dst_of(j)) = v;
       }
     };
@@ -324,7 +344,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       long long* dbg = (a.dbg && ew == 0 && lane == 0 && g < 96) ? a.dbg + 8 * ((size_t)blockIdx.x * 96 + g) : nullptr;
       if (dbg) dbg[0] = clock64();
 
-      // ---------------- QKV epilogue: + bias, bf16, operand tiles (V into buffer g & 1: P.V of pair g-1 may still run) ----------------
+      // ---------------- QKV epilogue: bf16 operand tiles (V into buffer g & 1: P.V of pair g-1 may still run) ----------------
       mbar_wait_warp(bar(AB_QKVFULL), ph, lane);
       if (dbg) dbg[1] = clock64();
       tc_fence_after();
@@ -333,27 +353,29 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 3; ++c) tmem_ld32_nowait(tlane + grp * 96 + c * 32, raw[c]);
         tmem_wait_ld();
-        const float* bb = s_bhp + hp * 192 + grp * 96;
         uint8_t* vbuf = sV + (g & 1) * SA_TILE;
         if (grp == 0) {  // columns [0,96): q h0 | q h1 | k h0
-          qkv_chunk(raw[0], bb, [&](int j) { return sQ + sa_sw128(row, j); });
-          qkv_chunk(raw[1], bb + 32, [&](int j) { return sQ + sa_sw128(row, 4 + j); });
-          qkv_chunk(raw[2], bb + 64, [&](int j) { return sK + sa_sw128(row, j); });
+          qkv_chunk(raw[0], [&](int j) { return sQ + sa_sw128(row, j); });
+          qkv_chunk(raw[1], [&](int j) { return sQ + sa_sw128(row, 4 + j); });
+          qkv_chunk(raw[2], [&](int j) { return sK + sa_sw128(row, j); });
         } else {  // columns [96,192): k h1 | v h0 | v h1
-          qkv_chunk(raw[0], bb, [&](int j) { return sK + sa_sw128(row, 4 + j); });
-          qkv_chunk(raw[1], bb + 32, [&](int j) { return vbuf + sa_sw64(row, j); });
-          qkv_chunk(raw[2], bb + 64, [&](int j) { return vbuf + 8192 + sa_sw64(row, j); });
+          qkv_chunk(raw[0], [&](int j) { return sK + sa_sw128(row, 4 + j); });
+          qkv_chunk(raw[1], [&](int j) { return vbuf + sa_sw64(row, j); });
+          qkv_chunk(raw[2], [&](int j) { return vbuf + 8192 + sa_sw64(row, j); });
         }
       }
+      // publish the operand tiles first: the score MMAs (and the next pair's projection) then run under the output epilogue
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(AB_OPREADY));
       if (dbg) dbg[2] = clock64();
       // ---------------- output of the previous pair (its P.V ran under this pair's QKV epilogue) ----------------
-      if (g > 0) out_epilogue(g - 1, inv_l_prev);
-      tc_fence_before();
-      fence_proxy_async();  // one proxy fence publishes both the operand tiles and the output staging
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(AB_OPREADY));
-        if (g > 0) mbar_arrive(bar(AB_OSTAGED));
+      if (g > 0) {
+        out_epilogue(g - 1, inv_l_prev);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(AB_OSTAGED));
       }
       if (dbg) dbg[3] = clock64();
 
@@ -362,9 +384,14 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       // bias row of this token: 64 bf16 = 8 chunks (fetched while the score MMAs finish)
       uint4 bq[8];
       {
-        const uint4* brow = sBias + (head * 64 + ri) * 8;
+        // keys 8c .. 8c+7 = key rows yj = 2c % 8, 2c % 8 + 1 at key columns 4 (c / 4) .. +3: two aligned runs of the table
+        const uint8_t* brow = sBiasRow + head * SA_BT_HEAD;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) bq[c] = brow[c ^ (ri & 7)];
+        for (int c = 0; c < 8; ++c) {
+          const uint8_t* p0 = brow + ((2 * c) & 7) * (SA_BT_PITCH * 2) + (c >> 2) * 8;
+          const uint2 r0 = *reinterpret_cast<const uint2*>(p0), r1 = *reinterpret_cast<const uint2*>(p0 + SA_BT_PITCH * 2);
+          bq[c] = make_uint4(r0.x, r0.y, r1.x, r1.y);
+        }
       }
       mbar_wait_warp(bar(AB_SFULL + grp), ph, lane);
       if (dbg) dbg[4] = clock64();
@@ -407,11 +434,16 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         uint32_t pk[32];
 #pragma unroll
         for (int p = 0; p < 32; ++p) {
-          float lo, hi;
-          f2_unpack(f2_add(s[p], nm), lo, hi);
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lo) : "f"(lo));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(hi));
-          const f32x2 e2 = f2_pack(lo, hi);
+          f32x2 e2;
+          if (SA_POLY_EVERY > 0 && p % (SA_POLY_EVERY > 0 ? SA_POLY_EVERY : 1) == SA_POLY_EVERY - 1) {
+            e2 = f2_exp2_poly(f2_add(s[p], nm));  // every SA_POLY_EVERY-th pair: FMA pipe instead of MUFU (the phase is MUFU-bound)
+          } else {
+            float lo, hi;
+            f2_unpack(f2_add(s[p], nm), lo, hi);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lo) : "f"(lo));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(hi) : "f"(hi));
+            e2 = f2_pack(lo, hi);
+          }
           acc2[p & 3] = f2_add(acc2[p & 3], e2);
           pk[p] = f2_to_bf16x2(e2);
         }
@@ -440,6 +472,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 3) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -452,6 +485,19 @@ int launch_swin_attn_fused(const AttnFusedArgs& f, cudaStream_t s) {
   SSR_CHECK(f.H % 8 == 0 && f.W % 8 == 0, SSR_E_INVALID, "swin_attn: %dx%d not a multiple of the 8x8 window", f.H, f.W);
   SSR_CHECK(f.shift == 0 || f.shift == 4, SSR_E_INVALID, "swin_attn: shift %d not in {0, 4}", f.shift);
   SSR_CHECK(f.ld_x == 192 && f.ld_o == 192, SSR_E_INVALID, "swin_attn: leading dims must be 192 (got %d / %d)", f.ld_x, f.ld_o);
+  // developer A/B switches: STUDIOSR_B200_ATTN_POLY=0 keeps every softmax exponential on MUFU, STUDIOSR_B200_ATTN_CLUSTER=1
+  // switches the weight multicast off
+  static int poly = -1, cl = 2;
+  if (poly < 0) {
+    const char* e = getenv("STUDIOSR_B200_ATTN_POLY");
+    poly = (e && e[0] == '0') ? 0 : SA_POLY_DEFAULT;
+    const char* c = getenv("STUDIOSR_B200_ATTN_CLUSTER");
+    cl = (c && c[0] == '1') ? 1 : 2;
+    SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
+    SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel<SA_POLY_DEFAULT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
+    SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
+    SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel<SA_POLY_DEFAULT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
+  }
   CUtensorMap tmX8, tmX4, tmO8, tmO4, tmW;
   auto map4d = [&](CUtensorMap* m, const void* base, int ld, int bh) {
     cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)f.W, (cuuint64_t)f.H, (cuuint64_t)f.B};
@@ -466,28 +512,47 @@ int launch_swin_attn_fused(const AttnFusedArgs& f, cudaStream_t s) {
   {
     cuuint64_t dims[2] = {192, 576};
     cuuint64_t str[1] = {192 * 2};
-    cuuint32_t box[2] = {64, 192};
+    cuuint32_t box[2] = {64, (cuuint32_t)(192 / cl)};
     SSR_TRY(make_tmap(&tmW, f.Whp, 2, 2, dims, str, box, 128));
   }
   AttnKArgs a;
-  a.bhp = f.bhp;
   a.bias_tab = reinterpret_cast<const uint4*>(f.bias_tab);
   a.B = f.B; a.H = f.H; a.W = f.W; a.shift = f.shift;
   a.nwx = f.W / 8; a.nwy = f.H / 8;
   a.n_windows = f.B * a.nwx * a.nwy;
   a.n_tiles = (a.n_windows + 1) / 2;
   a.dbg = g_tail_dbg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
-    attr_set = true;
-  }
   const int sms = num_sms_cached();
   const double T = (double)f.B * f.H * f.W;
   const double flops = T * (2.0 * 3 * f.C * f.C + 4.0 * 64 * f.C);  // qkv projection + (q k^T, p v) over 64 keys
   const double bytes = T * f.C * (2 + 2);
   ProfScope prof("swin_attn", flops, bytes, s);
-  swin_attn_kernel<<<a.n_tiles < sms ? a.n_tiles : sms, SA_THREADS, SA_SMEM, s>>>(tmX8, tmX4, tmO8, tmO4, tmW, a);
+  int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  if (cl == 1) {
+    if (poly == 0)
+      swin_attn_kernel<0, 1><<<grid, SA_THREADS, SA_SMEM, s>>>(tmX8, tmX4, tmO8, tmO4, tmW, a);
+    else
+      swin_attn_kernel<SA_POLY_DEFAULT, 1><<<grid, SA_THREADS, SA_SMEM, s>>>(tmX8, tmX4, tmO8, tmO4, tmW, a);
+  } else {
+    grid = (grid + 1) / 2 * 2;
+    if (grid > sms) grid -= 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SA_THREADS);
+    cfg.dynamicSmemBytes = SA_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (poly == 0)
+      SSR_CUDA(cudaLaunchKernelEx(&cfg, swin_attn_kernel<0, 2>, tmX8, tmX4, tmO8, tmO4, tmW, a));
+    else
+      SSR_CUDA(cudaLaunchKernelEx(&cfg, swin_attn_kernel<SA_POLY_DEFAULT, 2>, tmX8, tmX4, tmO8, tmO4, tmW, a));
+  }
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;

@@ -130,6 +130,11 @@ __device__ __forceinline__ void for_each_ring_entry(int my_tiles, F f) {
   }
 }
 
+// CL = CTAs per cluster.  With CL = 2 the two CTAs walk the same ring-entry sequence; each fetches 1/CL of every weight
+// entry and TMA-multicasts it into the slot of both, so Wproj / W1 / W2 (366 KB per 128-token tile, 56 % of the kernel's L2
+// reads -- the kernel runs at the chip's L2 throughput cap) leave L2 once per cluster.  A slot is reusable once the MMA
+// issuers of BOTH CTAs have released it: WEMPTY counts CL multicast commits.
+template <int CL>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWp,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -169,7 +174,8 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
     prefetch_tmap(&tmOutB2);
     for (int i = 0; i < SB_COUNT; ++i) {
       const bool cnt8 = i == SB_XNREADY || (i >= SB_HREADY && i < SB_HREADY + 2) || (i >= SB_YFREE && i < SB_YFREE + 2);
-      mbar_init(bar(i), cnt8 ? 8 : 1);
+      const bool wempty = i >= SB_WEMPTY && i < SB_WEMPTY + ST_WSLOTS;
+      mbar_init(bar(i), cnt8 ? 8 : wempty ? CL : 1);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -177,10 +183,16 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
   if (warp == 3) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_tiles = a.n_tiles;
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  // tiles of this CTA.  In a cluster every CTA takes the same number (the ring sequences must match): tile indices >= n_tiles
+  // are dummies whose rows lie beyond M -- TMA zero-fills their loads and drops their stores.
+  const int my_tiles = CL > 1 ? (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x
+                              : (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
   constexpr uint32_t IDESC_192 = umma_idesc(1, 128, 192), IDESC_64 = umma_idesc(1, 128, 64);
   constexpr uint32_t TY = 0, TX = 384;  // Y_s = TY + 192 s, X_b = TX + 64 b
 
@@ -205,15 +217,24 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
               tma_prefetch_2d(&tmResPf, idx * 64, row0);
               tma_prefetch_2d(&tmResPf, idx * 64 + 32, row0);
             }
-          } else if (kind == 1) {
-            mbar_expect_tx(fb, ST_WSLOT);
-            tma_load_2d(dst, &tmWp, fb, idx * 64, 0);
-          } else if (kind == 2) {
-            mbar_expect_tx(fb, ST_WSLOT);
-            for (int kb = 0; kb < 3; ++kb) tma_load_2d(dst + kb * 8192, &tmW1, fb, kb * 64, idx * 64);
           } else {
+            // weight entry: this CTA fetches rows [rank, rank + 1) / CL of every box; the whole slot (own part + the peers'
+            // multicast parts) completes on the own barrier
             mbar_expect_tx(fb, ST_WSLOT);
-            tma_load_2d(dst, &tmW2, fb, idx * 64, 0);
+            auto wload = [&](uint32_t d, const CUtensorMap* map, int c0, int r0, int rows) {
+              const int part = rows / CL;
+              if (CL > 1)
+                tma_load_2d_mc(d + crank * (uint32_t)part * 128u, map, fb, c0, r0 + (int)crank * part, kClMask);
+              else
+                tma_load_2d(d, map, fb, c0, r0);
+            };
+            if (kind == 1) {
+              wload(dst, &tmWp, idx * 64, 0, 192);
+            } else if (kind == 2) {
+              for (int kb = 0; kb < 3; ++kb) wload(dst + kb * 8192, &tmW1, kb * 64, idx * 64, 64);
+            } else {
+              wload(dst, &tmW2, idx * 64, 0, 192);
+            }
           }
         });
       }
@@ -234,8 +255,14 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
           tc_fence_after();
           return opaque(sbase) + ST_OFF_W + s * ST_WSLOT;
         };
+        auto slot_free = [&](int s) {  // the slot is free once the MMAs issued so far are done -- in every CTA of the cluster
+          if (CL > 1)
+            umma_commit_mc(bar(SB_WEMPTY + s), kClMask);
+          else
+            umma_commit(bar(SB_WEMPTY + s));
+        };
         auto w_release = [&]() {
-          umma_commit(bar(SB_WEMPTY + (wk % ST_WSLOTS)));
+          slot_free(wk % ST_WSLOTS);
           ++wk;
         };
         auto proj = [&](int it) {  // Y_s = o(it) Wproj^T ; s = it & 1
@@ -248,7 +275,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
             const uint64_t adesc = umma_desc_sw128(o_addr), bdesc = umma_desc_sw128(w_addr);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma<false>(tY, adesc + 2 * k, bdesc + 2 * k, IDESC_192, (kb | k) ? 1u : 0u);
-            umma_commit(bar(SB_WEMPTY + so));
+            slot_free(so);
             w_release();
           }
           umma_commit(bar(SB_PFULL + (it & 1)));
@@ -618,6 +645,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 3) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -639,9 +667,17 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
     return make_tmap(m, base, elem, 2, dims, str, box, sw);
   };
   SSR_TRY(map2d(&tmO, f.o, 2, f.ld_o, f.M, f.ld_o, 64, 128, 128));
-  SSR_TRY(map2d(&tmWp, f.Wp, 2, 192, 192, 192, 64, 192, 128));
-  SSR_TRY(map2d(&tmW1, f.W1, 2, 192, 384, 192, 64, 64, 128));
-  SSR_TRY(map2d(&tmW2, f.W2, 2, 384, 192, 384, 64, 192, 128));
+  // STUDIOSR_B200_TAIL_CLUSTER=2 switches the weight multicast on.  Measured (profiles/r02_cluster_multicast.txt): it takes
+  // 28 % of the kernel's L2 reads away and the tile period does not move (17.7k -> 18.1k cycles: the two CTAs now stall
+  // together), i.e. the kernel is not L2-bound; kept as an experiment switch, off by default.
+  static int cl = 0;
+  if (!cl) {
+    const char* e = getenv("STUDIOSR_B200_TAIL_CLUSTER");
+    cl = (e && e[0] == '2') ? 2 : 1;
+  }
+  SSR_TRY(map2d(&tmWp, f.Wp, 2, 192, 192, 192, 64, 192 / cl, 128));
+  SSR_TRY(map2d(&tmW1, f.W1, 2, 192, 384, 192, 64, 64 / cl, 128));
+  SSR_TRY(map2d(&tmW2, f.W2, 2, 384, 192, 384, 64, 192 / cl, 128));
   SSR_TRY(map2d(&tmRes, f.res, 4, 192, f.M, f.ldres, 32, 32, 128));
   SSR_TRY(map2d(&tmResPf, f.res, 4, 192, f.M, f.ldres, 32, 128, 128));
   const void* outf = f.out_f32 ? (const void*)f.out_f32 : (const void*)f.res;  // placeholder map when unused
@@ -666,15 +702,34 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
   a.dbg = g_tail_dbg;
   static bool attr_set = false;
   if (!attr_set) {
-    SSR_CUDA(cudaFuncSetAttribute(swin_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    SSR_CUDA(cudaFuncSetAttribute(swin_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    SSR_CUDA(cudaFuncSetAttribute(swin_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
     attr_set = true;
   }
   const int sms = num_sms_cached();
   const double flops = 2.0 * f.M * ((double)f.C * f.C + 2.0 * f.C * f.Hid);
   const double bytes = (double)f.M * f.C * (2 + 4 + (f.out_f32 ? 4 : 0) + (f.out_T ? 2 : 0) + (f.out_ln ? 2 : 0));
   ProfScope prof("swin_tail", flops, bytes, s);
-  swin_tail_kernel<<<a.n_tiles < sms ? a.n_tiles : sms, ST_THREADS, ST_SMEM, s>>>(tmO, tmWp, tmW1, tmW2, tmRes, tmResPf, tmOutF,
-                                                                                 tmOutB, tmOutB2, a);
+  int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  if (cl == 1) {
+    swin_tail_kernel<1><<<grid, ST_THREADS, ST_SMEM, s>>>(tmO, tmWp, tmW1, tmW2, tmRes, tmResPf, tmOutF, tmOutB, tmOutB2, a);
+  } else {
+    grid = (grid + 1) / 2 * 2;
+    if (grid > sms) grid -= 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(ST_THREADS);
+    cfg.dynamicSmemBytes = ST_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SSR_CUDA(cudaLaunchKernelEx(&cfg, swin_tail_kernel<2>, tmO, tmWp, tmW1, tmW2, tmRes, tmResPf, tmOutF, tmOutB, tmOutB2, a));
+  }
   count_launch();
   SSR_CUDA(cudaGetLastError());
   return SSR_OK;

@@ -257,9 +257,8 @@ static int fold_norm_into_linear(ssr_model* m, const std::string& norm, const st
   return SSR_OK;
 }
 
-int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* table, int C, int heads, void* Whp, float* bhp,
-                         void* bias_tab) {
-  SSR_CHECK(heads == 6 && C % heads == 0 && C / heads <= 32 && C <= 192, SSR_E_INVALID,
+int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* table, int C, int heads, void* Whp, void* bias_tab) {
+  SSR_CHECK(heads == 6 && C % heads == 0 && C / heads <= 32 && C + kAttnOnesChannels <= 192, SSR_E_INVALID,
             "fused attention packing: C=%d heads=%d unsupported", C, heads);
   const int d = C / heads;
   const float log2e = 1.4426950408889634f, qs = log2e / sqrtf((float)d);
@@ -270,22 +269,25 @@ int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* tabl
       const bool real = j < d;
       const int src = sec * C + head * d + j;
       const float sc = sec == 0 ? qs : 1.0f;
-      bhp[hp * 192 + n] = real ? bqkv[src] * sc : 0.0f;
-      for (int k = 0; k < 192; ++k)
-        W[((size_t)hp * 192 + n) * 192 + k] = __float2bfloat16_rn(real && k < C ? Wqkv[(size_t)src * C + k] * sc : 0.0f);
+      __nv_bfloat16* row = W + ((size_t)hp * 192 + n) * 192;
+      for (int k = 0; k < 192; ++k) row[k] = __float2bfloat16_rn(real && k < C ? Wqkv[(size_t)src * C + k] * sc : 0.0f);
+      // the bias rides in the GEMM: the A operand (norm1's output) is 1.0 in channels C, C+1; hi + lo keeps 16 mantissa bits
+      const float b = real ? bqkv[src] * sc : 0.0f;
+      row[C] = __float2bfloat16_rn(b);
+      row[C + 1] = __float2bfloat16_rn(b - __bfloat162float(row[C]));
     }
-  // relative-position bias in the kernel's window-token order r = (tx / 4) * 32 + ty * 4 + tx % 4 (swinir.py:57-67, 92-95)
-  uint8_t* bt = reinterpret_cast<uint8_t*>(bias_tab);
+  // relative-position bias (swinir.py:57-67, 92-95), compact: B[i][j] = T[yi - yj + 7][xi - xj + 7] = R[7 - yi + yj][7 - xi + xj]
+  // with R the table reversed in both axes, so the 8 x 8 keys of a window seen from token (yi, xi) are an 8 x 8 sub-block of R
+  // and every key quad (4 consecutive xj) is a contiguous run.  Four copies, shifted by 0..3 elements, make every run start
+  // 8-byte aligned: copy s serves tokens with (7 - xi) % 4 == s and stores R[a][b] at [a][b + (4 - s) % 4], row pitch 20.
+  __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(bias_tab);
+  for (size_t i = 0; i < kAttnBiasBytes / 2; ++i) bt[i] = __float2bfloat16_rn(0.0f);
   for (int hd = 0; hd < heads; ++hd)
-    for (int ri = 0; ri < 64; ++ri) {
-      const int yi = (ri & 31) >> 2, xi = (ri >> 5) * 4 + (ri & 3);
-      for (int rj = 0; rj < 64; ++rj) {
-        const int yj = (rj & 31) >> 2, xj = (rj >> 5) * 4 + (rj & 3);
-        const float v = table[(size_t)((yi - yj + 7) * 15 + (xi - xj + 7)) * heads + hd] * log2e;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        memcpy(bt + (size_t)hd * 8192 + ri * 128 + ((((rj >> 3) ^ (ri & 7))) << 4) + (rj & 7) * 2, &h, 2);
-      }
-    }
+    for (int sft = 0; sft < 4; ++sft)
+      for (int a = 0; a < 15; ++a)
+        for (int b = 0; b < 15; ++b)
+          bt[((size_t)(hd * 4 + sft) * 15 + a) * 20 + b + ((4 - sft) & 3)] =
+              __float2bfloat16_rn(table[(size_t)((14 - a) * 15 + (14 - b)) * heads + hd] * log2e);
   return SSR_OK;
 }
 
@@ -355,11 +357,12 @@ static int finalize_swinir(ssr_model* m) {
         const std::vector<float>* Bq = find_param(m, p + ".attn.qkv.bias", (size_t)3 * C);
         if (!Wq || !Bq) return SSR_E_STATE;
         B.whp_off = arena_alloc(m, kAttnWhpBytes);
-        B.bhp_off = arena_alloc(m, kAttnBhpBytes);
         B.btab_off = arena_alloc(m, kAttnBiasBytes);
         uint8_t* base = m->host_arena.data();
-        SSR_TRY(pack_attn_fused_host(Wq->data(), Bq->data(), T->data(), C, heads, base + B.whp_off,
-                                     reinterpret_cast<float*>(base + B.bhp_off), base + B.btab_off));
+        SSR_TRY(pack_attn_fused_host(Wq->data(), Bq->data(), T->data(), C, heads, base + B.whp_off, base + B.btab_off));
+        // norm1 (gamma pad = 0) writes its beta into the pad channels: 1.0 in C, C+1 switches the bias columns of Whp on
+        float* beta = reinterpret_cast<float*>(base + B.norm1.b_off);
+        for (int k = 0; k < kAttnOnesChannels; ++k) beta[C + k] = 1.0f;
       }
       L.blocks.push_back(B);
     }
@@ -903,13 +906,12 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
         AttnFusedArgs f;
         memset(&f, 0, sizeof(f));
         f.xn = W.xn; f.ld_x = CP; f.o = W.o; f.ld_o = L.QP;
-        f.Whp = m->arena + blk.whp_off; f.bhp = m->dev<float>(blk.bhp_off); f.bias_tab = m->arena + blk.btab_off;
+        f.Whp = m->arena + blk.whp_off; f.bias_tab = m->arena + blk.btab_off;
         f.B = B; f.H = Hp; f.W = Wp; f.shift = (bi % 2 == 0) ? 0 : c.window_size / 2;
         f.C = m->C; f.d = L.d;
         debug_nonfinite("xn", li, bi, W.xn, (size_t)T * CP, e, s);
         if (li == 0 && bi == 0) {
           debug_nonfinite("Whp", li, bi + 100, f.Whp, kAttnWhpBytes / 2, 2, s);
-          debug_nonfinite("bhp", li, bi + 100, f.bhp, kAttnBhpBytes / 4, 4, s);
           debug_nonfinite("btab", li, bi + 100, f.bias_tab, kAttnBiasBytes / 2, 2, s);
         }
         SSR_TRY(launch_swin_attn_fused(f, s));

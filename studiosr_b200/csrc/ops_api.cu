@@ -66,6 +66,14 @@ using namespace ssr;
 
 static long long* g_dbg_buf = nullptr;
 
+namespace ssr {
+__global__ void fill_ones_bf16_kernel(__nv_bfloat16* x, size_t M, int ld, int c0, int n) {
+  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < M)
+    for (int k = 0; k < n; ++k) x[r * ld + c0 + k] = __float2bfloat16_rn(1.0f);
+}
+}  // namespace ssr
+
 extern "C" {
 
 // developer diagnostics: per-CTA phase timestamps of the next ssr_op_linear launches (device buffer, 8 x int64 per CTA)
@@ -288,7 +296,6 @@ int ssr_op_swin_attn(const float* xn, const float* Wqkv, const float* bqkv, cons
   void* xp = c.take(M * 192 * 2);
   void* op = c.take(M * 192 * 2);
   void* whp = c.take(kAttnWhpBytes);
-  float* bhp = (float*)c.take(kAttnBhpBytes);
   void* btab = c.take(kAttnBiasBytes);
   SSR_CHECK(btab, SSR_E_WORKSPACE, "ssr_op_swin_attn: workspace too small (%zu B)", workspace_bytes);
   // test-only convenience: the operands are packed on the host exactly as ssr_model_finalize does
@@ -298,16 +305,17 @@ int ssr_op_swin_attn(const float* xn, const float* Wqkv, const float* bqkv, cons
   SSR_CUDA(cudaMemcpyAsync(ht.data(), bias_table, ht.size() * 4, cudaMemcpyDeviceToHost, s));
   SSR_CUDA(cudaStreamSynchronize(s));
   std::vector<uint8_t> pw(kAttnWhpBytes), pt(kAttnBiasBytes);
-  std::vector<float> pb(kAttnBhpBytes / 4);
-  SSR_TRY(pack_attn_fused_host(hW.data(), hb.data(), ht.data(), C, heads, pw.data(), pb.data(), pt.data()));
+  SSR_TRY(pack_attn_fused_host(hW.data(), hb.data(), ht.data(), C, heads, pw.data(), pt.data()));
   SSR_CUDA(cudaMemcpyAsync(whp, pw.data(), pw.size(), cudaMemcpyHostToDevice, s));
-  SSR_CUDA(cudaMemcpyAsync(bhp, pb.data(), pb.size() * 4, cudaMemcpyHostToDevice, s));
   SSR_CUDA(cudaMemcpyAsync(btab, pt.data(), pt.size(), cudaMemcpyHostToDevice, s));
   SSR_TRY(launch_pack_rows(xn, (int)M, C, xp, 192, 2, 0, s));
+  // the kernel's input contract (what norm1's padded beta produces inside a model): 1.0 in channels C, C+1
+  fill_ones_bf16_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(xp), M, 192, C, kAttnOnesChannels);
+  SSR_CUDA(cudaGetLastError());
   SSR_CUDA(cudaMemsetAsync(op, 0, M * 192 * 2, s));
   AttnFusedArgs f;
   memset(&f, 0, sizeof(f));
-  f.xn = xp; f.ld_x = 192; f.o = op; f.ld_o = 192; f.Whp = whp; f.bhp = bhp; f.bias_tab = btab;
+  f.xn = xp; f.ld_x = 192; f.o = op; f.ld_o = 192; f.Whp = whp; f.bias_tab = btab;
   f.B = B; f.H = H; f.W = W; f.shift = shift; f.C = C; f.d = d;
   SSR_TRY(launch_swin_attn_fused(f, s));
   SSR_TRY(launch_unpack_heads(op, 192, 2, o, (int)M, heads, d, 32, s));

@@ -219,22 +219,22 @@ int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t s);
 
 // fused QKV projection + (shifted-)window attention of one Swin block (bf16, 8x8 windows, 6 heads x 32 padded dims)
 struct AttnFusedArgs {
-  const void* xn;  // bf16 [B*H*W][ld_x]: LayerNorm1 output, pixel order
+  const void* xn;  // bf16 [B*H*W][ld_x]: LayerNorm1 output, pixel order; channels C and C+1 must hold 1.0 (they carry the qkv bias)
   int ld_x;
   void* o;  // bf16 [B*H*W][ld_o], channel = head*32 + j
   int ld_o;
-  const void* Whp;       // bf16 [3 pairs][192][192]: rows q h0 h1 | k h0 h1 | v h0 h1 (32 each); q rows x d^-1/2 log2(e)
-  const float* bhp;      // fp32 [3][192], same order / scaling
-  const void* bias_tab;  // bf16 [6][64][64] relative-position bias x log2(e), window-token order pi, chunk-swizzled
+  const void* Whp;       // bf16 [3 pairs][192][192]: rows q h0 h1 | k h0 h1 | v h0 h1 (32 each); q rows x d^-1/2 log2(e);
+                         // columns C, C+1 = the qkv bias of the row as hi + lo bf16 parts
+  const void* bias_tab;  // bf16 [6 heads][4 shifted copies][15][20]: reversed relative-position bias table x log2(e)
   int B, H, W, shift;
   int C, d;  // un-padded sizes (accounting)
 };
 int launch_swin_attn_fused(const AttnFusedArgs& a, cudaStream_t s);
-constexpr size_t kAttnWhpBytes = 3 * 192 * 192 * 2, kAttnBhpBytes = 3 * 192 * 4, kAttnBiasBytes = 6 * 64 * 64 * 2;
-// host-side packing of the three buffers above from the reference parameters (qkv.weight [3C][C], qkv.bias [3C],
-// relative_position_bias_table [225][heads]); heads must be 6 and C / heads <= 32
-int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* table, int C, int heads, void* Whp, float* bhp,
-                         void* bias_tab);
+constexpr size_t kAttnWhpBytes = 3 * 192 * 192 * 2, kAttnBiasBytes = 6 * 4 * 15 * 20 * 2;
+// host-side packing of the two buffers above from the reference parameters (qkv.weight [3C][C], qkv.bias [3C],
+// relative_position_bias_table [225][heads]); heads must be 6, C / heads <= 32 and C <= 190 (two pad channels for the bias)
+int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* table, int C, int heads, void* Whp, void* bias_tab);
+constexpr int kAttnOnesChannels = 2;  // norm1's output channels C .. C+1 are 1.0 for the fused attention kernel
 int launch_fold_ln_linear(const float* W, const float* b, const float* gamma, const float* beta, float* Wf, float* bf, int N, int K,
                           cudaStream_t s);
 int launch_pack_heads(const float* in, void* out, int M, int heads, int d, int DP, int ld, int elem, int round_tf32,

@@ -22,7 +22,7 @@ struct Block {
   LNp norm1, norm2;
   Lin qkv, proj, fc1, fc2;
   size_t bias_off = 0;  // float [heads][(2ws-1)^2]
-  size_t whp_off = 0, bhp_off = 0, btab_off = 0;  // fused attention kernel operands (k_swin_attn.cu)
+  size_t whp_off = 0, btab_off = 0;  // fused attention kernel operands (k_swin_attn.cu)
   // HAT: channel attention block of a HAB (hat.py:41-52)
   Lin cab0, cab2;
   size_t ca_w1 = 0, ca_b1 = 0, ca_w2 = 0, ca_b2 = 0;

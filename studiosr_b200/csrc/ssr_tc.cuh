@@ -87,6 +87,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- thread-block clusters: weight tiles are fetched from L2 once per cluster and multicast into every CTA's ring slot ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the box lands at the same shared-memory offset, and completes bytes on the mbarrier at the same offset, in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -132,6 +148,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 template <bool kTf32>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -296,6 +317,24 @@ __device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 a) {
   float lo, hi;
   f2_unpack(a, lo, hi);
   return pack_bf16x2(lo, hi);
+}
+// 2^x for a pair of non-positive x on the FMA pipe instead of the 16-lanes-per-clock MUFU: round-to-nearest split x = j + f
+// by the 1.5 * 2^23 magic add, degree-3 minimax of 2^f on [-0.5, 0.5] (relative error 7.5e-5, far below the bf16 rounding
+// of the probabilities it feeds), j added into the exponent field.  x is clamped at -126 (result 2^-126 instead of 0).
+__device__ __forceinline__ f32x2 f2_exp2_poly(f32x2 x) {
+  float lo, hi;
+  f2_unpack(x, lo, hi);
+  x = f2_pack(fmaxf(lo, -126.0f), fmaxf(hi, -126.0f));
+  const f32x2 magic = f2_splat(12582912.0f);
+  const f32x2 t = f2_add(x, magic);
+  const f32x2 f = f2_fma(f2_add(t, f2_splat(-12582912.0f)), f2_splat(-1.0f), x);
+  f32x2 p = f2_fma(f2_splat(0.0551716648042202f), f, f2_splat(0.2426111251115799f));
+  p = f2_fma(p, f, f2_splat(0.6932609677314758f));
+  p = f2_fma(p, f, f2_splat(0.9999280571937561f));
+  uint32_t pl, ph, tl, th;
+  f2_unpack_u(p, pl, ph);
+  f2_unpack_u(t, tl, th);
+  return f2_pack_u(pl + (tl << 23), ph + (th << 23));
 }
 __device__ __forceinline__ float f2_hsum(f32x2 a) {
   float lo, hi;
