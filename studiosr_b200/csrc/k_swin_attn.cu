@@ -21,7 +21,7 @@
 // [192,320) / [320,448) scores of head 0 / 1 of the pair over all 128 keys of the item (only the own window's 64 are
 // read), overwritten in place by P (packed bf16: 64 columns, the other window's half zeroed = block-diagonal P);
 // [448,512) O of the pair.
-// Warps: 0 = activation loads + output stores, 1,2 = weight producers, 3 = MMA issuer, 4..11 = epilogue
+// Warps: 0 = output stores, 1 = weight producer, 2 = activation loads, 3 = MMA issuer, 4..11 = epilogue
 // (lane quadrant = warp % 4; group = (warp - 4) / 4: column half in the QKV epilogue, head of the pair afterwards).
 #include "ssr_tc.cuh"
 
@@ -37,12 +37,12 @@ constexpr uint32_t SA_OFF_W = SA_OFF_XN + 3 * SA_TILE;             // weight rin
 constexpr uint32_t SA_OFF_Q = SA_OFF_W + SA_WSLOTS * SA_WSLOT;     // [128][64] bf16 SW128: q of the pair
 constexpr uint32_t SA_OFF_K = SA_OFF_Q + SA_TILE;                  // [128][64] bf16 SW128: k of the pair
 constexpr uint32_t SA_OFF_V = SA_OFF_K + SA_TILE;                  // 2 buffers x 2 heads x [128 tokens][32] bf16 SW64 (MN-major B operand)
-constexpr uint32_t SA_OFF_OST = SA_OFF_V + 2 * SA_TILE;            // [128][64] bf16 SW128 output staging
-// relative-position bias, compact: per head 4 copies (one per 8-byte alignment of a window row's start) of the reversed
-// 15 x 15 table, row pitch 20 bf16: the 64 values of a token row are 16 aligned runs of 4 (one per key quad)
-constexpr uint32_t SA_BT_PITCH = 20, SA_BT_COPY = 15 * SA_BT_PITCH * 2, SA_BT_HEAD = 4 * SA_BT_COPY;
+constexpr uint32_t SA_OFF_OST = SA_OFF_V + 2 * SA_TILE;            // 2 x [128][64] bf16 SW128 output staging (pair g -> buffer g & 1)
+// relative-position bias, compact: per head 2 copies (one per 4-byte alignment of a window row's start) of the reversed
+// 15 x 15 table, row pitch 16 bf16: the 64 values of a token row are 16 aligned runs of 4 (one per key quad)
+constexpr uint32_t SA_BT_PITCH = 16, SA_BT_COPY = 15 * SA_BT_PITCH * 2, SA_BT_HEAD = 2 * SA_BT_COPY;
 constexpr uint32_t SA_BIAS_BYTES = 6 * SA_BT_HEAD;
-constexpr uint32_t SA_OFF_BIAS = SA_OFF_OST + SA_TILE;
+constexpr uint32_t SA_OFF_BIAS = SA_OFF_OST + 2 * SA_TILE;
 constexpr uint32_t SA_OFF_BAR = SA_OFF_BIAS + SA_BIAS_BYTES;
 constexpr uint32_t SA_SMEM = SA_OFF_BAR + 256;  // the kernel has no static shared memory: the dynamic base is 1024-aligned (checked)
 static_assert(SA_SMEM <= 232448, "fused attention kernel exceeds the 227 KB shared-memory limit");
@@ -57,16 +57,17 @@ enum {
   AB_SFULL,     // [2] scores of head 0/1
   AB_PREADY = AB_SFULL + 2,  // [2] P of head 0/1 in TMEM (4 arrivals)
   AB_OFULL = AB_PREADY + 2,  // [2] O of head 0/1
-  AB_OSTAGED = AB_OFULL + 2, // output of pair g staged (8 arrivals)
-  AB_OSTFREE,                // staging drained by the TMA stores
-  AB_COUNT
+  AB_OSTAGED = AB_OFULL + 2,    // [2] output of pair g staged in buffer g & 1 (8 arrivals)
+  AB_OSTFREE = AB_OSTAGED + 2,  // [2] staging buffer drained by its TMA stores
+  AB_END = AB_OSTFREE + 2,
+  AB_COUNT = AB_END
 };
 
 struct AttnKArgs {
-  const uint4* bias_tab;  // [6 heads][4 copies][15][20] bf16 (pack_attn_fused_host), times log2(e)
+  const uint4* bias_tab;  // [6 heads][2 copies][15][16] bf16 (pack_attn_fused_host), times log2(e)
   int B, H, W, shift;
   int nwx, nwy, n_windows, n_tiles;
-  long long* dbg;  // optional phase timestamps (developer diagnostics): [CTA][g < 96][8]
+  long long* dbg;  // optional phase timestamps (developer diagnostics): [CTA][g < 96][16]: 0..5 epilogue warp 4, 8..13 MMA issuer, 14..15 store warp
 };
 
 __device__ __forceinline__ uint32_t sa_sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -119,7 +120,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
     prefetch_tmap(&tmW);
     for (int i = 0; i < AB_COUNT; ++i) {
       int cnt = 1;
-      if (i == AB_OPREADY || i == AB_OSTAGED) cnt = 8;
+      if (i == AB_OPREADY || i == AB_OSTAGED || i == AB_OSTAGED + 1) cnt = 8;
       if (i == AB_PREADY || i == AB_PREADY + 1) cnt = 4;
       if (i >= AB_WEMPTY && i < AB_WEMPTY + SA_WSLOTS) cnt = CL;  // released by the MMA issuer of every CTA of the cluster
       mbar_init(bar(i), cnt);
@@ -145,70 +146,45 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
   const uint32_t tACC = tmem_base, tS[2] = {tmem_base + 192, tmem_base + 320}, tO = tmem_base + 448;
 
   if (warp == 0) {
-    // =========================== activation loads + output stores ===========================
-    if (lane == 0) {
-      auto load_item = [&](int it) {
+    // =========================== output stores: lane = (window, x half) of the pair's staging tile ===========================
+    // (one thread needs ~500 cycles to issue a TMA store: four lanes issue their boxes with the same instruction)
+    for (int g = 0; g < G; ++g) {
+      const int it = g / 3, hp = g - 3 * it;
+      mbar_wait_warp(bar(AB_OSTAGED + (g & 1)), ((uint32_t)g >> 1) & 1u, lane);
+      long long* dbg = (a.dbg && lane == 0 && g < 96) ? a.dbg + 16 * ((size_t)blockIdx.x * 96 + g) : nullptr;
+      if (dbg) dbg[14] = clock64();
+      if (lane < 4) {
+        const int w = lane >> 1, hh = lane & 1;
         const int tile = blockIdx.x + it * gridDim.x;
-        mbar_expect_tx(bar(AB_XNFULL), 3 * SA_TILE);
-        for (int w = 0; w < 2; ++w) {
-          const WinPos p = win_pos(a, 2 * tile + w);
-          for (int hh = 0; hh < 2; ++hh) {
-            const int x = (p.x0 + 4 * hh) % a.W;
-            const uint32_t row_off = (uint32_t)(64 * w + 32 * hh) * 128u;
-            for (int kb = 0; kb < 3; ++kb) {
-              const uint32_t dst = sbase + SA_OFF_XN + kb * SA_TILE + row_off;
-              if (!p.ywrap) {
-                tma_load_4d(dst, &tmX8, bar(AB_XNFULL), kb * 64, x, p.y0, p.b);
-              } else {  // rows ty 0..3 at the bottom edge, ty 4..7 wrapped to the top
-                tma_load_4d(dst, &tmX4, bar(AB_XNFULL), kb * 64, x, p.y0, p.b);
-                tma_load_4d(dst + 16 * 128, &tmX4, bar(AB_XNFULL), kb * 64, x, 0, p.b);
-              }
-            }
-          }
-        }
-      };
-      auto store_pair = [&](int it, int hp) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        for (int w = 0; w < 2; ++w) {
-          const WinPos p = win_pos(a, 2 * tile + w);
-          if (!p.valid) continue;
-          for (int hh = 0; hh < 2; ++hh) {
-            const int x = (p.x0 + 4 * hh) % a.W;
-            const uint32_t src = sbase + SA_OFF_OST + (uint32_t)(64 * w + 32 * hh) * 128u;
-            if (!p.ywrap) {
-              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO8), "r"(src),
-                           "r"(hp * 64), "r"(x), "r"(p.y0), "r"(p.b)
-                           : "memory");
-            } else {
-              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO4), "r"(src),
-                           "r"(hp * 64), "r"(x), "r"(p.y0), "r"(p.b)
-                           : "memory");
-              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO4),
-                           "r"(src + 16 * 128), "r"(hp * 64), "r"(x), "r"(0), "r"(p.b)
-                           : "memory");
-            }
+        const WinPos p = win_pos(a, 2 * tile + w);
+        if (p.valid) {
+          const int x = (p.x0 + 4 * hh) % a.W;
+          const uint32_t src = sbase + SA_OFF_OST + (uint32_t)(g & 1) * SA_TILE + (uint32_t)(64 * w + 32 * hh) * 128u;
+          if (!p.ywrap) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO8), "r"(src),
+                         "r"(hp * 64), "r"(x), "r"(p.y0), "r"(p.b)
+                         : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO4), "r"(src),
+                         "r"(hp * 64), "r"(x), "r"(p.y0), "r"(p.b)
+                         : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmO4),
+                         "r"(src + 16 * 128), "r"(hp * 64), "r"(x), "r"(0), "r"(p.b)
+                         : "memory");
           }
         }
         bulk_commit();
-      };
-      if (my_tiles > 0) load_item(0);
-      for (int g = 0; g < G; ++g) {
-        const int it = g / 3, hp = g - 3 * it;
-        mbar_wait(bar(AB_OSTAGED), (uint32_t)g & 1u);
-        store_pair(it, hp);
-        bulk_wait_read<0>();
-        mbar_arrive(bar(AB_OSTFREE));
-        if (hp == 0 && it + 1 < my_tiles) {  // the QKV MMAs of the third pair release the input tile about now
-          mbar_wait(bar(AB_XNEMPTY), (uint32_t)it & 1u);
-          load_item(it + 1);
-        }
+        bulk_wait_read<0>();  // ~3.8k cycles after the staging was published; the other buffer takes the next pair meanwhile
       }
-      bulk_wait_all();
+      __syncwarp();
+      if (dbg) dbg[15] = clock64();
+      if (lane == 0) mbar_arrive(bar(AB_OSTFREE + (g & 1)));
     }
-  } else if (warp < 3) {
-    // =========================== weight producers (even / odd k-blocks) ===========================
+    if (lane < 4) bulk_wait_all();
+  } else if (warp == 1) {
+    // =========================== weight producer ===========================
     if (lane == 0) {
-      for (int e = warp - 1; e < 3 * G; e += 2) {
+      for (int e = 0; e < 3 * G; ++e) {
         const int g = e / 3, kb = e - 3 * g, hp = g % 3;
         const int s = e % SA_WSLOTS;
         mbar_wait(bar(AB_WEMPTY + s), (((uint32_t)e / SA_WSLOTS) & 1u) ^ 1u);
@@ -219,6 +195,32 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         else
           tma_load_2d(sbase + SA_OFF_W + s * SA_WSLOT, &tmW, bar(AB_WFULL + s), kb * 64, hp * 192);
       }
+    }
+  } else if (warp == 2) {
+    // =========================== activation loads: lane = (window, x half) of the item ===========================
+    // The next item's input is requested the moment the last projection of this item has read the tile (XNEMPTY); issued
+    // from the store thread it arrived ~1.8k cycles after the first projection of the item wanted it.
+    for (int it = 0; it < my_tiles; ++it) {
+      if (it > 0) mbar_wait_warp(bar(AB_XNEMPTY), (uint32_t)(it - 1) & 1u, lane);
+      if (lane == 0) mbar_expect_tx(bar(AB_XNFULL), 3 * SA_TILE);
+      __syncwarp();
+      if (lane < 4) {
+        const int w = lane >> 1, hh = lane & 1;
+        const int tile = blockIdx.x + it * gridDim.x;
+        const WinPos p = win_pos(a, 2 * tile + w);
+        const int x = (p.x0 + 4 * hh) % a.W;
+        const uint32_t row_off = (uint32_t)(64 * w + 32 * hh) * 128u;
+        for (int kb = 0; kb < 3; ++kb) {
+          const uint32_t dst = sbase + SA_OFF_XN + kb * SA_TILE + row_off;
+          if (!p.ywrap) {
+            tma_load_4d(dst, &tmX8, bar(AB_XNFULL), kb * 64, x, p.y0, p.b);
+          } else {  // rows ty 0..3 at the bottom edge, ty 4..7 wrapped to the top
+            tma_load_4d(dst, &tmX4, bar(AB_XNFULL), kb * 64, x, p.y0, p.b);
+            tma_load_4d(dst + 16 * 128, &tmX4, bar(AB_XNFULL), kb * 64, x, 0, p.b);
+          }
+        }
+      }
+      __syncwarp();
     }
   } else if (warp == 3) {
     // =========================== MMA issuer ===========================
@@ -242,31 +244,41 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         umma_commit(bar(AB_QKVFULL));
         if (g % 3 == 2) umma_commit(bar(AB_XNEMPTY));  // last reader of this item's input tile
       };
-      mbar_wait(bar(AB_XNFULL), 0);
-      tc_fence_after();
-      proj(0);
-      for (int g = 0; g < G; ++g) {
-        const uint32_t ph = (uint32_t)g & 1u;
-        mbar_wait(bar(AB_OPREADY), ph);  // q, k, v of pair g staged; accumulator drained
-        tc_fence_after();
+      auto scores = [&](int h) {  // S_h = q_h k_h^T over all 128 keys of the item (K = 32: bytes [64h, 64h+64) of a row)
         const uint64_t qd = umma_desc_sw128(sbase + SA_OFF_Q), kd = umma_desc_sw128(sbase + SA_OFF_K);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // S_h = q_h k_h^T over all 128 keys of the item (K = 32: bytes [64h, 64h+64) of a row)
-#pragma unroll
-          for (int k = 0; k < 2; ++k) umma<false>(tS[h], qd + 4 * h + 2 * k, kd + 4 * h + 2 * k, IDESC_S, k ? 1u : 0u);
-          umma_commit(bar(AB_SFULL + h));
+        for (int k = 0; k < 2; ++k) umma<false>(tS[h], qd + 4 * h + 2 * k, kd + 4 * h + 2 * k, IDESC_S, k ? 1u : 0u);
+        umma_commit(bar(AB_SFULL + h));
+      };
+      auto proj_next = [&](int g) {
+        if (g >= G) return;
+        if (g % 3 == 0) {
+          mbar_wait(bar(AB_XNFULL), (uint32_t)(g / 3) & 1u);
+          tc_fence_after();
         }
-        if (g + 1 < G) {  // next pair's projection runs under this pair's softmax
-          if ((g + 1) % 3 == 0) {
-            mbar_wait(bar(AB_XNFULL), (uint32_t)((g + 1) / 3) & 1u);
-            tc_fence_after();
-          }
-          proj(g + 1);
-        }
+        proj(g);
+      };
+      // Issue order per pair: scores(g), projection(g+1), P.V(g).  (Tried: P.V_h(g) -> scores_h(g+1) interleaved with the
+      // projection last, so that the next softmax starts earlier: pair period 4.9k -> 5.2k cycles, the projection then
+      // completes after the epilogue warps come back for it.)
+      proj_next(0);
+      for (int g = 0; g < G; ++g) {
+        const uint32_t ph = (uint32_t)g & 1u;
+        long long* dbg = (a.dbg && g < 96) ? a.dbg + 16 * ((size_t)blockIdx.x * 96 + g) : nullptr;
+        if (dbg) dbg[8] = clock64();
+        mbar_wait(bar(AB_OPREADY), ph);  // q, k, v of pair g staged; accumulator drained
+        tc_fence_after();
+        if (dbg) dbg[9] = clock64();
+        scores(0);
+        scores(1);
+        if (dbg) dbg[10] = clock64();
+        proj_next(g + 1);  // runs under this pair's softmax
+        if (dbg) dbg[11] = clock64();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // O_h = P_h v_h: A = P (TMEM, block-diagonal over the two windows), B = V_h MN-major
           mbar_wait(bar(AB_PREADY + h), ph);
           tc_fence_after();
+          if (dbg) dbg[12 + h] = clock64();
           const uint64_t vd = umma_desc_mn_sw64(sbase + SA_OFF_V + (uint32_t)(g & 1) * SA_TILE + h * 8192);
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // 16 keys per step: 8 packed columns of P, 16 rows (1 KB) of V
@@ -291,19 +303,21 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
     uint8_t* sO = smem + SA_OFF_OST;
     // this token's window coordinates (order r = (tx / 4) * 32 + ty * 4 + tx % 4) and its copy of the bias table
     const int yi = (ri & 31) >> 2, xi = (ri >> 5) * 4 + (ri & 3);
-    const int bt_s = (7 - xi) & 3;
-    const uint8_t* sBiasRow = smem + SA_OFF_BIAS + bt_s * SA_BT_COPY + (7 - yi) * (SA_BT_PITCH * 2) + (7 - xi + ((4 - bt_s) & 3)) * 2;
+    const int bt_s = (7 - xi) & 1;
+    const uint8_t* sBiasRow = smem + SA_OFF_BIAS + bt_s * SA_BT_COPY + (7 - yi) * (SA_BT_PITCH * 2) + (7 - xi + bt_s) * 2;
     constexpr float kMask = -100.0f * 1.4426950408889634f;
     bool yflag = false, xflag = false;
 
     // output of head `grp` of pair gg: O / l -> bf16 -> staging (runs one pair late, under the next pair's MMAs)
-    auto out_epilogue = [&](int gg, float inv_l) {
+    auto out_epilogue = [&](int gg, float inv_l, long long* dbg) {
       mbar_wait_warp(bar(AB_OFULL + grp), (uint32_t)gg & 1u, lane);
       tc_fence_after();
+      if (dbg) dbg[6] = clock64();
       uint32_t raw[32];
       tmem_ld32_nowait(tlane + (tO - tmem_base) + 32 * grp, raw);
-      if (gg > 0) mbar_wait_warp(bar(AB_OSTFREE), ((uint32_t)gg & 1u) ^ 1u, lane);  // stores of pair gg-1 have read the staging
+      if (gg > 1) mbar_wait_warp(bar(AB_OSTFREE + (gg & 1)), (((uint32_t)gg >> 1) & 1u) ^ 1u, lane);  // stores of pair gg-2 have read this buffer
       tmem_wait_ld();
+      if (dbg) dbg[7] = clock64();
       const f32x2 il = f2_splat(inv_l);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -312,7 +326,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         v.y = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 2], raw[8 * j + 3]), il));
         v.z = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 4], raw[8 * j + 5]), il));
         v.w = f2_to_bf16x2(f2_mul(f2_pack_u(raw[8 * j + 6], raw[8 * j + 7]), il));
-        *reinterpret_cast<uint4*>(sO + sa_sw128(row, 4 * grp + j)) = v;
+        *reinterpret_cast<uint4*>(sO + (gg & 1) * SA_TILE + sa_sw128(row, 4 * grp + j)) = v;
       }
     };  // the caller publishes the staging (fence.proxy.async + arrive on AB_OSTAGED) together with its own smem writes
     // QKV epilogue of one 32-column chunk: bf16 into the operand tile `dst_of(chunk j)` selects.  The qkv bias is already in
@@ -341,7 +355,7 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
         yflag = wy == a.nwy - 1;
         xflag = wx == a.nwx - 1;
       }
-      long long* dbg = (a.dbg && ew == 0 && lane == 0 && g < 96) ? a.dbg + 8 * ((size_t)blockIdx.x * 96 + g) : nullptr;
+      long long* dbg = (a.dbg && ew == 0 && lane == 0 && g < 96) ? a.dbg + 16 * ((size_t)blockIdx.x * 96 + g) : nullptr;
       if (dbg) dbg[0] = clock64();
 
       // ---------------- QKV epilogue: bf16 operand tiles (V into buffer g & 1: P.V of pair g-1 may still run) ----------------
@@ -372,10 +386,10 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       if (dbg) dbg[2] = clock64();
       // ---------------- output of the previous pair (its P.V ran under this pair's QKV epilogue) ----------------
       if (g > 0) {
-        out_epilogue(g - 1, inv_l_prev);
+        out_epilogue(g - 1, inv_l_prev, dbg);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(AB_OSTAGED));
+        if (lane == 0) mbar_arrive(bar(AB_OSTAGED + ((g - 1) & 1)));
       }
       if (dbg) dbg[3] = clock64();
 
@@ -389,8 +403,9 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint8_t* p0 = brow + ((2 * c) & 7) * (SA_BT_PITCH * 2) + (c >> 2) * 8;
-          const uint2 r0 = *reinterpret_cast<const uint2*>(p0), r1 = *reinterpret_cast<const uint2*>(p0 + SA_BT_PITCH * 2);
-          bq[c] = make_uint4(r0.x, r0.y, r1.x, r1.y);
+          const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p0);
+          const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p0 + SA_BT_PITCH * 2);
+          bq[c] = make_uint4(q0[0], q0[1], q1[0], q1[1]);
         }
       }
       mbar_wait_warp(bar(AB_SFULL + grp), ph, lane);
@@ -462,11 +477,11 @@ swin_attn_kernel(const __grid_constant__ CUtensorMap tmX8, const __grid_constant
       if (dbg) dbg[5] = clock64();
     }
     if (G > 0) {
-      out_epilogue(G - 1, inv_l_prev);
+      out_epilogue(G - 1, inv_l_prev, nullptr);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(AB_OSTAGED));
+      if (lane == 0) mbar_arrive(bar(AB_OSTAGED + ((G - 1) & 1)));
     }
   }
 
@@ -485,14 +500,14 @@ int launch_swin_attn_fused(const AttnFusedArgs& f, cudaStream_t s) {
   SSR_CHECK(f.H % 8 == 0 && f.W % 8 == 0, SSR_E_INVALID, "swin_attn: %dx%d not a multiple of the 8x8 window", f.H, f.W);
   SSR_CHECK(f.shift == 0 || f.shift == 4, SSR_E_INVALID, "swin_attn: shift %d not in {0, 4}", f.shift);
   SSR_CHECK(f.ld_x == 192 && f.ld_o == 192, SSR_E_INVALID, "swin_attn: leading dims must be 192 (got %d / %d)", f.ld_x, f.ld_o);
-  // developer A/B switches: STUDIOSR_B200_ATTN_POLY=0 keeps every softmax exponential on MUFU, STUDIOSR_B200_ATTN_CLUSTER=1
-  // switches the weight multicast off
-  static int poly = -1, cl = 2;
+  // developer A/B switches: STUDIOSR_B200_ATTN_POLY=0 keeps every softmax exponential on MUFU, STUDIOSR_B200_ATTN_CLUSTER=2
+  // switches the cluster-of-2 weight multicast on (measured neutral: profiles/r02_cluster_multicast.txt)
+  static int poly = -1, cl = 1;
   if (poly < 0) {
     const char* e = getenv("STUDIOSR_B200_ATTN_POLY");
     poly = (e && e[0] == '0') ? 0 : SA_POLY_DEFAULT;
     const char* c = getenv("STUDIOSR_B200_ATTN_CLUSTER");
-    cl = (c && c[0] == '1') ? 1 : 2;
+    cl = (c && c[0] == '2') ? 2 : 1;
     SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
     SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel<SA_POLY_DEFAULT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));
     SSR_CUDA(cudaFuncSetAttribute(swin_attn_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA_SMEM));

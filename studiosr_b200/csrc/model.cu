@@ -278,15 +278,15 @@ int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* tabl
     }
   // relative-position bias (swinir.py:57-67, 92-95), compact: B[i][j] = T[yi - yj + 7][xi - xj + 7] = R[7 - yi + yj][7 - xi + xj]
   // with R the table reversed in both axes, so the 8 x 8 keys of a window seen from token (yi, xi) are an 8 x 8 sub-block of R
-  // and every key quad (4 consecutive xj) is a contiguous run.  Four copies, shifted by 0..3 elements, make every run start
-  // 8-byte aligned: copy s serves tokens with (7 - xi) % 4 == s and stores R[a][b] at [a][b + (4 - s) % 4], row pitch 20.
+  // and every key quad (4 consecutive xj) is a contiguous run.  Two copies, shifted by 0 / 1 element, make every run start
+  // 4-byte aligned: copy s serves tokens with (7 - xi) % 2 == s and stores R[a][b] at [a][b + s], row pitch 16.
   __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(bias_tab);
   for (size_t i = 0; i < kAttnBiasBytes / 2; ++i) bt[i] = __float2bfloat16_rn(0.0f);
   for (int hd = 0; hd < heads; ++hd)
-    for (int sft = 0; sft < 4; ++sft)
+    for (int sft = 0; sft < 2; ++sft)
       for (int a = 0; a < 15; ++a)
         for (int b = 0; b < 15; ++b)
-          bt[((size_t)(hd * 4 + sft) * 15 + a) * 20 + b + ((4 - sft) & 3)] =
+          bt[((size_t)(hd * 2 + sft) * 15 + a) * 16 + b + sft] =
               __float2bfloat16_rn(table[(size_t)((14 - a) * 15 + (14 - b)) * heads + hd] * log2e);
   return SSR_OK;
 }

@@ -225,12 +225,12 @@ struct AttnFusedArgs {
   int ld_o;
   const void* Whp;       // bf16 [3 pairs][192][192]: rows q h0 h1 | k h0 h1 | v h0 h1 (32 each); q rows x d^-1/2 log2(e);
                          // columns C, C+1 = the qkv bias of the row as hi + lo bf16 parts
-  const void* bias_tab;  // bf16 [6 heads][4 shifted copies][15][20]: reversed relative-position bias table x log2(e)
+  const void* bias_tab;  // bf16 [6 heads][2 shifted copies][15][16]: reversed relative-position bias table x log2(e)
   int B, H, W, shift;
   int C, d;  // un-padded sizes (accounting)
 };
 int launch_swin_attn_fused(const AttnFusedArgs& a, cudaStream_t s);
-constexpr size_t kAttnWhpBytes = 3 * 192 * 192 * 2, kAttnBiasBytes = 6 * 4 * 15 * 20 * 2;
+constexpr size_t kAttnWhpBytes = 3 * 192 * 192 * 2, kAttnBiasBytes = 6 * 2 * 15 * 16 * 2;
 // host-side packing of the two buffers above from the reference parameters (qkv.weight [3C][C], qkv.bias [3C],
 // relative_position_bias_table [225][heads]); heads must be 6, C / heads <= 32 and C <= 190 (two pad channels for the bias)
 int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* table, int C, int heads, void* Whp, void* bias_tab);
