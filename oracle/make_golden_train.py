@@ -2,13 +2,14 @@
 (imported from /root/reference through oracle/ref_shim.py): model.train(), fp32, `loss = nn.L1Loss()(model(x), y)`,
 `loss.backward()` exactly as trainer.py:45,101-104 does, with drop_path_rate = 0 so the step is deterministic.
 
-    python -m oracle.make_golden_train
+    python -m oracle.make_golden_train [case ...]      (no names: every case; names: only those, the rest of meta_train.json is kept)
 
 Stored per case: the loss and, for every parameter, the gradient's L2 norm plus a strided sample of its entries
 (every `stride`-th element of the flattened gradient) -- enough to pin the oracle's autograd (tests/test_oracle.py) and,
 through it, the CUDA backward (tests/test_gpu_train.py) without committing megabytes of gradients."""
 import json
 import os
+import sys
 
 import numpy as np
 import torch
@@ -23,6 +24,7 @@ CASES = {
     # name: (arch, cfg, weight seed, input shape, input seed)
     "train_edsr_tiny_x4_2x24x20": ("edsr", dict(synth.EDSR_TINY), 5, (2, 3, 24, 20), 77),
     "train_edsr_tiny_x3_1x12x16": ("edsr", dict(synth.EDSR_TINY, scale=3, n_resblocks=1), 5, (1, 3, 12, 16), 77),
+    "train_rcan_tiny_x4_2x12x20": ("rcan", dict(synth.RCAN_TINY), 9, (2, 3, 12, 20), 55),
     "train_swinir_tiny_x4_2x16x24": ("swinir", synth.swinir_config(**synth.SWINIR_TINY), 11, (2, 3, 16, 24), 101),
     "train_swinir_tiny_x4_pad_1x20x28": ("swinir", synth.swinir_config(**synth.SWINIR_TINY), 11, (1, 3, 20, 28), 101),
     "train_swinir_c180_x4_1x16x16": ("swinir", synth.swinir_config(embed_dim=180, depths=[2, 2], num_heads=[6, 6]), 11,
@@ -46,10 +48,19 @@ def main() -> None:
     ref = import_reference()
     models = ref.models
     meta = {}
+    only = set(sys.argv[1:])
+    if only:
+        with open(os.path.join(OUT, "meta_train.json")) as f:
+            meta = json.load(f)["cases"]
     for name, (arch, cfg, wseed, shape, xseed) in CASES.items():
+        if only and name not in only:
+            continue
         if arch == "edsr":
             m = models.EDSR(**cfg)
             m.load_state_dict(synth.edsr_weights(cfg, wseed), strict=True)
+        elif arch == "rcan":
+            m = models.RCAN(**cfg)
+            m.load_state_dict(synth.rcan_weights(cfg, wseed), strict=True)
         else:
             m = models.SwinIR(drop_path_rate=DROP_RATE if arch == "swinir_dp" else 0.0, **cfg)
             m.load_state_dict(synth.swinir_weights(cfg, wseed), strict=True)

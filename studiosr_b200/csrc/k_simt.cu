@@ -928,6 +928,13 @@ __global__ void __launch_bounds__(256) ca_apply_kernel(const CaArgs a) {
     gate[c] = g;  // padded channels: t is zero there anyway
   }
   __syncthreads();
+  if (a.save_gate && blockIdx.x == 0) {  // training forward: keep the MLP's intermediates for the backward
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      a.save_pool[(size_t)b * a.C + c] = pooled[c];
+      a.save_gate[(size_t)b * a.C + c] = gate[c];
+    }
+    for (int r = threadIdx.x; r < a.R; r += blockDim.x) a.save_hid[(size_t)b * a.R + r] = hid[r];
+  }
   const int chunk = (a.HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * chunk, p1 = min(a.HW, p0 + chunk);
   const int c4n = a.CP / 4;
@@ -973,6 +980,104 @@ int launch_channel_attention(const CaArgs& a, cudaStream_t s) {
     ProfScope prof("ca_apply", 0.0, px * a.C * ((a.elem_t == 2 ? 2 : 4) + 4 + 4 + (a.out_T ? a.elem : 0)), s);
     const int blocks = a.HW >= 4096 ? 64 : (a.HW + 63) / 64;
     ca_apply_kernel<<<dim3(blocks, a.B), 256, 0, s>>>(a);
+    count_launch();
+  }
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
+// ---- channel attention backward (training; see CaBwdArgs) ----
+// stage 1: partial[b][split][c] = sum over a pixel slab of G * t
+__global__ void __launch_bounds__(256) ca_bwd_reduce_kernel(const float* G, const __nv_bfloat16* t, int ld, int HW, int C, int nsplit,
+                                                            float* partial) {
+  __shared__ float red[256];
+  const int b = blockIdx.y, split = blockIdx.x;
+  const int chunk = (HW + nsplit - 1) / nsplit;
+  const int p0 = split * chunk, p1 = min(HW, p0 + chunk);
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
+    float acc = 0.0f;
+    if (c < C)
+      for (int p = p0 + pl; p < p1; p += 4) {
+        const size_t i = ((size_t)b * HW + p) * ld + c;
+        acc = fmaf(G[i], __bfloat162float(t[i]), acc);
+      }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < C)
+      partial[((size_t)b * nsplit + split) * C + c] = red[threadIdx.x] + red[threadIdx.x + 64] + red[threadIdx.x + 128] + red[threadIdx.x + 192];
+    __syncthreads();
+  }
+}
+// stage 2 (one block; the samples are walked in order, so the parameter gradients are deterministic): the gate MLP's backward
+__global__ void __launch_bounds__(256) ca_bwd_gate_kernel(const CaBwdArgs a) {
+  __shared__ float dz2[256], dz1[64];
+  for (int b = 0; b < a.B; ++b) {
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      float ds = 0.0f;
+      for (int k = 0; k < a.nsplit; ++k) ds += a.partial[((size_t)b * a.nsplit + k) * a.C + c];
+      const float g = a.gate[(size_t)b * a.C + c];
+      dz2[c] = ds * g * (1.0f - g);
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < a.R; r += blockDim.x) {
+      float dh = 0.0f;
+      for (int c = 0; c < a.C; ++c) dh = fmaf(a.W2[c * a.R + r], dz2[c], dh);
+      dz1[r] = a.hid[(size_t)b * a.R + r] > 0.0f ? dh : 0.0f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      float dp = 0.0f;
+      for (int r = 0; r < a.R; ++r) dp = fmaf(a.W1[r * a.C + c], dz1[r], dp);
+      a.dpool[(size_t)b * a.C + c] = dp / (float)a.HW;
+      if (a.db2) a.db2[c] = (b ? a.db2[c] : 0.0f) + dz2[c];
+    }
+    if (a.db1)
+      for (int r = threadIdx.x; r < a.R; r += blockDim.x) a.db1[r] = (b ? a.db1[r] : 0.0f) + dz1[r];
+    for (int e = threadIdx.x; e < a.C * a.R; e += blockDim.x) {  // every entry is owned by one thread across all samples
+      if (a.dW2) {
+        const int c = e / a.R, r = e - c * a.R;
+        a.dW2[e] = (b ? a.dW2[e] : 0.0f) + dz2[c] * a.hid[(size_t)b * a.R + r];
+      }
+      if (a.dW1) {
+        const int r = e / a.C, c = e - r * a.C;
+        a.dW1[e] = (b ? a.dW1[e] : 0.0f) + dz1[r] * a.pool[(size_t)b * a.C + c];
+      }
+    }
+    __syncthreads();
+  }
+}
+// stage 3: dt = G * gate + dpool (bf16; padded channels zero)
+__global__ void __launch_bounds__(256) ca_bwd_apply_kernel(const CaBwdArgs a) {
+  const int c4n = a.CP / 4;
+  const size_t n = (size_t)a.B * a.HW * c4n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = e / c4n;
+    const int c = (int)(e - m * c4n) * 4, b = (int)(m / a.HW);
+    const float4 g = *reinterpret_cast<const float4*>(a.G + m * a.ld + c);
+    float o[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o[i] = c + i < a.C ? fmaf(o[i], a.gate[(size_t)b * a.C + c + i], a.dpool[(size_t)b * a.C + c + i]) : 0.0f;
+    uint2 pk;
+    pk.x = pack_bf16x2(o[0], o[1]);
+    pk.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.dt) + m * a.ld_dt + c) = pk;
+  }
+}
+int launch_channel_attention_bwd(const CaBwdArgs& a, cudaStream_t s) {
+  SSR_CHECK(a.C <= 256 && a.R <= 64 && a.CP % 4 == 0 && a.nsplit >= 1 && a.ld % 4 == 0 && a.ld_dt % 4 == 0, SSR_E_INVALID,
+            "channel attention backward: C=%d R=%d", a.C, a.R);
+  const double px = (double)a.B * a.HW;
+  {
+    ProfScope prof("ca_bwd", 0.0, px * a.C * (4 + 2 + 4 + 2), s);
+    ca_bwd_reduce_kernel<<<dim3(a.nsplit, a.B), 256, 0, s>>>(a.G, reinterpret_cast<const __nv_bfloat16*>(a.t), a.ld, a.HW, a.C, a.nsplit,
+                                                            a.partial);
+    count_launch();
+    ca_bwd_gate_kernel<<<1, 256, 0, s>>>(a);
+    count_launch();
+    const size_t n = (size_t)a.B * a.HW * (a.CP / 4);
+    ca_bwd_apply_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, s>>>(a);
     count_launch();
   }
   SSR_CUDA(cudaGetLastError());

@@ -253,8 +253,27 @@ struct CaArgs {
   void* out_T;     // T-typed copy for the next conv
   int ld_T, elem, round_tf32;
   float scale;  // out = res + t * gate * scale (1 for RCAN, conv_scale for HAT's CAB)
+  // training forward only (null otherwise): the gate MLP's intermediates, kept for launch_channel_attention_bwd
+  float *save_pool, *save_hid, *save_gate;  // fp32 [B][C], [B][R], [B][C]
 };
 int launch_channel_attention(const CaArgs& a, cudaStream_t s);
+
+// backward of out = res + t * sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2) (common.py:156-170 inside rcan.py:21-24):
+//   dt = G * gate + W1^T dz1 / HW,  dz1 = relu'(.) * W2^T dz2,  dz2 = gate (1 - gate) * sum_hw G t   (+ the four parameter gradients)
+struct CaBwdArgs {
+  const float* G;   // fp32 [B][HW][ld]: dL/d(out) (also dL/d(res): the caller keeps it)
+  const void* t;    // bf16 [B][HW][ld]: saved output of the second conv
+  int ld, B, HW, C, CP, R;
+  const float *W1, *W2;                 // fp32 [R][C], [C][R] (current values)
+  const float *pool, *hid, *gate;       // saved by the training forward
+  float* partial;                       // scratch [B][nsplit][C]
+  int nsplit;
+  float* dpool;                         // scratch [B][C]
+  float *dW1, *db1, *dW2, *db2;         // parameter gradients (PyTorch layouts, overwritten; any may be null)
+  void* dt;                             // bf16 [B][HW][ld_dt]
+  int ld_dt;
+};
+int launch_channel_attention_bwd(const CaBwdArgs& a, cudaStream_t s);
 
 // weight gradient of a conv3x3 / linear layer (k_wgrad_tc.cu): dWp[n][tap][c] += alpha * sum_p dY[p][n] X[p+off(tap)][c]
 struct WgradArgs {

@@ -36,6 +36,9 @@ struct LnT {
   const LNp* p = nullptr;
   int gi = -1, bi = -1;
 };
+struct CaT {  // channel-attention gate of an RCAB: bound-parameter indices
+  int w1 = -1, b1 = -1, w2 = -1, b2 = -1;
+};
 struct BlockT {
   LnT n1, n2;
   LinT qkv, proj, fc1, fc2;
@@ -64,6 +67,10 @@ struct ssr_train_state {
   size_t head_dwp = 0, head_dbp = 0;
   std::vector<int> e_res_a, e_res_b, e_up;  // indices into convs
   int e_body_tail = -1, e_last = -1;
+  // RCAN (head / body tail / upsampler / last conv share the EDSR fields)
+  std::vector<int> r_a, r_b, r_gt;  // indices into convs: the two convs of every RCAB (group-major), the conv closing each group
+  std::vector<ssr::CaT> r_ca;
+  int pack_cap = 0;                 // entries the batched (un)pack launches may carry
   // SwinIR
   std::vector<std::vector<BlockT>> s_blocks;
   std::vector<int> s_conv;  // RSTB convs
@@ -533,6 +540,384 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
   return launch_deferred_reductions(&t->red, s);  // every bias gradient's second stage, one launch
 }
 
+
+// =============================================================================================
+// RCAN (rcan.py:39-77) training executor: EDSR's head / upsampler / reconstruction conv around residual groups of RCABs
+// (conv - ReLU - conv - channel attention, rcan.py:11-24)
+// =============================================================================================
+static int bind_rcan(ssr_model* m) {
+  ssr_train_state* t = m->train;
+  const ssr_model_config& c = m->cfg;
+  const int F = m->F, R = F / c.reduction;
+  size_t a2 = 0;
+  t->zero_bias_off = a2;
+  a2 += 4096 * 4;
+  t->head_w = find_idx(t, "head.0.weight", (int64_t)F * 27);
+  t->head_b = find_idx(t, "head.0.bias", F);
+  if (t->head_w < 0 || t->head_b < 0) return SSR_E_STATE;
+  t->head_dwp = t->dwp_floats;
+  t->dwp_floats += (size_t)m->FP * 9 * 64;
+  t->head_dbp = t->dwp_floats;
+  t->dwp_floats += (size_t)m->FP;
+  t->red_floats += (size_t)592 * m->FP + 64;
+  t->red_entries += 1;
+  char nm[96];
+  for (int g = 0; g < c.n_resgroups; ++g) {
+    for (int b = 0; b < c.n_resblocks; ++b) {
+      const int i = g * c.n_resblocks + b;
+      snprintf(nm, sizeof(nm), "body.%d.body.%d.body", g, b);
+      const std::string p(nm);
+      const int ia = add_conv(t, p + ".0", &m->res_a[i], F, F, &a2);
+      const int ib = add_conv(t, p + ".2", &m->res_b[i], F, F, &a2);
+      if (ia < 0 || ib < 0) return SSR_E_STATE;
+      t->r_a.push_back(ia);
+      t->r_b.push_back(ib);
+      CaT ca;
+      ca.w1 = find_idx(t, p + ".3.conv_du.0.weight", (int64_t)R * F);
+      ca.b1 = find_idx(t, p + ".3.conv_du.0.bias", R);
+      ca.w2 = find_idx(t, p + ".3.conv_du.2.weight", (int64_t)F * R);
+      ca.b2 = find_idx(t, p + ".3.conv_du.2.bias", F);
+      if (ca.w1 < 0 || ca.b1 < 0 || ca.w2 < 0 || ca.b2 < 0) return SSR_E_STATE;
+      t->r_ca.push_back(ca);
+    }
+    snprintf(nm, sizeof(nm), "body.%d.body.%d", g, c.n_resblocks);
+    const int ig = add_conv(t, nm, &m->grp_tail[g], F, F, &a2);
+    if (ig < 0) return SSR_E_STATE;
+    t->r_gt.push_back(ig);
+  }
+  snprintf(nm, sizeof(nm), "body.%d", c.n_resgroups);
+  t->e_body_tail = add_conv(t, nm, &m->body_tail, F, F, &a2);
+  if (t->e_body_tail < 0) return SSR_E_STATE;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    snprintf(nm, sizeof(nm), "tail.0.%d", (int)(2 * i));
+    const int iu = add_conv(t, nm, &m->up[i], m->up[i].N, F, &a2);
+    if (iu < 0) return SSR_E_STATE;
+    t->e_up.push_back(iu);
+  }
+  t->e_last = add_conv(t, "tail.1", &m->last_lin, 3, F, &a2);
+  if (t->e_last < 0) return SSR_E_STATE;
+  t->pack_cap = (int)t->convs.size() + 4 * (int)t->r_ca.size() + 16;
+  t->arena2_bytes = a2 + 1024;
+  SSR_CUDA(cudaMalloc(&t->arena2, t->arena2_bytes));
+  SSR_CUDA(cudaMemset(t->arena2, 0, t->arena2_bytes));
+  return SSR_OK;
+}
+
+struct RcanTrainWs {
+  void* xin64;
+  float *x0, *r, *gin;
+  std::vector<void*> S;        // bf16 copies of the stream: head output, every RCAB output, every group output
+  std::vector<void*> tmp, t2;  // per RCAB: ReLU output, second conv's output (bf16)
+  float* gates;                // per RCAB: pool [B][F] | gate [B][F] | hid [B][R]
+  size_t gate_stride;
+  float *ca_partial, *dpool;
+  int nsplit;
+  void* bt;
+  std::vector<void*> hr, ghr;
+  void *dy64, *gU;
+  float *G, *G2, *Gt;
+  void *Gb, *Dh, *Dt;
+  float* dwp;
+  float* partial;
+  float* red_pool;
+  RedEntry* red_dev;
+  PackEntry* pack_dev;
+};
+
+static size_t plan_rcan_train(const ssr_model* m, void* base, int B, int H, int W, RcanTrainWs* w) {
+  Carver c(base);
+  const size_t T = (size_t)B * H * W;
+  const int FP = m->FP, nb = m->cfg.n_resblocks, ng = m->cfg.n_resgroups, nblk = nb * ng, R = m->F / m->cfg.reduction;
+  w->xin64 = c.take(T * 64 * 2);
+  w->x0 = (float*)c.take(T * FP * 4);
+  w->r = (float*)c.take(T * FP * 4);
+  w->gin = (float*)c.take(T * FP * 4);
+  w->S.resize(1 + (size_t)ng * (nb + 1));
+  for (void*& p : w->S) p = c.take(T * FP * 2);
+  w->tmp.resize(nblk);
+  w->t2.resize(nblk);
+  for (int i = 0; i < nblk; ++i) {
+    w->tmp[i] = c.take(T * FP * 2);
+    w->t2[i] = c.take(T * FP * 2);
+  }
+  w->gate_stride = (size_t)B * (2 * m->F + R);
+  w->gates = (float*)c.take(w->gate_stride * nblk * 4);
+  w->nsplit = std::max(1, std::min(64, H * W / 256));
+  w->ca_partial = (float*)c.take((size_t)B * w->nsplit * m->F * 4);
+  w->dpool = (float*)c.take((size_t)B * m->F * 4);
+  w->bt = c.take(T * FP * 2);
+  size_t px = T, gu_max = 0;
+  w->hr.resize(m->up.size());
+  w->ghr.resize(m->up.size());
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    gu_max = std::max(gu_max, px * (size_t)m->up[i].NP);
+    px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
+    w->hr[i] = c.take(px * FP * 2);
+    w->ghr[i] = c.take(px * FP * 2);
+  }
+  w->dy64 = c.take(px * 64 * 2);
+  w->gU = c.take(gu_max * 2);
+  w->G = (float*)c.take(T * FP * 4);
+  w->G2 = (float*)c.take(T * FP * 4);
+  w->Gt = (float*)c.take(T * FP * 4);
+  w->Gb = c.take(T * FP * 2);
+  w->Dh = c.take(T * FP * 2);
+  w->Dt = c.take(T * FP * 2);
+  w->dwp = (float*)c.take(m->train->dwp_floats * 4);
+  w->partial = (float*)c.take(kTrainPartialFloats * 4);
+  w->red_pool = (float*)c.take(m->train->red_floats * 4);
+  w->red_dev = (RedEntry*)c.take((size_t)(m->train->red_entries + 8) * sizeof(RedEntry));
+  w->pack_dev = (PackEntry*)c.take((size_t)m->train->pack_cap * sizeof(PackEntry));
+  return c.off + 1024;
+}
+
+static int train_forward_rcan(ssr_model* m, const float* const* params, const float* x, float* y, int B, int h, int w, void* ws,
+                              size_t ws_bytes, cudaStream_t s) {
+  ssr_train_state* t = m->train;
+  const ssr_model_config& c = m->cfg;
+  RcanTrainWs W;
+  const size_t need = plan_rcan_train(m, ws, B, h, w, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "train workspace %zu B < required %zu B", ws_bytes, need);
+  const int FP = m->FP, F = m->F, R = F / c.reduction, nb = c.n_resblocks;
+  // ---- re-pack the (updated) fp32 master weights: forward + dgrad operand layouts, the gates' small matrices as they are ----
+  t->pack_host.clear();
+  push_copy(t, params[t->head_w], m->dev<float>(m->conv_first_w), F * 27);
+  push_copy(t, params[t->head_b], m->dev<float>(m->conv_first_b), F);
+  for (const ConvT& cv : t->convs) SSR_TRY(repack_conv(m, cv, params, s));
+  for (size_t i = 0; i < t->r_ca.size(); ++i) {
+    push_copy(t, params[t->r_ca[i].w1], m->dev<float>(m->ca[i].w1), R * F);
+    push_copy(t, params[t->r_ca[i].b1], m->dev<float>(m->ca[i].b1), R);
+    push_copy(t, params[t->r_ca[i].w2], m->dev<float>(m->ca[i].w2), F * R);
+    push_copy(t, params[t->r_ca[i].b2], m->dev<float>(m->ca[i].b2), F);
+  }
+  SSR_CHECK((int)t->pack_host.size() <= t->pack_cap, SSR_E_STATE, "train: pack list overflow");
+  SSR_TRY(launch_pack_batched(t->pack_host.data(), W.pack_dev, (int)t->pack_host.size(), s));
+  // ---- forward (rcan.py:68-77), every GEMM operand kept for the backward ----
+  SSR_TRY(launch_nchw3_to_nhwc64(x, W.xin64, B, h, w, 1.0f, m->sub_bias, s));
+  {
+    ConvFirstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = x; a.fh = h; a.fw = w; a.h = h; a.w = w; a.Hp = h; a.Wp = w; a.pad_mode = 2; a.B = B;
+    a.in_scale = 1.0f;
+    for (int i = 0; i < 3; ++i) a.in_shift[i] = m->sub_bias[i];
+    a.Wc = m->dev<float>(m->conv_first_w);
+    a.bias = m->dev<float>(m->conv_first_b);
+    a.Cout = F;
+    a.out_f32 = W.x0; a.ld_f32 = FP; a.out_T = W.S[0]; a.ld_T = FP; a.elem = 2;
+    SSR_TRY(launch_conv_first(a, s));
+  }
+  int k = 0;  // index of the stream state that feeds the next layer
+  const float* gcur = W.x0;
+  for (int g = 0; g < c.n_resgroups; ++g) {
+    const float* rcur = gcur;
+    for (int b = 0; b < nb; ++b, ++k) {  // RCAB (rcan.py:21-24)
+      const int i = g * nb + b;
+      GemmArgs ga = gemm_base(m, m->res_a[i], W.S[k], FP, B, h, w);
+      ga.act = ACT_RELU;
+      ga.out_T = W.tmp[i];
+      ga.ld_T = FP;
+      SSR_TRY(run_gemm(m, ga, s));
+      GemmArgs gb = gemm_base(m, m->res_b[i], W.tmp[i], FP, B, h, w);
+      gb.out_T = W.t2[i];
+      gb.ld_T = FP;
+      SSR_TRY(run_gemm(m, gb, s));
+      float* gs = W.gates + W.gate_stride * i;
+      CaArgs ca;
+      memset(&ca, 0, sizeof(ca));
+      ca.t = W.t2[i]; ca.elem_t = 2; ca.res = rcur; ca.ld = FP; ca.B = B; ca.HW = h * w; ca.C = F; ca.CP = FP; ca.R = R;
+      ca.W1 = m->dev<float>(m->ca[i].w1); ca.b1 = m->dev<float>(m->ca[i].b1);
+      ca.W2 = m->dev<float>(m->ca[i].w2); ca.b2 = m->dev<float>(m->ca[i].b2);
+      ca.partial = W.ca_partial; ca.nsplit = W.nsplit;
+      ca.out_f32 = W.r; ca.out_T = W.S[k + 1]; ca.ld_T = FP; ca.elem = 2;
+      ca.scale = 1.0f;
+      ca.save_pool = gs; ca.save_gate = gs + (size_t)B * F; ca.save_hid = gs + (size_t)2 * B * F;
+      SSR_TRY(launch_channel_attention(ca, s));
+      rcur = W.r;
+    }
+    // group tail conv + group skip (rcan.py:33-36)
+    GemmArgs gt = gemm_base(m, m->grp_tail[g], W.S[k], FP, B, h, w);
+    gt.res = gcur;
+    gt.ldres = FP;
+    gt.out_f32 = W.gin;
+    gt.ld_f32 = FP;
+    gt.out_T = W.S[k + 1];
+    gt.ld_T = FP;
+    SSR_TRY(run_gemm(m, gt, s));
+    gcur = W.gin;
+    ++k;
+  }
+  {  // body tail conv + long skip (rcan.py:72-73)
+    GemmArgs g = gemm_base(m, m->body_tail, W.S[k], FP, B, h, w);
+    g.res = W.x0;
+    g.ldres = FP;
+    g.out_T = W.bt;
+    g.ld_T = FP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  const void* cur = W.bt;
+  int H = h, Wd = w;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    GemmArgs g = gemm_base(m, m->up[i], cur, FP, B, H, Wd);
+    g.out_T = W.hr[i];
+    g.ld_T = FP;
+    SSR_TRY(run_gemm(m, g, s));
+    cur = W.hr[i];
+    H *= m->up[i].ps_r;
+    Wd *= m->up[i].ps_r;
+  }
+  GemmArgs g = gemm_base(m, m->last_lin, cur, FP, B, H, Wd);
+  g.out3_f32 = y;
+  g.crop_h = H;
+  g.crop_w = Wd;
+  for (int i = 0; i < 3; ++i) g.out_shift[i] = m->add_bias[i];
+  g.out_scale = 1.0f;
+  g.u8_scale = 1.0f;
+  return run_gemm(m, g, s);
+}
+
+static int train_backward_rcan(ssr_model* m, const float* const* params, const float* dy, float* const* grads, int B, int h, int w,
+                               void* ws, size_t ws_bytes, cudaStream_t s) {
+  ssr_train_state* t = m->train;
+  const ssr_model_config& c = m->cfg;
+  RcanTrainWs W;
+  const size_t need = plan_rcan_train(m, ws, B, h, w, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "train workspace %zu B < required %zu B", ws_bytes, need);
+  (void)params;
+  const int FP = m->FP, F = m->F, R = F / c.reduction, nb = c.n_resblocks, ng = c.n_resgroups;
+  const size_t T = (size_t)B * h * w;
+  red_begin(t, W.red_pool, W.red_dev);
+  SSR_CUDA(cudaMemsetAsync(W.dwp, 0, t->dwp_floats * 4, s));
+  int H = h * c.scale, Wd = w * c.scale;
+  SSR_TRY(launch_nchw_to_nhwc(dy, W.dy64, B, 3, H, Wd, 64, 2, 0, s));
+  const int nup = (int)m->up.size();
+  {  // tail.1 (rcan.py:66,75)
+    const ConvT& cv = t->convs[t->e_last];
+    const void* X = nup ? W.hr[nup - 1] : W.bt;
+    SSR_TRY(wgrad_conv(m, cv, W.dy64, X, FP, B, H, Wd, 1.0f, W.dwp, W.partial, grads, s));
+    GemmArgs g = dgrad_base(m, cv, W.dy64, B, H, Wd);
+    if (nup) {
+      g.out_T = W.ghr[nup - 1];
+      g.ld_T = FP;
+    } else {
+      g.out_f32 = W.Gt;
+      g.ld_f32 = FP;
+      g.out_T = W.Gb;
+      g.ld_T = FP;
+    }
+    SSR_TRY(launch_gemm_tc(g, 2, s));
+  }
+  for (int k = nup - 1; k >= 0; --k) {  // Upsampler (common.py:124-137): PixelShuffle backward, then the conv
+    const ConvT& cv = t->convs[t->e_up[k]];
+    const int r = m->up[k].ps_r;
+    H /= r;
+    Wd /= r;
+    SSR_TRY(launch_unshuffle(W.ghr[k], W.gU, B, H, Wd, F, r, FP, s));
+    const void* X = k ? W.hr[k - 1] : W.bt;
+    SSR_TRY(wgrad_conv(m, cv, W.gU, X, FP, B, H, Wd, 1.0f, W.dwp, W.partial, grads, s));
+    GemmArgs g = dgrad_base(m, cv, W.gU, B, H, Wd);
+    if (k) {
+      g.out_T = W.ghr[k - 1];
+      g.ld_T = FP;
+    } else {
+      g.out_f32 = W.Gt;
+      g.ld_f32 = FP;
+      g.out_T = W.Gb;
+      g.ld_T = FP;
+    }
+    SSR_TRY(launch_gemm_tc(g, 2, s));
+  }
+  // res = body(x) + x (rcan.py:72-73): Gt = dL/d(res) feeds the body's last conv and, through the long skip, the head output
+  int k = ng * (nb + 1);  // stream state that fed the layer being differentiated
+  float* Ga = W.G;        // dL/d(current stream state), fp32 ...
+  float* Gn = W.G2;
+  void* Gb = W.Dh;        // ... and its bf16 copy
+  void* Dh = W.Gb;        // scratch for the gradient at the ReLU
+  {
+    const ConvT& cv = t->convs[t->e_body_tail];
+    SSR_TRY(wgrad_conv(m, cv, W.Gb, W.S[k], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
+    GemmArgs g = dgrad_base(m, cv, W.Gb, B, h, w);
+    g.out_f32 = Ga;
+    g.ld_f32 = FP;
+    g.out_T = Gb;
+    g.ld_T = FP;
+    SSR_TRY(launch_gemm_tc(g, 2, s));
+  }
+  for (int g = ng - 1; g >= 0; --g) {  // ResidualGroup: out = conv(rcabs(x)) + x  (rcan.py:27-36)
+    {  // Ga = dL/d(out) stays for the group skip; the conv's input gradient goes to Gn
+      const ConvT& cv = t->convs[t->r_gt[g]];
+      --k;
+      SSR_TRY(wgrad_conv(m, cv, Gb, W.S[k], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
+      GemmArgs gg = dgrad_base(m, cv, Gb, B, h, w);
+      gg.out_f32 = Gn;
+      gg.ld_f32 = FP;
+      SSR_TRY(launch_gemm_tc(gg, 2, s));
+    }
+    for (int b = nb - 1; b >= 0; --b) {  // RCAB: out = x + t * gate(t), t = conv_b(relu(conv_a(x)))  (rcan.py:11-24)
+      const int i = g * nb + b;
+      --k;
+      const ConvT& ca = t->convs[t->r_a[i]];
+      const ConvT& cb = t->convs[t->r_b[i]];
+      const float* gs = W.gates + W.gate_stride * i;
+      CaBwdArgs a;
+      memset(&a, 0, sizeof(a));
+      a.G = Gn; a.t = W.t2[i]; a.ld = FP; a.B = B; a.HW = h * w; a.C = F; a.CP = FP; a.R = R;
+      a.W1 = m->dev<float>(m->ca[i].w1); a.W2 = m->dev<float>(m->ca[i].w2);
+      a.pool = gs; a.gate = gs + (size_t)B * F; a.hid = gs + (size_t)2 * B * F;
+      a.partial = W.ca_partial; a.nsplit = W.nsplit; a.dpool = W.dpool;
+      a.dW1 = grads[t->r_ca[i].w1]; a.db1 = grads[t->r_ca[i].b1]; a.dW2 = grads[t->r_ca[i].w2]; a.db2 = grads[t->r_ca[i].b2];
+      a.dt = W.Dt; a.ld_dt = FP;
+      SSR_TRY(launch_channel_attention_bwd(a, s));
+      SSR_TRY(wgrad_conv(m, cb, W.Dt, W.tmp[i], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
+      GemmArgs gb = dgrad_base(m, cb, W.Dt, B, h, w);
+      gb.mask = W.tmp[i];  // ReLU backward: gate by the saved ReLU output
+      gb.ld_mask = FP;
+      gb.mask_slope = 0.0f;
+      gb.out_T = Dh;
+      gb.ld_T = FP;
+      SSR_TRY(launch_gemm_tc(gb, 2, s));
+      SSR_TRY(wgrad_conv(m, ca, Dh, W.S[k], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
+      GemmArgs ga = dgrad_base(m, ca, Dh, B, h, w);
+      ga.res = Gn;  // the RCAB's skip
+      ga.ldres = FP;
+      ga.out_f32 = Gn;
+      ga.ld_f32 = FP;
+      SSR_TRY(launch_gemm_tc(ga, 2, s));
+    }
+    // group skip: dL/d(group input) = Gn + Ga; with the long skip joining at the head output (g == 0)
+    if (g == 0) SSR_TRY(launch_add_inplace(Gn, W.Gt, nullptr, T * FP, s));
+    SSR_TRY(launch_add_inplace(Gn, Ga, Gb, T * FP, s));
+    std::swap(Ga, Gn);
+  }
+  // head conv (rcan.py:63,70): dW[n][ci][tap] = sum_p G[p][n] * (x - mean)[p + off(tap)][ci]
+  if (grads[t->head_w]) {
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dY = Gb; a.ldy = FP; a.X = W.xin64; a.ldx = 64; a.B = B; a.H = h; a.W = w; a.M = (int)T; a.taps = 9;
+    a.NoutP = FP; a.CinP = 64;
+    a.dWp = W.dwp + t->head_dwp;
+    a.dBp = nullptr;
+    a.alpha = 1.0f;
+    a.N_alg = F;
+    a.K_alg = 3;
+    SSR_TRY(launch_wgrad_tc(a, s));
+    PackEntry e;
+    memset(&e, 0, sizeof(e));
+    e.W = W.dwp + t->head_dwp;
+    e.Wf = grads[t->head_w];
+    e.bf = a.dBp;
+    e.b = grads[t->head_b];
+    e.kind = 0;
+    e.N = F;
+    e.K = 3;
+    e.KP = 64;
+    e.taps = 9;
+    t->unpack_host.push_back(e);
+  }
+  if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, FP, F, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  SSR_CHECK((int)t->unpack_host.size() <= t->pack_cap, SSR_E_STATE, "train: unpack list overflow");
+  SSR_TRY(launch_unpack_batched(t->unpack_host.data(), W.pack_dev, (int)t->unpack_host.size(), s));
+  return launch_deferred_reductions(&t->red, s);  // every bias gradient's second stage, one launch
+}
 
 // =============================================================================================
 // SwinIR (swinir.py:353-372) training executor
@@ -1283,8 +1668,8 @@ extern "C" {
 int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const int64_t* numels) {
   SSR_TRY(check_ready(m));
   SSR_CHECK(m->cfg.precision == SSR_PREC_BF16, SSR_E_INVALID, "the training path is built for the bf16 tensor-core precision only");
-  SSR_CHECK(m->cfg.arch == SSR_ARCH_EDSR || m->cfg.arch == SSR_ARCH_SWINIR, SSR_E_INVALID,
-            "the training path is built for EDSR and SwinIR (HAT / RCAN are inference-only)");
+  SSR_CHECK(m->cfg.arch == SSR_ARCH_EDSR || m->cfg.arch == SSR_ARCH_SWINIR || m->cfg.arch == SSR_ARCH_RCAN, SSR_E_INVALID,
+            "the training path is built for EDSR, RCAN and SwinIR (HAT is inference-only)");
   train_state_destroy(m);
   m->train = new ssr_train_state();
   for (int i = 0; i < n; ++i) {
@@ -1292,7 +1677,7 @@ int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const 
     m->train->numels.push_back(numels[i]);
     m->train->index[names[i]] = i;
   }
-  int r = m->cfg.arch == SSR_ARCH_EDSR ? bind_edsr(m) : bind_swinir(m);
+  int r = m->cfg.arch == SSR_ARCH_EDSR ? bind_edsr(m) : m->cfg.arch == SSR_ARCH_RCAN ? bind_rcan(m) : bind_swinir(m);
   if (r != SSR_OK) train_state_destroy(m);
   return r;
 }
@@ -1304,6 +1689,10 @@ size_t ssr_model_train_workspace_bytes(const ssr_model_t* m, int B, int H, int W
     train_padded(m, H, W, &Hp, &Wp);
     SwinTrainWs w;
     return plan_swin_train(m, nullptr, B, Hp, Wp, &w);
+  }
+  if (m->cfg.arch == SSR_ARCH_RCAN) {
+    RcanTrainWs w;
+    return plan_rcan_train(m, nullptr, B, H, W, &w);
   }
   EdsrTrainWs w;
   return plan_edsr_train(m, nullptr, B, H, W, &w);
@@ -1317,6 +1706,7 @@ int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const fl
   if (m->cfg.arch == SSR_ARCH_SWINIR)
     return train_forward_swinir(m, params, drop_scale, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   SSR_CHECK(drop_scale == nullptr, SSR_E_INVALID, "train_forward: drop_scale is a SwinIR option");
+  if (m->cfg.arch == SSR_ARCH_RCAN) return train_forward_rcan(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_forward_edsr(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -1327,6 +1717,8 @@ int ssr_model_train_backward(ssr_model_t* m, const float* dy, const float* drop_
   SSR_CHECK(dy && grads && B > 0 && H > 0 && W > 0, SSR_E_INVALID, "train_backward: bad argument");
   if (m->cfg.arch == SSR_ARCH_SWINIR)
     return train_backward_swinir(m, dy, drop_scale, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (m->cfg.arch == SSR_ARCH_RCAN)
+    return train_backward_rcan(m, nullptr, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_backward_edsr(m, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -113,7 +113,7 @@ class _NativeForwardOnly(torch.autograd.Function):
 
 class Model(nn.Module):
     ARCH = -1
-    TRAINABLE = False  # True for the model families whose backward is built (EDSR, SwinIR)
+    TRAINABLE = False  # True for the model families whose backward is built (EDSR, RCAN, SwinIR)
 
     def __init__(self, scale: int = 4, n_colors: int = 3, img_range: float = 1.0) -> None:
         super().__init__()

@@ -26,6 +26,7 @@ class ResidualGroup(nn.Module):  # rcan.py:27-36 (parameter container)
 
 class RCAN(Model):
     ARCH = _lib.SSR_ARCH_RCAN
+    TRAINABLE = True  # forward + backward (train.cu: residual groups of RCABs incl. the channel-attention gate)
 
     def __init__(self, scale: int = 4, n_colors: int = 3, img_range: float = 1.0, n_feats: int = 64, n_resblocks: int = 20,
                  n_resgroups: int = 10, reduction: int = 16) -> None:
