@@ -296,7 +296,8 @@ def run_ours(args):
     if sharded:  # one frame's tile list over all ranks: tiles -> all-gather -> band blend -> all-gather (studiosr_b200/sharding.py)
         from studiosr_b200.sharding import NativeTileBackend, ShardedTiledUpscaler
 
-        up = ShardedTiledUpscaler(NativeTileBackend(nat, FRAME_H, FRAME_W, SCALE, TILE, OVERLAP, args.chunk), dist)
+        up = ShardedTiledUpscaler(NativeTileBackend(nat, FRAME_H, FRAME_W, SCALE, TILE, OVERLAP, args.chunk), dist,
+                                  graph=not args.no_graph)
 
     def barrier():
         if dist is not None:

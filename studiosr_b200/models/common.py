@@ -94,8 +94,8 @@ class _NativeTrainStep(torch.autograd.Function):
 
 
 class _NativeForwardOnly(torch.autograd.Function):
-    """Differentiable-looking forward for the modes whose backward kernels are not built (fp32 / tf32 contractions, HAT,
-    RCAN): the forward runs natively (so the reference's own shape tests, which call the model in train mode with grad
+    """Differentiable-looking forward for the modes whose backward kernels are not built (fp32 / tf32 contractions, HAT):
+    the forward runs natively (so the reference's own shape tests, which call the model in train mode with grad
     enabled, pass unchanged), a backward through it fails loudly instead of returning something else."""
 
     @staticmethod
@@ -106,7 +106,7 @@ class _NativeForwardOnly(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         raise NotImplementedError(
-            f"studiosr_b200: no backward kernels for {ctx.why}; the training path covers EDSR and SwinIR under the Trainer's "
+            f"studiosr_b200: no backward kernels for {ctx.why}; the training path covers EDSR, RCAN and SwinIR under the Trainer's "
             "bf16 autocast (trainer.py:69,80) -- run under torch.autocast('cuda', dtype=torch.bfloat16) or set "
             "model.precision = 'bf16'")
 
