@@ -356,6 +356,17 @@ def test_sharded_tiles_and_band_blend_are_bit_identical_to_whole_frame():
         h_out = torch.empty((400, 520, 3), dtype=torch.uint8).pin_memory()
         up.upscale_host(torch.from_numpy(img).pin_memory(), h_out)
         assert torch.equal(h_out, whole.cpu())
+        # the same pass captured once and replayed as a CUDA graph (what bench.py's multi-GPU leg runs): a second, different
+        # frame through the replay must equal its own eager result
+        upg = ShardedTiledUpscaler(NativeTileBackend(nat, 100, 130, 4, 64, 16), graph=True)
+        assert torch.equal(upg.upscale(frame), whole)
+        img2 = synth.smooth_image_u8(100, 130, seed=4)
+        frame2 = torch.from_numpy(img2).cuda()
+        whole2 = nat.upscale_tiled_u8(frame2, 4, 64, 16)
+        assert not torch.equal(whole2, whole)
+        assert torch.equal(upg.upscale(frame2), whole2) and upg._graph is not None
+        upg.upscale_host(torch.from_numpy(img).pin_memory(), h_out)
+        assert torch.equal(h_out, whole.cpu())
 
 
 def test_hat_full_batch_of_two():
