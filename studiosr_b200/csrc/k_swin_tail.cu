@@ -2,7 +2,8 @@
 //
 //   t'  = o @ Wproj^T + bproj + res                (swinir.py:103,171)    [tcgen05 SS, acc in TMEM]
 //   xn2 = (t' - mean) * rstd                       (swinir.py:172; norm2's gamma/beta are folded into W1/b1 at pack time)
-//   h   = GELU(xn2 @ W1^T + b1)                    (common.py:185-186)    [6 chunks of 64 hidden units]
+//   h   = GELU(xn2 @ W1^T + b1)                    (common.py:185-186)    [6 chunks of 64 hidden units; b1 rides in the GEMM:
+//                                                   xn2's pad channels C, C+1 are 1.0 and W1's columns there hold b1 as hi + lo]
 //   t'' = t' + h @ W2^T + b2                       (common.py:188, swinir.py:172)
 //   out: t'' (fp32 residual stream), LayerNorm_next(t'') or a bf16 copy of t''
 //
@@ -53,7 +54,7 @@ constexpr uint32_t ST_OFF_W = ST_OFF_XN + 3 * ST_TILE;             // ring
 constexpr uint32_t ST_OFF_IO = ST_OFF_W + ST_WSLOTS * ST_WSLOT;    // per IO warp: B0, B1 (residual in, outputs out)
 constexpr uint32_t ST_IO_WARP = 2 * 4096;
 constexpr uint32_t ST_OFF_PAR = ST_OFF_IO + 8 * ST_IO_WARP;        // fp32 parameters
-constexpr int ST_NPAR = 192 * 4 + 384;                             // bp b2 g3 be3 | b1
+constexpr int ST_NPAR = 192 * 4;                                   // bp b2 g3 be3
 constexpr uint32_t ST_OFF_RED = ST_OFF_PAR + ST_NPAR * 4;          // [128][2] float2 cross-half reductions
 constexpr uint32_t ST_OFF_BAR = ST_OFF_RED + 128 * 2 * 8;
 constexpr uint32_t ST_SMEM = ST_OFF_BAR + 512 + 1024;
@@ -76,7 +77,7 @@ static_assert(SB_COUNT * 8 + 8 <= 512, "barrier area");
 
 struct TailArgs {
   int M, C, n_tiles;
-  const float *bp, *b1, *b2, *g3, *be3;  // b1 (and W1) carry norm2's affine
+  const float *bp, *b2, *g3, *be3;  // fc1's bias (with norm2's beta folded in) rides in W1's columns C, C+1
   int has_f32;  // store t'' as fp32
   int has_bf;   // store a bf16 tensor: LayerNorm_next(t'') if do_ln else t''
   int do_ln;
@@ -146,7 +147,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
   // instead of generic LD/ST for every staging access
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* par = reinterpret_cast<float*>(smem + ST_OFF_PAR);
-  float *s_bp = par, *s_b2 = par + 192, *s_g3 = par + 384, *s_be3 = par + 576, *s_b1 = par + 768;
+  float *s_bp = par, *s_b2 = par + 192, *s_g3 = par + 384, *s_be3 = par + 576;
   float2* red = reinterpret_cast<float2*>(smem + ST_OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + SB_COUNT);
@@ -161,7 +162,6 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
     s_g3[i] = a.g3 ? __ldg(a.g3 + i) : 0.f;
     s_be3[i] = a.be3 ? __ldg(a.be3 + i) : 0.f;
   }
-  for (int i = threadIdx.x; i < 384; i += ST_THREADS) s_b1[i] = __ldg(a.b1 + i);
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmO);
     prefetch_tmap(&tmWp);
@@ -438,7 +438,7 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
       // the xn2 tile is shared by consecutive tiles: the fc1 MMAs of the previous tile must have read it
       if (it > 0) mbar_wait_warp(bar(SB_XNFREE), (uint32_t)(it - 1) & 1u, lane);
       if (dbg) dbg[3] = clock64();
-      // xn2 in the SWIZZLE_128B K-major layout TMA would have produced.  Padded channels must stay exact zeros.
+      // xn2 in the SWIZZLE_128B K-major layout TMA would have produced
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int nb = hf * 96 + c * 32;
@@ -448,9 +448,9 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             w[i] = f2_to_bf16x2(f2_fma(tv[c][4 * qd + i], sc2, sh2));
-            if (c == 2 && mask_tail) {
+            if (c == 2 && mask_tail) {  // padded channels: 1.0 in C, C+1 (they carry fc1's bias: W1 holds it there), zeros after
               const int col = nb + 8 * qd + 2 * i;
-              w[i] = col >= a.C ? 0u : (col + 1 >= a.C ? (w[i] & 0xffffu) : w[i]);
+              w[i] = col == a.C ? 0x3F803F80u : (col > a.C ? 0u : w[i]);
             }
           }
           const int col = nb + 8 * qd;
@@ -626,12 +626,10 @@ swin_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant_
         tmem_ld32_nowait(tx, raw);
         tmem_wait_ld();
         uint32_t pk[16];
-        const float* bb = s_b1 + ch * 64 + hf * 32;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bv = *reinterpret_cast<const float4*>(bb + 4 * j);
-          pk[2 * j + 0] = gelu2_bf16(f2_add(f2_pack_u(raw[4 * j], raw[4 * j + 1]), f2_pack(bv.x, bv.y)), kC0, kC1, kHalf);
-          pk[2 * j + 1] = gelu2_bf16(f2_add(f2_pack_u(raw[4 * j + 2], raw[4 * j + 3]), f2_pack(bv.z, bv.w)), kC0, kC1, kHalf);
+        for (int j = 0; j < 8; ++j) {  // b1 is already in the accumulator (xn2's channels C, C+1 are 1.0, W1's columns there hold it)
+          pk[2 * j + 0] = gelu2_bf16(f2_pack_u(raw[4 * j], raw[4 * j + 1]), kC0, kC1, kHalf);
+          pk[2 * j + 1] = gelu2_bf16(f2_pack_u(raw[4 * j + 2], raw[4 * j + 3]), kC0, kC1, kHalf);
         }
         tmem_st16_u32(tx, pk);  // K index 2i, 2i+1 of this half -> column i (low half = even k)
         tmem_wait_st();
@@ -658,6 +656,7 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
   SSR_CHECK(f.CP == 192 && f.HP == 384 && f.QP == 192, SSR_E_INVALID, "swin_tail: unsupported padded dims %d/%d/%d", f.CP, f.HP,
             f.QP);
   SSR_CHECK(!(f.out_T && f.out_ln), SSR_E_INVALID, "swin_tail: at most one bf16 output");
+  SSR_CHECK(f.C % 2 == 0 && f.C + 2 <= f.CP, SSR_E_INVALID, "swin_tail: C=%d leaves no pad channel pair for the fc1 bias", f.C);
   SSR_CHECK(f.ldres % 4 == 0 && (!f.out_f32 || f.ld_f32 % 4 == 0), SSR_E_INVALID, "swin_tail: fp32 leading dims must be 16-byte multiples");
   CUtensorMap tmO, tmWp, tmW1, tmW2, tmRes, tmResPf, tmOutF, tmOutB, tmOutB2;
   auto map2d = [&](CUtensorMap* m, const void* base, int elem, int cols, int rows, int ld, int box_c, int box_r, int sw) {
@@ -694,7 +693,7 @@ int launch_mlp_fused(const MlpFusedArgs& f, cudaStream_t s) {
   }
   TailArgs a;
   a.M = f.M; a.C = f.C; a.n_tiles = (f.M + 127) / 128;
-  a.bp = f.bp; a.b1 = f.b1; a.b2 = f.b2; a.g3 = f.g3; a.be3 = f.be3;
+  a.bp = f.bp; a.b2 = f.b2; a.g3 = f.g3; a.be3 = f.be3;
   a.has_f32 = f.out_f32 != nullptr;
   a.has_bf = outb != nullptr;
   a.do_ln = f.out_ln != nullptr;

@@ -253,6 +253,11 @@ static int fold_norm_into_linear(ssr_model* m, const std::string& norm, const st
       acc += (double)w * (*be)[k];
     }
     reinterpret_cast<float*>(m->host_arena.data() + out.b_off)[n] = (float)acc;
+    // the fused tail kernel takes the bias from the GEMM itself: its A operand is 1.0 in channels K, K+1
+    SSR_CHECK(K + 2 <= KP, SSR_E_INVALID, "fold_norm_into_linear: K=%d leaves no pad channel pair for the bias", K);
+    const float hi = __bfloat162float(__float2bfloat16_rn((float)acc));
+    store_w(m, out.w_off, (size_t)n * KP + K, hi, (size_t)out.NP * KP);
+    store_w(m, out.w_off, (size_t)n * KP + K + 1, (float)acc - hi, (size_t)out.NP * KP);
   }
   return SSR_OK;
 }
@@ -951,7 +956,7 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
         memset(&f, 0, sizeof(f));
         f.o = W.o; f.ld_o = L.QP; f.M = T; f.C = m->C; f.Hid = m->HID; f.CP = CP; f.HP = m->HP; f.QP = L.QP;
         f.Wp = m->arena + blk.proj.w_off; f.W1 = m->arena + blk.fc1.w_off; f.W2 = m->arena + blk.fc2.w_off;
-        f.bp = m->dev<float>(blk.proj.b_off); f.b1 = m->dev<float>(blk.fc1.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
+        f.bp = m->dev<float>(blk.proj.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
         f.res = bi == 0 ? W.g : W.t; f.ldres = CP;
         f.eps = 1e-5f;
         if (bi + 1 < depth) {
@@ -1276,7 +1281,7 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
         memset(&f, 0, sizeof(f));
         f.o = W.o; f.ld_o = L.QP; f.M = T; f.C = m->C; f.Hid = m->HID; f.CP = CP; f.HP = m->HP; f.QP = L.QP;
         f.Wp = m->arena + blk.proj.w_off; f.W1 = m->arena + blk.fc1.w_off; f.W2 = m->arena + blk.fc2.w_off;
-        f.bp = m->dev<float>(blk.proj.b_off); f.b1 = m->dev<float>(blk.fc1.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
+        f.bp = m->dev<float>(blk.proj.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
         f.res = W.t; f.ldres = CP; f.eps = 1e-5f;
         f.out_f32 = W.t; f.ld_f32 = CP; f.out_ln = W.xn; f.ld_ln = CP;
         f.g3 = m->dev<float>(next->g_off); f.be3 = m->dev<float>(next->b_off);
@@ -1308,7 +1313,7 @@ static int forward_hat(ssr_model* m, const InputSpec& in, const OutputSpec& out,
         memset(&f, 0, sizeof(f));
         f.o = W.o; f.ld_o = L.QP; f.M = T; f.C = m->C; f.Hid = m->HID; f.CP = CP; f.HP = m->HP; f.QP = L.QP;
         f.Wp = m->arena + blk.proj.w_off; f.W1 = m->arena + blk.fc1.w_off; f.W2 = m->arena + blk.fc2.w_off;
-        f.bp = m->dev<float>(blk.proj.b_off); f.b1 = m->dev<float>(blk.fc1.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
+        f.bp = m->dev<float>(blk.proj.b_off); f.b2 = m->dev<float>(blk.fc2.b_off);
         f.res = W.t; f.ldres = CP; f.eps = 1e-5f;
         f.out_T = W.tb; f.ld_T = CP;
         SSR_TRY(launch_mlp_fused(f, s));

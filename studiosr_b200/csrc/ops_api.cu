@@ -67,6 +67,14 @@ using namespace ssr;
 static long long* g_dbg_buf = nullptr;
 
 namespace ssr {
+__global__ void fill_bias_cols_bf16_kernel(__nv_bfloat16* w, const float* b, int N, int ld, int c0) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b[n]);
+    w[(size_t)n * ld + c0] = hi;
+    w[(size_t)n * ld + c0 + 1] = __float2bfloat16_rn(b[n] - __bfloat162float(hi));
+  }
+}
 __global__ void fill_ones_bf16_kernel(__nv_bfloat16* x, size_t M, int ld, int c0, int n) {
   const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < M)
@@ -224,20 +232,22 @@ int ssr_op_swin_mlp(const float* o, const float* res, const float* Wp, const flo
   SSR_TRY(launch_pack_heads(Wp, wp, C, heads, d, DP, QP, 2, 0, s));
   SSR_CUDA(cudaMemsetAsync(w1, 0, (size_t)HP * CP * 2, s));
   SSR_TRY(launch_pack_rows(w1f, hidden, C, w1, CP, 2, 0, s));
+  // fc1's (folded) bias rides in W1's pad columns C, C+1 as hi + lo bf16 parts, exactly as ssr_model_finalize packs it
+  fill_bias_cols_bf16_kernel<<<(hidden + 255) / 256, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(w1), b1f, hidden, CP, C);
+  SSR_CUDA(cudaGetLastError());
   SSR_CUDA(cudaMemsetAsync(w2, 0, (size_t)CP * HP * 2, s));
   SSR_TRY(launch_pack_rows(W2, C, hidden, w2, HP, 2, 0, s));
-  float *vbp = vec, *vb2 = vec + CP, *vg3 = vec + 4 * CP, *vbe3 = vec + 5 * CP, *vb1 = vec + 6 * CP;
+  float *vbp = vec, *vb2 = vec + CP, *vg3 = vec + 4 * CP, *vbe3 = vec + 5 * CP;
   SSR_TRY(launch_pack_rows(bp, 1, C, vbp, CP, 4, 0, s));
   SSR_TRY(launch_pack_rows(b2, 1, C, vb2, CP, 4, 0, s));
   if (g3) {
     SSR_TRY(launch_pack_rows(g3, 1, C, vg3, CP, 4, 0, s));
     SSR_TRY(launch_pack_rows(be3, 1, C, vbe3, CP, 4, 0, s));
   }
-  SSR_TRY(launch_pack_rows(b1f, 1, hidden, vb1, HP, 4, 0, s));
   MlpFusedArgs f;
   memset(&f, 0, sizeof(f));
   f.o = op; f.ld_o = QP; f.M = M; f.C = C; f.Hid = hidden; f.CP = CP; f.HP = HP; f.QP = QP;
-  f.Wp = wp; f.W1 = w1; f.W2 = w2; f.bp = vbp; f.b1 = vb1; f.b2 = vb2;
+  f.Wp = wp; f.W1 = w1; f.W2 = w2; f.bp = vbp; f.b2 = vb2;
   f.res = rp; f.ldres = CP; f.out_f32 = yp; f.ld_f32 = CP; f.eps = 1e-5f;
   if (g3) {
     f.g3 = vg3; f.be3 = vbe3; f.out_ln = ylp; f.ld_ln = CP;

@@ -204,7 +204,8 @@ struct MlpFusedArgs {
   int ld_o;
   int M, C, Hid, CP, HP, QP;
   const void *Wp, *W1, *W2;  // packed bf16 [CP][QP], [HP][CP], [CP][HP]
-  const float *bp, *b1, *b2, *g3, *be3;  // padded fp32 vectors (g3/be3 may be null)
+  const float *bp, *b2, *g3, *be3;  // padded fp32 vectors (g3/be3 may be null).  fc1's bias is not an argument: W1's
+                                     // columns C, C+1 hold it as hi + lo bf16 parts (the kernel feeds 1.0 there)
   const float* res;
   int ldres;
   float* out_f32;
