@@ -163,7 +163,11 @@ int ssr_model_upscale_tiled_u8_host(ssr_model_t* m, const uint8_t* frame_host, u
  *                            x [B,3,H,W] -> y [B,3,sH,sW] (fp32 NCHW) and keeps every GEMM operand in `workspace`.
  *   ssr_model_train_backward dy = dL/dy (DEVICE fp32 NCHW).  grads[i] = DEVICE fp32 buffer for dL/d(param i), overwritten
  *                            (NULL: not wanted, e.g. frozen entries).  `workspace` must be the buffer, untouched, that
- *                            the matching train_forward used.  dL/dx is not produced (the Trainer never asks for it).
+ *                            the matching train_forward used.
+ *   ssr_model_train_input_grad  dL/dx (DEVICE fp32 NCHW [B,3,H,W], overwritten) of the step whose train_backward ran last on
+ *                            this handle (the Trainer never asks for it; autograd users with x.requires_grad do): the first
+ *                            conv's data gradient through the input normalisation and the training-mode reflect pad.  The
+ *                            workspace of that backward must still be untouched.
  *   drop_scale               stochastic depth of SwinIR (timm DropPath, swinir.py:137,171-172): DEVICE fp32
  *                            [2 * n_blocks][B], entry [2k][b] / [2k+1][b] = the factor (0 or 1/keep_prob) applied to sample b's
  *                            attention / MLP branch of block k (blocks in forward order); NULL = no stochastic depth.  The host
@@ -176,6 +180,7 @@ int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const fl
                             int H, int W, void* workspace, size_t workspace_bytes, void* stream);
 int ssr_model_train_backward(ssr_model_t* m, const float* dy, const float* drop_scale, float* const* grads, int B, int H, int W,
                              void* workspace, size_t workspace_bytes, void* stream);
+int ssr_model_train_input_grad(ssr_model_t* m, float* dx, int B, int H, int W, void* stream);
 
 /* ---- the rest of the Trainer step on flat fp32 DEVICE buffers (trainer.py:102-109,133-139) -----------------------------
  * ssr_l1_loss    nn.L1Loss (trainer.py:45): *loss = mean |out - y| over n elements and, when dout != NULL, the backward seed

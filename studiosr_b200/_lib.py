@@ -58,6 +58,7 @@ SYMBOLS = {
                                         c_void_p, c_size_t, c_void_p]),
     "ssr_model_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p,
                                          c_size_t, c_void_p]),
+    "ssr_model_train_input_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ssr_l1_loss_workspace_bytes": (c_size_t, []),
     "ssr_l1_loss": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_double,

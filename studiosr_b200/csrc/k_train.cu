@@ -487,6 +487,53 @@ int launch_input_nhwc64(const float* x, void* out, int B, int h, int w, int Hp, 
   return SSR_OK;
 }
 
+// dL/dx of the first conv (3 -> C, zero padding) composed with the input normalisation and the training-mode reflect pad
+// (the adjoints of conv_first_kernel / input_nhwc64_kernel):
+//   dxp[b][ci][y][x] = sum_{ky,kx,n} G[b][y-ky+1][x-kx+1][n] * W[n][ci][ky][kx]      on the padded Hp x Wp grid
+//   dx[b][ci][sy][sx] += scale * dxp[b][ci][y][x]   for every padded (y, x) that reads source pixel (sy, sx)
+// One warp per padded pixel, lanes over the channels; the <= 4 padded pixels of a reflected source pixel meet in an atomicAdd.
+__global__ void __launch_bounds__(256) conv_first_dgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Wc, int C,
+                                                               int B, int h, int w, int Hp, int Wp, float scale, float* __restrict__ dx) {
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= (long long)B * Hp * Wp) return;
+  const int x = (int)(p % Wp), y = (int)((p / Wp) % Hp), b = (int)(p / ((long long)Wp * Hp));
+  float acc[3] = {0.0f, 0.0f, 0.0f};
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y - ky + 1;
+    if (yy < 0 || yy >= Hp) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x - kx + 1;
+      if (xx < 0 || xx >= Wp) continue;
+      const float* g = G + ((size_t)((size_t)b * Hp + yy) * Wp + xx) * ldg;
+      for (int n = lane; n < C; n += 32) {
+        const float gv = g[n];
+        const float* wn = Wc + (size_t)n * 27 + ky * 3 + kx;
+        acc[0] = fmaf(gv, wn[0], acc[0]);
+        acc[1] = fmaf(gv, wn[9], acc[1]);
+        acc[2] = fmaf(gv, wn[18], acc[2]);
+      }
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[ci] += __shfl_xor_sync(0xffffffffu, acc[ci], o);
+  if (lane < 3) {
+    const int sy = y < h ? y : 2 * (h - 1) - y, sx = x < w ? x : 2 * (w - 1) - x;
+    atomicAdd(dx + ((size_t)b * 3 + lane) * h * w + (size_t)sy * w + sx, scale * acc[lane]);
+  }
+}
+int launch_conv_first_dgrad(const float* G, int ldg, const float* Wc, int C, int B, int h, int w, int Hp, int Wp, float scale,
+                            float* dx, cudaStream_t s) {
+  SSR_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * 3 * h * w * 4, s));
+  const long long warps = (long long)B * Hp * Wp;
+  conv_first_dgrad_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(G, ldg, Wc, C, B, h, w, Hp, Wp, scale, dx);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 // output gradient fp32 NCHW [B,3,ch,cw] (the cropped image) -> bf16 NHWC [B,Hs,Ws,64] of the un-cropped reconstruction
 // conv output: lanes 0..2 = dy * scale inside the crop, zero outside and in the pad lanes
 __global__ void grad_nhwc64_kernel(const float* __restrict__ dy, __nv_bfloat16* out, int B, int ch, int cw, int Hs, int Ws,

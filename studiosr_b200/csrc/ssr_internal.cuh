@@ -387,6 +387,9 @@ int launch_colsum(const void* dY, int elem, int ld, int M, int NP, int Cout, int
 int launch_unshuffle(const void* in, void* out, int B, int H, int W, int C, int r, int ld_in, cudaStream_t s);
 int launch_nchw3_to_nhwc64(const float* in, void* out, int B, int H, int W, float scale, const float* shift3, cudaStream_t s);
 int launch_add_inplace(float* a, const float* b, void* out_bf, size_t n, cudaStream_t s);
+// dL/dx from the gradient at the first conv's output (fp32 [B*Hp*Wp][ldg]); dx fp32 NCHW [B][3][h][w], overwritten
+int launch_conv_first_dgrad(const float* G, int ldg, const float* Wc, int C, int B, int h, int w, int Hp, int Wp, float scale,
+                            float* dx, cudaStream_t s);
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(const GemmArgs& g, int elem, cudaStream_t s);

@@ -71,6 +71,10 @@ struct ssr_train_state {
   std::vector<int> r_a, r_b, r_gt;  // indices into convs: the two convs of every RCAB (group-major), the conv closing each group
   std::vector<ssr::CaT> r_ca;
   int pack_cap = 0;                 // entries the batched (un)pack launches may carry
+  // left behind by the last train_backward for ssr_model_train_input_grad: dL/d(first conv's output), fp32
+  const float* dx_G = nullptr;
+  int dx_ld = 0, dx_C = 0, dx_B = 0, dx_h = 0, dx_w = 0, dx_Hp = 0, dx_Wp = 0;
+  float dx_scale = 1.0f;
   // SwinIR
   std::vector<std::vector<BlockT>> s_blocks;
   std::vector<int> s_conv;  // RSTB convs
@@ -536,6 +540,8 @@ static int train_backward_edsr(ssr_model* m, const float* dy, float* const* grad
     t->unpack_host.push_back(e);
   }
   if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, FP, m->F, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  t->dx_G = W.G; t->dx_ld = FP; t->dx_C = m->F; t->dx_B = B; t->dx_h = h; t->dx_w = w; t->dx_Hp = h; t->dx_Wp = w;
+  t->dx_scale = 1.0f;  // sub_mean is an identity-weight 1x1 conv (common.py:108-121)
   SSR_TRY(launch_unpack_batched(t->unpack_host.data(), W.pack_dev, (int)t->unpack_host.size(), s));
   return launch_deferred_reductions(&t->red, s);  // every bias gradient's second stage, one launch
 }
@@ -914,6 +920,8 @@ static int train_backward_rcan(ssr_model* m, const float* const* params, const f
     t->unpack_host.push_back(e);
   }
   if (grads[t->head_b]) SSR_TRY(launch_colsum(Gb, 2, FP, (int)T, FP, F, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  t->dx_G = Ga; t->dx_ld = FP; t->dx_C = F; t->dx_B = B; t->dx_h = h; t->dx_w = w; t->dx_Hp = h; t->dx_Wp = w;
+  t->dx_scale = 1.0f;
   SSR_CHECK((int)t->unpack_host.size() <= t->pack_cap, SSR_E_STATE, "train: unpack list overflow");
   SSR_TRY(launch_unpack_batched(t->unpack_host.data(), W.pack_dev, (int)t->unpack_host.size(), s));
   return launch_deferred_reductions(&t->red, s);  // every bias gradient's second stage, one launch
@@ -1656,6 +1664,8 @@ static int train_backward_swinir(ssr_model* m, const float* dy, const float* dro
     t->unpack_host.push_back(e);
   }
   if (grads[t->head_b]) SSR_TRY(launch_colsum(W.Gtb, 2, CP, T, CP, C, 0, 1.0f, grads[t->head_b], W.partial, s, &t->red));
+  t->dx_G = W.Gt; t->dx_ld = CP; t->dx_C = C; t->dx_B = B; t->dx_h = h; t->dx_w = w; t->dx_Hp = Hp; t->dx_Wp = Wp;
+  t->dx_scale = 1.0f / m->cfg.img_range;  // Normalizer (common.py:222-233): x_in = (x - mean * range) / range
   SSR_TRY(launch_unpack_batched(t->unpack_host.data(), W.pack_dev, (int)t->unpack_host.size(), s));
   return launch_deferred_reductions(&t->red, s);  // bias / LayerNorm-parameter gradients: all second stages, one launch
 }
@@ -1720,6 +1730,16 @@ int ssr_model_train_backward(ssr_model_t* m, const float* dy, const float* drop_
   if (m->cfg.arch == SSR_ARCH_RCAN)
     return train_backward_rcan(m, nullptr, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_backward_edsr(m, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ssr_model_train_input_grad(ssr_model_t* m, float* dx, int B, int H, int W, void* stream) {
+  SSR_TRY(check_ready(m));
+  SSR_CHECK(m->train != nullptr && m->train->dx_G != nullptr, SSR_E_STATE, "train_input_grad: no ssr_model_train_backward has run");
+  const ssr_train_state* t = m->train;
+  SSR_CHECK(dx && B == t->dx_B && H == t->dx_h && W == t->dx_w, SSR_E_INVALID, "train_input_grad: shape [%d,3,%d,%d] is not the last backward's [%d,3,%d,%d]",
+            B, H, W, t->dx_B, t->dx_h, t->dx_w);
+  return launch_conv_first_dgrad(t->dx_G, t->dx_ld, m->dev<float>(m->conv_first_w), t->dx_C, B, H, W, t->dx_Hp, t->dx_Wp, t->dx_scale, dx,
+                                 (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -61,19 +61,18 @@ def converge_images(images: List[torch.Tensor]) -> torch.Tensor:
 class _NativeTrainStep(torch.autograd.Function):
     """`out = model(x)` / `loss.backward()` of the Trainer step (trainer.py:97-105) through libssr_b200:
     forward keeps every GEMM operand in a workspace, backward produces all parameter gradients (fp32, PyTorch
-    layouts) with the tensor-core dgrad / wgrad kernels.  dL/dx is not produced."""
+    layouts) with the tensor-core dgrad / wgrad kernels, and dL/dx when the input asks for it."""
 
     @staticmethod
     def forward(ctx, x, model, nat, drop_scale, *tensors):
         y, ws = nat.train_forward(x, [t.detach() for t in tensors], model.scale, drop_scale)
         ctx.nat, ctx.ws, ctx.shape, ctx.drop_scale, ctx.model = nat, ws, tuple(x.shape), drop_scale, model
+        ctx.xdtype = x.dtype
         ctx.meta = [(t.shape, t.numel(), t.requires_grad) for t in tensors]
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("studiosr_b200: the gradient with respect to the input image is not built")
         # one flat buffer: grads are views into it, every slice on a 16-byte boundary -- the layout engine.FusedAdam keeps its
         # parameters in, so the optimizer update is one launch and a data-parallel exchange one all-reduce
         total = sum((n + 3) // 4 * 4 for _, n, rg in ctx.meta if rg)
@@ -86,11 +85,12 @@ class _NativeTrainStep(torch.autograd.Function):
             else:
                 grads.append(None)
         ctx.nat.train_backward(dy, grads, ctx.shape, ctx.ws, ctx.drop_scale)
+        dx = ctx.nat.train_input_grad(ctx.shape, dy.device).to(ctx.xdtype) if ctx.needs_input_grad[0] else None  # (reads the workspace)
         ctx.ws = None
         sync = getattr(ctx.model, "_grad_sync", None)  # engine.DistributedDataParallel: the gradient mean over ranks
         if sync is not None:
             sync(flat)
-        return (None, None, None, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
 class _NativeForwardOnly(torch.autograd.Function):
@@ -237,7 +237,7 @@ class Model(nn.Module):
         """Differentiable forward (the Trainer's `model(x)`, trainer.py:101-102)."""
         # the backward kernels mirror the TRAINING branch of the forward (reflect padding, stochastic depth); a differentiable
         # call in eval mode keeps the eval forward and fails loudly on backward
-        if precision != "bf16" or not self._trainable() or x.requires_grad or not self.training:
+        if precision != "bf16" or not self._trainable() or not self.training:
             params = [p for p in self.parameters() if p.requires_grad]
             return _NativeForwardOnly.apply(x, self, precision, self._pad_mode(), *params)
         named = {k: v for k, v in self.state_dict(keep_vars=True).items() if v.is_floating_point()}

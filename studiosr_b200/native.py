@@ -141,6 +141,14 @@ class NativeModel:
                                                          None if drop_scale is None else drop_scale.data_ptr(), self._ptr_array(grads), B, H, W,
                                                          ws.data_ptr(), ws.numel(), _stream_ptr(dy.device)))
 
+    def train_input_grad(self, shape, device) -> torch.Tensor:
+        """dL/dx of the step whose train_backward ran last (its workspace must still be alive)."""
+        B, _, H, W = shape
+        dx = torch.empty((B, 3, H, W), dtype=torch.float32, device=device)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.ssr_model_train_input_grad(self.handle, dx.data_ptr(), B, H, W, _stream_ptr(dx.device)))
+        return dx
+
     def upscale_u8(self, img: torch.Tensor, scale: int, graph: bool = False) -> torch.Tensor:
         """img: uint8 [B,H,W,3] on the device -> uint8 [B,sH,sW,3]."""
         B, H, W, _ = img.shape

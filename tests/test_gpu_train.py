@@ -383,8 +383,49 @@ def test_swinir_drop_path_training_step():
     assert torch.equal(y1, y2)  # ... but the inference path takes no masks
 
 
+@pytest.mark.parametrize("arch,B,H,W", [("edsr", 2, 12, 20), ("rcan", 1, 9, 11), ("swinir", 2, 16, 24), ("swinir-reflect-pad", 1, 20, 27)])
+def test_input_gradient(arch, B, H, W):
+    """dL/dx (ssr_model_train_input_grad: the first conv's data gradient through the normalisation and, for SwinIR, the
+    training-mode reflect pad of common.py:277-282) against fp32 autograd over the oracle."""
+    from studiosr_b200.models import EDSR, RCAN, SwinIR
+
+    if arch == "edsr":
+        cfg = synth.EDSR_TINY
+        P = synth.edsr_weights(cfg, 5)
+        model, fwd = EDSR(**cfg), lambda Q, x: O.edsr_forward(Q, x, cfg)
+    elif arch == "rcan":
+        cfg = synth.RCAN_TINY
+        P = synth.rcan_weights(cfg, 9)
+        model, fwd = RCAN(**cfg), lambda Q, x: O.rcan_forward(Q, x, cfg)
+    else:
+        cfg = synth.swinir_config(**synth.SWINIR_TINY)
+        P = synth.swinir_weights(cfg, 11)
+        kw = {k: cfg[k] for k in ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size", "mlp_ratio",
+                                  "upsampler")}
+        model, fwd = SwinIR(drop_path_rate=0.0, **kw), lambda Q, x: O.swinir_forward(Q, x, cfg, training=True)
+    x = synth.image_batch((B, 3, H, W), 77)
+    tgt = synth.image_batch((B, 3, H * cfg["scale"], W * cfg["scale"]), 78)
+    xr = x.clone().requires_grad_(True)
+    F.l1_loss(fwd(P, xr), tgt).backward()
+    xa = x.clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        la = F.l1_loss(fwd(P, xa), tgt)
+    la.backward()
+    model.load_state_dict(P, strict=True)
+    model = model.cuda().train()
+    xc = x.clone().cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = F.l1_loss(model(xc), tgt.cuda())
+    loss.backward()
+    assert xc.grad is not None and xc.grad.shape == x.shape and torch.isfinite(xc.grad).all()
+    e, e_ref = _rel(xc.grad.cpu(), xr.grad), _rel(xa.grad.float(), xr.grad)
+    print(f"dL/dx {arch}: rel err {e:.3e} (reference under bf16 autocast: {e_ref:.3e})")
+    assert e <= max(3e-2, 2.0 * e_ref), (e, e_ref)
+    assert all(p.grad is not None for p in model.parameters() if p.requires_grad)  # the parameter gradients come with it
+
+
 def test_training_modes_without_backward_fail_loudly():
-    """fp32-mode training, HAT training and dL/dx are not built: the forward still runs (the reference's own shape
+    """fp32-mode training and HAT training are not built: the forward still runs (the reference's own shape
     tests call the model in train mode), the backward raises instead of returning something else."""
     from studiosr_b200.models import EDSR, HAT
 
@@ -393,11 +434,6 @@ def test_training_modes_without_backward_fail_loudly():
     y = m(x)  # fp32 mode (no autocast)
     assert y.shape == (1, 3, 32, 32) and y.requires_grad
     with pytest.raises(NotImplementedError, match="no backward kernels"):
-        y.sum().backward()
-    xr = x.clone().requires_grad_(True)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        y = m(xr)
-    with pytest.raises(NotImplementedError):
         y.sum().backward()
     r = HAT(drop_path_rate=0.0, **synth.HAT_TINY).cuda().train()
     with torch.autocast("cuda", dtype=torch.bfloat16):
