@@ -219,6 +219,27 @@ def test_tiled_inference_matches_oracle_tiler():
     assert np.array_equal(m.inference_tiled(small), m.inference(small))
 
 
+@pytest.mark.parametrize("H,W,tile,overlap", [(40, 150, 64, 16), (97, 64, 48, 8), (64, 64, 64, 16), (130, 70, 32, 12)])
+def test_tiled_inference_ragged_frames_and_chunking(H, W, tile, overlap):
+    """Frames with one side below the tile size, tile / overlap pairs other than 64 / 16, clamped last tiles: the device tiler
+    equals the oracle tiler, and processing the tile list in chunks (a bounded workspace) changes nothing, bit for bit."""
+    cfg = synth.swinir_config(**synth.SWINIR_TINY)
+    P = synth.swinir_weights(cfg, 11)
+    m = _swinir(cfg, 11).eval()
+    img = synth.smooth_image_u8(H, W, seed=H + W)
+    x = torch.from_numpy(img.astype(np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)
+    ref_u8 = O.quantize_u8(O.tiled_upscale(lambda t: O.swinir_forward(P, t, cfg), x, 4, tile=tile, overlap=overlap)[0], 1.0).numpy()
+    out = m.inference_tiled(img, tile=tile, overlap=overlap, precision="fp32")
+    d = np.abs(out.astype(np.int32) - ref_u8.astype(np.int32))
+    assert out.shape == (4 * H, 4 * W, 3) and d.max() <= 1 and (d > 0).mean() < 2e-3, (d.max(), (d > 0).mean())
+    frame = torch.from_numpy(img).cuda()
+    for prec in ("fp32", "bf16"):
+        nat = m._native(frame.device, prec)
+        whole = nat.upscale_tiled_u8(frame, 4, tile, overlap)
+        for chunk in (1, 2, 3):
+            assert torch.equal(nat.upscale_tiled_u8(frame, 4, tile, overlap, chunk), whole), (prec, chunk)
+
+
 def test_reference_shape_tests_pass_unchanged():
     """The reference's own API gate (tests/models/test_swinir.py:8-26, test_edsr.py) on the drop-in:
     default full-size config, train mode, 8x8 and 12x12 inputs, every scale."""

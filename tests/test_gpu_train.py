@@ -153,6 +153,21 @@ def test_rcan_backward(name, cfg, B, H, W):
     assert worst[0] <= 1.0, f"RCAN {name}: gradient rel err {worst[1]:.3e} vs reference-bf16 {worst[2]:.3e} at {worst[3]}"
 
 
+def test_rcan_default_depth_training_step():
+    """The default RCAN (10 groups x 20 RCABs, rcan.py:39-50) through one native training step: every one of its 1600+
+    parameter tensors gets a finite gradient, the loss equals the oracle's, and a sample of the gradients (first / last
+    group, the gates) stays within the bf16 bound."""
+    cfg = dict(scale=2, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=20, n_resgroups=10, reduction=16)
+    model, Pr, Pa, loss, loss_ref = _rcan_case(cfg, 1, 16, 16, 9, 55)
+    assert abs(loss - loss_ref) < 5e-3 * max(1.0, abs(loss_ref)), (loss, loss_ref)
+    named = dict(model.named_parameters())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in named.values() if p.requires_grad)
+    for k in ("head.0.weight", "body.0.body.0.body.0.weight", "body.0.body.0.body.3.conv_du.2.weight", "body.9.body.19.body.2.weight",
+              "body.9.body.20.weight", "body.10.weight", "tail.1.weight"):
+        e, e_ref = _rel(named[k].grad.cpu(), Pr[k].grad), _rel(Pa[k].grad.float(), Pr[k].grad)
+        assert e <= max(5e-2, 2.5 * e_ref), (k, e, e_ref)
+
+
 def test_edsr_train_step_updates_weights():
     """Two optimiser steps through the unchanged torch.optim.Adam: the device-side re-pack must pick up the new weights."""
     from studiosr_b200.models import EDSR
