@@ -359,6 +359,51 @@ def rcan_forward(P: Dict, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
     return F.conv2d(y, P["add_mean.weight"], P["add_mean.bias"])
 
 
+# --------------------------------------------------------------------------- HAN
+def han_lam(x5: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    """LAM_Module (han.py:12-33): attention between the N stacked feature maps.  x5 [B, N, C, H, W] -> [B, N*C, H, W].
+    energy = Q Q^T over the flattened C*H*W axis, softmax of (row max - energy), out = gamma * (attention @ Q) + x."""
+    B, N, C, H, W = x5.shape
+    q = x5.reshape(B, N, -1)
+    energy = torch.bmm(q, q.transpose(1, 2))
+    energy_new = energy.max(dim=-1, keepdim=True)[0].expand_as(energy) - energy
+    att = torch.softmax(energy_new, dim=-1)
+    out = torch.bmm(att, q).reshape(B, N, C, H, W)
+    return (gamma * out + x5).reshape(B, N * C, H, W)
+
+
+def han_csam(P: Dict, x: torch.Tensor) -> torch.Tensor:
+    """CSAM_Module (han.py:36-52): one 3x3x3 Conv3d over the (C, H, W) volume, sigmoid, x * (gamma * s) + x."""
+    s = torch.sigmoid(F.conv3d(x.unsqueeze(1), P["csa.conv.weight"], P["csa.conv.bias"], padding=1))
+    return x * (P["csa.gamma"] * s).reshape(x.shape) + x
+
+
+def han_forward(P: Dict, x: torch.Tensor, cfg: Dict) -> torch.Tensor:
+    """han.py:90-113: the RCAN trunk whose ng + 1 body outputs are stacked (newest first, :94-99), layer attention + last_conv
+    on the stack, channel-spatial attention on the trunk output, `last` on their concatenation, long skip, tail."""
+    dt = x.dtype
+    P = {k: v.to(dt) for k, v in P.items()}
+    x = F.conv2d(x, P["sub_mean.weight"], P["sub_mean.bias"])
+    x = conv3x3(P, "head.0", x)
+    nb, ng = cfg["n_resblocks"], cfg["n_resgroups"]
+    res, stack = x, []
+    for gi in range(ng):
+        r = res
+        for bi in range(nb):
+            p = f"body.{gi}.body.{bi}.body"
+            t = conv3x3(P, p + ".2", torch.relu(conv3x3(P, p + ".0", r)))
+            r = channel_attention(P, p + ".3", t) + r
+        res = conv3x3(P, f"body.{gi}.body.{nb}", r) + res
+        stack.insert(0, res)
+    res = conv3x3(P, f"body.{ng}", res)
+    stack.insert(0, res)
+    out2 = conv3x3(P, "last_conv", han_lam(torch.stack(stack, dim=1), P["la.gamma"]))
+    out1 = han_csam(P, res)
+    res = conv3x3(P, "last", torch.cat([out1, out2], dim=1)) + x
+    y = conv3x3(P, "tail.1", _upsampler(P, "tail.0", res, cfg["scale"], cfg["n_feats"]))
+    return F.conv2d(y, P["add_mean.weight"], P["add_mean.bias"])
+
+
 # --------------------------------------------------------------------------- Model.inference + tiler
 def quantize_u8(y: torch.Tensor, img_range: float) -> torch.Tensor:
     """common.py:44-45 -- [3,H,W] float -> [H,W,3] uint8 (round half to even, clip)."""

@@ -248,6 +248,29 @@ def rcan_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
     return sd
 
 
+HAN_DEFAULT = dict(scale=4, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=20, n_resgroups=10, reduction=16)
+# (han.py:87 hard-codes `n_feats * 11` input channels for last_conv, i.e. n_resgroups must be 10; the tiny model keeps that)
+HAN_TINY = dict(scale=4, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=1, n_resgroups=10, reduction=16)
+
+
+def han_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of reference HAN(**cfg) (han.py:55-88: the RCAN trunk plus csa = CSAM_Module :36-52, la = LAM_Module :12-33,
+    last_conv, last), synthetic values.  The two gammas are zero-initialised upstream; here they are O(1) so that both attention
+    modules take part in the output."""
+    g = _gen(seed)
+    sd = rcan_weights(cfg, seed + 1000)
+    tail = OrderedDict((k, sd.pop(k)) for k in list(sd.keys()) if k.startswith("tail."))
+    F = cfg["n_feats"]
+    sd["csa.gamma"] = torch.tensor([0.7])
+    sd["csa.conv.weight"] = torch.randn(1, 1, 3, 3, 3, generator=g) * 0.3
+    sd["csa.conv.bias"] = torch.randn(1, generator=g) * 0.1
+    sd["la.gamma"] = torch.tensor([0.5])
+    _conv(g, sd, "last_conv", F, 11 * F, gain=0.5)
+    _conv(g, sd, "last", F, 2 * F, gain=0.7)
+    sd.update(tail)
+    return sd
+
+
 def image_batch(shape, seed: int = 1234) -> torch.Tensor:
     """Synthetic LR input in [0,1] (torch.rand, seed 1234)."""
     return torch.rand(*shape, generator=_gen(seed), dtype=torch.float32)

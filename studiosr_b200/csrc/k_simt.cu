@@ -986,6 +986,141 @@ int launch_channel_attention(const CaArgs& a, cudaStream_t s) {
   return SSR_OK;
 }
 
+// =============================================================================================
+// HAN (han.py): layer attention (LAM_Module :12-33) and channel-spatial attention (CSAM_Module :36-52)
+// The N = 11 stacked feature maps live as N fp32 planes [B*HW][ld]; the flattened C*H*W axis of the reference is any fixed
+// order of one image's (pixel, channel) pairs, so the pixel-major planes serve as they are.
+// =============================================================================================
+constexpr int HAN_N = 11, HAN_NP = HAN_N * (HAN_N + 1) / 2;
+// stage 1: energy[b][n][m] = sum over one image of X_n X_m (upper triangle, fp64 accumulation across blocks)
+__global__ void __launch_bounds__(256) han_gram_kernel(const float* stack, size_t plane, int ld, int HW, int C, double* energy) {
+  __shared__ float red[8][HAN_NP];
+  const int b = blockIdx.y;
+  const size_t n_el = (size_t)HW * C;
+  float acc[HAN_NP];
+#pragma unroll
+  for (int i = 0; i < HAN_NP; ++i) acc[i] = 0.0f;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = e / C;
+    const int c = (int)(e - p * C);
+    const float* src = stack + ((size_t)b * HW + p) * ld + c;
+    float v[HAN_N];
+#pragma unroll
+    for (int n = 0; n < HAN_N; ++n) v[n] = src[(size_t)n * plane];
+    int k = 0;
+#pragma unroll
+    for (int n = 0; n < HAN_N; ++n)
+#pragma unroll
+      for (int m2 = n; m2 < HAN_N; ++m2) acc[k] = fmaf(v[n], v[m2], acc[k]), ++k;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < HAN_NP; ++i) {
+    float a = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp][i] = a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HAN_NP; i += blockDim.x) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)red[w][i];
+    atomicAdd(energy + (size_t)b * HAN_NP + i, t);
+  }
+}
+// stage 2: attention = softmax(row max - energy) (han.py:24-26); out[n] = gamma * sum_m attention[n][m] X_m + X_n, written as the
+// [pixel][n * C + c] operand of last_conv
+__global__ void __launch_bounds__(256) han_lam_apply_kernel(const float* stack, size_t plane, int ld, int HW, int C, const double* energy,
+                                                            const float* gamma, void* out, int ld_out, int elem, int rtf32) {
+  __shared__ float att[HAN_N][HAN_N];
+  const int b = blockIdx.y;
+  if (threadIdx.x < HAN_N) {
+    const int n = threadIdx.x;
+    double e[HAN_N], mx = -1e300;
+    for (int m2 = 0; m2 < HAN_N; ++m2) {
+      const int lo = n < m2 ? n : m2, hi = n < m2 ? m2 : n;
+      e[m2] = energy[(size_t)b * HAN_NP + lo * HAN_N - lo * (lo - 1) / 2 + (hi - lo)];
+      mx = e[m2] > mx ? e[m2] : mx;
+    }
+    // energy_new = max - e >= 0; its softmax, shifted by its own maximum (= max - min e)
+    double mn = 1e300, sum = 0.0;
+    for (int m2 = 0; m2 < HAN_N; ++m2) mn = e[m2] < mn ? e[m2] : mn;
+    for (int m2 = 0; m2 < HAN_N; ++m2) {
+      e[m2] = exp((mx - e[m2]) - (mx - mn));
+      sum += e[m2];
+    }
+    for (int m2 = 0; m2 < HAN_N; ++m2) att[n][m2] = (float)(e[m2] / sum);
+  }
+  __syncthreads();
+  const float g = gamma[0];
+  const size_t n_el = (size_t)HW * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = e / C;
+    const int c = (int)(e - p * C);
+    const size_t row = (size_t)b * HW + p;
+    const float* src = stack + row * ld + c;
+    float v[HAN_N];
+#pragma unroll
+    for (int n = 0; n < HAN_N; ++n) v[n] = src[(size_t)n * plane];
+#pragma unroll
+    for (int n = 0; n < HAN_N; ++n) {
+      float a = 0.0f;
+#pragma unroll
+      for (int m2 = 0; m2 < HAN_N; ++m2) a = fmaf(att[n][m2], v[m2], a);
+      store_elem(out, row * ld_out + (size_t)n * C + c, elem, fmaf(g, a, v[n]), rtf32);
+    }
+  }
+}
+int launch_han_lam(const float* stack, size_t plane, int ld, int B, int HW, int C, double* energy, const float* gamma, void* out,
+                   int ld_out, int elem, int rtf32, cudaStream_t s) {
+  SSR_CUDA(cudaMemsetAsync(energy, 0, (size_t)B * HAN_NP * sizeof(double), s));
+  const int blocks = (int)std::min<size_t>(((size_t)HW * C + 255) / 256, 256);
+  ProfScope prof("han_lam", 2.0 * B * HW * C * (HAN_NP + HAN_N * HAN_N), (double)B * HW * C * (2.0 * HAN_N * 4 + HAN_N * elem), s);
+  han_gram_kernel<<<dim3(blocks, B), 256, 0, s>>>(stack, plane, ld, HW, C, energy);
+  count_launch();
+  han_lam_apply_kernel<<<dim3(blocks, B), 256, 0, s>>>(stack, plane, ld, HW, C, energy, gamma, out, ld_out, elem, rtf32);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+// CSAM: s = sigmoid(Conv3d(1, 1, 3, padding 1) over the (C, H, W) volume); out = x * (gamma * s) + x
+__global__ void __launch_bounds__(256) han_csam_kernel(const float* x, int ld, int B, int H, int W, int C, const float* w27, const float* bias,
+                                                       const float* gamma, void* out, int ld_out, int elem, int rtf32) {
+  const size_t n_el = (size_t)B * H * W * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const size_t p = e / C;
+    const int xx = (int)(p % W), yy = (int)((p / W) % H), b = (int)(p / ((size_t)W * H));
+    float a = bias[0];
+    for (int dc = 0; dc < 3; ++dc) {
+      const int cc = c + dc - 1;
+      if (cc < 0 || cc >= C) continue;
+      for (int dy = 0; dy < 3; ++dy) {
+        const int y2 = yy + dy - 1;
+        if (y2 < 0 || y2 >= H) continue;
+        for (int dx = 0; dx < 3; ++dx) {
+          const int x2 = xx + dx - 1;
+          if (x2 < 0 || x2 >= W) continue;
+          a = fmaf(w27[(dc * 3 + dy) * 3 + dx], x[(((size_t)b * H + y2) * W + x2) * ld + cc], a);
+        }
+      }
+    }
+    const float v = x[p * ld + c];
+    const float sgm = 1.0f / (1.0f + expf(-a));
+    store_elem(out, p * ld_out + c, elem, fmaf(v, gamma[0] * sgm, v), rtf32);
+  }
+}
+int launch_han_csam(const float* x, int ld, int B, int H, int W, int C, const float* w27, const float* bias, const float* gamma,
+                    void* out, int ld_out, int elem, int rtf32, cudaStream_t s) {
+  const size_t n = (size_t)B * H * W * C;
+  ProfScope prof("han_csam", 2.0 * 27 * n, (double)n * (4 + elem), s);
+  han_csam_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 32), 256, 0, s>>>(x, ld, B, H, W, C, w27, bias, gamma, out, ld_out, elem,
+                                                                                      rtf32);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 // ---- channel attention backward (training; see CaBwdArgs) ----
 // stage 1: partial[b][split][c] = sum over a pixel slab of G * t
 __global__ void __launch_bounds__(256) ca_bwd_reduce_kernel(const float* G, const __nv_bfloat16* t, int ld, int HW, int C, int nsplit,

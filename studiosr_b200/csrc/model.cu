@@ -615,6 +615,23 @@ static int finalize_rcan(ssr_model* m) {  // rcan.py:39-66
   return SSR_OK;
 }
 
+static int finalize_han(ssr_model* m) {  // han.py:55-88 = the RCAN trunk (finalize_rcan) + csa, la, last_conv, last
+  const ssr_model_config& c = m->cfg;
+  SSR_CHECK(c.n_resgroups == 10, SSR_E_INVALID, "HAN: last_conv takes n_feats * 11 channels (han.py:87), i.e. n_resgroups must be 10 (got %d)",
+            c.n_resgroups);
+  SSR_CHECK(c.n_feats % 64 == 0, SSR_E_INVALID, "HAN: n_feats %d is not a multiple of 64", c.n_feats);
+  SSR_TRY(finalize_rcan(m));
+  const int F = m->F;
+  SSR_TRY(pack_conv(m, "last_conv", F, 11 * F, 0, &m->han_last_conv));
+  SSR_TRY(pack_conv(m, "last", F, 2 * F, 0, &m->han_last));
+  m->csa_w = pack_raw(m, "csa.conv.weight", 27);
+  m->csa_b = pack_raw(m, "csa.conv.bias", 1);
+  m->csa_gamma = pack_raw(m, "csa.gamma", 1);
+  m->la_gamma = pack_raw(m, "la.gamma", 1);
+  if (m->csa_w == (size_t)-1 || m->csa_b == (size_t)-1 || m->csa_gamma == (size_t)-1 || m->la_gamma == (size_t)-1) return SSR_E_STATE;
+  return SSR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // workspace planning
 static void padded_size(const ssr_model* m, int H, int W, int pad_mode, int* Hp, int* Wp) {
@@ -1456,6 +1473,127 @@ static int forward_rcan(ssr_model* m, const InputSpec& in, const OutputSpec& out
   return run_tail(m, W.tmp, FP, B, h, w, W.hr[0], W.hr[1], h, w, m->add_bias, 1.0f, out, s);
 }
 
+// ---- HAN (han.py:90-113) ----
+struct HanWs {
+  float *x, *r, *t2, *partial, *stack;
+  double* energy;
+  void *rb, *tmp, *lam, *cat, *hr[2];
+  int nsplit;
+};
+static size_t plan_han(const ssr_model* m, void* base, int B, int H, int W, HanWs* w) {
+  Carver c(base);
+  const size_t T = (size_t)B * H * W, e = m->elem;
+  const int HW = H * W;
+  w->nsplit = HW >= 16384 ? 64 : (HW + 255) / 256;
+  w->x = (float*)c.take(T * m->FP * 4);
+  w->r = (float*)c.take(T * m->FP * 4);
+  w->t2 = (float*)c.take(T * m->FP * 4);
+  w->stack = (float*)c.take(11 * T * m->FP * 4);  // plane n: 0 = body's last conv, 1 + k = group 9 - k (newest first, han.py:94-99)
+  w->partial = (float*)c.take((size_t)B * w->nsplit * m->F * 4);
+  w->energy = (double*)c.take((size_t)B * 66 * 8);
+  w->rb = c.take(T * m->FP * e);
+  w->tmp = c.take(T * m->FP * e);
+  w->lam = c.take(T * 11 * m->FP * e);
+  w->cat = c.take(T * 2 * m->FP * e);
+  size_t need[2] = {0, 0};
+  size_t px = T;
+  for (size_t i = 0; i < m->up.size(); ++i) {
+    px *= (size_t)m->up[i].ps_r * m->up[i].ps_r;
+    if (px * m->FP > need[i & 1]) need[i & 1] = px * m->FP;
+  }
+  for (int i = 0; i < 2; ++i) w->hr[i] = need[i] ? c.take(need[i] * e) : nullptr;
+  return c.off + 1024;
+}
+
+static int forward_han(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, void* ws, size_t ws_bytes,
+                       cudaStream_t s) {
+  const ssr_model_config& c = m->cfg;
+  HanWs W;
+  const size_t need = plan_han(m, ws, B, h, w, &W);
+  SSR_CHECK(ws && need <= ws_bytes, SSR_E_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+  const int FP = m->FP, F = m->F, e = m->elem, R = F / c.reduction, ng = c.n_resgroups;
+  const int rtf = c.precision == SSR_PREC_TF32;
+  const size_t T = (size_t)B * h * w, plane = T * FP;
+  {  // sub_mean + head (han.py:91-92)
+    ConvFirstArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = in.in; a.in_u8 = in.in_u8; a.fh = in.fh; a.fw = in.fw;
+    a.tile_mode = in.tile_mode; a.tile = in.tile; a.stride = in.stride; a.tiles_x = in.tiles_x; a.tile_begin = in.tile_begin;
+    a.h = h; a.w = w; a.Hp = h; a.Wp = w; a.pad_mode = 2; a.B = B;
+    a.in_scale = (in.in_u8 && c.img_range == 1.0f) ? 1.0f / 255.0f : 1.0f;
+    for (int i = 0; i < 3; ++i) a.in_shift[i] = m->sub_bias[i];
+    a.Wc = m->dev<float>(m->conv_first_w);
+    a.bias = m->dev<float>(m->conv_first_b);
+    a.Cout = F;
+    a.out_f32 = W.x; a.ld_f32 = FP; a.out_T = W.rb; a.ld_T = FP; a.elem = e;
+    a.round_tf32 = rtf;
+    SSR_TRY(launch_conv_first(a, s));
+  }
+  const float* gcur = W.x;  // input of the current residual group (fp32 stream)
+  for (int g = 0; g < ng; ++g) {
+    const float* rcur = gcur;
+    for (int b = 0; b < c.n_resblocks; ++b) {  // RCAB (rcan.py:21-24)
+      const int i = g * c.n_resblocks + b;
+      GemmArgs ga = gemm_base(m, m->res_a[i], W.rb, FP, B, h, w);
+      ga.act = ACT_RELU;
+      ga.out_T = W.tmp;
+      ga.ld_T = FP;
+      SSR_TRY(run_gemm(m, ga, s));
+      GemmArgs gb = gemm_base(m, m->res_b[i], W.tmp, FP, B, h, w);
+      gb.out_f32 = W.t2;
+      gb.ld_f32 = FP;
+      SSR_TRY(run_gemm(m, gb, s));
+      CaArgs ca;
+      memset(&ca, 0, sizeof(ca));
+      ca.t = W.t2; ca.res = rcur; ca.ld = FP; ca.B = B; ca.HW = h * w; ca.C = F; ca.CP = FP; ca.R = R;
+      ca.W1 = m->dev<float>(m->ca[i].w1); ca.b1 = m->dev<float>(m->ca[i].b1);
+      ca.W2 = m->dev<float>(m->ca[i].w2); ca.b2 = m->dev<float>(m->ca[i].b2);
+      ca.partial = W.partial; ca.nsplit = W.nsplit;
+      ca.out_f32 = W.r; ca.out_T = W.rb; ca.ld_T = FP; ca.elem = e; ca.round_tf32 = rtf;
+      ca.scale = 1.0f;
+      SSR_TRY(launch_channel_attention(ca, s));
+      rcur = W.r;
+    }
+    // group tail conv + group skip (rcan.py:33-36); the group's output is plane ng - g of the stack
+    float* slot = W.stack + (size_t)(ng - g) * plane;
+    GemmArgs gt = gemm_base(m, m->grp_tail[g], W.rb, FP, B, h, w);
+    gt.res = gcur;
+    gt.ldres = FP;
+    gt.out_f32 = slot;
+    gt.ld_f32 = FP;
+    gt.out_T = W.rb;
+    gt.ld_T = FP;
+    SSR_TRY(run_gemm(m, gt, s));
+    gcur = slot;
+  }
+  {  // body's last conv (han.py:93-99, no skip here): plane 0
+    GemmArgs g = gemm_base(m, m->body_tail, W.rb, FP, B, h, w);
+    g.out_f32 = W.stack;
+    g.ld_f32 = FP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  // layer attention over the 11 planes (han.py:101) -> last_conv's operand [pixel][11 F]
+  SSR_TRY(launch_han_lam(W.stack, plane, FP, B, h * w, F, W.energy, m->dev<float>(m->la_gamma), W.lam, 11 * FP, e, rtf, s));
+  {  // out2 = last_conv(.) (han.py:102) -> channels [F, 2F) of the concatenation
+    GemmArgs g = gemm_base(m, m->han_last_conv, W.lam, 11 * FP, B, h, w);
+    g.out_T = reinterpret_cast<uint8_t*>(W.cat) + (size_t)FP * e;
+    g.ld_T = 2 * FP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  // out1 = csa(out1) (han.py:104) -> channels [0, F)
+  SSR_TRY(launch_han_csam(W.stack, FP, B, h, w, F, m->dev<float>(m->csa_w), m->dev<float>(m->csa_b), m->dev<float>(m->csa_gamma), W.cat,
+                          2 * FP, e, rtf, s));
+  {  // res = last(cat) + x (han.py:105-108)
+    GemmArgs g = gemm_base(m, m->han_last, W.cat, 2 * FP, B, h, w);
+    g.res = W.x;
+    g.ldres = FP;
+    g.out_T = W.tmp;
+    g.ld_T = FP;
+    SSR_TRY(run_gemm(m, g, s));
+  }
+  return run_tail(m, W.tmp, FP, B, h, w, W.hr[0], W.hr[1], h, w, m->add_bias, 1.0f, out, s);
+}
+
 int check_ready(ssr_model* m) {
   SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
   SSR_CHECK(m->finalized, SSR_E_STATE, "model not finalised (call ssr_model_finalize)");
@@ -1470,6 +1608,7 @@ static int forward_any(ssr_model* m, const InputSpec& in, const OutputSpec& out,
   SSR_CHECK(B > 0 && h > 0 && w > 0, SSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, h, w);
   if (m->cfg.arch == SSR_ARCH_SWINIR) return forward_swinir(m, in, out, B, h, w, pad_mode, ws, ws_bytes, s);
   if (m->cfg.arch == SSR_ARCH_RCAN) return forward_rcan(m, in, out, B, h, w, ws, ws_bytes, s);
+  if (m->cfg.arch == SSR_ARCH_HAN) return forward_han(m, in, out, B, h, w, ws, ws_bytes, s);
   if (m->cfg.arch == SSR_ARCH_HAT) return forward_hat(m, in, out, B, h, w, ws, ws_bytes, s);
   return forward_edsr(m, in, out, B, h, w, ws, ws_bytes, s);
 }
@@ -1484,6 +1623,10 @@ static size_t workspace_any(const ssr_model* m, int B, int H, int W, int pad_mod
   if (m->cfg.arch == SSR_ARCH_RCAN) {
     RcanWs w;
     return plan_rcan(m, nullptr, B, H, W, &w);
+  }
+  if (m->cfg.arch == SSR_ARCH_HAN) {
+    HanWs w;
+    return plan_han(m, nullptr, B, H, W, &w);
   }
   if (m->cfg.arch == SSR_ARCH_HAT) {
     int Hp, Wp;
@@ -1569,7 +1712,7 @@ int ssr_device_check(int device) {
 
 int ssr_model_create(const ssr_model_config* cfg, int device, ssr_model_t** out) {
   SSR_CHECK(cfg && out, SSR_E_INVALID, "null argument");
-  SSR_CHECK(cfg->arch >= SSR_ARCH_SWINIR && cfg->arch <= SSR_ARCH_HAT, SSR_E_INVALID, "unknown arch %d", cfg->arch);
+  SSR_CHECK(cfg->arch >= SSR_ARCH_SWINIR && cfg->arch <= SSR_ARCH_HAN, SSR_E_INVALID, "unknown arch %d", cfg->arch);
   SSR_CHECK(cfg->precision >= 0 && cfg->precision <= 3, SSR_E_INVALID, "unknown precision %d", cfg->precision);
   SSR_CHECK(cfg->scale >= 1 && cfg->scale <= 8, SSR_E_INVALID, "bad scale %d", cfg->scale);
   if (cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_HAT)
@@ -1596,6 +1739,7 @@ int ssr_model_finalize(ssr_model_t* m) {
   m->host_arena.clear();
   int r = m->cfg.arch == SSR_ARCH_SWINIR ? finalize_swinir(m)
           : m->cfg.arch == SSR_ARCH_RCAN ? finalize_rcan(m)
+          : m->cfg.arch == SSR_ARCH_HAN  ? finalize_han(m)
           : m->cfg.arch == SSR_ARCH_HAT  ? finalize_hat(m)
                                          : finalize_edsr(m);
   if (r != SSR_OK) return r;

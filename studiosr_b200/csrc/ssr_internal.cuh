@@ -259,6 +259,14 @@ struct CaArgs {
 };
 int launch_channel_attention(const CaArgs& a, cudaStream_t s);
 
+// HAN (han.py:12-52).  stack: 11 fp32 planes [B*HW][ld], `plane` elements apart (plane 0 = newest body output).
+// launch_han_lam: layer attention, out = T-typed [B*HW][ld_out] with column n * C + c; energy = scratch [B][66] doubles.
+int launch_han_lam(const float* stack, size_t plane, int ld, int B, int HW, int C, double* energy, const float* gamma, void* out,
+                   int ld_out, int elem, int rtf32, cudaStream_t s);
+// launch_han_csam: x fp32 [B*H*W][ld] -> out = x * (gamma * sigmoid(conv3d(x))) + x, T-typed [B*H*W][ld_out]
+int launch_han_csam(const float* x, int ld, int B, int H, int W, int C, const float* w27, const float* bias, const float* gamma,
+                    void* out, int ld_out, int elem, int rtf32, cudaStream_t s);
+
 // backward of out = res + t * sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2) (common.py:156-170 inside rcan.py:21-24):
 //   dt = G * gate + W1^T dz1 / HW,  dz1 = relu'(.) * W2^T dz2,  dz2 = gate (1 - gate) * sum_hw G t   (+ the four parameter gradients)
 struct CaBwdArgs {

@@ -72,6 +72,9 @@ struct ssr_model {
     size_t w1 = 0, b1 = 0, w2 = 0, b2 = 0;  // fp32 [R][C], [R], [C][R], [C]
   };
   std::vector<CaP> ca;
+  // HAN: the RCAN trunk plus last_conv (11 F -> F), last (2 F -> F), the CSAM Conv3d (27 weights + bias) and the two gammas
+  Lin han_last_conv, han_last;
+  size_t csa_w = 0, csa_b = 0, csa_gamma = 0, la_gamma = 0;
 
   ssr_train_state* train = nullptr;  // training executor state (train.cu), owned
 

@@ -1,7 +1,8 @@
 from .common import Model
 from .edsr import EDSR
+from .han import HAN
 from .hat import HAT
 from .rcan import RCAN
 from .swinir import SwinIR
 
-__all__ = ["Model", "SwinIR", "HAT", "EDSR", "RCAN"]
+__all__ = ["Model", "SwinIR", "HAT", "EDSR", "RCAN", "HAN"]

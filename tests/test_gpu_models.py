@@ -187,6 +187,58 @@ def test_rcan_matches_reference_golden(name, prec, golden_meta):
         _check_bf16(name, y, ref)
 
 
+HAN_CASES = ["han_tiny_x4_2x12x20", "han_tiny_x2_1x9x11", "han_tiny_x3_1x8x8", "han_full_x4_1x16x16"]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "tf32x3", "bf16"])
+@pytest.mark.parametrize("name", HAN_CASES)
+def test_han_matches_reference_golden(name, prec, golden_meta):
+    """HAN forward (han.py:90-113: the RCAN trunk, layer attention over its 11 outputs, channel-spatial attention, last_conv /
+    last) against the reference's own outputs."""
+    from studiosr_b200.models import HAN
+
+    c = golden_meta[name]
+    m = HAN(**c["cfg"])
+    m.load_state_dict(synth.han_weights(c["cfg"], c["wseed"]), strict=True)
+    m = m.cuda().eval()
+    m.precision = prec
+    x = synth.image_batch(c["shape"], c["xseed"]).cuda()
+    with torch.no_grad():
+        y = m(x).float().cpu()
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    err = (y - ref).abs().max().item()
+    if prec in ABS_TOL:
+        tol = ABS_TOL[prec] * (4 if "full" in name else 1)  # 400 convs deep: summation-order noise accumulates
+        assert err <= tol, f"{name} [{prec}] max-abs {err:.3e}"
+    else:  # no stored reference-autocast error for HAN: bf16 is held to RCAN's level on the same trunk
+        rms = (y - ref).pow(2).mean().sqrt().item()
+        assert err <= (1.2e-1 if "full" in name else 4e-2) and rms <= (2.5e-2 if "full" in name else 8e-3), (name, err, rms)
+
+
+def test_han_inference_u8_and_train_mode_forward():
+    """The reference-facing entry points on HAN: Model.inference (uint8 in / out) equals the quantised fp32 forward, and the
+    train-mode forward runs (the backward is not built and says so)."""
+    from studiosr_b200.models import HAN
+
+    cfg = synth.HAN_TINY
+    m = HAN(**cfg)
+    m.load_state_dict(synth.han_weights(cfg, 41), strict=True)
+    m = m.cuda().eval()
+    img = synth.smooth_image_u8(20, 28, seed=5)
+    out = m.inference(img)
+    x = torch.from_numpy(img.astype(np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)
+    ref = O.quantize_u8(O.han_forward(synth.han_weights(cfg, 41), x, cfg)[0], 1.0).numpy()
+    d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert out.shape == (80, 112, 3) and d.max() <= 1 and (d > 0).mean() < 2e-3
+    m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x.cuda())
+    assert y.shape == (1, 3, 80, 112)
+    with pytest.raises(NotImplementedError, match="no backward kernels"):
+        y.sum().backward()
+
+
 def test_inference_u8_matches_reference(golden_meta):
     g = load_golden("swinir_tiny_x4_inference_u8")
     m = _swinir(golden_meta["swinir_ops"]["cfg"], 11)
@@ -257,7 +309,7 @@ def test_reference_shape_tests_pass_unchanged():
 
 
 def test_reference_shape_tests_hat_rcan_pass_unchanged():
-    """tests/models/test_hat.py:8-21 and test_rcan.py:8-25 of the reference on the drop-in: default full-size configs, train
+    """tests/models/test_hat.py:8-21, test_rcan.py:8-25 and test_han.py:8-25 of the reference on the drop-in: default full-size configs, train
     mode with grad enabled (as the reference's tests call them), every scale."""
     from studiosr_b200.models import HAT, RCAN
 
@@ -268,6 +320,14 @@ def test_reference_shape_tests_hat_rcan_pass_unchanged():
         del model
     for scale in (2, 3, 4, 8):
         model = RCAN(scale=scale, n_colors=3).cuda()
+        for hw in (8, 12):
+            y = model(torch.randn(1, 3, hw, hw).cuda())
+            assert y.shape == (1, 3, scale * hw, scale * hw) and torch.isfinite(y).all()
+        del model
+    from studiosr_b200.models import HAN  # tests/models/test_han.py:8-25
+
+    for scale in (2, 3, 4, 8):
+        model = HAN(scale=scale, n_colors=3).cuda()
         for hw in (8, 12):
             y = model(torch.randn(1, 3, hw, hw).cuda())
             assert y.shape == (1, 3, scale * hw, scale * hw) and torch.isfinite(y).all()

@@ -20,6 +20,7 @@ EDSR_CASES = ["edsr_tiny_x4_2x12x20", "edsr_tiny_x2_1x9x11", "edsr_tiny_x3_1x8x8
 HAT_CASES = ["hat_tiny_x4_eval_2x20x40", "hat_tiny_x4_train_1x32x32", "hat_tiny_x2_eval_1x16x48", "hat_tiny_x3_eval_1x17x17",
              "hat_full_x4_eval_1x64x64"]
 RCAN_CASES = ["rcan_tiny_x4_2x12x20", "rcan_tiny_x2_1x9x11", "rcan_tiny_x3_1x8x8", "rcan_full_x4_1x24x24"]
+HAN_CASES = ["han_tiny_x4_2x12x20", "han_tiny_x2_1x9x11", "han_tiny_x3_1x8x8", "han_full_x4_1x16x16"]
 
 
 @pytest.mark.parametrize("name", SWINIR_CASES)
@@ -64,6 +65,18 @@ def test_rcan_oracle_matches_reference_golden(name, golden_meta):
     P = synth.rcan_weights(c["cfg"], c["wseed"])
     x = synth.image_batch(c["shape"], c["xseed"])
     y = O.rcan_forward(P, x, c["cfg"])
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    assert (y - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("name", HAN_CASES)
+def test_han_oracle_matches_reference_golden(name, golden_meta):
+    """oracle/sr_oracle.py:han_forward (LAM han.py:12-33, CSAM :36-52) vs the reference's own HAN forward (fixtures: oracle/make_golden_han.py)."""
+    c = golden_meta[name]
+    P = synth.han_weights(c["cfg"], c["wseed"])
+    x = synth.image_batch(c["shape"], c["xseed"])
+    y = O.han_forward(P, x, c["cfg"])
     ref = torch.from_numpy(load_golden(name)["y"])
     assert list(y.shape) == c["out_shape"]
     assert (y - ref).abs().max().item() <= 2e-5
