@@ -40,7 +40,8 @@ enum {
   SSR_E_WORKSPACE = -5  /* workspace too small */
 };
 
-enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1, SSR_ARCH_RCAN = 2, SSR_ARCH_HAT = 3, SSR_ARCH_HAN = 4 };
+enum { SSR_ARCH_SWINIR = 0, SSR_ARCH_EDSR = 1, SSR_ARCH_RCAN = 2, SSR_ARCH_HAT = 3, SSR_ARCH_HAN = 4,
+       SSR_ARCH_SWINFIR = 5 /* SwinIR's config; every RSTB conv and conv_after_body is an SFB (swinfir.py:68-114) */ };
 
 /* arithmetic of the contractions */
 enum {

@@ -171,14 +171,34 @@ def _upsampler(P: Dict, pre: str, x: torch.Tensor, scale: int, n_feats: int, num
 
 
 # --------------------------------------------------------------------------- SwinIR
+def conv1x1(P: Dict, name: str, x: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d(cin, cout, 1, 1, 0) on NCHW."""
+    return F.conv2d(x, P[name + ".weight"], P[name + ".bias"])
+
+
+def sfb(P: Dict, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """SwinFIR's SFB (swinfir.py:68-80) on NCHW: fusion(cat[SpatialB(x) :53-65, SpectralTransform(x) :37-50]) with the
+    FourierUnit :9-34 (rfftn over (H, W), norm "ortho"; 1x1 conv + LeakyReLU(0.2) on [real | imag]; irfftn back to H x W)."""
+    sp = conv3x3(P, pre + ".S.body.2", F.leaky_relu(conv3x3(P, pre + ".S.body.0", x), 0.2)) + x
+    y = F.leaky_relu(conv1x1(P, pre + ".F.conv_before_fft.0", x), 0.2)
+    c = y.shape[1]
+    f = torch.fft.rfftn(y, dim=(-2, -1), norm="ortho")
+    f = F.leaky_relu(conv1x1(P, pre + ".F.fu.conv_layer", torch.cat((f.real, f.imag), dim=1)), 0.2)
+    fo = torch.fft.irfftn(torch.complex(f[:, :c], f[:, c:]), s=y.shape[-2:], dim=(-2, -1), norm="ortho")
+    sf = conv1x1(P, pre + ".F.conv_after_fft", fo + y)
+    return conv1x1(P, pre + ".fusion", torch.cat([sp, sf], dim=1))
+
+
 def swinir_forward(P: Dict, x: torch.Tensor, cfg: Dict, training: bool = False, drop_scale=None) -> torch.Tensor:
     """swinir.py:353-372 (+ forward_features :342-351, RSTB :245-246).  drop_scale [2 * n_blocks, B] = the stochastic-depth
-    factors of this step (row 2k / 2k+1: attention / MLP branch of block k), None = drop_path off.
+    factors of this step (row 2k / 2k+1: attention / MLP branch of block k), None = drop_path off.  cfg["sfb"] = True: SwinFIR
+    (swinfir.py:83-114): every RSTB conv and conv_after_body is an SFB.
 
     x: [B, n_colors, H, W] float -> [B, n_colors, s*H, s*W]."""
     dt = x.dtype
     P = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in P.items()}
     ws, s, C = cfg["window_size"], cfg["scale"], cfg["embed_dim"]
+    body_conv = sfb if cfg.get("sfb") else conv3x3
     h0, w0 = x.shape[2:]
     x = pad_for_train(x, ws) if training else pad_for_eval(x, ws)
     mean = torch.tensor(RGB_MEAN, dtype=dt).view(1, 3, 1, 1)
@@ -194,9 +214,9 @@ def swinir_forward(P: Dict, x: torch.Tensor, cfg: Dict, training: bool = False, 
             drop = None if drop_scale is None else (drop_scale[2 * k], drop_scale[2 * k + 1])
             t = swin_block(P, f"layers.{li}.residual_group.blocks.{bi}", t, cfg["num_heads"][li], ws, shift, drop)
             k += 1
-        t = conv3x3(P, f"layers.{li}.conv", t.permute(0, 3, 1, 2)).permute(0, 2, 3, 1) + g
+        t = body_conv(P, f"layers.{li}.conv", t.permute(0, 3, 1, 2)).permute(0, 2, 3, 1) + g
     t = layer_norm(t, P["norm.weight"], P["norm.bias"])
-    y = conv3x3(P, "conv_after_body", t.permute(0, 3, 1, 2)) + x0
+    y = body_conv(P, "conv_after_body", t.permute(0, 3, 1, 2)) + x0
     if cfg["upsampler"] == "pixelshuffle":
         y = F.leaky_relu(conv3x3(P, "conv_before_upsample.0", y), 0.01)
         y = conv3x3(P, "conv_last", _upsampler(P, "upsample", y, s, 64))

@@ -122,6 +122,38 @@ def swinir_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]"
     return sd
 
 
+def _conv1(g, sd, name, cout, cin, gain=1.0):
+    _conv(g, sd, name, cout, cin, k=1, gain=gain)
+
+
+def swinfir_weights(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of reference SwinFIR(**cfg) (swinfir.py:83-114): SwinIR whose RSTB convs and conv_after_body are SFB modules
+    (S = SpatialB, F = SpectralTransform with the FourierUnit, fusion), synthetic values."""
+    g = _gen(seed + 500)
+    sd = swinir_weights(cfg, seed)
+    C = cfg["embed_dim"]
+    out = OrderedDict()
+
+    def sfb(pre):
+        _conv(g, out, pre + ".S.body.0", C, C, gain=0.7)
+        _conv(g, out, pre + ".S.body.2", C, C, gain=0.5)
+        _conv1(g, out, pre + ".F.conv_before_fft.0", C // 2, C)
+        _conv1(g, out, pre + ".F.fu.conv_layer", C, C)
+        _conv1(g, out, pre + ".F.conv_after_fft", C, C // 2, gain=0.7)
+        _conv1(g, out, pre + ".fusion", C, 2 * C, gain=0.5)
+
+    for k, v in sd.items():  # keep the module order of the reference's state_dict
+        if k.endswith(".conv.weight") and k.startswith("layers.") and k.count(".") == 3:
+            sfb(k[: -len(".weight")])
+        elif k == "conv_after_body.weight":
+            sfb("conv_after_body")
+        elif (k.endswith(".conv.bias") and k.startswith("layers.") and k.count(".") == 3) or k == "conv_after_body.bias":
+            continue
+        else:
+            out[k] = v
+    return out
+
+
 EDSR_DEFAULT = dict(scale=4, n_colors=3, img_range=1.0, n_feats=256, n_resblocks=32, res_scale=0.1)
 EDSR_TINY = dict(scale=4, n_colors=3, img_range=1.0, n_feats=64, n_resblocks=3, res_scale=0.1)
 RGB_MEAN = (0.4488, 0.4371, 0.4040)

@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssr_b200.so")
 
-SSR_ARCH_SWINIR, SSR_ARCH_EDSR, SSR_ARCH_RCAN, SSR_ARCH_HAT, SSR_ARCH_HAN = 0, 1, 2, 3, 4
+SSR_ARCH_SWINIR, SSR_ARCH_EDSR, SSR_ARCH_RCAN, SSR_ARCH_HAT, SSR_ARCH_HAN, SSR_ARCH_SWINFIR = 0, 1, 2, 3, 4, 5
 PREC_FP32, PREC_TF32, PREC_BF16, PREC_TF32X3 = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "tf32x3": PREC_TF32X3}
 PAD_EVAL, PAD_TRAIN = 0, 1

@@ -296,12 +296,36 @@ int pack_attn_fused_host(const float* Wqkv, const float* bqkv, const float* tabl
   return SSR_OK;
 }
 
+static bool is_swin(const ssr_model* m) { return m->cfg.arch == SSR_ARCH_SWINIR || m->cfg.arch == SSR_ARCH_SWINFIR; }
+
+// SFB (swinfir.py:68-80).  The 1x1 convs are Linears over pixels / spectrum bins; the fusion conv reads the concatenation
+// [S(x) | F(x)] whose halves are CP columns apart in the workspace, hence its column map.
+static int pack_sfb(ssr_model* m, const std::string& pre, Sfb* S) {
+  const int C = m->C, CP = m->CP, c2 = C / 2, c2P = round_up(c2, 64);
+  SSR_CHECK(C % 2 == 0, SSR_E_INVALID, "SwinFIR: embed_dim %d is odd", C);
+  auto one = [](int) { return 1.0f; };
+  SSR_TRY(pack_conv(m, pre + ".S.body.0", C, C, 0, &S->s0));
+  SSR_TRY(pack_conv(m, pre + ".S.body.2", C, C, 0, &S->s2));
+  SSR_TRY(pack_linear(m, pre + ".F.conv_before_fft.0", c2, C, c2P, CP, [=](int n) { return n < c2 ? n : -1; },
+                      [=](int k) { return k < C ? k : -1; }, one, &S->before));
+  SSR_TRY(pack_linear(m, pre + ".F.fu.conv_layer", C, C, CP, CP, [=](int n) { return n < C ? n : -1; }, [=](int k) { return k < C ? k : -1; },
+                      one, &S->fu));
+  SSR_TRY(pack_linear(m, pre + ".F.conv_after_fft", C, c2, CP, c2P, [=](int n) { return n < C ? n : -1; },
+                      [=](int k) { return k < c2 ? k : -1; }, one, &S->after));
+  SSR_TRY(pack_linear(m, pre + ".fusion", C, 2 * C, CP, 2 * CP, [=](int n) { return n < C ? n : -1; },
+                      [=](int k) { return k < C ? k : (k >= CP && k - CP < C ? C + k - CP : -1); }, one, &S->fusion));
+  return SSR_OK;
+}
+
 static int finalize_swinir(ssr_model* m) {
   const ssr_model_config& c = m->cfg;
   SSR_CHECK(c.n_colors == 3, SSR_E_INVALID, "n_colors must be 3");
   SSR_CHECK(c.window_size == 8 || c.precision == SSR_PREC_FP32, SSR_E_INVALID,
             "tensor-core window attention supports window_size 8 (got %d)", c.window_size);
   const int C = c.embed_dim;
+  m->sfb = c.arch == SSR_ARCH_SWINFIR;
+  SSR_CHECK(!m->sfb || c.precision != SSR_PREC_BF16, SSR_E_INVALID,
+            "SwinFIR runs in the fp32-class precisions (fp32 / tf32 / tf32x3): the reference trains and ships it in fp32 (swinfir.py:126)");
   m->C = C;
   m->CP = round_up(C, 64);
   m->HID = (int)(C * c.mlp_ratio);
@@ -373,11 +397,17 @@ static int finalize_swinir(ssr_model* m) {
     }
     char nm[64];
     snprintf(nm, sizeof(nm), "layers.%d.conv", li);
-    SSR_TRY(pack_conv(m, nm, C, C, 0, &L.conv));
+    if (m->sfb)
+      SSR_TRY(pack_sfb(m, nm, &L.sfb));
+    else
+      SSR_TRY(pack_conv(m, nm, C, C, 0, &L.conv));
     m->layers.push_back(L);
   }
   SSR_TRY(pack_ln(m, "norm", C, m->CP, &m->final_norm));
-  SSR_TRY(pack_conv(m, "conv_after_body", C, C, 0, &m->conv_after_body));
+  if (m->sfb)
+    SSR_TRY(pack_sfb(m, "conv_after_body", &m->sfb_after_body));
+  else
+    SSR_TRY(pack_conv(m, "conv_after_body", C, C, 0, &m->conv_after_body));
   std::vector<int> rs;
   upsampler_plan(c.scale, &rs);
   m->up.clear();
@@ -635,7 +665,7 @@ static int finalize_han(ssr_model* m) {  // han.py:55-88 = the RCAN trunk (final
 // ---------------------------------------------------------------------------------------------
 // workspace planning
 static void padded_size(const ssr_model* m, int H, int W, int pad_mode, int* Hp, int* Wp) {
-  if (m->cfg.arch != SSR_ARCH_SWINIR && m->cfg.arch != SSR_ARCH_HAT) {
+  if (!is_swin(m) && m->cfg.arch != SSR_ARCH_HAT) {
     *Hp = H;
     *Wp = W;
     return;
@@ -654,6 +684,9 @@ struct SwinWs {
   float *x0, *g, *t;
   void *xn, *qkv, *o, *hbuf, *tb, *cbu, *hr[2];
   size_t hr_elems[2];
+  // SwinFIR (fp32-class precisions only, so every buffer is fp32): SpatialB's hidden map, [S(x) | F(x)], the SpectralTransform's
+  // half-width maps before / after the Fourier unit, three half-spectrum arrays [B*Hp*(Wp/2+1)][CP]
+  float *sfb_s1, *sfb_cat, *sfb_y, *sfb_z, *sfb_fa, *sfb_fb, *sfb_fc;
 };
 
 static size_t plan_swinir(const ssr_model* m, void* base, int B, int Hp, int Wp, SwinWs* w) {
@@ -668,6 +701,16 @@ static size_t plan_swinir(const ssr_model* m, void* base, int B, int Hp, int Wp,
   w->hbuf = c.take(T * m->HP * e);
   w->tb = c.take(T * m->CP * e);
   w->cbu = c.take(T * 64 * e);
+  if (m->sfb) {
+    const size_t c2P = (size_t)round_up(m->C / 2, 64), Mf = (size_t)B * Hp * (Wp / 2 + 1);
+    w->sfb_s1 = (float*)c.take(T * m->CP * 4);
+    w->sfb_cat = (float*)c.take(T * 2 * m->CP * 4);
+    w->sfb_y = (float*)c.take(T * c2P * 4);
+    w->sfb_z = (float*)c.take(T * c2P * 4);
+    w->sfb_fa = (float*)c.take(Mf * m->CP * 4);
+    w->sfb_fb = (float*)c.take(Mf * m->CP * 4);
+    w->sfb_fc = (float*)c.take(Mf * m->CP * 4);
+  }
   // high-resolution ping-pong buffers of the pixel-shuffle tail (64 channels)
   size_t need[2] = {0, 0};
   size_t px = T;
@@ -836,6 +879,58 @@ static void debug_nonfinite(const char* what, int li, int bi, const void* p, siz
   }
 }
 
+// SFB(x) = fusion(cat[S(x), F(x)]) (swinfir.py:68-80) on pixel-major fp32 maps.  xa = x as the GEMM operand (tf32-rounded in
+// the tf32 mode), xr = x for the SpatialB skip.  `epi` puts the caller's epilogue (skip, fp32 / LayerNorm outputs) on the
+// fusion GEMM, which takes the place of the plain conv's.
+template <typename Epi>
+static int run_sfb(ssr_model* m, const Sfb& S, const void* xa, const float* xr, int B, int Hp, int Wp, const SwinWs& W, Epi epi,
+                   cudaStream_t s) {
+  const int CP = m->CP, c2 = m->C / 2, c2P = round_up(c2, 64), Wf = Wp / 2 + 1;
+  const int rtf = m->cfg.precision == SSR_PREC_TF32;
+  {  // S: conv - LeakyReLU(0.2) - conv + x (swinfir.py:53-65) -> columns [0, CP) of the concatenation
+    GemmArgs a = gemm_base(m, S.s0, xa, CP, B, Hp, Wp);
+    a.act = ACT_LEAKY;
+    a.slope = 0.2f;
+    a.out_T = W.sfb_s1;
+    a.ld_T = CP;
+    SSR_TRY(run_gemm(m, a, s));
+    GemmArgs b = gemm_base(m, S.s2, W.sfb_s1, CP, B, Hp, Wp);
+    b.res = xr;
+    b.ldres = CP;
+    b.out_T = W.sfb_cat;
+    b.ld_T = 2 * CP;
+    SSR_TRY(run_gemm(m, b, s));
+  }
+  {  // F: y = LeakyReLU(conv1x1(x)) (swinfir.py:40-43,47)
+    GemmArgs a = gemm_base(m, S.before, xa, CP, B, Hp, Wp);
+    a.act = ACT_LEAKY;
+    a.slope = 0.2f;
+    a.out_f32 = W.sfb_y;  // un-rounded copy: input of the transform and of the `output + x` skip
+    a.ld_f32 = c2P;
+    SSR_TRY(run_gemm(m, a, s));
+  }
+  // FourierUnit (swinfir.py:18-34): rfft2 -> 1x1 conv + LeakyReLU on [real | imag] -> irfft2, then + y (swinfir.py:49)
+  SSR_TRY(launch_rfft2(W.sfb_y, c2P, W.sfb_fa, W.sfb_fb, CP, B, Hp, Wp, c2, rtf, s));
+  {
+    GemmArgs a = gemm_base(m, S.fu, W.sfb_fb, CP, B, Hp, Wf);
+    a.act = ACT_LEAKY;
+    a.slope = 0.2f;
+    a.out_f32 = W.sfb_fc;
+    a.ld_f32 = CP;
+    SSR_TRY(run_gemm(m, a, s));
+  }
+  SSR_TRY(launch_irfft2_add(W.sfb_fc, CP, W.sfb_fa, W.sfb_y, c2P, W.sfb_z, c2P, B, Hp, Wp, c2, 4, rtf, s));
+  {  // conv_after_fft (swinfir.py:49) -> columns [CP, 2 CP)
+    GemmArgs a = gemm_base(m, S.after, W.sfb_z, c2P, B, Hp, Wp);
+    a.out_T = W.sfb_cat + CP;
+    a.ld_T = 2 * CP;
+    SSR_TRY(run_gemm(m, a, s));
+  }
+  GemmArgs f = gemm_base(m, S.fusion, W.sfb_cat, 2 * CP, B, Hp, Wp);
+  epi(f);
+  return run_gemm(m, f, s);
+}
+
 static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, int pad_mode,
                           void* ws, size_t ws_bytes, cudaStream_t s) {
   const ssr_model_config& c = m->cfg;
@@ -849,6 +944,10 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
   const int CP = m->CP, e = m->elem;
   const int T = B * Hp * Wp;
   const int rtf = c.precision == SSR_PREC_TF32;
+  if (m->sfb) {  // the FFT kernels write channels [0, 2 c2) / [0, c2) only: the padded K columns of the GEMMs that follow must be 0
+    SSR_CUDA(cudaMemsetAsync(W.sfb_fb, 0, (size_t)B * Hp * (Wp / 2 + 1) * CP * 4, s));
+    SSR_CUDA(cudaMemsetAsync(W.sfb_z, 0, (size_t)T * round_up(m->C / 2, 64) * 4, s));
+  }
 
   {  // pad + normalise + conv_first (swinir.py:356-361)
     ConvFirstArgs a;
@@ -1014,31 +1113,49 @@ static int forward_swinir(ssr_model* m, const InputSpec& in, const OutputSpec& o
         } else {
           g.out_T = W.tb;
           g.ld_T = CP;
+          if (m->sfb) {  // SwinFIR: the SFB's SpatialB skip reads the un-rounded fp32 stream
+            g.out_f32 = W.t;
+            g.ld_f32 = CP;
+          }
         }
         SSR_TRY(run_gemm(m, g, s));
       }
     }
     {  // RSTB conv + group residual (swinir.py:245-246); epilogue = next layer's first norm1 or the final norm
-      GemmArgs g = gemm_base(m, L.conv, W.tb, CP, B, Hp, Wp);
-      g.res = W.g;
-      g.ldres = CP;
-      if (li + 1 < nL) {
-        g.out_f32 = W.g;
-        g.ld_f32 = CP;
-        set_ln(m, g, m->layers[li + 1].blocks[0].norm1, W.xn, CP);
+      auto epilogue = [&](GemmArgs& g) {
+        g.res = W.g;
+        g.ldres = CP;
+        if (li + 1 < nL) {
+          g.out_f32 = W.g;
+          g.ld_f32 = CP;
+          set_ln(m, g, m->layers[li + 1].blocks[0].norm1, W.xn, CP);
+        } else {
+          set_ln(m, g, m->final_norm, W.xn, CP);
+        }
+      };
+      if (m->sfb) {  // SwinFIR: resi_connection = SFB (swinfir.py:112)
+        SSR_TRY(run_sfb(m, L.sfb, W.tb, W.t, B, Hp, Wp, W, epilogue, s));
       } else {
-        set_ln(m, g, m->final_norm, W.xn, CP);
+        GemmArgs g = gemm_base(m, L.conv, W.tb, CP, B, Hp, Wp);
+        epilogue(g);
+        SSR_TRY(run_gemm(m, g, s));
       }
-      SSR_TRY(run_gemm(m, g, s));
     }
   }
   {  // conv_after_body + long skip (swinir.py:362)
-    GemmArgs g = gemm_base(m, m->conv_after_body, W.xn, CP, B, Hp, Wp);
-    g.res = W.x0;
-    g.ldres = CP;
-    g.out_T = W.tb;
-    g.ld_T = CP;
-    SSR_TRY(run_gemm(m, g, s));
+    auto epilogue = [&](GemmArgs& g) {
+      g.res = W.x0;
+      g.ldres = CP;
+      g.out_T = W.tb;
+      g.ld_T = CP;
+    };
+    if (m->sfb) {  // SwinFIR: conv_after_body = SFB (swinfir.py:114); its input is the final norm's (T-typed = fp32) output
+      SSR_TRY(run_sfb(m, m->sfb_after_body, W.xn, reinterpret_cast<const float*>(W.xn), B, Hp, Wp, W, epilogue, s));
+    } else {
+      GemmArgs g = gemm_base(m, m->conv_after_body, W.xn, CP, B, Hp, Wp);
+      epilogue(g);
+      SSR_TRY(run_gemm(m, g, s));
+    }
   }
   float shift[3] = {kRgbMean[0], kRgbMean[1], kRgbMean[2]};
   if (c.upsampler == 0) {
@@ -1606,7 +1723,7 @@ int check_ready(ssr_model* m) {
 static int forward_any(ssr_model* m, const InputSpec& in, const OutputSpec& out, int B, int h, int w, int pad_mode,
                        void* ws, size_t ws_bytes, cudaStream_t s) {
   SSR_CHECK(B > 0 && h > 0 && w > 0, SSR_E_INVALID, "bad shape B=%d H=%d W=%d", B, h, w);
-  if (m->cfg.arch == SSR_ARCH_SWINIR) return forward_swinir(m, in, out, B, h, w, pad_mode, ws, ws_bytes, s);
+  if (is_swin(m)) return forward_swinir(m, in, out, B, h, w, pad_mode, ws, ws_bytes, s);
   if (m->cfg.arch == SSR_ARCH_RCAN) return forward_rcan(m, in, out, B, h, w, ws, ws_bytes, s);
   if (m->cfg.arch == SSR_ARCH_HAN) return forward_han(m, in, out, B, h, w, ws, ws_bytes, s);
   if (m->cfg.arch == SSR_ARCH_HAT) return forward_hat(m, in, out, B, h, w, ws, ws_bytes, s);
@@ -1614,7 +1731,7 @@ static int forward_any(ssr_model* m, const InputSpec& in, const OutputSpec& out,
 }
 
 static size_t workspace_any(const ssr_model* m, int B, int H, int W, int pad_mode) {
-  if (m->cfg.arch == SSR_ARCH_SWINIR) {
+  if (is_swin(m)) {
     int Hp, Wp;
     padded_size(m, H, W, pad_mode, &Hp, &Wp);
     SwinWs w;
@@ -1712,10 +1829,10 @@ int ssr_device_check(int device) {
 
 int ssr_model_create(const ssr_model_config* cfg, int device, ssr_model_t** out) {
   SSR_CHECK(cfg && out, SSR_E_INVALID, "null argument");
-  SSR_CHECK(cfg->arch >= SSR_ARCH_SWINIR && cfg->arch <= SSR_ARCH_HAN, SSR_E_INVALID, "unknown arch %d", cfg->arch);
+  SSR_CHECK(cfg->arch >= SSR_ARCH_SWINIR && cfg->arch <= SSR_ARCH_SWINFIR, SSR_E_INVALID, "unknown arch %d", cfg->arch);
   SSR_CHECK(cfg->precision >= 0 && cfg->precision <= 3, SSR_E_INVALID, "unknown precision %d", cfg->precision);
   SSR_CHECK(cfg->scale >= 1 && cfg->scale <= 8, SSR_E_INVALID, "bad scale %d", cfg->scale);
-  if (cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_HAT)
+  if (cfg->arch == SSR_ARCH_SWINIR || cfg->arch == SSR_ARCH_SWINFIR || cfg->arch == SSR_ARCH_HAT)
     SSR_CHECK(cfg->n_layers > 0 && cfg->n_layers <= SSR_MAX_LAYERS, SSR_E_INVALID, "bad n_layers %d", cfg->n_layers);
   SSR_TRY(ssr_device_check(device));
   ssr_model* m = new ssr_model();
@@ -1737,7 +1854,7 @@ int ssr_model_finalize(ssr_model_t* m) {
   SSR_CHECK(m != nullptr, SSR_E_INVALID, "null model");
   SSR_CUDA(cudaSetDevice(m->device));
   m->host_arena.clear();
-  int r = m->cfg.arch == SSR_ARCH_SWINIR ? finalize_swinir(m)
+  int r = is_swin(m) ? finalize_swinir(m)
           : m->cfg.arch == SSR_ARCH_RCAN ? finalize_rcan(m)
           : m->cfg.arch == SSR_ARCH_HAN  ? finalize_han(m)
           : m->cfg.arch == SSR_ARCH_HAT  ? finalize_hat(m)

@@ -259,6 +259,13 @@ struct CaArgs {
 };
 int launch_channel_attention(const CaArgs& a, cudaStream_t s);
 
+// SwinFIR's FourierUnit (swinfir.py:9-34), k_fft.cu: torch.fft.rfftn / irfftn over (H, W) with norm "ortho" as direct DFTs.
+// Complex rows hold the real parts in columns [0, c) and the imaginary parts in [c, 2c).  tmp: scratch like `spec`.
+int launch_rfft2(const float* in, int ld_in, float* tmp, float* spec, int ld_spec, int B, int H, int W, int c, int rtf32, cudaStream_t s);
+// out = irfft2(spec) + add (T-typed, [B*H*W][ld_out])
+int launch_irfft2_add(const float* spec, int ld_spec, float* tmp, const float* add, int ld_add, void* out, int ld_out, int B, int H, int W,
+                      int c, int elem, int rtf32, cudaStream_t s);
+
 // HAN (han.py:12-52).  stack: 11 fp32 planes [B*HW][ld], `plane` elements apart (plane 0 = newest body output).
 // launch_han_lam: layer attention, out = T-typed [B*HW][ld_out] with column n * C + c; energy = scratch [B][66] doubles.
 int launch_han_lam(const float* stack, size_t plane, int ld, int B, int HW, int C, double* energy, const float* gamma, void* out,

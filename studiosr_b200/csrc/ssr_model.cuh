@@ -27,9 +27,14 @@ struct Block {
   Lin cab0, cab2;
   size_t ca_w1 = 0, ca_b1 = 0, ca_w2 = 0, ca_b2 = 0;
 };
+// SwinFIR's SFB (swinfir.py:68-80): SpatialB convs, SpectralTransform 1x1 convs (as Linears), fusion
+struct Sfb {
+  Lin s0, s2, before, fu, after, fusion;
+};
 struct Layer {
   std::vector<Block> blocks;
   Lin conv;
+  Sfb sfb;  // replaces `conv` when the model is a SwinFIR
   int heads = 0, d = 0, DP = 0, QP = 0;
   Block ocab;  // HAT: overlapping cross-attention block closing the group (hat.py:198-293)
 };
@@ -73,6 +78,8 @@ struct ssr_model {
   };
   std::vector<CaP> ca;
   // HAN: the RCAN trunk plus last_conv (11 F -> F), last (2 F -> F), the CSAM Conv3d (27 weights + bias) and the two gammas
+  Sfb sfb_after_body;  // SwinFIR: conv_after_body
+  bool sfb = false;
   Lin han_last_conv, han_last;
   size_t csa_w = 0, csa_b = 0, csa_gamma = 0, la_gamma = 0;
 

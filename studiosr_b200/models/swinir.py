@@ -56,10 +56,10 @@ class BasicLayer(nn.Module):
 
 
 class RSTB(nn.Module):
-    def __init__(self, dim: int, depth: int, num_heads: int, window_size: int, mlp_ratio: float) -> None:
+    def __init__(self, dim: int, depth: int, num_heads: int, window_size: int, mlp_ratio: float, resi_connection=None) -> None:
         super().__init__()
         self.residual_group = BasicLayer(dim, depth, num_heads, window_size, mlp_ratio)
-        self.conv = nn.Conv2d(dim, dim, 3, 1, 1)
+        self.conv = resi_connection(dim) if resi_connection else nn.Conv2d(dim, dim, 3, 1, 1)  # swinir.py:241
 
 
 class SwinIR(Model):
@@ -83,8 +83,9 @@ class SwinIR(Model):
         resi_connection: Optional[nn.Module] = None,
     ) -> None:
         super().__init__(scale, n_colors, img_range)
-        if resi_connection is not None:
-            raise NotImplementedError("resi_connection (SwinFIR hook, swinfir.py:112) is outside the native path")
+        if resi_connection is not None and (getattr(resi_connection, "__name__", "") != "SFB" or self.ARCH != _lib.SSR_ARCH_SWINFIR):
+            raise NotImplementedError("resi_connection: only SwinFIR (models/swinfir.py: SFB in every RSTB and as conv_after_body, "
+                                      "swinfir.py:83-114) has a native path")
         if drop_rate != 0.0 or attn_drop_rate != 0.0:
             raise NotImplementedError("dropout > 0 is not part of the native path (reference default is 0.0)")
         assert upsampler in ("pixelshuffle", "pixelshuffledirect")
@@ -102,7 +103,7 @@ class SwinIR(Model):
         self.conv_first = nn.Conv2d(n_colors, embed_dim, 3, 1, 1)
         self.patch_embed = PatchEmbed(embed_dim)
         self.layers = nn.ModuleList(
-            RSTB(embed_dim, depths[i], num_heads[i], window_size, mlp_ratio) for i in range(len(depths)))
+            RSTB(embed_dim, depths[i], num_heads[i], window_size, mlp_ratio, resi_connection) for i in range(len(depths)))
         self.norm = nn.LayerNorm(embed_dim)
         self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
         if upsampler == "pixelshuffle":

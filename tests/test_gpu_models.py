@@ -239,6 +239,46 @@ def test_han_inference_u8_and_train_mode_forward():
         y.sum().backward()
 
 
+SWINFIR_CASES = ["swinfir_tiny_x4_eval_1x12x20", "swinfir_tiny_x2_eval_2x16x16", "swinfir_tiny_x4_train_1x16x24", "swinfir_c180_x4_eval_1x8x8"]
+_SWIN_KW = ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size", "mlp_ratio", "upsampler")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("name", SWINFIR_CASES)
+def test_swinfir_matches_reference_golden(name, prec, golden_meta):
+    """SwinFIR forward (swinfir.py:83-114: SFB = spatial convs + FourierUnit + fusion in every RSTB and as conv_after_body; the
+    2-D real FFT pair is k_fft.cu) against the reference's own outputs."""
+    from studiosr_b200.models import SwinFIR
+
+    c = golden_meta[name]
+    m = SwinFIR(drop_path_rate=0.0, **{k: c["cfg"][k] for k in _SWIN_KW})
+    m.load_state_dict(synth.swinfir_weights(c["cfg"], c["wseed"]), strict=True)
+    m = m.cuda().train(c["training"])
+    m.precision = prec
+    x = synth.image_batch(c["shape"], c["xseed"]).cuda()
+    with torch.no_grad():
+        y = m(x).float().cpu()
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    err = (y - ref).abs().max().item()
+    assert err <= ABS_TOL[prec], f"{name} [{prec}] max-abs {err:.3e}"
+
+
+def test_swinfir_reference_shape_test_and_bf16_refusal():
+    """tests/models/test_swinfir.py of the reference on the drop-in (default full-size model, every scale), and the bf16 mode
+    refuses loudly (the reference trains and ships SwinFIR in fp32, swinfir.py:126)."""
+    from studiosr_b200.models import SwinFIR
+
+    for scale in (2, 3, 4, 8):
+        model = SwinFIR(scale=scale, n_colors=3).cuda()
+        for hw in (8, 12):
+            y = model(torch.randn(1, 3, hw, hw).cuda())
+            assert y.shape == (1, 3, scale * hw, scale * hw) and torch.isfinite(y).all()
+    with pytest.raises(NotImplementedError, match="fp32-class"):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            model(torch.randn(1, 3, 8, 8).cuda())
+
+
 def test_inference_u8_matches_reference(golden_meta):
     g = load_golden("swinir_tiny_x4_inference_u8")
     m = _swinir(golden_meta["swinir_ops"]["cfg"], 11)

@@ -82,6 +82,22 @@ def test_han_oracle_matches_reference_golden(name, golden_meta):
     assert (y - ref).abs().max().item() <= 2e-5
 
 
+SWINFIR_CASES = ["swinfir_tiny_x4_eval_1x12x20", "swinfir_tiny_x2_eval_2x16x16", "swinfir_tiny_x4_train_1x16x24", "swinfir_c180_x4_eval_1x8x8"]
+
+
+@pytest.mark.parametrize("name", SWINFIR_CASES)
+def test_swinfir_oracle_matches_reference_golden(name, golden_meta):
+    """oracle/sr_oracle.py:swinir_forward with cfg["sfb"] (SFB swinfir.py:68-80, FourierUnit :9-34) vs the reference's own
+    SwinFIR forward (fixtures: oracle/make_golden_swinfir.py)."""
+    c = golden_meta[name]
+    P = synth.swinfir_weights(c["cfg"], c["wseed"])
+    x = synth.image_batch(c["shape"], c["xseed"])
+    y = O.swinir_forward(P, x, c["cfg"], training=c["training"])
+    ref = torch.from_numpy(load_golden(name)["y"])
+    assert list(y.shape) == c["out_shape"]
+    assert (y - ref).abs().max().item() <= 2e-5
+
+
 @pytest.mark.parametrize("name", EDSR_CASES)
 def test_edsr_oracle_matches_reference_golden(name, golden_meta):
     c = golden_meta[name]
