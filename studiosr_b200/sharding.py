@@ -118,8 +118,18 @@ class ShardedTiledUpscaler:
             lib = getattr(self.be, "lib", None)
             l0 = lib.ssr_launch_count() if lib is not None else 0
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._pass(self.frame_in)
+            except Exception as exc:  # e.g. a collective algorithm that cannot be captured: stay eager (same collective order,
+                # so ranks that did capture and ranks that did not still match)
+                import warnings
+
+                warnings.warn(f"studiosr_b200.sharding: CUDA-graph capture of the sharded pass failed ({exc!r}); running eagerly")
+                self.use_graph = False
+                torch.cuda.synchronize(dev)
                 self._pass(self.frame_in)
+                return self.frame_all[:self.out_rows]
             self._graph_kernels = (lib.ssr_launch_count() - l0) if lib is not None else 0
             self._graph = g
         self._graph.replay()
