@@ -40,7 +40,7 @@ constexpr int ST_THREADS = 640;
 constexpr int ST_IO_WARP0 = 4, ST_GELU_WARP0 = 12;
 // register budgets after setmaxnreg (the CTA's pool is 640 x 96 = 61440 registers)
 #ifndef ST_REGS_WG0
-#define ST_REGS_WG0 48
+#define ST_REGS_WG0 40
 #define ST_REGS_IO 152
 #define ST_REGS_GELU 64
 #endif
