@@ -328,6 +328,8 @@ def test_tiled_inference_ragged_frames_and_chunking(H, W, tile, overlap):
     for prec in ("fp32", "bf16"):
         nat = m._native(frame.device, prec)
         whole = nat.upscale_tiled_u8(frame, 4, tile, overlap)
+        # the host entry point (two passes with the D2H of the finished rows under the last tile row's compute) == the device one
+        assert np.array_equal(m.inference_tiled(img, tile=tile, overlap=overlap, precision=prec), whole.cpu().numpy()), prec
         for chunk in (1, 2, 3):
             assert torch.equal(nat.upscale_tiled_u8(frame, 4, tile, overlap, chunk), whole), (prec, chunk)
 
