@@ -25,6 +25,7 @@ CASES = {
     "train_edsr_tiny_x4_2x24x20": ("edsr", dict(synth.EDSR_TINY), 5, (2, 3, 24, 20), 77),
     "train_edsr_tiny_x3_1x12x16": ("edsr", dict(synth.EDSR_TINY, scale=3, n_resblocks=1), 5, (1, 3, 12, 16), 77),
     "train_rcan_tiny_x4_2x12x20": ("rcan", dict(synth.RCAN_TINY), 9, (2, 3, 12, 20), 55),
+    "train_han_tiny_x4_2x12x16": ("han", dict(synth.HAN_TINY), 13, (2, 3, 12, 16), 57),
     "train_swinir_tiny_x4_2x16x24": ("swinir", synth.swinir_config(**synth.SWINIR_TINY), 11, (2, 3, 16, 24), 101),
     "train_swinir_tiny_x4_pad_1x20x28": ("swinir", synth.swinir_config(**synth.SWINIR_TINY), 11, (1, 3, 20, 28), 101),
     "train_swinir_c180_x4_1x16x16": ("swinir", synth.swinir_config(embed_dim=180, depths=[2, 2], num_heads=[6, 6]), 11,
@@ -61,6 +62,11 @@ def main() -> None:
         elif arch == "rcan":
             m = models.RCAN(**cfg)
             m.load_state_dict(synth.rcan_weights(cfg, wseed), strict=True)
+        elif arch == "han":
+            from studiosr.models.han import HAN
+
+            m = HAN(**cfg)
+            m.load_state_dict(synth.han_weights(cfg, wseed), strict=True)
         else:
             m = models.SwinIR(drop_path_rate=DROP_RATE if arch == "swinir_dp" else 0.0, **cfg)
             m.load_state_dict(synth.swinir_weights(cfg, wseed), strict=True)

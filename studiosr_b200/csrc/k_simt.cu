@@ -1121,6 +1121,202 @@ int launch_han_csam(const float* x, int ld, int B, int H, int W, int C, const fl
   return SSR_OK;
 }
 
+// ---- HAN backward (training) ----
+// LAM: out_n = gamma * sum_m A[n][m] X_m + X_n, A = softmax(max - E), E = X X^T.  With D[n][m] = <dOut_n, X_m>:
+//   dgamma = sum A (.) D;  dA = gamma D;  dEnew = A (.) (dA - rowsum(A (.) dA));  dE = -dEnew (the row-max term cancels: softmax
+//   gradients sum to zero over a row);  dX_n = dOut_n + gamma sum_m A[m][n] dOut_m + sum_m (dE[n][m] + dE[m][n]) X_m.
+// stage 1: D[b][n][m] (blockIdx.z = n), fp64 accumulation across blocks.  dOut is [pixel][n * C + c].
+__global__ void __launch_bounds__(256) han_gram2_kernel(const float* dout, int ld_d, const float* stack, size_t plane, int ld, int HW, int C,
+                                                        double* D) {
+  __shared__ float red[8][HAN_N];
+  const int b = blockIdx.y, n = blockIdx.z;
+  const size_t n_el = (size_t)HW * C;
+  float acc[HAN_N];
+#pragma unroll
+  for (int i = 0; i < HAN_N; ++i) acc[i] = 0.0f;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = e / C;
+    const int c = (int)(e - p * C);
+    const size_t row = (size_t)b * HW + p;
+    const float g = dout[row * ld_d + (size_t)n * C + c];
+    const float* src = stack + row * ld + c;
+#pragma unroll
+    for (int m2 = 0; m2 < HAN_N; ++m2) acc[m2] = fmaf(g, src[(size_t)m2 * plane], acc[m2]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < HAN_N; ++i) {
+    float a = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp][i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < HAN_N) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)red[w][threadIdx.x];
+    atomicAdd(D + ((size_t)b * HAN_N + n) * HAN_N + threadIdx.x, t);
+  }
+}
+// stage 2 (one block per image): the 11 x 11 algebra.  coef[b][0][n][m] = gamma A[m][n], coef[b][1][n][m] = dE[n][m] + dE[m][n]
+__global__ void han_lam_bwd_small_kernel(const double* energy, const double* D, const float* gamma, float* coef, float* dgamma) {
+  __shared__ double A[HAN_N][HAN_N], dE[HAN_N][HAN_N];
+  const int b = blockIdx.x, n = threadIdx.x;
+  const double g = (double)gamma[0];
+  if (n < HAN_N) {
+    double e[HAN_N], mx = -1e300, mn = 1e300, sum = 0.0;
+    for (int m2 = 0; m2 < HAN_N; ++m2) {
+      const int lo = n < m2 ? n : m2, hi = n < m2 ? m2 : n;
+      e[m2] = energy[(size_t)b * HAN_NP + lo * HAN_N - lo * (lo - 1) / 2 + (hi - lo)];
+      mx = e[m2] > mx ? e[m2] : mx;
+      mn = e[m2] < mn ? e[m2] : mn;
+    }
+    for (int m2 = 0; m2 < HAN_N; ++m2) {
+      e[m2] = exp((mx - e[m2]) - (mx - mn));
+      sum += e[m2];
+    }
+    double dot = 0.0, dg = 0.0;
+    for (int m2 = 0; m2 < HAN_N; ++m2) {
+      A[n][m2] = e[m2] / sum;
+      const double d = D[((size_t)b * HAN_N + n) * HAN_N + m2];
+      dg += A[n][m2] * d;
+      dot += A[n][m2] * g * d;
+    }
+    for (int m2 = 0; m2 < HAN_N; ++m2) dE[n][m2] = -A[n][m2] * (g * D[((size_t)b * HAN_N + n) * HAN_N + m2] - dot);
+    atomicAdd(dgamma, (float)dg);
+  }
+  __syncthreads();
+  if (n < HAN_N)
+    for (int m2 = 0; m2 < HAN_N; ++m2) {
+      coef[((size_t)b * 2 + 0) * HAN_N * HAN_N + n * HAN_N + m2] = (float)(g * A[m2][n]);
+      coef[((size_t)b * 2 + 1) * HAN_N * HAN_N + n * HAN_N + m2] = (float)(dE[n][m2] + dE[m2][n]);
+    }
+}
+// stage 3: dX planes (fp32 [11][B*HW][ld])
+__global__ void __launch_bounds__(256) han_lam_bwd_apply_kernel(const float* dout, int ld_d, const float* stack, size_t plane, int ld, int HW,
+                                                                int C, const float* coef, float* dstack) {
+  __shared__ float cf[2][HAN_N][HAN_N];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * HAN_N * HAN_N; i += blockDim.x) (&cf[0][0][0])[i] = coef[(size_t)b * 2 * HAN_N * HAN_N + i];
+  __syncthreads();
+  const size_t n_el = (size_t)HW * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = e / C;
+    const int c = (int)(e - p * C);
+    const size_t row = (size_t)b * HW + p;
+    float g[HAN_N], v[HAN_N];
+#pragma unroll
+    for (int m2 = 0; m2 < HAN_N; ++m2) {
+      g[m2] = dout[row * ld_d + (size_t)m2 * C + c];
+      v[m2] = stack[row * ld + c + (size_t)m2 * plane];
+    }
+#pragma unroll
+    for (int n = 0; n < HAN_N; ++n) {
+      float a = g[n];
+#pragma unroll
+      for (int m2 = 0; m2 < HAN_N; ++m2) a = fmaf(cf[0][n][m2], g[m2], fmaf(cf[1][n][m2], v[m2], a));
+      dstack[(size_t)n * plane + row * ld + c] = a;
+    }
+  }
+}
+int launch_han_lam_bwd(const float* dout, int ld_d, const float* stack, size_t plane, int ld, int B, int HW, int C, const double* energy,
+                       const float* gamma, double* D, float* coef, float* dgamma, float* dstack, cudaStream_t s) {
+  SSR_CUDA(cudaMemsetAsync(D, 0, (size_t)B * HAN_N * HAN_N * sizeof(double), s));
+  SSR_CHECK(dgamma != nullptr, SSR_E_INVALID, "han_lam_bwd: dgamma scratch missing");
+  SSR_CUDA(cudaMemsetAsync(dgamma, 0, 4, s));
+  const int blocks = (int)std::min<size_t>(((size_t)HW * C + 255) / 256, 128);
+  ProfScope prof("han_lam_bwd", 0.0, (double)B * HW * C * 4.0 * 4 * HAN_N, s);
+  han_gram2_kernel<<<dim3(blocks, B, HAN_N), 256, 0, s>>>(dout, ld_d, stack, plane, ld, HW, C, D);
+  count_launch();
+  han_lam_bwd_small_kernel<<<B, 32, 0, s>>>(energy, D, gamma, coef, dgamma);
+  count_launch();
+  han_lam_bwd_apply_kernel<<<dim3(blocks, B), 256, 0, s>>>(dout, ld_d, stack, plane, ld, HW, C, coef, dstack);
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+// CSAM backward.  out = x (1 + gamma s), s = sigmoid(pre), pre = conv3d(x) + b.  With g = dL/dout:
+//   dpre = g x gamma s (1 - s);  dx = g (1 + gamma s) + conv3d^T(dpre);  dgamma = sum g x s;  db = sum dpre;  dW[tap] = sum dpre x[. + off(tap)]
+// pass 1: dpre, the direct part of dx, and the 29 scalar sums (scal: [0] dgamma, [1] db, [2..29) dW)
+__global__ void __launch_bounds__(256) han_csam_bwd1_kernel(const float* x, int ld, const float* g, int ld_g, int B, int H, int W, int C,
+                                                            const float* w27, const float* bias, const float* gamma, float* dpre, float* dxd,
+                                                            float* scal) {
+  __shared__ float red[8][29];
+  float acc[29];
+#pragma unroll
+  for (int i = 0; i < 29; ++i) acc[i] = 0.0f;
+  const float gm = gamma[0];
+  const size_t n_el = (size_t)B * H * W * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const size_t p = e / C;
+    const int xx = (int)(p % W), yy = (int)((p / W) % H), b = (int)(p / ((size_t)W * H));
+    float nb[27];
+    float pre = bias[0];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const int cc = c + t / 9 - 1, y2 = yy + (t / 3) % 3 - 1, x2 = xx + t % 3 - 1;
+      nb[t] = (cc >= 0 && cc < C && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? x[(((size_t)b * H + y2) * W + x2) * ld + cc] : 0.0f;
+      pre = fmaf(w27[t], nb[t], pre);
+    }
+    const float v = nb[13], gg = g[p * ld_g + c];
+    const float sg = 1.0f / (1.0f + expf(-pre));
+    const float dp = gg * v * gm * sg * (1.0f - sg);
+    dpre[p * ld + c] = dp;
+    dxd[p * ld + c] = gg * fmaf(gm, sg, 1.0f);
+    acc[0] = fmaf(gg * v, sg, acc[0]);
+    acc[1] += dp;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[2 + t] = fmaf(dp, nb[t], acc[2 + t]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 29; ++i) {
+    float a = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp][i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 29) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(scal + threadIdx.x, t);
+  }
+}
+// pass 2: G0 = acc_in (the LAM's gradient of the same plane) + dxd + conv3d^T(dpre); fp32 + bf16 copy
+__global__ void __launch_bounds__(256) han_csam_bwd2_kernel(const float* dpre, const float* dxd, const float* acc_in, int ld, int B, int H, int W,
+                                                            int C, const float* w27, float* out, __nv_bfloat16* out_bf) {
+  const size_t n_el = (size_t)B * H * W * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const size_t p = e / C;
+    const int xx = (int)(p % W), yy = (int)((p / W) % H), b = (int)(p / ((size_t)W * H));
+    float a = dxd[p * ld + c] + acc_in[p * ld + c];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {  // x[q] fed pre[q - off(t)] with weight w[t]
+      const int cc = c - (t / 9 - 1), y2 = yy - ((t / 3) % 3 - 1), x2 = xx - (t % 3 - 1);
+      if (cc >= 0 && cc < C && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) a = fmaf(w27[t], dpre[(((size_t)b * H + y2) * W + x2) * ld + cc], a);
+    }
+    out[p * ld + c] = a;
+    out_bf[p * ld + c] = __float2bfloat16_rn(a);
+  }
+}
+int launch_han_csam_bwd(const float* x, int ld, const float* g, int ld_g, const float* acc_in, int B, int H, int W, int C, const float* w27,
+                        const float* bias, const float* gamma, float* dpre, float* dxd, float* scal, float* out, void* out_bf,
+                        cudaStream_t s) {
+  SSR_CUDA(cudaMemsetAsync(scal, 0, 29 * 4, s));
+  const size_t n = (size_t)B * H * W * C;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  ProfScope prof("han_csam_bwd", 4.0 * 27 * n, (double)n * 4 * 6, s);
+  han_csam_bwd1_kernel<<<grid, 256, 0, s>>>(x, ld, g, ld_g, B, H, W, C, w27, bias, gamma, dpre, dxd, scal);
+  count_launch();
+  han_csam_bwd2_kernel<<<grid, 256, 0, s>>>(dpre, dxd, acc_in, ld, B, H, W, C, w27, out, reinterpret_cast<__nv_bfloat16*>(out_bf));
+  count_launch();
+  SSR_CUDA(cudaGetLastError());
+  return SSR_OK;
+}
+
 // ---- channel attention backward (training; see CaBwdArgs) ----
 // stage 1: partial[b][split][c] = sum over a pixel slab of G * t
 __global__ void __launch_bounds__(256) ca_bwd_reduce_kernel(const float* G, const __nv_bfloat16* t, int ld, int HW, int C, int nsplit,

@@ -274,6 +274,16 @@ int launch_han_lam(const float* stack, size_t plane, int ld, int B, int HW, int 
 int launch_han_csam(const float* x, int ld, int B, int H, int W, int C, const float* w27, const float* bias, const float* gamma,
                     void* out, int ld_out, int elem, int rtf32, cudaStream_t s);
 
+// HAN training.  launch_han_lam_bwd: dout = fp32 [B*HW][ld_d] gradient of the layer attention's output (column n * C + c),
+// energy = what launch_han_lam left behind; D [B][121] doubles and coef [B][2][121] floats are scratch; dgamma (1 float) and dstack (11 fp32 planes like `stack`) are outputs.
+int launch_han_lam_bwd(const float* dout, int ld_d, const float* stack, size_t plane, int ld, int B, int HW, int C, const double* energy,
+                       const float* gamma, double* D, float* coef, float* dgamma, float* dstack, cudaStream_t s);
+// launch_han_csam_bwd: g = dL/d(csa output) (fp32, ld_g), acc_in = gradient already at x from elsewhere; out / out_bf = total
+// gradient at x; scal [29] = dgamma, dbias, dW[27]; dpre / dxd = scratch like x.
+int launch_han_csam_bwd(const float* x, int ld, const float* g, int ld_g, const float* acc_in, int B, int H, int W, int C, const float* w27,
+                        const float* bias, const float* gamma, float* dpre, float* dxd, float* scal, float* out, void* out_bf,
+                        cudaStream_t s);
+
 // backward of out = res + t * sigmoid(W2 relu(W1 mean_hw(t) + b1) + b2) (common.py:156-170 inside rcan.py:21-24):
 //   dt = G * gate + W1^T dz1 / HW,  dz1 = relu'(.) * W2^T dz2,  dz2 = gate (1 - gate) * sum_hw G t   (+ the four parameter gradients)
 struct CaBwdArgs {

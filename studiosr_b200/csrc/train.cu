@@ -71,6 +71,8 @@ struct ssr_train_state {
   std::vector<int> r_a, r_b, r_gt;  // indices into convs: the two convs of every RCAB (group-major), the conv closing each group
   std::vector<ssr::CaT> r_ca;
   int pack_cap = 0;                 // entries the batched (un)pack launches may carry
+  // HAN (the RCAN fields plus): convs last_conv / last, bound indices of csa.conv.weight / .bias, csa.gamma, la.gamma
+  int h_last_conv = -1, h_last = -1, h_csa_w = -1, h_csa_b = -1, h_csa_g = -1, h_la_g = -1;
   // left behind by the last train_backward for ssr_model_train_input_grad: dL/d(first conv's output), fp32
   const float* dx_G = nullptr;
   int dx_ld = 0, dx_C = 0, dx_B = 0, dx_h = 0, dx_w = 0, dx_Hp = 0, dx_Wp = 0;
@@ -375,13 +377,14 @@ static GemmArgs dgrad_base(const ssr_model* m, const ConvT& c, const void* dY, i
 }
 
 static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const void* X, int ldx, int B, int H, int W, float alpha,
-                      float* dwp, float* partial, float* const* grads, cudaStream_t s) {
+                      float* dwp, float* partial, float* const* grads, cudaStream_t s, int ldy = 0) {
   const Lin& L = *c.fwd;
+  if (ldy <= 0) ldy = L.NP;
   if (grads[c.wi]) {
     WgradArgs a;
     memset(&a, 0, sizeof(a));
     a.dY = dY;
-    a.ldy = L.NP;
+    a.ldy = ldy;
     a.X = X;
     a.ldx = ldx;
     a.B = B;
@@ -414,7 +417,7 @@ static int wgrad_conv(const ssr_model* m, const ConvT& c, const void* dY, const 
     m->train->unpack_host.push_back(e);
   }
   if (grads[c.bi])
-    SSR_TRY(launch_colsum(dY, 2, L.NP, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s, &m->train->red));
+    SSR_TRY(launch_colsum(dY, 2, ldy, B * H * W, L.NP, c.Cout, L.ps_r, alpha, grads[c.bi], partial, s, &m->train->red));
   return SSR_OK;
 }
 
@@ -602,7 +605,16 @@ static int bind_rcan(ssr_model* m) {
   }
   t->e_last = add_conv(t, "tail.1", &m->last_lin, 3, F, &a2);
   if (t->e_last < 0) return SSR_E_STATE;
-  t->pack_cap = (int)t->convs.size() + 4 * (int)t->r_ca.size() + 16;
+  if (m->cfg.arch == SSR_ARCH_HAN) {  // han.py:84-88
+    t->h_last_conv = add_conv(t, "last_conv", &m->han_last_conv, F, 11 * F, &a2);
+    t->h_last = add_conv(t, "last", &m->han_last, F, 2 * F, &a2);
+    t->h_csa_w = find_idx(t, "csa.conv.weight", 27);
+    t->h_csa_b = find_idx(t, "csa.conv.bias", 1);
+    t->h_csa_g = find_idx(t, "csa.gamma", 1);
+    t->h_la_g = find_idx(t, "la.gamma", 1);
+    if (t->h_last_conv < 0 || t->h_last < 0 || t->h_csa_w < 0 || t->h_csa_b < 0 || t->h_csa_g < 0 || t->h_la_g < 0) return SSR_E_STATE;
+  }
+  t->pack_cap = (int)t->convs.size() + 4 * (int)t->r_ca.size() + 24;
   t->arena2_bytes = a2 + 1024;
   SSR_CUDA(cudaMalloc(&t->arena2, t->arena2_bytes));
   SSR_CUDA(cudaMemset(t->arena2, 0, t->arena2_bytes));
@@ -628,6 +640,11 @@ struct RcanTrainWs {
   float* red_pool;
   RedEntry* red_dev;
   PackEntry* pack_dev;
+  // HAN: the 11 fp32 planes of the stack and of its gradient, the layer attention's scratch, last_conv's operand / gradient,
+  // the concatenation and its gradient, the CSAM backward's scratch
+  float *h_stack, *h_dstack, *h_dlam, *h_dcat, *h_dpre, *h_dxd, *h_coef, *h_scal;
+  double *h_energy, *h_D;
+  void *h_lam, *h_cat, *h_dcatb;
 };
 
 static size_t plan_rcan_train(const ssr_model* m, void* base, int B, int H, int W, RcanTrainWs* w) {
@@ -674,6 +691,21 @@ static size_t plan_rcan_train(const ssr_model* m, void* base, int B, int H, int 
   w->red_pool = (float*)c.take(m->train->red_floats * 4);
   w->red_dev = (RedEntry*)c.take((size_t)(m->train->red_entries + 8) * sizeof(RedEntry));
   w->pack_dev = (PackEntry*)c.take((size_t)m->train->pack_cap * sizeof(PackEntry));
+  if (m->cfg.arch == SSR_ARCH_HAN) {
+    w->h_stack = (float*)c.take(11 * T * FP * 4);
+    w->h_dstack = (float*)c.take(11 * T * FP * 4);
+    w->h_dlam = (float*)c.take(T * 11 * FP * 4);
+    w->h_dcat = (float*)c.take(T * 2 * FP * 4);
+    w->h_dpre = (float*)c.take(T * FP * 4);
+    w->h_dxd = (float*)c.take(T * FP * 4);
+    w->h_coef = (float*)c.take((size_t)B * 2 * 121 * 4);
+    w->h_scal = (float*)c.take(32 * 4);
+    w->h_energy = (double*)c.take((size_t)B * 66 * 8);
+    w->h_D = (double*)c.take((size_t)B * 121 * 8);
+    w->h_lam = c.take(T * 11 * FP * 2);
+    w->h_cat = c.take(T * 2 * FP * 2);
+    w->h_dcatb = c.take(T * 2 * FP * 2);
+  }
   return c.off + 1024;
 }
 
@@ -696,9 +728,17 @@ static int train_forward_rcan(ssr_model* m, const float* const* params, const fl
     push_copy(t, params[t->r_ca[i].w2], m->dev<float>(m->ca[i].w2), F * R);
     push_copy(t, params[t->r_ca[i].b2], m->dev<float>(m->ca[i].b2), F);
   }
+  const bool han = c.arch == SSR_ARCH_HAN;
+  if (han) {
+    push_copy(t, params[t->h_csa_w], m->dev<float>(m->csa_w), 27);
+    push_copy(t, params[t->h_csa_b], m->dev<float>(m->csa_b), 1);
+    push_copy(t, params[t->h_csa_g], m->dev<float>(m->csa_gamma), 1);
+    push_copy(t, params[t->h_la_g], m->dev<float>(m->la_gamma), 1);
+  }
   SSR_CHECK((int)t->pack_host.size() <= t->pack_cap, SSR_E_STATE, "train: pack list overflow");
   SSR_TRY(launch_pack_batched(t->pack_host.data(), W.pack_dev, (int)t->pack_host.size(), s));
-  // ---- forward (rcan.py:68-77), every GEMM operand kept for the backward ----
+  const size_t plane = (size_t)B * h * w * FP;
+  // ---- forward (rcan.py:68-77 / han.py:90-113), every GEMM operand kept for the backward ----
   SSR_TRY(launch_nchw3_to_nhwc64(x, W.xin64, B, h, w, 1.0f, m->sub_bias, s));
   {
     ConvFirstArgs a;
@@ -741,24 +781,43 @@ static int train_forward_rcan(ssr_model* m, const float* const* params, const fl
       rcur = W.r;
     }
     // group tail conv + group skip (rcan.py:33-36)
+    float* gout = han ? W.h_stack + (size_t)(c.n_resgroups - g) * plane : W.gin;  // HAN: the group's plane of the stack
     GemmArgs gt = gemm_base(m, m->grp_tail[g], W.S[k], FP, B, h, w);
     gt.res = gcur;
     gt.ldres = FP;
-    gt.out_f32 = W.gin;
+    gt.out_f32 = gout;
     gt.ld_f32 = FP;
     gt.out_T = W.S[k + 1];
     gt.ld_T = FP;
     SSR_TRY(run_gemm(m, gt, s));
-    gcur = W.gin;
+    gcur = gout;
     ++k;
   }
-  {  // body tail conv + long skip (rcan.py:72-73)
+  if (!han) {  // body tail conv + long skip (rcan.py:72-73)
     GemmArgs g = gemm_base(m, m->body_tail, W.S[k], FP, B, h, w);
     g.res = W.x0;
     g.ldres = FP;
     g.out_T = W.bt;
     g.ld_T = FP;
     SSR_TRY(run_gemm(m, g, s));
+  } else {  // han.py:93-108: plane 0, layer attention -> last_conv, channel-spatial attention, last + long skip
+    GemmArgs g0 = gemm_base(m, m->body_tail, W.S[k], FP, B, h, w);
+    g0.out_f32 = W.h_stack;
+    g0.ld_f32 = FP;
+    SSR_TRY(run_gemm(m, g0, s));
+    SSR_TRY(launch_han_lam(W.h_stack, plane, FP, B, h * w, F, W.h_energy, m->dev<float>(m->la_gamma), W.h_lam, 11 * FP, 2, 0, s));
+    GemmArgs g1 = gemm_base(m, m->han_last_conv, W.h_lam, 11 * FP, B, h, w);
+    g1.out_T = reinterpret_cast<uint8_t*>(W.h_cat) + (size_t)FP * 2;
+    g1.ld_T = 2 * FP;
+    SSR_TRY(run_gemm(m, g1, s));
+    SSR_TRY(launch_han_csam(W.h_stack, FP, B, h, w, F, m->dev<float>(m->csa_w), m->dev<float>(m->csa_b), m->dev<float>(m->csa_gamma),
+                            W.h_cat, 2 * FP, 2, 0, s));
+    GemmArgs g2 = gemm_base(m, m->han_last, W.h_cat, 2 * FP, B, h, w);
+    g2.res = W.x0;
+    g2.ldres = FP;
+    g2.out_T = W.bt;
+    g2.ld_T = FP;
+    SSR_TRY(run_gemm(m, g2, s));
   }
   const void* cur = W.bt;
   int H = h, Wd = w;
@@ -838,15 +897,54 @@ static int train_backward_rcan(ssr_model* m, const float* const* params, const f
   float* Gn = W.G2;
   void* Gb = W.Dh;        // ... and its bf16 copy
   void* Dh = W.Gb;        // scratch for the gradient at the ReLU
+  const bool han = c.arch == SSR_ARCH_HAN;
+  const size_t plane = T * FP;
+  const void* body_dy = W.Gb;  // dL/d(output of the body's last conv), bf16
+  if (han) {  // han.py:101-108 in reverse: last, last_conv, layer attention, channel-spatial attention
+    const ConvT& cl = t->convs[t->h_last];
+    SSR_TRY(wgrad_conv(m, cl, W.Gb, W.h_cat, 2 * FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
+    {
+      GemmArgs g = dgrad_base(m, cl, W.Gb, B, h, w);
+      g.out_f32 = W.h_dcat;
+      g.ld_f32 = 2 * FP;
+      g.out_T = W.h_dcatb;
+      g.ld_T = 2 * FP;
+      SSR_TRY(launch_gemm_tc(g, 2, s));
+    }
+    const ConvT& clc = t->convs[t->h_last_conv];
+    const void* dy2 = reinterpret_cast<const uint8_t*>(W.h_dcatb) + (size_t)FP * 2;  // channels [F, 2F): last_conv's output
+    SSR_TRY(wgrad_conv(m, clc, dy2, W.h_lam, 11 * FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s, 2 * FP));
+    for (int j = 0; j < 11; ++j) {  // data gradient plane by plane (64 of the 704 input channels per GEMM)
+      GemmArgs g = dgrad_base(m, clc, dy2, B, h, w);
+      g.lda = 2 * FP;
+      g.Wt = m->train->arena2 + clc.dg_off + (size_t)j * FP * 9 * clc.fwd->NP * 2;
+      g.N = FP;
+      g.NP = FP;
+      g.N_alg = FP;
+      g.out_f32 = W.h_dlam + (size_t)j * FP;
+      g.ld_f32 = 11 * FP;
+      SSR_TRY(launch_gemm_tc(g, 2, s));
+    }
+    float* dla = grads[t->h_la_g] ? grads[t->h_la_g] : W.h_scal + 30;
+    SSR_TRY(launch_han_lam_bwd(W.h_dlam, 11 * FP, W.h_stack, plane, FP, B, h * w, F, W.h_energy, m->dev<float>(m->la_gamma), W.h_D, W.h_coef,
+                               dla, W.h_dstack, s));
+    SSR_TRY(launch_han_csam_bwd(W.h_stack, FP, W.h_dcat, 2 * FP, W.h_dstack, B, h, w, F, m->dev<float>(m->csa_w), m->dev<float>(m->csa_b),
+                                m->dev<float>(m->csa_gamma), W.h_dpre, W.h_dxd, W.h_scal, Gn, W.Dt, s));
+    if (grads[t->h_csa_g]) SSR_CUDA(cudaMemcpyAsync(grads[t->h_csa_g], W.h_scal, 4, cudaMemcpyDeviceToDevice, s));
+    if (grads[t->h_csa_b]) SSR_CUDA(cudaMemcpyAsync(grads[t->h_csa_b], W.h_scal + 1, 4, cudaMemcpyDeviceToDevice, s));
+    if (grads[t->h_csa_w]) SSR_CUDA(cudaMemcpyAsync(grads[t->h_csa_w], W.h_scal + 2, 27 * 4, cudaMemcpyDeviceToDevice, s));
+    body_dy = W.Dt;
+  }
   {
     const ConvT& cv = t->convs[t->e_body_tail];
-    SSR_TRY(wgrad_conv(m, cv, W.Gb, W.S[k], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
-    GemmArgs g = dgrad_base(m, cv, W.Gb, B, h, w);
+    SSR_TRY(wgrad_conv(m, cv, body_dy, W.S[k], FP, B, h, w, 1.0f, W.dwp, W.partial, grads, s));
+    GemmArgs g = dgrad_base(m, cv, body_dy, B, h, w);
     g.out_f32 = Ga;
     g.ld_f32 = FP;
     g.out_T = Gb;
     g.ld_T = FP;
     SSR_TRY(launch_gemm_tc(g, 2, s));
+    if (han) SSR_TRY(launch_add_inplace(Ga, W.h_dstack + plane, Gb, T * FP, s));  // the last group's own plane of the stack
   }
   for (int g = ng - 1; g >= 0; --g) {  // ResidualGroup: out = conv(rcabs(x)) + x  (rcan.py:27-36)
     {  // Ga = dL/d(out) stays for the group skip; the conv's input gradient goes to Gn
@@ -893,6 +991,8 @@ static int train_backward_rcan(ssr_model* m, const float* const* params, const f
     if (g == 0) SSR_TRY(launch_add_inplace(Gn, W.Gt, nullptr, T * FP, s));
     SSR_TRY(launch_add_inplace(Gn, Ga, Gb, T * FP, s));
     std::swap(Ga, Gn);
+    if (han && g > 0)  // the previous group's output is also plane ng - (g - 1) of the stack
+      SSR_TRY(launch_add_inplace(Ga, W.h_dstack + (size_t)(ng - g + 1) * plane, Gb, T * FP, s));
   }
   // head conv (rcan.py:63,70): dW[n][ci][tap] = sum_p G[p][n] * (x - mean)[p + off(tap)][ci]
   if (grads[t->head_w]) {
@@ -1678,8 +1778,8 @@ extern "C" {
 int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const int64_t* numels) {
   SSR_TRY(check_ready(m));
   SSR_CHECK(m->cfg.precision == SSR_PREC_BF16, SSR_E_INVALID, "the training path is built for the bf16 tensor-core precision only");
-  SSR_CHECK(m->cfg.arch == SSR_ARCH_EDSR || m->cfg.arch == SSR_ARCH_SWINIR || m->cfg.arch == SSR_ARCH_RCAN, SSR_E_INVALID,
-            "the training path is built for EDSR, RCAN and SwinIR (HAT is inference-only)");
+  SSR_CHECK(m->cfg.arch == SSR_ARCH_EDSR || m->cfg.arch == SSR_ARCH_SWINIR || m->cfg.arch == SSR_ARCH_RCAN || m->cfg.arch == SSR_ARCH_HAN,
+            SSR_E_INVALID, "the training path is built for EDSR, RCAN, HAN and SwinIR (HAT and SwinFIR are inference-only)");
   train_state_destroy(m);
   m->train = new ssr_train_state();
   for (int i = 0; i < n; ++i) {
@@ -1687,7 +1787,8 @@ int ssr_model_train_bind(ssr_model_t* m, int n, const char* const* names, const 
     m->train->numels.push_back(numels[i]);
     m->train->index[names[i]] = i;
   }
-  int r = m->cfg.arch == SSR_ARCH_EDSR ? bind_edsr(m) : m->cfg.arch == SSR_ARCH_RCAN ? bind_rcan(m) : bind_swinir(m);
+  const bool rcan_like = m->cfg.arch == SSR_ARCH_RCAN || m->cfg.arch == SSR_ARCH_HAN;
+  int r = m->cfg.arch == SSR_ARCH_EDSR ? bind_edsr(m) : rcan_like ? bind_rcan(m) : bind_swinir(m);
   if (r != SSR_OK) train_state_destroy(m);
   return r;
 }
@@ -1700,7 +1801,7 @@ size_t ssr_model_train_workspace_bytes(const ssr_model_t* m, int B, int H, int W
     SwinTrainWs w;
     return plan_swin_train(m, nullptr, B, Hp, Wp, &w);
   }
-  if (m->cfg.arch == SSR_ARCH_RCAN) {
+  if (m->cfg.arch == SSR_ARCH_RCAN || m->cfg.arch == SSR_ARCH_HAN) {
     RcanTrainWs w;
     return plan_rcan_train(m, nullptr, B, H, W, &w);
   }
@@ -1716,7 +1817,7 @@ int ssr_model_train_forward(ssr_model_t* m, const float* const* params, const fl
   if (m->cfg.arch == SSR_ARCH_SWINIR)
     return train_forward_swinir(m, params, drop_scale, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   SSR_CHECK(drop_scale == nullptr, SSR_E_INVALID, "train_forward: drop_scale is a SwinIR option");
-  if (m->cfg.arch == SSR_ARCH_RCAN) return train_forward_rcan(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (m->cfg.arch == SSR_ARCH_RCAN || m->cfg.arch == SSR_ARCH_HAN) return train_forward_rcan(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_forward_edsr(m, params, x, y, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -1727,7 +1828,7 @@ int ssr_model_train_backward(ssr_model_t* m, const float* dy, const float* drop_
   SSR_CHECK(dy && grads && B > 0 && H > 0 && W > 0, SSR_E_INVALID, "train_backward: bad argument");
   if (m->cfg.arch == SSR_ARCH_SWINIR)
     return train_backward_swinir(m, dy, drop_scale, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
-  if (m->cfg.arch == SSR_ARCH_RCAN)
+  if (m->cfg.arch == SSR_ARCH_RCAN || m->cfg.arch == SSR_ARCH_HAN)
     return train_backward_rcan(m, nullptr, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
   return train_backward_edsr(m, dy, grads, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -106,7 +106,7 @@ class _NativeForwardOnly(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         raise NotImplementedError(
-            f"studiosr_b200: no backward kernels for {ctx.why}; the training path covers EDSR, RCAN and SwinIR under the Trainer's "
+            f"studiosr_b200: no backward kernels for {ctx.why}; the training path covers EDSR, RCAN, HAN and SwinIR under the Trainer's "
             "bf16 autocast (trainer.py:69,80) -- run under torch.autocast('cuda', dtype=torch.bfloat16) or set "
             "model.precision = 'bf16'")
 

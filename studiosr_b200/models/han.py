@@ -2,7 +2,7 @@
 trunk in libssr_b200 (implicit-GEMM convs, fused channel-attention gates) whose eleven body outputs feed the layer-attention
 module (LAM, han.py:12-33: 11 x 11 gram matrix over C*H*W, softmax, re-mix -- three small kernels) and the channel-spatial
 attention module (CSAM, han.py:36-52: one 3x3x3 Conv3d over the (C, H, W) volume + sigmoid gate), then `last_conv`
-(704 -> 64) and `last` (128 -> 64) on the same implicit-GEMM kernel.  Inference only."""
+(704 -> 64) and `last` (128 -> 64) on the same implicit-GEMM kernel.  Trainable under the Trainer's bf16 autocast like RCAN."""
 import os
 from typing import Dict
 
@@ -31,6 +31,7 @@ class CSAM_Module(nn.Module):  # han.py:36-52 (parameter container)
 
 class HAN(Model):
     ARCH = _lib.SSR_ARCH_HAN
+    TRAINABLE = True  # forward + backward (train.cu: the RCAN executor + the layer / channel-spatial attention adjoints)
 
     def __init__(self, scale: int = 4, n_colors: int = 3, img_range: float = 1.0, n_feats: int = 64, n_resblocks: int = 20,
                  n_resgroups: int = 10, reduction: int = 16) -> None:

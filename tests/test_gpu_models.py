@@ -218,7 +218,7 @@ def test_han_matches_reference_golden(name, prec, golden_meta):
 
 def test_han_inference_u8_and_train_mode_forward():
     """The reference-facing entry points on HAN: Model.inference (uint8 in / out) equals the quantised fp32 forward, and the
-    train-mode forward runs (the backward is not built and says so)."""
+    train-mode forward + backward run."""
     from studiosr_b200.models import HAN
 
     cfg = synth.HAN_TINY
@@ -235,8 +235,8 @@ def test_han_inference_u8_and_train_mode_forward():
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y = m(x.cuda())
     assert y.shape == (1, 3, 80, 112)
-    with pytest.raises(NotImplementedError, match="no backward kernels"):
-        y.sum().backward()
+    y.sum().backward()  # the native backward (tests/test_gpu_train.py::test_han_backward checks the values)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)
 
 
 SWINFIR_CASES = ["swinfir_tiny_x4_eval_1x12x20", "swinfir_tiny_x2_eval_2x16x16", "swinfir_tiny_x4_train_1x16x24", "swinfir_c180_x4_eval_1x8x8"]

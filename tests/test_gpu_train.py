@@ -153,6 +153,53 @@ def test_rcan_backward(name, cfg, B, H, W):
     assert worst[0] <= 1.0, f"RCAN {name}: gradient rel err {worst[1]:.3e} vs reference-bf16 {worst[2]:.3e} at {worst[3]}"
 
 
+@pytest.mark.parametrize("name,cfg,B,H,W", [
+    ("tiny", synth.HAN_TINY, 2, 12, 16),
+    ("x2-two-blocks", dict(synth.HAN_TINY, scale=2, n_resblocks=2), 1, 16, 12),
+    ("x3-ragged", dict(synth.HAN_TINY, scale=3), 2, 9, 13),
+])
+def test_han_backward(name, cfg, B, H, W):
+    """HAN training step (han.py:90-113): the RCAN executor plus the adjoints of the layer attention (gram / softmax / re-mix),
+    of the channel-spatial attention (Conv3d) and of last_conv / last, against fp32 autograd over the oracle, bounded by the
+    reference's own bf16 error."""
+    from studiosr_b200.models import HAN
+
+    P = synth.han_weights(cfg, 13)
+    x = synth.image_batch((B, 3, H, W), 57)
+    tgt = synth.image_batch((B, 3, H * cfg["scale"], W * cfg["scale"]), 58)
+    Pr = {k: v.clone().requires_grad_(v.is_floating_point() and "mean" not in k) for k, v in P.items()}
+    loss_ref = F.l1_loss(O.han_forward(Pr, x, cfg), tgt)
+    loss_ref.backward()
+    Pa = {k: v.clone().requires_grad_(v.is_floating_point() and "mean" not in k) for k, v in P.items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        la = F.l1_loss(O.han_forward(Pa, x, cfg), tgt)
+    la.backward()
+    model = HAN(**cfg)
+    model.load_state_dict(P, strict=True)
+    model = model.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = F.l1_loss(model(x.cuda()), tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 3e-3 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
+    report = []
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        e = _rel(p.grad.cpu(), Pr[k].grad)
+        e_ref = _rel(Pa[k].grad.float(), Pr[k].grad)
+        # (the channel-attention gates' parameters see gradients ~1e-5 that are sums with heavy cancellation: the reference's own
+        # bf16 run is off by 1 % to 150 % there depending on the case, hence the wider floor)
+        report.append((e / max(1e-1 if ".conv_du." in k else 3e-2, 2.0 * e_ref), e, e_ref, k))
+    worst = max(report)
+    print(f"HAN {name}: worst gradient rel err {worst[1]:.3e} (reference under bf16 autocast: {worst[2]:.3e}) at {worst[3]}")
+    for k in ("la.gamma", "csa.gamma", "csa.conv.weight", "last_conv.weight", "last.weight"):
+        r = [t for t in report if t[3] == k][0]
+        print(f"    {k}: {r[1]:.3e} (reference bf16 {r[2]:.3e})")
+    assert worst[0] <= 1.0, f"HAN {name}: gradient rel err {worst[1]:.3e} vs reference-bf16 {worst[2]:.3e} at {worst[3]}"
+
+
 def test_rcan_default_depth_training_step():
     """The default RCAN (10 groups x 20 RCABs, rcan.py:39-50) through one native training step: every one of its 1600+
     parameter tensors gets a finite gradient, the loss equals the oracle's, and a sample of the gradients (first / last
@@ -247,8 +294,12 @@ def test_swinir_backward(name, over, B, H, W):
 @pytest.mark.parametrize("name", ["train_edsr_tiny_x4_2x24x20", "train_rcan_tiny_x4_2x12x20", "train_swinir_tiny_x4_pad_1x20x28",
                                   "train_swinir_c180_x4_1x16x16"])
 def test_backward_against_reference_golden_gradients(name):
-    """CUDA gradients directly against gradients the reference's own loss.backward() produced (oracle/make_golden_train.py)."""
-    from studiosr_b200.models import EDSR, RCAN, SwinIR
+    """CUDA gradients directly against gradients the reference's own loss.backward() produced (oracle/make_golden_train.py).
+    (HAN's golden gradients, train_han_tiny_x4_2x12x16, pin the ORACLE's autograd in tests/test_oracle.py; the CUDA path is held to
+    that oracle in test_han_backward on the identical case, relative to the reference's own bf16-autocast error: the layer
+    attention's softmax over sums of ~10^4 terms makes several gradients move by 30 %+ under ANY bf16 rounding, the
+    reference's included, so a fixed 6 % bound against fp32 gradients cannot hold there.)"""
+    from studiosr_b200.models import EDSR, HAN, RCAN, SwinIR
 
     with open(os.path.join(GOLD, "meta_train.json")) as f:
         c = json.load(f)["cases"][name]
@@ -262,6 +313,9 @@ def test_backward_against_reference_golden_gradients(name):
     elif c["arch"] == "rcan":
         model = RCAN(**cfg)
         model.load_state_dict(synth.rcan_weights(cfg, c["wseed"]), strict=True)
+    elif c["arch"] == "han":
+        model = HAN(**cfg)
+        model.load_state_dict(synth.han_weights(cfg, c["wseed"]), strict=True)
     else:
         kw = {k: cfg[k] for k in ("scale", "n_colors", "img_range", "embed_dim", "depths", "num_heads", "window_size",
                                   "mlp_ratio", "upsampler")}
@@ -279,11 +333,11 @@ def test_backward_against_reference_golden_gradients(name):
         got = p.grad.flatten()[::c["stride"]].cpu()
         # the bias-table gradient is a sum of dS entries with heavy cancellation: the reference's own bf16 autocast run is
         # off by the same 5-10 % there (see test_swinir_backward, which bounds it by 2x that error)
-        tol = 0.15 if k.endswith("relative_position_bias_table") else 6e-2
+        tol = 0.15 if k.endswith("relative_position_bias_table") else (0.12 if k.startswith(("csa.", "la.")) else 6e-2)
         assert _rel(got, ref) < tol, f"{k}: rel err {_rel(got, ref):.3e}"
         # (the channel-attention gate's parameters see gradients of 1e-4 that are sums over all pixels with cancellation:
         # test_rcan_backward bounds them by the reference's own bf16-autocast error)
-        ntol = 8e-2 if ".conv_du." in k else 3e-2
+        ntol = 8e-2 if (".conv_du." in k or k.startswith(("csa.", "la."))) else 3e-2
         assert abs(p.grad.norm().item() - float(gold[k + "::norm"][0])) < ntol * float(gold[k + "::norm"][0]) + 1e-9, k
 
 

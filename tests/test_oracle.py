@@ -181,10 +181,10 @@ def test_oracle_backward_matches_reference_gradients(name):
         P = synth.edsr_weights(cfg, c["wseed"])
         Q = {k: v.clone().requires_grad_(v.is_floating_point() and "mean" not in k) for k, v in P.items()}
         loss = F.l1_loss(O.edsr_forward(Q, x, cfg), tgt)
-    elif c["arch"] == "rcan":
-        P = synth.rcan_weights(cfg, c["wseed"])
+    elif c["arch"] in ("rcan", "han"):
+        P = (synth.rcan_weights if c["arch"] == "rcan" else synth.han_weights)(cfg, c["wseed"])
         Q = {k: v.clone().requires_grad_(v.is_floating_point() and "mean" not in k) for k, v in P.items()}
-        loss = F.l1_loss(O.rcan_forward(Q, x, cfg), tgt)
+        loss = F.l1_loss((O.rcan_forward if c["arch"] == "rcan" else O.han_forward)(Q, x, cfg), tgt)
     else:
         P = synth.swinir_weights(cfg, c["wseed"])
         Q = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
