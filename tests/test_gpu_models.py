@@ -279,6 +279,33 @@ def test_swinfir_reference_shape_test_and_bf16_refusal():
             model(torch.randn(1, 3, 8, 8).cuda())
 
 
+def test_f3_families_through_inference_and_tiler():
+    """HAN and SwinFIR behind the caller-facing entry points: Model.inference (uint8 in / out) and the tiler equal the oracle's
+    forward / tiler on the same weights (<= 1 LSB on a small share of pixels)."""
+    from studiosr_b200.models import HAN, SwinFIR
+
+    img = synth.smooth_image_u8(40, 52, seed=9)
+    x = torch.from_numpy(img.astype(np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)
+    cfg_h = dict(synth.HAN_TINY, scale=2)
+    Ph = synth.han_weights(cfg_h, 42)
+    han = HAN(**cfg_h)
+    han.load_state_dict(Ph, strict=True)
+    han = han.cuda().eval()
+    cfg_s = dict(synth.swinir_config(**synth.SWINIR_TINY), scale=2, sfb=True)
+    Ps = synth.swinfir_weights(cfg_s, 22)
+    fir = SwinFIR(drop_path_rate=0.0, **{k: cfg_s[k] for k in _SWIN_KW})
+    fir.load_state_dict(Ps, strict=True)
+    fir = fir.cuda().eval()
+    for name, m, fwd in (("han", han, lambda t: O.han_forward(Ph, t, cfg_h)), ("swinfir", fir, lambda t: O.swinir_forward(Ps, t, cfg_s))):
+        m.precision = "fp32"
+        ref = O.quantize_u8(fwd(x)[0], 1.0).numpy()
+        d = np.abs(m.inference(img).astype(np.int32) - ref.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 2e-3, (name, d.max(), (d > 0).mean())
+        ref_t = O.quantize_u8(O.tiled_upscale(fwd, x, 2, tile=32, overlap=8)[0], 1.0).numpy()
+        d = np.abs(m.inference_tiled(img, tile=32, overlap=8, precision="fp32").astype(np.int32) - ref_t.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 2e-3, (name, "tiled", d.max(), (d > 0).mean())
+
+
 def test_inference_u8_matches_reference(golden_meta):
     g = load_golden("swinir_tiny_x4_inference_u8")
     m = _swinir(golden_meta["swinir_ops"]["cfg"], 11)
