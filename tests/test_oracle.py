@@ -239,3 +239,111 @@ def test_oracle_psnr_and_augmentation_match_reference_goldens():
         xs, ys, flags = PairedAugment(size=12, scale=4, rng=rng, device="cpu").draw(lq.shape[0], lq.shape[1])
         x, y = O.augment_pair(lq, hr, 12, 4, xs, ys, flags)
         assert np.array_equal(x, g["aug_x"][i]) and np.array_equal(y, g["aug_y"][i]), seed
+
+
+def _dft_pair_as_k_fft(y: np.ndarray):
+    """numpy restatement of the four passes of studiosr_b200/csrc/k_fft.cu (direct DFTs with a twiddle table indexed by
+    k * x mod L, norm "ortho", c2r ignoring the imaginary parts of the DC / Nyquist bins): y [H, W] -> (spectrum, round trip)."""
+    H, W = y.shape
+    Wf = W // 2 + 1
+    sc = 1.0 / np.sqrt(H * W)
+    twW = np.exp(-2j * np.pi * np.arange(W) / W)
+    twH = np.exp(-2j * np.pi * np.arange(H) / H)
+    a = np.zeros((H, Wf), dtype=np.complex128)
+    for k in range(Wf):  # pass 1: real -> complex along W
+        a[:, k] = (y * twW[(k * np.arange(W)) % W][None, :]).sum(axis=1) * sc
+    spec = np.zeros_like(a)
+    for k in range(H):  # pass 2: complex along H
+        spec[k] = (a * twH[(k * np.arange(H)) % H][:, None]).sum(axis=0)
+    b = np.zeros_like(spec)
+    for h in range(H):  # pass 3: inverse along H
+        b[h] = (spec * np.conj(twH[(h * np.arange(H)) % H])[:, None]).sum(axis=0)
+    out = np.zeros((H, W))
+    for x in range(W):  # pass 4: complex -> real along W
+        acc = b[:, 0].real.copy()
+        for k in range(1, Wf):
+            t = np.conj(twW[(k * x) % W])
+            if 2 * k == W:
+                acc += b[:, k].real * t.real
+            else:
+                acc += 2.0 * (b[:, k].real * t.real - b[:, k].imag * t.imag)
+        out[:, x] = acc * sc
+    return spec, out
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (16, 24), (9, 12), (12, 7), (5, 5)])
+def test_fft_algorithm_of_k_fft_matches_torch_fft(H, W):
+    """The algorithm of the SwinFIR FFT kernels (even and odd lengths) against torch.fft.rfftn / irfftn with norm="ortho" -- the
+    calls swinfir.py:20,31 makes.  (The kernels themselves are checked on the GPU through the SwinFIR goldens, whose padded
+    sizes are always multiples of 8; this pins the odd-length and Nyquist handling of the formulae.)"""
+    rng = np.random.default_rng(H * 100 + W)
+    y = rng.standard_normal((H, W))
+    spec, back = _dft_pair_as_k_fft(y)
+    ref = torch.fft.rfftn(torch.from_numpy(y), dim=(-2, -1), norm="ortho").numpy()
+    assert np.abs(spec - ref).max() < 1e-12
+    assert np.abs(back - y).max() < 1e-12
+    # a spectrum that is NOT Hermitian-consistent (what the 1x1 conv + LeakyReLU of the FourierUnit produces): same answer as irfftn
+    z = rng.standard_normal((H, W // 2 + 1)) + 1j * rng.standard_normal((H, W // 2 + 1))
+    Hh, Wf = z.shape
+    sc = 1.0 / np.sqrt(H * W)
+    twW = np.exp(-2j * np.pi * np.arange(W) / W)
+    twH = np.exp(-2j * np.pi * np.arange(H) / H)
+    b = np.stack([(z * np.conj(twH[(h * np.arange(H)) % H])[:, None]).sum(axis=0) for h in range(H)])
+    out = np.zeros((H, W))
+    for x in range(W):
+        acc = b[:, 0].real.copy()
+        for k in range(1, Wf):
+            t = np.conj(twW[(k * x) % W])
+            acc += b[:, k].real * t.real if 2 * k == W else 2.0 * (b[:, k].real * t.real - b[:, k].imag * t.imag)
+        out[:, x] = acc * sc
+    ref2 = torch.fft.irfftn(torch.from_numpy(z), s=(H, W), dim=(-2, -1), norm="ortho").numpy()
+    assert np.abs(out - ref2).max() < 1e-11
+
+
+def test_han_lam_backward_formulae_match_autograd():
+    """The closed-form adjoint of HAN's layer attention used by k_simt.cu (han_gram2 / han_lam_bwd_small / han_lam_bwd_apply):
+    with D = <dOut_n, X_m>, A = softmax(max - E), E = X X^T:  dgamma = sum A.D;  dE = -A.(gamma D - rowsum(A.gamma D))  (the row-max
+    term cancels);  dX = dOut + gamma A^T dOut + (dE + dE^T) X  -- against torch autograd over oracle.han_lam."""
+    torch.manual_seed(3)
+    B, N, C, H, W = 2, 11, 4, 3, 5
+    x = (torch.randn(B, N, C, H, W, dtype=torch.float64) * 0.3).requires_grad_(True)
+    gamma = torch.tensor([0.7], dtype=torch.float64, requires_grad=True)
+    out = O.han_lam(x, gamma)
+    g = torch.randn_like(out)
+    out.backward(g)
+    X = x.detach().reshape(B, N, -1)
+    G = g.reshape(B, N, -1)
+    E = X @ X.transpose(1, 2)
+    A = torch.softmax(E.max(dim=-1, keepdim=True)[0] - E, dim=-1)
+    D = G @ X.transpose(1, 2)
+    dgamma = (A * D).sum()
+    dA = gamma.detach() * D
+    dE = -A * (dA - (A * dA).sum(dim=-1, keepdim=True))
+    dX = G + gamma.detach() * (A.transpose(1, 2) @ G) + (dE + dE.transpose(1, 2)) @ X
+    assert torch.allclose(dX.reshape(x.shape), x.grad, atol=1e-10)
+    assert abs(dgamma.item() - gamma.grad.item()) < 1e-10
+
+
+def test_han_csam_backward_formulae_match_autograd():
+    """The adjoint of HAN's channel-spatial attention used by k_simt.cu (han_csam_bwd1 / bwd2): dpre = g x gamma s (1 - s);
+    dx = g (1 + gamma s) + conv3d^T(dpre); dgamma = sum g x s; db = sum dpre; dW[tap] = sum dpre x[. + off(tap)]."""
+    torch.manual_seed(5)
+    B, C, H, W = 2, 6, 4, 5
+    x = torch.randn(B, C, H, W, dtype=torch.float64, requires_grad=True)
+    P = {"csa.conv.weight": (torch.randn(1, 1, 3, 3, 3, dtype=torch.float64) * 0.3).requires_grad_(True),
+         "csa.conv.bias": torch.tensor([0.1], dtype=torch.float64, requires_grad=True),
+         "csa.gamma": torch.tensor([0.7], dtype=torch.float64, requires_grad=True)}
+    out = O.han_csam(P, x)
+    g = torch.randn_like(out)
+    out.backward(g)
+    xd, Wt, gm = x.detach(), P["csa.conv.weight"].detach(), P["csa.gamma"].detach()
+    pre = torch.nn.functional.conv3d(xd.unsqueeze(1), Wt, P["csa.conv.bias"].detach(), padding=1).squeeze(1)
+    sg = torch.sigmoid(pre)
+    dpre = g * xd * gm * sg * (1 - sg)
+    dx = g * (1 + gm * sg) + torch.nn.functional.conv_transpose3d(dpre.unsqueeze(1), Wt, padding=1).squeeze(1)
+    assert torch.allclose(dx, x.grad, atol=1e-10)
+    assert abs((g * xd * sg).sum().item() - P["csa.gamma"].grad.item()) < 1e-9
+    assert abs(dpre.sum().item() - P["csa.conv.bias"].grad.item()) < 1e-9
+    xp = torch.nn.functional.pad(xd, (1, 1, 1, 1, 1, 1))
+    dW = torch.stack([(dpre * xp[:, dc:dc + C, dy:dy + H, dx_:dx_ + W]).sum() for dc in range(3) for dy in range(3) for dx_ in range(3)])
+    assert torch.allclose(dW, P["csa.conv.weight"].grad.flatten(), atol=1e-9)
