@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import sr_oracle as O
 from oracle import synth
@@ -347,3 +348,62 @@ def test_han_csam_backward_formulae_match_autograd():
     xp = torch.nn.functional.pad(xd, (1, 1, 1, 1, 1, 1))
     dW = torch.stack([(dpre * xp[:, dc:dc + C, dy:dy + H, dx_:dx_ + W]).sum() for dc in range(3) for dy in range(3) for dx_ in range(3)])
     assert torch.allclose(dW, P["csa.conv.weight"].grad.flatten(), atol=1e-9)
+
+
+def test_channel_attention_backward_formulae_match_autograd():
+    """The adjoint of out = res + t * sigmoid(W2 relu(W1 mean(t) + b1) + b2) used by k_simt.cu (ca_bwd_reduce / gate / apply):
+    dz2 = gate (1 - gate) sum_hw(G t);  dz1 = relu'(.) W2^T dz2;  dt = G gate + W1^T dz1 / HW;  dW2 = dz2 h^T, dW1 = dz1 p^T."""
+    torch.manual_seed(7)
+    B, C, R, H, W = 2, 8, 2, 3, 4
+    t = torch.randn(B, C, H, W, dtype=torch.float64, requires_grad=True)
+    P = {"ca.conv_du.0.weight": torch.randn(R, C, 1, 1, dtype=torch.float64, requires_grad=True),
+         "ca.conv_du.0.bias": torch.randn(R, dtype=torch.float64, requires_grad=True),
+         "ca.conv_du.2.weight": torch.randn(C, R, 1, 1, dtype=torch.float64, requires_grad=True),
+         "ca.conv_du.2.bias": torch.randn(C, dtype=torch.float64, requires_grad=True)}
+    out = O.channel_attention(P, "ca", t)
+    G = torch.randn_like(out)
+    out.backward(G)
+    W1, b1 = P["ca.conv_du.0.weight"].detach().reshape(R, C), P["ca.conv_du.0.bias"].detach()
+    W2, b2 = P["ca.conv_du.2.weight"].detach().reshape(C, R), P["ca.conv_du.2.bias"].detach()
+    td = t.detach()
+    p = td.mean(dim=(2, 3))
+    z1 = p @ W1.t() + b1
+    h = torch.relu(z1)
+    gate = torch.sigmoid(h @ W2.t() + b2)
+    ds = (G * td).sum(dim=(2, 3))
+    dz2 = ds * gate * (1 - gate)
+    dz1 = (dz2 @ W2) * (z1 > 0)
+    dt = G * gate[:, :, None, None] + (dz1 @ W1)[:, :, None, None] / (H * W)
+    assert torch.allclose(dt, t.grad, atol=1e-10)
+    assert torch.allclose(dz2.t() @ h, P["ca.conv_du.2.weight"].grad.reshape(C, R), atol=1e-10)
+    assert torch.allclose(dz1.t() @ p, P["ca.conv_du.0.weight"].grad.reshape(R, C), atol=1e-10)
+    assert torch.allclose(dz2.sum(0), P["ca.conv_du.2.bias"].grad, atol=1e-10) and torch.allclose(dz1.sum(0), P["ca.conv_du.0.bias"].grad, atol=1e-10)
+
+
+@pytest.mark.parametrize("h,w", [(16, 24), (20, 27), (9, 8)])
+def test_input_gradient_formula_with_reflect_pad_matches_autograd(h, w):
+    """dL/dx as conv_first_dgrad_kernel computes it (k_train.cu): the first conv's data gradient on the padded grid,
+    dxp[ci][y][x] = sum_{ky,kx,n} G[y - ky + 1][x - kx + 1][n] W[n][ci][ky][kx], folded back through the training-mode reflect pad
+    (padded (y, x) reads source (y < h ? y : 2 (h - 1) - y, same for x), common.py:277-282) and scaled by 1 / img_range."""
+    torch.manual_seed(h * 31 + w)
+    C, ws, img_range = 5, 8, 2.0
+    x = torch.rand(1, 3, h, w, dtype=torch.float64, requires_grad=True)
+    Wc = torch.randn(C, 3, 3, 3, dtype=torch.float64)
+    mean = torch.tensor(synth.RGB_MEAN, dtype=torch.float64).view(1, 3, 1, 1)
+    xp = O.pad_for_train(x, ws) / img_range - mean
+    y = F.conv2d(xp, Wc, padding=1)
+    G = torch.randn_like(y)
+    y.backward(G)
+    Hp, Wp = y.shape[2:]
+    dx = torch.zeros(3, h, w, dtype=torch.float64)
+    Gp = F.pad(G[0], (1, 1, 1, 1))
+    for yy in range(Hp):
+        sy = yy if yy < h else 2 * (h - 1) - yy
+        for xx in range(Wp):
+            sx = xx if xx < w else 2 * (w - 1) - xx
+            acc = torch.zeros(3, dtype=torch.float64)
+            for ky in range(3):
+                for kx in range(3):
+                    acc += Gp[:, yy - ky + 1 + 1, xx - kx + 1 + 1] @ Wc[:, :, ky, kx]
+            dx[:, sy, sx] += acc / img_range
+    assert torch.allclose(dx, x.grad[0], atol=1e-10)
