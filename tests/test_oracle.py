@@ -407,3 +407,38 @@ def test_input_gradient_formula_with_reflect_pad_matches_autograd(h, w):
                     acc += Gp[:, yy - ky + 1 + 1, xx - kx + 1 + 1] @ Wc[:, :, ky, kx]
             dx[:, sy, sx] += acc / img_range
     assert torch.allclose(dx, x.grad[0], atol=1e-10)
+
+
+def test_compact_relative_position_bias_addressing():
+    """The addressing the fused attention kernel uses for the relative-position bias (k_swin_attn.cu + pack_attn_fused_host):
+    window tokens in the order r = (tx / 4) * 32 + ty * 4 + tx % 4; B[i][j] = R[7 - yi + yj][7 - xi + xj] with R the 15 x 15 table
+    reversed in both axes, stored in two copies shifted by (7 - xi) % 2 elements at a row pitch of 16, read as 4-element runs
+    (one per key quad) -- against the reference gather table[relative_position_index] (swinir.py:57-67, 92-95)."""
+    ws, heads = 8, 6
+    g = torch.Generator().manual_seed(1)
+    table = torch.randn((2 * ws - 1) ** 2, heads, generator=g)
+    ref = O.rel_pos_bias(table, ws)  # [heads, 64, 64] in row-major window-token order t = ty * 8 + tx
+    copies = np.zeros((heads, 2, 15, 16), dtype=np.float32)
+    for hd in range(heads):
+        for sft in range(2):
+            for a in range(15):
+                for b in range(15):
+                    copies[hd, sft, a, b + sft] = table[(14 - a) * 15 + (14 - b), hd]
+
+    def tok(r):  # kernel token index -> (y, x) inside the window
+        return (r & 31) >> 2, (r >> 5) * 4 + (r & 3)
+
+    for hd in range(heads):
+        for ri in range(64):
+            yi, xi = tok(ri)
+            s_ = (7 - xi) & 1
+            row0, col0 = 7 - yi, 7 - xi + s_
+            assert col0 % 2 == 0  # every run starts 4-byte aligned (bf16)
+            got = np.zeros(64, dtype=np.float32)
+            for c in range(8):  # keys 8c .. 8c+7: key rows (2c) % 8 and + 1, key columns 4 (c / 4) .. + 3
+                for u in range(2):
+                    run = copies[hd, s_, row0 + ((2 * c) & 7) + u, col0 + 4 * (c >> 2): col0 + 4 * (c >> 2) + 4]
+                    got[8 * c + 4 * u: 8 * c + 4 * u + 4] = run
+            for rj in range(64):
+                yj, xj = tok(rj)
+                assert got[rj] == ref[hd, yi * 8 + xi, yj * 8 + xj].item(), (hd, ri, rj)
